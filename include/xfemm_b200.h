@@ -1,0 +1,223 @@
+/* xfemm_b200 — C ABI of the B200-native fsolver hot path.
+ *
+ * Plain C types only (pointers, sizes, int status: 0 = ok, non-zero = error; text via
+ * xfemm_last_error()).  No exceptions cross this boundary, no torch types appear in it.
+ * One handle per problem, so batches (rotor-angle / frequency sweeps) and multi-GPU runs are
+ * simply several handles; a handle is bound to the CUDA device that was current at creation.
+ * All array arguments are HOST buffers unless the name ends in _dev.
+ *
+ * What each group replaces in the reference (paths relative to the xfemm tree):
+ *   xfemm_linprob_*   cfemm/libfemm/spars.h:38-83    class CBigLinProb  (Create/Put/Get/Wipe/
+ *                     SetValue/Periodicity/AntiPeriodicity/MultA/MultPC/Dot/PCGSolve,
+ *                     spars.cpp:80-474)
+ *   xfemm_clinprob_*  cfemm/libfemm/cspars.h:37-95   class CBigComplexLinProb (cspars.cpp:119-1081)
+ *   xfemm_mag_*       cfemm/fsolver/static2d.cpp:53-1033  FSolver::Static2D
+ *                     cfemm/fsolver/staticaxi.cpp:45-794  FSolver::StaticAxisymmetric
+ *                     cfemm/fsolver/harmonic2d.cpp:38-890 FSolver::Harmonic2D
+ *                     cfemm/fsolver/harmonicaxi.cpp:34-821 FSolver::HarmonicAxisymmetric
+ *   xfemm_pattern_*   the sparsity structure the reference grows implicitly through
+ *                     CBigLinProb::Put (spars.cpp:105-142) during assembly + Periodicity
+ *   xfemm_renumber_*  cfemm/libfemm/cuthill.cpp:40-391 (Cuthill–McKee + element comb sort)
+ *   xfemm_fsolver_*   cfemm/fsolver/main.cpp:39-84 and mfemm/mexfsolver.cpp:34-135 (file-level
+ *                     entry: LoadProblemFile + runSolver, exit codes 0/1/2)
+ */
+#ifndef XFEMM_B200_H
+#define XFEMM_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XFEMM_OK 0
+#define XFEMM_ERR_CUDA 1      /* CUDA runtime error or no usable device            */
+#define XFEMM_ERR_ARG 2       /* invalid argument                                  */
+#define XFEMM_ERR_SINGULAR 3  /* zero diagonal (reference: PCGSolve returns false) */
+#define XFEMM_ERR_DIVERGED 4  /* NaN / breakdown / iteration cap                   */
+#define XFEMM_ERR_IO 5
+
+/* preconditioners for the Krylov solvers */
+#define XFEMM_PRECOND_JACOBI 0
+#define XFEMM_PRECOND_MCSSOR 1 /* multicolour SSOR (GPU-parallel stand-in for the serial SSOR) */
+
+typedef struct xfemm_linprob xfemm_linprob;   /* real symmetric system on the device    */
+typedef struct xfemm_clinprob xfemm_clinprob; /* complex symmetric system on the device */
+typedef struct xfemm_mag xfemm_mag;           /* magnetics mesh + materials on the device */
+typedef struct xfemm_fsolver xfemm_fsolver;   /* host-side FSolver object (file level)   */
+
+/* ------------------------------------------------------------------ runtime */
+int xfemm_cuda_init(int device);        /* cudaSetDevice + context warm-up; XFEMM_ERR_CUDA if no GPU */
+int xfemm_device_count(void);
+const char *xfemm_last_error(void);     /* thread-local message of the last failing call */
+const char *xfemm_version(void);
+
+/* ------------------------------------------------------------------ solve statistics */
+typedef struct xfemm_solve_info
+{
+    int iterations;        /* Krylov iterations performed                                  */
+    int precond;           /* preconditioner actually used                                 */
+    int colors;            /* colours of the multicolour ordering (0 for Jacobi)           */
+    int status;            /* XFEMM_OK / XFEMM_ERR_SINGULAR / XFEMM_ERR_DIVERGED            */
+    double er;             /* reference stopping measure sqrt((z.r)/(z0.b)) at exit         */
+    double relres;         /* true ||b-Ax||2 / ||b||2 at exit                               */
+    double solve_ms;       /* CUDA-event time of the Krylov loop (excl. format conversion) */
+    double setup_ms;       /* CUDA-event time of per-solve setup (SELL fill, diag, …)      */
+    double bytes_per_iter; /* algorithmic bytes one iteration moves (SURVEY §8d formula)   */
+} xfemm_solve_info;
+
+/* ------------------------------------------------------------------ real linear problem
+ * Pattern: full (both triangles) CSR with sorted int32 columns, every row holds its diagonal.
+ * Row/column numbering is the caller's (the Cuthill–McKee order of the reference). */
+int xfemm_linprob_create(int n, const int *rowptr, const int *colidx, xfemm_linprob **out);
+int xfemm_linprob_destroy(xfemm_linprob *p);
+int xfemm_linprob_n(const xfemm_linprob *p);
+long long xfemm_linprob_nnz(const xfemm_linprob *p);
+int xfemm_linprob_wipe(xfemm_linprob *p);                               /* spars.cpp:348 Wipe  */
+int xfemm_linprob_set_values(xfemm_linprob *p, const double *vals_csr); /* H2D, CSR order      */
+int xfemm_linprob_get_values(xfemm_linprob *p, double *vals_csr);       /* D2H                 */
+int xfemm_linprob_set_rhs(xfemm_linprob *p, const double *b);
+int xfemm_linprob_get_rhs(xfemm_linprob *p, double *b);
+int xfemm_linprob_set_solution(xfemm_linprob *p, const double *V);
+int xfemm_linprob_get_solution(xfemm_linprob *p, double *V);
+/* spars.cpp:318 SetValue, applied for `count` nodes at once; x_first = value of the first
+ * SetValue call on that node (used for the neighbours' RHS), x_last = value of the last call
+ * (used for the node's own RHS); bdw = CBigLinProb::bdw (0 = whole matrix). */
+int xfemm_linprob_dirichlet(xfemm_linprob *p, int count, const int *nodes, const double *x_first,
+                            const double *x_last, int bdw);
+/* spars.cpp:421/366 Periodicity (type 0) / AntiPeriodicity (type 1), applied in list order. */
+int xfemm_linprob_periodic(xfemm_linprob *p, int npairs, const int *ni, const int *nj, const int *type);
+/* spars.cpp:238 PCGSolve.  warm != 0 keeps the current solution as initial guess.
+ * max_iter <= 0 → default cap (the reference has none). */
+int xfemm_linprob_pcg(xfemm_linprob *p, double precision, int warm, int precond, int max_iter,
+                      xfemm_solve_info *info);
+int xfemm_linprob_multa(xfemm_linprob *p, const double *x, double *y);  /* spars.cpp:167 MultA */
+int xfemm_linprob_multpc(xfemm_linprob *p, int precond, const double *x, double *y); /* :197   */
+/* timing hooks for bench.py: run `reps` SpMVs / PCG iterations on resident data, device-timed */
+int xfemm_linprob_bench_spmv(xfemm_linprob *p, int reps, double *ms_per_rep);
+
+/* ------------------------------------------------------------------ sparsity pattern
+ * Builds the structure CBigLinProb ends up with after assembly + boundary conditions:
+ * mesh graph ∪ air-gap-element 10x10 blocks ∪ periodic fill (symbolic replay of
+ * spars.cpp:421-474 in list order).  Output arrays are malloc'ed; free with xfemm_free. */
+int xfemm_pattern_build(int n_rows /* nodes + appended circuit unknowns */,
+                        int n_elems, const int *tri, int tri_stride /* ints per element: 3 or 4 */,
+                        int n_age_cells, const int *age_nodes /* n_age_cells*10 */,
+                        int n_extra, const int *extra_i, const int *extra_j /* extra symmetric couplings */,
+                        int n_pbc, const int *pbc_i, const int *pbc_j,
+                        int **rowptr_out, int **colidx_out);
+void xfemm_free(void *ptr);
+
+/* ------------------------------------------------------------------ renumbering (host, integer, bit-exact)
+ * edges: n_edges*2 node pairs in .edge file order.  newnum_out[i] = new index of node i.
+ * cuthill.cpp:94-391 */
+int xfemm_renumber_cuthill(int n_nodes, int n_edges, const int *edges, int *newnum_out, int *bandwidth_out);
+/* cuthill.cpp:40-85: the reference's (incomplete) comb sort on p0+p1+p2; order_out[k] = index of
+ * the input element that ends up at position k. */
+int xfemm_renumber_sort_elements(int n_elems, const int *tri, int *order_out);
+
+/* ------------------------------------------------------------------ magnetics assembly
+ * Per-label record: everything an element needs besides its geometry is a function of its
+ * block label (reference: labellist[lbl] → blockproplist[BlockType], circproplist[InCircuit]). */
+typedef struct xfemm_mag_label
+{
+    double mu1, mu2;      /* linear (Iter==0) relative permeabilities after lamination rules   */
+    double Jsrc;          /* J_block + circuit term  [MA/m^2]   (static2d.cpp:483-504)          */
+    double H_c;           /* coercivity [A/m]                                                 */
+    double magdir;        /* magnetisation direction [deg] (per-element override: magdir_elem) */
+    double lamfill;       /* lamination fill factor                                           */
+    int lamtype;          /* lamination type                                                  */
+    int bh_offset;        /* first point of this label's B-H table in the flat arrays, or -1  */
+    int bh_points;        /* number of B-H points (0 = linear)                                */
+    int is_external;      /* axisymmetric external region flag                                */
+    /* harmonic-only fields */
+    double mu1_im, mu2_im;  /* imaginary parts of the complex permeabilities                  */
+    double sigma;           /* conductivity seen by the eddy term [MS/m]                      */
+    double Jsrc_im;
+    int circuit;            /* index of the circuit unknown row (harmonic Case 0), or -1       */
+    int pad_;
+} xfemm_mag_label;
+
+typedef struct xfemm_mag_desc
+{
+    int axisymmetric;            /* 0 planar (static2d.cpp), 1 axisymmetric (staticaxi.cpp)   */
+    int n_nodes, n_elems;
+    const double *xy;            /* n_nodes*2, centimetres, solver (Cuthill–McKee) order        */
+    const int *tri;              /* n_elems*4: p0,p1,p2,label                                  */
+    const double *magdir_elem;   /* optional n_elems (NULL = use the label's)                  */
+    int n_labels;
+    const xfemm_mag_label *labels;
+    int n_bh;                    /* flat B-H tables: B, H, slope (real parts for statics)       */
+    const double *bh_B, *bh_H, *bh_slope;
+    const double *bh_H_im, *bh_slope_im; /* optional (harmonic)                                */
+    /* mixed (BdryFormat 2) edges: element index, local side, c0, c1   (static2d.cpp:460-480)  */
+    int n_mixed;
+    const int *mixed_elem_side;  /* n_mixed*2 */
+    const double *mixed_c0c1;    /* n_mixed*2 */
+    /* air-gap elements, flattened to ring cells (static2d.cpp:277-348)                          */
+    int n_age_cells;
+    const int *age_nodes;        /* n_age_cells*10                                             */
+    const double *age_weights;   /* n_age_cells*10                                             */
+    const int *age_matrix_id;    /* n_age_cells: which 10x10 matrix                            */
+    int n_age_matrices;
+    const double *age_matrices;  /* n_age_matrices*100, row-major, upper triangle used          */
+    /* point currents  (static2d.cpp:819-825)                                                   */
+    int n_point_src;
+    const int *point_src_node;
+    const double *point_src_val; /* 0.01*J                                                     */
+    /* axisymmetric extras */
+    double ext_zo, ext_ro, ext_ri; /* external region (staticaxi.cpp:611-617), in cm           */
+    double r_eps;                  /* 1e-6*units: nodes with |r| below are on the axis          */
+} xfemm_mag_desc;
+
+/* creates the device mesh and binds it to a linear problem whose pattern contains the mesh graph */
+int xfemm_mag_create(const xfemm_mag_desc *desc, xfemm_linprob *lin, xfemm_mag **out);
+int xfemm_mag_destroy(xfemm_mag *m);
+/* replaces the per-label table (Newton-independent inputs such as circuit currents) */
+int xfemm_mag_set_labels(xfemm_mag *m, int n_labels, const xfemm_mag_label *labels);
+/* replaces the air-gap-element tables (rotor-angle sweeps reuse mesh + pattern) */
+int xfemm_mag_set_age(xfemm_mag *m, int n_age_cells, const int *age_nodes, const double *age_weights,
+                      const int *age_matrix_id, int n_age_matrices, const double *age_matrices);
+/* One assembly pass into the bound linear problem: Wipe (iter>0), AGE blocks, element loop,
+ * point currents.  iter==0 uses the linear permeabilities; iter>0 evaluates B from the current
+ * solution, looks up nu(B), dnu/dB^2 and adds the Newton term (static2d.cpp:683-805).
+ * elapsed_ms (optional) receives the CUDA-event time. */
+int xfemm_mag_assemble_static(xfemm_mag *m, int iter, double *elapsed_ms);
+/* element permeabilities of the last assembly pass (n_elems*2: mu1, mu2) */
+int xfemm_mag_get_mu(xfemm_mag *m, double *mu12);
+/* Newton bookkeeping on the device (static2d.cpp:953-989): saves V_old, returns
+ * ||V-V_old||^2 and ||V||^2, blends V = relax*V + (1-relax)*V_old. */
+int xfemm_linprob_save_solution(xfemm_linprob *p);
+int xfemm_linprob_newton_norms(xfemm_linprob *p, double *dv2, double *v2);
+int xfemm_linprob_relax(xfemm_linprob *p, double relax);
+/* planar: b = V*c ; axisymmetric: b = V*c*2*pi*r*0.01 (static2d.cpp:1018-1021, staticaxi.cpp:779-783) */
+int xfemm_mag_solution_to_A(xfemm_mag *m, double *A_host);
+
+/* ------------------------------------------------------------------ file-level entry
+ * The call a user of fsolver / mexfsolver makes: basename without ".fem";
+ * returns 0 ok, 1 problem loading .fem, 2 solve failed (main.cpp:72-83, mexfsolver.cpp:122-134). */
+int xfemm_fsolver_run(const char *basename, int verbose);
+/* finer-grained variant used by the tests and the benchmark */
+int xfemm_fsolver_open(const char *basename, int verbose, xfemm_fsolver **out); /* LoadProblemFile */
+int xfemm_fsolver_load_mesh(xfemm_fsolver *s, int delete_files);                /* LoadMesh        */
+int xfemm_fsolver_renumber(xfemm_fsolver *s, int delete_files);                 /* Cuthill         */
+int xfemm_fsolver_solve(xfemm_fsolver *s);     /* Static2D / StaticAxisymmetric / Harmonic*       */
+int xfemm_fsolver_write(xfemm_fsolver *s);     /* WriteStatic2D / WriteHarmonic2D                  */
+int xfemm_fsolver_close(xfemm_fsolver *s);
+int xfemm_fsolver_counts(xfemm_fsolver *s, int *n_nodes, int *n_elems, int *n_pbc, int *n_age,
+                         int *bandwidth, int *n_unknowns, int *is_complex);
+int xfemm_fsolver_get_nodes(xfemm_fsolver *s, double *xy, int *bc);      /* solver order, cm      */
+int xfemm_fsolver_get_elems(xfemm_fsolver *s, int *elems8);              /* p0 p1 p2 lbl blk e0-2 */
+int xfemm_fsolver_get_pbc(xfemm_fsolver *s, int *pbc3);
+int xfemm_fsolver_get_permutation(xfemm_fsolver *s, int *newnum);
+int xfemm_fsolver_get_pattern(xfemm_fsolver *s, long long *nnz, int *rowptr, int *colidx); /* colidx NULL → only nnz */
+int xfemm_fsolver_get_system(xfemm_fsolver *s, double *vals_csr, double *rhs); /* last assembled+BC'd system */
+int xfemm_fsolver_get_solution(xfemm_fsolver *s, double *V, double *A);  /* complex: 2 doubles/entry */
+int xfemm_fsolver_get_mu(xfemm_fsolver *s, double *mu12);
+/* stats: newton steps, per-step Krylov iterations and device ms (arrays sized >= 64) */
+int xfemm_fsolver_get_stats(xfemm_fsolver *s, int *newton_steps, int *iters, double *solve_ms,
+                            double *assemble_ms, double *relres);
+int xfemm_fsolver_set_option(xfemm_fsolver *s, const char *key, double value); /* "precond", "max_iter", "keep_system" */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

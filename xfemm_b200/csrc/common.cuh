@@ -1,0 +1,90 @@
+// Shared helpers for the xfemm_b200 CUDA sources (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include <string>
+#include "../../include/xfemm_b200.h"
+
+namespace xb {
+
+void set_error(const char *fmt, ...);
+
+#define XB_CUDA(call)                                                                      \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess) {                                                           \
+            xb::set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,             \
+                          cudaGetErrorString(e_));                                         \
+            return XFEMM_ERR_CUDA;                                                         \
+        }                                                                                  \
+    } while (0)
+
+#define XB_ARG(cond, msg)                                                                  \
+    do {                                                                                   \
+        if (!(cond)) { xb::set_error("invalid argument: %s", msg); return XFEMM_ERR_ARG; } \
+    } while (0)
+
+template <typename T>
+struct DevBuf
+{
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    cudaError_t alloc(size_t count)
+    {
+        release();
+        n = count;
+        if (count == 0) return cudaSuccess;
+        return cudaMalloc((void **)&p, count * sizeof(T));
+    }
+    cudaError_t upload(const T *h, size_t count, cudaStream_t s = 0)
+    {
+        if (count != n) { cudaError_t e = alloc(count); if (e != cudaSuccess) return e; }
+        if (count == 0) return cudaSuccess;
+        return cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s);
+    }
+    cudaError_t zero(cudaStream_t s = 0) { return n ? cudaMemsetAsync(p, 0, n * sizeof(T), s) : cudaSuccess; }
+};
+
+// ---- device-side reductions -------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Sum over a thread block; result valid in every thread.  `smem` needs 33 doubles.
+__device__ __forceinline__ double block_sum(double v, double *smem)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads(); // protect smem reuse between consecutive calls
+    if (lane == 0) smem[wid] = v;
+    __syncthreads();
+    if (wid == 0)
+    {
+        double t = (lane < nw) ? smem[lane] : 0.0;
+        t = warp_sum(t);
+        if (lane == 0) smem[32] = t;
+    }
+    __syncthreads();
+    return smem[32];
+}
+
+// Deterministic re-reduction of per-block partials by every block (fixed order → every block
+// gets the bit-identical value, so data-dependent control flow stays uniform across the grid).
+__device__ __forceinline__ double reduce_partials(const double *__restrict__ part, int count, double *smem)
+{
+    double v = 0.0;
+    for (int i = threadIdx.x; i < count; i += blockDim.x) v += __ldcg(part + i);
+    return block_sum(v, smem);
+}
+
+} // namespace xb

@@ -1,0 +1,25 @@
+// Solver layout (internal row order + split SELL-32) built on the host once per pattern.
+#pragma once
+#include <vector>
+
+namespace xb {
+
+struct SellLayout
+{
+    int n_pad = 0, nslices = 0, ncolors = 0;
+    long long sell_len = 0;
+    std::vector<int> i2c;         // internal row -> caller row (-1 = padding row)
+    std::vector<int> c2i;         // caller row -> internal row
+    std::vector<int> color_slice; // first slice of each colour (ncolors+1), or {0,nslices}
+    std::vector<int> slice_ptr;   // nslices+1, offsets into sell_* (multiples of 32)
+    std::vector<int> slice_wl;    // width of the "lower" block of each slice
+    std::vector<int> sell_col;    // internal column per slot (padding: own row)
+    std::vector<int> sell_src;    // CSR index per slot (-1 padding)
+    std::vector<int> diag_src;    // CSR index of the diagonal per internal row (-1 padding row)
+};
+
+int greedy_coloring(int n, const int *rowptr, const int *col, std::vector<int> &color);
+void build_sell_layout(int n, const int *rowptr, const int *col, const std::vector<int> *color,
+                       int ncolors, int sigma, SellLayout &L);
+
+} // namespace xb

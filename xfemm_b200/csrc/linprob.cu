@@ -1,0 +1,992 @@
+// xfemm_linprob_* — GPU backend of CBigLinProb (reference: cfemm/libfemm/spars.cpp:80-474).
+// Hand-written sm_100a kernels: SELL-32 SpMV, fused vector updates with warp-shuffle + block
+// reductions, Jacobi and multicolour-SSOR preconditioned CG as ONE persistent cooperative
+// kernel (no host round trips inside the Krylov loop), Dirichlet / periodic boundary kernels.
+#include "linprob.cuh"
+#include <cooperative_groups.h>
+#include <algorithm>
+#include <unordered_map>
+#include <cmath>
+#include <cstdlib>
+
+namespace cg = cooperative_groups;
+
+namespace xb {
+
+static thread_local std::string g_err;
+void set_error(const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+}
+const char *last_error() { return g_err.c_str(); }
+
+static inline int env_int(const char *name, int dflt)
+{
+    const char *v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+// =====================================================================================
+// small utility kernels
+// =====================================================================================
+__global__ void k_sell_fill(long long len, const int *__restrict__ src, const double *__restrict__ vals,
+                            double *__restrict__ out)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < len; i += (long long)gridDim.x * blockDim.x)
+    {
+        int s = src[i];
+        out[i] = s >= 0 ? vals[s] : 0.0;
+    }
+}
+
+__global__ void k_diag_fill(int n_pad, const int *__restrict__ diag_src, const double *__restrict__ vals,
+                            double *__restrict__ diag, double *__restrict__ dinv, int *singular_row)
+{
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_pad) return;
+    int s = diag_src[r];
+    double d = s >= 0 ? vals[s] : 0.0;
+    diag[r] = d;
+    dinv[r] = (d != 0.0) ? 1.0 / d : 0.0;
+    if (s >= 0 && d == 0.0) atomicMin(singular_row, r);
+}
+
+// caller order -> internal order (padding rows get 0)
+__global__ void k_to_internal(int n_pad, const int *__restrict__ i2c, const double *__restrict__ in, double *__restrict__ out)
+{
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_pad) return;
+    int i = i2c[r];
+    out[r] = i >= 0 ? in[i] : 0.0;
+}
+__global__ void k_from_internal(int n_pad, const int *__restrict__ i2c, const double *__restrict__ in, double *__restrict__ out)
+{
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_pad) return;
+    int i = i2c[r];
+    if (i >= 0) out[i] = in[r];
+}
+
+// =====================================================================================
+// SELL-32 SpMV building block: one warp computes 32 rows of y = A x (lower + upper + diagonal)
+// =====================================================================================
+__device__ __forceinline__ double sell_row_offdiag(const double *__restrict__ val, const int *__restrict__ col,
+                                                    int base, int k0, int k1, int lane, const double *x)
+{
+    double acc = 0.0;
+    const double *v = val + base + lane;
+    const int *c = col + base + lane;
+#pragma unroll 4
+    for (int k = k0; k < k1; k++)
+    {
+        // matrix stream: read once per pass → evict-first so the vectors stay resident in L2
+        double a = __ldcs(v + k * 32);
+        int j = __ldcs(c + k * 32);
+        acc = fma(a, x[j], acc);
+    }
+    return acc;
+}
+
+__global__ void __launch_bounds__(256)
+k_spmv(int nslices, const int *__restrict__ slice_ptr, const int *__restrict__ sell_col,
+       const double *__restrict__ sell_val, const double *__restrict__ diag, const double *x, double *y)
+{
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int s = warp; s < nslices; s += nwarps)
+    {
+        const int base = slice_ptr[s];
+        const int w = (slice_ptr[s + 1] - base) >> 5;
+        const int row = s * 32 + lane;
+        double acc = sell_row_offdiag(sell_val, sell_col, base, 0, w, lane, x);
+        y[row] = fma(diag[row], x[row], acc);
+    }
+}
+
+// res2 = sum (b-u)^2, b2 = sum b^2 → two scalars (deterministic two-stage)
+__global__ void k_resnorm_partial(int n, const double *__restrict__ b, const double *__restrict__ u, double *part)
+{
+    __shared__ double sm[33];
+    double a = 0, c = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        double bb = b[i], d = bb - u[i];
+        a = fma(d, d, a);
+        c = fma(bb, bb, c);
+    }
+    a = block_sum(a, sm);
+    c = block_sum(c, sm);
+    if (threadIdx.x == 0) { part[blockIdx.x] = a; part[gridDim.x + blockIdx.x] = c; }
+}
+__global__ void k_reduce2_final(int nblk, const double *part, double *out2)
+{
+    __shared__ double sm[33];
+    double a = 0, c = 0;
+    for (int i = threadIdx.x; i < nblk; i += blockDim.x) { a += part[i]; c += part[nblk + i]; }
+    a = block_sum(a, sm);
+    c = block_sum(c, sm);
+    if (threadIdx.x == 0) { out2[0] = a; out2[1] = c; }
+}
+
+// =====================================================================================
+// Persistent preconditioned CG (reference recurrence: spars.cpp:238-316)
+// =====================================================================================
+struct PcgArgs
+{
+    int n_pad, nslices, ncolors;
+    const int *slice_ptr, *slice_wl, *sell_col, *color_slice;
+    const double *sell_val, *diag, *dinv, *b;
+    double *x, *r, *p, *u, *z;
+    double *part; // 2*gridDim
+    double precision, omega;
+    int max_iter, warm;
+    double *mail; // [0]=iters [1]=er [2]=status [3]=res_o [4]=res
+};
+
+template <int PRECOND>
+__device__ __forceinline__ double precond_apply(const PcgArgs &a, cg::grid_group &grid, int r0, int r1,
+                                                int warp_g, int nwarps_g, int lane)
+{
+    // returns this thread's partial of r.z ; z is left in a.z (MC-SSOR) or implied (Jacobi)
+    double dot = 0.0;
+    if (PRECOND == XFEMM_PRECOND_JACOBI)
+    {
+        for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x)
+        {
+            double ri = a.r[i];
+            dot = fma(ri * a.dinv[i], ri, dot);
+        }
+        return dot;
+    }
+    // ---- multicolour SSOR:  z = w(2-w) (D+wU)^-1 D (D+wL)^-1 r   (spars.cpp:197-236, colour order)
+    const double w = a.omega, c0 = w * (2.0 - w);
+    const int m = a.ncolors;
+    // start: z = c0*r ; colour 0 has no lower part → finish its forward step here
+    {
+        const int rc0 = a.color_slice[1] * 32;
+        for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x)
+        {
+            double v = c0 * a.r[i];
+            if (i < rc0) v *= a.dinv[i];
+            a.z[i] = v;
+        }
+    }
+    grid.sync();
+    // forward sweep, colours 1..m-1
+    for (int c = 1; c < m; c++)
+    {
+        const int sa = a.color_slice[c], sb = a.color_slice[c + 1];
+        for (int s = sa + warp_g; s < sb; s += nwarps_g)
+        {
+            const int base = a.slice_ptr[s], wl = a.slice_wl[s], row = s * 32 + lane;
+            double acc = sell_row_offdiag(a.sell_val, a.sell_col, base, 0, wl, lane, a.z);
+            double v = (a.z[row] - w * acc) * a.dinv[row];
+            a.z[row] = v;
+            if (c == m - 1) dot = fma(a.r[row], v, dot); // last colour is final after the forward sweep
+        }
+        grid.sync();
+    }
+    // backward sweep, colours m-2..0:  z_i -= w/d_i * sum_upper a_ij z_j
+    for (int c = m - 2; c >= 0; c--)
+    {
+        const int sa = a.color_slice[c], sb = a.color_slice[c + 1];
+        for (int s = sa + warp_g; s < sb; s += nwarps_g)
+        {
+            const int base = a.slice_ptr[s], wl = a.slice_wl[s], row = s * 32 + lane;
+            const int wtot = (a.slice_ptr[s + 1] - base) >> 5;
+            double acc = sell_row_offdiag(a.sell_val, a.sell_col, base, wl, wtot, lane, a.z);
+            double v = a.z[row] - w * acc * a.dinv[row];
+            a.z[row] = v;
+            dot = fma(a.r[row], v, dot);
+        }
+        if (c > 0) grid.sync();
+    }
+    if (m == 1) // degenerate: diagonal matrix
+        for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x) dot = fma(a.r[i], a.z[i], dot);
+    return dot;
+}
+
+template <int PRECOND>
+__global__ void __launch_bounds__(512, 2) k_pcg(PcgArgs a)
+{
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sm[33];
+    const int lane = threadIdx.x & 31;
+    const int nwarps_b = blockDim.x >> 5, warp_b = threadIdx.x >> 5;
+    const int warp_g = blockIdx.x * nwarps_b + warp_b, nwarps_g = gridDim.x * nwarps_b;
+    const int G = gridDim.x;
+    // contiguous chunk of slices / rows owned by this block in the vector phases
+    const int s0 = (int)((long long)a.nslices * blockIdx.x / G);
+    const int s1 = (int)((long long)a.nslices * (blockIdx.x + 1) / G);
+    const int r0 = s0 * 32, r1 = s1 * 32;
+    double *partA = a.part, *partB = a.part + G;
+
+    // ---- res_o = b . M^-1 b   (spars.cpp:257-259) ; z0 is computed with r := b
+    for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x)
+    {
+        a.r[i] = a.b[i];
+        if (!a.warm) a.x[i] = 0.0;
+    }
+    grid.sync();
+    double part = precond_apply<PRECOND>(a, grid, r0, r1, warp_g, nwarps_g, lane);
+    part = block_sum(part, sm);
+    if (threadIdx.x == 0) partA[blockIdx.x] = part;
+    grid.sync();
+    const double res_o = reduce_partials(partA, G, sm);
+    if (res_o == 0.0)
+    {
+        if (blockIdx.x == 0 && threadIdx.x == 0) { a.mail[0] = 0; a.mail[1] = 0; a.mail[2] = XFEMM_OK; a.mail[3] = 0; a.mail[4] = 0; }
+        return;
+    }
+    // ---- r = b - A x
+    if (a.warm)
+    {
+        for (int s = s0 + warp_b; s < s1; s += nwarps_b)
+        {
+            const int base = a.slice_ptr[s], w = (a.slice_ptr[s + 1] - base) >> 5, row = s * 32 + lane;
+            double acc = sell_row_offdiag(a.sell_val, a.sell_col, base, 0, w, lane, a.x);
+            a.r[row] = a.b[row] - fma(a.diag[row], a.x[row], acc);
+        }
+        grid.sync();
+    }
+    // ---- z = M^-1 r ; p = z ; res = z.r
+    part = precond_apply<PRECOND>(a, grid, r0, r1, warp_g, nwarps_g, lane);
+    part = block_sum(part, sm);
+    if (threadIdx.x == 0) partB[blockIdx.x] = part;
+    grid.sync();
+    double res = reduce_partials(partB, G, sm);
+    for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x)
+        a.p[i] = (PRECOND == XFEMM_PRECOND_JACOBI) ? a.r[i] * a.dinv[i] : a.z[i];
+    grid.sync();
+
+    int it = 0;
+    int status = XFEMM_OK;
+    double er = 0.0;
+    while (true)
+    {
+        // step i: u = A p ; pAp
+        part = 0.0;
+        for (int s = s0 + warp_b; s < s1; s += nwarps_b)
+        {
+            const int base = a.slice_ptr[s], w = (a.slice_ptr[s + 1] - base) >> 5, row = s * 32 + lane;
+            double acc = sell_row_offdiag(a.sell_val, a.sell_col, base, 0, w, lane, a.p);
+            const double pr = a.p[row];
+            acc = fma(a.diag[row], pr, acc);
+            a.u[row] = acc;
+            part = fma(pr, acc, part);
+        }
+        part = block_sum(part, sm);
+        if (threadIdx.x == 0) partA[blockIdx.x] = part;
+        grid.sync();
+        const double pAp = reduce_partials(partA, G, sm);
+        if (!(pAp > 0.0)) { status = XFEMM_ERR_DIVERGED; break; }
+        const double del = res / pAp;
+        // steps ii, iii: V += del P ; R -= del U   (fused; Jacobi also fuses z.r)
+        if (PRECOND == XFEMM_PRECOND_JACOBI)
+        {
+            part = 0.0;
+            for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x)
+            {
+                a.x[i] = fma(del, a.p[i], a.x[i]);
+                double ri = fma(-del, a.u[i], a.r[i]);
+                a.r[i] = ri;
+                part = fma(ri * a.dinv[i], ri, part);
+            }
+        }
+        else
+        {
+            for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x)
+            {
+                a.x[i] = fma(del, a.p[i], a.x[i]);
+                a.r[i] = fma(-del, a.u[i], a.r[i]);
+            }
+            grid.sync();
+            // step iv: z = M^-1 r ; z.r
+            part = precond_apply<PRECOND>(a, grid, r0, r1, warp_g, nwarps_g, lane);
+        }
+        part = block_sum(part, sm);
+        if (threadIdx.x == 0) partB[blockIdx.x] = part;
+        grid.sync();
+        const double res_new = reduce_partials(partB, G, sm);
+        const double rho = res_new / res;
+        res = res_new;
+        // step v: P = Z + rho P
+        for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x)
+        {
+            double zi = (PRECOND == XFEMM_PRECOND_JACOBI) ? a.r[i] * a.dinv[i] : a.z[i];
+            a.p[i] = fma(rho, a.p[i], zi);
+        }
+        it++;
+        er = sqrt(res / res_o);
+        if (!(er == er)) { status = XFEMM_ERR_DIVERGED; break; }
+        if (er <= a.precision) break;
+        if (it >= a.max_iter) { status = XFEMM_ERR_DIVERGED; break; }
+        grid.sync();
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+    {
+        a.mail[0] = it; a.mail[1] = er; a.mail[2] = status; a.mail[3] = res_o; a.mail[4] = res;
+    }
+}
+
+// one application of the preconditioner as its own cooperative kernel (MultPC, tests)
+template <int PRECOND>
+__global__ void __launch_bounds__(512, 2) k_precond_only(PcgArgs a)
+{
+    cg::grid_group grid = cg::this_grid();
+    const int lane = threadIdx.x & 31;
+    const int nwarps_b = blockDim.x >> 5, warp_b = threadIdx.x >> 5;
+    const int warp_g = blockIdx.x * nwarps_b + warp_b, nwarps_g = gridDim.x * nwarps_b;
+    const int G = gridDim.x;
+    const int s0 = (int)((long long)a.nslices * blockIdx.x / G);
+    const int s1 = (int)((long long)a.nslices * (blockIdx.x + 1) / G);
+    const int r0 = s0 * 32, r1 = s1 * 32;
+    precond_apply<PRECOND>(a, grid, r0, r1, warp_g, nwarps_g, lane);
+    if (PRECOND == XFEMM_PRECOND_JACOBI)
+        for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x) a.z[i] = a.r[i] * a.dinv[i];
+}
+
+// =====================================================================================
+// boundary conditions on the CSR representation
+// =====================================================================================
+__global__ void k_fill_int(int n, int *p, int v)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void k_dir_scatter(int count, const int *__restrict__ nodes, int *dir_idx)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < count) dir_idx[nodes[k]] = k;
+}
+// SetValue for all Dirichlet nodes at once (reference semantics, spars.cpp:318-346):
+//   entry {k,i} is eliminated when i is fixed and i-bdw <= k < i+bdw (whole column if bdw==0);
+//   free row k:  b[k] -= A[k,i]*x_first(i) ; fixed row i: b[i] = A[i,i]*x_last(i).
+__global__ void k_dirichlet(int n, const int *__restrict__ rowptr, const int *__restrict__ col, double *vals,
+                            double *b, const int *__restrict__ dir_idx, const double *__restrict__ xf,
+                            const double *__restrict__ xl, int bdw)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int dk = dir_idx[k];
+    const int s0 = rowptr[k], s1 = rowptr[k + 1];
+    double bk = b[k], dkk = 0.0;
+    for (int s = s0; s < s1; s++)
+    {
+        const int c = col[s];
+        if (c == k) { dkk = vals[s]; continue; }
+        const int dc = dir_idx[c];
+        // eliminated by SetValue(c): c-bdw <= k < c+bdw ; by SetValue(k): k-bdw <= c < k+bdw
+        const bool by_c = dc >= 0 && (bdw == 0 || (k >= c - bdw && k < c + bdw));
+        const bool by_k = dk >= 0 && (bdw == 0 || (c >= k - bdw && c < k + bdw));
+        if (by_c || by_k)
+        {
+            if (by_c && dk < 0) bk = fma(-vals[s], xf[dc], bk);
+            vals[s] = 0.0;
+        }
+    }
+    if (dk >= 0) bk = dkk * xl[dk];
+    b[k] = bk;
+}
+
+// Periodicity / AntiPeriodicity in list order (spars.cpp:421-474 / 366-419).  The host plan
+// groups pairs into dependency levels (pairs of one level touch disjoint entries); one block
+// walks the levels, one warp per pair, lanes over the coupled rows k.
+//   item (4 ints): slot(k,i) slot(i,k) slot(k,j) slot(j,k)
+//   meta (6 ints): i, j, type, slot(i,i), slot(j,j), unused
+__global__ void __launch_bounds__(1024)
+k_periodic(int nlevels, const int *__restrict__ level_ptr, const int *__restrict__ item_ptr,
+           const int *__restrict__ meta, const int *__restrict__ items, double *vals, double *b)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int lv = 0; lv < nlevels; lv++)
+    {
+        for (int pr = level_ptr[lv] + warp; pr < level_ptr[lv + 1]; pr += nw)
+        {
+            const int *m = meta + 6 * pr;
+            const double sgn = m[2] ? -1.0 : 1.0;
+            for (int it = item_ptr[pr] + lane; it < item_ptr[pr + 1]; it += 32)
+            {
+                const int *q = items + 4 * it;
+                double v1 = __ldcg(vals + q[0]), v2 = __ldcg(vals + q[2]);
+                if (v1 != 0.0 || v2 != 0.0)
+                {
+                    double c = (v1 + sgn * v2) / 2.0;
+                    __stcg(vals + q[0], c); __stcg(vals + q[1], c);
+                    __stcg(vals + q[2], sgn * c); __stcg(vals + q[3], sgn * c);
+                }
+            }
+            if (lane == 0)
+            {
+                double c = m[2] ? 0.5 * (__ldcg(vals + m[3]) + __ldcg(vals + m[4]))
+                                : (__ldcg(vals + m[3]) + __ldcg(vals + m[4])) / 2.0;
+                __stcg(vals + m[3], c); __stcg(vals + m[4], c);
+                double bi = __ldcg(b + m[0]), bj = __ldcg(b + m[1]);
+                double cb = 0.5 * (bi + sgn * bj);
+                __stcg(b + m[0], cb); __stcg(b + m[1], sgn * cb);
+            }
+        }
+        __threadfence_block();
+        __syncthreads();
+    }
+}
+
+// Newton bookkeeping (static2d.cpp:953-989)
+__global__ void k_newton_norms(int n, const double *__restrict__ V, const double *__restrict__ Vold, double *part)
+{
+    __shared__ double sm[33];
+    double a = 0, c = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        double v = V[i], d = v - Vold[i];
+        a = fma(d, d, a);
+        c = fma(v, v, c);
+    }
+    a = block_sum(a, sm);
+    c = block_sum(c, sm);
+    if (threadIdx.x == 0) { part[blockIdx.x] = a; part[gridDim.x + blockIdx.x] = c; }
+}
+__global__ void k_relax(int n, double *V, const double *__restrict__ Vold, double relax)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) V[i] = relax * V[i] + (1.0 - relax) * Vold[i];
+}
+
+// =====================================================================================
+// host side
+// =====================================================================================
+int linprob_build_layout(xfemm_linprob *p, int precond)
+{
+    if (p->layout_precond == precond) return XFEMM_OK;
+    SellLayout &L = p->lay;
+    const int sigma = env_int("XFEMM_SELL_SIGMA", 1024);
+    if (precond == XFEMM_PRECOND_MCSSOR)
+    {
+        std::vector<int> color;
+        int nc = greedy_coloring(p->n, p->h_rowptr.data(), p->h_col.data(), color);
+        build_sell_layout(p->n, p->h_rowptr.data(), p->h_col.data(), &color, nc, sigma, L);
+    }
+    else
+        build_sell_layout(p->n, p->h_rowptr.data(), p->h_col.data(), nullptr, 0, sigma, L);
+    cudaStream_t st = p->stream;
+    XB_CUDA(p->i2c.upload(L.i2c.data(), L.i2c.size(), st));
+    XB_CUDA(p->c2i.upload(L.c2i.data(), L.c2i.size(), st));
+    XB_CUDA(p->slice_ptr.upload(L.slice_ptr.data(), L.slice_ptr.size(), st));
+    XB_CUDA(p->slice_wl.upload(L.slice_wl.data(), L.slice_wl.size(), st));
+    XB_CUDA(p->sell_col.upload(L.sell_col.data(), L.sell_col.size(), st));
+    XB_CUDA(p->sell_src.upload(L.sell_src.data(), L.sell_src.size(), st));
+    XB_CUDA(p->diag_src.upload(L.diag_src.data(), L.diag_src.size(), st));
+    XB_CUDA(p->color_slice.upload(L.color_slice.data(), L.color_slice.size(), st));
+    XB_CUDA(p->sell_val.alloc(L.sell_len));
+    for (auto *v : {&p->diag, &p->dinv, &p->x, &p->r, &p->p, &p->u, &p->z, &p->bint})
+    {
+        XB_CUDA(v->alloc(L.n_pad));
+        XB_CUDA(v->zero(st));
+    }
+    XB_CUDA(cudaStreamSynchronize(st));
+    // the big host vectors are no longer needed
+    std::vector<int>().swap(L.sell_col);
+    std::vector<int>().swap(L.sell_src);
+    std::vector<int>().swap(L.diag_src);
+    p->layout_precond = precond;
+    return XFEMM_OK;
+}
+
+static int refresh_values(xfemm_linprob *p, int *singular_row)
+{
+    const SellLayout &L = p->lay;
+    cudaStream_t st = p->stream;
+    int *d_flag = (int *)(p->d_mail.p + 8);
+    int big = 0x7fffffff;
+    XB_CUDA(cudaMemcpyAsync(d_flag, &big, sizeof(int), cudaMemcpyHostToDevice, st));
+    int blocks = (int)std::min<long long>((L.sell_len + 255) / 256, (long long)p->num_sms * 16);
+    if (blocks < 1) blocks = 1;
+    k_sell_fill<<<blocks, 256, 0, st>>>(L.sell_len, p->sell_src.p, p->vals.p, p->sell_val.p);
+    k_diag_fill<<<(L.n_pad + 255) / 256, 256, 0, st>>>(L.n_pad, p->diag_src.p, p->vals.p, p->diag.p, p->dinv.p, d_flag);
+    int flag = 0;
+    XB_CUDA(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    XB_CUDA(cudaStreamSynchronize(st));
+    XB_CUDA(cudaGetLastError());
+    *singular_row = (flag == big) ? -1 : flag;
+    return XFEMM_OK;
+}
+
+template <typename K>
+static int coop_grid(xfemm_linprob *p, K kernel, int threads, int *grid_out)
+{
+    int per_sm = 0;
+    XB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0));
+    if (per_sm < 1) { set_error("cooperative kernel does not fit on an SM"); return XFEMM_ERR_CUDA; }
+    per_sm = std::min(per_sm, env_int("XFEMM_PCG_BLOCKS_PER_SM", 2));
+    int grid = p->num_sms * per_sm;
+    // no point in more warps than slices
+    int warps_per_block = threads / 32;
+    int need = (p->lay.nslices + warps_per_block - 1) / warps_per_block;
+    grid = std::max(1, std::min(grid, need));
+    if (grid > p->max_grid)
+    {
+        XB_CUDA(p->partials.alloc((size_t)4 * grid));
+        p->max_grid = grid;
+    }
+    *grid_out = grid;
+    return XFEMM_OK;
+}
+
+static PcgArgs make_args(xfemm_linprob *p, double precision, int warm, int max_iter)
+{
+    PcgArgs a;
+    a.n_pad = p->lay.n_pad; a.nslices = p->lay.nslices; a.ncolors = p->lay.ncolors;
+    a.slice_ptr = p->slice_ptr.p; a.slice_wl = p->slice_wl.p; a.sell_col = p->sell_col.p;
+    a.color_slice = p->color_slice.p;
+    a.sell_val = p->sell_val.p; a.diag = p->diag.p; a.dinv = p->dinv.p; a.b = p->bint.p;
+    a.x = p->x.p; a.r = p->r.p; a.p = p->p.p; a.u = p->u.p; a.z = p->z.p;
+    a.part = p->partials.p;
+    a.precision = precision;
+    const char *om = getenv("XFEMM_SSOR_OMEGA");
+    a.omega = om ? atof(om) : 1.2;
+    a.max_iter = max_iter; a.warm = warm;
+    a.mail = p->d_mail.p;
+    return a;
+}
+
+} // namespace xb
+
+using namespace xb;
+
+// =====================================================================================
+// C ABI
+// =====================================================================================
+extern "C" {
+
+const char *xfemm_last_error(void) { return xb::last_error(); }
+const char *xfemm_version(void) { return "xfemm_b200 0.1 (sm_100a)"; }
+
+int xfemm_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int xfemm_cuda_init(int device)
+{
+    int n = xfemm_device_count();
+    if (n <= 0) { set_error("no CUDA device available: the xfemm_b200 backend has no CPU fallback"); return XFEMM_ERR_CUDA; }
+    XB_ARG(device >= 0 && device < n, "device index out of range");
+    XB_CUDA(cudaSetDevice(device));
+    XB_CUDA(cudaFree(0));
+    return XFEMM_OK;
+}
+
+int xfemm_linprob_create(int n, const int *rowptr, const int *colidx, xfemm_linprob **out)
+{
+    XB_ARG(n > 0 && rowptr && colidx && out, "n, rowptr, colidx, out");
+    XB_ARG(rowptr[0] == 0, "rowptr[0] must be 0");
+    if (xfemm_device_count() <= 0) { set_error("no CUDA device available: the xfemm_b200 backend has no CPU fallback"); return XFEMM_ERR_CUDA; }
+    const long long nnz = rowptr[n];
+    // validate: sorted columns, diagonal present
+    for (int i = 0; i < n; i++)
+    {
+        bool diag = false;
+        for (int s = rowptr[i]; s < rowptr[i + 1]; s++)
+        {
+            int c = colidx[s];
+            if (c < 0 || c >= n || (s > rowptr[i] && colidx[s - 1] >= c)) { set_error("row %d: columns must be sorted, unique and in range", i); return XFEMM_ERR_ARG; }
+            if (c == i) diag = true;
+        }
+        if (!diag) { set_error("row %d has no diagonal entry", i); return XFEMM_ERR_ARG; }
+    }
+    xfemm_linprob *p = new xfemm_linprob;
+    p->n = n; p->nnz = nnz;
+    int rc = XFEMM_OK;
+    auto fail = [&](int code) { delete p; return code; };
+    if (cudaGetDevice(&p->device) != cudaSuccess) { set_error("cudaGetDevice failed"); return fail(XFEMM_ERR_CUDA); }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, p->device) != cudaSuccess) { set_error("cudaGetDeviceProperties failed"); return fail(XFEMM_ERR_CUDA); }
+    if (!prop.cooperativeLaunch) { set_error("device lacks cooperative launch"); return fail(XFEMM_ERR_CUDA); }
+    p->num_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream create failed"); return fail(XFEMM_ERR_CUDA); }
+    p->h_rowptr.assign(rowptr, rowptr + n + 1);
+    p->h_col.assign(colidx, colidx + nnz);
+    auto body = [&]() -> int {
+        XB_CUDA(p->rowptr.upload(rowptr, n + 1, p->stream));
+        XB_CUDA(p->col.upload(colidx, nnz, p->stream));
+        XB_CUDA(p->vals.alloc(nnz)); XB_CUDA(p->vals.zero(p->stream));
+        XB_CUDA(p->b.alloc(n)); XB_CUDA(p->b.zero(p->stream));
+        XB_CUDA(p->V.alloc(n)); XB_CUDA(p->V.zero(p->stream));
+        XB_CUDA(p->Vold.alloc(n)); XB_CUDA(p->Vold.zero(p->stream));
+        XB_CUDA(p->d_mail.alloc(16)); XB_CUDA(p->d_mail.zero(p->stream));
+        XB_CUDA(p->dir_idx.alloc(n));
+        k_fill_int<<<(n + 255) / 256, 256, 0, p->stream>>>(n, p->dir_idx.p, -1);
+        XB_CUDA(cudaStreamSynchronize(p->stream));
+        return XFEMM_OK;
+    };
+    rc = body();
+    if (rc != XFEMM_OK) { xfemm_linprob_destroy(p); return rc; }
+    *out = p;
+    return XFEMM_OK;
+}
+
+int xfemm_linprob_destroy(xfemm_linprob *p)
+{
+    if (!p) return XFEMM_OK;
+    if (p->stream) { cudaStreamSynchronize(p->stream); cudaStreamDestroy(p->stream); }
+    delete p;
+    return XFEMM_OK;
+}
+
+int xfemm_linprob_n(const xfemm_linprob *p) { return p ? p->n : 0; }
+long long xfemm_linprob_nnz(const xfemm_linprob *p) { return p ? p->nnz : 0; }
+
+int xfemm_linprob_wipe(xfemm_linprob *p)
+{
+    XB_ARG(p, "null handle");
+    XB_CUDA(p->vals.zero(p->stream));
+    XB_CUDA(p->b.zero(p->stream));
+    return XFEMM_OK;
+}
+
+#define XB_COPY_IN(buf, src, cnt)                                                                        \
+    XB_ARG(p && (src), "null pointer");                                                                    \
+    XB_CUDA(cudaMemcpyAsync((buf).p, (src), (size_t)(cnt) * sizeof(double), cudaMemcpyHostToDevice, p->stream)); \
+    XB_CUDA(cudaStreamSynchronize(p->stream));                                                             \
+    return XFEMM_OK
+#define XB_COPY_OUT(buf, dst, cnt)                                                                       \
+    XB_ARG(p && (dst), "null pointer");                                                                    \
+    XB_CUDA(cudaMemcpyAsync((dst), (buf).p, (size_t)(cnt) * sizeof(double), cudaMemcpyDeviceToHost, p->stream)); \
+    XB_CUDA(cudaStreamSynchronize(p->stream));                                                             \
+    return XFEMM_OK
+
+int xfemm_linprob_set_values(xfemm_linprob *p, const double *v) { XB_COPY_IN(p->vals, v, p->nnz); }
+int xfemm_linprob_get_values(xfemm_linprob *p, double *v) { XB_COPY_OUT(p->vals, v, p->nnz); }
+int xfemm_linprob_set_rhs(xfemm_linprob *p, const double *b) { XB_COPY_IN(p->b, b, p->n); }
+int xfemm_linprob_get_rhs(xfemm_linprob *p, double *b) { XB_COPY_OUT(p->b, b, p->n); }
+int xfemm_linprob_set_solution(xfemm_linprob *p, const double *V) { XB_COPY_IN(p->V, V, p->n); }
+int xfemm_linprob_get_solution(xfemm_linprob *p, double *V) { XB_COPY_OUT(p->V, V, p->n); }
+
+int xfemm_linprob_dirichlet(xfemm_linprob *p, int count, const int *nodes, const double *x_first,
+                            const double *x_last, int bdw)
+{
+    XB_ARG(p, "null handle");
+    if (count <= 0) return XFEMM_OK;
+    XB_ARG(nodes && x_first && x_last, "null arrays");
+    for (int k = 0; k < count; k++) XB_ARG(nodes[k] >= 0 && nodes[k] < p->n, "Dirichlet node out of range");
+    cudaStream_t st = p->stream;
+    XB_CUDA(p->dir_nodes.upload(nodes, count, st));
+    XB_CUDA(p->dir_first.upload(x_first, count, st));
+    XB_CUDA(p->dir_last.upload(x_last, count, st));
+    k_dir_scatter<<<(count + 255) / 256, 256, 0, st>>>(count, p->dir_nodes.p, p->dir_idx.p);
+    k_dirichlet<<<(p->n + 255) / 256, 256, 0, st>>>(p->n, p->rowptr.p, p->col.p, p->vals.p, p->b.p, p->dir_idx.p,
+                                                    p->dir_first.p, p->dir_last.p, bdw);
+    // restore the scratch map for the next call
+    k_fill_int<<<(p->n + 255) / 256, 256, 0, st>>>(p->n, p->dir_idx.p, -1);
+    XB_CUDA(cudaGetLastError());
+    XB_CUDA(cudaStreamSynchronize(st));
+    return XFEMM_OK;
+}
+
+static inline int find_slot(const xfemm_linprob *p, int row, int c)
+{
+    const int *b = p->h_col.data() + p->h_rowptr[row], *e = p->h_col.data() + p->h_rowptr[row + 1];
+    const int *it = std::lower_bound(b, e, c);
+    return (it != e && *it == c) ? (int)(it - p->h_col.data()) : -1;
+}
+
+int xfemm_linprob_periodic(xfemm_linprob *p, int npairs, const int *ni, const int *nj, const int *type)
+{
+    XB_ARG(p, "null handle");
+    if (npairs <= 0) return XFEMM_OK;
+    XB_ARG(ni && nj && type, "null arrays");
+    // FNV-1a over the pair list → reuse the plan across Newton steps / sweep angles
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](int v) { h ^= (uint32_t)v; h *= 1099511628211ull; };
+    for (int k = 0; k < npairs; k++) { mix(ni[k]); mix(nj[k]); mix(type[k]); }
+    if (h != p->pbc_hash || npairs != p->pbc_pairs)
+    {
+        // ---- build the plan: symbolic replay in list order on the (fixed) pattern
+        std::vector<int> item_ptr(npairs + 1, 0), meta((size_t)6 * npairs), items, level(npairs, 0);
+        std::unordered_map<long long, int> last_level; // slot / rhs id → last level that touched it
+        std::vector<int> ks;
+        int nlevels = 0;
+        for (int k = 0; k < npairs; k++)
+        {
+            int i = ni[k], j = nj[k];
+            XB_ARG(i >= 0 && i < p->n && j >= 0 && j < p->n && i != j, "periodic pair out of range");
+            if (j < i) std::swap(i, j);
+            ks.clear();
+            for (int s = p->h_rowptr[i]; s < p->h_rowptr[i + 1]; s++) ks.push_back(p->h_col[s]);
+            for (int s = p->h_rowptr[j]; s < p->h_rowptr[j + 1]; s++) ks.push_back(p->h_col[s]);
+            std::sort(ks.begin(), ks.end());
+            ks.erase(std::unique(ks.begin(), ks.end()), ks.end());
+            int lv = 0;
+            auto touch = [&](long long id) { auto f = last_level.find(id); if (f != last_level.end()) lv = std::max(lv, f->second + 1); };
+            size_t first_item = items.size() / 4;
+            for (int kk : ks)
+            {
+                if (kk == i || kk == j) continue;
+                int s_ki = find_slot(p, kk, i), s_ik = find_slot(p, i, kk);
+                int s_kj = find_slot(p, kk, j), s_jk = find_slot(p, j, kk);
+                if (s_ki < 0 || s_ik < 0 || s_kj < 0 || s_jk < 0)
+                {
+                    set_error("pattern lacks the periodic fill for pair (%d,%d) row %d — build it with xfemm_pattern_build", i, j, kk);
+                    return XFEMM_ERR_ARG;
+                }
+                items.insert(items.end(), {s_ki, s_ik, s_kj, s_jk});
+                touch(s_ki); touch(s_ik); touch(s_kj); touch(s_jk);
+            }
+            int s_ii = find_slot(p, i, i), s_jj = find_slot(p, j, j);
+            touch(s_ii); touch(s_jj);
+            touch(-1 - (long long)i); touch(-1 - (long long)j);
+            for (size_t q = first_item * 4; q < items.size(); q++) last_level[items[q]] = lv;
+            last_level[s_ii] = lv; last_level[s_jj] = lv;
+            last_level[-1 - (long long)i] = lv; last_level[-1 - (long long)j] = lv;
+            level[k] = lv;
+            nlevels = std::max(nlevels, lv + 1);
+            item_ptr[k + 1] = (int)(items.size() / 4);
+            int *m = &meta[(size_t)6 * k];
+            m[0] = i; m[1] = j; m[2] = type[k]; m[3] = s_ii; m[4] = s_jj; m[5] = 0;
+        }
+        // reorder pairs by level (stable → list order inside a level)
+        std::vector<int> order(npairs);
+        for (int k = 0; k < npairs; k++) order[k] = k;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return level[a] < level[b]; });
+        std::vector<int> level_ptr(nlevels + 1, 0), item_ptr2(npairs + 1, 0), meta2((size_t)6 * npairs), items2;
+        items2.reserve(items.size());
+        for (int q = 0; q < npairs; q++)
+        {
+            int k = order[q];
+            level_ptr[level[k] + 1]++;
+            for (int t = item_ptr[k] * 4; t < item_ptr[k + 1] * 4; t++) items2.push_back(items[t]);
+            item_ptr2[q + 1] = (int)(items2.size() / 4);
+            for (int t = 0; t < 6; t++) meta2[(size_t)6 * q + t] = meta[(size_t)6 * k + t];
+        }
+        for (int l = 0; l < nlevels; l++) level_ptr[l + 1] += level_ptr[l];
+        cudaStream_t st = p->stream;
+        XB_CUDA(p->pbc_level_ptr.upload(level_ptr.data(), level_ptr.size(), st));
+        XB_CUDA(p->pbc_item_ptr.upload(item_ptr2.data(), item_ptr2.size(), st));
+        XB_CUDA(p->pbc_meta.upload(meta2.data(), meta2.size(), st));
+        if (items2.empty()) items2.assign(4, 0);
+        XB_CUDA(p->pbc_items.upload(items2.data(), items2.size(), st));
+        XB_CUDA(cudaStreamSynchronize(st));
+        p->pbc_hash = h; p->pbc_pairs = npairs; p->pbc_levels = nlevels;
+    }
+    k_periodic<<<1, 1024, 0, p->stream>>>(p->pbc_levels, p->pbc_level_ptr.p, p->pbc_item_ptr.p, p->pbc_meta.p,
+                                          p->pbc_items.p, p->vals.p, p->b.p);
+    XB_CUDA(cudaGetLastError());
+    XB_CUDA(cudaStreamSynchronize(p->stream));
+    return XFEMM_OK;
+}
+
+static int prepare_solver(xfemm_linprob *p, int precond, int *singular)
+{
+    int rc = linprob_build_layout(p, precond);
+    if (rc != XFEMM_OK) return rc;
+    return refresh_values(p, singular);
+}
+
+int xfemm_linprob_pcg(xfemm_linprob *p, double precision, int warm, int precond, int max_iter,
+                      xfemm_solve_info *info)
+{
+    XB_ARG(p, "null handle");
+    XB_ARG(precond == XFEMM_PRECOND_JACOBI || precond == XFEMM_PRECOND_MCSSOR, "unknown preconditioner");
+    cudaStream_t st = p->stream;
+    cudaEvent_t e0, e1, e2;
+    XB_CUDA(cudaEventCreate(&e0)); XB_CUDA(cudaEventCreate(&e1)); XB_CUDA(cudaEventCreate(&e2));
+    XB_CUDA(cudaEventRecord(e0, st));
+    int singular = -1;
+    int rc = prepare_solver(p, precond, &singular);
+    if (rc != XFEMM_OK) return rc;
+    xfemm_solve_info local;
+    memset(&local, 0, sizeof local);
+    local.precond = precond;
+    local.colors = p->lay.ncolors;
+    if (singular >= 0)
+    {
+        // reference: "singular flag tripped" → PCGSolve returns false (spars.cpp:245-249)
+        set_error("singular flag tripped at internal row %d of %d", singular, p->n);
+        local.status = XFEMM_ERR_SINGULAR;
+        if (info) *info = local;
+        return XFEMM_ERR_SINGULAR;
+    }
+    const int n_pad = p->lay.n_pad;
+    k_to_internal<<<(n_pad + 255) / 256, 256, 0, st>>>(n_pad, p->i2c.p, p->b.p, p->bint.p);
+    if (warm) k_to_internal<<<(n_pad + 255) / 256, 256, 0, st>>>(n_pad, p->i2c.p, p->V.p, p->x.p);
+    if (max_iter <= 0) max_iter = env_int("XFEMM_MAX_ITER", 200000);
+    PcgArgs a = make_args(p, precision, warm ? 1 : 0, max_iter);
+    int grid = 0;
+    void *kargs[] = {&a};
+    XB_CUDA(cudaEventRecord(e1, st));
+    if (precond == XFEMM_PRECOND_JACOBI)
+    {
+        rc = coop_grid(p, k_pcg<XFEMM_PRECOND_JACOBI>, 512, &grid);
+        if (rc != XFEMM_OK) return rc;
+        a.part = p->partials.p;
+        XB_CUDA(cudaLaunchCooperativeKernel((void *)k_pcg<XFEMM_PRECOND_JACOBI>, dim3(grid), dim3(512), kargs, 0, st));
+    }
+    else
+    {
+        rc = coop_grid(p, k_pcg<XFEMM_PRECOND_MCSSOR>, 512, &grid);
+        if (rc != XFEMM_OK) return rc;
+        a.part = p->partials.p;
+        XB_CUDA(cudaLaunchCooperativeKernel((void *)k_pcg<XFEMM_PRECOND_MCSSOR>, dim3(grid), dim3(512), kargs, 0, st));
+    }
+    XB_CUDA(cudaEventRecord(e2, st));
+    XB_CUDA(cudaMemcpyAsync(p->h_mail, p->d_mail.p, 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    XB_CUDA(cudaStreamSynchronize(st));
+    XB_CUDA(cudaGetLastError());
+    local.iterations = (int)p->h_mail[0];
+    local.er = p->h_mail[1];
+    local.status = (int)p->h_mail[2];
+    const bool trivial = (p->h_mail[3] == 0.0); // res_o == 0 → reference returns without touching V
+    if (!trivial)
+    {
+        k_from_internal<<<(n_pad + 255) / 256, 256, 0, st>>>(n_pad, p->i2c.p, p->x.p, p->V.p);
+        // true relative residual ||b - A x|| / ||b||
+        int sb = std::max(1, std::min((p->lay.nslices + 7) / 8, p->num_sms * 8));
+        k_spmv<<<sb, 256, 0, st>>>(p->lay.nslices, p->slice_ptr.p, p->sell_col.p, p->sell_val.p, p->diag.p, p->x.p, p->u.p);
+        int nb = std::max(1, std::min((n_pad + 255) / 256, 512));
+        if (p->max_grid < nb) { XB_CUDA(p->partials.alloc((size_t)4 * nb)); p->max_grid = nb; }
+        k_resnorm_partial<<<nb, 256, 0, st>>>(n_pad, p->bint.p, p->u.p, p->partials.p);
+        k_reduce2_final<<<1, 256, 0, st>>>(nb, p->partials.p, p->d_mail.p + 10);
+        XB_CUDA(cudaMemcpyAsync(p->h_mail + 10, p->d_mail.p + 10, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        XB_CUDA(cudaStreamSynchronize(st));
+        XB_CUDA(cudaGetLastError());
+        local.relres = p->h_mail[11] > 0 ? sqrt(p->h_mail[10] / p->h_mail[11]) : 0.0;
+    }
+    float ms_setup = 0, ms_solve = 0;
+    cudaEventElapsedTime(&ms_setup, e0, e1);
+    cudaEventElapsedTime(&ms_solve, e1, e2);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    local.setup_ms = ms_setup;
+    local.solve_ms = ms_solve;
+    // algorithmic bytes per iteration, SURVEY §8(d): Krylov part 12 nnz + 124 n, MC-SSOR adds 12 nnz + 40 n
+    const double nn = (double)p->n, nz = (double)p->nnz;
+    local.bytes_per_iter = 12.0 * nz + 124.0 * nn + (precond == XFEMM_PRECOND_MCSSOR ? 12.0 * nz + 40.0 * nn : 0.0);
+    if (info) *info = local;
+    if (local.status != XFEMM_OK)
+    {
+        set_error("PCG did not converge: %d iterations, er=%g", local.iterations, local.er);
+        return local.status;
+    }
+    return XFEMM_OK;
+}
+
+int xfemm_linprob_multa(xfemm_linprob *p, const double *x, double *y)
+{
+    XB_ARG(p && x && y, "null pointer");
+    int singular = -1;
+    int precond = p->layout_precond >= 0 ? p->layout_precond : XFEMM_PRECOND_JACOBI;
+    int rc = prepare_solver(p, precond, &singular);
+    if (rc != XFEMM_OK) return rc;
+    cudaStream_t st = p->stream;
+    const int n_pad = p->lay.n_pad;
+    // stage through V-sized scratch: Vold is free between Newton steps only, so use r/u
+    XB_CUDA(cudaMemcpyAsync(p->Vold.p, x, (size_t)p->n * sizeof(double), cudaMemcpyHostToDevice, st));
+    k_to_internal<<<(n_pad + 255) / 256, 256, 0, st>>>(n_pad, p->i2c.p, p->Vold.p, p->r.p);
+    int sb = std::max(1, std::min((p->lay.nslices + 7) / 8, p->num_sms * 8));
+    k_spmv<<<sb, 256, 0, st>>>(p->lay.nslices, p->slice_ptr.p, p->sell_col.p, p->sell_val.p, p->diag.p, p->r.p, p->u.p);
+    k_from_internal<<<(n_pad + 255) / 256, 256, 0, st>>>(n_pad, p->i2c.p, p->u.p, p->Vold.p);
+    XB_CUDA(cudaMemcpyAsync(y, p->Vold.p, (size_t)p->n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    XB_CUDA(cudaStreamSynchronize(st));
+    XB_CUDA(cudaGetLastError());
+    return XFEMM_OK;
+}
+
+int xfemm_linprob_multpc(xfemm_linprob *p, int precond, const double *x, double *y)
+{
+    XB_ARG(p && x && y, "null pointer");
+    int singular = -1;
+    int rc = prepare_solver(p, precond, &singular);
+    if (rc != XFEMM_OK) return rc;
+    cudaStream_t st = p->stream;
+    const int n_pad = p->lay.n_pad;
+    XB_CUDA(cudaMemcpyAsync(p->Vold.p, x, (size_t)p->n * sizeof(double), cudaMemcpyHostToDevice, st));
+    k_to_internal<<<(n_pad + 255) / 256, 256, 0, st>>>(n_pad, p->i2c.p, p->Vold.p, p->r.p);
+    PcgArgs a = make_args(p, 0, 0, 0);
+    int grid = 0;
+    void *kargs[] = {&a};
+    if (precond == XFEMM_PRECOND_JACOBI)
+    {
+        rc = coop_grid(p, k_precond_only<XFEMM_PRECOND_JACOBI>, 512, &grid);
+        if (rc != XFEMM_OK) return rc;
+        XB_CUDA(cudaLaunchCooperativeKernel((void *)k_precond_only<XFEMM_PRECOND_JACOBI>, dim3(grid), dim3(512), kargs, 0, st));
+    }
+    else
+    {
+        rc = coop_grid(p, k_precond_only<XFEMM_PRECOND_MCSSOR>, 512, &grid);
+        if (rc != XFEMM_OK) return rc;
+        XB_CUDA(cudaLaunchCooperativeKernel((void *)k_precond_only<XFEMM_PRECOND_MCSSOR>, dim3(grid), dim3(512), kargs, 0, st));
+    }
+    k_from_internal<<<(n_pad + 255) / 256, 256, 0, st>>>(n_pad, p->i2c.p, p->z.p, p->Vold.p);
+    XB_CUDA(cudaMemcpyAsync(y, p->Vold.p, (size_t)p->n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    XB_CUDA(cudaStreamSynchronize(st));
+    XB_CUDA(cudaGetLastError());
+    return XFEMM_OK;
+}
+
+int xfemm_linprob_bench_spmv(xfemm_linprob *p, int reps, double *ms_per_rep)
+{
+    XB_ARG(p && reps > 0 && ms_per_rep, "arguments");
+    int singular = -1;
+    int precond = p->layout_precond >= 0 ? p->layout_precond : XFEMM_PRECOND_JACOBI;
+    int rc = prepare_solver(p, precond, &singular);
+    if (rc != XFEMM_OK) return rc;
+    cudaStream_t st = p->stream;
+    cudaEvent_t e0, e1;
+    XB_CUDA(cudaEventCreate(&e0)); XB_CUDA(cudaEventCreate(&e1));
+    int sb = std::max(1, std::min((p->lay.nslices + 7) / 8, p->num_sms * 8));
+    for (int w = 0; w < 3; w++)
+        k_spmv<<<sb, 256, 0, st>>>(p->lay.nslices, p->slice_ptr.p, p->sell_col.p, p->sell_val.p, p->diag.p, p->bint.p, p->u.p);
+    XB_CUDA(cudaEventRecord(e0, st));
+    for (int w = 0; w < reps; w++)
+        k_spmv<<<sb, 256, 0, st>>>(p->lay.nslices, p->slice_ptr.p, p->sell_col.p, p->sell_val.p, p->diag.p, p->bint.p, p->u.p);
+    XB_CUDA(cudaEventRecord(e1, st));
+    XB_CUDA(cudaStreamSynchronize(st));
+    XB_CUDA(cudaGetLastError());
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *ms_per_rep = ms / reps;
+    return XFEMM_OK;
+}
+
+int xfemm_linprob_save_solution(xfemm_linprob *p)
+{
+    XB_ARG(p, "null handle");
+    XB_CUDA(cudaMemcpyAsync(p->Vold.p, p->V.p, (size_t)p->n * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    return XFEMM_OK;
+}
+
+int xfemm_linprob_newton_norms(xfemm_linprob *p, double *dv2, double *v2)
+{
+    XB_ARG(p && dv2 && v2, "null pointer");
+    cudaStream_t st = p->stream;
+    int nb = std::max(1, std::min((p->n + 255) / 256, 512));
+    if (p->max_grid < nb) { XB_CUDA(p->partials.alloc((size_t)4 * nb)); p->max_grid = nb; }
+    k_newton_norms<<<nb, 256, 0, st>>>(p->n, p->V.p, p->Vold.p, p->partials.p);
+    k_reduce2_final<<<1, 256, 0, st>>>(nb, p->partials.p, p->d_mail.p + 12);
+    XB_CUDA(cudaMemcpyAsync(p->h_mail + 12, p->d_mail.p + 12, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    XB_CUDA(cudaStreamSynchronize(st));
+    XB_CUDA(cudaGetLastError());
+    *dv2 = p->h_mail[12];
+    *v2 = p->h_mail[13];
+    return XFEMM_OK;
+}
+
+int xfemm_linprob_relax(xfemm_linprob *p, double relax)
+{
+    XB_ARG(p, "null handle");
+    k_relax<<<(p->n + 255) / 256, 256, 0, p->stream>>>(p->n, p->V.p, p->Vold.p, relax);
+    XB_CUDA(cudaGetLastError());
+    return XFEMM_OK;
+}
+
+void xfemm_free(void *ptr) { free(ptr); }
+
+} // extern "C"

@@ -1,0 +1,59 @@
+// Device-side real symmetric linear problem (backend of CBigLinProb; reference: cfemm/libfemm/spars.h:38-83).
+#pragma once
+#include "common.cuh"
+#include "layout.h"
+#include <vector>
+#include <cstdint>
+
+// Data layout in HBM (all FP64 values, int32 indices):
+//   "boundary" representation, numbered as the caller numbers unknowns (Cuthill–McKee order):
+//       rowptr[n+1], col[nnz] (full CSR, both triangles, sorted), vals[nnz], b[n], V[n]
+//     → written by the assembly kernels (atomics into CSR slots) and the boundary-condition
+//       kernels; this is what xfemm_linprob_get_values() exports and the parity tests compare.
+//   "solver" representation, internal row order (colour-major, then length-sorted windows):
+//       split SELL-32: slices of 32 rows stored column-major, per slice [lower block | upper
+//       block] (lower = neighbour earlier in the internal order = lower colour), diagonal kept
+//       apart.  A warp owns a slice, lane = row, so every matrix load is a fully coalesced
+//       256 B (values) / 128 B (columns) line.  sell_src[slot] = CSR index feeding the slot
+//       (-1 = padding) so a refill after re-assembly is one gather pass.
+//       Work vectors x,r,p,u,z,diag,dinv,bint live in the same internal order.
+struct xfemm_linprob
+{
+    int n = 0;
+    long long nnz = 0;
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+
+    // boundary representation
+    std::vector<int> h_rowptr, h_col;
+    xb::DevBuf<int> rowptr, col;
+    xb::DevBuf<double> vals, b, V, Vold;
+
+    // solver representation
+    xb::SellLayout lay;            // host copy (small vectors kept; big ones cleared after upload)
+    int layout_precond = -1;       // preconditioner the current layout was built for
+    xb::DevBuf<int> i2c, c2i, slice_ptr, slice_wl, sell_col, sell_src, diag_src;
+    xb::DevBuf<double> sell_val, diag, dinv;
+    xb::DevBuf<double> x, r, p, u, z, bint;
+    xb::DevBuf<double> partials;   // 2 * max_grid
+    xb::DevBuf<int> color_slice;
+    int max_grid = 0;
+
+    // Dirichlet scratch
+    xb::DevBuf<int> dir_idx, dir_nodes;
+    xb::DevBuf<double> dir_first, dir_last;
+
+    // periodic plan (cached per pair list)
+    uint64_t pbc_hash = 0;
+    int pbc_pairs = 0, pbc_levels = 0, pbc_max_level_pairs = 0;
+    xb::DevBuf<int> pbc_level_ptr, pbc_item_ptr, pbc_meta, pbc_items;
+
+    // result mailbox
+    xb::DevBuf<double> d_mail;
+    double h_mail[16];
+};
+
+namespace xb {
+int linprob_build_layout(xfemm_linprob *p, int precond);
+} // namespace xb

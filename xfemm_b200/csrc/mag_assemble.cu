@@ -1,0 +1,491 @@
+// xfemm_mag_* — per-triangle stiffness / source assembly on the GPU.
+// Replaces the element loops of FSolver::Static2D (cfemm/fsolver/static2d.cpp:352-816) and
+// FSolver::StaticAxisymmetric (cfemm/fsolver/staticaxi.cpp:189-640): one thread per element,
+// B-H reluctivity lookup + Newton d(nu)/dB^2 term on the device, FP64 atomics into the fixed
+// CSR pattern of the bound linear problem through a per-element slot map built once per mesh.
+#include "linprob.cuh"
+#include <vector>
+#include <algorithm>
+#include <cmath>
+
+#define XB_PI 3.141592653589793238462643383
+#define XB_MUO 1.2566370614359173e-6
+
+struct xfemm_mag
+{
+    xfemm_linprob *lin = nullptr;
+    int axisymmetric = 0;
+    int n_nodes = 0, n_elems = 0, n_labels = 0, n_bh = 0;
+    xb::DevBuf<double> xy;        // n_nodes*2 (double2)
+    xb::DevBuf<int> tri;          // n_elems*4 (int4: p0,p1,p2,label)
+    xb::DevBuf<int> emap;         // 9*n_elems, SoA: emap[q*n_elems+e] = CSR slot of (p_j,p_k), q=3j+k
+    xb::DevBuf<double> magdir;    // optional per element
+    xb::DevBuf<xfemm_mag_label> labels;
+    xb::DevBuf<double> bhB, bhH, bhS;
+    xb::DevBuf<double> mu;        // n_elems*2
+    // mixed-BC edges
+    int n_mixed = 0;
+    xb::DevBuf<int> mixed_es;
+    xb::DevBuf<double> mixed_c;
+    // air-gap elements
+    int n_age_cells = 0, n_age_mats = 0;
+    xb::DevBuf<int> age_nodes, age_mid;
+    xb::DevBuf<double> age_w, age_mats;
+    // point sources
+    int n_psrc = 0;
+    xb::DevBuf<int> psrc_node;
+    xb::DevBuf<double> psrc_val;
+    double ext_zo = 0, ext_ro = 0, ext_ri = 0, r_eps = 0;
+    xb::DevBuf<int> err_flag;
+};
+
+namespace xb {
+
+__device__ __forceinline__ int csr_find(const int *__restrict__ rowptr, const int *__restrict__ col, int row, int c)
+{
+    int lo = rowptr[row], hi = rowptr[row + 1] - 1;
+    while (lo <= hi)
+    {
+        int mid = (lo + hi) >> 1;
+        int v = col[mid];
+        if (v == c) return mid;
+        if (v < c) lo = mid + 1; else hi = mid - 1;
+    }
+    return -1;
+}
+
+__global__ void k_build_emap(int ne, const int4 *__restrict__ tri, const int *__restrict__ rowptr,
+                             const int *__restrict__ col, int *__restrict__ emap, int *err)
+{
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ne) return;
+    int4 t = tri[e];
+    int n[3] = {t.x, t.y, t.z};
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+        {
+            int s = csr_find(rowptr, col, n[j], n[k]);
+            if (s < 0) atomicExch(err, 1);
+            emap[(size_t)(3 * j + k) * ne + e] = s;
+        }
+}
+
+// Cubic-Hermite H(B) lookup: nu = H/B and dnu/dB^2 (reference: CMaterialProp.cpp:1007-1057).
+__device__ __forceinline__ void bh_props(const double *__restrict__ Bd, const double *__restrict__ Hd,
+                                         const double *__restrict__ Sd, int npts, double mu_x, double B,
+                                         double &v, double &dv)
+{
+    double b = fabs(B);
+    if (npts == 0) { v = mu_x; dv = 0; return; }
+    if (b == 0) { v = Sd[0]; dv = 0; return; }
+    if (b > Bd[npts - 1])
+    {
+        double h = Hd[npts - 1] + Sd[npts - 1] * (b - Bd[npts - 1]);
+        double dh = Sd[npts - 1];
+        v = h / b;
+        dv = 0.5 * (dh / (b * b) - h / (b * b * b));
+        return;
+    }
+    v = 0; dv = 0; // (the reference leaves v,dv untouched if no interval matches; cannot happen for b>=Bd[0]=0)
+    for (int i = 0; i < npts - 1; i++)
+    {
+        if (b >= Bd[i] && b <= Bd[i + 1])
+        {
+            double l = Bd[i + 1] - Bd[i];
+            double z = (b - Bd[i]) / l, z2 = z * z;
+            double h = (1. - 3. * z2 + 2. * z2 * z) * Hd[i] + z * (1. - 2. * z + z2) * l * Sd[i] +
+                       z2 * (3. - 2. * z) * Hd[i + 1] + z2 * (z - 1.) * l * Sd[i + 1];
+            double dh = 6. * z * (z - 1.) * Hd[i] / l + (1. - 4. * z + 3. * z * z) * Sd[i] +
+                        6. * z * (1. - z) * Hd[i + 1] / l + z * (3. * z - 2.) * Sd[i + 1];
+            v = h / b;
+            dv = 0.5 * (dh / (b * b) - h / (b * b * b));
+            return;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// planar magnetostatic element (static2d.cpp:368-815)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_assemble_static2d(int ne, int iter, const int4 *__restrict__ tri, const double2 *__restrict__ xy,
+                    const int *__restrict__ emap, const xfemm_mag_label *__restrict__ labels,
+                    const double *__restrict__ magdir_elem, const double *__restrict__ bhB,
+                    const double *__restrict__ bhH, const double *__restrict__ bhS,
+                    const double *__restrict__ V, double *vals, double *b, double2 *mu_out)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ne) return;
+    const double c = XB_PI * 4.e-05;
+    const int4 t = tri[e];
+    const int n[3] = {t.x, t.y, t.z};
+    const double2 P0 = xy[n[0]], P1 = xy[n[1]], P2 = xy[n[2]];
+    const double p[3] = {P1.y - P2.y, P2.y - P0.y, P0.y - P1.y};
+    const double q[3] = {P2.x - P1.x, P0.x - P2.x, P1.x - P0.x};
+    const double a = (p[0] * q[1] - p[1] * q[0]) / 2.;
+    const double K = -1. / (4. * a);
+    const xfemm_mag_label L = labels[t.w];
+
+    double Mx[3][3], My[3][3], Mn[3][3], be[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+    {
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+        {
+            Mx[j][k] = K * p[j] * p[k];
+            My[j][k] = K * q[j] * q[k];
+            Mn[j][k] = 0.;
+        }
+        // current density incl. circuit term (static2d.cpp:483-504)
+        be[j] = -(L.Jsrc) * a / 3.;
+    }
+    // permanent magnet (static2d.cpp:584-598); dx,dy of side j→k are -q, p of the opposite node
+    if (L.H_c != 0.)
+    {
+        const double th = (magdir_elem ? magdir_elem[e] : L.magdir) * XB_PI / 180.;
+        const double cs = cos(th), sn = sin(th);
+        const double X[3] = {P0.x, P1.x, P2.x}, Y[3] = {P0.y, P1.y, P2.y};
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+        {
+            const int k = (j + 1) % 3;
+            const double Km = 0.0001 * L.H_c * (cs * (X[k] - X[j]) + sn * (Y[k] - Y[j])) / 2.;
+            be[j] += Km;
+            be[k] += Km;
+        }
+    }
+
+    double mu1 = L.mu1, mu2 = L.mu2;
+    double Vn[3] = {0., 0., 0.};
+    if (iter > 0 && L.bh_points > 0)
+    {
+        Vn[0] = V[n[0]]; Vn[1] = V[n[1]]; Vn[2] = V[n[2]];
+        const double *Bd = bhB + L.bh_offset, *Hd = bhH + L.bh_offset, *Sd = bhS + L.bh_offset;
+        double v[3], u[3], nu, dv;
+        if (L.lamtype == 0)
+        {
+            // static2d.cpp:687-717 (mu1==mu2 always holds for B-H materials here: GetSlopes sets mu_y=mu_x)
+            double B1 = 0., B2 = 0.;
+#pragma unroll
+            for (int j = 0; j < 3; j++) { B1 += Vn[j] * q[j]; B2 += Vn[j] * p[j]; }
+            const double B = c * sqrt(B1 * B1 + B2 * B2) / (0.02 * a);
+            bh_props(Bd, Hd, Sd, L.bh_points, L.mu1, B, nu, dv);
+            const double mu = 1. / (XB_MUO * nu);
+            mu1 = mu; mu2 = mu;
+#pragma unroll
+            for (int j = 0; j < 3; j++)
+            {
+                v[j] = 0;
+#pragma unroll
+                for (int w = 0; w < 3; w++) v[j] += (Mx[j][w] + My[j][w]) * Vn[w];
+            }
+            const double Kn = -200. * c * c * c * dv / a;
+#pragma unroll
+            for (int j = 0; j < 3; j++)
+#pragma unroll
+                for (int w = 0; w < 3; w++) Mn[j][w] = Kn * v[j] * v[w];
+        }
+        else if (L.lamtype == 1 || L.lamtype == 2)
+        {
+            // laminated in-plane variants (static2d.cpp:719-796)
+            const double tt = L.lamfill;
+            double B1 = 0., B2 = 0.;
+#pragma unroll
+            for (int j = 0; j < 3; j++)
+            {
+                if (L.lamtype == 1) { B1 += Vn[j] * q[j]; B2 += Vn[j] * p[j] / tt; }
+                else { B1 += (Vn[j] * q[j]) / tt; B2 += Vn[j] * p[j]; }
+            }
+            const double B = c * sqrt(B1 * B1 + B2 * B2) / (0.02 * a);
+            bh_props(Bd, Hd, Sd, L.bh_points, L.mu1, B, nu, dv);
+            const double mu = 1. / (XB_MUO * nu);
+            if (L.lamtype == 1) { mu1 = mu * tt; mu2 = mu / (tt + mu * (1. - tt)); }
+            else { mu2 = mu * tt; mu1 = mu / (tt + mu * (1. - tt)); }
+#pragma unroll
+            for (int j = 0; j < 3; j++)
+            {
+                v[j] = 0; u[j] = 0;
+#pragma unroll
+                for (int w = 0; w < 3; w++)
+                {
+                    if (L.lamtype == 1)
+                    {
+                        v[j] += (My[j][w] / tt + Mx[j][w]) * Vn[w];
+                        u[j] += (My[j][w] / tt + tt * Mx[j][w]) * Vn[w];
+                    }
+                    else
+                    {
+                        v[j] += (Mx[j][w] / tt + My[j][w]) * Vn[w];
+                        u[j] += (Mx[j][w] / tt + tt * My[j][w]) * Vn[w];
+                    }
+                }
+            }
+            const double Kn = -100. * c * c * c * dv / a;
+#pragma unroll
+            for (int j = 0; j < 3; j++)
+#pragma unroll
+                for (int w = 0; w < 3; w++) Mn[j][w] = Kn * (v[j] * u[w] + v[w] * u[j]);
+        }
+    }
+    if (mu_out) mu_out[e] = make_double2(mu1, mu2);
+
+    // Me = Mx/mu2 + My/mu1 + Mn ; be += Mn V ; scatter -Me, -be (static2d.cpp:799-815)
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+    {
+        double bj = be[j];
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+        {
+            const double me = Mx[j][k] / mu2 + My[j][k] / mu1 + Mn[j][k];
+            bj += Mn[j][k] * Vn[k];
+            atomicAdd(vals + emap[(size_t)(3 * j + k) * ne + e], -me);
+        }
+        atomicAdd(b + n[j], -bj);
+    }
+}
+
+// mixed (Robin) boundary edges, BdryFormat==2 (static2d.cpp:460-480)
+__global__ void k_mixed_edges(int nm, int ne, const int *__restrict__ es, const double *__restrict__ c01,
+                              const int4 *__restrict__ tri, const double2 *__restrict__ xy,
+                              const int *__restrict__ emap, double *vals, double *b)
+{
+    int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= nm) return;
+    const double c = XB_PI * 4.e-05;
+    const int e = es[2 * m], j = es[2 * m + 1], k = (j + 1) % 3;
+    const int4 t = tri[e];
+    const int n[3] = {t.x, t.y, t.z};
+    const double2 A = xy[n[j]], B = xy[n[k]];
+    const double l = sqrt((B.x - A.x) * (B.x - A.x) + (B.y - A.y) * (B.y - A.y));
+    const double K = -0.0001 * c * c01[2 * m] * l / 6.;
+    atomicAdd(vals + emap[(size_t)(3 * j + j) * ne + e], -(K * 2.));
+    atomicAdd(vals + emap[(size_t)(3 * k + k) * ne + e], -(K * 2.));
+    atomicAdd(vals + emap[(size_t)(3 * j + k) * ne + e], -K);
+    atomicAdd(vals + emap[(size_t)(3 * k + j) * ne + e], -K);
+    const double K2 = (c01[2 * m + 1] * l / 2.) * 0.0001;
+    atomicAdd(b + n[j], -K2);
+    atomicAdd(b + n[k], -K2);
+}
+
+// air-gap element ring cells: L.AddTo(MG[ii][jj]*ww[ii]*ww[jj], nn[ii], nn[jj]) for jj>=ii
+// (static2d.cpp:345-347).  sign=-1 for the harmonic formulation (harmonic2d.cpp:382).
+__global__ void k_age_scatter(int ncells, const int *__restrict__ nodes, const double *__restrict__ w,
+                              const int *__restrict__ mid, const double *__restrict__ mats,
+                              const int *__restrict__ rowptr, const int *__restrict__ col, double *vals,
+                              double sign, int *err)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ncells * 55) return;
+    const int cell = t / 55;
+    int q = t % 55, ii = 0;
+    while (q >= 10 - ii) { q -= 10 - ii; ii++; }
+    const int jj = ii + q;
+    const int a = nodes[cell * 10 + ii], bnode = nodes[cell * 10 + jj];
+    const double v = sign * (mats[mid[cell] * 100 + ii * 10 + jj] * w[cell * 10 + ii] * w[cell * 10 + jj]);
+    const int s1 = csr_find(rowptr, col, a, bnode);
+    if (s1 < 0) { atomicExch(err, 2); return; }
+    atomicAdd(vals + s1, v);
+    if (a != bnode)
+    {
+        const int s2 = csr_find(rowptr, col, bnode, a);
+        if (s2 < 0) { atomicExch(err, 2); return; }
+        atomicAdd(vals + s2, v);
+    }
+}
+
+__global__ void k_point_sources(int np, const int *__restrict__ node, const double *__restrict__ val, double *b)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < np) atomicAdd(b + node[i], val[i]);
+}
+
+__global__ void k_scale_to_A(int n, const double *__restrict__ V, const double2 *__restrict__ xy, int axi, double *out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double c = XB_PI * 4.e-05;
+    double v = V[i] * c;
+    if (axi) v = V[i] * c * 2. * XB_PI * xy[i].x * 0.01; // staticaxi.cpp:779-783
+    out[i] = v;
+}
+
+} // namespace xb
+
+using namespace xb;
+
+extern "C" {
+
+int xfemm_mag_set_labels(xfemm_mag *m, int n_labels, const xfemm_mag_label *labels)
+{
+    XB_ARG(m && labels && n_labels > 0, "labels");
+    XB_CUDA(m->labels.upload(labels, n_labels, m->lin->stream));
+    XB_CUDA(cudaStreamSynchronize(m->lin->stream));
+    m->n_labels = n_labels;
+    return XFEMM_OK;
+}
+
+int xfemm_mag_set_age(xfemm_mag *m, int n_age_cells, const int *age_nodes, const double *age_weights,
+                      const int *age_matrix_id, int n_age_matrices, const double *age_matrices)
+{
+    XB_ARG(m, "null handle");
+    m->n_age_cells = n_age_cells;
+    m->n_age_mats = n_age_matrices;
+    if (n_age_cells <= 0) return XFEMM_OK;
+    XB_ARG(age_nodes && age_weights && age_matrix_id && age_matrices && n_age_matrices > 0, "AGE tables");
+    for (int i = 0; i < n_age_cells * 10; i++) XB_ARG(age_nodes[i] >= 0 && age_nodes[i] < m->n_nodes, "AGE node out of range");
+    for (int i = 0; i < n_age_cells; i++) XB_ARG(age_matrix_id[i] >= 0 && age_matrix_id[i] < n_age_matrices, "AGE matrix id");
+    cudaStream_t st = m->lin->stream;
+    XB_CUDA(m->age_nodes.upload(age_nodes, (size_t)n_age_cells * 10, st));
+    XB_CUDA(m->age_w.upload(age_weights, (size_t)n_age_cells * 10, st));
+    XB_CUDA(m->age_mid.upload(age_matrix_id, n_age_cells, st));
+    XB_CUDA(m->age_mats.upload(age_matrices, (size_t)n_age_matrices * 100, st));
+    XB_CUDA(cudaStreamSynchronize(st));
+    return XFEMM_OK;
+}
+
+int xfemm_mag_create(const xfemm_mag_desc *d, xfemm_linprob *lin, xfemm_mag **out)
+{
+    XB_ARG(d && lin && out, "null pointer");
+    XB_ARG(d->n_nodes > 0 && d->n_elems > 0 && d->xy && d->tri && d->labels && d->n_labels > 0, "mesh arrays");
+    XB_ARG(d->n_nodes <= lin->n, "linear problem smaller than the mesh");
+    for (int e = 0; e < d->n_elems; e++)
+    {
+        const int *t = d->tri + 4 * (size_t)e;
+        if (t[0] < 0 || t[0] >= d->n_nodes || t[1] < 0 || t[1] >= d->n_nodes || t[2] < 0 || t[2] >= d->n_nodes ||
+            t[3] < 0 || t[3] >= d->n_labels)
+        {
+            set_error("element %d has node or label index out of range", e);
+            return XFEMM_ERR_ARG;
+        }
+    }
+    xfemm_mag *m = new xfemm_mag;
+    m->lin = lin;
+    m->axisymmetric = d->axisymmetric;
+    m->n_nodes = d->n_nodes; m->n_elems = d->n_elems; m->n_bh = d->n_bh;
+    m->ext_zo = d->ext_zo; m->ext_ro = d->ext_ro; m->ext_ri = d->ext_ri; m->r_eps = d->r_eps;
+    cudaStream_t st = lin->stream;
+    auto body = [&]() -> int {
+        XB_CUDA(m->xy.upload(d->xy, (size_t)d->n_nodes * 2, st));
+        XB_CUDA(m->tri.upload(d->tri, (size_t)d->n_elems * 4, st));
+        if (d->magdir_elem) XB_CUDA(m->magdir.upload(d->magdir_elem, d->n_elems, st));
+        if (d->n_bh > 0)
+        {
+            XB_ARG(d->bh_B && d->bh_H && d->bh_slope, "B-H tables");
+            XB_CUDA(m->bhB.upload(d->bh_B, d->n_bh, st));
+            XB_CUDA(m->bhH.upload(d->bh_H, d->n_bh, st));
+            XB_CUDA(m->bhS.upload(d->bh_slope, d->n_bh, st));
+        }
+        m->n_mixed = d->n_mixed;
+        if (d->n_mixed > 0)
+        {
+            XB_ARG(d->mixed_elem_side && d->mixed_c0c1, "mixed-BC arrays");
+            XB_CUDA(m->mixed_es.upload(d->mixed_elem_side, (size_t)d->n_mixed * 2, st));
+            XB_CUDA(m->mixed_c.upload(d->mixed_c0c1, (size_t)d->n_mixed * 2, st));
+        }
+        m->n_psrc = d->n_point_src;
+        if (d->n_point_src > 0)
+        {
+            XB_ARG(d->point_src_node && d->point_src_val, "point source arrays");
+            XB_CUDA(m->psrc_node.upload(d->point_src_node, d->n_point_src, st));
+            XB_CUDA(m->psrc_val.upload(d->point_src_val, d->n_point_src, st));
+        }
+        XB_CUDA(m->mu.alloc((size_t)d->n_elems * 2));
+        XB_CUDA(m->emap.alloc((size_t)d->n_elems * 9));
+        XB_CUDA(m->err_flag.alloc(1));
+        XB_CUDA(m->err_flag.zero(st));
+        k_build_emap<<<(d->n_elems + 255) / 256, 256, 0, st>>>(d->n_elems, (const int4 *)m->tri.p, lin->rowptr.p,
+                                                                lin->col.p, m->emap.p, m->err_flag.p);
+        int flag = 0;
+        XB_CUDA(cudaMemcpyAsync(&flag, m->err_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        XB_CUDA(cudaStreamSynchronize(st));
+        XB_CUDA(cudaGetLastError());
+        if (flag) { set_error("the linear problem's pattern does not contain the mesh graph"); return XFEMM_ERR_ARG; }
+        return XFEMM_OK;
+    };
+    int rc = body();
+    if (rc == XFEMM_OK) rc = xfemm_mag_set_labels(m, d->n_labels, d->labels);
+    if (rc == XFEMM_OK)
+        rc = xfemm_mag_set_age(m, d->n_age_cells, d->age_nodes, d->age_weights, d->age_matrix_id, d->n_age_matrices,
+                               d->age_matrices);
+    if (rc != XFEMM_OK) { delete m; return rc; }
+    *out = m;
+    return XFEMM_OK;
+}
+
+int xfemm_mag_destroy(xfemm_mag *m)
+{
+    if (!m) return XFEMM_OK;
+    if (m->lin && m->lin->stream) cudaStreamSynchronize(m->lin->stream);
+    delete m;
+    return XFEMM_OK;
+}
+
+int xfemm_mag_assemble_static(xfemm_mag *m, int iter, double *elapsed_ms)
+{
+    XB_ARG(m && m->lin, "null handle");
+    XB_ARG(!m->axisymmetric, "axisymmetric assembly is not available in this build");
+    xfemm_linprob *L = m->lin;
+    cudaStream_t st = L->stream;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (elapsed_ms) { XB_CUDA(cudaEventCreate(&e0)); XB_CUDA(cudaEventCreate(&e1)); XB_CUDA(cudaEventRecord(e0, st)); }
+    // Wipe (static2d.cpp:186-189); on iter 0 the caller hands over a fresh problem, wiping is harmless
+    XB_CUDA(L->vals.zero(st));
+    XB_CUDA(L->b.zero(st));
+    XB_CUDA(m->err_flag.zero(st));
+    if (m->n_age_cells > 0)
+    {
+        int nt = m->n_age_cells * 55;
+        k_age_scatter<<<(nt + 127) / 128, 128, 0, st>>>(m->n_age_cells, m->age_nodes.p, m->age_w.p, m->age_mid.p,
+                                                        m->age_mats.p, L->rowptr.p, L->col.p, L->vals.p, 1.0, m->err_flag.p);
+    }
+    k_assemble_static2d<<<(m->n_elems + 255) / 256, 256, 0, st>>>(
+        m->n_elems, iter, (const int4 *)m->tri.p, (const double2 *)m->xy.p, m->emap.p, m->labels.p,
+        m->magdir.n ? m->magdir.p : nullptr, m->bhB.p, m->bhH.p, m->bhS.p, L->V.p, L->vals.p, L->b.p, (double2 *)m->mu.p);
+    if (m->n_mixed > 0)
+        k_mixed_edges<<<(m->n_mixed + 127) / 128, 128, 0, st>>>(m->n_mixed, m->n_elems, m->mixed_es.p, m->mixed_c.p,
+                                                                (const int4 *)m->tri.p, (const double2 *)m->xy.p,
+                                                                m->emap.p, L->vals.p, L->b.p);
+    if (m->n_psrc > 0)
+        k_point_sources<<<(m->n_psrc + 127) / 128, 128, 0, st>>>(m->n_psrc, m->psrc_node.p, m->psrc_val.p, L->b.p);
+    int flag = 0;
+    XB_CUDA(cudaMemcpyAsync(&flag, m->err_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (elapsed_ms) XB_CUDA(cudaEventRecord(e1, st));
+    XB_CUDA(cudaStreamSynchronize(st));
+    XB_CUDA(cudaGetLastError());
+    if (elapsed_ms)
+    {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        *elapsed_ms = ms;
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
+    if (flag) { set_error("air-gap element couples nodes that are missing from the pattern"); return XFEMM_ERR_ARG; }
+    return XFEMM_OK;
+}
+
+int xfemm_mag_get_mu(xfemm_mag *m, double *mu12)
+{
+    XB_ARG(m && mu12, "null pointer");
+    XB_CUDA(cudaMemcpyAsync(mu12, m->mu.p, (size_t)m->n_elems * 2 * sizeof(double), cudaMemcpyDeviceToHost, m->lin->stream));
+    XB_CUDA(cudaStreamSynchronize(m->lin->stream));
+    return XFEMM_OK;
+}
+
+int xfemm_mag_solution_to_A(xfemm_mag *m, double *A_host)
+{
+    XB_ARG(m && A_host, "null pointer");
+    xfemm_linprob *L = m->lin;
+    cudaStream_t st = L->stream;
+    // reference: L.b[i] = L.V[i]*c — the RHS array doubles as the result array (static2d.cpp:1018-1021)
+    k_scale_to_A<<<(m->n_nodes + 255) / 256, 256, 0, st>>>(m->n_nodes, L->V.p, (const double2 *)m->xy.p, m->axisymmetric, L->b.p);
+    XB_CUDA(cudaMemcpyAsync(A_host, L->b.p, (size_t)m->n_nodes * sizeof(double), cudaMemcpyDeviceToHost, st));
+    XB_CUDA(cudaStreamSynchronize(st));
+    XB_CUDA(cudaGetLastError());
+    return XFEMM_OK;
+}
+
+} // extern "C"

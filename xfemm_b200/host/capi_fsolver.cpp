@@ -1,0 +1,231 @@
+// xfemm_fsolver_* — file-level C entry points around the FSolver class: what cfemm/fsolver/main.cpp
+// and mfemm/mexfsolver.cpp do with the reference class, exposed with plain C types so that
+// ctypes / MEX / Lua bindings (and this repo's tests and bench) can drive the same path.
+#include "fsolver.h"
+#include "../../include/xfemm_b200.h"
+#include <cstring>
+
+namespace xb { void set_error(const char *fmt, ...); }
+
+struct xfemm_fsolver
+{
+    FSolver S;
+    CBigLinProb *L = nullptr;
+    CBigComplexLinProb *Lc = nullptr;
+    bool verbose = false;
+    ~xfemm_fsolver() { delete L; delete Lc; }
+};
+
+static int quiet(const char *, ...) { return 0; }
+
+extern "C" {
+
+int xfemm_fsolver_run(const char *basename, int verbose)
+{
+    if (!basename) return 1;
+    FSolver S;
+    S.PathName = basename;
+    if (!verbose) { S.WarnMessage = quiet; S.PrintMessage = quiet; }
+    if (!S.LoadProblemFile()) return 1;
+    if (!S.runSolver(verbose != 0)) return 2;
+    return 0;
+}
+
+int xfemm_fsolver_open(const char *basename, int verbose, xfemm_fsolver **out)
+{
+    if (!basename || !out) { xb::set_error("null argument"); return XFEMM_ERR_ARG; }
+    xfemm_fsolver *s = new xfemm_fsolver;
+    s->verbose = verbose != 0;
+    s->S.PathName = basename;
+    if (!verbose) { s->S.WarnMessage = quiet; s->S.PrintMessage = quiet; }
+    if (!s->S.LoadProblemFile())
+    {
+        delete s;
+        xb::set_error("problem loading %s.fem", basename);
+        return XFEMM_ERR_IO;
+    }
+    *out = s;
+    return XFEMM_OK;
+}
+
+int xfemm_fsolver_close(xfemm_fsolver *s) { delete s; return XFEMM_OK; }
+
+int xfemm_fsolver_load_mesh(xfemm_fsolver *s, int delete_files)
+{
+    if (!s) return XFEMM_ERR_ARG;
+    LoadMeshErr e = s->S.LoadMesh(delete_files != 0);
+    if (e != NOERROR) { xb::set_error("%s", FSolver::getErrorString(e).c_str()); return XFEMM_ERR_IO; }
+    return XFEMM_OK;
+}
+
+int xfemm_fsolver_renumber(xfemm_fsolver *s, int delete_files)
+{
+    if (!s) return XFEMM_ERR_ARG;
+    if (!s->S.Cuthill(delete_files != 0)) { xb::set_error("problem renumbering node points"); return XFEMM_ERR_IO; }
+    return XFEMM_OK;
+}
+
+int xfemm_fsolver_solve(xfemm_fsolver *s)
+{
+    if (!s) return XFEMM_ERR_ARG;
+    FSolver &S = s->S;
+    int ok;
+    if (S.Frequency == 0)
+    {
+        delete s->L;
+        s->L = new CBigLinProb;
+        s->L->Precision = S.Precision;
+        s->L->Create(S.NumNodes, S.BandWidth);
+        ok = (S.ProblemType == femm::PLANAR) ? S.Static2D(*s->L) : S.StaticAxisymmetric(*s->L);
+    }
+    else
+    {
+        delete s->Lc;
+        s->Lc = new CBigComplexLinProb;
+        s->Lc->Precision = S.Precision;
+        s->Lc->Create(S.NumNodes + S.NumCircProps, S.BandWidth, S.NumNodes);
+        ok = (S.ProblemType == femm::PLANAR) ? S.Harmonic2D(*s->Lc, s->verbose) : S.HarmonicAxisymmetric(*s->Lc, s->verbose);
+    }
+    if (ok != 1)
+    {
+        std::string prev = xfemm_last_error();
+        xb::set_error("solve failed (%s)", prev.c_str());
+        return XFEMM_ERR_DIVERGED;
+    }
+    return XFEMM_OK;
+}
+
+int xfemm_fsolver_write(xfemm_fsolver *s)
+{
+    if (!s) return XFEMM_ERR_ARG;
+    int ok = 0;
+    if (s->L) ok = s->S.WriteStatic2D(*s->L);
+    else if (s->Lc) ok = s->S.WriteHarmonic2D(*s->Lc);
+    if (!ok) { xb::set_error("couldn't write results to disk"); return XFEMM_ERR_IO; }
+    return XFEMM_OK;
+}
+
+int xfemm_fsolver_counts(xfemm_fsolver *s, int *n_nodes, int *n_elems, int *n_pbc, int *n_age, int *bandwidth,
+                         int *n_unknowns, int *is_complex)
+{
+    if (!s) return XFEMM_ERR_ARG;
+    const FSolver &S = s->S;
+    if (n_nodes) *n_nodes = S.NumNodes;
+    if (n_elems) *n_elems = S.NumEls;
+    if (n_pbc) *n_pbc = S.NumPBCs;
+    if (n_age) *n_age = S.NumAirGapElems;
+    if (bandwidth) *bandwidth = S.BandWidth;
+    if (is_complex) *is_complex = S.Frequency != 0;
+    if (n_unknowns) *n_unknowns = S.Frequency != 0 ? S.NumNodes + S.NumCircProps : S.NumNodes;
+    return XFEMM_OK;
+}
+
+int xfemm_fsolver_get_nodes(xfemm_fsolver *s, double *xy, int *bc)
+{
+    if (!s) return XFEMM_ERR_ARG;
+    for (int i = 0; i < s->S.NumNodes; i++)
+    {
+        if (xy) { xy[2 * (size_t)i] = s->S.meshnode[i].x; xy[2 * (size_t)i + 1] = s->S.meshnode[i].y; }
+        if (bc) bc[i] = s->S.meshnode[i].BoundaryMarker;
+    }
+    return XFEMM_OK;
+}
+
+int xfemm_fsolver_get_elems(xfemm_fsolver *s, int *e8)
+{
+    if (!s || !e8) return XFEMM_ERR_ARG;
+    for (int i = 0; i < s->S.NumEls; i++)
+    {
+        const femmsolver::CMElement &e = s->S.meshele[i];
+        int *r = e8 + 8 * (size_t)i;
+        r[0] = e.p[0]; r[1] = e.p[1]; r[2] = e.p[2]; r[3] = e.lbl; r[4] = e.blk; r[5] = e.e[0]; r[6] = e.e[1]; r[7] = e.e[2];
+    }
+    return XFEMM_OK;
+}
+
+int xfemm_fsolver_get_pbc(xfemm_fsolver *s, int *pbc3)
+{
+    if (!s || !pbc3) return XFEMM_ERR_ARG;
+    for (int i = 0; i < s->S.NumPBCs; i++)
+    {
+        pbc3[3 * i] = s->S.pbclist[i].x; pbc3[3 * i + 1] = s->S.pbclist[i].y; pbc3[3 * i + 2] = s->S.pbclist[i].t;
+    }
+    return XFEMM_OK;
+}
+
+int xfemm_fsolver_get_permutation(xfemm_fsolver *s, int *newnum)
+{
+    if (!s || !newnum || (int)s->S.cmPermutation.size() != s->S.NumNodes) { xb::set_error("no permutation available"); return XFEMM_ERR_ARG; }
+    memcpy(newnum, s->S.cmPermutation.data(), sizeof(int) * s->S.NumNodes);
+    return XFEMM_OK;
+}
+
+int xfemm_fsolver_get_pattern(xfemm_fsolver *s, long long *nnz, int *rowptr, int *colidx)
+{
+    if (!s || s->S.sysRowptr.empty()) { xb::set_error("no system kept: set option keep_system=1 before solving"); return XFEMM_ERR_ARG; }
+    if (nnz) *nnz = (long long)s->S.sysCol.size();
+    if (rowptr) memcpy(rowptr, s->S.sysRowptr.data(), sizeof(int) * s->S.sysRowptr.size());
+    if (colidx) memcpy(colidx, s->S.sysCol.data(), sizeof(int) * s->S.sysCol.size());
+    return XFEMM_OK;
+}
+
+int xfemm_fsolver_get_system(xfemm_fsolver *s, double *vals, double *rhs)
+{
+    if (!s || s->S.sysVals.empty()) { xb::set_error("no system kept: set option keep_system=1 before solving"); return XFEMM_ERR_ARG; }
+    if (vals) memcpy(vals, s->S.sysVals.data(), sizeof(double) * s->S.sysVals.size());
+    if (rhs) memcpy(rhs, s->S.sysRhs.data(), sizeof(double) * s->S.sysRhs.size());
+    return XFEMM_OK;
+}
+
+int xfemm_fsolver_get_solution(xfemm_fsolver *s, double *V, double *A)
+{
+    if (!s) return XFEMM_ERR_ARG;
+    if (s->L)
+    {
+        if (V) memcpy(V, s->L->V, sizeof(double) * s->L->n);
+        if (A) memcpy(A, s->L->b, sizeof(double) * s->L->n);
+        return XFEMM_OK;
+    }
+    if (s->Lc)
+    {
+        if (V) memcpy(V, s->Lc->V, sizeof(CComplex) * s->Lc->n);
+        if (A) memcpy(A, s->Lc->b, sizeof(CComplex) * s->Lc->n);
+        return XFEMM_OK;
+    }
+    xb::set_error("no solution available");
+    return XFEMM_ERR_ARG;
+}
+
+int xfemm_fsolver_get_mu(xfemm_fsolver *s, double *mu12)
+{
+    if (!s || !s->S.magdev) { xb::set_error("no device mesh"); return XFEMM_ERR_ARG; }
+    return xfemm_mag_get_mu(s->S.magdev, mu12);
+}
+
+int xfemm_fsolver_get_stats(xfemm_fsolver *s, int *newton_steps, int *iters, double *solve_ms, double *assemble_ms,
+                            double *relres)
+{
+    if (!s) return XFEMM_ERR_ARG;
+    const FSolverStats &st = s->S.stats;
+    if (newton_steps) *newton_steps = st.newton_iters;
+    for (size_t k = 0; k < st.pcg_iters.size() && k < 64; k++)
+    {
+        if (iters) iters[k] = st.pcg_iters[k];
+        if (solve_ms) solve_ms[k] = st.pcg_ms[k];
+        if (assemble_ms && k < st.assemble_ms.size()) assemble_ms[k] = st.assemble_ms[k];
+    }
+    if (relres) *relres = st.final_relres;
+    return XFEMM_OK;
+}
+
+int xfemm_fsolver_set_option(xfemm_fsolver *s, const char *key, double value)
+{
+    if (!s || !key) return XFEMM_ERR_ARG;
+    if (!strcmp(key, "precond")) { s->S.precondOption = (int)value; return XFEMM_OK; }
+    if (!strcmp(key, "max_iter")) { s->S.maxIterOption = (int)value; return XFEMM_OK; }
+    if (!strcmp(key, "keep_system")) { s->S.keepSystem = value != 0; return XFEMM_OK; }
+    xb::set_error("unknown option %s", key);
+    return XFEMM_ERR_ARG;
+}
+
+} // extern "C"

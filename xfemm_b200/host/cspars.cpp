@@ -1,0 +1,48 @@
+// CBigComplexLinProb facade (reference: cfemm/libfemm/cspars.cpp:119-1081).
+// The complex-symmetric device solver is not part of this build yet: the object can be created
+// and filled with vectors, but PBCGSolveMod fails loudly instead of falling back to a CPU solve.
+#include "cspars.h"
+#include <cstdio>
+#include <cstdlib>
+
+CBigComplexLinProb::CBigComplexLinProb()
+    : P(nullptr), U(nullptr), R(nullptr), V(nullptr), Z(nullptr), b(nullptr), uu(nullptr), vv(nullptr), M(nullptr),
+      Mh(nullptr), Ma(nullptr), Ms(nullptr), n(0), bdw(0), bNewton(0), NumNodes(0), Precision(1e-8), Lambda(1.5),
+      precond(0), lastIterations(0), lastSolveMs(0), lastRelRes(0), dev(nullptr)
+{
+}
+
+CBigComplexLinProb::~CBigComplexLinProb()
+{
+    free(P); free(U); free(R); free(V); free(Z); free(b); free(uu); free(vv);
+}
+
+int CBigComplexLinProb::Create(int d, int bw, int nodes)
+{
+    bdw = bw;
+    NumNodes = nodes;
+    n = d;
+    b = (CComplex *)calloc(d, sizeof(CComplex));
+    V = (CComplex *)calloc(d, sizeof(CComplex));
+    P = (CComplex *)calloc(d, sizeof(CComplex));
+    R = (CComplex *)calloc(d, sizeof(CComplex));
+    U = (CComplex *)calloc(d, sizeof(CComplex));
+    Z = (CComplex *)calloc(d, sizeof(CComplex));
+    uu = (CComplex *)calloc(d, sizeof(CComplex));
+    vv = (CComplex *)calloc(d, sizeof(CComplex));
+    return 1;
+}
+
+void CBigComplexLinProb::attachDevice(xfemm_clinprob *d) { dev = d; }
+void CBigComplexLinProb::Put(CComplex, int, int, int) { fprintf(stderr, "xfemm_b200: CBigComplexLinProb::Put is not available in this build\n"); }
+CComplex CBigComplexLinProb::Get(int, int, int) { return CComplex(0); }
+void CBigComplexLinProb::AddTo(CComplex v, int p, int q) { Put(Get(p, q) + v, p, q); }
+void CBigComplexLinProb::SetValue(int, CComplex) {}
+void CBigComplexLinProb::Periodicity(int, int) {}
+void CBigComplexLinProb::AntiPeriodicity(int, int) {}
+void CBigComplexLinProb::Wipe() {}
+int CBigComplexLinProb::PBCGSolveMod(int, bool)
+{
+    fprintf(stderr, "xfemm_b200: the complex-symmetric device solver is not available in this build\n");
+    return 0;
+}

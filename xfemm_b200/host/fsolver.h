@@ -1,0 +1,269 @@
+// Drop-in host-side interface of the fsolver hot path (B200 backend).
+//
+// This header mirrors the PUBLIC face of the reference classes so that the reference's callers
+// (cfemm/fsolver/main.cpp:39-84, mfemm/mexfsolver.cpp:34-135, cfemm/femmcli/LuaMagneticsCommands.cpp:817-843)
+// compile against it unchanged:
+//   class FSolver            — cfemm/fsolver/fsolver.h:50-150 over cfemm/libfemm/feasolver.h:76-209
+//   femm::CNode, femmsolver::CMElement, femm::CM*Prop, femmsolver::CAirGapElement … (data records)
+// Everything numerical behind Static2D/StaticAxisymmetric/Harmonic2D/HarmonicAxisymmetric and
+// CBigLinProb/CBigComplexLinProb runs on the GPU through the C ABI in include/xfemm_b200.h.
+// There is no CPU solve path: without a CUDA device these calls fail loudly.
+#ifndef XFEMM_B200_FSOLVER_H
+#define XFEMM_B200_FSOLVER_H
+
+#include "femmcomplex.h"
+#include "spars.h"
+#include "cspars.h"
+
+#include <string>
+#include <vector>
+
+#ifndef PI
+#define PI 3.141592653589793238462643383
+#endif
+#ifndef DEG
+#define DEG 0.01745329251994329576923690768
+#endif
+#ifndef muo
+#define muo 1.2566370614359173e-6
+#endif
+
+enum LoadMeshErr
+{
+    NOERROR,
+    BADFEMFILE,
+    BADNODEFILE,
+    BADPBCFILE,
+    BADELEMENTFILE,
+    BADEDGEFILE,
+    MISSINGMATPROPS,
+    ELMLABELTOOBIG
+};
+
+namespace femm
+{
+enum LengthUnit { LengthInches = 0, LengthMillimeters = 1, LengthCentimeters = 2, LengthMeters = 3, LengthMils = 4, LengthMicrometers = 5 };
+enum CoordsType { CART = 0, POLAR = 1 };
+enum ProblemType { PLANAR = 0, AXISYMMETRIC = 1 };
+extern const double LengthConvMeters[6];
+
+int PrintWarningMsg(const char *message, ...);
+
+struct CNode
+{
+    double x = 0, y = 0;
+    int BoundaryMarker = -1;
+};
+
+struct CCommonPoint
+{
+    int x = 0, y = 0, t = 0;
+};
+
+struct CQuadPoint
+{
+    int n0, n1, n2, n3;
+    double w0, w1, w2, w3;
+};
+
+struct CMPointProp
+{
+    std::string PointName = "New Point Property";
+    CComplex J, A;
+};
+
+struct CMBoundaryProp
+{
+    std::string BdryName = "New Boundary";
+    int BdryFormat = 0;
+    double InnerAngle = 0, OuterAngle = 0;
+    double A0 = 0, A1 = 0, A2 = 0, phi = 0;
+    double Mu = 0, Sig = 0;
+    CComplex c0, c1;
+};
+
+// Magnetic material incl. the cubic-Hermite H(B) table (reference: cfemm/libfemm/CMaterialProp.h,
+// CMMaterialProp + CMSolverMaterialProp).  Spline set-up stays on the host; evaluation during
+// assembly happens on the device from the uploaded tables.
+struct CMSolverMaterialProp
+{
+    std::string BlockName = "New Material";
+    double mu_x = 1, mu_y = 1;
+    int BHpoints = 0;
+    std::vector<double> Bdata;
+    std::vector<CComplex> Hdata;
+    std::vector<CComplex> slope;
+    int LamType = 0;
+    double LamFill = 1;
+    double H_c = 0, Nrg = 0;
+    CComplex J;
+    double Cduct = 0, Lam_d = 0;
+    double Theta_hn = 0, Theta_hx = 0, Theta_hy = 0;
+    int NStrands = 0;
+    double WireD = 0;
+    double MuMax = 0;
+    double Theta_m = 0;
+    CComplex mu_fdx, mu_fdy;
+
+    void GetSlopes(double omega);                        // CMaterialProp.cpp:127-348
+    void clearSlopes() { slope.clear(); }
+    CComplex LaminatedBH(double w, int i);               // CMaterialProp.cpp:1062-1171
+    CComplex GetH(double B);                             // CMaterialProp.cpp:960-987
+    CComplex GetdHdB(double B);                          // CMaterialProp.cpp:461-486
+    CComplex Get_v(double B);                            // CMaterialProp.cpp:899-904
+    void GetBHProps(double B, CComplex &v, CComplex &dv); // CMaterialProp.cpp:1007-1057
+    void GetBHProps(double B, double &v, double &dv);
+    void IncrementalPermeability(double B, double &mu1, double &mu2);
+    void incrementalPermeability(double B, double w, CComplex &mu1, CComplex &mu2);
+};
+
+struct CMCircuit
+{
+    std::string CircName = "New Circuit";
+    int CircType = 0;
+    CComplex Amps, dVolts;
+    int OrigCirc = 0;
+    CComplex J, dV;
+    int Case = 0;
+};
+
+struct CMBlockLabel
+{
+    double x = 0, y = 0, MaxArea = 0;
+    int InGroup = 0;
+    bool IsExternal = false, IsDefault = false;
+    int BlockType = -1, InCircuit = -1;
+    CComplex ProximityMu;
+    int Turns = 1;
+    bool bIsWound = false;
+    double MagDir = 0;
+    std::string MagDirFctn;
+    int Case = 0;
+    CComplex J, dVolts;
+    double FillFactor = 1;
+    CComplex o, mu;
+};
+} // namespace femm
+
+namespace femmsolver
+{
+struct CMElement
+{
+    int p[3] = {0, 0, 0};
+    int e[3] = {-1, -1, -1};
+    int blk = 0, lbl = 0;
+    CComplex mu1, mu2, v12;
+    double magdir = 0;
+    double Jprev = 0;
+};
+
+struct CAirGapElement
+{
+    std::string BdryName;
+    int BdryFormat = 0;
+    int totalArcElements = 0;
+    double totalArcLength = 0;
+    double ri = 0, ro = 0;
+    double InnerAngle = 0, OuterAngle = 0;
+    double InnerShift = 0, OuterShift = 0;
+    CComplex agc;
+    std::vector<femm::CQuadPoint> quadNode;
+};
+} // namespace femmsolver
+
+struct xfemm_mag; // opaque device problem (include/xfemm_b200.h)
+
+// Per-run metrics the B200 backend records (not in the reference).
+struct FSolverStats
+{
+    int newton_iters = 0;
+    std::vector<int> pcg_iters;      // linear iterations of each (Newton) solve
+    std::vector<double> pcg_ms;      // device-timed
+    std::vector<double> assemble_ms; // device-timed (assembly + boundary conditions)
+    double final_relres = 0;         // true ||b-Ax||/||b|| of the last solve
+    double t_load_mesh = 0, t_renumber = 0, t_pattern = 0, t_upload = 0, t_write = 0;
+};
+
+class FSolver
+{
+public:
+    FSolver();
+    virtual ~FSolver();
+
+    // ---- general problem attributes (feasolver.h:98-120)
+    double FileFormat, Precision, MinAngle, Depth;
+    femm::LengthUnit LengthUnits;
+    femm::CoordsType Coords;
+    femm::ProblemType ProblemType;
+    double extZo, extRo, extRi;
+    std::string comment;
+    int ACSolver;
+    bool DoForceMaxMeshArea, DoSmartMesh, bMultiplyDefinedLabels;
+
+    int BandWidth;
+    std::vector<femmsolver::CMElement> meshele;
+    int NumNodes, NumEls;
+    int NumBlockProps, NumPBCs, NumLineProps, NumPointProps, NumCircProps, NumBlockLabels, NumAirGapElems;
+    std::vector<femm::CCommonPoint> pbclist;
+    std::string PathName;
+    int PrevType;
+    std::string previousSolutionFile;
+
+    std::vector<femm::CMPointProp> nodeproplist;
+    std::vector<femm::CMBoundaryProp> lineproplist;
+    std::vector<femm::CMSolverMaterialProp> blockproplist;
+    std::vector<femm::CMCircuit> circproplist;
+    std::vector<femm::CMBlockLabel> labellist;
+    std::vector<femmsolver::CAirGapElement> agelist;
+
+    // ---- fsolver.h:65-75
+    double Frequency;
+    double Relax;
+    std::vector<femm::CNode> meshnode;
+    int NumCircPropsOrig;
+
+    int (*WarnMessage)(const char *, ...);
+    int (*PrintMessage)(const char *, ...);
+
+    // ---- operations (same names, argument meaning and return conventions as the reference)
+    bool LoadProblemFile();                        // fsolver.cpp:202-348
+    LoadMeshErr LoadMesh(bool deleteFiles = true); // fsolver.cpp:350-718
+    int Cuthill(bool deleteFiles = true);          // cuthill.cpp:94-391
+    int SortElements();                            // cuthill.cpp:40-85
+    int Static2D(CBigLinProb &L);                  // static2d.cpp:53-1033
+    int WriteStatic2D(CBigLinProb &L);             // static2d.cpp:1038-1195
+    int StaticAxisymmetric(CBigLinProb &L);        // staticaxi.cpp:45-794
+    int Harmonic2D(CBigComplexLinProb &L, bool verbose = false);          // harmonic2d.cpp:38-890
+    int WriteHarmonic2D(CBigComplexLinProb &L);                           // harmonic2d.cpp:892-1036
+    int HarmonicAxisymmetric(CBigComplexLinProb &L, bool verbose = false); // harmonicaxi.cpp:34-821
+    void GetFillFactor(int lbl);                   // fsolver.cpp:1083-1194
+    double ElmArea(int i);                         // fsolver.cpp:1196-1211
+    virtual bool runSolver(bool verbose = false);  // fsolver.cpp:1213-1338
+    virtual void CleanUp();
+    static std::string getErrorString(LoadMeshErr err);
+
+    // ---- B200 backend extras
+    FSolverStats stats;
+    std::vector<double> Aprev;
+    // newnum[i] = solver index of mesh-file node i (the Cuthill–McKee permutation), kept for parity checks
+    std::vector<int> cmPermutation;
+    std::vector<int> edgeList;   // .edge node pairs cached by LoadMesh for Cuthill
+    int precondOption;           // XFEMM_PRECOND_* or -1 = backend default
+    int maxIterOption;           // <=0 = backend default
+    xfemm_mag *magdev;           // device mesh of the last solve (kept for queries), owned
+    void releaseDevice();
+    // optional host snapshot of the last assembled + boundary-conditioned system (parity tests)
+    bool keepSystem;
+    std::vector<int> sysRowptr, sysCol;
+    std::vector<double> sysVals, sysRhs;
+
+protected:
+    void SortNodes(const std::vector<int> &newnum); // fsolver.cpp:1341-1353
+    bool parseFem(const std::string &file);
+    int staticSolve(CBigLinProb &L, bool axisymmetric);
+    int harmonicSolve(CBigComplexLinProb &L, bool axisymmetric, bool verbose);
+};
+
+double Power(double x, int n);
+
+#endif

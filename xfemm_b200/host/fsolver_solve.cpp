@@ -1,0 +1,607 @@
+// FSolver: renumbering, problem set-up and the Newton loop of the magnetostatic formulations.
+// Host orchestration only — every O(elements) / O(nnz) arithmetic step runs on the GPU through
+// the C ABI (include/xfemm_b200.h).  Reference behaviour mirrored:
+//   FEASolver::Cuthill/SortElements   cfemm/libfemm/cuthill.cpp:40-391
+//   FSolver::SortNodes                cfemm/fsolver/fsolver.cpp:1341-1353
+//   FSolver::GetFillFactor, ElmArea   cfemm/fsolver/fsolver.cpp:1083-1211
+//   FSolver::runSolver                cfemm/fsolver/fsolver.cpp:1213-1338
+//   FSolver::Static2D                 cfemm/fsolver/static2d.cpp:53-1033
+//   FSolver::StaticAxisymmetric       cfemm/fsolver/staticaxi.cpp:45-794
+#include "fsolver.h"
+#include "../../include/xfemm_b200.h"
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <cstring>
+#include <map>
+
+using namespace femm;
+using namespace femmsolver;
+typedef std::complex<double> cplx;
+
+namespace xb { void age_cell_matrix(double ci, double co, double K, double *MG); }
+
+static double wall() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+void FSolver::releaseDevice()
+{
+    if (magdev) { xfemm_mag_destroy(magdev); magdev = nullptr; }
+}
+
+// ---------------------------------------------------------------------------------------
+// renumbering
+// ---------------------------------------------------------------------------------------
+void FSolver::SortNodes(const std::vector<int> &newnum)
+{
+    // the reference cycles swaps until every node sits at its new index; the result is
+    // "node i moves to position newnum[i]"
+    std::vector<CNode> out(meshnode.size());
+    for (int i = 0; i < NumNodes; i++) out[newnum[i]] = meshnode[i];
+    meshnode.swap(out);
+}
+
+int FSolver::SortElements()
+{
+    std::vector<int> tri(3 * (size_t)NumEls), order(NumEls);
+    for (int k = 0; k < NumEls; k++)
+        for (int j = 0; j < 3; j++) tri[3 * (size_t)k + j] = meshele[k].p[j];
+    if (xfemm_renumber_sort_elements(NumEls, tri.data(), order.data()) != XFEMM_OK) return false;
+    std::vector<CMElement> out(NumEls);
+    for (int k = 0; k < NumEls; k++) out[k] = meshele[order[k]];
+    meshele.swap(out);
+    return true;
+}
+
+int FSolver::Cuthill(bool deleteFiles)
+{
+    std::string edgeFile = PathName + ".edge";
+    if (edgeList.empty())
+    {
+        // LoadMesh normally caches the edge list; fall back to the file like the reference
+        FILE *fp = fopen(edgeFile.c_str(), "rt");
+        if (!fp) { printf("Couldn't open %s", edgeFile.c_str()); return false; }
+        long nl = 0, flag = 0;
+        if (fscanf(fp, "%li", &nl) != 1 || fscanf(fp, "%li", &flag) != 1) { fclose(fp); return false; }
+        edgeList.resize(2 * (size_t)nl);
+        for (long i = 0; i < nl; i++)
+        {
+            long idx, mk;
+            if (fscanf(fp, "%li %i %i %li", &idx, &edgeList[2 * i], &edgeList[2 * i + 1], &mk) != 4) { fclose(fp); return false; }
+        }
+        fclose(fp);
+    }
+    if (deleteFiles) remove(edgeFile.c_str());
+    std::vector<int> newnum(NumNodes);
+    int bw = 0;
+    if (xfemm_renumber_cuthill(NumNodes, (int)(edgeList.size() / 2), edgeList.data(), newnum.data(), &bw) != XFEMM_OK)
+        return false;
+    BandWidth = bw;
+    for (int i = 0; i < NumPBCs; i++)
+    {
+        pbclist[i].x = newnum[pbclist[i].x];
+        pbclist[i].y = newnum[pbclist[i].y];
+    }
+    for (auto &age : agelist)
+        for (auto &q : age.quadNode)
+        {
+            q.n0 = newnum[q.n0]; q.n1 = newnum[q.n1]; q.n2 = newnum[q.n2]; q.n3 = newnum[q.n3];
+        }
+    for (int i = 0; i < NumEls; i++)
+        for (int j = 0; j < 3; j++) meshele[i].p[j] = newnum[meshele[i].p[j]];
+    SortNodes(newnum);
+    cmPermutation = newnum;
+    SortElements();
+    std::vector<int>().swap(edgeList);
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------
+double FSolver::ElmArea(int i)
+{
+    const int *n = meshele[i].p;
+    double b0 = meshnode[n[1]].y - meshnode[n[2]].y;
+    double b1 = meshnode[n[2]].y - meshnode[n[0]].y;
+    double c0 = meshnode[n[2]].x - meshnode[n[1]].x;
+    double c1 = meshnode[n[0]].x - meshnode[n[2]].x;
+    return 0.0001 * (b0 * c1 - b1 * c0) / 2.;
+}
+
+void FSolver::GetFillFactor(int lbl)
+{
+    CMSolverMaterialProp *bp = &blockproplist[labellist[lbl].BlockType];
+    CMBlockLabel *bl = &labellist[lbl];
+    bl->bIsWound = (abs(bl->Turns) > 1) || (bp->LamType > 2);
+    if ((Frequency == 0) || (bp->LamType < 3)) { bl->ProximityMu = 1.; return; }
+
+    double atot = 0;
+    for (int i = 0; i < NumEls; i++)
+        if (meshele[i].lbl == lbl) atot += ElmArea(i);
+    if (atot == 0) return;
+    if (bp->Cduct == 0) { bl->ProximityMu = 1; return; }
+    const cplx I1(0, 1);
+    int wiretype = bp->LamType - 3;
+    double W, d, fill, dd, o, R = 0, awire = 0, c1 = 0, c2 = 0;
+    if (wiretype == 3) // rectangular wire → equivalent foil
+    {
+        W = 2. * PI * Frequency;
+        d = bp->WireD * 0.001;
+        fill = fabs(d * d * ((double)bl->Turns) / atot);
+        dd = d / sqrt(fill);
+        fill = d / dd;
+        o = bp->Cduct * (d / dd) * 1.e6;
+        cplx ufd = muo * std::tanh(std::sqrt(I1 * W * o * muo) * d / 2.) / (std::sqrt(I1 * W * o * muo) * d / 2.);
+        bl->ProximityMu = CComplex((fill * ufd + (1. - fill) * muo) / muo);
+        return;
+    }
+    switch (wiretype)
+    {
+    case 0: R = bp->WireD * 0.0005; awire = PI * R * R * ((double)bp->NStrands) * ((double)bl->Turns); break;
+    case 1: R = bp->WireD * 0.0005 * sqrt((double)bp->NStrands); awire = PI * R * R * ((double)bl->Turns); break;
+    case 2: R = bp->WireD * 0.0005; awire = PI * R * R * ((double)bp->NStrands) * ((double)bl->Turns); break;
+    }
+    fill = fabs(awire / atot);
+    o = bp->Cduct * 1.e6;
+    W = 2. * PI * Frequency * o * muo * R * R / 2.;
+    switch (wiretype)
+    {
+    case 0: case 1: case 2:
+        c1 = 0.7756067409818643 + fill * (0.6873854335408803 + fill * (0.06841584481674128 - 0.07143732702512284 * fill));
+        c2 = 1.5 * fill / c1;
+        break;
+    case 4:
+        c1 = 0.7270741505617485 + 0.8902950067721367 * fill + 0.11894736885885195 * fill * fill - 0.12247276254503957 * fill * fill * fill;
+        c2 = 0.006784920229549677 + 1.8942880489198526 * fill - 1.3631438759519217 * fill * fill + 0.504431701685587 * fill * fill * fill;
+        break;
+    case 5:
+        c1 = 0.7486913529860821 + 0.9042845510838825 * fill + 0.1361040321433224 * fill * fill - 0.10652380745682069 * fill * fill * fill;
+        c2 = 0.006790468527313965 + 1.8945509985370095 * fill - 1.3643501010185972 * fill * fill + 0.5036765577982594 * fill * fill * fill;
+        break;
+    }
+    cplx ufd = c2 * (std::tanh(std::sqrt(c1 * I1 * W)) / std::sqrt(c1 * I1 * W)) + (1. - c2);
+    bl->ProximityMu = CComplex(ufd);
+}
+
+// ---------------------------------------------------------------------------------------
+bool FSolver::runSolver(bool verbose)
+{
+    double t0 = wall();
+    LoadMeshErr err = LoadMesh();
+    if (err != NOERROR) { WarnMessage(getErrorString(err).c_str()); return false; }
+    stats.t_load_mesh = wall() - t0;
+    if (previousSolutionFile.empty())
+    {
+        if (verbose) PrintMessage("renumbering nodes using Cuthill-McKee method\n");
+        t0 = wall();
+        if (!Cuthill()) { WarnMessage("problem renumbering node points\n"); return false; }
+        stats.t_renumber = wall() - t0;
+    }
+    if (verbose)
+    {
+        PrintMessage("solving...\n");
+        std::string st = "Problem Statistics:\n" + std::to_string(NumNodes) + " nodes\n" + std::to_string(NumEls) +
+                         " elements\nPrecision: " + std::to_string(Precision) + "\n";
+        PrintMessage(st.c_str());
+    }
+    if (Frequency == 0)
+    {
+        CBigLinProb L;
+        L.Precision = Precision;
+        if (L.Create(NumNodes, BandWidth) == false) { WarnMessage("couldn't allocate enough space for matrices\n"); return false; }
+        if (ProblemType == PLANAR)
+        {
+            if (Static2D(L) != true) { WarnMessage("Couldn't solve the problem\n"); return false; }
+            if (verbose) PrintMessage("Static 2-D problem solved\n");
+        }
+        else
+        {
+            if (StaticAxisymmetric(L) != true) { WarnMessage("Couldn't solve the problem"); return false; }
+            if (verbose) PrintMessage("Static axisymmetric problem solved\n");
+        }
+        t0 = wall();
+        if (WriteStatic2D(L) == false) { WarnMessage("couldn't write results to disk\n"); return false; }
+        stats.t_write = wall() - t0;
+        if (verbose) PrintMessage("results written to disk\n");
+    }
+    else
+    {
+        CBigComplexLinProb L;
+        L.Precision = Precision;
+        if (!L.Create(NumNodes + NumCircProps, BandWidth, NumNodes)) { WarnMessage("couldn't allocate enough space for matrices\n"); return false; }
+        if (ProblemType == PLANAR)
+        {
+            if (!Harmonic2D(L, verbose)) { WarnMessage("Couldn't solve the problem\n"); return false; }
+            if (verbose) PrintMessage("Harmonic 2-D problem solved\n");
+        }
+        else
+        {
+            if (!HarmonicAxisymmetric(L, verbose)) { WarnMessage("Couldn't solve the problem\n"); return false; }
+            if (verbose) PrintMessage("Harmonic axisymmetric problem solved\n");
+        }
+        t0 = wall();
+        if (!WriteHarmonic2D(L)) { WarnMessage("couldn't write results to disk\n"); return false; }
+        stats.t_write = wall() - t0;
+        if (verbose) PrintMessage("results written to disk.\n");
+    }
+    return true;
+}
+
+int FSolver::Static2D(CBigLinProb &L) { return staticSolve(L, false); }
+int FSolver::StaticAxisymmetric(CBigLinProb &L) { return staticSolve(L, true); }
+
+// ---------------------------------------------------------------------------------------
+// shared set-up pieces
+// ---------------------------------------------------------------------------------------
+namespace
+{
+// Flattens the air-gap elements into ring cells: 10 nodes + 10 weights per cell and one 10x10
+// matrix per AGE (static2d.cpp:192-343).
+void flatten_age(const std::vector<CAirGapElement> &agelist, std::vector<int> &nodes, std::vector<double> &w,
+                 std::vector<int> &mid, std::vector<double> &mats, bool harmonicWeights)
+{
+    nodes.clear(); w.clear(); mid.clear(); mats.clear();
+    for (size_t a = 0; a < agelist.size(); a++)
+    {
+        const CAirGapElement &g = agelist[a];
+        const int N = g.totalArcElements;
+        double dt = (PI / 180.) * (g.totalArcLength / N);
+        double K = 2. * (g.ro - g.ri) / (dt * (g.ro + g.ri));
+        double ci = g.InnerShift, co = g.OuterShift;
+        if (ci > co) { ci = ci - co; co = 0; }
+        else { ci = 1 - co + ci; co = 1; }
+        mats.resize(mats.size() + 100);
+        xb::age_cell_matrix(ci, co, K, &mats[mats.size() - 100]);
+        for (int k = 0; k < N; k++)
+        {
+            int nn[10];
+            double ww[10];
+            const CQuadPoint &qm = g.quadNode[(k - 1) < 0 ? N - 1 : k - 1];
+            const CQuadPoint &q0 = g.quadNode[k];
+            const CQuadPoint &q1 = g.quadNode[k + 1];
+            const CQuadPoint &q2 = g.quadNode[(k + 2) > N ? 1 : k + 2];
+            nn[0] = qm.n0; ww[0] = qm.w0;
+            nn[1] = q0.n0; ww[1] = q0.w0;
+            nn[2] = q0.n1; ww[2] = q0.w1;
+            nn[3] = q1.n1; ww[3] = q1.w1;
+            nn[4] = q2.n1; ww[4] = q2.w1;
+            nn[5] = qm.n2; ww[5] = qm.w2;
+            nn[6] = q0.n2; ww[6] = q0.w2;
+            nn[7] = q0.n3; ww[7] = q0.w3;
+            nn[8] = q1.n3; ww[8] = q1.w3;
+            nn[9] = q2.n3; ww[9] = q2.w3;
+            if (g.BdryFormat == 1)
+            {
+                if (k == 0) { ww[0] = -ww[0]; ww[5] = -ww[5]; }
+                // static: last cell flips the far end (static2d.cpp:338); the harmonic code tests
+                // k==totalArcElements, which never holds inside the loop (harmonic2d.cpp:373)
+                if (!harmonicWeights && (k + 1) == N) { ww[4] = -ww[4]; ww[9] = -ww[9]; }
+            }
+            nodes.insert(nodes.end(), nn, nn + 10);
+            w.insert(w.end(), ww, ww + 10);
+            mid.push_back((int)a);
+        }
+    }
+}
+} // namespace
+
+// ---------------------------------------------------------------------------------------
+// magnetostatics
+// ---------------------------------------------------------------------------------------
+int FSolver::staticSolve(CBigLinProb &L, bool axi)
+{
+    const double c = PI * 4.e-05;
+    static const double units[] = {2.54, 0.1, 1., 100., 0.00254, 1.e-04};
+    stats = FSolverStats();
+    releaseDevice();
+    if (xfemm_device_count() <= 0)
+    {
+        WarnMessage("xfemm_b200: no CUDA device available (this backend has no CPU solve path)\n");
+        return false;
+    }
+    if (axi)
+    {
+        WarnMessage("xfemm_b200: axisymmetric magnetostatics is not available in this build\n");
+        return false;
+    }
+    for (int i = 0; i < NumBlockLabels; i++) GetFillFactor(i);
+    for (int i = 0; i < NumBlockLabels; i++)
+        if (!labellist[i].MagDirFctn.empty())
+        {
+            // the reference evaluates the expression per element with its embedded Lua
+            // interpreter (static2d.cpp:513-583), which is outside the accelerated path
+            WarnMessage("xfemm_b200: Lua magnetization direction functions are not supported\n");
+            return -7;
+        }
+
+    // ---- circuits (static2d.cpp:84-167): area, conductance and source integrals per circuit
+    if (NumCircProps > 0)
+    {
+        std::vector<double> I1(NumCircProps, 0.), I2(NumCircProps, 0.), I3(NumCircProps, 0.);
+        for (int i = 0; i < NumEls; i++)
+        {
+            const CMElement &El = meshele[i];
+            if (El.lbl < 0) continue;
+            const int ic = labellist[El.lbl].InCircuit;
+            if (ic == -1) continue;
+            const int *n = El.p;
+            double p0 = meshnode[n[1]].y - meshnode[n[2]].y, p1 = meshnode[n[2]].y - meshnode[n[0]].y;
+            double q0 = meshnode[n[2]].x - meshnode[n[1]].x, q1 = meshnode[n[0]].x - meshnode[n[2]].x;
+            double a = (p0 * q1 - p1 * q0) / 2.;
+            double Cduct = blockproplist[El.blk].Cduct;
+            if (labellist[El.lbl].bIsWound) Cduct = 0;
+            I1[ic] += a;
+            I2[ic] += a * Cduct;
+            I3[ic] += blockproplist[El.blk].J.re * a * 100.;
+        }
+        for (int i = 0; i < NumCircProps; i++)
+        {
+            CMCircuit &cp = circproplist[i];
+            if (cp.CircType == 0)
+            {
+                if (I2[i] == 0)
+                {
+                    cp.Case = 1;
+                    cp.J = (I1[i] == 0.) ? 0. : 0.01 * (cp.Amps.re - I3[i]) / I1[i];
+                }
+                else
+                {
+                    cp.Case = 0;
+                    cp.dV = -0.01 * (cp.Amps.re - I3[i]) / I2[i];
+                }
+            }
+            else
+            {
+                cp.Case = 0;
+                cp.dV = cp.dVolts.re;
+            }
+        }
+    }
+
+    // ---- per-label table and flat B-H tables
+    std::vector<xfemm_mag_label> labels(NumBlockLabels);
+    std::vector<double> bhB, bhH, bhS;
+    std::vector<int> bhOffset(NumBlockProps, -1);
+    for (int k = 0; k < NumBlockProps; k++)
+    {
+        const CMSolverMaterialProp &bp = blockproplist[k];
+        if (bp.BHpoints <= 0) continue;
+        bhOffset[k] = (int)bhB.size();
+        for (int i = 0; i < bp.BHpoints; i++)
+        {
+            bhB.push_back(bp.Bdata[i]);
+            bhH.push_back(bp.Hdata[i].re);
+            bhS.push_back(bp.slope[i].re);
+        }
+    }
+    bool anyNonlinearLabel = false;
+    std::vector<char> labelNonlinear(NumBlockLabels, 0);
+    for (int l = 0; l < NumBlockLabels; l++)
+    {
+        xfemm_mag_label &T = labels[l];
+        memset(&T, 0, sizeof T);
+        const CMBlockLabel &bl = labellist[l];
+        T.bh_offset = -1;
+        T.circuit = -1;
+        T.mu1 = T.mu2 = 1;
+        if (bl.BlockType < 0 || bl.BlockType >= NumBlockProps) continue;
+        const CMSolverMaterialProp &bp = blockproplist[bl.BlockType];
+        // linear permeabilities of the first pass (static2d.cpp:603-631)
+        double t = bp.LamFill, mu;
+        T.mu1 = -1; T.mu2 = -1;
+        if (bp.LamType == 0) { T.mu1 = bp.mu_x * t + (1. - t); T.mu2 = bp.mu_y * t + (1. - t); }
+        if (bp.LamType == 1) { mu = bp.mu_x; T.mu1 = mu * t + (1. - t); T.mu2 = mu / (t + mu * (1. - t)); }
+        if (bp.LamType == 2) { mu = bp.mu_y; T.mu2 = mu * t + (1. - t); T.mu1 = mu / (t + mu * (1. - t)); }
+        if (bp.LamType > 2) { T.mu1 = 1; T.mu2 = 1; }
+        // source current density incl. the circuit contribution (static2d.cpp:483-504)
+        double tc = 0;
+        if (bl.InCircuit >= 0)
+        {
+            const CMCircuit &cp = circproplist[bl.InCircuit];
+            if (cp.Case == 1) tc = cp.J.Re();
+            if (cp.Case == 0) tc = -cp.dV.Re() * bp.Cduct;
+        }
+        T.Jsrc = bp.J.re + tc;
+        T.H_c = bp.H_c;
+        T.magdir = bl.MagDir;
+        T.lamfill = bp.LamFill;
+        T.lamtype = bp.LamType;
+        T.bh_points = bp.BHpoints;
+        T.bh_offset = bhOffset[bl.BlockType];
+        T.is_external = bl.IsExternal ? 1 : 0;
+        T.sigma = bp.Cduct;
+        if (bp.BHpoints != 0) { labelNonlinear[l] = 1; anyNonlinearLabel = true; }
+    }
+    // LinearFlag turns false as soon as one element sits in a B-H material (static2d.cpp:633-639)
+    bool LinearFlag = true;
+    if (anyNonlinearLabel)
+        for (int i = 0; i < NumEls && LinearFlag; i++)
+            if (labelNonlinear[meshele[i].lbl]) LinearFlag = false;
+
+    // ---- element table, mixed-BC edges, Dirichlet list, point sources
+    std::vector<int> tri(4 * (size_t)NumEls);
+    std::vector<int> mixedES;
+    std::vector<double> mixedC;
+    std::vector<int> dirNodes;
+    std::vector<double> dirFirst, dirLast;
+    std::vector<int> dirSlot(NumNodes, -1);
+    auto setValue = [&](int node, double x) {
+        int &s = dirSlot[node];
+        if (s < 0) { s = (int)dirNodes.size(); dirNodes.push_back(node); dirFirst.push_back(x); dirLast.push_back(x); }
+        else dirLast[s] = x;
+    };
+    std::vector<int> psNode;
+    std::vector<double> psVal;
+    for (int i = 0; i < NumNodes; i++)
+        if (meshnode[i].BoundaryMarker >= 0)
+        {
+            psNode.push_back(i);
+            psVal.push_back(0.01 * nodeproplist[meshnode[i].BoundaryMarker].J.re);
+        }
+    // fixed potentials at points (static2d.cpp:827-838) come first, then along segments
+    for (int i = 0; i < NumNodes; i++)
+        if (meshnode[i].BoundaryMarker >= 0)
+        {
+            const CMPointProp &pp = nodeproplist[meshnode[i].BoundaryMarker];
+            if ((pp.J.re == 0) && (pp.J.im == 0)) setValue(i, pp.A.re / c);
+        }
+    for (int i = 0; i < NumEls; i++)
+    {
+        const CMElement &El = meshele[i];
+        int *t4 = &tri[4 * (size_t)i];
+        t4[0] = El.p[0]; t4[1] = El.p[1]; t4[2] = El.p[2]; t4[3] = El.lbl;
+        for (int j = 0; j < 3; j++)
+        {
+            if (El.e[j] < 0) continue;
+            const CMBoundaryProp &bp = lineproplist[El.e[j]];
+            const int k = (j + 1) % 3;
+            if (bp.BdryFormat == 2)
+            {
+                mixedES.push_back(i); mixedES.push_back(j);
+                mixedC.push_back(bp.c0.re); mixedC.push_back(bp.c1.re);
+            }
+            if (bp.BdryFormat == 0)
+            {
+                // static2d.cpp:854-921
+                for (int node : {El.p[j], El.p[k]})
+                {
+                    double x = meshnode[node].x, y = meshnode[node].y, a;
+                    if (Coords == CART)
+                    {
+                        x /= units[LengthUnits];
+                        y /= units[LengthUnits];
+                        a = bp.A0 + x * bp.A1 + y * bp.A2;
+                    }
+                    else
+                    {
+                        double r = sqrt(x * x + y * y), th;
+                        if ((x == 0) && (y == 0)) th = 0; else th = atan2(y, x) / DEG;
+                        r /= units[LengthUnits];
+                        a = bp.A0 + r * bp.A1 + th * bp.A2;
+                    }
+                    a *= cos(bp.phi * DEG);
+                    setValue(node, a / c);
+                }
+            }
+        }
+    }
+    std::vector<int> ageNodes, ageMid;
+    std::vector<double> ageW, ageMats;
+    flatten_age(agelist, ageNodes, ageW, ageMid, ageMats, false);
+    std::vector<int> pbcI(NumPBCs), pbcJ(NumPBCs), pbcT(NumPBCs);
+    for (int k = 0; k < NumPBCs; k++) { pbcI[k] = pbclist[k].x; pbcJ[k] = pbclist[k].y; pbcT[k] = pbclist[k].t; }
+
+    // ---- sparsity pattern → device problem
+    double t0 = wall();
+    int *rowptr = nullptr, *colidx = nullptr;
+    if (xfemm_pattern_build(NumNodes, NumEls, tri.data(), 4, (int)ageMid.size(), ageNodes.data(), 0, nullptr, nullptr,
+                            NumPBCs, pbcI.data(), pbcJ.data(), &rowptr, &colidx) != XFEMM_OK)
+    {
+        WarnMessage(xfemm_last_error());
+        return false;
+    }
+    stats.t_pattern = wall() - t0;
+    t0 = wall();
+    xfemm_linprob *lin = nullptr;
+    int rc = xfemm_linprob_create(NumNodes, rowptr, colidx, &lin);
+    if (rc == XFEMM_OK) L.attachDevice(lin, rowptr, colidx);
+    if (rc == XFEMM_OK && keepSystem)
+    {
+        sysRowptr.assign(rowptr, rowptr + NumNodes + 1);
+        sysCol.assign(colidx, colidx + rowptr[NumNodes]);
+    }
+    xfemm_free(rowptr);
+    xfemm_free(colidx);
+    if (rc != XFEMM_OK) { WarnMessage(xfemm_last_error()); return false; }
+
+    std::vector<double> xy(2 * (size_t)NumNodes);
+    for (int i = 0; i < NumNodes; i++) { xy[2 * (size_t)i] = meshnode[i].x; xy[2 * (size_t)i + 1] = meshnode[i].y; }
+    xfemm_mag_desc D;
+    memset(&D, 0, sizeof D);
+    D.axisymmetric = axi ? 1 : 0;
+    D.n_nodes = NumNodes; D.n_elems = NumEls;
+    D.xy = xy.data(); D.tri = tri.data();
+    D.n_labels = NumBlockLabels; D.labels = labels.data();
+    D.n_bh = (int)bhB.size(); D.bh_B = bhB.data(); D.bh_H = bhH.data(); D.bh_slope = bhS.data();
+    D.n_mixed = (int)(mixedES.size() / 2); D.mixed_elem_side = mixedES.data(); D.mixed_c0c1 = mixedC.data();
+    D.n_age_cells = (int)ageMid.size(); D.age_nodes = ageNodes.data(); D.age_weights = ageW.data();
+    D.age_matrix_id = ageMid.data(); D.n_age_matrices = (int)agelist.size(); D.age_matrices = ageMats.data();
+    D.n_point_src = (int)psNode.size(); D.point_src_node = psNode.data(); D.point_src_val = psVal.data();
+    D.ext_zo = extZo * units[LengthUnits]; D.ext_ro = extRo * units[LengthUnits]; D.ext_ri = extRi * units[LengthUnits];
+    D.r_eps = 1.e-6 * units[LengthUnits];
+    if (xfemm_mag_create(&D, lin, &magdev) != XFEMM_OK) { WarnMessage(xfemm_last_error()); return false; }
+    stats.t_upload = wall() - t0;
+
+    const int precond = precondOption >= 0 ? precondOption : L.precond;
+    int Iter = 0;
+    double res = 0, lastres = 0;
+    do
+    {
+        PrintMessage("Matrix Construction\n");
+        double ms_asm = 0;
+        if (xfemm_mag_assemble_static(magdev, Iter, &ms_asm) != XFEMM_OK) { WarnMessage(xfemm_last_error()); return false; }
+        double tb = wall();
+        if (xfemm_linprob_dirichlet(lin, (int)dirNodes.size(), dirNodes.data(), dirFirst.data(), dirLast.data(), L.bdw) != XFEMM_OK ||
+            xfemm_linprob_periodic(lin, NumPBCs, pbcI.data(), pbcJ.data(), pbcT.data()) != XFEMM_OK)
+        {
+            WarnMessage(xfemm_last_error());
+            return false;
+        }
+        stats.assemble_ms.push_back(ms_asm + (wall() - tb) * 1e3);
+        if (keepSystem)
+        {
+            sysVals.resize(sysCol.size());
+            sysRhs.resize(NumNodes);
+            xfemm_linprob_get_values(lin, sysVals.data());
+            xfemm_linprob_get_rhs(lin, sysRhs.data());
+        }
+        xfemm_linprob_save_solution(lin); // V_old = V
+        PrintMessage("Conjugate Gradient Solver\n");
+        xfemm_solve_info info;
+        rc = xfemm_linprob_pcg(lin, L.Precision, Iter, precond, maxIterOption, &info);
+        stats.pcg_iters.push_back(info.iterations);
+        stats.pcg_ms.push_back(info.solve_ms);
+        stats.final_relres = info.relres;
+        L.lastIterations = info.iterations; L.lastSolveMs = info.solve_ms; L.lastRelRes = info.relres;
+        if (rc != XFEMM_OK) { WarnMessage(xfemm_last_error()); return false; }
+
+        if (LinearFlag == false)
+        {
+            double x = 0, y = 0;
+            xfemm_linprob_newton_norms(lin, &x, &y);
+            if (y == 0) LinearFlag = true;
+            else { lastres = res; res = sqrt(x / y); }
+            if (Iter > 5)
+            {
+                if ((res > lastres) && (Relax > 0.125)) Relax /= 2.;
+                else Relax += 0.1 * (1. - Relax);
+                xfemm_linprob_relax(lin, Relax);
+            }
+            char outstr[256];
+            snprintf(outstr, sizeof outstr, "Newton Iteration(%i) Relax=%.4g\n", Iter, Relax);
+            PrintMessage(outstr);
+        }
+        if ((res < 100. * Precision) && (Iter > 0)) LinearFlag = true;
+        Iter++;
+    } while (LinearFlag == false);
+    stats.newton_iters = Iter;
+
+    // results back to the caller's arrays: L.V internal units, L.b = A (static2d.cpp:1018-1021)
+    if (xfemm_linprob_get_solution(lin, L.V) != XFEMM_OK || xfemm_mag_solution_to_A(magdev, L.b) != XFEMM_OK)
+    {
+        WarnMessage(xfemm_last_error());
+        return false;
+    }
+    // bookkeeping the reference keeps per element
+    for (int i = 0; i < NumEls; i++) meshele[i].Jprev += Iter * labels[meshele[i].lbl].Jsrc;
+    return true;
+}
+
+int FSolver::Harmonic2D(CBigComplexLinProb &L, bool verbose) { return harmonicSolve(L, false, verbose); }
+int FSolver::HarmonicAxisymmetric(CBigComplexLinProb &L, bool verbose) { return harmonicSolve(L, true, verbose); }
+
+int FSolver::harmonicSolve(CBigComplexLinProb &, bool, bool)
+{
+    WarnMessage("xfemm_b200: time-harmonic formulations are not available in this build\n");
+    return false;
+}

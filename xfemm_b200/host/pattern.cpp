@@ -1,0 +1,282 @@
+// Sparsity pattern and renumbering (host side, integer work, bit-exact with the reference).
+//
+//  xfemm_pattern_build      — structure that CBigLinProb grows implicitly through Put()
+//                             (cfemm/libfemm/spars.cpp:105-142) while Static2D assembles
+//                             (static2d.cpp:345-347, 807-812) and applies Periodicity
+//                             (spars.cpp:421-474), produced here in one pass as full CSR.
+//  xfemm_renumber_cuthill   — cfemm/libfemm/cuthill.cpp:94-350 (Cuthill–McKee, not reversed)
+//  xfemm_renumber_sort_elements — cfemm/libfemm/cuthill.cpp:40-85 (the incomplete comb sort)
+#include "../../include/xfemm_b200.h"
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <unordered_map>
+#include <vector>
+
+namespace xb { void set_error(const char *fmt, ...); }
+
+extern "C" {
+
+int xfemm_pattern_build(int n_rows, int n_elems, const int *tri, int tri_stride,
+                        int n_age_cells, const int *age_nodes,
+                        int n_extra, const int *extra_i, const int *extra_j,
+                        int n_pbc, const int *pbc_i, const int *pbc_j,
+                        int **rowptr_out, int **colidx_out)
+{
+    if (n_rows <= 0 || !rowptr_out || !colidx_out || (n_elems > 0 && (!tri || tri_stride < 3)))
+    {
+        xb::set_error("xfemm_pattern_build: invalid arguments");
+        return XFEMM_ERR_ARG;
+    }
+    const int n = n_rows;
+    // ---- pass 1: element graph as CSR with duplicates, then sort+unique per row
+    std::vector<int> cnt(n + 1, 0);
+    for (int e = 0; e < n_elems; e++)
+    {
+        const int *t = tri + (size_t)e * tri_stride;
+        for (int j = 0; j < 3; j++)
+        {
+            if (t[j] < 0 || t[j] >= n) { xb::set_error("element %d: node index out of range", e); return XFEMM_ERR_ARG; }
+            cnt[t[j] + 1] += 2;
+        }
+    }
+    for (int i = 0; i < n; i++) cnt[i + 1] += 1; // diagonal
+    for (int i = 0; i < n; i++) cnt[i + 1] += cnt[i];
+    std::vector<int> adj((size_t)cnt[n]);
+    {
+        std::vector<int> pos(cnt.begin(), cnt.end() - 1);
+        for (int i = 0; i < n; i++) adj[pos[i]++] = i;
+        for (int e = 0; e < n_elems; e++)
+        {
+            const int *t = tri + (size_t)e * tri_stride;
+            const int a = t[0], b = t[1], c = t[2];
+            adj[pos[a]++] = b; adj[pos[a]++] = c;
+            adj[pos[b]++] = a; adj[pos[b]++] = c;
+            adj[pos[c]++] = a; adj[pos[c]++] = b;
+        }
+    }
+    std::vector<int> rp(n + 1, 0);
+    {
+        size_t w = 0;
+        for (int i = 0; i < n; i++)
+        {
+            int *b = adj.data() + cnt[i], *e = adj.data() + cnt[i + 1];
+            std::sort(b, e);
+            e = std::unique(b, e);
+            size_t len = e - b;
+            if (adj.data() + w != b) memmove(adj.data() + w, b, len * sizeof(int));
+            w += len;
+            rp[i + 1] = (int)w;
+        }
+        adj.resize(w);
+    }
+    // ---- extras: AGE blocks, explicit couplings, periodic fill (symbolic replay in list order)
+    std::unordered_map<int, std::vector<int>> extra; // row -> additional columns (unsorted, may repeat)
+    auto has = [&](int r, int c) -> bool {
+        const int *b = adj.data() + rp[r], *e = adj.data() + rp[r + 1];
+        if (std::binary_search(b, e, c)) return true;
+        auto f = extra.find(r);
+        if (f == extra.end()) return false;
+        return std::find(f->second.begin(), f->second.end(), c) != f->second.end();
+    };
+    auto add = [&](int r, int c) {
+        if (!has(r, c)) extra[r].push_back(c);
+        if (r != c && !has(c, r)) extra[c].push_back(r);
+    };
+    for (int k = 0; k < n_age_cells; k++)
+    {
+        const int *nn = age_nodes + (size_t)k * 10;
+        for (int a = 0; a < 10; a++)
+        {
+            if (nn[a] < 0 || nn[a] >= n) { xb::set_error("AGE cell %d: node out of range", k); return XFEMM_ERR_ARG; }
+            for (int b = a; b < 10; b++) add(nn[a], nn[b]);
+        }
+    }
+    for (int k = 0; k < n_extra; k++)
+    {
+        if (extra_i[k] < 0 || extra_i[k] >= n || extra_j[k] < 0 || extra_j[k] >= n) { xb::set_error("extra coupling %d out of range", k); return XFEMM_ERR_ARG; }
+        add(extra_i[k], extra_j[k]);
+    }
+    std::vector<int> nb;
+    for (int k = 0; k < n_pbc; k++)
+    {
+        const int i = pbc_i[k], j = pbc_j[k];
+        if (i < 0 || i >= n || j < 0 || j >= n) { xb::set_error("periodic pair %d out of range", k); return XFEMM_ERR_ARG; }
+        nb.clear();
+        for (int r : {i, j})
+        {
+            nb.insert(nb.end(), adj.begin() + rp[r], adj.begin() + rp[r + 1]);
+            auto f = extra.find(r);
+            if (f != extra.end()) nb.insert(nb.end(), f->second.begin(), f->second.end());
+        }
+        std::sort(nb.begin(), nb.end());
+        nb.erase(std::unique(nb.begin(), nb.end()), nb.end());
+        for (int kk : nb)
+        {
+            if (kk == i || kk == j) continue;
+            add(kk, i);
+            add(kk, j);
+        }
+    }
+    // ---- merge
+    size_t total = adj.size();
+    for (auto &kv : extra) total += kv.second.size();
+    int *rowptr = (int *)malloc(sizeof(int) * (size_t)(n + 1));
+    int *col = (int *)malloc(sizeof(int) * std::max<size_t>(total, 1));
+    if (!rowptr || !col) { free(rowptr); free(col); xb::set_error("out of memory"); return XFEMM_ERR_ARG; }
+    size_t w = 0;
+    rowptr[0] = 0;
+    for (int i = 0; i < n; i++)
+    {
+        const int *b = adj.data() + rp[i], *e = adj.data() + rp[i + 1];
+        auto f = extra.empty() ? extra.end() : extra.find(i);
+        if (f == extra.end())
+        {
+            memcpy(col + w, b, (e - b) * sizeof(int));
+            w += e - b;
+        }
+        else
+        {
+            std::vector<int> &x = f->second;
+            std::sort(x.begin(), x.end());
+            x.erase(std::unique(x.begin(), x.end()), x.end());
+            int *o = std::set_union(b, e, x.data(), x.data() + x.size(), col + w);
+            w = o - col;
+        }
+        rowptr[i + 1] = (int)w;
+    }
+    *rowptr_out = rowptr;
+    *colidx_out = col;
+    return XFEMM_OK;
+}
+
+// Cuthill–McKee exactly as the reference numbers nodes: adjacency from the .edge list in file
+// order, each list stably ordered by neighbour degree (the reference's bubble sort with a strict
+// '<' is a stable sort), start at the first node of minimum degree with the "stop scanning once
+// a degree-2 node has been seen" shortcut, FIFO numbering, restart on disconnected components.
+int xfemm_renumber_cuthill(int n_nodes, int n_edges, const int *edges, int *newnum, int *bandwidth_out)
+{
+    if (n_nodes <= 0 || n_edges < 0 || !newnum || (n_edges > 0 && !edges))
+    {
+        xb::set_error("xfemm_renumber_cuthill: invalid arguments");
+        return XFEMM_ERR_ARG;
+    }
+    const int n = n_nodes;
+    std::vector<int> deg(n, 0);
+    for (int e = 0; e < n_edges; e++)
+    {
+        int a = edges[2 * e], b = edges[2 * e + 1];
+        if (a < 0 || a >= n || b < 0 || b >= n) { xb::set_error("edge %d out of range", e); return XFEMM_ERR_ARG; }
+        deg[a]++; deg[b]++;
+    }
+    std::vector<int> ptr(n + 1, 0);
+    for (int i = 0; i < n; i++) ptr[i + 1] = ptr[i] + deg[i];
+    std::vector<int> con((size_t)ptr[n]);
+    {
+        std::vector<int> pos(ptr.begin(), ptr.end() - 1);
+        for (int e = 0; e < n_edges; e++)
+        {
+            int a = edges[2 * e], b = edges[2 * e + 1];
+            con[pos[a]++] = b;
+            con[pos[b]++] = a;
+        }
+    }
+    for (int i = 0; i < n; i++)
+        std::stable_sort(con.begin() + ptr[i], con.begin() + ptr[i + 1], [&](int a, int b) { return deg[a] < deg[b]; });
+
+    // start node (cuthill.cpp:233-245): the scan stops right after the first index >= 1 at which
+    // the running minimum equals 2.
+    int start = 0;
+    {
+        int best = deg[0];
+        for (int i = 1; i < n; i++)
+        {
+            if (deg[i] < best) { best = deg[i]; start = i; }
+            if (best == 2) break;
+        }
+    }
+    for (int i = 0; i < n; i++) newnum[i] = -1;
+    std::vector<int> queue(n, -1);
+    int count = 1, head = 0; // head = position in `queue` of the node being expanded
+    newnum[start] = 0;
+    queue[0] = start;
+    int cur = start;
+    if (n > 1)
+    {
+        do
+        {
+            for (int s = ptr[cur]; s < ptr[cur + 1]; s++)
+            {
+                int nbn = con[s];
+                if (newnum[nbn] < 0) { newnum[nbn] = count; queue[count] = nbn; count++; }
+            }
+            head = newnum[cur] + 1;
+            if (head < n && queue[head] < 0)
+            {
+                // component exhausted (cuthill.cpp:269-301): first unvisited node, then the
+                // unvisited node of smallest degree (strict '<'), with the same j==2 shortcut
+                int pick = -1, best = 0;
+                for (int i = 0; i < n; i++)
+                    if (newnum[i] < 0) { best = deg[i]; pick = i; break; }
+                for (int i = 0; i < n; i++)
+                {
+                    if (newnum[i] < 0 && deg[i] < best) { best = deg[i]; pick = i; }
+                    if (best == 2) break;
+                }
+                if (pick < 0) break;
+                newnum[pick] = count;
+                queue[count] = pick;
+                count++;
+                cur = pick;
+            }
+            else if (head < n)
+                cur = queue[head];
+        } while (count < n);
+    }
+    if (bandwidth_out)
+    {
+        int wide = 0;
+        for (int i = 0; i < n; i++)
+            for (int s = ptr[i]; s < ptr[i + 1]; s++)
+                wide = std::max(wide, std::abs(newnum[i] - newnum[con[s]]));
+        *bandwidth_out = wide + 1;
+    }
+    return XFEMM_OK;
+}
+
+// The reference's element "sort" (cuthill.cpp:40-85) is a comb sort whose loop also ends after
+// the first pass without a swap, so the result is only partially ordered; the exact sequence of
+// swaps is replayed here on (key, original index) pairs.
+int xfemm_renumber_sort_elements(int n_elems, const int *tri, int *order_out)
+{
+    if (n_elems < 0 || (n_elems > 0 && (!tri || !order_out))) { xb::set_error("invalid arguments"); return XFEMM_ERR_ARG; }
+    std::vector<int> key(n_elems);
+    for (int k = 0; k < n_elems; k++)
+    {
+        key[k] = tri[3 * (size_t)k] + tri[3 * (size_t)k + 1] + tri[3 * (size_t)k + 2];
+        order_out[k] = k;
+    }
+    int gap = n_elems;
+    bool swapped;
+    do
+    {
+        if (gap > 1)
+        {
+            gap = (int)(((long long)gap * 10) / 13);
+            if (gap == 10 || gap == 9) gap = 11;
+        }
+        swapped = false;
+        for (int j = 0; j + gap < n_elems; j++)
+        {
+            if (key[j] > key[j + gap])
+            {
+                std::swap(key[j], key[j + gap]);
+                std::swap(order_out[j], order_out[j + gap]);
+                swapped = true;
+            }
+        }
+    } while (gap > 1 && swapped);
+    return XFEMM_OK;
+}
+
+} // extern "C"
