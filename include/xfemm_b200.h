@@ -49,6 +49,10 @@ int xfemm_cuda_init(int device);        /* cudaSetDevice + context warm-up; XFEM
 int xfemm_device_count(void);
 const char *xfemm_last_error(void);     /* thread-local message of the last failing call */
 const char *xfemm_version(void);
+/* accounting for benchmarks: bytes copied host→device / device→host by this library since the
+ * last reset, and the number of kernels it has launched */
+void xfemm_transfer_bytes(long long *h2d, long long *d2h, int reset);
+long long xfemm_launch_count(void);
 
 /* ------------------------------------------------------------------ solve statistics */
 typedef struct xfemm_solve_info
@@ -103,7 +107,14 @@ int xfemm_pattern_build(int n_rows /* nodes + appended circuit unknowns */,
                         int n_age_cells, const int *age_nodes /* n_age_cells*10 */,
                         int n_extra, const int *extra_i, const int *extra_j /* extra symmetric couplings */,
                         int n_pbc, const int *pbc_i, const int *pbc_j,
-                        int **rowptr_out, int **colidx_out);
+                        int **rowptr_out, int **colidx_out,
+                        unsigned char **fill_out /* optional: 1 = slot exists only through the periodic replay */);
+/* The reference creates periodic fill only where a value is non-zero at that moment
+ * (spars.cpp:442: if v1!=0 || v2!=0), which the structural replay cannot know.  Hand the fill
+ * flags to the problem and, after the boundary conditions ran, ask which slots the reference's
+ * linked lists would contain: exists[s] = !fill[s] || written by the periodic kernel. */
+int xfemm_linprob_set_fill_mask(xfemm_linprob *p, const unsigned char *fill);
+int xfemm_linprob_get_exists_mask(xfemm_linprob *p, unsigned char *exists);
 void xfemm_free(void *ptr);
 
 /* ------------------------------------------------------------------ renumbering (host, integer, bit-exact)
@@ -200,10 +211,14 @@ int xfemm_fsolver_open(const char *basename, int verbose, xfemm_fsolver **out); 
 int xfemm_fsolver_load_mesh(xfemm_fsolver *s, int delete_files);                /* LoadMesh        */
 int xfemm_fsolver_renumber(xfemm_fsolver *s, int delete_files);                 /* Cuthill         */
 int xfemm_fsolver_solve(xfemm_fsolver *s);     /* Static2D / StaticAxisymmetric / Harmonic*       */
+/* re-runs assembly + boundary conditions + solve (the whole Newton loop) on the device objects
+ * left resident by xfemm_fsolver_solve: no host set-up, no mesh upload */
+int xfemm_fsolver_resolve(xfemm_fsolver *s);
 int xfemm_fsolver_write(xfemm_fsolver *s);     /* WriteStatic2D / WriteHarmonic2D                  */
 int xfemm_fsolver_close(xfemm_fsolver *s);
 int xfemm_fsolver_counts(xfemm_fsolver *s, int *n_nodes, int *n_elems, int *n_pbc, int *n_age,
                          int *bandwidth, int *n_unknowns, int *is_complex);
+long long xfemm_fsolver_nnz(xfemm_fsolver *s);                           /* full-CSR nonzeros of the resident system */
 int xfemm_fsolver_get_nodes(xfemm_fsolver *s, double *xy, int *bc);      /* solver order, cm      */
 int xfemm_fsolver_get_elems(xfemm_fsolver *s, int *elems8);              /* p0 p1 p2 lbl blk e0-2 */
 int xfemm_fsolver_get_pbc(xfemm_fsolver *s, int *pbc3);

@@ -1,0 +1,90 @@
+"""GPU parity: planar magnetostatics through the C ABI against the reference dumps.
+
+Bars (north_star): renumbering + CSR structure bit-exact, nodal A within 1e-6 relative L2.
+The assembled + boundary-conditioned system is additionally compared entry by entry (1e-11
+relative to the largest entry; FP64 atomics and FMA contraction reorder the sums)."""
+import numpy as np
+import pytest
+
+import xfemm_b200 as X
+from util import load_ref, rel_l2, stage_case, upper_from_full
+
+pytestmark = pytest.mark.gpu
+
+
+def _solve(name, tmp_path, precond):
+    base = stage_case(name, tmp_path)
+    S = X.FSolver(base)
+    S.set_option("keep_system", 1)
+    S.set_option("precond", precond)
+    S.load_mesh(False)
+    S.renumber(False)
+    S.solve()
+    return S
+
+
+@pytest.mark.parametrize("name", ["tb", "tb30"])
+@pytest.mark.parametrize("precond", [X.PRECOND_JACOBI, X.PRECOND_MCSSOR])
+def test_linear_planar_matches_reference(name, precond, tmp_path):
+    ref, meta = load_ref(name)
+    S = _solve(name, tmp_path, precond)
+    rowptr, col, vals, rhs = S.system()
+    urp, ucol, uval = upper_from_full(rowptr, col, vals)
+    # structure: bit-exact
+    assert np.array_equal(urp, ref["step0_rowptr"])
+    assert np.array_equal(ucol, ref["step0_col"])
+    # values + RHS of the system handed to the solver
+    scale = np.abs(ref["step0_val"]).max()
+    assert np.abs(uval - ref["step0_val"]).max() <= 1e-11 * scale
+    assert np.abs(rhs - ref["step0_rhs"]).max() <= 1e-11 * np.abs(ref["step0_rhs"]).max()
+    # symmetric storage is consistent
+    n = len(rowptr) - 1
+    import scipy.sparse as sp
+    A = sp.csr_matrix((vals, col, rowptr), shape=(n, n))
+    assert abs(A - A.T).max() <= 4e-16 * scale  # (i,j) and (j,i) are summed by independent atomics
+    # solution
+    V, Afield = S.solution()
+    assert rel_l2(V, ref["V"]) <= 1e-6
+    assert rel_l2(Afield, ref["A"]) <= 1e-6
+    st = S.stats()
+    assert st["newton_steps"] == 1
+    assert st["relres"] < 1e-8
+    print(name, "precond", precond, "iters", st["iters"], "reference", meta["iters"], "relres", st["relres"],
+          "relL2(V)", rel_l2(V, ref["V"]))
+
+
+def test_nonlinear_newton_matches_reference(tmp_path):
+    ref, meta = load_ref("temp1")
+    S = _solve("temp1", tmp_path, X.PRECOND_MCSSOR)
+    st = S.stats()
+    V, Afield = S.solution()
+    print("temp1 newton", st["newton_steps"], "iters", st["iters"], "reference", meta["solves"], meta["iters"],
+          "relL2", rel_l2(V, ref["V"]))
+    assert st["newton_steps"] == meta["solves"]
+    # the last Newton system (Jacobian + RHS) is assembled identically …
+    rowptr, col, vals, rhs = S.system()
+    urp, ucol, uval = upper_from_full(rowptr, col, vals)
+    last = meta["solves"] - 1
+    assert np.array_equal(urp, ref[f"step{last}_rowptr"])
+    assert np.array_equal(ucol, ref[f"step{last}_col"])
+    scale = np.abs(ref[f"step{last}_val"]).max()
+    assert np.abs(uval - ref[f"step{last}_val"]).max() <= 1e-9 * scale
+    assert np.abs(rhs - ref[f"step{last}_rhs"]).max() <= 1e-9 * np.abs(ref[f"step{last}_rhs"]).max()
+    # … but the reference's own answer is only as converged as its stopping rule made it: with
+    # Precision 1e-8 and a warm start its last PCGSolve does a single iteration and leaves V
+    # 3.4e-6 (relative L2) away from the exact solution of its own last linear system.  The 1e-6
+    # bar is therefore applied against that exact solution, and the distance to the reference's V
+    # is bounded by the reference's own error.
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+    n = len(rowptr) - 1
+    U = sp.csr_matrix((ref[f"step{last}_val"], ref[f"step{last}_col"], ref[f"step{last}_rowptr"]), shape=(n, n))
+    Aref = (U + sp.triu(U, 1).T).tocsc()
+    exact = spl.spsolve(Aref, ref[f"step{last}_rhs"])
+    ref_err = rel_l2(ref["V"], exact)
+    print("reference V vs exact solution of its last system:", ref_err, " ours:", rel_l2(V, exact))
+    assert rel_l2(V, exact) <= 1e-6
+    assert rel_l2(V, ref["V"]) <= ref_err + 1e-6
+    mu = S.mu()
+    refmu = ref["mu"][:, [0, 2]]
+    assert np.abs(mu - refmu).max() <= 1e-5 * np.abs(refmu).max()

@@ -47,6 +47,9 @@ SIGNATURES = {
     "xfemm_device_count": (C.c_int, []),
     "xfemm_last_error": (C.c_char_p, []),
     "xfemm_version": (C.c_char_p, []),
+    "xfemm_transfer_bytes": (None, [C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.c_int]),
+    "xfemm_launch_count": (C.c_longlong, []),
+    "xfemm_fsolver_nnz": (C.c_longlong, [_P]),
     "xfemm_linprob_create": (C.c_int, [C.c_int, _ip, _ip, C.POINTER(_P)]),
     "xfemm_linprob_destroy": (C.c_int, [_P]),
     "xfemm_linprob_n": (C.c_int, [_P]),
@@ -68,7 +71,10 @@ SIGNATURES = {
     "xfemm_linprob_newton_norms": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "xfemm_linprob_relax": (C.c_int, [_P, C.c_double]),
     "xfemm_pattern_build": (C.c_int, [C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, C.c_int, _P, _P, C.c_int, _P, _P,
-                                       C.POINTER(C.POINTER(C.c_int)), C.POINTER(C.POINTER(C.c_int))]),
+                                       C.POINTER(C.POINTER(C.c_int)), C.POINTER(C.POINTER(C.c_int)),
+                                       C.POINTER(C.POINTER(C.c_ubyte))]),
+    "xfemm_linprob_set_fill_mask": (C.c_int, [_P, _P]),
+    "xfemm_linprob_get_exists_mask": (C.c_int, [_P, _P]),
     "xfemm_free": (None, [_P]),
     "xfemm_renumber_cuthill": (C.c_int, [C.c_int, C.c_int, _ip, _ip, C.POINTER(C.c_int)]),
     "xfemm_renumber_sort_elements": (C.c_int, [C.c_int, _ip, _ip]),
@@ -84,6 +90,7 @@ SIGNATURES = {
     "xfemm_fsolver_load_mesh": (C.c_int, [_P, C.c_int]),
     "xfemm_fsolver_renumber": (C.c_int, [_P, C.c_int]),
     "xfemm_fsolver_solve": (C.c_int, [_P]),
+    "xfemm_fsolver_resolve": (C.c_int, [_P]),
     "xfemm_fsolver_write": (C.c_int, [_P]),
     "xfemm_fsolver_close": (C.c_int, [_P]),
     "xfemm_fsolver_counts": (C.c_int, [_P] + [C.POINTER(C.c_int)] * 7),
@@ -161,8 +168,9 @@ def sort_elements(tri):
     return order
 
 
-def pattern_build(n_rows, tri, age_nodes=None, pbc=None, extra=None):
-    """Full CSR pattern (rowptr, col) of mesh graph + AGE blocks + periodic fill."""
+def pattern_build(n_rows, tri, age_nodes=None, pbc=None, extra=None, with_fill=False):
+    """Full CSR pattern (rowptr, col[, fill]) of mesh graph + AGE blocks + periodic fill."""
+    fp = C.POINTER(C.c_ubyte)()
     tri = _i32(tri)
     stride = tri.shape[1]
     age = _i32(age_nodes).reshape(-1, 10) if age_nodes is not None and len(age_nodes) else None
@@ -181,12 +189,17 @@ def pattern_build(n_rows, tri, age_nodes=None, pbc=None, extra=None):
     rp = C.POINTER(C.c_int)()
     cp = C.POINTER(C.c_int)()
     _check(lib().xfemm_pattern_build(n_rows, len(tri), _ptr(tri), stride, 0 if age is None else len(age), _ptr(age),
-                                     nex, _ptr(ei), _ptr(ej), npbc, _ptr(pi), _ptr(pj), C.byref(rp), C.byref(cp)),
+                                     nex, _ptr(ei), _ptr(ej), npbc, _ptr(pi), _ptr(pj), C.byref(rp), C.byref(cp),
+                                     C.byref(fp) if with_fill else None),
            "pattern_build")
     rowptr = np.ctypeslib.as_array(rp, shape=(n_rows + 1,)).copy()
     col = np.ctypeslib.as_array(cp, shape=(int(rowptr[-1]),)).copy()
     lib().xfemm_free(rp)
     lib().xfemm_free(cp)
+    if with_fill:
+        fill = np.ctypeslib.as_array(fp, shape=(int(rowptr[-1]),)).copy()
+        lib().xfemm_free(fp)
+        return rowptr, col, fill
     return rowptr, col
 
 
@@ -306,6 +319,10 @@ class FSolver:
 
     def solve(self):
         _check(lib().xfemm_fsolver_solve(self.h), "solve")
+
+    def resolve(self):
+        """Re-runs the Newton loop (assembly + BCs + solve) on the resident device problem."""
+        _check(lib().xfemm_fsolver_resolve(self.h), "resolve")
 
     def write(self):
         _check(lib().xfemm_fsolver_write(self.h), "write")

@@ -11,6 +11,9 @@ namespace xb {
 
 void set_error(const char *fmt, ...);
 
+// bookkeeping for bench.py: bytes crossing PCIe and kernels launched by this library
+extern long long g_h2d_bytes, g_d2h_bytes, g_launch;
+
 #define XB_CUDA(call)                                                                      \
     do {                                                                                   \
         cudaError_t e_ = (call);                                                           \
@@ -47,6 +50,7 @@ struct DevBuf
     {
         if (count != n) { cudaError_t e = alloc(count); if (e != cudaSuccess) return e; }
         if (count == 0) return cudaSuccess;
+        g_h2d_bytes += (long long)(count * sizeof(T));
         return cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s);
     }
     cudaError_t zero(cudaStream_t s = 0) { return n ? cudaMemsetAsync(p, 0, n * sizeof(T), s) : cudaSuccess; }

@@ -24,6 +24,7 @@ void set_error(const char *fmt, ...)
     g_err = buf;
 }
 const char *last_error() { return g_err.c_str(); }
+long long g_h2d_bytes = 0, g_d2h_bytes = 0, g_launch = 0;
 
 static inline int env_int(const char *name, int dflt)
 {
@@ -402,7 +403,8 @@ __global__ void k_dirichlet(int n, const int *__restrict__ rowptr, const int *__
 //   meta (6 ints): i, j, type, slot(i,i), slot(j,j), unused
 __global__ void __launch_bounds__(1024)
 k_periodic(int nlevels, const int *__restrict__ level_ptr, const int *__restrict__ item_ptr,
-           const int *__restrict__ meta, const int *__restrict__ items, double *vals, double *b)
+           const int *__restrict__ meta, const int *__restrict__ items, double *vals, double *b,
+           const unsigned char *__restrict__ fill_mask, unsigned char *created)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     for (int lv = 0; lv < nlevels; lv++)
@@ -420,6 +422,12 @@ k_periodic(int nlevels, const int *__restrict__ level_ptr, const int *__restrict
                     double c = (v1 + sgn * v2) / 2.0;
                     __stcg(vals + q[0], c); __stcg(vals + q[1], c);
                     __stcg(vals + q[2], sgn * c); __stcg(vals + q[3], sgn * c);
+                    if (fill_mask)
+                    {
+#pragma unroll
+                        for (int t = 0; t < 4; t++)
+                            if (fill_mask[q[t]]) created[q[t]] = 1;
+                    }
                 }
             }
             if (lane == 0)
@@ -507,8 +515,8 @@ static int refresh_values(xfemm_linprob *p, int *singular_row)
     XB_CUDA(cudaMemcpyAsync(d_flag, &big, sizeof(int), cudaMemcpyHostToDevice, st));
     int blocks = (int)std::min<long long>((L.sell_len + 255) / 256, (long long)p->num_sms * 16);
     if (blocks < 1) blocks = 1;
-    k_sell_fill<<<blocks, 256, 0, st>>>(L.sell_len, p->sell_src.p, p->vals.p, p->sell_val.p);
-    k_diag_fill<<<(L.n_pad + 255) / 256, 256, 0, st>>>(L.n_pad, p->diag_src.p, p->vals.p, p->diag.p, p->dinv.p, d_flag);
+    ++xb::g_launch, k_sell_fill<<<blocks, 256, 0, st>>>(L.sell_len, p->sell_src.p, p->vals.p, p->sell_val.p);
+    ++xb::g_launch, k_diag_fill<<<(L.n_pad + 255) / 256, 256, 0, st>>>(L.n_pad, p->diag_src.p, p->vals.p, p->diag.p, p->dinv.p, d_flag);
     int flag = 0;
     XB_CUDA(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
     XB_CUDA(cudaStreamSynchronize(st));
@@ -623,7 +631,7 @@ int xfemm_linprob_create(int n, const int *rowptr, const int *colidx, xfemm_linp
         XB_CUDA(p->Vold.alloc(n)); XB_CUDA(p->Vold.zero(p->stream));
         XB_CUDA(p->d_mail.alloc(16)); XB_CUDA(p->d_mail.zero(p->stream));
         XB_CUDA(p->dir_idx.alloc(n));
-        k_fill_int<<<(n + 255) / 256, 256, 0, p->stream>>>(n, p->dir_idx.p, -1);
+        ++xb::g_launch, k_fill_int<<<(n + 255) / 256, 256, 0, p->stream>>>(n, p->dir_idx.p, -1);
         XB_CUDA(cudaStreamSynchronize(p->stream));
         return XFEMM_OK;
     };
@@ -654,11 +662,13 @@ int xfemm_linprob_wipe(xfemm_linprob *p)
 
 #define XB_COPY_IN(buf, src, cnt)                                                                        \
     XB_ARG(p && (src), "null pointer");                                                                    \
+    xb::g_h2d_bytes += (long long)(cnt) * 8;                                                               \
     XB_CUDA(cudaMemcpyAsync((buf).p, (src), (size_t)(cnt) * sizeof(double), cudaMemcpyHostToDevice, p->stream)); \
     XB_CUDA(cudaStreamSynchronize(p->stream));                                                             \
     return XFEMM_OK
 #define XB_COPY_OUT(buf, dst, cnt)                                                                       \
     XB_ARG(p && (dst), "null pointer");                                                                    \
+    xb::g_d2h_bytes += (long long)(cnt) * 8;                                                               \
     XB_CUDA(cudaMemcpyAsync((dst), (buf).p, (size_t)(cnt) * sizeof(double), cudaMemcpyDeviceToHost, p->stream)); \
     XB_CUDA(cudaStreamSynchronize(p->stream));                                                             \
     return XFEMM_OK
@@ -681,11 +691,11 @@ int xfemm_linprob_dirichlet(xfemm_linprob *p, int count, const int *nodes, const
     XB_CUDA(p->dir_nodes.upload(nodes, count, st));
     XB_CUDA(p->dir_first.upload(x_first, count, st));
     XB_CUDA(p->dir_last.upload(x_last, count, st));
-    k_dir_scatter<<<(count + 255) / 256, 256, 0, st>>>(count, p->dir_nodes.p, p->dir_idx.p);
-    k_dirichlet<<<(p->n + 255) / 256, 256, 0, st>>>(p->n, p->rowptr.p, p->col.p, p->vals.p, p->b.p, p->dir_idx.p,
+    ++xb::g_launch, k_dir_scatter<<<(count + 255) / 256, 256, 0, st>>>(count, p->dir_nodes.p, p->dir_idx.p);
+    ++xb::g_launch, k_dirichlet<<<(p->n + 255) / 256, 256, 0, st>>>(p->n, p->rowptr.p, p->col.p, p->vals.p, p->b.p, p->dir_idx.p,
                                                     p->dir_first.p, p->dir_last.p, bdw);
     // restore the scratch map for the next call
-    k_fill_int<<<(p->n + 255) / 256, 256, 0, st>>>(p->n, p->dir_idx.p, -1);
+    ++xb::g_launch, k_fill_int<<<(p->n + 255) / 256, 256, 0, st>>>(p->n, p->dir_idx.p, -1);
     XB_CUDA(cudaGetLastError());
     XB_CUDA(cudaStreamSynchronize(st));
     return XFEMM_OK;
@@ -776,8 +786,9 @@ int xfemm_linprob_periodic(xfemm_linprob *p, int npairs, const int *ni, const in
         XB_CUDA(cudaStreamSynchronize(st));
         p->pbc_hash = h; p->pbc_pairs = npairs; p->pbc_levels = nlevels;
     }
-    k_periodic<<<1, 1024, 0, p->stream>>>(p->pbc_levels, p->pbc_level_ptr.p, p->pbc_item_ptr.p, p->pbc_meta.p,
-                                          p->pbc_items.p, p->vals.p, p->b.p);
+    ++xb::g_launch, k_periodic<<<1, 1024, 0, p->stream>>>(p->pbc_levels, p->pbc_level_ptr.p, p->pbc_item_ptr.p, p->pbc_meta.p,
+                                          p->pbc_items.p, p->vals.p, p->b.p,
+                                          p->fill_mask.n ? p->fill_mask.p : nullptr, p->created.p);
     XB_CUDA(cudaGetLastError());
     XB_CUDA(cudaStreamSynchronize(p->stream));
     return XFEMM_OK;
@@ -815,8 +826,8 @@ int xfemm_linprob_pcg(xfemm_linprob *p, double precision, int warm, int precond,
         return XFEMM_ERR_SINGULAR;
     }
     const int n_pad = p->lay.n_pad;
-    k_to_internal<<<(n_pad + 255) / 256, 256, 0, st>>>(n_pad, p->i2c.p, p->b.p, p->bint.p);
-    if (warm) k_to_internal<<<(n_pad + 255) / 256, 256, 0, st>>>(n_pad, p->i2c.p, p->V.p, p->x.p);
+    ++xb::g_launch, k_to_internal<<<(n_pad + 255) / 256, 256, 0, st>>>(n_pad, p->i2c.p, p->b.p, p->bint.p);
+    if (warm) ++xb::g_launch, k_to_internal<<<(n_pad + 255) / 256, 256, 0, st>>>(n_pad, p->i2c.p, p->V.p, p->x.p);
     if (max_iter <= 0) max_iter = env_int("XFEMM_MAX_ITER", 200000);
     PcgArgs a = make_args(p, precision, warm ? 1 : 0, max_iter);
     int grid = 0;
@@ -827,14 +838,14 @@ int xfemm_linprob_pcg(xfemm_linprob *p, double precision, int warm, int precond,
         rc = coop_grid(p, k_pcg<XFEMM_PRECOND_JACOBI>, 512, &grid);
         if (rc != XFEMM_OK) return rc;
         a.part = p->partials.p;
-        XB_CUDA(cudaLaunchCooperativeKernel((void *)k_pcg<XFEMM_PRECOND_JACOBI>, dim3(grid), dim3(512), kargs, 0, st));
+        ++xb::g_launch; XB_CUDA(cudaLaunchCooperativeKernel((void *)k_pcg<XFEMM_PRECOND_JACOBI>, dim3(grid), dim3(512), kargs, 0, st));
     }
     else
     {
         rc = coop_grid(p, k_pcg<XFEMM_PRECOND_MCSSOR>, 512, &grid);
         if (rc != XFEMM_OK) return rc;
         a.part = p->partials.p;
-        XB_CUDA(cudaLaunchCooperativeKernel((void *)k_pcg<XFEMM_PRECOND_MCSSOR>, dim3(grid), dim3(512), kargs, 0, st));
+        ++xb::g_launch; XB_CUDA(cudaLaunchCooperativeKernel((void *)k_pcg<XFEMM_PRECOND_MCSSOR>, dim3(grid), dim3(512), kargs, 0, st));
     }
     XB_CUDA(cudaEventRecord(e2, st));
     XB_CUDA(cudaMemcpyAsync(p->h_mail, p->d_mail.p, 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -846,14 +857,14 @@ int xfemm_linprob_pcg(xfemm_linprob *p, double precision, int warm, int precond,
     const bool trivial = (p->h_mail[3] == 0.0); // res_o == 0 → reference returns without touching V
     if (!trivial)
     {
-        k_from_internal<<<(n_pad + 255) / 256, 256, 0, st>>>(n_pad, p->i2c.p, p->x.p, p->V.p);
+        ++xb::g_launch, k_from_internal<<<(n_pad + 255) / 256, 256, 0, st>>>(n_pad, p->i2c.p, p->x.p, p->V.p);
         // true relative residual ||b - A x|| / ||b||
         int sb = std::max(1, std::min((p->lay.nslices + 7) / 8, p->num_sms * 8));
-        k_spmv<<<sb, 256, 0, st>>>(p->lay.nslices, p->slice_ptr.p, p->sell_col.p, p->sell_val.p, p->diag.p, p->x.p, p->u.p);
+        ++xb::g_launch, k_spmv<<<sb, 256, 0, st>>>(p->lay.nslices, p->slice_ptr.p, p->sell_col.p, p->sell_val.p, p->diag.p, p->x.p, p->u.p);
         int nb = std::max(1, std::min((n_pad + 255) / 256, 512));
         if (p->max_grid < nb) { XB_CUDA(p->partials.alloc((size_t)4 * nb)); p->max_grid = nb; }
-        k_resnorm_partial<<<nb, 256, 0, st>>>(n_pad, p->bint.p, p->u.p, p->partials.p);
-        k_reduce2_final<<<1, 256, 0, st>>>(nb, p->partials.p, p->d_mail.p + 10);
+        ++xb::g_launch, k_resnorm_partial<<<nb, 256, 0, st>>>(n_pad, p->bint.p, p->u.p, p->partials.p);
+        ++xb::g_launch, k_reduce2_final<<<1, 256, 0, st>>>(nb, p->partials.p, p->d_mail.p + 10);
         XB_CUDA(cudaMemcpyAsync(p->h_mail + 10, p->d_mail.p + 10, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
         XB_CUDA(cudaStreamSynchronize(st));
         XB_CUDA(cudaGetLastError());
@@ -888,10 +899,10 @@ int xfemm_linprob_multa(xfemm_linprob *p, const double *x, double *y)
     const int n_pad = p->lay.n_pad;
     // stage through V-sized scratch: Vold is free between Newton steps only, so use r/u
     XB_CUDA(cudaMemcpyAsync(p->Vold.p, x, (size_t)p->n * sizeof(double), cudaMemcpyHostToDevice, st));
-    k_to_internal<<<(n_pad + 255) / 256, 256, 0, st>>>(n_pad, p->i2c.p, p->Vold.p, p->r.p);
+    ++xb::g_launch, k_to_internal<<<(n_pad + 255) / 256, 256, 0, st>>>(n_pad, p->i2c.p, p->Vold.p, p->r.p);
     int sb = std::max(1, std::min((p->lay.nslices + 7) / 8, p->num_sms * 8));
-    k_spmv<<<sb, 256, 0, st>>>(p->lay.nslices, p->slice_ptr.p, p->sell_col.p, p->sell_val.p, p->diag.p, p->r.p, p->u.p);
-    k_from_internal<<<(n_pad + 255) / 256, 256, 0, st>>>(n_pad, p->i2c.p, p->u.p, p->Vold.p);
+    ++xb::g_launch, k_spmv<<<sb, 256, 0, st>>>(p->lay.nslices, p->slice_ptr.p, p->sell_col.p, p->sell_val.p, p->diag.p, p->r.p, p->u.p);
+    ++xb::g_launch, k_from_internal<<<(n_pad + 255) / 256, 256, 0, st>>>(n_pad, p->i2c.p, p->u.p, p->Vold.p);
     XB_CUDA(cudaMemcpyAsync(y, p->Vold.p, (size_t)p->n * sizeof(double), cudaMemcpyDeviceToHost, st));
     XB_CUDA(cudaStreamSynchronize(st));
     XB_CUDA(cudaGetLastError());
@@ -907,7 +918,7 @@ int xfemm_linprob_multpc(xfemm_linprob *p, int precond, const double *x, double 
     cudaStream_t st = p->stream;
     const int n_pad = p->lay.n_pad;
     XB_CUDA(cudaMemcpyAsync(p->Vold.p, x, (size_t)p->n * sizeof(double), cudaMemcpyHostToDevice, st));
-    k_to_internal<<<(n_pad + 255) / 256, 256, 0, st>>>(n_pad, p->i2c.p, p->Vold.p, p->r.p);
+    ++xb::g_launch, k_to_internal<<<(n_pad + 255) / 256, 256, 0, st>>>(n_pad, p->i2c.p, p->Vold.p, p->r.p);
     PcgArgs a = make_args(p, 0, 0, 0);
     int grid = 0;
     void *kargs[] = {&a};
@@ -915,15 +926,15 @@ int xfemm_linprob_multpc(xfemm_linprob *p, int precond, const double *x, double 
     {
         rc = coop_grid(p, k_precond_only<XFEMM_PRECOND_JACOBI>, 512, &grid);
         if (rc != XFEMM_OK) return rc;
-        XB_CUDA(cudaLaunchCooperativeKernel((void *)k_precond_only<XFEMM_PRECOND_JACOBI>, dim3(grid), dim3(512), kargs, 0, st));
+        ++xb::g_launch; XB_CUDA(cudaLaunchCooperativeKernel((void *)k_precond_only<XFEMM_PRECOND_JACOBI>, dim3(grid), dim3(512), kargs, 0, st));
     }
     else
     {
         rc = coop_grid(p, k_precond_only<XFEMM_PRECOND_MCSSOR>, 512, &grid);
         if (rc != XFEMM_OK) return rc;
-        XB_CUDA(cudaLaunchCooperativeKernel((void *)k_precond_only<XFEMM_PRECOND_MCSSOR>, dim3(grid), dim3(512), kargs, 0, st));
+        ++xb::g_launch; XB_CUDA(cudaLaunchCooperativeKernel((void *)k_precond_only<XFEMM_PRECOND_MCSSOR>, dim3(grid), dim3(512), kargs, 0, st));
     }
-    k_from_internal<<<(n_pad + 255) / 256, 256, 0, st>>>(n_pad, p->i2c.p, p->z.p, p->Vold.p);
+    ++xb::g_launch, k_from_internal<<<(n_pad + 255) / 256, 256, 0, st>>>(n_pad, p->i2c.p, p->z.p, p->Vold.p);
     XB_CUDA(cudaMemcpyAsync(y, p->Vold.p, (size_t)p->n * sizeof(double), cudaMemcpyDeviceToHost, st));
     XB_CUDA(cudaStreamSynchronize(st));
     XB_CUDA(cudaGetLastError());
@@ -942,10 +953,10 @@ int xfemm_linprob_bench_spmv(xfemm_linprob *p, int reps, double *ms_per_rep)
     XB_CUDA(cudaEventCreate(&e0)); XB_CUDA(cudaEventCreate(&e1));
     int sb = std::max(1, std::min((p->lay.nslices + 7) / 8, p->num_sms * 8));
     for (int w = 0; w < 3; w++)
-        k_spmv<<<sb, 256, 0, st>>>(p->lay.nslices, p->slice_ptr.p, p->sell_col.p, p->sell_val.p, p->diag.p, p->bint.p, p->u.p);
+        ++xb::g_launch, k_spmv<<<sb, 256, 0, st>>>(p->lay.nslices, p->slice_ptr.p, p->sell_col.p, p->sell_val.p, p->diag.p, p->bint.p, p->u.p);
     XB_CUDA(cudaEventRecord(e0, st));
     for (int w = 0; w < reps; w++)
-        k_spmv<<<sb, 256, 0, st>>>(p->lay.nslices, p->slice_ptr.p, p->sell_col.p, p->sell_val.p, p->diag.p, p->bint.p, p->u.p);
+        ++xb::g_launch, k_spmv<<<sb, 256, 0, st>>>(p->lay.nslices, p->slice_ptr.p, p->sell_col.p, p->sell_val.p, p->diag.p, p->bint.p, p->u.p);
     XB_CUDA(cudaEventRecord(e1, st));
     XB_CUDA(cudaStreamSynchronize(st));
     XB_CUDA(cudaGetLastError());
@@ -969,8 +980,8 @@ int xfemm_linprob_newton_norms(xfemm_linprob *p, double *dv2, double *v2)
     cudaStream_t st = p->stream;
     int nb = std::max(1, std::min((p->n + 255) / 256, 512));
     if (p->max_grid < nb) { XB_CUDA(p->partials.alloc((size_t)4 * nb)); p->max_grid = nb; }
-    k_newton_norms<<<nb, 256, 0, st>>>(p->n, p->V.p, p->Vold.p, p->partials.p);
-    k_reduce2_final<<<1, 256, 0, st>>>(nb, p->partials.p, p->d_mail.p + 12);
+    ++xb::g_launch, k_newton_norms<<<nb, 256, 0, st>>>(p->n, p->V.p, p->Vold.p, p->partials.p);
+    ++xb::g_launch, k_reduce2_final<<<1, 256, 0, st>>>(nb, p->partials.p, p->d_mail.p + 12);
     XB_CUDA(cudaMemcpyAsync(p->h_mail + 12, p->d_mail.p + 12, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
     XB_CUDA(cudaStreamSynchronize(st));
     XB_CUDA(cudaGetLastError());
@@ -982,10 +993,40 @@ int xfemm_linprob_newton_norms(xfemm_linprob *p, double *dv2, double *v2)
 int xfemm_linprob_relax(xfemm_linprob *p, double relax)
 {
     XB_ARG(p, "null handle");
-    k_relax<<<(p->n + 255) / 256, 256, 0, p->stream>>>(p->n, p->V.p, p->Vold.p, relax);
+    ++xb::g_launch, k_relax<<<(p->n + 255) / 256, 256, 0, p->stream>>>(p->n, p->V.p, p->Vold.p, relax);
     XB_CUDA(cudaGetLastError());
     return XFEMM_OK;
 }
+
+int xfemm_linprob_set_fill_mask(xfemm_linprob *p, const unsigned char *fill)
+{
+    XB_ARG(p && fill, "null pointer");
+    XB_CUDA(p->fill_mask.upload(fill, (size_t)p->nnz, p->stream));
+    XB_CUDA(p->created.alloc((size_t)p->nnz));
+    XB_CUDA(p->created.zero(p->stream));
+    XB_CUDA(cudaStreamSynchronize(p->stream));
+    return XFEMM_OK;
+}
+
+int xfemm_linprob_get_exists_mask(xfemm_linprob *p, unsigned char *exists)
+{
+    XB_ARG(p && exists, "null pointer");
+    if (!p->fill_mask.n) { memset(exists, 1, (size_t)p->nnz); return XFEMM_OK; }
+    std::vector<unsigned char> f((size_t)p->nnz), c((size_t)p->nnz);
+    XB_CUDA(cudaMemcpyAsync(f.data(), p->fill_mask.p, f.size(), cudaMemcpyDeviceToHost, p->stream));
+    XB_CUDA(cudaMemcpyAsync(c.data(), p->created.p, c.size(), cudaMemcpyDeviceToHost, p->stream));
+    XB_CUDA(cudaStreamSynchronize(p->stream));
+    for (size_t s = 0; s < f.size(); s++) exists[s] = (!f[s] || c[s]) ? 1 : 0;
+    return XFEMM_OK;
+}
+
+void xfemm_transfer_bytes(long long *h2d, long long *d2h, int reset)
+{
+    if (h2d) *h2d = xb::g_h2d_bytes;
+    if (d2h) *d2h = xb::g_d2h_bytes;
+    if (reset) { xb::g_h2d_bytes = 0; xb::g_d2h_bytes = 0; }
+}
+long long xfemm_launch_count(void) { return xb::g_launch; }
 
 void xfemm_free(void *ptr) { free(ptr); }
 

@@ -397,7 +397,7 @@ int xfemm_mag_create(const xfemm_mag_desc *d, xfemm_linprob *lin, xfemm_mag **ou
         XB_CUDA(m->emap.alloc((size_t)d->n_elems * 9));
         XB_CUDA(m->err_flag.alloc(1));
         XB_CUDA(m->err_flag.zero(st));
-        k_build_emap<<<(d->n_elems + 255) / 256, 256, 0, st>>>(d->n_elems, (const int4 *)m->tri.p, lin->rowptr.p,
+        ++xb::g_launch, k_build_emap<<<(d->n_elems + 255) / 256, 256, 0, st>>>(d->n_elems, (const int4 *)m->tri.p, lin->rowptr.p,
                                                                 lin->col.p, m->emap.p, m->err_flag.p);
         int flag = 0;
         XB_CUDA(cudaMemcpyAsync(&flag, m->err_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -419,7 +419,8 @@ int xfemm_mag_create(const xfemm_mag_desc *d, xfemm_linprob *lin, xfemm_mag **ou
 int xfemm_mag_destroy(xfemm_mag *m)
 {
     if (!m) return XFEMM_OK;
-    if (m->lin && m->lin->stream) cudaStreamSynchronize(m->lin->stream);
+    // the bound linear problem may already be gone (it is owned by the caller's CBigLinProb);
+    // cudaFree in the DevBuf destructors synchronises on its own
     delete m;
     return XFEMM_OK;
 }
@@ -439,18 +440,18 @@ int xfemm_mag_assemble_static(xfemm_mag *m, int iter, double *elapsed_ms)
     if (m->n_age_cells > 0)
     {
         int nt = m->n_age_cells * 55;
-        k_age_scatter<<<(nt + 127) / 128, 128, 0, st>>>(m->n_age_cells, m->age_nodes.p, m->age_w.p, m->age_mid.p,
+        ++xb::g_launch, k_age_scatter<<<(nt + 127) / 128, 128, 0, st>>>(m->n_age_cells, m->age_nodes.p, m->age_w.p, m->age_mid.p,
                                                         m->age_mats.p, L->rowptr.p, L->col.p, L->vals.p, 1.0, m->err_flag.p);
     }
-    k_assemble_static2d<<<(m->n_elems + 255) / 256, 256, 0, st>>>(
+    ++xb::g_launch, k_assemble_static2d<<<(m->n_elems + 255) / 256, 256, 0, st>>>(
         m->n_elems, iter, (const int4 *)m->tri.p, (const double2 *)m->xy.p, m->emap.p, m->labels.p,
         m->magdir.n ? m->magdir.p : nullptr, m->bhB.p, m->bhH.p, m->bhS.p, L->V.p, L->vals.p, L->b.p, (double2 *)m->mu.p);
     if (m->n_mixed > 0)
-        k_mixed_edges<<<(m->n_mixed + 127) / 128, 128, 0, st>>>(m->n_mixed, m->n_elems, m->mixed_es.p, m->mixed_c.p,
+        ++xb::g_launch, k_mixed_edges<<<(m->n_mixed + 127) / 128, 128, 0, st>>>(m->n_mixed, m->n_elems, m->mixed_es.p, m->mixed_c.p,
                                                                 (const int4 *)m->tri.p, (const double2 *)m->xy.p,
                                                                 m->emap.p, L->vals.p, L->b.p);
     if (m->n_psrc > 0)
-        k_point_sources<<<(m->n_psrc + 127) / 128, 128, 0, st>>>(m->n_psrc, m->psrc_node.p, m->psrc_val.p, L->b.p);
+        ++xb::g_launch, k_point_sources<<<(m->n_psrc + 127) / 128, 128, 0, st>>>(m->n_psrc, m->psrc_node.p, m->psrc_val.p, L->b.p);
     int flag = 0;
     XB_CUDA(cudaMemcpyAsync(&flag, m->err_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     if (elapsed_ms) XB_CUDA(cudaEventRecord(e1, st));
@@ -481,6 +482,8 @@ int xfemm_mag_solution_to_A(xfemm_mag *m, double *A_host)
     xfemm_linprob *L = m->lin;
     cudaStream_t st = L->stream;
     // reference: L.b[i] = L.V[i]*c — the RHS array doubles as the result array (static2d.cpp:1018-1021)
+    ++xb::g_launch;
+    xb::g_d2h_bytes += (long long)m->n_nodes * 8;
     k_scale_to_A<<<(m->n_nodes + 255) / 256, 256, 0, st>>>(m->n_nodes, L->V.p, (const double2 *)m->xy.p, m->axisymmetric, L->b.p);
     XB_CUDA(cudaMemcpyAsync(A_host, L->b.p, (size_t)m->n_nodes * sizeof(double), cudaMemcpyDeviceToHost, st));
     XB_CUDA(cudaStreamSynchronize(st));

@@ -13,7 +13,7 @@ struct xfemm_fsolver
     CBigLinProb *L = nullptr;
     CBigComplexLinProb *Lc = nullptr;
     bool verbose = false;
-    ~xfemm_fsolver() { delete L; delete Lc; }
+    ~xfemm_fsolver() { S.releaseDevice(); delete L; delete Lc; }
 };
 
 static int quiet(const char *, ...) { return 0; }
@@ -72,6 +72,7 @@ int xfemm_fsolver_solve(xfemm_fsolver *s)
     int ok;
     if (S.Frequency == 0)
     {
+        S.releaseDevice();
         delete s->L;
         s->L = new CBigLinProb;
         s->L->Precision = S.Precision;
@@ -87,6 +88,18 @@ int xfemm_fsolver_solve(xfemm_fsolver *s)
         ok = (S.ProblemType == femm::PLANAR) ? S.Harmonic2D(*s->Lc, s->verbose) : S.HarmonicAxisymmetric(*s->Lc, s->verbose);
     }
     if (ok != 1)
+    {
+        std::string prev = xfemm_last_error();
+        xb::set_error("solve failed (%s)", prev.c_str());
+        return XFEMM_ERR_DIVERGED;
+    }
+    return XFEMM_OK;
+}
+
+int xfemm_fsolver_resolve(xfemm_fsolver *s)
+{
+    if (!s || !s->L) { xb::set_error("no resident static problem (call xfemm_fsolver_solve first)"); return XFEMM_ERR_ARG; }
+    if (s->S.staticNewton(*s->L) != 1)
     {
         std::string prev = xfemm_last_error();
         xb::set_error("solve failed (%s)", prev.c_str());
@@ -118,6 +131,12 @@ int xfemm_fsolver_counts(xfemm_fsolver *s, int *n_nodes, int *n_elems, int *n_pb
     if (is_complex) *is_complex = S.Frequency != 0;
     if (n_unknowns) *n_unknowns = S.Frequency != 0 ? S.NumNodes + S.NumCircProps : S.NumNodes;
     return XFEMM_OK;
+}
+
+long long xfemm_fsolver_nnz(xfemm_fsolver *s)
+{
+    if (!s || !s->L || !s->L->device()) return 0;
+    return xfemm_linprob_nnz(s->L->device());
 }
 
 int xfemm_fsolver_get_nodes(xfemm_fsolver *s, double *xy, int *bc)

@@ -252,6 +252,14 @@ public:
     int maxIterOption;           // <=0 = backend default
     xfemm_mag *magdev;           // device mesh of the last solve (kept for queries), owned
     void releaseDevice();
+    // host-side inputs of the Newton loop that stay valid while the device problem is resident
+    struct StaticPlan
+    {
+        std::vector<int> dirNodes, pbcI, pbcJ, pbcT;
+        std::vector<double> dirFirst, dirLast, labelJsrc;
+        bool linear = true, ready = false;
+    } plan;
+    int staticNewton(CBigLinProb &L); // re-runnable on the resident device problem
     // optional host snapshot of the last assembled + boundary-conditioned system (parity tests)
     bool keepSystem;
     std::vector<int> sysRowptr, sysCol;

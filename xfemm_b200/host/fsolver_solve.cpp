@@ -14,6 +14,7 @@
 #include <cmath>
 #include <complex>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 
@@ -22,6 +23,19 @@ using namespace femmsolver;
 typedef std::complex<double> cplx;
 
 namespace xb { void age_cell_matrix(double ci, double co, double K, double *MG); }
+
+// debugging aid: XFEMM_DEBUG_DUMP=<dir> writes raw little-endian arrays per Newton step
+static void debug_dump(const char *name, int step, const void *data, size_t bytes)
+{
+    const char *dir = getenv("XFEMM_DEBUG_DUMP");
+    if (!dir) return;
+    char path[1024];
+    snprintf(path, sizeof path, "%s/step%d_%s.bin", dir, step, name);
+    FILE *f = fopen(path, "wb");
+    if (!f) return;
+    fwrite(data, 1, bytes, f);
+    fclose(f);
+}
 
 static double wall() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
@@ -494,8 +508,9 @@ int FSolver::staticSolve(CBigLinProb &L, bool axi)
     // ---- sparsity pattern → device problem
     double t0 = wall();
     int *rowptr = nullptr, *colidx = nullptr;
+    unsigned char *fillmask = nullptr;
     if (xfemm_pattern_build(NumNodes, NumEls, tri.data(), 4, (int)ageMid.size(), ageNodes.data(), 0, nullptr, nullptr,
-                            NumPBCs, pbcI.data(), pbcJ.data(), &rowptr, &colidx) != XFEMM_OK)
+                            NumPBCs, pbcI.data(), pbcJ.data(), &rowptr, &colidx, keepSystem ? &fillmask : nullptr) != XFEMM_OK)
     {
         WarnMessage(xfemm_last_error());
         return false;
@@ -505,11 +520,8 @@ int FSolver::staticSolve(CBigLinProb &L, bool axi)
     xfemm_linprob *lin = nullptr;
     int rc = xfemm_linprob_create(NumNodes, rowptr, colidx, &lin);
     if (rc == XFEMM_OK) L.attachDevice(lin, rowptr, colidx);
-    if (rc == XFEMM_OK && keepSystem)
-    {
-        sysRowptr.assign(rowptr, rowptr + NumNodes + 1);
-        sysCol.assign(colidx, colidx + rowptr[NumNodes]);
-    }
+    if (rc == XFEMM_OK && fillmask) rc = xfemm_linprob_set_fill_mask(lin, fillmask);
+    xfemm_free(fillmask);
     xfemm_free(rowptr);
     xfemm_free(colidx);
     if (rc != XFEMM_OK) { WarnMessage(xfemm_last_error()); return false; }
@@ -532,6 +544,26 @@ int FSolver::staticSolve(CBigLinProb &L, bool axi)
     if (xfemm_mag_create(&D, lin, &magdev) != XFEMM_OK) { WarnMessage(xfemm_last_error()); return false; }
     stats.t_upload = wall() - t0;
 
+    plan.dirNodes = dirNodes; plan.dirFirst = dirFirst; plan.dirLast = dirLast;
+    plan.pbcI = pbcI; plan.pbcJ = pbcJ; plan.pbcT = pbcT;
+    plan.labelJsrc.resize(NumBlockLabels);
+    for (int l = 0; l < NumBlockLabels; l++) plan.labelJsrc[l] = labels[l].Jsrc;
+    plan.linear = LinearFlag;
+    plan.ready = true;
+    return staticNewton(L);
+}
+
+// Newton / "LinearFlag" loop of Static2D (static2d.cpp:177-1016) on the resident device problem:
+// assemble → Dirichlet → periodic → PCG → relaxation bookkeeping.  Can be re-run on the same
+// device objects (bench.py's device-resident timing, rotor-angle sweeps).
+int FSolver::staticNewton(CBigLinProb &L)
+{
+    if (!plan.ready || !magdev || !L.device()) { WarnMessage("xfemm_b200: no prepared device problem\n"); return false; }
+    xfemm_linprob *lin = L.device();
+    bool LinearFlag = plan.linear;
+    int rc;
+    Relax = 1.;
+    stats.pcg_iters.clear(); stats.pcg_ms.clear(); stats.assemble_ms.clear();
     const int precond = precondOption >= 0 ? precondOption : L.precond;
     int Iter = 0;
     double res = 0, lastres = 0;
@@ -541,8 +573,8 @@ int FSolver::staticSolve(CBigLinProb &L, bool axi)
         double ms_asm = 0;
         if (xfemm_mag_assemble_static(magdev, Iter, &ms_asm) != XFEMM_OK) { WarnMessage(xfemm_last_error()); return false; }
         double tb = wall();
-        if (xfemm_linprob_dirichlet(lin, (int)dirNodes.size(), dirNodes.data(), dirFirst.data(), dirLast.data(), L.bdw) != XFEMM_OK ||
-            xfemm_linprob_periodic(lin, NumPBCs, pbcI.data(), pbcJ.data(), pbcT.data()) != XFEMM_OK)
+        if (xfemm_linprob_dirichlet(lin, (int)plan.dirNodes.size(), plan.dirNodes.data(), plan.dirFirst.data(), plan.dirLast.data(), L.bdw) != XFEMM_OK ||
+            xfemm_linprob_periodic(lin, NumPBCs, plan.pbcI.data(), plan.pbcJ.data(), plan.pbcT.data()) != XFEMM_OK)
         {
             WarnMessage(xfemm_last_error());
             return false;
@@ -550,10 +582,24 @@ int FSolver::staticSolve(CBigLinProb &L, bool axi)
         stats.assemble_ms.push_back(ms_asm + (wall() - tb) * 1e3);
         if (keepSystem)
         {
-            sysVals.resize(sysCol.size());
+            // snapshot for the parity tests, pruned to the entries the reference's linked lists hold
+            const int *rp0 = L.patternRowptr(), *col0 = L.patternCol();
+            const size_t nnz0 = (size_t)rp0[NumNodes];
+            std::vector<double> v0(nnz0);
+            std::vector<unsigned char> ex(nnz0);
             sysRhs.resize(NumNodes);
-            xfemm_linprob_get_values(lin, sysVals.data());
+            xfemm_linprob_get_values(lin, v0.data());
             xfemm_linprob_get_rhs(lin, sysRhs.data());
+            xfemm_linprob_get_exists_mask(lin, ex.data());
+            sysRowptr.assign(NumNodes + 1, 0);
+            sysCol.clear();
+            sysVals.clear();
+            for (int i = 0; i < NumNodes; i++)
+            {
+                for (int q = rp0[i]; q < rp0[i + 1]; q++)
+                    if (ex[q]) { sysCol.push_back(col0[q]); sysVals.push_back(v0[q]); }
+                sysRowptr[i + 1] = (int)sysCol.size();
+            }
         }
         xfemm_linprob_save_solution(lin); // V_old = V
         PrintMessage("Conjugate Gradient Solver\n");
@@ -564,6 +610,17 @@ int FSolver::staticSolve(CBigLinProb &L, bool axi)
         stats.final_relres = info.relres;
         L.lastIterations = info.iterations; L.lastSolveMs = info.solve_ms; L.lastRelRes = info.relres;
         if (rc != XFEMM_OK) { WarnMessage(xfemm_last_error()); return false; }
+        if (getenv("XFEMM_DEBUG_DUMP"))
+        {
+            std::vector<double> tmp(NumNodes);
+            xfemm_linprob_get_solution(lin, tmp.data());
+            debug_dump("vout", Iter, tmp.data(), tmp.size() * sizeof(double));
+            if (keepSystem)
+            {
+                debug_dump("vals", Iter, sysVals.data(), sysVals.size() * sizeof(double));
+                debug_dump("rhs", Iter, sysRhs.data(), sysRhs.size() * sizeof(double));
+            }
+        }
 
         if (LinearFlag == false)
         {
@@ -593,7 +650,7 @@ int FSolver::staticSolve(CBigLinProb &L, bool axi)
         return false;
     }
     // bookkeeping the reference keeps per element
-    for (int i = 0; i < NumEls; i++) meshele[i].Jprev += Iter * labels[meshele[i].lbl].Jsrc;
+    for (int i = 0; i < NumEls; i++) meshele[i].Jprev += Iter * plan.labelJsrc[meshele[i].lbl];
     return true;
 }
 

@@ -21,7 +21,7 @@ int xfemm_pattern_build(int n_rows, int n_elems, const int *tri, int tri_stride,
                         int n_age_cells, const int *age_nodes,
                         int n_extra, const int *extra_i, const int *extra_j,
                         int n_pbc, const int *pbc_i, const int *pbc_j,
-                        int **rowptr_out, int **colidx_out)
+                        int **rowptr_out, int **colidx_out, unsigned char **fill_out)
 {
     if (n_rows <= 0 || !rowptr_out || !colidx_out || (n_elems > 0 && (!tri || tri_stride < 3)))
     {
@@ -70,18 +70,21 @@ int xfemm_pattern_build(int n_rows, int n_elems, const int *tri, int tri_stride,
         }
         adj.resize(w);
     }
-    // ---- extras: AGE blocks, explicit couplings, periodic fill (symbolic replay in list order)
-    std::unordered_map<int, std::vector<int>> extra; // row -> additional columns (unsorted, may repeat)
+    // ---- extras: AGE blocks and explicit couplings (created by assembly), then the periodic
+    // fill (symbolic replay of Periodicity in list order; kept apart so that callers can tell
+    // which slots exist only if the value-dependent reference code would have created them)
+    std::unordered_map<int, std::vector<int>> extra, fill; // row -> additional columns
+    auto in_map = [](const std::unordered_map<int, std::vector<int>> &m, int r, int c) -> bool {
+        auto f = m.find(r);
+        return f != m.end() && std::find(f->second.begin(), f->second.end(), c) != f->second.end();
+    };
     auto has = [&](int r, int c) -> bool {
         const int *b = adj.data() + rp[r], *e = adj.data() + rp[r + 1];
-        if (std::binary_search(b, e, c)) return true;
-        auto f = extra.find(r);
-        if (f == extra.end()) return false;
-        return std::find(f->second.begin(), f->second.end(), c) != f->second.end();
+        return std::binary_search(b, e, c) || in_map(extra, r, c) || in_map(fill, r, c);
     };
-    auto add = [&](int r, int c) {
-        if (!has(r, c)) extra[r].push_back(c);
-        if (r != c && !has(c, r)) extra[c].push_back(r);
+    auto add = [&](std::unordered_map<int, std::vector<int>> &m, int r, int c) {
+        if (!has(r, c)) m[r].push_back(c);
+        if (r != c && !has(c, r)) m[c].push_back(r);
     };
     for (int k = 0; k < n_age_cells; k++)
     {
@@ -89,13 +92,13 @@ int xfemm_pattern_build(int n_rows, int n_elems, const int *tri, int tri_stride,
         for (int a = 0; a < 10; a++)
         {
             if (nn[a] < 0 || nn[a] >= n) { xb::set_error("AGE cell %d: node out of range", k); return XFEMM_ERR_ARG; }
-            for (int b = a; b < 10; b++) add(nn[a], nn[b]);
+            for (int b = a; b < 10; b++) add(extra, nn[a], nn[b]);
         }
     }
     for (int k = 0; k < n_extra; k++)
     {
         if (extra_i[k] < 0 || extra_i[k] >= n || extra_j[k] < 0 || extra_j[k] >= n) { xb::set_error("extra coupling %d out of range", k); return XFEMM_ERR_ARG; }
-        add(extra_i[k], extra_j[k]);
+        add(extra, extra_i[k], extra_j[k]);
     }
     std::vector<int> nb;
     for (int k = 0; k < n_pbc; k++)
@@ -106,45 +109,62 @@ int xfemm_pattern_build(int n_rows, int n_elems, const int *tri, int tri_stride,
         for (int r : {i, j})
         {
             nb.insert(nb.end(), adj.begin() + rp[r], adj.begin() + rp[r + 1]);
-            auto f = extra.find(r);
-            if (f != extra.end()) nb.insert(nb.end(), f->second.begin(), f->second.end());
+            for (auto *m : {&extra, &fill})
+            {
+                auto f = m->find(r);
+                if (f != m->end()) nb.insert(nb.end(), f->second.begin(), f->second.end());
+            }
         }
         std::sort(nb.begin(), nb.end());
         nb.erase(std::unique(nb.begin(), nb.end()), nb.end());
         for (int kk : nb)
         {
             if (kk == i || kk == j) continue;
-            add(kk, i);
-            add(kk, j);
+            add(fill, kk, i);
+            add(fill, kk, j);
         }
     }
     // ---- merge
     size_t total = adj.size();
     for (auto &kv : extra) total += kv.second.size();
+    for (auto &kv : fill) total += kv.second.size();
     int *rowptr = (int *)malloc(sizeof(int) * (size_t)(n + 1));
     int *col = (int *)malloc(sizeof(int) * std::max<size_t>(total, 1));
-    if (!rowptr || !col) { free(rowptr); free(col); xb::set_error("out of memory"); return XFEMM_ERR_ARG; }
+    unsigned char *isfill = fill_out ? (unsigned char *)calloc(std::max<size_t>(total, 1), 1) : nullptr;
+    if (!rowptr || !col || (fill_out && !isfill)) { free(rowptr); free(col); free(isfill); xb::set_error("out of memory"); return XFEMM_ERR_ARG; }
     size_t w = 0;
     rowptr[0] = 0;
+    std::vector<int> merged;
     for (int i = 0; i < n; i++)
     {
         const int *b = adj.data() + rp[i], *e = adj.data() + rp[i + 1];
-        auto f = extra.empty() ? extra.end() : extra.find(i);
-        if (f == extra.end())
+        auto fe = extra.empty() ? extra.end() : extra.find(i);
+        auto ff = fill.empty() ? fill.end() : fill.find(i);
+        if (fe == extra.end() && ff == fill.end())
         {
             memcpy(col + w, b, (e - b) * sizeof(int));
             w += e - b;
         }
         else
         {
-            std::vector<int> &x = f->second;
-            std::sort(x.begin(), x.end());
-            x.erase(std::unique(x.begin(), x.end()), x.end());
-            int *o = std::set_union(b, e, x.data(), x.data() + x.size(), col + w);
-            w = o - col;
+            merged.assign(b, e);
+            if (fe != extra.end()) merged.insert(merged.end(), fe->second.begin(), fe->second.end());
+            size_t nonfill = merged.size();
+            if (ff != fill.end()) merged.insert(merged.end(), ff->second.begin(), ff->second.end());
+            // (column, is-fill) pairs; the `has` test above guarantees the three sources are disjoint
+            std::vector<std::pair<int, int>> pr(merged.size());
+            for (size_t q = 0; q < merged.size(); q++) pr[q] = {merged[q], q >= nonfill ? 1 : 0};
+            std::sort(pr.begin(), pr.end());
+            for (auto &x : pr)
+            {
+                col[w] = x.first;
+                if (isfill) isfill[w] = (unsigned char)x.second;
+                w++;
+            }
         }
         rowptr[i + 1] = (int)w;
     }
+    if (fill_out) *fill_out = isfill;
     *rowptr_out = rowptr;
     *colidx_out = col;
     return XFEMM_OK;

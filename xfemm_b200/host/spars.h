@@ -65,6 +65,8 @@ public:
     // binds an externally built device problem (ownership passes to this object)
     void attachDevice(xfemm_linprob *d, const int *rowptr, const int *col);
     void invalidateHostCopy() { hostValuesValid = false; }
+    const int *patternRowptr() const { return csrRowptr.data(); }
+    const int *patternCol() const { return csrCol.data(); }
 
 private:
     struct Ent { int c; double x; };
