@@ -179,6 +179,9 @@ typedef struct xfemm_mag_desc
     double r_eps;                  /* 1e-6*units: nodes with |r| below are on the axis          */
 } xfemm_mag_desc;
 
+/* 10x10 matrix of one air-gap-element ring cell for mesh shifts ci, co and aspect ratio
+ * K = dr/(R dtheta) (static2d.cpp:200-274); MG100 row-major, symmetric */
+int xfemm_age_cell_matrix(double ci, double co, double K, double *MG100);
 /* creates the device mesh and binds it to a linear problem whose pattern contains the mesh graph */
 int xfemm_mag_create(const xfemm_mag_desc *desc, xfemm_linprob *lin, xfemm_mag **out);
 int xfemm_mag_destroy(xfemm_mag *m);

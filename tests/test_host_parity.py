@@ -1,0 +1,125 @@
+"""CPU-side checks of the product's host layer (no GPU compute): the C-ABI library loads and exports
+every symbol include/xfemm_b200.h declares, .fem/mesh parsing, Cuthill–McKee renumbering, the comb
+sort and the sparsity pattern are bit-exact with the reference golden data, and the solver refuses
+to run without a CUDA device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import tempfile
+
+import numpy as np
+import pytest
+
+import xfemm_b200 as X
+from oracle import fsolver_oracle as O
+from oracle.age_matrix import age_matrix
+from util import age_cells, load_ref, stage_case, upper_from_full
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "xfemm_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(xfemm_[A-Za-z0-9_]+)\s*\(", hdr))
+    assert len(declared) > 50
+    lib = C.CDLL(X.LIB_PATH)
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, missing
+    # the Python binding covers the same set
+    assert declared == set(X.SIGNATURES), sorted(declared ^ set(X.SIGNATURES))
+
+
+@pytest.mark.parametrize("name", ["tb", "tb30", "temp1"])
+def test_load_renumber_pattern_bit_exact(name, tmp_path):
+    ref, meta = load_ref(name)
+    S = X.FSolver(stage_case(name, tmp_path))
+    S.load_mesh(False)
+    S.renumber(False)
+    c = S.counts()
+    assert (c["n_nodes"], c["n_elems"], c["n_pbc"], c["bandwidth"]) == (meta["n_nodes"], meta["n_elems"], meta["n_pbc"], meta["bandwidth"])
+    xy, bc = S.nodes()
+    assert np.array_equal(xy, ref["nodes"]) and np.array_equal(bc, ref["node_bc"])
+    assert np.array_equal(S.elems(), ref["elems"])
+    assert np.array_equal(S.pbc(), ref["pbc"])
+    # pattern: every entry of the reference's upper-triangular lists is present; the only extras are
+    # flagged periodic fill (the reference creates those only where a value is non-zero at run time)
+    cells = age_cells(ref["age0_qn"]) if "age0_qn" in ref else None
+    rowptr, col, fill = X.pattern_build(c["n_nodes"], S.elems()[:, :4], cells, S.pbc(), with_fill=True)
+    n = c["n_nodes"]
+    rows = np.repeat(np.arange(n), np.diff(rowptr))
+    up = col >= rows
+    mine = set(zip(rows[up].tolist(), col[up].tolist()))
+    mine_nofill = set(zip(rows[up & (fill == 0)].tolist(), col[up & (fill == 0)].tolist()))
+    rrows = np.repeat(np.arange(n), np.diff(ref["step0_rowptr"]))
+    refset = set(zip(rrows.tolist(), ref["step0_col"].tolist()))
+    assert refset <= mine
+    assert mine_nofill <= refset
+    if name != "temp1":
+        assert mine == refset
+    # symmetric structure, sorted rows, diagonal present
+    assert all(np.all(np.diff(col[rowptr[i]:rowptr[i + 1]]) > 0) for i in range(0, n, 97))
+    import scipy.sparse as sp
+    P = sp.csr_matrix((np.ones(len(col)), col, rowptr), shape=(n, n))
+    assert (P != P.T).nnz == 0 and P.diagonal().min() == 1
+
+
+def test_renumbering_primitives_match_oracle_on_random_graphs():
+    rng = np.random.default_rng(1)
+    for n in (1, 2, 17, 300):
+        # random planar-ish graph: ring + chords, plus an isolated component to exercise the restart
+        edges = [(i, (i + 1) % n) for i in range(n)] if n > 2 else ([(0, 1)] if n == 2 else [])
+        edges += [tuple(rng.integers(0, n, 2)) for _ in range(n // 2)]
+        edges = np.array([e for e in edges if e[0] != e[1]], dtype=np.int32).reshape(-1, 2)
+        newnum, bw = X.renumber_cuthill(n, edges)
+        onew = np.empty(n, dtype=np.int32)
+        obw = C.c_int(0)
+        O.lib().orc_cuthill(n, len(edges), edges.ctypes.data_as(C.c_void_p), onew.ctypes.data_as(C.c_void_p), C.byref(obw))
+        assert np.array_equal(newnum, onew) and bw == obw.value
+        assert sorted(newnum.tolist()) == list(range(n))
+    for ne in (0, 1, 9, 10, 11, 12, 13, 14, 1000):
+        tri = rng.integers(0, 500, (ne, 3)).astype(np.int32)
+        order = X.sort_elements(tri) if ne else np.zeros(0, dtype=np.int32)
+        oorder = np.empty(ne, dtype=np.int32)
+        if ne:
+            O.lib().orc_sort_elements(ne, tri.ctypes.data_as(C.c_void_p), oorder.ctypes.data_as(C.c_void_p))
+        assert np.array_equal(order, oorder)
+
+
+def test_age_cell_matrix_reduced_form_matches_55_closed_forms():
+    lib = X.lib()
+    rng = np.random.default_rng(2)
+    for _ in range(50):
+        ci, co, K = rng.random(), rng.random(), rng.uniform(0.1, 8.0)
+        mine = X.age_cell_matrix(ci, co, K)
+        ref = age_matrix(ci, co, K)
+        assert np.abs(mine - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max())
+
+
+def test_bad_inputs_fail_loudly(tmp_path):
+    with pytest.raises(X.XfemmError):
+        X.FSolver(str(tmp_path / "does_not_exist"))
+    S = X.FSolver(stage_case("tb", tmp_path))
+    os.remove(str(tmp_path / "tb.ele"))
+    with pytest.raises(X.XfemmError):
+        S.load_mesh(False)
+    assert X.fsolver_run(str(tmp_path / "nope")) == 1   # main.cpp: exit code 1 = problem loading .fem
+    with pytest.raises(X.XfemmError):
+        X.pattern_build(3, np.array([[0, 1, 7]], dtype=np.int32))
+
+
+@pytest.mark.skipif(X.device_count() > 0, reason="only meaningful on a box without a GPU")
+def test_no_cpu_fallback(tmp_path):
+    """Without a CUDA device the hot path must refuse to run rather than compute on the CPU."""
+    with pytest.raises(X.XfemmError):
+        X.cuda_init(0)
+    S = X.FSolver(stage_case("tb", tmp_path))
+    S.load_mesh(False)
+    S.renumber(False)
+    with pytest.raises(X.XfemmError):
+        S.solve()
+    rowptr = np.array([0, 1, 2], dtype=np.int32)
+    col = np.array([0, 1], dtype=np.int32)
+    with pytest.raises(X.XfemmError):
+        X.LinProb(rowptr, col)
+    assert X.fsolver_run(stage_case("tb30", tmp_path)) == 2   # main.cpp: exit code 2 = solve failed

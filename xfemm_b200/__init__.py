@@ -78,6 +78,7 @@ SIGNATURES = {
     "xfemm_free": (None, [_P]),
     "xfemm_renumber_cuthill": (C.c_int, [C.c_int, C.c_int, _ip, _ip, C.POINTER(C.c_int)]),
     "xfemm_renumber_sort_elements": (C.c_int, [C.c_int, _ip, _ip]),
+    "xfemm_age_cell_matrix": (C.c_int, [C.c_double, C.c_double, C.c_double, _dp]),
     "xfemm_mag_create": (C.c_int, [_P, _P, C.POINTER(_P)]),
     "xfemm_mag_destroy": (C.c_int, [_P]),
     "xfemm_mag_set_labels": (C.c_int, [_P, C.c_int, _P]),
@@ -149,6 +150,13 @@ def _f64(a):
 
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def age_cell_matrix(ci, co, K):
+    """10x10 air-gap-element cell matrix (static2d.cpp:200-274)."""
+    MG = np.zeros(100, dtype=np.float64)
+    _check(lib().xfemm_age_cell_matrix(ci, co, K, MG), "age_cell_matrix")
+    return MG.reshape(10, 10)
 
 
 def renumber_cuthill(n_nodes, edges):

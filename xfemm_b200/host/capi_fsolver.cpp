@@ -5,7 +5,18 @@
 #include "../../include/xfemm_b200.h"
 #include <cstring>
 
-namespace xb { void set_error(const char *fmt, ...); }
+namespace xb
+{
+void set_error(const char *fmt, ...);
+void age_cell_matrix(double ci, double co, double K, double *MG);
+}
+
+extern "C" int xfemm_age_cell_matrix(double ci, double co, double K, double *MG100)
+{
+    if (!MG100 || K == 0) { xb::set_error("invalid arguments"); return XFEMM_ERR_ARG; }
+    xb::age_cell_matrix(ci, co, K, MG100);
+    return XFEMM_OK;
+}
 
 struct xfemm_fsolver
 {
