@@ -141,7 +141,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mesh-size", type=float, default=0.0018, help="block-label mesh size in cm (0.0018 → ~2M DOF)")
-    ap.add_argument("--precond", default=os.environ.get("XFEMM_PRECOND", "mcssor"), choices=["jacobi", "mcssor"])
+    ap.add_argument("--precond", default=os.environ.get("XFEMM_PRECOND", "jacobi"), choices=["jacobi", "mcssor"])
     ap.add_argument("--ref-iters", type=int, default=40)
     ap.add_argument("--ref-pbc", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -249,6 +249,17 @@ def main():
     elapsed = time.perf_counter() - t0
     sampler.stop_flag = True
     st = S.stats()
+    # the other GPU-parallel preconditioner on the same resident problem, for the record
+    variant = None
+    if rank == 0 and world == 1:
+        other = X.PRECOND_MCSSOR if precond == X.PRECOND_JACOBI else X.PRECOND_JACOBI
+        S.set_option("precond", other)
+        S.resolve()
+        S.resolve()
+        vs = S.stats()
+        variant = {"preconditioner": "mcssor" if other == X.PRECOND_MCSSOR else "jacobi", "iterations": sum(vs["iters"]),
+                   "pcg_ms": sum(vs["solve_ms"]), "relres": vs["relres"]}
+        S.set_option("precond", precond)
     if world > 1:
         t = torch.tensor([elapsed], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -287,6 +298,7 @@ def main():
                      "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "bytes_per_iter": bytes_iter},
         "e2e": {"value": e2e, "unit": "s/problem", "h2d_bytes_per_step": int(h2d.value), "d2h_bytes_per_step": int(d2h.value)},
+        "variant": variant,
         "host_setup_s": {"load_mesh": t_load, "cuthill": t_cm},
         "gpu_launches": int(X.lib().xfemm_launch_count()) if hasattr(X.lib(), "xfemm_launch_count") else None,
         "clocks": sampler.summary(),

@@ -143,7 +143,9 @@ typedef struct xfemm_mag_label
     double mu1_im, mu2_im;  /* imaginary parts of the complex permeabilities                  */
     double sigma;           /* conductivity seen by the eddy term [MS/m]                      */
     double Jsrc_im;
-    int circuit;            /* index of the circuit unknown row (harmonic Case 0), or -1       */
+    double dVs;             /* axisymmetric: circuit voltage-gradient source = dVs / R_element
+                               (-100 dV sigma, staticaxi.cpp:338-339); 0 otherwise              */
+    int circuit;           /* index of the circuit unknown row (harmonic Case 0), or -1       */
     int pad_;
 } xfemm_mag_label;
 

@@ -75,7 +75,82 @@ def case_temp1(tmp):
     return "temp1"
 
 
-CASES = {"tb": case_tb, "tb30": case_tb30, "temp1": case_temp1}
+# ---------------------------------------------------------------------------------------------
+# authored fixtures (the reference ships no axisymmetric, harmonic or strongly saturated case)
+# ---------------------------------------------------------------------------------------------
+STEEL_BH = [(0, 0), (0.7004, 238.7325), (1.351, 795.775), (1.624, 3183.1), (1.77, 7957.75), (2, 31831),
+            (2.13, 79577.5), (2.25, 159155), (2.46, 318310)]  # 1117 steel of cfemm/fsolver/test/Temp1.fem
+
+
+def fem_text(problemtype, frequency, precision, bdrys, blocks, circuits, points, segments, arcs, labels, units="centimeters",
+             acsolver=0):
+    L = ["[Format]      =  4.0", f"[Frequency]   =  {frequency}", f"[Precision]   =  {precision}", "[MinAngle]    =  30",
+         "[DoSmartMesh] =  1", "[Depth]       =  1", f"[LengthUnits] =  {units}", f"[ProblemType] =  {problemtype}",
+         "[Coordinates] =  cartesian", f"[ACSolver]    =  {acsolver}", "[PrevType]    =  0", '[PrevSoln]    =  ""',
+         '[Comment]     =  "authored fixture"', "[PointProps]   = 0", f"[BdryProps]   = {len(bdrys)}"]
+    for b in bdrys:
+        d = {"BdryType": 0, "A_0": 0, "A_1": 0, "A_2": 0, "Phi": 0, "c0": 0, "c0i": 0, "c1": 0, "c1i": 0, "Mu_ssd": 0,
+             "Sigma_ssd": 0, "innerangle": 0, "outerangle": 0}
+        d.update(b)
+        L += ["  <BeginBdry>", f'    <BdryName> = "{d.pop("name")}"'] + [f"    <{k}> = {v}" for k, v in d.items()] + ["  <EndBdry>"]
+    L.append(f"[BlockProps]  = {len(blocks)}")
+    for b in blocks:
+        d = {"Mu_x": 1, "Mu_y": 1, "H_c": 0, "H_cAngle": 0, "J_re": 0, "J_im": 0, "Sigma": 0, "d_lam": 0, "Phi_h": 0,
+             "Phi_hx": 0, "Phi_hy": 0, "LamType": 0, "LamFill": 1, "NStrands": 0, "WireD": 0}
+        bh = b.get("bh", [])
+        d.update({k: v for k, v in b.items() if k not in ("name", "bh")})
+        L += ["  <BeginBlock>", f'    <BlockName> = "{b["name"]}"'] + [f"    <{k}> = {v}" for k, v in d.items()]
+        L.append(f"    <BHPoints> = {len(bh)}")
+        L += [f"      {x!r}\t{y!r}" for x, y in bh]
+        L.append("  <EndBlock>")
+    L.append(f"[CircuitProps]  = {len(circuits)}")
+    for c in circuits:
+        L += ["  <BeginCircuit>", f'    <CircuitName> = "{c["name"]}"', f"    <TotalAmps_re> = {c.get('amps', 0)}",
+              f"    <TotalAmps_im> = {c.get('amps_im', 0)}", f"    <CircuitType> = {c.get('type', 1)}", "  <EndCircuit>"]
+    L.append(f"[NumPoints] = {len(points)}")
+    L += [f"{x!r}\t{y!r}\t0\t0" for x, y in points]
+    L.append(f"[NumSegments] = {len(segments)}")
+    L += [f"{a}\t{b}\t-1\t{bd}\t0\t0" for a, b, bd in segments]
+    L.append(f"[NumArcSegments] = {len(arcs)}")
+    L += [f"{a}\t{b}\t{ang}\t{seg}\t{bd}\t0\t0\t{seg}" for a, b, ang, seg, bd in arcs]
+    L.append("[NumHoles] = 0")
+    L.append(f"[NumBlockLabels] = {len(labels)}")
+    L += [f"{x!r}\t{y!r}\t{blk}\t{size!r}\t{circ}\t{magdir}\t0\t{turns}\t{ext}" for x, y, blk, size, circ, magdir, turns, ext in labels]
+    return "\n".join(L) + "\n"
+
+
+def solenoid(problemtype, frequency, precision, mesh=0.25, amps=25, steel_extra=None, coil_sigma=0, magnet_sigma=0, acsolver=0):
+    """Solenoid with a saturating 1117-steel plunger on the axis, a series-connected 200-turn coil and
+    a magnet ring, inside a half disc of radius 10 cm with A=0 on the arc (cross-section in r>=0)."""
+    steel = {"name": "1117 Steel", "Mu_x": 1777, "Mu_y": 1777, "bh": STEEL_BH}
+    steel.update(steel_extra or {})
+    blocks = [{"name": "Air"}, {"name": "Coil", "Sigma": coil_sigma}, steel,
+              {"name": "Magnet", "Mu_x": 1.049, "Mu_y": 1.049, "H_c": 979000, "Sigma": magnet_sigma}]
+    pts = [(0.0, -10.0), (0.0, 10.0), (1.0, -2.0), (2.0, -2.0), (2.0, 2.0), (1.0, 2.0), (0.0, -1.0), (0.8, -1.0), (0.8, 3.0),
+           (0.0, 3.0), (3.0, -0.5), (4.0, -0.5), (4.0, 0.5), (3.0, 0.5)]
+    segs = [(0, 6, 0), (6, 9, 0), (9, 1, 0), (2, 3, 0), (3, 4, 0), (4, 5, 0), (5, 2, 0), (6, 7, 0), (7, 8, 0), (8, 9, 0),
+            (10, 11, 0), (11, 12, 0), (12, 13, 0), (13, 10, 0)]
+    arcs = [(0, 1, 180, 5, 1)]
+    labels = [(5.0, 5.0, 1, 4 * mesh, 0, 0, 1, 0), (1.5, 0.0, 2, mesh, 1, 0, 200, 0), (0.4, 1.0, 3, mesh, 0, 0, 1, 0),
+              (3.5, 0.0, 4, mesh, 0, 90, 1, 0)]
+    return fem_text(problemtype, frequency, precision, [{"name": "A=0", "BdryType": 0}], blocks,
+                    [{"name": "coil", "amps": amps, "type": 1}], pts, segs, arcs, labels, acsolver=acsolver)
+
+
+def case_axi1(tmp):
+    """config 4 stand-in: StaticAxisymmetric, nodes on the r=0 axis, series circuit, magnet, B-H steel (Newton)."""
+    _write_fem(os.path.join(tmp, "axi1.fem"), solenoid("axisymmetric", 0, "1e-08", amps=400))
+    return "axi1"
+
+
+def case_sat2d(tmp):
+    """config 3 stand-in: the same cross-section solved as a planar problem — strongly saturated
+    steel, several Newton steps, parallel circuit with a bulk conductor (Case 0 voltage gradient)."""
+    _write_fem(os.path.join(tmp, "sat2d.fem"), solenoid("planar", 0, "1e-08", coil_sigma=58, amps=2000))
+    return "sat2d"
+
+
+CASES = {"tb": case_tb, "tb30": case_tb30, "temp1": case_temp1, "axi1": case_axi1, "sat2d": case_sat2d}
 
 
 def run_case(name):

@@ -34,7 +34,7 @@ class MagLabel(C.Structure):
     _fields_ = [("mu1", C.c_double), ("mu2", C.c_double), ("Jsrc", C.c_double), ("H_c", C.c_double),
                 ("magdir", C.c_double), ("lamfill", C.c_double), ("lamtype", C.c_int), ("bh_offset", C.c_int),
                 ("bh_points", C.c_int), ("is_external", C.c_int), ("mu1_im", C.c_double), ("mu2_im", C.c_double),
-                ("sigma", C.c_double), ("Jsrc_im", C.c_double), ("circuit", C.c_int), ("pad_", C.c_int)]
+                ("sigma", C.c_double), ("Jsrc_im", C.c_double), ("dVs", C.c_double), ("circuit", C.c_int), ("pad_", C.c_int)]
 
 
 _P = C.c_void_p

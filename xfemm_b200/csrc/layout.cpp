@@ -9,30 +9,38 @@
 
 namespace xb {
 
-// Greedy distance-1 colouring in the caller's (Cuthill–McKee) row order.
-int greedy_coloring(int n, const int *rowptr, const int *col, std::vector<int> &color)
+// Greedy distance-1 colouring in the caller's (Cuthill–McKee) row order with a cap on the
+// number of colours.  A first-order triangulation needs 5-7 colours; the few rows that carry
+// air-gap-element 10-cliques or periodic fill would push a plain greedy colouring to 12-13 and
+// every extra colour costs two grid-wide barriers per preconditioner application.  When a row
+// finds all `max_colors` colours taken it joins the colour with the fewest clashes; the clashing
+// couplings are reported by the layout as "extra" entries: they stay in the matrix (SpMV) but
+// are left out of the SSOR sweeps, i.e. the preconditioner is the multicolour SSOR of the matrix
+// without those couplings — still symmetric positive definite for any positive diagonal.
+int greedy_coloring(int n, const int *rowptr, const int *col, int max_colors, std::vector<int> &color)
 {
     color.assign(n, -1);
     int ncol = 0;
-    std::vector<int> mark(64, -1);
+    if (max_colors < 2) max_colors = 2;
+    std::vector<int> cnt(max_colors, 0);
     for (int i = 0; i < n; i++)
     {
+        std::fill(cnt.begin(), cnt.end(), 0);
         for (int s = rowptr[i]; s < rowptr[i + 1]; s++)
         {
             int j = col[s];
             if (j == i) continue;
             int c = color[j];
-            if (c >= 0)
-            {
-                if (c >= (int)mark.size()) mark.resize(2 * c + 2, -1);
-                mark[c] = i;
-            }
+            if (c >= 0) cnt[c]++;
         }
-        int c = 0;
-        while (c < (int)mark.size() && mark[c] == i) c++;
-        if (c >= (int)mark.size()) mark.resize(2 * c + 2, -1);
-        color[i] = c;
-        if (c + 1 > ncol) ncol = c + 1;
+        int best = 0;
+        for (int c = 0; c < max_colors; c++)
+        {
+            if (cnt[c] == 0) { best = c; break; }
+            if (cnt[c] < cnt[best]) best = c;
+        }
+        color[i] = best;
+        if (best + 1 > ncol) ncol = best + 1;
     }
     return ncol;
 }
@@ -41,11 +49,12 @@ void build_sell_layout(int n, const int *rowptr, const int *col, const std::vect
                        int ncolors, int sigma, SellLayout &L)
 {
     // ---- internal order: by colour (if any), inside a colour keep the caller's order, then
-    // sort windows of `sigma` rows by (lower count, upper count) so slices are homogeneous.
+    // sort windows of `sigma` rows by their entry counts so slices are homogeneous.
     std::vector<int> order(n);
     std::iota(order.begin(), order.end(), 0);
     std::vector<int> color_start; // in rows (unpadded sequence positions)
-    if (color_in && ncolors > 0)
+    const bool colored = color_in && ncolors > 0;
+    if (colored)
     {
         const std::vector<int> &color = *color_in;
         std::vector<int> cnt(ncolors + 1, 0);
@@ -62,46 +71,39 @@ void build_sell_layout(int n, const int *rowptr, const int *col, const std::vect
     }
     const int ngroups = (int)color_start.size() - 1;
 
-    // provisional internal index (without padding) to classify lower/upper entries
-    // lower = neighbour placed earlier in the internal order.  With colours this is exactly
-    // "neighbour has a lower colour" because a colour class has no internal couplings.
+    // classification of an off-diagonal (i,j): 0 lower (j earlier in the internal order = lower
+    // colour), 1 upper, 2 extra (same colour: excluded from the SSOR sweeps).  Sorting inside a
+    // window only permutes rows of one colour, so for coloured layouts the class never depends
+    // on the final position; for the uncoloured layout lower/upper is merely a storage split
+    // and is evaluated on the final order below.
+    auto klass = [&](int i, int j, const std::vector<int> &rank) -> int {
+        if (colored)
+        {
+            int ci = (*color_in)[i], cj = (*color_in)[j];
+            if (ci == cj) return 2;
+            return cj < ci ? 0 : 1;
+        }
+        return rank[j] < rank[i] ? 0 : 1;
+    };
     std::vector<int> rank(n);
     for (int k = 0; k < n; k++) rank[order[k]] = k;
-    std::vector<unsigned char> nlow(n), nup(n);
-    for (int i = 0; i < n; i++)
-    {
-        int lo = 0, up = 0;
-        for (int s = rowptr[i]; s < rowptr[i + 1]; s++)
-        {
-            int j = col[s];
-            if (j == i) continue;
-            if (rank[j] < rank[i]) lo++; else up++;
-        }
-        nlow[i] = (unsigned char)std::min(lo, 255);
-        nup[i] = (unsigned char)std::min(up, 255);
-    }
-    // NOTE: sorting inside a window changes ranks inside the window; for the colour layout
-    // this never flips lower/upper (same colour ⇒ not coupled).  For the uncoloured layout
-    // lower/upper is only a storage split (SpMV uses both halves), so a flip is harmless as
-    // long as the classification used for storage is the final one → recompute after sorting.
     if (sigma > 1)
     {
-        for (int g = 0; g < ngroups; g++)
+        std::vector<int> key(n);
+        for (int i = 0; i < n; i++)
         {
+            int c[3] = {0, 0, 0};
+            for (int s = rowptr[i]; s < rowptr[i + 1]; s++)
+                if (col[s] != i) c[klass(i, col[s], rank)]++;
+            key[i] = colored ? (std::min(c[0], 63) * 64 + std::min(c[1], 63)) * 64 + std::min(c[2], 63)
+                             : (rowptr[i + 1] - rowptr[i]);
+        }
+        for (int g = 0; g < ngroups; g++)
             for (int w0 = color_start[g]; w0 < color_start[g + 1]; w0 += sigma)
             {
                 int w1 = std::min(w0 + sigma, color_start[g + 1]);
-                std::stable_sort(order.begin() + w0, order.begin() + w1, [&](int a, int b) {
-                    int ka = (rowptr[a + 1] - rowptr[a]), kb = (rowptr[b + 1] - rowptr[b]);
-                    if (ncolors > 0)
-                    {
-                        ka = nlow[a] * 256 + nup[a];
-                        kb = nlow[b] * 256 + nup[b];
-                    }
-                    return ka > kb;
-                });
+                std::stable_sort(order.begin() + w0, order.begin() + w1, [&](int a, int b) { return key[a] > key[b]; });
             }
-        }
     }
 
     // ---- padded internal numbering: every colour starts on a slice boundary
@@ -119,39 +121,40 @@ void build_sell_layout(int n, const int *rowptr, const int *col, const std::vect
     L.c2i.assign(n, -1);
     for (int r = 0; r < L.n_pad; r++) if (L.i2c[r] >= 0) L.c2i[L.i2c[r]] = r;
 
-    // ---- split SELL: per slice [lower block | upper block], diagonal kept apart
+    // ---- split SELL: per slice [lower | upper | extra] blocks, diagonal kept apart
     L.slice_ptr.assign(L.nslices + 1, 0);
     L.slice_wl.assign(L.nslices, 0);
-    std::vector<int> lo_cnt(L.n_pad, 0), up_cnt(L.n_pad, 0);
+    L.slice_wu.assign(L.nslices, 0);
+    L.n_extra = 0;
+    std::vector<std::pair<int, int>> part[3]; // (internal col, csr index)
+    std::vector<int> width(3 * (size_t)L.nslices, 0);
     for (int r = 0; r < L.n_pad; r++)
     {
         int i = L.i2c[r];
         if (i < 0) continue;
+        int c[3] = {0, 0, 0};
         for (int s = rowptr[i]; s < rowptr[i + 1]; s++)
-        {
-            int j = col[s];
-            if (j == i) continue;
-            if (L.c2i[j] < r) lo_cnt[r]++; else up_cnt[r]++;
-        }
+            if (col[s] != i) c[klass(i, col[s], L.c2i)]++;
+        L.n_extra += c[2];
+        for (int q = 0; q < 3; q++) width[3 * (size_t)(r / 32) + q] = std::max(width[3 * (size_t)(r / 32) + q], c[q]);
     }
     long long total = 0;
     for (int s = 0; s < L.nslices; s++)
     {
-        int wl = 0, wu = 0;
-        for (int l = 0; l < 32; l++) { wl = std::max(wl, lo_cnt[s * 32 + l]); wu = std::max(wu, up_cnt[s * 32 + l]); }
-        L.slice_wl[s] = wl;
+        L.slice_wl[s] = width[3 * (size_t)s];
+        L.slice_wu[s] = width[3 * (size_t)s + 1];
         L.slice_ptr[s] = (int)total;
-        total += (long long)(wl + wu) * 32;
+        total += (long long)(width[3 * (size_t)s] + width[3 * (size_t)s + 1] + width[3 * (size_t)s + 2]) * 32;
     }
     L.slice_ptr[L.nslices] = (int)total;
     L.sell_len = total;
     L.sell_col.assign(total, 0);
     L.sell_src.assign(total, -1);
     L.diag_src.assign(L.n_pad, -1);
-    std::vector<std::pair<int, int>> lo, up; // (internal col, csr index)
     for (int s = 0; s < L.nslices; s++)
     {
-        const int base = L.slice_ptr[s], wl = L.slice_wl[s];
+        const int base = L.slice_ptr[s];
+        const int off[3] = {0, L.slice_wl[s], L.slice_wl[s] + L.slice_wu[s]};
         const int w = (L.slice_ptr[s + 1] - base) / 32;
         for (int l = 0; l < 32; l++)
         {
@@ -159,25 +162,21 @@ void build_sell_layout(int n, const int *rowptr, const int *col, const std::vect
             for (int k = 0; k < w; k++) L.sell_col[base + k * 32 + l] = r; // padding points at self
             int i = L.i2c[r];
             if (i < 0) continue;
-            lo.clear(); up.clear();
+            for (auto &p : part) p.clear();
             for (int q = rowptr[i]; q < rowptr[i + 1]; q++)
             {
                 int j = col[q];
                 if (j == i) { L.diag_src[r] = q; continue; }
-                int jc = L.c2i[j];
-                if (jc < r) lo.emplace_back(jc, q); else up.emplace_back(jc, q);
+                part[klass(i, j, L.c2i)].emplace_back(L.c2i[j], q);
             }
-            std::sort(lo.begin(), lo.end());
-            std::sort(up.begin(), up.end());
-            for (size_t k = 0; k < lo.size(); k++)
+            for (int t = 0; t < 3; t++)
             {
-                L.sell_col[base + (int)k * 32 + l] = lo[k].first;
-                L.sell_src[base + (int)k * 32 + l] = lo[k].second;
-            }
-            for (size_t k = 0; k < up.size(); k++)
-            {
-                L.sell_col[base + (wl + (int)k) * 32 + l] = up[k].first;
-                L.sell_src[base + (wl + (int)k) * 32 + l] = up[k].second;
+                std::sort(part[t].begin(), part[t].end());
+                for (size_t k = 0; k < part[t].size(); k++)
+                {
+                    L.sell_col[base + (off[t] + (int)k) * 32 + l] = part[t][k].first;
+                    L.sell_src[base + (off[t] + (int)k) * 32 + l] = part[t][k].second;
+                }
             }
         }
     }

@@ -8,17 +8,19 @@ struct SellLayout
 {
     int n_pad = 0, nslices = 0, ncolors = 0;
     long long sell_len = 0;
+    long long n_extra = 0;        // couplings excluded from the SSOR sweeps (same-colour clashes)
     std::vector<int> i2c;         // internal row -> caller row (-1 = padding row)
     std::vector<int> c2i;         // caller row -> internal row
     std::vector<int> color_slice; // first slice of each colour (ncolors+1), or {0,nslices}
     std::vector<int> slice_ptr;   // nslices+1, offsets into sell_* (multiples of 32)
     std::vector<int> slice_wl;    // width of the "lower" block of each slice
+    std::vector<int> slice_wu;    // width of the "upper" block (then the "extra" block to the end)
     std::vector<int> sell_col;    // internal column per slot (padding: own row)
     std::vector<int> sell_src;    // CSR index per slot (-1 padding)
     std::vector<int> diag_src;    // CSR index of the diagonal per internal row (-1 padding row)
 };
 
-int greedy_coloring(int n, const int *rowptr, const int *col, std::vector<int> &color);
+int greedy_coloring(int n, const int *rowptr, const int *col, int max_colors, std::vector<int> &color);
 void build_sell_layout(int n, const int *rowptr, const int *col, const std::vector<int> *color,
                        int ncolors, int sigma, SellLayout &L);
 

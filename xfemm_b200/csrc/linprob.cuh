@@ -33,9 +33,9 @@ struct xfemm_linprob
     // solver representation
     xb::SellLayout lay;            // host copy (small vectors kept; big ones cleared after upload)
     int layout_precond = -1;       // preconditioner the current layout was built for
-    xb::DevBuf<int> i2c, c2i, slice_ptr, slice_wl, sell_col, sell_src, diag_src;
+    xb::DevBuf<int> i2c, c2i, slice_ptr, slice_wl, slice_wu, sell_col, sell_src, diag_src;
     xb::DevBuf<double> sell_val, diag, dinv;
-    xb::DevBuf<double> x, r, p, u, z, bint;
+    xb::DevBuf<double> x, r, p, u, z, w, bint;
     xb::DevBuf<double> partials;   // 2 * max_grid
     xb::DevBuf<int> color_slice;
     int max_grid = 0;

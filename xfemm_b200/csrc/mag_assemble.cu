@@ -248,10 +248,197 @@ k_assemble_static2d(int ne, int iter, const int4 *__restrict__ tri, const double
     }
 }
 
-// mixed (Robin) boundary edges, BdryFormat==2 (static2d.cpp:460-480)
+// ---------------------------------------------------------------------------------------
+// axisymmetric magnetostatic element (staticaxi.cpp:169-633): r-weighted matrices with the
+// a_hat / R_hat (log-mean radius) terms, special cases for nodes on the axis, B from the element
+// energy, conformally mapped external region.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_assemble_staticaxi(int ne, int iter, const int4 *__restrict__ tri, const double2 *__restrict__ xy,
+                     const int *__restrict__ emap, const xfemm_mag_label *__restrict__ labels,
+                     const double *__restrict__ magdir_elem, const double *__restrict__ bhB,
+                     const double *__restrict__ bhH, const double *__restrict__ bhS,
+                     const double *__restrict__ V, double *vals, double *b, double2 *mu_out,
+                     double ext_zo, double ext_ro, double ext_ri)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ne) return;
+    const double c = XB_PI * 4.e-05;
+    const int4 t4 = tri[e];
+    const int n[3] = {t4.x, t4.y, t4.z};
+    const double2 P0 = xy[n[0]], P1 = xy[n[1]], P2 = xy[n[2]];
+    const double X[3] = {P0.x, P1.x, P2.x}, Y[3] = {P0.y, P1.y, P2.y};
+    const double rn[3] = {P0.x, P1.x, P2.x};
+    const double p[3] = {P1.y - P2.y, P2.y - P0.y, P0.y - P1.y};
+    const double q[3] = {P2.x - P1.x, P0.x - P2.x, P1.x - P0.x};
+    const double g[3] = {(P2.x + P1.x) / 2., (P0.x + P2.x) / 2., (P1.x + P0.x) / 2.};
+    const double a = (p[0] * q[1] - p[1] * q[0]) / 2.;
+    const double R = (P0.x + P1.x + P2.x) / 3.;
+    double a_hat = 0;
+#pragma unroll
+    for (int j = 0; j < 3; j++) a_hat += (rn[j] * rn[j] * p[j] / (4. * R));
+    const double vol = 2. * R * a_hat;
+    int flag = 0;
+#pragma unroll
+    for (int j = 0; j < 3; j++) if (rn[j] < 1.e-06) flag++;
+    double R_hat = 0.;
+    if (flag == 2) R_hat = R;
+    else if (flag == 1)
+    {
+        // staticaxi.cpp:226-244 (one node on the axis)
+        if (rn[0] < 1.e-06) R_hat = (fabs(rn[1] - rn[2]) < 1.e-06) ? rn[2] / 2. : (rn[1] - rn[2]) / (2. * log(rn[1]) - 2. * log(rn[2]));
+        if (rn[1] < 1.e-06) R_hat = (fabs(rn[2] - rn[0]) < 1.e-06) ? rn[0] / 2. : (rn[2] - rn[0]) / (2. * log(rn[2]) - 2. * log(rn[0]));
+        if (rn[2] < 1.e-06) R_hat = (fabs(rn[0] - rn[1]) < 1.e-06) ? rn[1] / 2. : (rn[0] - rn[1]) / (2. * log(rn[0]) - 2. * log(rn[1]));
+    }
+    else
+    {
+        if (fabs(q[0]) < 1.e-06) R_hat = (q[1] * q[1]) / (2. * (-q[1] + rn[0] * log(rn[0] / rn[2])));
+        else if (fabs(q[1]) < 1.e-06) R_hat = (q[2] * q[2]) / (2. * (-q[2] + rn[1] * log(rn[1] / rn[0])));
+        else if (fabs(q[2]) < 1.e-06) R_hat = (q[0] * q[0]) / (2. * (-q[0] + rn[2] * log(rn[2] / rn[1])));
+        else R_hat = -(q[0] * q[1] * q[2]) / (2. * (q[0] * rn[0] * log(rn[0]) + q[1] * rn[1] * log(rn[1]) + q[2] * rn[2] * log(rn[2])));
+    }
+    const xfemm_mag_label L = labels[t4.w];
+    double Mx[3][3], My[3][3], Mn[3][3], be[3];
+    const double Kx = (-1. / (2. * a_hat * R)), Ky = (-1. / (2. * a_hat * R_hat));
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+        {
+            Mx[j][k] = Kx * p[j] * rn[j] * p[k] * rn[k];
+            My[j][k] = Ky * (q[j] * rn[j]) * (q[k] * rn[k]) * (g[j] / R) * (g[k] / R);
+            Mn[j][k] = 0.;
+        }
+    {
+        // nodes on the r=0 line get the trace on their diagonal (staticaxi.cpp:276-277; the loop
+        // runs in order, so a later node sees the already patched entries)
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+            if (rn[j] < 1.e-06) Mx[j][j] += Mx[0][0] + Mx[1][1] + Mx[2][2];
+    }
+    // source current density (staticaxi.cpp:332-348): circuit voltage term carries 1/R
+    const double Jel = L.Jsrc + L.dVs / R;
+#pragma unroll
+    for (int j = 0; j < 3; j++) be[j] = -2. * R * Jel * a / 3.;
+    if (L.H_c != 0.)
+    {
+        const double th = (magdir_elem ? magdir_elem[e] : L.magdir) * XB_PI / 180.;
+        const double cs = cos(th), sn = sin(th);
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+        {
+            const int k = (j + 1) % 3;
+            const double r = (X[j] + X[k]) / 2.;
+            const double Km = -0.0001 * r * L.H_c * (cs * (X[k] - X[j]) + sn * (Y[k] - Y[j]));
+            be[j] += Km;
+            be[k] += Km;
+        }
+    }
+    double mu1 = L.mu1, mu2 = L.mu2;
+    if (L.is_external)
+    {
+        // conformally mapped exterior (staticaxi.cpp:611-617): applied at Iter 0 and kept
+        const double Z = (Y[0] + Y[1] + Y[2]) / 3. - ext_zo;
+        const double kludge = (R * R + Z * Z) * ext_ri / (ext_ro * ext_ro * ext_ro);
+        mu1 /= kludge;
+        mu2 /= kludge;
+    }
+    double Vn[3] = {0., 0., 0.};
+    if (iter > 0 && L.bh_points > 0)
+    {
+        Vn[0] = V[n[0]]; Vn[1] = V[n[1]]; Vn[2] = V[n[2]];
+        const double *Bd = bhB + L.bh_offset, *Hd = bhH + L.bh_offset, *Sd = bhS + L.bh_offset;
+        const double tt = L.lamfill;
+        double v[3], u[3], nu, dv = 0;
+        // B from the element energy (staticaxi.cpp:511-520 / 542-552 / 575-585)
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+        {
+            v[j] = 0;
+#pragma unroll
+            for (int w = 0; w < 3; w++)
+            {
+                double m = Mx[j][w] + My[j][w];
+                if (L.lamtype == 1) m = Mx[j][w] + My[j][w] / (tt * tt);
+                if (L.lamtype == 2) m = Mx[j][w] / (tt * tt) + My[j][w];
+                v[j] += m * Vn[w];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 3; j++) dv += Vn[j] * v[j];
+        dv *= (10000. * c * c / vol);
+        const double B = sqrt(fabs(dv));
+        if (L.lamtype <= 2)
+        {
+            bh_props(Bd, Hd, Sd, L.bh_points, L.mu1, B, nu, dv);
+            const double mu = 1. / (XB_MUO * nu);
+            if (L.lamtype == 0)
+            {
+                mu1 = mu; mu2 = mu;
+                const double Kn = -200. * c * c * c * dv / vol;
+#pragma unroll
+                for (int j = 0; j < 3; j++)
+                {
+                    v[j] = 0;
+#pragma unroll
+                    for (int w = 0; w < 3; w++) v[j] += (Mx[j][w] + My[j][w]) * Vn[w];
+                }
+#pragma unroll
+                for (int j = 0; j < 3; j++)
+#pragma unroll
+                    for (int w = 0; w < 3; w++) Mn[j][w] = Kn * v[j] * v[w];
+            }
+            else
+            {
+                if (L.lamtype == 1) { mu1 = mu * tt; mu2 = mu / (tt + mu * (1. - tt)); }
+                else { mu2 = mu * tt; mu1 = mu / (tt + mu * (1. - tt)); }
+#pragma unroll
+                for (int j = 0; j < 3; j++)
+                {
+                    v[j] = 0; u[j] = 0;
+#pragma unroll
+                    for (int w = 0; w < 3; w++)
+                    {
+                        if (L.lamtype == 1)
+                        {
+                            v[j] += (My[j][w] / tt + Mx[j][w]) * Vn[w];
+                            u[j] += (My[j][w] / tt + tt * Mx[j][w]) * Vn[w];
+                        }
+                        else
+                        {
+                            v[j] += (Mx[j][w] / tt + My[j][w]) * Vn[w];
+                            u[j] += (Mx[j][w] / tt + tt * My[j][w]) * Vn[w];
+                        }
+                    }
+                }
+                const double Kn = -100. * c * c * c * dv / vol;
+#pragma unroll
+                for (int j = 0; j < 3; j++)
+#pragma unroll
+                    for (int w = 0; w < 3; w++) Mn[j][w] = Kn * (v[j] * u[w] + v[w] * u[j]);
+            }
+        }
+    }
+    if (mu_out) mu_out[e] = make_double2(mu1, mu2);
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+    {
+        double bj = be[j];
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+        {
+            const double me = Mx[j][k] / mu2 + My[j][k] / mu1 + Mn[j][k];
+            bj += Mn[j][k] * Vn[k];
+            atomicAdd(vals + emap[(size_t)(3 * j + k) * ne + e], -me);
+        }
+        atomicAdd(b + n[j], -bj);
+    }
+}
+
+// mixed (Robin) boundary edges, BdryFormat==2 (static2d.cpp:460-480; staticaxi.cpp:308-329 adds 2r)
 __global__ void k_mixed_edges(int nm, int ne, const int *__restrict__ es, const double *__restrict__ c01,
                               const int4 *__restrict__ tri, const double2 *__restrict__ xy,
-                              const int *__restrict__ emap, double *vals, double *b)
+                              const int *__restrict__ emap, double *vals, double *b, int axi)
 {
     int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= nm) return;
@@ -261,12 +448,13 @@ __global__ void k_mixed_edges(int nm, int ne, const int *__restrict__ es, const 
     const int n[3] = {t.x, t.y, t.z};
     const double2 A = xy[n[j]], B = xy[n[k]];
     const double l = sqrt((B.x - A.x) * (B.x - A.x) + (B.y - A.y) * (B.y - A.y));
-    const double K = -0.0001 * c * c01[2 * m] * l / 6.;
+    const double rfac = axi ? 2. * ((A.x + B.x) / 2.) : 1.;
+    const double K = axi ? -0.0001 * c * rfac * c01[2 * m] * l / 6. : -0.0001 * c * c01[2 * m] * l / 6.;
     atomicAdd(vals + emap[(size_t)(3 * j + j) * ne + e], -(K * 2.));
     atomicAdd(vals + emap[(size_t)(3 * k + k) * ne + e], -(K * 2.));
     atomicAdd(vals + emap[(size_t)(3 * j + k) * ne + e], -K);
     atomicAdd(vals + emap[(size_t)(3 * k + j) * ne + e], -K);
-    const double K2 = (c01[2 * m + 1] * l / 2.) * 0.0001;
+    const double K2 = axi ? (c01[2 * m + 1] * l / 2.) * 0.0001 * rfac : (c01[2 * m + 1] * l / 2.) * 0.0001;
     atomicAdd(b + n[j], -K2);
     atomicAdd(b + n[k], -K2);
 }
@@ -428,7 +616,6 @@ int xfemm_mag_destroy(xfemm_mag *m)
 int xfemm_mag_assemble_static(xfemm_mag *m, int iter, double *elapsed_ms)
 {
     XB_ARG(m && m->lin, "null handle");
-    XB_ARG(!m->axisymmetric, "axisymmetric assembly is not available in this build");
     xfemm_linprob *L = m->lin;
     cudaStream_t st = L->stream;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -443,13 +630,19 @@ int xfemm_mag_assemble_static(xfemm_mag *m, int iter, double *elapsed_ms)
         ++xb::g_launch, k_age_scatter<<<(nt + 127) / 128, 128, 0, st>>>(m->n_age_cells, m->age_nodes.p, m->age_w.p, m->age_mid.p,
                                                         m->age_mats.p, L->rowptr.p, L->col.p, L->vals.p, 1.0, m->err_flag.p);
     }
-    ++xb::g_launch, k_assemble_static2d<<<(m->n_elems + 255) / 256, 256, 0, st>>>(
-        m->n_elems, iter, (const int4 *)m->tri.p, (const double2 *)m->xy.p, m->emap.p, m->labels.p,
-        m->magdir.n ? m->magdir.p : nullptr, m->bhB.p, m->bhH.p, m->bhS.p, L->V.p, L->vals.p, L->b.p, (double2 *)m->mu.p);
+    if (m->axisymmetric)
+        ++xb::g_launch, k_assemble_staticaxi<<<(m->n_elems + 255) / 256, 256, 0, st>>>(
+            m->n_elems, iter, (const int4 *)m->tri.p, (const double2 *)m->xy.p, m->emap.p, m->labels.p,
+            m->magdir.n ? m->magdir.p : nullptr, m->bhB.p, m->bhH.p, m->bhS.p, L->V.p, L->vals.p, L->b.p,
+            (double2 *)m->mu.p, m->ext_zo, m->ext_ro, m->ext_ri);
+    else
+        ++xb::g_launch, k_assemble_static2d<<<(m->n_elems + 255) / 256, 256, 0, st>>>(
+            m->n_elems, iter, (const int4 *)m->tri.p, (const double2 *)m->xy.p, m->emap.p, m->labels.p,
+            m->magdir.n ? m->magdir.p : nullptr, m->bhB.p, m->bhH.p, m->bhS.p, L->V.p, L->vals.p, L->b.p, (double2 *)m->mu.p);
     if (m->n_mixed > 0)
         ++xb::g_launch, k_mixed_edges<<<(m->n_mixed + 127) / 128, 128, 0, st>>>(m->n_mixed, m->n_elems, m->mixed_es.p, m->mixed_c.p,
                                                                 (const int4 *)m->tri.p, (const double2 *)m->xy.p,
-                                                                m->emap.p, L->vals.p, L->b.p);
+                                                                m->emap.p, L->vals.p, L->b.p, m->axisymmetric);
     if (m->n_psrc > 0)
         ++xb::g_launch, k_point_sources<<<(m->n_psrc + 127) / 128, 128, 0, st>>>(m->n_psrc, m->psrc_node.p, m->psrc_val.p, L->b.p);
     int flag = 0;

@@ -313,11 +313,6 @@ int FSolver::staticSolve(CBigLinProb &L, bool axi)
         WarnMessage("xfemm_b200: no CUDA device available (this backend has no CPU solve path)\n");
         return false;
     }
-    if (axi)
-    {
-        WarnMessage("xfemm_b200: axisymmetric magnetostatics is not available in this build\n");
-        return false;
-    }
     for (int i = 0; i < NumBlockLabels; i++) GetFillFactor(i);
     for (int i = 0; i < NumBlockLabels; i++)
         if (!labellist[i].MagDirFctn.empty())
@@ -345,7 +340,9 @@ int FSolver::staticSolve(CBigLinProb &L, bool axi)
             double Cduct = blockproplist[El.blk].Cduct;
             if (labellist[El.lbl].bIsWound) Cduct = 0;
             I1[ic] += a;
-            I2[ic] += a * Cduct;
+            // staticaxi.cpp:99-106: the conductance integral carries 100/r of the element centroid
+            if (axi) I2[ic] += 100. * a * Cduct / ((meshnode[n[0]].x + meshnode[n[1]].x + meshnode[n[2]].x) / 3.);
+            else I2[ic] += a * Cduct;
             I3[ic] += blockproplist[El.blk].J.re * a * 100.;
         }
         for (int i = 0; i < NumCircProps; i++)
@@ -403,9 +400,19 @@ int FSolver::staticSolve(CBigLinProb &L, bool axi)
         // linear permeabilities of the first pass (static2d.cpp:603-631)
         double t = bp.LamFill, mu;
         T.mu1 = -1; T.mu2 = -1;
-        if (bp.LamType == 0) { T.mu1 = bp.mu_x * t + (1. - t); T.mu2 = bp.mu_y * t + (1. - t); }
-        if (bp.LamType == 1) { mu = bp.mu_x; T.mu1 = mu * t + (1. - t); T.mu2 = mu / (t + mu * (1. - t)); }
-        if (bp.LamType == 2) { mu = bp.mu_y; T.mu2 = mu * t + (1. - t); T.mu1 = mu / (t + mu * (1. - t)); }
+        if (!axi)
+        {
+            if (bp.LamType == 0) { T.mu1 = bp.mu_x * t + (1. - t); T.mu2 = bp.mu_y * t + (1. - t); }
+            if (bp.LamType == 1) { mu = bp.mu_x; T.mu1 = mu * t + (1. - t); T.mu2 = mu / (t + mu * (1. - t)); }
+            if (bp.LamType == 2) { mu = bp.mu_y; T.mu2 = mu * t + (1. - t); T.mu1 = mu / (t + mu * (1. - t)); }
+        }
+        else
+        {
+            // staticaxi.cpp:431-447 — literally: type 0 drops the (1-t) term, type 2 assigns like type 1
+            if (bp.LamType == 0) { T.mu1 = bp.mu_x * t; T.mu2 = bp.mu_y * t; }
+            if (bp.LamType == 1) { mu = bp.mu_x; T.mu1 = mu * t + (1. - t); T.mu2 = mu / (t + mu * (1. - t)); }
+            if (bp.LamType == 2) { mu = bp.mu_y; T.mu1 = mu * t + (1. - t); T.mu2 = mu / (t + mu * (1. - t)); }
+        }
         if (bp.LamType > 2) { T.mu1 = 1; T.mu2 = 1; }
         // source current density incl. the circuit contribution (static2d.cpp:483-504)
         double tc = 0;
@@ -413,7 +420,11 @@ int FSolver::staticSolve(CBigLinProb &L, bool axi)
         {
             const CMCircuit &cp = circproplist[bl.InCircuit];
             if (cp.Case == 1) tc = cp.J.Re();
-            if (cp.Case == 0) tc = -cp.dV.Re() * bp.Cduct;
+            if (cp.Case == 0)
+            {
+                if (axi) T.dVs = -100. * cp.dV.Re() * bp.Cduct; // divided by the element's R on the device
+                else tc = -cp.dV.Re() * bp.Cduct;
+            }
         }
         T.Jsrc = bp.J.re + tc;
         T.H_c = bp.H_c;
@@ -450,15 +461,21 @@ int FSolver::staticSolve(CBigLinProb &L, bool axi)
         if (meshnode[i].BoundaryMarker >= 0)
         {
             psNode.push_back(i);
-            psVal.push_back(0.01 * nodeproplist[meshnode[i].BoundaryMarker].J.re);
+            double pv = 0.01 * nodeproplist[meshnode[i].BoundaryMarker].J.re;
+            if (axi) pv = (0.01 * nodeproplist[meshnode[i].BoundaryMarker].J.re * 2. * meshnode[i].x); // staticaxi.cpp:636-641
+            psVal.push_back(pv);
         }
     // fixed potentials at points (static2d.cpp:827-838) come first, then along segments
     for (int i = 0; i < NumNodes; i++)
+    {
+        // staticaxi.cpp:644-651: nodes on the axis are pinned to zero
+        if (axi && fabs(meshnode[i].x) < (units[LengthUnits] * 1.e-06)) { setValue(i, 0.); continue; }
         if (meshnode[i].BoundaryMarker >= 0)
         {
             const CMPointProp &pp = nodeproplist[meshnode[i].BoundaryMarker];
             if ((pp.J.re == 0) && (pp.J.im == 0)) setValue(i, pp.A.re / c);
         }
+    }
     for (int i = 0; i < NumEls; i++)
     {
         const CMElement &El = meshele[i];
@@ -494,6 +511,8 @@ int FSolver::staticSolve(CBigLinProb &L, bool axi)
                         a = bp.A0 + r * bp.A1 + th * bp.A2;
                     }
                     a *= cos(bp.phi * DEG);
+                    // staticaxi.cpp:674,686: nodes with x == 0 keep the axis condition
+                    if (axi && (meshnode[node].x / units[LengthUnits]) == 0) continue;
                     setValue(node, a / c);
                 }
             }
@@ -501,7 +520,7 @@ int FSolver::staticSolve(CBigLinProb &L, bool axi)
     }
     std::vector<int> ageNodes, ageMid;
     std::vector<double> ageW, ageMats;
-    flatten_age(agelist, ageNodes, ageW, ageMid, ageMats, false);
+    if (!axi) flatten_age(agelist, ageNodes, ageW, ageMid, ageMats, false); // StaticAxisymmetric has no AGE loop
     std::vector<int> pbcI(NumPBCs), pbcJ(NumPBCs), pbcT(NumPBCs);
     for (int k = 0; k < NumPBCs; k++) { pbcI[k] = pbclist[k].x; pbcJ[k] = pbclist[k].y; pbcT[k] = pbclist[k].t; }
 
@@ -537,7 +556,7 @@ int FSolver::staticSolve(CBigLinProb &L, bool axi)
     D.n_bh = (int)bhB.size(); D.bh_B = bhB.data(); D.bh_H = bhH.data(); D.bh_slope = bhS.data();
     D.n_mixed = (int)(mixedES.size() / 2); D.mixed_elem_side = mixedES.data(); D.mixed_c0c1 = mixedC.data();
     D.n_age_cells = (int)ageMid.size(); D.age_nodes = ageNodes.data(); D.age_weights = ageW.data();
-    D.age_matrix_id = ageMid.data(); D.n_age_matrices = (int)agelist.size(); D.age_matrices = ageMats.data();
+    D.age_matrix_id = ageMid.data(); D.n_age_matrices = (int)(ageMats.size() / 100); D.age_matrices = ageMats.data();
     D.n_point_src = (int)psNode.size(); D.point_src_node = psNode.data(); D.point_src_val = psVal.data();
     D.ext_zo = extZo * units[LengthUnits]; D.ext_ro = extRo * units[LengthUnits]; D.ext_ri = extRi * units[LengthUnits];
     D.r_eps = 1.e-6 * units[LengthUnits];
