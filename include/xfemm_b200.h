@@ -207,6 +207,90 @@ int xfemm_linprob_relax(xfemm_linprob *p, double relax);
 /* planar: b = V*c ; axisymmetric: b = V*c*2*pi*r*0.01 (static2d.cpp:1018-1021, staticaxi.cpp:779-783) */
 int xfemm_mag_solution_to_A(xfemm_mag *m, double *A_host);
 
+/* ------------------------------------------------------------------ complex-symmetric linear problem
+ * Values, right-hand side and solution are interleaved (re,im) doubles — layout of the reference's
+ * CComplex {double re, im} (cfemm/libfemm/liblua/femmcomplex.h:31).  n_nodes = number of mesh
+ * unknowns; rows n_nodes..n-1 are circuit unknowns (always inside the SetValue scan range,
+ * cspars.cpp:500-503). */
+int xfemm_clinprob_create(int n, int n_nodes, const int *rowptr, const int *colidx, xfemm_clinprob **out);
+int xfemm_clinprob_destroy(xfemm_clinprob *p);
+int xfemm_clinprob_n(const xfemm_clinprob *p);
+long long xfemm_clinprob_nnz(const xfemm_clinprob *p);
+int xfemm_clinprob_wipe(xfemm_clinprob *p);                                /* cspars.cpp:539 Wipe */
+int xfemm_clinprob_set_values(xfemm_clinprob *p, const double *vals_csr);
+int xfemm_clinprob_get_values(xfemm_clinprob *p, double *vals_csr);
+int xfemm_clinprob_set_rhs(xfemm_clinprob *p, const double *b);
+int xfemm_clinprob_get_rhs(xfemm_clinprob *p, double *b);
+int xfemm_clinprob_set_solution(xfemm_clinprob *p, const double *V);
+int xfemm_clinprob_get_solution(xfemm_clinprob *p, double *V);
+int xfemm_clinprob_dirichlet(xfemm_clinprob *p, int count, const int *nodes, const double *x_first,
+                             const double *x_last, int bdw);                /* cspars.cpp:482 SetValue */
+int xfemm_clinprob_periodic(xfemm_clinprob *p, int npairs, const int *ni, const int *nj, const int *type); /* :677 */
+int xfemm_clinprob_set_fill_mask(xfemm_clinprob *p, const unsigned char *fill);
+int xfemm_clinprob_get_exists_mask(xfemm_clinprob *p, unsigned char *exists);
+/* cspars.cpp:1062 PBCGSolveMod for the complex-symmetric case: cold start = 3 CG steps on the
+ * normal equations (PCGSQStart, :764) then COCG (PBCGSolve, :822); stop on ||r||/||b|| <= precision */
+int xfemm_clinprob_cocg(xfemm_clinprob *p, double precision, int warm, int precond, int max_iter,
+                        xfemm_solve_info *info);
+int xfemm_clinprob_save_solution(xfemm_clinprob *p);
+int xfemm_clinprob_newton_norms(xfemm_clinprob *p, int count, double *dv2, double *v2); /* first `count` rows */
+int xfemm_clinprob_relax(xfemm_clinprob *p, double relax);
+
+/* ------------------------------------------------------------------ time-harmonic assembly */
+typedef struct xfemm_cmag_label
+{
+    double mu1[2], mu2[2]; /* complex relative permeabilities of the first pass (lamination / proximity models applied) */
+    double J[2];           /* J_block + a-priori circuit current density [MA/m^2] (harmonic2d.cpp:518-530)             */
+    double dVs[2];         /* axisymmetric a-priori voltage gradient term, divided by R on the device                 */
+    double sigma_eddy;     /* conductivity of the eddy-current mass term (0: wound or laminated block)               */
+    double sigma_circ;     /* conductivity coupling the element to its Case-2 circuit unknown                        */
+    int circuit;           /* Case 2: index k of the circuit unknown (row n_nodes+k), else -1                        */
+    int bh_offset, bh_points, lamtype, is_external, pad_;
+} xfemm_cmag_label;
+
+typedef struct xfemm_cmag_desc
+{
+    int axisymmetric;
+    int n_nodes, n_elems;
+    double omega;                 /* 2 pi f */
+    const double *xy;             /* n_nodes*2, cm, solver order */
+    const int *tri;               /* n_elems*4: p0,p1,p2,label */
+    int n_labels;
+    const xfemm_cmag_label *labels;
+    int n_bh;
+    const double *bh_B, *bh_H, *bh_H_im, *bh_slope, *bh_slope_im;
+    /* boundary sides of type 2 (mixed) and 1 (small skin depth): element, local side and 7 doubles:
+     * type, c0.re, c0.im, c1.re, c1.im, Kssd.re, Kssd.im (Kssd = (1+j)/(-ds*Mu*100), harmonic2d.cpp:502-514) */
+    int n_sides;
+    const int *side_elem_side;
+    const double *side_coeffs;
+    int n_age_cells;
+    const int *age_nodes;
+    const double *age_weights;
+    const int *age_matrix_id;
+    int n_age_matrices;
+    const double *age_matrices;
+    /* additive right-hand-side terms: point currents (-0.01 J) and total-current constraints of Case-2 circuits */
+    int n_rhs_add;
+    const int *rhs_add_row;
+    const double *rhs_add_val;    /* complex */
+    /* circuit rows whose diagonal is set to A(0,0) after the Dirichlet conditions (Case < 2) */
+    int n_fix_diag;
+    const int *fix_diag_rows;
+    double ext_zo, ext_ro, ext_ri;
+} xfemm_cmag_desc;
+
+typedef struct xfemm_cmag xfemm_cmag;
+int xfemm_cmag_create(const xfemm_cmag_desc *desc, xfemm_clinprob *lin, xfemm_cmag **out);
+int xfemm_cmag_destroy(xfemm_cmag *m);
+int xfemm_cmag_set_labels(xfemm_cmag *m, int n_labels, const xfemm_cmag_label *labels);
+/* one assembly pass (Wipe, AGE blocks with the harmonic sign, elements, boundary sides, RHS terms);
+ * iter>0 re-evaluates the permeability of B-H elements by successive approximation */
+int xfemm_cmag_assemble(xfemm_cmag *m, int iter, double *elapsed_ms);
+int xfemm_cmag_fix_circuit_diagonals(xfemm_cmag *m);
+int xfemm_cmag_get_mu(xfemm_cmag *m, double *mu4);               /* n_elems*4: mu1.re, mu1.im, mu2.re, mu2.im */
+int xfemm_cmag_solution_to_A(xfemm_cmag *m, double *A_host);      /* n complex: A (nodes) and circuit results  */
+
 /* ------------------------------------------------------------------ file-level entry
  * The call a user of fsolver / mexfsolver makes: basename without ".fem";
  * returns 0 ok, 1 problem loading .fem, 2 solve failed (main.cpp:72-83, mexfsolver.cpp:122-134). */

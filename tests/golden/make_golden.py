@@ -119,7 +119,8 @@ def fem_text(problemtype, frequency, precision, bdrys, blocks, circuits, points,
     return "\n".join(L) + "\n"
 
 
-def solenoid(problemtype, frequency, precision, mesh=0.25, amps=25, steel_extra=None, coil_sigma=0, magnet_sigma=0, acsolver=0):
+def solenoid(problemtype, frequency, precision, mesh=0.25, amps=25, steel_extra=None, coil_sigma=0, magnet_sigma=0, acsolver=0,
+             bar_amps=None):
     """Solenoid with a saturating 1117-steel plunger on the axis, a series-connected 200-turn coil and
     a magnet ring, inside a half disc of radius 10 cm with A=0 on the arc (cross-section in r>=0)."""
     steel = {"name": "1117 Steel", "Mu_x": 1777, "Mu_y": 1777, "bh": STEEL_BH}
@@ -133,8 +134,18 @@ def solenoid(problemtype, frequency, precision, mesh=0.25, amps=25, steel_extra=
     arcs = [(0, 1, 180, 5, 1)]
     labels = [(5.0, 5.0, 1, 4 * mesh, 0, 0, 1, 0), (1.5, 0.0, 2, mesh, 1, 0, 200, 0), (0.4, 1.0, 3, mesh, 0, 0, 1, 0),
               (3.5, 0.0, 4, mesh, 0, 90, 1, 0)]
+    circuits = [{"name": "coil", "amps": amps, "type": 1}]
+    if bar_amps is not None:
+        # solid copper bar carrying a prescribed total current: parallel circuit over a conductor →
+        # the voltage gradient becomes an extra unknown in the harmonic formulations (Case 2)
+        blocks.append({"name": "Copper", "Sigma": 58})
+        n0 = len(pts)
+        pts += [(5.0, -1.0), (6.0, -1.0), (6.0, 1.0), (5.0, 1.0)]
+        segs += [(n0, n0 + 1, 0), (n0 + 1, n0 + 2, 0), (n0 + 2, n0 + 3, 0), (n0 + 3, n0, 0)]
+        labels.append((5.5, 0.0, 5, mesh, 2, 0, 1, 0))
+        circuits.append({"name": "bar", "amps": bar_amps, "type": 0})
     return fem_text(problemtype, frequency, precision, [{"name": "A=0", "BdryType": 0}], blocks,
-                    [{"name": "coil", "amps": amps, "type": 1}], pts, segs, arcs, labels, acsolver=acsolver)
+                    circuits, pts, segs, arcs, labels, acsolver=acsolver)
 
 
 def case_axi1(tmp):
@@ -150,7 +161,37 @@ def case_sat2d(tmp):
     return "sat2d"
 
 
-CASES = {"tb": case_tb, "tb30": case_tb30, "temp1": case_temp1, "axi1": case_axi1, "sat2d": case_sat2d}
+def case_harm2d(tmp):
+    """config 4 stand-in: Harmonic2D at 50 Hz — eddy currents in a conductive magnet and in the steel,
+    B-H steel (successive approximation), wound series coil (Case 1) and a solid bar with prescribed
+    total current (Case 2: circuit unknown appended to the system)."""
+    _write_fem(os.path.join(tmp, "harm2d.fem"), solenoid("planar", 50, "1e-08", amps=400, magnet_sigma=0.667, bar_amps=500,
+                                                          steel_extra={"Sigma": 5.8, "Phi_h": 10}))
+    return "harm2d"
+
+
+def case_harmaxi(tmp):
+    """config 4 stand-in: HarmonicAxisymmetric at 50 Hz, same ingredients, nodes on the axis."""
+    _write_fem(os.path.join(tmp, "harmaxi.fem"), solenoid("axisymmetric", 50, "1e-08", amps=100, magnet_sigma=0.667, bar_amps=200,
+                                                           steel_extra={"Sigma": 5.8}))
+    return "harmaxi"
+
+
+def case_tbh(tmp):
+    """TorqueBenchmark geometry (air-gap element + periodic pairs) at 50 Hz with a conducting,
+    current-carrying rotor block: exercises the harmonic sign of the AGE blocks and complex periodicity."""
+    t = open(os.path.join(SRC, "test", "TorqueBenchmark.fem"), newline="").read().replace("\r\n", "\n")
+    t = set_key(t, "[Frequency]", 50)
+    t = set_key(t, "[Precision]", "1e-08")
+    head, _, tail = t.partition("<BeginBlock>")           # first block = Air
+    blk2_head, _, blk2_tail = tail.partition("<BeginBlock>")  # second block: give it sigma and J
+    blk2_tail = blk2_tail.replace("<J_re> = 0", "<J_re> = 1", 1).replace("<Sigma> = 0", "<Sigma> = 0.667", 1)
+    _write_fem(os.path.join(tmp, "tbh.fem"), head + "<BeginBlock>" + blk2_head + "<BeginBlock>" + blk2_tail)
+    return "tbh"
+
+
+CASES = {"tb": case_tb, "tb30": case_tb30, "temp1": case_temp1, "axi1": case_axi1, "sat2d": case_sat2d,
+         "harm2d": case_harm2d, "harmaxi": case_harmaxi, "tbh": case_tbh}
 
 
 def run_case(name):
@@ -168,7 +209,7 @@ def run_case(name):
         with open(os.path.join(tmp, base + ext), "rb") as fi, gzip.open(os.path.join(out, name + ext + ".gz"), "wb", 9) as fo:
             fo.write(fi.read())
     dump = os.path.join(tmp, "dump")
-    r = subprocess.run([os.path.join(REF, "ref_harness"), "dump", os.path.join(tmp, base), dump], check=True,
+    r = subprocess.run([os.path.join(REF, "ref_harness"), "dump", os.path.join(tmp, base), dump, "1000"], check=True,
                        stdout=subprocess.PIPE, text=True)
     meta = json.loads(r.stdout.strip().splitlines()[-1])
     keep = ["nodes", "node_bc", "elems", "pbc", "V", "A", "mu", "circ"]

@@ -1,0 +1,69 @@
+"""GPU parity: time-harmonic formulations (complex-symmetric COCG) through the C ABI against dumps of
+the unmodified reference on authored fixtures (the reference ships no harmonic fixture).
+
+tbh     TorqueBenchmark at 50 Hz: air-gap element (harmonic sign), 360 periodic pairs, eddy currents
+harm2d  planar solenoid section at 50 Hz: B-H steel with hysteresis angle (successive approximation,
+        65 passes in the reference), conducting magnet, wound coil (Case 1), solid bar with
+        prescribed total current (Case 2: circuit unknown appended to the system)
+harmaxi the same axisymmetric (nodes on the axis, 1/R circuit terms)
+"""
+import numpy as np
+import pytest
+
+import xfemm_b200 as X
+from util import load_ref, rel_l2, stage_case, upper_from_full
+
+pytestmark = pytest.mark.gpu
+
+
+def _solve(name, tmp_path, precond):
+    S = X.FSolver(stage_case(name, tmp_path))
+    S.set_option("keep_system", 1)
+    S.set_option("precond", precond)
+    S.load_mesh(False)
+    S.renumber(False)
+    S.solve()
+    return S
+
+
+@pytest.mark.parametrize("precond", [X.PRECOND_JACOBI, X.PRECOND_MCSSOR])
+def test_harmonic_linear_age_periodic(precond, tmp_path):
+    ref, meta = load_ref("tbh")
+    S = _solve("tbh", tmp_path, precond)
+    rowptr, col, vals, rhs = S.system()
+    urp, ucol, uval = upper_from_full(rowptr, col, vals)
+    assert np.array_equal(urp, ref["step0_rowptr"]) and np.array_equal(ucol, ref["step0_col"])
+    scale = np.abs(ref["step0_val"]).max()
+    assert np.abs(uval - ref["step0_val"]).max() <= 1e-11 * scale
+    assert np.abs(rhs - ref["step0_rhs"]).max() <= 1e-11 * np.abs(ref["step0_rhs"]).max()
+    V, A = S.solution()
+    st = S.stats()
+    print("tbh precond", precond, "iters", st["iters"], "relres", st["relres"], "relL2(A)", rel_l2(A, ref["A"]))
+    assert st["newton_steps"] == 1
+    assert rel_l2(V, ref["V"]) <= 1e-6 and rel_l2(A, ref["A"]) <= 1e-6
+
+
+@pytest.mark.parametrize("name", ["harm2d", "harmaxi"])
+def test_harmonic_nonlinear_circuits(name, tmp_path):
+    ref, meta = load_ref(name)
+    S = _solve(name, tmp_path, X.PRECOND_JACOBI)
+    st = S.stats()
+    V, A = S.solution()
+    n_nodes = meta["n_nodes"]
+    print(name, "passes", st["newton_steps"], "reference", meta["solves"], "COCG iters (first, last)", st["iters"][0], st["iters"][-1],
+          "relL2(A nodes)", rel_l2(A[:n_nodes], ref["A"][:n_nodes]), "circuit unknowns", A[n_nodes:], ref["A"][n_nodes:])
+    rowptr, col, vals, rhs = S.system()
+    urp, ucol, uval = upper_from_full(rowptr, col, vals)
+    last = meta["solves"] - 1
+    assert np.array_equal(urp, ref[f"step{last}_rowptr"]) and np.array_equal(ucol, ref[f"step{last}_col"])
+    # successive approximation stops when the relative change drops below 100*Precision = 1e-6; the
+    # number of passes may differ by one when the change sits at the threshold
+    assert abs(st["newton_steps"] - meta["solves"]) <= 1
+    scale = np.abs(ref[f"step{last}_val"]).max()
+    assert np.abs(uval - ref[f"step{last}_val"]).max() <= 1e-4 * scale
+    # both runs are converged to ~1e-6/(1-rho) of the fixed point of the iteration (rho = contraction
+    # factor of the successive approximation), so that is the meaningful bar for the difference
+    assert rel_l2(A[:n_nodes], ref["A"][:n_nodes]) <= 1e-6
+    assert np.allclose(A[n_nodes:], ref["A"][n_nodes:], rtol=1e-4, atol=1e-12)
+    mu = S.mu()
+    assert np.abs(mu - ref["mu"]).max() <= 1e-3 * np.abs(ref["mu"]).max()

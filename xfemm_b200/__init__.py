@@ -86,6 +86,32 @@ SIGNATURES = {
     "xfemm_mag_assemble_static": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double)]),
     "xfemm_mag_get_mu": (C.c_int, [_P, _dp]),
     "xfemm_mag_solution_to_A": (C.c_int, [_P, _dp]),
+    "xfemm_clinprob_create": (C.c_int, [C.c_int, C.c_int, _ip, _ip, C.POINTER(_P)]),
+    "xfemm_clinprob_destroy": (C.c_int, [_P]),
+    "xfemm_clinprob_n": (C.c_int, [_P]),
+    "xfemm_clinprob_nnz": (C.c_longlong, [_P]),
+    "xfemm_clinprob_wipe": (C.c_int, [_P]),
+    "xfemm_clinprob_set_values": (C.c_int, [_P, _P]),
+    "xfemm_clinprob_get_values": (C.c_int, [_P, _P]),
+    "xfemm_clinprob_set_rhs": (C.c_int, [_P, _P]),
+    "xfemm_clinprob_get_rhs": (C.c_int, [_P, _P]),
+    "xfemm_clinprob_set_solution": (C.c_int, [_P, _P]),
+    "xfemm_clinprob_get_solution": (C.c_int, [_P, _P]),
+    "xfemm_clinprob_dirichlet": (C.c_int, [_P, C.c_int, _ip, _P, _P, C.c_int]),
+    "xfemm_clinprob_periodic": (C.c_int, [_P, C.c_int, _ip, _ip, _ip]),
+    "xfemm_clinprob_set_fill_mask": (C.c_int, [_P, _P]),
+    "xfemm_clinprob_get_exists_mask": (C.c_int, [_P, _P]),
+    "xfemm_clinprob_cocg": (C.c_int, [_P, C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(SolveInfo)]),
+    "xfemm_clinprob_save_solution": (C.c_int, [_P]),
+    "xfemm_clinprob_newton_norms": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "xfemm_clinprob_relax": (C.c_int, [_P, C.c_double]),
+    "xfemm_cmag_create": (C.c_int, [_P, _P, C.POINTER(_P)]),
+    "xfemm_cmag_destroy": (C.c_int, [_P]),
+    "xfemm_cmag_set_labels": (C.c_int, [_P, C.c_int, _P]),
+    "xfemm_cmag_assemble": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double)]),
+    "xfemm_cmag_fix_circuit_diagonals": (C.c_int, [_P]),
+    "xfemm_cmag_get_mu": (C.c_int, [_P, _P]),
+    "xfemm_cmag_solution_to_A": (C.c_int, [_P, _P]),
     "xfemm_fsolver_run": (C.c_int, [C.c_char_p, C.c_int]),
     "xfemm_fsolver_open": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(_P)]),
     "xfemm_fsolver_load_mesh": (C.c_int, [_P, C.c_int]),
@@ -102,7 +128,7 @@ SIGNATURES = {
     "xfemm_fsolver_get_pattern": (C.c_int, [_P, C.POINTER(C.c_longlong), _P, _P]),
     "xfemm_fsolver_get_system": (C.c_int, [_P, _P, _P]),
     "xfemm_fsolver_get_solution": (C.c_int, [_P, _P, _P]),
-    "xfemm_fsolver_get_mu": (C.c_int, [_P, _dp]),
+    "xfemm_fsolver_get_mu": (C.c_int, [_P, _P]),
     "xfemm_fsolver_get_stats": (C.c_int, [_P, C.POINTER(C.c_int), _ip, _dp, _dp, C.POINTER(C.c_double)]),
     "xfemm_fsolver_set_option": (C.c_int, [_P, C.c_char_p, C.c_double]),
 }
@@ -390,9 +416,9 @@ class FSolver:
         return V, A
 
     def mu(self):
-        n = self.counts()["n_elems"]
-        m = np.empty((n, 2), dtype=np.float64)
-        _check(lib().xfemm_fsolver_get_mu(self.h, m.reshape(-1)), "get_mu")
+        c = self.counts()
+        m = np.empty((c["n_elems"], 4 if c["is_complex"] else 2), dtype=np.float64)
+        _check(lib().xfemm_fsolver_get_mu(self.h, _ptr(m)), "get_mu")
         return m
 
     def stats(self):

@@ -1,0 +1,33 @@
+// Device-side complex-symmetric linear problem (backend of CBigComplexLinProb; cspars.h:37-95).
+#pragma once
+#include "common.cuh"
+#include "layout.h"
+#include <vector>
+#include <cstdint>
+
+typedef double2 cd;
+
+struct xfemm_clinprob
+{
+    int n = 0, n_nodes = 0;
+    long long nnz = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<int> h_rowptr, h_col;
+    xb::DevBuf<int> rowptr, col;
+    xb::DevBuf<cd> vals, b, V, Vold;
+    xb::SellLayout lay;
+    int layout_precond = -1;
+    xb::DevBuf<int> i2c, c2i, slice_ptr, slice_wl, slice_wu, sell_col, sell_src, diag_src, color_slice;
+    xb::DevBuf<cd> sell_val, diag, dinv, x, r, p, u, z, w, bint;
+    xb::DevBuf<double> partials, d_mail;
+    int max_grid = 0;
+    double h_mail[16];
+    xb::DevBuf<int> dir_idx, dir_nodes;
+    xb::DevBuf<cd> dir_first, dir_last;
+    uint64_t pbc_hash = 0;
+    int pbc_pairs = 0, pbc_levels = 0;
+    xb::DevBuf<int> pbc_level_ptr, pbc_item_ptr, pbc_meta, pbc_items;
+    xb::DevBuf<unsigned char> fill_mask, created;
+};
+

@@ -183,3 +183,72 @@ void build_sell_layout(int n, const int *rowptr, const int *col, const std::vect
 }
 
 } // namespace xb
+
+#include <unordered_map>
+namespace xb {
+
+int build_pbc_plan(int n, const int *rowptr, const int *col, int npairs, const int *ni, const int *nj,
+                   const int *type, std::vector<int> &level_ptr, std::vector<int> &item_ptr,
+                   std::vector<int> &meta, std::vector<int> &items, int err[3])
+{
+    auto slot = [&](int row, int c) -> int {
+        const int *b = col + rowptr[row], *e = col + rowptr[row + 1];
+        const int *it = std::lower_bound(b, e, c);
+        return (it != e && *it == c) ? (int)(it - col) : -1;
+    };
+    std::vector<int> iptr(npairs + 1, 0), m0((size_t)6 * npairs), it0, level(npairs, 0);
+    std::unordered_map<long long, int> last; // slot / rhs id → last level that touched it
+    std::vector<int> ks;
+    int nlevels = 0;
+    for (int k = 0; k < npairs; k++)
+    {
+        int i = ni[k], j = nj[k];
+        if (i < 0 || i >= n || j < 0 || j >= n || i == j) { err[0] = i; err[1] = j; err[2] = -1; return -1; }
+        if (j < i) std::swap(i, j);
+        ks.clear();
+        ks.insert(ks.end(), col + rowptr[i], col + rowptr[i + 1]);
+        ks.insert(ks.end(), col + rowptr[j], col + rowptr[j + 1]);
+        std::sort(ks.begin(), ks.end());
+        ks.erase(std::unique(ks.begin(), ks.end()), ks.end());
+        int lv = 0;
+        auto touch = [&](long long id) { auto f = last.find(id); if (f != last.end()) lv = std::max(lv, f->second + 1); };
+        const size_t first = it0.size();
+        for (int kk : ks)
+        {
+            if (kk == i || kk == j) continue;
+            int s[4] = {slot(kk, i), slot(i, kk), slot(kk, j), slot(j, kk)};
+            if (s[0] < 0 || s[1] < 0 || s[2] < 0 || s[3] < 0) { err[0] = i; err[1] = j; err[2] = kk; return -1; }
+            for (int t = 0; t < 4; t++) { it0.push_back(s[t]); touch(s[t]); }
+        }
+        const int sii = slot(i, i), sjj = slot(j, j);
+        touch(sii); touch(sjj); touch(-1 - (long long)i); touch(-1 - (long long)j);
+        for (size_t q = first; q < it0.size(); q++) last[it0[q]] = lv;
+        last[sii] = lv; last[sjj] = lv; last[-1 - (long long)i] = lv; last[-1 - (long long)j] = lv;
+        level[k] = lv;
+        nlevels = std::max(nlevels, lv + 1);
+        iptr[k + 1] = (int)(it0.size() / 4);
+        int *m = &m0[(size_t)6 * k];
+        m[0] = i; m[1] = j; m[2] = type[k]; m[3] = sii; m[4] = sjj; m[5] = 0;
+    }
+    std::vector<int> order(npairs);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return level[a] < level[b]; });
+    level_ptr.assign(nlevels + 1, 0);
+    item_ptr.assign(npairs + 1, 0);
+    meta.assign((size_t)6 * npairs, 0);
+    items.clear();
+    items.reserve(it0.size());
+    for (int q = 0; q < npairs; q++)
+    {
+        int k = order[q];
+        level_ptr[level[k] + 1]++;
+        items.insert(items.end(), it0.begin() + (size_t)iptr[k] * 4, it0.begin() + (size_t)iptr[k + 1] * 4);
+        item_ptr[q + 1] = (int)(items.size() / 4);
+        for (int t = 0; t < 6; t++) meta[(size_t)6 * q + t] = m0[(size_t)6 * k + t];
+    }
+    for (int l = 0; l < nlevels; l++) level_ptr[l + 1] += level_ptr[l];
+    if (items.empty()) items.assign(4, 0);
+    return nlevels;
+}
+
+} // namespace xb

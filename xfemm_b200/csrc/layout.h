@@ -25,3 +25,14 @@ void build_sell_layout(int n, const int *rowptr, const int *col, const std::vect
                        int ncolors, int sigma, SellLayout &L);
 
 } // namespace xb
+
+namespace xb {
+// Plan for applying Periodicity/AntiPeriodicity pairs in list order on a fixed CSR pattern
+// (reference: spars.cpp:366-474, cspars.cpp:677-758): pairs are grouped into dependency levels
+// (pairs of a level touch disjoint entries), items are (slot(k,i), slot(i,k), slot(k,j), slot(j,k)),
+// meta is (i, j, type, slot(i,i), slot(j,j), 0) per pair.  Returns the number of levels, -1 on a
+// missing slot (err_i/err_j/err_k tell which).
+int build_pbc_plan(int n, const int *rowptr, const int *col, int npairs, const int *ni, const int *nj,
+                   const int *type, std::vector<int> &level_ptr, std::vector<int> &item_ptr,
+                   std::vector<int> &meta, std::vector<int> &items, int err[3]);
+} // namespace xb

@@ -92,6 +92,7 @@ int xfemm_fsolver_solve(xfemm_fsolver *s)
     }
     else
     {
+        S.releaseDevice();
         delete s->Lc;
         s->Lc = new CBigComplexLinProb;
         s->Lc->Precision = S.Precision;
@@ -228,6 +229,7 @@ int xfemm_fsolver_get_solution(xfemm_fsolver *s, double *V, double *A)
 
 int xfemm_fsolver_get_mu(xfemm_fsolver *s, double *mu12)
 {
+    if (s && s->S.cmagdev) return xfemm_cmag_get_mu(s->S.cmagdev, mu12); // 4 doubles per element
     if (!s || !s->S.magdev) { xb::set_error("no device mesh"); return XFEMM_ERR_ARG; }
     return xfemm_mag_get_mu(s->S.magdev, mu12);
 }

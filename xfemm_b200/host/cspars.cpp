@@ -1,7 +1,9 @@
 // CBigComplexLinProb facade (reference: cfemm/libfemm/cspars.cpp:119-1081).
-// The complex-symmetric device solver is not part of this build yet: the object can be created
-// and filled with vectors, but PBCGSolveMod fails loudly instead of falling back to a CPU solve.
+// The B200 FSolver assembles harmonic problems on the device and binds the device problem with
+// attachDevice(); host-side assembly through Put/AddTo (not used by any caller of the reference
+// outside fsolver itself) is not provided and fails loudly.
 #include "cspars.h"
+#include "../../include/xfemm_b200.h"
 #include <cstdio>
 #include <cstdlib>
 
@@ -14,6 +16,7 @@ CBigComplexLinProb::CBigComplexLinProb()
 
 CBigComplexLinProb::~CBigComplexLinProb()
 {
+    if (dev) xfemm_clinprob_destroy(dev);
     free(P); free(U); free(R); free(V); free(Z); free(b); free(uu); free(vv);
 }
 
@@ -33,7 +36,11 @@ int CBigComplexLinProb::Create(int d, int bw, int nodes)
     return 1;
 }
 
-void CBigComplexLinProb::attachDevice(xfemm_clinprob *d) { dev = d; }
+void CBigComplexLinProb::attachDevice(xfemm_clinprob *d)
+{
+    if (dev && dev != d) xfemm_clinprob_destroy(dev);
+    dev = d;
+}
 void CBigComplexLinProb::Put(CComplex, int, int, int) { fprintf(stderr, "xfemm_b200: CBigComplexLinProb::Put is not available in this build\n"); }
 CComplex CBigComplexLinProb::Get(int, int, int) { return CComplex(0); }
 void CBigComplexLinProb::AddTo(CComplex v, int p, int q) { Put(Get(p, q) + v, p, q); }
@@ -41,8 +48,16 @@ void CBigComplexLinProb::SetValue(int, CComplex) {}
 void CBigComplexLinProb::Periodicity(int, int) {}
 void CBigComplexLinProb::AntiPeriodicity(int, int) {}
 void CBigComplexLinProb::Wipe() {}
-int CBigComplexLinProb::PBCGSolveMod(int, bool)
+int CBigComplexLinProb::PBCGSolveMod(int flag, bool)
 {
-    fprintf(stderr, "xfemm_b200: the complex-symmetric device solver is not available in this build\n");
-    return 0;
+    if (!dev)
+    {
+        fprintf(stderr, "xfemm_b200: CBigComplexLinProb has no device problem attached\n");
+        return 0;
+    }
+    xfemm_solve_info info;
+    int rc = xfemm_clinprob_cocg(dev, Precision, flag, precond, 0, &info);
+    lastIterations = info.iterations; lastSolveMs = info.solve_ms; lastRelRes = info.relres;
+    if (rc != XFEMM_OK) { fprintf(stderr, "%s\n", xfemm_last_error()); return 0; }
+    return xfemm_clinprob_get_solution(dev, (double *)V) == XFEMM_OK;
 }

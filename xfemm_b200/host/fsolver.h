@@ -251,6 +251,7 @@ public:
     int precondOption;           // XFEMM_PRECOND_* or -1 = backend default
     int maxIterOption;           // <=0 = backend default
     xfemm_mag *magdev;           // device mesh of the last solve (kept for queries), owned
+    struct xfemm_cmag *cmagdev;  // same for the time-harmonic formulations
     void releaseDevice();
     // host-side inputs of the Newton loop that stay valid while the device problem is resident
     struct StaticPlan

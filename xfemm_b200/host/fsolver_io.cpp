@@ -107,6 +107,7 @@ FSolver::FSolver()
     precondOption = -1;
     maxIterOption = 0;
     magdev = nullptr;
+    cmagdev = nullptr;
     keepSystem = false;
 }
 
@@ -632,11 +633,13 @@ bool echo_fem(const std::string &path, FILE *fp)
 }
 } // namespace
 
-static void write_tail(FSolver &S, FILE *fp)
+static void write_tail(FSolver &S, FILE *fp, bool harmonic)
 {
-    // periodic pairs and air-gap tables (static2d.cpp:1150-1191)
+    // periodic pairs and air-gap tables (static2d.cpp:1150-1191 ; harmonic2d.cpp:994-1030 uses
+    // a different separator in the pair rows)
     fprintf(fp, "%i\n", S.NumPBCs);
-    for (int k = 0; k < S.NumPBCs; k++) fprintf(fp, "%i\t%i\t%i\n", S.pbclist[k].x, S.pbclist[k].y, S.pbclist[k].t);
+    for (int k = 0; k < S.NumPBCs; k++)
+        fprintf(fp, harmonic ? "%i  %i %i\n" : "%i\t%i\t%i\n", S.pbclist[k].x, S.pbclist[k].y, S.pbclist[k].t);
     fprintf(fp, "%i\n", S.NumAirGapElems);
     for (int i = 0; i < S.NumAirGapElems; i++)
     {
@@ -695,7 +698,7 @@ int FSolver::WriteStatic2D(CBigLinProb &L)
             if (circproplist[i].Case == 1) fprintf(fp, "1\t%.17g\n", circproplist[i].J.Re());
         }
     }
-    write_tail(*this, fp);
+    write_tail(*this, fp, false);
     fclose(fp);
     return true;
 }
@@ -744,9 +747,10 @@ int FSolver::WriteHarmonic2D(CBigComplexLinProb &L)
         {
             if (circproplist[i].Case == 0) fprintf(fp, "0\t%.17g\t%.17g\n", circproplist[i].dV.Re(), circproplist[i].dV.Im());
             if (circproplist[i].Case == 1) fprintf(fp, "1\t%.17g\t%.17g\n", circproplist[i].J.Re(), circproplist[i].J.Im());
+            if (circproplist[i].Case == 2) fprintf(fp, "0\t%.17g\t%.17g\n", L.b[NumNodes + i].Re(), L.b[NumNodes + i].Im());
         }
     }
-    write_tail(*this, fp);
+    write_tail(*this, fp, true);
     fclose(fp);
     return true;
 }

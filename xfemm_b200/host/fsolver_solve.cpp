@@ -42,6 +42,7 @@ static double wall() { return std::chrono::duration<double>(std::chrono::steady_
 void FSolver::releaseDevice()
 {
     if (magdev) { xfemm_mag_destroy(magdev); magdev = nullptr; }
+    if (cmagdev) { xfemm_cmag_destroy(cmagdev); cmagdev = nullptr; }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -247,7 +248,7 @@ int FSolver::StaticAxisymmetric(CBigLinProb &L) { return staticSolve(L, true); }
 // ---------------------------------------------------------------------------------------
 // shared set-up pieces
 // ---------------------------------------------------------------------------------------
-namespace
+namespace xbhost
 {
 // Flattens the air-gap elements into ring cells: 10 nodes + 10 weights per cell and one 10x10
 // matrix per AGE (static2d.cpp:192-343).
@@ -297,7 +298,8 @@ void flatten_age(const std::vector<CAirGapElement> &agelist, std::vector<int> &n
         }
     }
 }
-} // namespace
+} // namespace xbhost
+using xbhost::flatten_age;
 
 // ---------------------------------------------------------------------------------------
 // magnetostatics
@@ -676,8 +678,4 @@ int FSolver::staticNewton(CBigLinProb &L)
 int FSolver::Harmonic2D(CBigComplexLinProb &L, bool verbose) { return harmonicSolve(L, false, verbose); }
 int FSolver::HarmonicAxisymmetric(CBigComplexLinProb &L, bool verbose) { return harmonicSolve(L, true, verbose); }
 
-int FSolver::harmonicSolve(CBigComplexLinProb &, bool, bool)
-{
-    WarnMessage("xfemm_b200: time-harmonic formulations are not available in this build\n");
-    return false;
-}
+// harmonicSolve lives in fsolver_harmonic.cpp
