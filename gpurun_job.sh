@@ -1,2 +1,2 @@
 set -x
-python -m pytest tests/test_gpu_harmonic.py -m gpu -x -q -s 2>&1 | tail -40
+python -m pytest tests/test_gpu_sweep.py -m gpu -x -q -s 2>&1 | tail -40

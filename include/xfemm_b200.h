@@ -303,6 +303,12 @@ int xfemm_fsolver_solve(xfemm_fsolver *s);     /* Static2D / StaticAxisymmetric 
 /* re-runs assembly + boundary conditions + solve (the whole Newton loop) on the device objects
  * left resident by xfemm_fsolver_solve: no host set-up, no mesh upload */
 int xfemm_fsolver_resolve(xfemm_fsolver *s);
+/* Rotor-angle sweeps without re-meshing: regenerates the ring tables of air-gap element
+ * `age_index` for new inner (rotor) / outer (stator) angles in degrees, as fmesher would write
+ * them into the .pbc file (cfemm/fmesher/writepoly.cpp:1853-1966).  Follow with
+ * xfemm_fsolver_solve, or with xfemm_fsolver_resolve if the problem was solved with option
+ * "age_union_pattern" = 1 (pattern independent of the angle). */
+int xfemm_fsolver_set_rotor_angle(xfemm_fsolver *s, int age_index, double inner_angle_deg, double outer_angle_deg);
 int xfemm_fsolver_write(xfemm_fsolver *s);     /* WriteStatic2D / WriteHarmonic2D                  */
 int xfemm_fsolver_close(xfemm_fsolver *s);
 int xfemm_fsolver_counts(xfemm_fsolver *s, int *n_nodes, int *n_elems, int *n_pbc, int *n_age,

@@ -118,6 +118,7 @@ SIGNATURES = {
     "xfemm_fsolver_renumber": (C.c_int, [_P, C.c_int]),
     "xfemm_fsolver_solve": (C.c_int, [_P]),
     "xfemm_fsolver_resolve": (C.c_int, [_P]),
+    "xfemm_fsolver_set_rotor_angle": (C.c_int, [_P, C.c_int, C.c_double, C.c_double]),
     "xfemm_fsolver_write": (C.c_int, [_P]),
     "xfemm_fsolver_close": (C.c_int, [_P]),
     "xfemm_fsolver_counts": (C.c_int, [_P] + [C.POINTER(C.c_int)] * 7),
@@ -357,6 +358,10 @@ class FSolver:
     def resolve(self):
         """Re-runs the Newton loop (assembly + BCs + solve) on the resident device problem."""
         _check(lib().xfemm_fsolver_resolve(self.h), "resolve")
+
+    def set_rotor_angle(self, inner_deg, outer_deg=0.0, age_index=0):
+        """Re-targets an air-gap element to a new rotor angle without re-meshing."""
+        _check(lib().xfemm_fsolver_set_rotor_angle(self.h, age_index, float(inner_deg), float(outer_deg)), "set_rotor_angle")
 
     def write(self):
         _check(lib().xfemm_fsolver_write(self.h), "write")

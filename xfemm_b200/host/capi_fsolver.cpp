@@ -120,6 +120,17 @@ int xfemm_fsolver_resolve(xfemm_fsolver *s)
     return XFEMM_OK;
 }
 
+int xfemm_fsolver_set_rotor_angle(xfemm_fsolver *s, int age_index, double inner_angle_deg, double outer_angle_deg)
+{
+    if (!s) return XFEMM_ERR_ARG;
+    if (!s->S.setAirGapAngles(age_index, inner_angle_deg, outer_angle_deg))
+    {
+        xb::set_error("cannot re-target air-gap element %d", age_index);
+        return XFEMM_ERR_ARG;
+    }
+    return XFEMM_OK;
+}
+
 int xfemm_fsolver_write(xfemm_fsolver *s)
 {
     if (!s) return XFEMM_ERR_ARG;
@@ -256,6 +267,7 @@ int xfemm_fsolver_set_option(xfemm_fsolver *s, const char *key, double value)
     if (!strcmp(key, "precond")) { s->S.precondOption = (int)value; return XFEMM_OK; }
     if (!strcmp(key, "max_iter")) { s->S.maxIterOption = (int)value; return XFEMM_OK; }
     if (!strcmp(key, "keep_system")) { s->S.keepSystem = value != 0; return XFEMM_OK; }
+    if (!strcmp(key, "age_union_pattern")) { s->S.ageUnionPattern = value != 0; return XFEMM_OK; }
     xb::set_error("unknown option %s", key);
     return XFEMM_ERR_ARG;
 }

@@ -258,8 +258,11 @@ public:
     {
         std::vector<int> dirNodes, pbcI, pbcJ, pbcT;
         std::vector<double> dirFirst, dirLast, labelJsrc;
-        bool linear = true, ready = false;
+        bool linear = true, ready = false, ageDirty = false;
     } plan;
+    bool ageUnionPattern;        // couple all ring nodes of an air-gap element structurally (sweeps)
+    // regenerates the ring tables of air-gap element `ageIndex` for new rotor/stator angles [deg]
+    bool setAirGapAngles(int ageIndex, double innerAngle, double outerAngle);
     int staticNewton(CBigLinProb &L); // re-runnable on the resident device problem
     // optional host snapshot of the last assembled + boundary-conditioned system (parity tests)
     bool keepSystem;

@@ -109,6 +109,7 @@ FSolver::FSolver()
     magdev = nullptr;
     cmagdev = nullptr;
     keepSystem = false;
+    ageUnionPattern = false;
 }
 
 FSolver::~FSolver() { releaseDevice(); }

@@ -530,7 +530,20 @@ int FSolver::staticSolve(CBigLinProb &L, bool axi)
     double t0 = wall();
     int *rowptr = nullptr, *colidx = nullptr;
     unsigned char *fillmask = nullptr;
-    if (xfemm_pattern_build(NumNodes, NumEls, tri.data(), 4, (int)ageMid.size(), ageNodes.data(), 0, nullptr, nullptr,
+    // rotor-angle sweeps re-target the air-gap tables on the resident problem: couple every pair of
+    // ring nodes structurally so the pattern does not depend on the angle (2n ring nodes, n = 96)
+    std::vector<int> exI, exJ;
+    if (ageUnionPattern)
+        for (const auto &g : agelist)
+        {
+            std::vector<int> ring;
+            for (const auto &q : g.quadNode) { ring.push_back(q.n0); ring.push_back(q.n1); ring.push_back(q.n2); ring.push_back(q.n3); }
+            std::sort(ring.begin(), ring.end());
+            ring.erase(std::unique(ring.begin(), ring.end()), ring.end());
+            for (size_t a = 0; a < ring.size(); a++)
+                for (size_t b = a; b < ring.size(); b++) { exI.push_back(ring[a]); exJ.push_back(ring[b]); }
+        }
+    if (xfemm_pattern_build(NumNodes, NumEls, tri.data(), 4, (int)ageMid.size(), ageNodes.data(), (int)exI.size(), exI.data(), exJ.data(),
                             NumPBCs, pbcI.data(), pbcJ.data(), &rowptr, &colidx, keepSystem ? &fillmask : nullptr) != XFEMM_OK)
     {
         WarnMessage(xfemm_last_error());
@@ -585,6 +598,19 @@ int FSolver::staticNewton(CBigLinProb &L)
     int rc;
     Relax = 1.;
     stats.pcg_iters.clear(); stats.pcg_ms.clear(); stats.assemble_ms.clear();
+    if (plan.ageDirty)
+    {
+        std::vector<int> ageNodes, ageMid;
+        std::vector<double> ageW, ageMats;
+        flatten_age(agelist, ageNodes, ageW, ageMid, ageMats, false);
+        if (xfemm_mag_set_age(magdev, (int)ageMid.size(), ageNodes.data(), ageW.data(), ageMid.data(),
+                              (int)(ageMats.size() / 100), ageMats.data()) != XFEMM_OK)
+        {
+            WarnMessage(xfemm_last_error());
+            return false;
+        }
+        plan.ageDirty = false;
+    }
     const int precond = precondOption >= 0 ? precondOption : L.precond;
     int Iter = 0;
     double res = 0, lastres = 0;
@@ -679,3 +705,62 @@ int FSolver::Harmonic2D(CBigComplexLinProb &L, bool verbose) { return harmonicSo
 int FSolver::HarmonicAxisymmetric(CBigComplexLinProb &L, bool verbose) { return harmonicSolve(L, true, verbose); }
 
 // harmonicSolve lives in fsolver_harmonic.cpp
+
+// ---------------------------------------------------------------------------------------
+// Rotor position without re-meshing.  fmesher rebuilds the ring tables of an
+// air-gap element from the boundary nodes, their angular positions and the inner/outer angle
+// (cfemm/fmesher/writepoly.cpp:1853-1966); the mesh itself does not depend on the angle.  The same
+// table is regenerated here from the table already loaded: ring nodes are mapped onto the annulus
+// grid for every periodic copy, sorted by angle, and bracketed per annulus cell.
+// ---------------------------------------------------------------------------------------
+bool FSolver::setAirGapAngles(int ageIndex, double innerAngle, double outerAngle)
+{
+    if (ageIndex < 0 || ageIndex >= (int)agelist.size()) return false;
+    CAirGapElement &g = agelist[ageIndex];
+    const int n = g.totalArcElements;
+    if (n <= 0 || (int)g.quadNode.size() != n + 1) return false;
+    const double dtta = g.totalArcLength / n;
+    const int n0 = (int)std::lround(360. / dtta);
+    const int n1 = (int)std::lround(360. / g.totalArcLength);
+    // the n distinct boundary nodes of each ring, in the order they first appear in the table
+    std::vector<int> inner, outer;
+    auto push_unique = [](std::vector<int> &v, int x) { if (std::find(v.begin(), v.end(), x) == v.end()) v.push_back(x); };
+    for (const auto &q : g.quadNode) { push_unique(inner, q.n0); push_unique(inner, q.n1); push_unique(outer, q.n2); push_unique(outer, q.n3); }
+    if ((int)inner.size() != n || (int)outer.size() != n) return false;
+    const double cm = 100 * LengthConvMeters[LengthUnits];
+    const cplx agc(g.agc.re * cm, g.agc.im * cm);
+    struct RingPt { int node; double z, sgn; };
+    auto build = [&](const std::vector<int> &nodes, double angle) {
+        std::vector<RingPt> ring;
+        ring.reserve(n0);
+        for (int j = 0; j < n1; j++)
+        {
+            const double dL = ((g.BdryFormat == 1) && (j % 2 != 0)) ? -1 : 1;
+            const cplx rot = std::exp(cplx(0, 1) * ((j * g.totalArcLength + angle) * 0.017453292519943295));
+            for (int node : nodes)
+            {
+                cplx a0 = rot * (cplx(meshnode[node].x, meshnode[node].y) - agc);
+                double ang = (a0.imag() >= 0) ? std::arg(a0) : (std::arg(a0) + 2. * PI);
+                ring.push_back({node, ang * (180. / PI) / dtta, dL});
+            }
+        }
+        std::stable_sort(ring.begin(), ring.end(), [](const RingPt &a, const RingPt &b) { return a.z < b.z; });
+        return ring;
+    };
+    std::vector<RingPt> I = build(inner, innerAngle), O = build(outer, outerAngle);
+    if ((int)I.size() != n0 || (int)O.size() != n0) return false;
+    g.InnerAngle = innerAngle;
+    g.OuterAngle = outerAngle;
+    g.InnerShift = I[0].z;
+    g.OuterShift = O[0].z;
+    for (int i = 0; i <= n; i++)
+    {
+        int p1 = i; if (p1 == n0) p1 = 0;
+        int p0 = p1 - 1; if (p0 < 0) p0 = n0 + p0;
+        CQuadPoint &q = g.quadNode[i];
+        q.n0 = I[p0].node; q.w0 = I[p0].sgn; q.n1 = I[p1].node; q.w1 = I[p1].sgn;
+        q.n2 = O[p0].node; q.w2 = O[p0].sgn; q.n3 = O[p1].node; q.w3 = O[p1].sgn;
+    }
+    plan.ageDirty = true;
+    return true;
+}
