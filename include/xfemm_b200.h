@@ -74,6 +74,7 @@ typedef struct xfemm_solve_info
 int xfemm_linprob_create(int n, const int *rowptr, const int *colidx, xfemm_linprob **out);
 int xfemm_linprob_destroy(xfemm_linprob *p);
 int xfemm_linprob_n(const xfemm_linprob *p);
+int xfemm_linprob_get_pattern(xfemm_linprob *p, int *rowptr, int *colidx); /* host copy of the CSR pattern; either may be NULL */
 long long xfemm_linprob_nnz(const xfemm_linprob *p);
 int xfemm_linprob_wipe(xfemm_linprob *p);                               /* spars.cpp:348 Wipe  */
 int xfemm_linprob_set_values(xfemm_linprob *p, const double *vals_csr); /* H2D, CSR order      */
@@ -291,6 +292,27 @@ int xfemm_cmag_fix_circuit_diagonals(xfemm_cmag *m);
 int xfemm_cmag_get_mu(xfemm_cmag *m, double *mu4);               /* n_elems*4: mu1.re, mu1.im, mu2.re, mu2.im */
 int xfemm_cmag_solution_to_A(xfemm_cmag *m, double *A_host);      /* n complex: A (nodes) and circuit results  */
 
+/* ------------------------------------------------------------------ row-block partitioned PCG (one mesh, several GPUs)
+ * Every rank holds the assembled, boundary-conditioned global problem `g` on its GPU and owns rows
+ * [r0,r1) of it.  The caller (one process per GPU) moves the halo of the search direction and
+ * all-reduces the scalars with torch.distributed/NCCL over NVLink; buffers named *_dev are DEVICE
+ * pointers.  glob_dev = 3 doubles on the device: [res, pAp, res_new], already all-reduced. */
+typedef struct xfemm_dist xfemm_dist;
+int xfemm_dist_create(xfemm_linprob *g, int r0, int r1, xfemm_dist **out);
+int xfemm_dist_destroy(xfemm_dist *d);
+int xfemm_dist_sizes(xfemm_dist *d, int *n_own, int *n_halo);
+int xfemm_dist_halo_columns(xfemm_dist *d, int *global_cols);              /* sorted global ids this rank needs */
+int xfemm_dist_set_send_rows(xfemm_dist *d, int n_send, const int *global_rows);
+int xfemm_dist_refresh(xfemm_dist *d);                                     /* pull owned rows of values + RHS from g */
+int xfemm_dist_init(xfemm_dist *d, double *scal_dev);                      /* x=0, r=b, p=D^-1 r ; scal = local r.D^-1 r */
+int xfemm_dist_pack(xfemm_dist *d, double *sendbuf_dev);
+int xfemm_dist_unpack(xfemm_dist *d, const double *recvbuf_dev);
+int xfemm_dist_spmv_dot(xfemm_dist *d, double *scal_dev);                  /* u = A p ; scal = local p.u */
+int xfemm_dist_update(xfemm_dist *d, const double *glob_dev, double *scal_dev); /* x,r update ; scal = local r.D^-1 r */
+int xfemm_dist_direction(xfemm_dist *d, const double *glob_dev);           /* p = D^-1 r + (res_new/res) p */
+int xfemm_dist_get_solution(xfemm_dist *d, double *x_own);
+unsigned long long xfemm_dist_stream(xfemm_dist *d);                       /* cudaStream_t the kernels run on */
+
 /* ------------------------------------------------------------------ file-level entry
  * The call a user of fsolver / mexfsolver makes: basename without ".fem";
  * returns 0 ok, 1 problem loading .fem, 2 solve failed (main.cpp:72-83, mexfsolver.cpp:122-134). */
@@ -313,6 +335,7 @@ int xfemm_fsolver_write(xfemm_fsolver *s);     /* WriteStatic2D / WriteHarmonic2
 int xfemm_fsolver_close(xfemm_fsolver *s);
 int xfemm_fsolver_counts(xfemm_fsolver *s, int *n_nodes, int *n_elems, int *n_pbc, int *n_age,
                          int *bandwidth, int *n_unknowns, int *is_complex);
+xfemm_linprob *xfemm_fsolver_linprob(xfemm_fsolver *s);                  /* resident real system (owned by s), or NULL */
 long long xfemm_fsolver_nnz(xfemm_fsolver *s);                           /* full-CSR nonzeros of the resident system */
 int xfemm_fsolver_get_nodes(xfemm_fsolver *s, double *xy, int *bc);      /* solver order, cm      */
 int xfemm_fsolver_get_elems(xfemm_fsolver *s, int *elems8);              /* p0 p1 p2 lbl blk e0-2 */

@@ -112,6 +112,22 @@ SIGNATURES = {
     "xfemm_cmag_fix_circuit_diagonals": (C.c_int, [_P]),
     "xfemm_cmag_get_mu": (C.c_int, [_P, _P]),
     "xfemm_cmag_solution_to_A": (C.c_int, [_P, _P]),
+    "xfemm_linprob_get_pattern": (C.c_int, [_P, _P, _P]),
+    "xfemm_dist_create": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P)]),
+    "xfemm_dist_destroy": (C.c_int, [_P]),
+    "xfemm_dist_sizes": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "xfemm_dist_halo_columns": (C.c_int, [_P, _ip]),
+    "xfemm_dist_set_send_rows": (C.c_int, [_P, C.c_int, _P]),
+    "xfemm_dist_refresh": (C.c_int, [_P]),
+    "xfemm_dist_init": (C.c_int, [_P, _P]),
+    "xfemm_dist_pack": (C.c_int, [_P, _P]),
+    "xfemm_dist_unpack": (C.c_int, [_P, _P]),
+    "xfemm_dist_spmv_dot": (C.c_int, [_P, _P]),
+    "xfemm_dist_update": (C.c_int, [_P, _P, _P]),
+    "xfemm_dist_direction": (C.c_int, [_P, _P]),
+    "xfemm_dist_get_solution": (C.c_int, [_P, _dp]),
+    "xfemm_dist_stream": (C.c_ulonglong, [_P]),
+    "xfemm_fsolver_linprob": (_P, [_P]),
     "xfemm_fsolver_run": (C.c_int, [C.c_char_p, C.c_int]),
     "xfemm_fsolver_open": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(_P)]),
     "xfemm_fsolver_load_mesh": (C.c_int, [_P, C.c_int]),
@@ -177,6 +193,10 @@ def _f64(a):
 
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def check(rc, what="xfemm"):
+    _check(rc, what)
 
 
 def age_cell_matrix(ci, co, K):

@@ -783,6 +783,13 @@ int xfemm_linprob_destroy(xfemm_linprob *p)
 }
 
 int xfemm_linprob_n(const xfemm_linprob *p) { return p ? p->n : 0; }
+int xfemm_linprob_get_pattern(xfemm_linprob *p, int *rowptr, int *colidx)
+{
+    XB_ARG(p, "null handle");
+    if (rowptr) std::copy(p->h_rowptr.begin(), p->h_rowptr.end(), rowptr);
+    if (colidx) std::copy(p->h_col.begin(), p->h_col.end(), colidx);
+    return XFEMM_OK;
+}
 long long xfemm_linprob_nnz(const xfemm_linprob *p) { return p ? p->nnz : 0; }
 
 int xfemm_linprob_wipe(xfemm_linprob *p)
@@ -933,6 +940,37 @@ static int prepare_solver(xfemm_linprob *p, int precond, int *singular)
     if (rc != XFEMM_OK) return rc;
     return refresh_values(p, singular);
 }
+
+} // extern "C"  (internal helpers shared with dist.cu follow)
+
+namespace xb {
+// layout + SELL refill + diagonal for `precond`; XFEMM_ERR_SINGULAR on a zero diagonal
+int linprob_prepare(xfemm_linprob *p, int precond)
+{
+    int singular = -1;
+    int rc = prepare_solver(p, precond, &singular);
+    if (rc != XFEMM_OK) return rc;
+    if (singular >= 0) { set_error("singular flag tripped at internal row %d of %d", singular, p->n); return XFEMM_ERR_SINGULAR; }
+    return XFEMM_OK;
+}
+// bint = b in internal order ; V = x back in caller order
+int linprob_load_rhs_internal(xfemm_linprob *p)
+{
+    const int n_pad = p->lay.n_pad;
+    ++g_launch, k_to_internal<<<(n_pad + 255) / 256, 256, 0, p->stream>>>(n_pad, p->i2c.p, p->b.p, p->bint.p);
+    XB_CUDA(cudaGetLastError());
+    return XFEMM_OK;
+}
+int linprob_store_solution_internal(xfemm_linprob *p)
+{
+    const int n_pad = p->lay.n_pad;
+    ++g_launch, k_from_internal<<<(n_pad + 255) / 256, 256, 0, p->stream>>>(n_pad, p->i2c.p, p->x.p, p->V.p);
+    XB_CUDA(cudaGetLastError());
+    return XFEMM_OK;
+}
+} // namespace xb
+
+extern "C" {
 
 int xfemm_linprob_pcg(xfemm_linprob *p, double precision, int warm, int precond, int max_iter,
                       xfemm_solve_info *info)

@@ -57,4 +57,7 @@ struct xfemm_linprob
 
 namespace xb {
 int linprob_build_layout(xfemm_linprob *p, int precond);
+int linprob_prepare(xfemm_linprob *p, int precond);
+int linprob_load_rhs_internal(xfemm_linprob *p);
+int linprob_store_solution_internal(xfemm_linprob *p);
 } // namespace xb

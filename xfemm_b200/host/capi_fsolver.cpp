@@ -156,6 +156,8 @@ int xfemm_fsolver_counts(xfemm_fsolver *s, int *n_nodes, int *n_elems, int *n_pb
     return XFEMM_OK;
 }
 
+xfemm_linprob *xfemm_fsolver_linprob(xfemm_fsolver *s) { return (s && s->L) ? s->L->device() : nullptr; }
+
 long long xfemm_fsolver_nnz(xfemm_fsolver *s)
 {
     if (!s || !s->L || !s->L->device()) return 0;
@@ -267,6 +269,7 @@ int xfemm_fsolver_set_option(xfemm_fsolver *s, const char *key, double value)
     if (!strcmp(key, "precond")) { s->S.precondOption = (int)value; return XFEMM_OK; }
     if (!strcmp(key, "max_iter")) { s->S.maxIterOption = (int)value; return XFEMM_OK; }
     if (!strcmp(key, "keep_system")) { s->S.keepSystem = value != 0; return XFEMM_OK; }
+    if (!strcmp(key, "assemble_only")) { s->S.assembleOnly = value != 0; return XFEMM_OK; }
     if (!strcmp(key, "age_union_pattern")) { s->S.ageUnionPattern = value != 0; return XFEMM_OK; }
     xb::set_error("unknown option %s", key);
     return XFEMM_ERR_ARG;

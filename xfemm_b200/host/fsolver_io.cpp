@@ -110,6 +110,7 @@ FSolver::FSolver()
     cmagdev = nullptr;
     keepSystem = false;
     ageUnionPattern = false;
+    assembleOnly = false;
 }
 
 FSolver::~FSolver() { releaseDevice(); }

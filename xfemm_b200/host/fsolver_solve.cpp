@@ -648,6 +648,7 @@ int FSolver::staticNewton(CBigLinProb &L)
                 sysRowptr[i + 1] = (int)sysCol.size();
             }
         }
+        if (assembleOnly) { stats.newton_iters = 0; return true; } // the caller solves (row-partitioned PCG)
         xfemm_linprob_save_solution(lin); // V_old = V
         PrintMessage("Conjugate Gradient Solver\n");
         xfemm_solve_info info;
