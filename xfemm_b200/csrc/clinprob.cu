@@ -141,7 +141,7 @@ __device__ __forceinline__ cd csell_row(const cd *__restrict__ val, const int *_
 
 __global__ void __launch_bounds__(256)
 kc_spmv(int nslices, const int *__restrict__ slice_ptr, const int *__restrict__ sell_col, const cd *__restrict__ sell_val,
-        const cd *__restrict__ diag, const cd *x, cd *y)
+        const cd *__restrict__ diag, const cd *x, cd *y, const unsigned *__restrict__ wide_mask)
 {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -150,6 +150,7 @@ kc_spmv(int nslices, const int *__restrict__ slice_ptr, const int *__restrict__ 
     {
         const int base = slice_ptr[s], w = (slice_ptr[s + 1] - base) >> 5, row = s * 32 + lane;
         cd acc = csell_row(sell_val, sell_col, base, 0, w, lane, x);
+        if (wide_mask && ((wide_mask[s] >> lane) & 1u)) acc = w_add(acc, y[row]); // left there by k_wide_pre
         y[row] = cfma(diag[row], x[row], acc);
     }
 }
@@ -164,6 +165,9 @@ struct CocgArgs
     double precision, omega;
     int max_iter, warm;
     double *mail;
+    WideView wide;
+    const cd *wide_val;
+    cd *wide_acc;
 };
 
 __device__ __forceinline__ int cnext_slice(int *ctr, int lane)
@@ -247,6 +251,8 @@ __global__ void __launch_bounds__(512, 1) k_cocg(CocgArgs a)
     const int s1 = (int)((long long)a.nslices * (blockIdx.x + 1) / G);
     const int r0 = s0 * 32, r1 = s1 * 32;
     double *partA = a.part, *partB = a.part + 2 * G, *partC = a.part + 4 * G;
+    int wk0 = 0, wk1 = 0; // wide rows (circuit rows, air-gap rings) of this block's chunk
+    if (a.wide.n_rows) wide_range(a.wide, r0, r1, wk0, wk1);
 
     // ||b||^2 ; r = b ; x = 0 unless warm
     double pn = 0.0;
@@ -270,12 +276,14 @@ __global__ void __launch_bounds__(512, 1) k_cocg(CocgArgs a)
     }
     if (a.warm)
     {
+        wide_rows_block<cd>(a.wide, a.wide_val, a.wide_acc, wk0, wk1, a.x, a.u);
         if (threadIdx.x == 0) s_next = s0;
         __syncthreads();
         for (int s = cnext_slice(&s_next, lane); s < s1; s = cnext_slice(&s_next, lane))
         {
             const int base = a.slice_ptr[s], w = (a.slice_ptr[s + 1] - base) >> 5, row = s * 32 + lane;
             cd acc = csell_row(a.sell_val, a.sell_col, base, 0, w, lane, a.x);
+            if (wk1 > wk0 && ((a.wide.mask[s] >> lane) & 1u)) acc = w_add(acc, a.u[row]);
             a.r[row] = csub(a.b[row], cfma(a.diag[row], a.x[row], acc));
         }
         grid.sync();
@@ -294,12 +302,14 @@ __global__ void __launch_bounds__(512, 1) k_cocg(CocgArgs a)
     {
         // u = A p ; p.u (unconjugated)
         part = make_double2(0., 0.);
+        wide_rows_block<cd>(a.wide, a.wide_val, a.wide_acc, wk0, wk1, a.p, a.u);
         if (threadIdx.x == 0) s_next = s0;
         __syncthreads();
         for (int s = cnext_slice(&s_next, lane); s < s1; s = cnext_slice(&s_next, lane))
         {
             const int base = a.slice_ptr[s], w = (a.slice_ptr[s + 1] - base) >> 5, row = s * 32 + lane;
             cd acc = csell_row(a.sell_val, a.sell_col, base, 0, w, lane, a.p);
+            if (wk1 > wk0 && ((a.wide.mask[s] >> lane) & 1u)) acc = w_add(acc, a.u[row]);
             const cd pr = a.p[row];
             acc = cfma(a.diag[row], pr, acc);
             a.u[row] = acc;
@@ -475,10 +485,10 @@ static int cbuild_layout(xfemm_clinprob *p, int precond)
     {
         std::vector<int> color;
         int nc = greedy_coloring(p->n, p->h_rowptr.data(), p->h_col.data(), cenv_int("XFEMM_MAX_COLORS", 7), color);
-        build_sell_layout(p->n, p->h_rowptr.data(), p->h_col.data(), &color, nc, sigma, L);
+        build_sell_layout(p->n, p->h_rowptr.data(), p->h_col.data(), &color, nc, sigma, L, cenv_int("XFEMM_WIDE_ROW", 64));
     }
     else
-        build_sell_layout(p->n, p->h_rowptr.data(), p->h_col.data(), nullptr, 0, sigma, L);
+        build_sell_layout(p->n, p->h_rowptr.data(), p->h_col.data(), nullptr, 0, sigma, L, cenv_int("XFEMM_WIDE_ROW", 64));
     cudaStream_t st = p->stream;
     XB_CUDA(p->i2c.upload(L.i2c.data(), L.i2c.size(), st));
     XB_CUDA(p->c2i.upload(L.c2i.data(), L.c2i.size(), st));
@@ -489,6 +499,7 @@ static int cbuild_layout(xfemm_clinprob *p, int precond)
     XB_CUDA(p->sell_src.upload(L.sell_src.data(), L.sell_src.size(), st));
     XB_CUDA(p->diag_src.upload(L.diag_src.data(), L.diag_src.size(), st));
     XB_CUDA(p->color_slice.upload(L.color_slice.data(), L.color_slice.size(), st));
+    XB_CUDA(p->wide.upload(L, st));
     XB_CUDA(p->sell_val.alloc(L.sell_len));
     for (auto *v : {&p->diag, &p->dinv, &p->x, &p->r, &p->p, &p->u, &p->z, &p->w, &p->bint})
     {
@@ -499,6 +510,8 @@ static int cbuild_layout(xfemm_clinprob *p, int precond)
     std::vector<int>().swap(L.sell_col);
     std::vector<int>().swap(L.sell_src);
     std::vector<int>().swap(L.diag_src);
+    std::vector<int>().swap(L.wide_col);
+    std::vector<int>().swap(L.wide_src);
     p->layout_precond = precond;
     return XFEMM_OK;
 }
@@ -512,6 +525,7 @@ static int crefresh_values(xfemm_clinprob *p, int *singular_row)
     XB_CUDA(cudaMemcpyAsync(d_flag, &big, sizeof(int), cudaMemcpyHostToDevice, st));
     int blocks = (int)std::max<long long>(1, std::min<long long>((L.sell_len + 255) / 256, (long long)p->num_sms * 16));
     ++g_launch, kc_sell_fill<<<blocks, 256, 0, st>>>(L.sell_len, p->sell_src.p, p->vals.p, p->sell_val.p);
+    p->wide.fill(p->vals.p, st);
     ++g_launch, kc_diag_fill<<<(L.n_pad + 255) / 256, 256, 0, st>>>(L.n_pad, p->diag_src.p, p->vals.p, p->diag.p, p->dinv.p, d_flag);
     int flag = 0;
     XB_CUDA(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -535,6 +549,7 @@ static CocgArgs cmake_args(xfemm_clinprob *p, double precision, int warm, int ma
     a.omega = om ? atof(om) : 1.2;
     a.max_iter = max_iter; a.warm = warm;
     a.mail = p->d_mail.p;
+    a.wide = p->wide.view(); a.wide_val = p->wide.val.p; a.wide_acc = p->wide.acc.p;
     return a;
 }
 
@@ -746,7 +761,9 @@ int xfemm_clinprob_cocg(xfemm_clinprob *p, double precision, int warm, int preco
     {
         // ---- PCGSQStart with M = D: operator T y = conj(A D^-1 conj(D^-1 A y)), rhs g = conj(A D^-1 conj(D^-1 b))
         auto spmv = [&](const cd *in, cd *out) {
-            ++g_launch, kc_spmv<<<sb, 256, 0, st>>>(p->lay.nslices, p->slice_ptr.p, p->sell_col.p, p->sell_val.p, p->diag.p, in, out);
+            p->wide.pre(in, out, st);
+            ++g_launch, kc_spmv<<<sb, 256, 0, st>>>(p->lay.nslices, p->slice_ptr.p, p->sell_col.p, p->sell_val.p, p->diag.p, in, out,
+                                                    p->wide.n_rows ? p->wide.mask.p : nullptr);
         };
         auto applyT = [&](const cd *in, cd *out, cd *tmp) {
             spmv(in, tmp);                                                         // tmp = A in
@@ -807,7 +824,9 @@ int xfemm_clinprob_cocg(xfemm_clinprob *p, double precision, int warm, int preco
     local.status = (int)p->h_mail[2];
     ++g_launch, kc_from_internal<<<nb, 256, 0, st>>>(n_pad, p->i2c.p, p->x.p, p->V.p);
     // true relative residual
-    ++g_launch, kc_spmv<<<sb, 256, 0, st>>>(p->lay.nslices, p->slice_ptr.p, p->sell_col.p, p->sell_val.p, p->diag.p, p->x.p, p->u.p);
+    p->wide.pre(p->x.p, p->u.p, st);
+    ++g_launch, kc_spmv<<<sb, 256, 0, st>>>(p->lay.nslices, p->slice_ptr.p, p->sell_col.p, p->sell_val.p, p->diag.p, p->x.p, p->u.p,
+                                            p->wide.n_rows ? p->wide.mask.p : nullptr);
     int nb2 = std::max(1, std::min(nb, 512));
     if (p->max_grid < nb2) { XB_CUDA(p->partials.alloc((size_t)8 * nb2)); p->max_grid = nb2; }
     ++g_launch, kc_resnorm_partial<<<nb2, 256, 0, st>>>(n_pad, p->bint.p, p->u.p, p->partials.p);

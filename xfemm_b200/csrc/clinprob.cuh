@@ -2,6 +2,7 @@
 #pragma once
 #include "common.cuh"
 #include "layout.h"
+#include "wide_rows.cuh"
 #include <vector>
 #include <cstdint>
 
@@ -21,6 +22,7 @@ struct xfemm_clinprob
     xb::DevBuf<int> i2c, c2i, slice_ptr, slice_wl, slice_wu, sell_col, sell_src, diag_src, color_slice;
     xb::DevBuf<cd> sell_val, diag, dinv, x, r, p, u, z, w, bint;
     xb::DevBuf<double> partials, d_mail;
+    xb::WideDev<cd> wide;
     int max_grid = 0;
     double h_mail[16];
     xb::DevBuf<int> dir_idx, dir_nodes;

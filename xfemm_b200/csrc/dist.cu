@@ -80,7 +80,8 @@ __global__ void kd_init(int n_pad, const unsigned char *__restrict__ owned, cons
 __global__ void __launch_bounds__(256)
 kd_spmv_dot(int nslices, const int *__restrict__ slice_ptr, const int *__restrict__ sell_col,
             const double *__restrict__ sell_val, const double *__restrict__ diag,
-            const unsigned char *__restrict__ owned, const double *p, double *u, double *part)
+            const unsigned char *__restrict__ owned, const double *p, double *u, double *part,
+            const unsigned *__restrict__ wide_mask)
 {
     __shared__ double sm[33];
     const int lane = threadIdx.x & 31;
@@ -95,6 +96,7 @@ kd_spmv_dot(int nslices, const int *__restrict__ slice_ptr, const int *__restric
         const int *c = sell_col + base + lane;
 #pragma unroll 8
         for (int k = 0; k < w; k++) acc = fma(__ldcs(v + k * 32), p[__ldcs(c + k * 32)], acc);
+        if (wide_mask && ((wide_mask[s] >> lane) & 1u)) acc += u[row]; // left there by k_wide_pre
         const double pr = p[row];
         acc = fma(diag[row], pr, acc);
         u[row] = acc;
@@ -287,8 +289,10 @@ int xfemm_dist_spmv_dot(xfemm_dist *d, double *scal_dev)
     XB_ARG(d && scal_dev, "null pointer");
     xfemm_linprob *L = d->loc;
     int sb = std::max(1, std::min((L->lay.nslices + 7) / 8, d->nblk));
+    L->wide.pre(L->p.p, L->u.p, L->stream);
     ++g_launch, kd_spmv_dot<<<sb, 256, 0, L->stream>>>(L->lay.nslices, L->slice_ptr.p, L->sell_col.p, L->sell_val.p, L->diag.p,
-                                                       d->owned.p, L->p.p, L->u.p, d->partials.p);
+                                                       d->owned.p, L->p.p, L->u.p, d->partials.p,
+                                                       L->wide.n_rows ? L->wide.mask.p : nullptr);
     ++g_launch, kd_reduce<<<1, 256, 0, L->stream>>>(sb, d->partials.p, scal_dev, 1);
     XB_CUDA(cudaGetLastError());
     return XFEMM_OK;

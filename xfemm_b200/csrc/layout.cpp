@@ -46,8 +46,15 @@ int greedy_coloring(int n, const int *rowptr, const int *col, int max_colors, st
 }
 
 void build_sell_layout(int n, const int *rowptr, const int *col, const std::vector<int> *color_in,
-                       int ncolors, int sigma, SellLayout &L)
+                       int ncolors, int sigma, SellLayout &L, int wide_threshold)
 {
+    // rows with more than `wide_threshold` off-diagonals leave the SELL structure (see layout.h)
+    std::vector<unsigned char> wide(n, 0);
+    bool any_wide = false;
+    if (wide_threshold > 0)
+        for (int i = 0; i < n; i++)
+            if (rowptr[i + 1] - rowptr[i] - 1 > wide_threshold) { wide[i] = 1; any_wide = true; }
+
     // ---- internal order: by colour (if any), inside a colour keep the caller's order, then
     // sort windows of `sigma` rows by their entry counts so slices are homogeneous.
     std::vector<int> order(n);
@@ -79,6 +86,7 @@ void build_sell_layout(int n, const int *rowptr, const int *col, const std::vect
     auto klass = [&](int i, int j, const std::vector<int> &rank) -> int {
         if (colored)
         {
+            if (wide[j]) return 2; // the partner row keeps no sweep coupling either → M stays symmetric
             int ci = (*color_in)[i], cj = (*color_in)[j];
             if (ci == cj) return 2;
             return cj < ci ? 0 : 1;
@@ -93,10 +101,11 @@ void build_sell_layout(int n, const int *rowptr, const int *col, const std::vect
         for (int i = 0; i < n; i++)
         {
             int c[3] = {0, 0, 0};
-            for (int s = rowptr[i]; s < rowptr[i + 1]; s++)
-                if (col[s] != i) c[klass(i, col[s], rank)]++;
+            if (!wide[i])
+                for (int s = rowptr[i]; s < rowptr[i + 1]; s++)
+                    if (col[s] != i) c[klass(i, col[s], rank)]++;
             key[i] = colored ? (std::min(c[0], 63) * 64 + std::min(c[1], 63)) * 64 + std::min(c[2], 63)
-                             : (rowptr[i + 1] - rowptr[i]);
+                             : (wide[i] ? 0 : rowptr[i + 1] - rowptr[i]);
         }
         for (int g = 0; g < ngroups; g++)
             for (int w0 = color_start[g]; w0 < color_start[g + 1]; w0 += sigma)
@@ -133,8 +142,9 @@ void build_sell_layout(int n, const int *rowptr, const int *col, const std::vect
         int i = L.i2c[r];
         if (i < 0) continue;
         int c[3] = {0, 0, 0};
-        for (int s = rowptr[i]; s < rowptr[i + 1]; s++)
-            if (col[s] != i) c[klass(i, col[s], L.c2i)]++;
+        if (!wide[i])
+            for (int s = rowptr[i]; s < rowptr[i + 1]; s++)
+                if (col[s] != i) c[klass(i, col[s], L.c2i)]++;
         L.n_extra += c[2];
         for (int q = 0; q < 3; q++) width[3 * (size_t)(r / 32) + q] = std::max(width[3 * (size_t)(r / 32) + q], c[q]);
     }
@@ -167,6 +177,7 @@ void build_sell_layout(int n, const int *rowptr, const int *col, const std::vect
             {
                 int j = col[q];
                 if (j == i) { L.diag_src[r] = q; continue; }
+                if (wide[i]) continue;
                 part[klass(i, j, L.c2i)].emplace_back(L.c2i[j], q);
             }
             for (int t = 0; t < 3; t++)
@@ -178,6 +189,34 @@ void build_sell_layout(int n, const int *rowptr, const int *col, const std::vect
                     L.sell_src[base + (off[t] + (int)k) * 32 + l] = part[t][k].second;
                 }
             }
+        }
+    }
+
+    // ---- wide rows: row-wise storage in segments
+    L.wide_row.clear(); L.wide_rseg.assign(1, 0); L.wide_sptr.assign(1, 0);
+    L.wide_col.clear(); L.wide_src.clear(); L.slice_wide.clear();
+    if (any_wide)
+    {
+        L.slice_wide.assign(L.nslices, 0u);
+        std::vector<std::pair<int, int>> ent;
+        for (int r = 0; r < L.n_pad; r++)
+        {
+            int i = L.i2c[r];
+            if (i < 0 || !wide[i]) continue;
+            L.slice_wide[r / 32] |= 1u << (r % 32);
+            L.wide_row.push_back(r);
+            ent.clear();
+            for (int q = rowptr[i]; q < rowptr[i + 1]; q++)
+                if (col[q] != i) ent.emplace_back(L.c2i[col[q]], q);
+            std::sort(ent.begin(), ent.end());
+            for (size_t k = 0; k < ent.size(); k++)
+            {
+                if (k && k % SellLayout::WIDE_SEG == 0) L.wide_sptr.push_back((int)L.wide_col.size());
+                L.wide_col.push_back(ent[k].first);
+                L.wide_src.push_back(ent[k].second);
+            }
+            L.wide_sptr.push_back((int)L.wide_col.size());
+            L.wide_rseg.push_back((int)L.wide_sptr.size() - 1);
         }
     }
 }

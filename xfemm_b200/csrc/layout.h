@@ -18,11 +18,22 @@ struct SellLayout
     std::vector<int> sell_col;    // internal column per slot (padding: own row)
     std::vector<int> sell_src;    // CSR index per slot (-1 padding)
     std::vector<int> diag_src;    // CSR index of the diagonal per internal row (-1 padding row)
+    // "wide" rows (more off-diagonals than the threshold: air-gap rings with the angle-independent
+    // pattern, circuit rows of the harmonic formulations) are kept OUT of the SELL slices — one of
+    // them would stretch a whole slice and a single warp would walk it — and stored row-wise in
+    // segments of <= WIDE_SEG entries that the warps of the owning block share.
+    static constexpr int WIDE_SEG = 256;
+    std::vector<int> wide_row;    // internal row per wide row, ascending
+    std::vector<int> wide_rseg;   // first segment of each wide row (n_wide+1)
+    std::vector<int> wide_sptr;   // segment offsets into wide_col/wide_src (n_seg+1)
+    std::vector<int> wide_col;    // internal column per entry
+    std::vector<int> wide_src;    // CSR index per entry
+    std::vector<unsigned> slice_wide; // per slice: bit l set = row 32*s+l is a wide row (empty if none)
 };
 
 int greedy_coloring(int n, const int *rowptr, const int *col, int max_colors, std::vector<int> &color);
 void build_sell_layout(int n, const int *rowptr, const int *col, const std::vector<int> *color,
-                       int ncolors, int sigma, SellLayout &L);
+                       int ncolors, int sigma, SellLayout &L, int wide_threshold = 64);
 
 } // namespace xb
 

@@ -95,7 +95,8 @@ __device__ __forceinline__ double sell_row_offdiag(const double *__restrict__ va
 
 __global__ void __launch_bounds__(256)
 k_spmv(int nslices, const int *__restrict__ slice_ptr, const int *__restrict__ sell_col,
-       const double *__restrict__ sell_val, const double *__restrict__ diag, const double *x, double *y)
+       const double *__restrict__ sell_val, const double *__restrict__ diag, const double *x, double *y,
+       const unsigned *__restrict__ wide_mask)
 {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -106,6 +107,7 @@ k_spmv(int nslices, const int *__restrict__ slice_ptr, const int *__restrict__ s
         const int w = (slice_ptr[s + 1] - base) >> 5;
         const int row = s * 32 + lane;
         double acc = sell_row_offdiag(sell_val, sell_col, base, 0, w, lane, x);
+        if (wide_mask && ((wide_mask[s] >> lane) & 1u)) acc += y[row]; // off-diagonal part left there by k_wide_pre
         y[row] = fma(diag[row], x[row], acc);
     }
 }
@@ -148,6 +150,9 @@ struct PcgArgs
     double precision, omega;
     int max_iter, warm;
     double *mail; // [0]=iters [1]=er [2]=status [3]=res_o [4]=res
+    WideView wide; // rows outside the SELL slices
+    const double *wide_val;
+    double *wide_acc;
 };
 
 // dynamic distribution of a block's slices over its warps (shared-memory ticket counter)
@@ -236,6 +241,8 @@ __global__ void __launch_bounds__(512, 2) k_pcg(PcgArgs a)
     const int s1 = (int)((long long)a.nslices * (blockIdx.x + 1) / G);
     const int r0 = s0 * 32, r1 = s1 * 32;
     double *partA = a.part, *partB = a.part + G;
+    int wk0 = 0, wk1 = 0; // wide rows of this block's chunk
+    if (a.wide.n_rows) wide_range(a.wide, r0, r1, wk0, wk1);
 
     // ---- res_o = b . M^-1 b   (spars.cpp:257-259) ; z0 is computed with r := b
     for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x)
@@ -257,10 +264,13 @@ __global__ void __launch_bounds__(512, 2) k_pcg(PcgArgs a)
     // ---- r = b - A x
     if (a.warm)
     {
+        wide_rows_block<double>(a.wide, a.wide_val, a.wide_acc, wk0, wk1, a.x, a.u);
+        __syncthreads();
         for (int s = s0 + warp_b; s < s1; s += nwarps_b)
         {
             const int base = a.slice_ptr[s], w = (a.slice_ptr[s + 1] - base) >> 5, row = s * 32 + lane;
             double acc = sell_row_offdiag(a.sell_val, a.sell_col, base, 0, w, lane, a.x);
+            if (wk1 > wk0 && ((a.wide.mask[s] >> lane) & 1u)) acc += a.u[row];
             a.r[row] = a.b[row] - fma(a.diag[row], a.x[row], acc);
         }
         grid.sync();
@@ -282,12 +292,14 @@ __global__ void __launch_bounds__(512, 2) k_pcg(PcgArgs a)
     {
         // step i: u = A p ; pAp   (warps of a block pull slices of the block's chunk dynamically)
         part = 0.0;
+        wide_rows_block<double>(a.wide, a.wide_val, a.wide_acc, wk0, wk1, a.p, a.u);
         if (threadIdx.x == 0) s_next = s0;
         __syncthreads();
         for (int s = next_slice(&s_next, lane); s < s1; s = next_slice(&s_next, lane))
         {
             const int base = a.slice_ptr[s], w = (a.slice_ptr[s + 1] - base) >> 5, row = s * 32 + lane;
             double acc = sell_row_offdiag(a.sell_val, a.sell_col, base, 0, w, lane, a.p);
+            if (wk1 > wk0 && ((a.wide.mask[s] >> lane) & 1u)) acc += a.u[row];
             const double pr = a.p[row];
             acc = fma(a.diag[row], pr, acc);
             a.u[row] = acc;
@@ -347,128 +359,6 @@ __global__ void __launch_bounds__(512, 2) k_pcg(PcgArgs a)
     }
 }
 
-// Jacobi-preconditioned CG in the Chronopoulos–Gear arrangement: the same Krylov iterates as the
-// reference recurrence (spars.cpp:262-313) in exact arithmetic, but both inner products of an
-// iteration are formed in one place, so an iteration costs two grid-wide barriers instead of three.
-//   U-phase (own rows): p = u + beta p ; s = w + beta s ; x += alpha p ; r -= alpha s ; u = D^-1 r ; (r,u)
-//   S-phase           : w = A u ; (w,u)
-// Stopping rule unchanged: sqrt((r,u)/(b,D^-1 b)) <= Precision.
-__global__ void __launch_bounds__(512, 2) k_pcg_jacobi(PcgArgs a)
-{
-    cg::grid_group grid = cg::this_grid();
-    __shared__ double sm[33];
-    __shared__ int s_next;
-    const int lane = threadIdx.x & 31;
-    const int G = gridDim.x;
-    const int s0 = (int)((long long)a.nslices * blockIdx.x / G);
-    const int s1 = (int)((long long)a.nslices * (blockIdx.x + 1) / G);
-    const int r0 = s0 * 32, r1 = s1 * 32;
-    double *partA = a.part, *partG = a.part + G, *partD = a.part + 2 * G;
-    double *P = a.p, *S = a.u, *U = a.z, *W = a.w;
-
-    // res_o = b . D^-1 b ; x = 0 unless warm ; r = b
-    double part = 0.0;
-    for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x)
-    {
-        const double bi = a.b[i];
-        part = fma(bi * a.dinv[i], bi, part);
-        a.r[i] = bi;
-        if (!a.warm) a.x[i] = 0.0;
-    }
-    part = block_sum(part, sm);
-    if (threadIdx.x == 0) partA[blockIdx.x] = part;
-    grid.sync();
-    const double res_o = reduce_partials(partA, G, sm);
-    if (res_o == 0.0)
-    {
-        if (blockIdx.x == 0 && threadIdx.x == 0) { a.mail[0] = 0; a.mail[1] = 0; a.mail[2] = XFEMM_OK; a.mail[3] = 0; a.mail[4] = 0; }
-        return;
-    }
-    if (a.warm)
-    {
-        if (threadIdx.x == 0) s_next = s0;
-        __syncthreads();
-        for (int s = next_slice(&s_next, lane); s < s1; s = next_slice(&s_next, lane))
-        {
-            const int base = a.slice_ptr[s], w = (a.slice_ptr[s + 1] - base) >> 5, row = s * 32 + lane;
-            double acc = sell_row_offdiag(a.sell_val, a.sell_col, base, 0, w, lane, a.x);
-            a.r[row] = a.b[row] - fma(a.diag[row], a.x[row], acc);
-        }
-        __syncthreads();
-    }
-    // u = D^-1 r ; gamma = (r,u)
-    part = 0.0;
-    for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x)
-    {
-        const double ri = a.r[i], ui = ri * a.dinv[i];
-        U[i] = ui;
-        part = fma(ri, ui, part);
-    }
-    part = block_sum(part, sm);
-    if (threadIdx.x == 0) partG[blockIdx.x] = part;
-    grid.sync();
-    double gamma = reduce_partials(partG, G, sm);
-    double alpha = 0.0, beta = 0.0;
-    bool first = true;
-    int it = 0, status = XFEMM_OK;
-    double er = sqrt(gamma / res_o);
-    while (true)
-    {
-        // S-phase: w = A u ; delta = (w,u)
-        part = 0.0;
-        if (threadIdx.x == 0) s_next = s0;
-        __syncthreads();
-        for (int s = next_slice(&s_next, lane); s < s1; s = next_slice(&s_next, lane))
-        {
-            const int base = a.slice_ptr[s], w = (a.slice_ptr[s + 1] - base) >> 5, row = s * 32 + lane;
-            double acc = sell_row_offdiag(a.sell_val, a.sell_col, base, 0, w, lane, U);
-            const double ur = U[row];
-            acc = fma(a.diag[row], ur, acc);
-            W[row] = acc;
-            part = fma(ur, acc, part);
-        }
-        part = block_sum(part, sm);
-        if (threadIdx.x == 0) partD[blockIdx.x] = part;
-        grid.sync();
-        const double delta = reduce_partials(partD, G, sm);
-        const double denom = first ? delta : delta - beta * gamma / alpha;
-        if (!(denom > 0.0)) { status = XFEMM_ERR_DIVERGED; break; }
-        alpha = gamma / denom;
-        // U-phase
-        part = 0.0;
-        for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x)
-        {
-            const double pi = first ? U[i] : fma(beta, P[i], U[i]);
-            const double si = first ? W[i] : fma(beta, S[i], W[i]);
-            P[i] = pi;
-            S[i] = si;
-            a.x[i] = fma(alpha, pi, a.x[i]);
-            const double ri = fma(-alpha, si, a.r[i]);
-            a.r[i] = ri;
-            const double ui = ri * a.dinv[i];
-            U[i] = ui;
-            part = fma(ri, ui, part);
-        }
-        first = false;
-        part = block_sum(part, sm);
-        if (threadIdx.x == 0) partG[blockIdx.x] = part;
-        it++;
-        grid.sync();
-        const double gamma_new = reduce_partials(partG, G, sm);
-        er = sqrt(gamma_new / res_o);
-        if (!(er == er)) { status = XFEMM_ERR_DIVERGED; break; }
-        if (er <= a.precision) break;
-        if (it >= a.max_iter) { status = XFEMM_ERR_DIVERGED; break; }
-        beta = gamma_new / gamma;
-        gamma = gamma_new;
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0)
-    {
-        a.mail[0] = it; a.mail[1] = er; a.mail[2] = status; a.mail[3] = res_o; a.mail[4] = gamma;
-    }
-}
-
-// one application of the preconditioner as its own cooperative kernel (MultPC, tests)
 template <int PRECOND>
 __global__ void __launch_bounds__(512, 2) k_precond_only(PcgArgs a)
 {
@@ -610,10 +500,10 @@ int linprob_build_layout(xfemm_linprob *p, int precond)
     {
         std::vector<int> color;
         int nc = greedy_coloring(p->n, p->h_rowptr.data(), p->h_col.data(), env_int("XFEMM_MAX_COLORS", 7), color);
-        build_sell_layout(p->n, p->h_rowptr.data(), p->h_col.data(), &color, nc, sigma, L);
+        build_sell_layout(p->n, p->h_rowptr.data(), p->h_col.data(), &color, nc, sigma, L, env_int("XFEMM_WIDE_ROW", 64));
     }
     else
-        build_sell_layout(p->n, p->h_rowptr.data(), p->h_col.data(), nullptr, 0, sigma, L);
+        build_sell_layout(p->n, p->h_rowptr.data(), p->h_col.data(), nullptr, 0, sigma, L, env_int("XFEMM_WIDE_ROW", 64));
     cudaStream_t st = p->stream;
     XB_CUDA(p->i2c.upload(L.i2c.data(), L.i2c.size(), st));
     XB_CUDA(p->c2i.upload(L.c2i.data(), L.c2i.size(), st));
@@ -624,6 +514,7 @@ int linprob_build_layout(xfemm_linprob *p, int precond)
     XB_CUDA(p->sell_src.upload(L.sell_src.data(), L.sell_src.size(), st));
     XB_CUDA(p->diag_src.upload(L.diag_src.data(), L.diag_src.size(), st));
     XB_CUDA(p->color_slice.upload(L.color_slice.data(), L.color_slice.size(), st));
+    XB_CUDA(p->wide.upload(L, st));
     XB_CUDA(p->sell_val.alloc(L.sell_len));
     for (auto *v : {&p->diag, &p->dinv, &p->x, &p->r, &p->p, &p->u, &p->z, &p->w, &p->bint})
     {
@@ -635,6 +526,8 @@ int linprob_build_layout(xfemm_linprob *p, int precond)
     std::vector<int>().swap(L.sell_col);
     std::vector<int>().swap(L.sell_src);
     std::vector<int>().swap(L.diag_src);
+    std::vector<int>().swap(L.wide_col);
+    std::vector<int>().swap(L.wide_src);
     p->layout_precond = precond;
     return XFEMM_OK;
 }
@@ -649,6 +542,7 @@ static int refresh_values(xfemm_linprob *p, int *singular_row)
     int blocks = (int)std::min<long long>((L.sell_len + 255) / 256, (long long)p->num_sms * 16);
     if (blocks < 1) blocks = 1;
     ++xb::g_launch, k_sell_fill<<<blocks, 256, 0, st>>>(L.sell_len, p->sell_src.p, p->vals.p, p->sell_val.p);
+    p->wide.fill(p->vals.p, st);
     ++xb::g_launch, k_diag_fill<<<(L.n_pad + 255) / 256, 256, 0, st>>>(L.n_pad, p->diag_src.p, p->vals.p, p->diag.p, p->dinv.p, d_flag);
     int flag = 0;
     XB_CUDA(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -693,7 +587,17 @@ static PcgArgs make_args(xfemm_linprob *p, double precision, int warm, int max_i
     a.omega = om ? atof(om) : 1.2;
     a.max_iter = max_iter; a.warm = warm;
     a.mail = p->d_mail.p;
+    a.wide = p->wide.view(); a.wide_val = p->wide.val.p; a.wide_acc = p->wide.acc.p;
     return a;
+}
+
+// y = A x on the solver representation (wide rows first, then the SELL slices)
+static void launch_spmv(xfemm_linprob *p, const double *x, double *y)
+{
+    const int sb = std::max(1, std::min((p->lay.nslices + 7) / 8, p->num_sms * 8));
+    p->wide.pre(x, y, p->stream);
+    ++g_launch, k_spmv<<<sb, 256, 0, p->stream>>>(p->lay.nslices, p->slice_ptr.p, p->sell_col.p, p->sell_val.p, p->diag.p, x, y,
+                                                  p->wide.n_rows ? p->wide.mask.p : nullptr);
 }
 
 } // namespace xb
@@ -1006,16 +910,14 @@ int xfemm_linprob_pcg(xfemm_linprob *p, double precision, int warm, int precond,
     XB_CUDA(cudaEventRecord(e1, st));
     if (precond == XFEMM_PRECOND_JACOBI)
     {
-        // Default: the reference's three-phase recurrence (u=Ap | x,r update + z.r | p update).  The
-        // Chronopoulos–Gear two-barrier variant (XFEMM_JACOBI_CG2=1) saves one barrier per iteration
-        // but moves 20 n more bytes; measured on B200 at 2 M DOF: 0.103 vs 0.093 ms/iteration.
-        const bool classic = env_int("XFEMM_JACOBI_CG2", 0) == 0;
-        rc = classic ? coop_grid(p, k_pcg<XFEMM_PRECOND_JACOBI>, 512, &grid) : coop_grid(p, k_pcg_jacobi, 512, &grid);
+        // The reference's three-phase recurrence (u=Ap | x,r update + z.r | p update).  A
+        // Chronopoulos–Gear two-barrier arrangement was tried and dropped: it saves one barrier per
+        // iteration but moves 20 n more bytes; measured on B200 at 2 M DOF: 0.103 vs 0.093 ms/iteration.
+        rc = coop_grid(p, k_pcg<XFEMM_PRECOND_JACOBI>, 512, &grid);
         if (rc != XFEMM_OK) return rc;
         a.part = p->partials.p;
         ++xb::g_launch;
-        XB_CUDA(cudaLaunchCooperativeKernel(classic ? (void *)k_pcg<XFEMM_PRECOND_JACOBI> : (void *)k_pcg_jacobi, dim3(grid),
-                                            dim3(512), kargs, 0, st));
+        XB_CUDA(cudaLaunchCooperativeKernel((void *)k_pcg<XFEMM_PRECOND_JACOBI>, dim3(grid), dim3(512), kargs, 0, st));
     }
     else
     {
@@ -1037,7 +939,8 @@ int xfemm_linprob_pcg(xfemm_linprob *p, double precision, int warm, int precond,
         ++xb::g_launch, k_from_internal<<<(n_pad + 255) / 256, 256, 0, st>>>(n_pad, p->i2c.p, p->x.p, p->V.p);
         // true relative residual ||b - A x|| / ||b||
         int sb = std::max(1, std::min((p->lay.nslices + 7) / 8, p->num_sms * 8));
-        ++xb::g_launch, k_spmv<<<sb, 256, 0, st>>>(p->lay.nslices, p->slice_ptr.p, p->sell_col.p, p->sell_val.p, p->diag.p, p->x.p, p->u.p);
+        (void)sb;
+        launch_spmv(p, p->x.p, p->u.p);
         int nb = std::max(1, std::min((n_pad + 255) / 256, 512));
         if (p->max_grid < nb) { XB_CUDA(p->partials.alloc((size_t)4 * nb)); p->max_grid = nb; }
         ++xb::g_launch, k_resnorm_partial<<<nb, 256, 0, st>>>(n_pad, p->bint.p, p->u.p, p->partials.p);
@@ -1078,7 +981,8 @@ int xfemm_linprob_multa(xfemm_linprob *p, const double *x, double *y)
     XB_CUDA(cudaMemcpyAsync(p->Vold.p, x, (size_t)p->n * sizeof(double), cudaMemcpyHostToDevice, st));
     ++xb::g_launch, k_to_internal<<<(n_pad + 255) / 256, 256, 0, st>>>(n_pad, p->i2c.p, p->Vold.p, p->r.p);
     int sb = std::max(1, std::min((p->lay.nslices + 7) / 8, p->num_sms * 8));
-    ++xb::g_launch, k_spmv<<<sb, 256, 0, st>>>(p->lay.nslices, p->slice_ptr.p, p->sell_col.p, p->sell_val.p, p->diag.p, p->r.p, p->u.p);
+    (void)sb;
+    launch_spmv(p, p->r.p, p->u.p);
     ++xb::g_launch, k_from_internal<<<(n_pad + 255) / 256, 256, 0, st>>>(n_pad, p->i2c.p, p->u.p, p->Vold.p);
     XB_CUDA(cudaMemcpyAsync(y, p->Vold.p, (size_t)p->n * sizeof(double), cudaMemcpyDeviceToHost, st));
     XB_CUDA(cudaStreamSynchronize(st));
@@ -1130,10 +1034,10 @@ int xfemm_linprob_bench_spmv(xfemm_linprob *p, int reps, double *ms_per_rep)
     XB_CUDA(cudaEventCreate(&e0)); XB_CUDA(cudaEventCreate(&e1));
     int sb = std::max(1, std::min((p->lay.nslices + 7) / 8, p->num_sms * 8));
     for (int w = 0; w < 3; w++)
-        ++xb::g_launch, k_spmv<<<sb, 256, 0, st>>>(p->lay.nslices, p->slice_ptr.p, p->sell_col.p, p->sell_val.p, p->diag.p, p->bint.p, p->u.p);
+        launch_spmv(p, p->bint.p, p->u.p);
     XB_CUDA(cudaEventRecord(e0, st));
     for (int w = 0; w < reps; w++)
-        ++xb::g_launch, k_spmv<<<sb, 256, 0, st>>>(p->lay.nslices, p->slice_ptr.p, p->sell_col.p, p->sell_val.p, p->diag.p, p->bint.p, p->u.p);
+        launch_spmv(p, p->bint.p, p->u.p);
     XB_CUDA(cudaEventRecord(e1, st));
     XB_CUDA(cudaStreamSynchronize(st));
     XB_CUDA(cudaGetLastError());

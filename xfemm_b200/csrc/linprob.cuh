@@ -2,6 +2,7 @@
 #pragma once
 #include "common.cuh"
 #include "layout.h"
+#include "wide_rows.cuh"
 #include <vector>
 #include <cstdint>
 
@@ -38,6 +39,7 @@ struct xfemm_linprob
     xb::DevBuf<double> x, r, p, u, z, w, bint;
     xb::DevBuf<double> partials;   // 2 * max_grid
     xb::DevBuf<int> color_slice;
+    xb::WideDev<double> wide;      // rows kept out of the SELL slices (layout.h)
     int max_grid = 0;
 
     // Dirichlet scratch

@@ -138,9 +138,10 @@ class DistPCG:
         self.sendbuf = torch.zeros(max(1, self.n_send), dtype=torch.float64, device=dev)
         self.recvbuf = torch.zeros(max(1, self.n_halo), dtype=torch.float64, device=dev)
         self.g = torch.zeros(4, dtype=torch.float64, device=dev)  # res, pAp, res_new, res_0
-        self.launches = 0
+        self._graphs = {}
 
     def close(self):
+        self._graphs = {}
         if getattr(self, "h", None):
             self.lib.xfemm_dist_destroy(self.h)
             self.h = None
@@ -155,39 +156,59 @@ class DistPCG:
         """Pull this rank's rows of the (re-)assembled global system."""
         self.X.check(self.lib.xfemm_dist_refresh(self.h))
 
-    def solve(self, precision: float = 1e-8, max_iter: int | None = None, check_every: int = 25):
+    def _iteration(self):
+        """One CG iteration: halo of p -> u = A p, p.u -> x, r update, r.D^-1 r -> new direction."""
+        dist, lib, X, g = self.dist, self.lib, self.X, self.g
+        gp = g.data_ptr()
+        X.check(lib.xfemm_dist_pack(self.h, C.c_void_p(self.sendbuf.data_ptr())))
+        exchange(dist, self.sendbuf[: self.n_send], self.recvbuf[: self.n_halo], self.send_splits, self.recv_splits, self.rank)
+        X.check(lib.xfemm_dist_unpack(self.h, C.c_void_p(self.recvbuf.data_ptr())))
+        X.check(lib.xfemm_dist_spmv_dot(self.h, C.c_void_p(gp + 8)))
+        dist.all_reduce(g[1:2])
+        X.check(lib.xfemm_dist_update(self.h, C.c_void_p(gp), C.c_void_p(gp + 16)))
+        dist.all_reduce(g[2:3])
+        X.check(lib.xfemm_dist_direction(self.h, C.c_void_p(gp)))
+        g[0:1].copy_(g[2:3])
+
+    def solve(self, precision: float = 1e-8, max_iter: int | None = None, check_every: int = 50,
+              use_graph: bool | None = None):
+        """Runs the iteration until ||r||_M/||r0||_M <= precision, checked every `check_every`
+        iterations (the only host synchronisation).  On NCCL a batch of `check_every` iterations is
+        captured once into a CUDA graph (kernels + collectives) and replayed, so the loop is not
+        bound by launch overhead."""
         torch, dist, lib, X, g = self.torch, self.dist, self.lib, self.X, self.g
         max_iter = max_iter or max(4 * self.n, 1000)
-        gp = g.data_ptr()
-        snd, rcv = self.sendbuf, self.recvbuf
-        ss, rs = self.send_splits, self.recv_splits
+        if use_graph is None:
+            use_graph = dist.get_backend() == "nccl"
         its = 0
         with torch.cuda.stream(self.stream):
             t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             t0.record()
-            X.check(lib.xfemm_dist_init(self.h, C.c_void_p(gp)))
+            X.check(lib.xfemm_dist_init(self.h, C.c_void_p(g.data_ptr())))
             dist.all_reduce(g[0:1])
             g[3:4].copy_(g[0:1])
             res0 = float(g[3].item())
-            er = 1.0
-            if res0 == 0.0:
-                er = 0.0
+            er = 0.0 if res0 == 0.0 else 1.0
+            graph = self._graphs.get(check_every) if use_graph else None
             while er > precision and its < max_iter:
-                for _ in range(min(check_every, max_iter - its)):
-                    X.check(lib.xfemm_dist_pack(self.h, C.c_void_p(snd.data_ptr())))
-                    exchange(dist, snd[: self.n_send], rcv[: self.n_halo], ss, rs, self.rank)
-                    X.check(lib.xfemm_dist_unpack(self.h, C.c_void_p(rcv.data_ptr())))
-                    X.check(lib.xfemm_dist_spmv_dot(self.h, C.c_void_p(gp + 8)))
-                    dist.all_reduce(g[1:2])
-                    X.check(lib.xfemm_dist_update(self.h, C.c_void_p(gp), C.c_void_p(gp + 16)))
-                    dist.all_reduce(g[2:3])
-                    X.check(lib.xfemm_dist_direction(self.h, C.c_void_p(gp)))
-                    g[0:1].copy_(g[2:3])
-                    its += 1
+                if use_graph and graph is None and its > 0:
+                    # communicators are warm after the first eager batch: capture the next one
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph, stream=self.stream, capture_error_mode="thread_local"):
+                        for _ in range(check_every):
+                            self._iteration()
+                    self._graphs[check_every] = graph
+                if graph is not None:
+                    graph.replay()
+                    its += check_every
+                else:
+                    for _ in range(check_every):
+                        self._iteration()
+                    its += check_every
                 er = math.sqrt(max(float(g[0].item()), 0.0) / res0)
             t1.record()
             t1.synchronize()
-        return {"iterations": its, "er": er, "solve_ms": t0.elapsed_time(t1),
+        return {"iterations": its, "er": er, "solve_ms": t0.elapsed_time(t1), "graph": graph is not None,
                 "n_own": self.n_own, "n_halo": self.n_halo, "n_send": self.n_send}
 
     def gather_solution(self) -> np.ndarray:
