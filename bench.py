@@ -200,7 +200,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mesh-size", type=float, default=0.0018, help="block-label mesh size in cm (0.0018 → ~2M DOF)")
-    ap.add_argument("--precond", default=os.environ.get("XFEMM_PRECOND", "jacobi"), choices=["jacobi", "mcssor"])
+    ap.add_argument("--precond", default=os.environ.get("XFEMM_PRECOND", "jacobi"), choices=["jacobi", "mcssor", "amg"])
     ap.add_argument("--ref-iters", type=int, default=40)
     ap.add_argument("--ref-pbc", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -250,7 +250,7 @@ def main():
     if world > 1:
         dist.barrier()
     base = os.path.join(workdir, "case")
-    precond = X.PRECOND_JACOBI if args.precond == "jacobi" else X.PRECOND_MCSSOR
+    precond = {"jacobi": X.PRECOND_JACOBI, "mcssor": X.PRECOND_MCSSOR, "amg": X.PRECOND_AMG}[args.precond]
     if args.partitioned:
         return run_partitioned(args, base, workload, rank, local_rank, world)
     t0 = time.time()
@@ -324,13 +324,17 @@ def main():
     # the other GPU-parallel preconditioner on the same resident problem, for the record
     variant = None
     if rank == 0 and world == 1:
-        other = X.PRECOND_MCSSOR if precond == X.PRECOND_JACOBI else X.PRECOND_JACOBI
-        S.set_option("precond", other)
-        S.resolve()
-        S.resolve()
-        vs = S.stats()
-        variant = {"preconditioner": "mcssor" if other == X.PRECOND_MCSSOR else "jacobi", "iterations": sum(vs["iters"]),
-                   "pcg_ms": sum(vs["solve_ms"]), "relres": vs["relres"]}
+        variant = []
+        names = {X.PRECOND_JACOBI: "jacobi", X.PRECOND_MCSSOR: "mcssor", X.PRECOND_AMG: "amg"}
+        for other in names:
+            if other == precond:
+                continue
+            S.set_option("precond", other)
+            S.resolve()
+            S.resolve()
+            vs = S.stats()
+            variant.append({"preconditioner": names[other], "iterations": sum(vs["iters"]),
+                            "pcg_ms": sum(vs["solve_ms"]), "relres": vs["relres"]})
         S.set_option("precond", precond)
     if world > 1:
         t = torch.tensor([elapsed], device="cuda", dtype=torch.float64)

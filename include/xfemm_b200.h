@@ -38,6 +38,7 @@ extern "C" {
 /* preconditioners for the Krylov solvers */
 #define XFEMM_PRECOND_JACOBI 0
 #define XFEMM_PRECOND_MCSSOR 1 /* multicolour SSOR (GPU-parallel stand-in for the serial SSOR) */
+#define XFEMM_PRECOND_AMG 2    /* aggregation-multigrid V-cycle (real problems only) */
 
 typedef struct xfemm_linprob xfemm_linprob;   /* real symmetric system on the device    */
 typedef struct xfemm_clinprob xfemm_clinprob; /* complex symmetric system on the device */

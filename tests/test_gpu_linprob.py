@@ -48,7 +48,7 @@ CASES = [
 
 
 @pytest.mark.parametrize("name,kw", CASES, ids=[c[0] for c in CASES])
-@pytest.mark.parametrize("precond", [X.PRECOND_JACOBI, X.PRECOND_MCSSOR])
+@pytest.mark.parametrize("precond", [X.PRECOND_JACOBI, X.PRECOND_MCSSOR, X.PRECOND_AMG])
 def test_multa_multpc_pcg(name, kw, precond):
     A = _matrix(**kw)
     n = A.shape[0]

@@ -24,7 +24,7 @@ def _solve(name, tmp_path, precond):
 
 
 @pytest.mark.parametrize("name", ["tb", "tb30"])
-@pytest.mark.parametrize("precond", [X.PRECOND_JACOBI, X.PRECOND_MCSSOR])
+@pytest.mark.parametrize("precond", [X.PRECOND_JACOBI, X.PRECOND_MCSSOR, X.PRECOND_AMG])
 def test_linear_planar_matches_reference(name, precond, tmp_path):
     ref, meta = load_ref(name)
     S = _solve(name, tmp_path, precond)

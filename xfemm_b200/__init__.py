@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libxfemm_b200.so")
 
 PRECOND_JACOBI = 0
 PRECOND_MCSSOR = 1
+PRECOND_AMG = 2
 
 
 class XfemmError(RuntimeError):

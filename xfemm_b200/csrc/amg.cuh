@@ -1,0 +1,204 @@
+// Aggregation multigrid preconditioner for the real symmetric solver (XFEMM_PRECOND_AMG).
+//
+// The reference preconditions PCGSolve with serial SSOR (spars.cpp:197-236); on a GPU that
+// recurrence does not parallelise, Jacobi costs ~3.5x its iterations and multicolour SSOR pays two
+// grid barriers per colour.  A V-cycle over a hierarchy of plain (unsmoothed, piecewise-constant)
+// aggregates needs 20-40x fewer CG iterations than Jacobi on these first-order triangle meshes
+// and is made of the same building blocks as the solver itself: SELL-32 SpMV passes, row-wise
+// vector passes and grid barriers, all inside the ONE persistent PCG kernel.
+//
+//   hierarchy (host, once per sparsity pattern): greedy distance-1 aggregation on the pattern,
+//       coarse pattern = aggregate graph, per coarse CSR slot the list of fine slots that sum into
+//       it (Galerkin product P^T A P with P = aggregate indicator → a gather-sum, deterministic).
+//   values (device, every solve): level l+1 values from level l by that gather-sum, then the usual
+//       SELL / diagonal refill of each level.
+//   cycle: damped-Jacobi pre- and post-smoothing (same weight → symmetric), coarse correction
+//       scaled by an over-correction factor (plain aggregation under-estimates the correction),
+//       coarsest level (<= 64 rows or stalled coarsening) by a fixed number of Jacobi sweeps in one
+//       block.  M^-1 is a fixed symmetric positive definite operator, so CG applies.
+#pragma once
+#include "linprob.cuh"
+#include <cooperative_groups.h>
+#include <memory>
+
+namespace xb {
+
+constexpr int AMG_MAX_LEVELS = 12;
+
+// device view of one level, internal (SELL) row order
+struct AmgLev
+{
+    int n_pad = 0, nslices = 0;
+    const int *slice_ptr = nullptr, *sell_col = nullptr;
+    const double *sell_val = nullptr, *diag = nullptr, *dinv = nullptr;
+    WideView wide;
+    const double *wide_val = nullptr;
+    double *wide_acc = nullptr;
+    double *x = nullptr, *b = nullptr, *t = nullptr; // iterate, right-hand side, result / scratch
+    const int *agg = nullptr;                          // row -> row of the next level (-1: not represented)
+    const int *mptr = nullptr, *mem = nullptr;         // row of the NEXT level -> member rows of this level
+};
+
+struct AmgArgs
+{
+    int nlev = 0;
+    int coarse_sweeps = 31; // odd: the result of the coarsest level lands in its t buffer
+    double omega = 0.7, over = 1.8;
+    AmgLev lev[AMG_MAX_LEVELS];
+};
+
+// host side: one coarse level = a complete linear problem (pattern, values, SELL layout, vectors)
+struct AmgHierarchy
+{
+    struct Transfer
+    {
+        DevBuf<int> gptr, gsrc; // coarse CSR slot -> contributing fine CSR slots
+        DevBuf<int> agg;        // fine internal row -> coarse internal row
+        DevBuf<int> mptr, mem;  // coarse internal row -> fine internal rows
+        long long nnz_coarse = 0;
+    };
+    std::vector<xfemm_linprob *> coarse; // levels 1..
+    std::vector<std::unique_ptr<Transfer>> xfer; // xfer[l]: level l -> l+1
+    std::vector<int> level_n, level_nnz;
+    ~AmgHierarchy();
+};
+
+int amg_build(xfemm_linprob *fine, std::unique_ptr<AmgHierarchy> &out);
+int amg_refresh(xfemm_linprob *fine, AmgHierarchy &h);
+void amg_fill_args(xfemm_linprob *fine, AmgHierarchy &h, AmgArgs &g);
+
+// --------------------------------------------------------------------------------------------
+// device: grid-wide V-cycle.  Every block owns a contiguous chunk of slices of every level.
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ double amg_sell_row(const AmgLev &L, int s, int lane, const double *x)
+{
+    const int base = L.slice_ptr[s], w = (L.slice_ptr[s + 1] - base) >> 5;
+    double acc = 0.0;
+    const double *v = L.sell_val + base + lane;
+    const int *c = L.sell_col + base + lane;
+#pragma unroll 8
+    for (int k = 0; k < w; k++) acc = fma(__ldcs(v + k * 32), x[__ldcs(c + k * 32)], acc);
+    return acc;
+}
+
+// y-phase over the block's slices of level L: calls epi(row, (A x)[row]) for every own row
+template <class Epi>
+__device__ __forceinline__ void amg_spmv_phase(const AmgLev &L, int s0, int s1, int wk0, int wk1, const double *x,
+                                               double *wide_tmp, int *s_next, Epi epi)
+{
+    const int lane = threadIdx.x & 31;
+    wide_rows_block<double>(L.wide, L.wide_val, L.wide_acc, wk0, wk1, x, wide_tmp);
+    if (threadIdx.x == 0) *s_next = s0;
+    __syncthreads();
+    while (true)
+    {
+        int s = 0;
+        if (lane == 0) s = atomicAdd(s_next, 1);
+        s = __shfl_sync(0xffffffffu, s, 0);
+        if (s >= s1) break;
+        const int row = s * 32 + lane;
+        double acc = amg_sell_row(L, s, lane, x);
+        if (wk1 > wk0 && ((L.wide.mask[s] >> lane) & 1u)) acc += wide_tmp[row];
+        acc = fma(L.diag[row], x[row], acc);
+        epi(row, acc);
+    }
+    __syncthreads(); // s_next is reused by the next phase
+}
+
+// z = M^-1 r.  Level 0: b = r (input), t = z (output), x = scratch.  Returns this thread's partial of r.z.
+__device__ __forceinline__ double amg_vcycle(const AmgArgs &g, cooperative_groups::grid_group &grid, int *s_next,
+                                             const int *s_wk /* [2*AMG_MAX_LEVELS] in shared memory */)
+{
+    const int G = gridDim.x, B = blockIdx.x;
+    const int last = g.nlev - 1;
+    const double w = g.omega;
+    double dot = 0.0;
+    // ---- down: pre-smooth from a zero guess, residual, restrict
+    {
+        const AmgLev &L = g.lev[0];
+        const int r0 = (int)((long long)L.nslices * B / G) * 32, r1 = (int)((long long)L.nslices * (B + 1) / G) * 32;
+        for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x) L.x[i] = w * L.dinv[i] * L.b[i];
+        if (last == 0)
+        {
+            // degenerate one-level hierarchy: M^-1 = damped Jacobi
+            for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x) { L.t[i] = L.x[i]; dot = fma(L.b[i], L.x[i], dot); }
+            return dot;
+        }
+    }
+    grid.sync();
+    for (int l = 0; l < last; l++)
+    {
+        const AmgLev &L = g.lev[l];
+        const AmgLev &C = g.lev[l + 1];
+        const int s0 = (int)((long long)L.nslices * B / G), s1 = (int)((long long)L.nslices * (B + 1) / G);
+        // t = b - A x   (t doubles as the scratch the wide rows leave their partial sums in)
+        amg_spmv_phase(L, s0, s1, s_wk[2 * l], s_wk[2 * l + 1], L.x, L.t, s_next,
+                       [&](int row, double ax) { L.t[row] = L.b[row] - ax; });
+        grid.sync();
+        // coarse right-hand side = sum over the aggregate ; coarse pre-smooth fused
+        const int c0 = (int)((long long)C.nslices * B / G) * 32, c1 = (int)((long long)C.nslices * (B + 1) / G) * 32;
+        for (int I = c0 + threadIdx.x; I < c1; I += blockDim.x)
+        {
+            double s = 0.0;
+            for (int k = L.mptr[I]; k < L.mptr[I + 1]; k++) s += L.t[L.mem[k]];
+            C.b[I] = s;
+            C.x[I] = w * C.dinv[I] * s;
+        }
+        grid.sync();
+    }
+    // ---- coarsest level: Jacobi sweeps by block 0 (x -> t -> x ... ends in t)
+    if (B == 0)
+    {
+        const AmgLev &L = g.lev[last];
+        const int lane = threadIdx.x & 31, warp_b = threadIdx.x >> 5, nwarps_b = blockDim.x >> 5;
+        double *src = L.x, *dst = L.t;
+        for (int it = 0; it < g.coarse_sweeps; it++)
+        {
+            wide_rows_block<double>(L.wide, L.wide_val, L.wide_acc, 0, L.wide.n_rows, src, dst);
+            __syncthreads();
+            for (int s = warp_b; s < L.nslices; s += nwarps_b)
+            {
+                const int row = s * 32 + lane;
+                double acc = amg_sell_row(L, s, lane, src);
+                if (L.wide.n_rows && ((L.wide.mask[s] >> lane) & 1u)) acc += dst[row];
+                const double xr = src[row];
+                acc = fma(L.diag[row], xr, acc);
+                dst[row] = fma(w * L.dinv[row], L.b[row] - acc, xr);
+            }
+            __syncthreads();
+            double *tmp = src; src = dst; dst = tmp;
+        }
+    }
+    grid.sync();
+    // ---- up: add the (over-)corrected coarse result, post-smooth into t
+    for (int l = last - 1; l >= 0; l--)
+    {
+        const AmgLev &L = g.lev[l];
+        const AmgLev &C = g.lev[l + 1];
+        const int s0 = (int)((long long)L.nslices * B / G), s1 = (int)((long long)L.nslices * (B + 1) / G);
+        const double over = g.over;
+        for (int i = s0 * 32 + threadIdx.x; i < s1 * 32; i += blockDim.x)
+        {
+            const int I = L.agg[i];
+            if (I >= 0) L.x[i] = fma(over, C.t[I], L.x[i]);
+        }
+        grid.sync();
+        if (l > 0)
+        {
+            amg_spmv_phase(L, s0, s1, s_wk[2 * l], s_wk[2 * l + 1], L.x, L.t, s_next,
+                           [&](int row, double ax) { L.t[row] = fma(w * L.dinv[row], L.b[row] - ax, L.x[row]); });
+            grid.sync();
+        }
+        else
+        {
+            amg_spmv_phase(L, s0, s1, s_wk[0], s_wk[1], L.x, L.t, s_next, [&](int row, double ax) {
+                const double br = L.b[row], z = fma(w * L.dinv[row], br - ax, L.x[row]);
+                L.t[row] = z;
+                dot = fma(br, z, dot);
+            });
+        }
+    }
+    return dot;
+}
+
+} // namespace xb

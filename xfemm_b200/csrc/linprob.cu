@@ -3,6 +3,7 @@
 // reductions, Jacobi and multicolour-SSOR preconditioned CG as ONE persistent cooperative
 // kernel (no host round trips inside the Krylov loop), Dirichlet / periodic boundary kernels.
 #include "linprob.cuh"
+#include "amg.cuh"
 #include <cooperative_groups.h>
 #include <algorithm>
 #include <unordered_map>
@@ -164,11 +165,12 @@ __device__ __forceinline__ int next_slice(int *ctr, int lane)
 }
 
 template <int PRECOND>
-__device__ __forceinline__ double precond_apply(const PcgArgs &a, cg::grid_group &grid, int r0, int r1,
-                                                int warp_g, int nwarps_g, int lane)
+__device__ __forceinline__ double precond_apply(const PcgArgs &a, const AmgArgs &g, cg::grid_group &grid, int r0, int r1,
+                                                int warp_g, int nwarps_g, int lane, int *s_next, const int *s_wk)
 {
-    // returns this thread's partial of r.z ; z is left in a.z (MC-SSOR) or implied (Jacobi)
+    // returns this thread's partial of r.z ; z is left in a.z (MC-SSOR, AMG) or implied (Jacobi)
     double dot = 0.0;
+    if (PRECOND == XFEMM_PRECOND_AMG) return amg_vcycle(g, grid, s_next, s_wk);
     if (PRECOND == XFEMM_PRECOND_JACOBI)
     {
         for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x)
@@ -227,11 +229,12 @@ __device__ __forceinline__ double precond_apply(const PcgArgs &a, cg::grid_group
 }
 
 template <int PRECOND>
-__global__ void __launch_bounds__(512, 2) k_pcg(PcgArgs a)
+__global__ void __launch_bounds__(512, 2) k_pcg(PcgArgs a, AmgArgs g)
 {
     cg::grid_group grid = cg::this_grid();
     __shared__ double sm[33];
     __shared__ int s_next;
+    __shared__ int s_wk[2 * AMG_MAX_LEVELS];
     const int lane = threadIdx.x & 31;
     const int nwarps_b = blockDim.x >> 5, warp_b = threadIdx.x >> 5;
     const int warp_g = blockIdx.x * nwarps_b + warp_b, nwarps_g = gridDim.x * nwarps_b;
@@ -243,6 +246,19 @@ __global__ void __launch_bounds__(512, 2) k_pcg(PcgArgs a)
     double *partA = a.part, *partB = a.part + G;
     int wk0 = 0, wk1 = 0; // wide rows of this block's chunk
     if (a.wide.n_rows) wide_range(a.wide, r0, r1, wk0, wk1);
+    if (PRECOND == XFEMM_PRECOND_AMG)
+    {
+        // wide rows of this block's chunk of every level
+        if (threadIdx.x < g.nlev)
+        {
+            const AmgLev &L = g.lev[threadIdx.x];
+            int k0 = 0, k1 = 0;
+            if (L.wide.n_rows)
+                wide_range(L.wide, (int)((long long)L.nslices * blockIdx.x / G) * 32, (int)((long long)L.nslices * (blockIdx.x + 1) / G) * 32, k0, k1);
+            s_wk[2 * threadIdx.x] = k0; s_wk[2 * threadIdx.x + 1] = k1;
+        }
+        __syncthreads();
+    }
 
     // ---- res_o = b . M^-1 b   (spars.cpp:257-259) ; z0 is computed with r := b
     for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x)
@@ -251,7 +267,7 @@ __global__ void __launch_bounds__(512, 2) k_pcg(PcgArgs a)
         if (!a.warm) a.x[i] = 0.0;
     }
     grid.sync();
-    double part = precond_apply<PRECOND>(a, grid, r0, r1, warp_g, nwarps_g, lane);
+    double part = precond_apply<PRECOND>(a, g, grid, r0, r1, warp_g, nwarps_g, lane, &s_next, s_wk);
     part = block_sum(part, sm);
     if (threadIdx.x == 0) partA[blockIdx.x] = part;
     grid.sync();
@@ -276,7 +292,7 @@ __global__ void __launch_bounds__(512, 2) k_pcg(PcgArgs a)
         grid.sync();
     }
     // ---- z = M^-1 r ; p = z ; res = z.r
-    part = precond_apply<PRECOND>(a, grid, r0, r1, warp_g, nwarps_g, lane);
+    part = precond_apply<PRECOND>(a, g, grid, r0, r1, warp_g, nwarps_g, lane, &s_next, s_wk);
     part = block_sum(part, sm);
     if (threadIdx.x == 0) partB[blockIdx.x] = part;
     grid.sync();
@@ -332,7 +348,7 @@ __global__ void __launch_bounds__(512, 2) k_pcg(PcgArgs a)
             }
             grid.sync();
             // step iv: z = M^-1 r ; z.r
-            part = precond_apply<PRECOND>(a, grid, r0, r1, warp_g, nwarps_g, lane);
+            part = precond_apply<PRECOND>(a, g, grid, r0, r1, warp_g, nwarps_g, lane, &s_next, s_wk);
         }
         part = block_sum(part, sm);
         if (threadIdx.x == 0) partB[blockIdx.x] = part;
@@ -360,9 +376,11 @@ __global__ void __launch_bounds__(512, 2) k_pcg(PcgArgs a)
 }
 
 template <int PRECOND>
-__global__ void __launch_bounds__(512, 2) k_precond_only(PcgArgs a)
+__global__ void __launch_bounds__(512, 2) k_precond_only(PcgArgs a, AmgArgs g)
 {
     cg::grid_group grid = cg::this_grid();
+    __shared__ int s_next;
+    __shared__ int s_wk[2 * AMG_MAX_LEVELS];
     const int lane = threadIdx.x & 31;
     const int nwarps_b = blockDim.x >> 5, warp_b = threadIdx.x >> 5;
     const int warp_g = blockIdx.x * nwarps_b + warp_b, nwarps_g = gridDim.x * nwarps_b;
@@ -370,7 +388,19 @@ __global__ void __launch_bounds__(512, 2) k_precond_only(PcgArgs a)
     const int s0 = (int)((long long)a.nslices * blockIdx.x / G);
     const int s1 = (int)((long long)a.nslices * (blockIdx.x + 1) / G);
     const int r0 = s0 * 32, r1 = s1 * 32;
-    precond_apply<PRECOND>(a, grid, r0, r1, warp_g, nwarps_g, lane);
+    if (PRECOND == XFEMM_PRECOND_AMG)
+    {
+        if (threadIdx.x < g.nlev)
+        {
+            const AmgLev &L = g.lev[threadIdx.x];
+            int k0 = 0, k1 = 0;
+            if (L.wide.n_rows)
+                wide_range(L.wide, (int)((long long)L.nslices * blockIdx.x / G) * 32, (int)((long long)L.nslices * (blockIdx.x + 1) / G) * 32, k0, k1);
+            s_wk[2 * threadIdx.x] = k0; s_wk[2 * threadIdx.x + 1] = k1;
+        }
+        __syncthreads();
+    }
+    precond_apply<PRECOND>(a, g, grid, r0, r1, warp_g, nwarps_g, lane, &s_next, s_wk);
     if (PRECOND == XFEMM_PRECOND_JACOBI)
         for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x) a.z[i] = a.r[i] * a.dinv[i];
 }
@@ -493,7 +523,10 @@ __global__ void k_relax(int n, double *V, const double *__restrict__ Vold, doubl
 // =====================================================================================
 int linprob_build_layout(xfemm_linprob *p, int precond)
 {
+    if (precond == XFEMM_PRECOND_AMG) precond = XFEMM_PRECOND_JACOBI; // same uncoloured layout
     if (p->layout_precond == precond) return XFEMM_OK;
+    delete p->amg; // its transfer maps are tied to the internal row order
+    p->amg = nullptr;
     SellLayout &L = p->lay;
     const int sigma = env_int("XFEMM_SELL_SIGMA", 1024);
     if (precond == XFEMM_PRECOND_MCSSOR)
@@ -532,7 +565,9 @@ int linprob_build_layout(xfemm_linprob *p, int precond)
     return XFEMM_OK;
 }
 
-static int refresh_values(xfemm_linprob *p, int *singular_row)
+int linprob_refresh_values(xfemm_linprob *p, int *singular_row);
+static int refresh_values(xfemm_linprob *p, int *singular_row) { return linprob_refresh_values(p, singular_row); }
+int linprob_refresh_values(xfemm_linprob *p, int *singular_row)
 {
     const SellLayout &L = p->lay;
     cudaStream_t st = p->stream;
@@ -681,7 +716,10 @@ int xfemm_linprob_create(int n, const int *rowptr, const int *colidx, xfemm_linp
 int xfemm_linprob_destroy(xfemm_linprob *p)
 {
     if (!p) return XFEMM_OK;
-    if (p->stream) { cudaStreamSynchronize(p->stream); cudaStreamDestroy(p->stream); }
+    if (p->stream) cudaStreamSynchronize(p->stream);
+    delete p->amg;
+    p->amg = nullptr;
+    if (p->stream) cudaStreamDestroy(p->stream);
     delete p;
     return XFEMM_OK;
 }
@@ -842,7 +880,16 @@ static int prepare_solver(xfemm_linprob *p, int precond, int *singular)
 {
     int rc = linprob_build_layout(p, precond);
     if (rc != XFEMM_OK) return rc;
-    return refresh_values(p, singular);
+    rc = refresh_values(p, singular);
+    if (rc != XFEMM_OK || precond != XFEMM_PRECOND_AMG) return rc;
+    if (!p->amg)
+    {
+        std::unique_ptr<AmgHierarchy> h;
+        rc = amg_build(p, h);
+        if (rc != XFEMM_OK) return rc;
+        p->amg = h.release();
+    }
+    return amg_refresh(p, *p->amg);
 }
 
 } // extern "C"  (internal helpers shared with dist.cu follow)
@@ -880,7 +927,7 @@ int xfemm_linprob_pcg(xfemm_linprob *p, double precision, int warm, int precond,
                       xfemm_solve_info *info)
 {
     XB_ARG(p, "null handle");
-    XB_ARG(precond == XFEMM_PRECOND_JACOBI || precond == XFEMM_PRECOND_MCSSOR, "unknown preconditioner");
+    XB_ARG(precond == XFEMM_PRECOND_JACOBI || precond == XFEMM_PRECOND_MCSSOR || precond == XFEMM_PRECOND_AMG, "unknown preconditioner");
     cudaStream_t st = p->stream;
     cudaEvent_t e0, e1, e2;
     XB_CUDA(cudaEventCreate(&e0)); XB_CUDA(cudaEventCreate(&e1)); XB_CUDA(cudaEventCreate(&e2));
@@ -891,7 +938,7 @@ int xfemm_linprob_pcg(xfemm_linprob *p, double precision, int warm, int precond,
     xfemm_solve_info local;
     memset(&local, 0, sizeof local);
     local.precond = precond;
-    local.colors = p->lay.ncolors;
+    local.colors = precond == XFEMM_PRECOND_AMG ? 1 + (int)p->amg->coarse.size() : p->lay.ncolors; // AMG: levels
     if (singular >= 0)
     {
         // reference: "singular flag tripped" → PCGSolve returns false (spars.cpp:245-249)
@@ -906,7 +953,9 @@ int xfemm_linprob_pcg(xfemm_linprob *p, double precision, int warm, int precond,
     if (max_iter <= 0) max_iter = env_int("XFEMM_MAX_ITER", 200000);
     PcgArgs a = make_args(p, precision, warm ? 1 : 0, max_iter);
     int grid = 0;
-    void *kargs[] = {&a};
+    AmgArgs g;
+    if (precond == XFEMM_PRECOND_AMG) amg_fill_args(p, *p->amg, g);
+    void *kargs[] = {&a, &g};
     XB_CUDA(cudaEventRecord(e1, st));
     if (precond == XFEMM_PRECOND_JACOBI)
     {
@@ -918,6 +967,13 @@ int xfemm_linprob_pcg(xfemm_linprob *p, double precision, int warm, int precond,
         a.part = p->partials.p;
         ++xb::g_launch;
         XB_CUDA(cudaLaunchCooperativeKernel((void *)k_pcg<XFEMM_PRECOND_JACOBI>, dim3(grid), dim3(512), kargs, 0, st));
+    }
+    else if (precond == XFEMM_PRECOND_AMG)
+    {
+        rc = coop_grid(p, k_pcg<XFEMM_PRECOND_AMG>, 512, &grid);
+        if (rc != XFEMM_OK) return rc;
+        a.part = p->partials.p;
+        ++xb::g_launch; XB_CUDA(cudaLaunchCooperativeKernel((void *)k_pcg<XFEMM_PRECOND_AMG>, dim3(grid), dim3(512), kargs, 0, st));
     }
     else
     {
@@ -1002,12 +1058,21 @@ int xfemm_linprob_multpc(xfemm_linprob *p, int precond, const double *x, double 
     ++xb::g_launch, k_to_internal<<<(n_pad + 255) / 256, 256, 0, st>>>(n_pad, p->i2c.p, p->Vold.p, p->r.p);
     PcgArgs a = make_args(p, 0, 0, 0);
     int grid = 0;
-    void *kargs[] = {&a};
+    AmgArgs g;
+    if (precond == XFEMM_PRECOND_AMG) amg_fill_args(p, *p->amg, g);
+    void *kargs[] = {&a, &g};
     if (precond == XFEMM_PRECOND_JACOBI)
     {
         rc = coop_grid(p, k_precond_only<XFEMM_PRECOND_JACOBI>, 512, &grid);
         if (rc != XFEMM_OK) return rc;
         ++xb::g_launch; XB_CUDA(cudaLaunchCooperativeKernel((void *)k_precond_only<XFEMM_PRECOND_JACOBI>, dim3(grid), dim3(512), kargs, 0, st));
+    }
+    else if (precond == XFEMM_PRECOND_AMG)
+    {
+        rc = coop_grid(p, k_precond_only<XFEMM_PRECOND_AMG>, 512, &grid);
+        if (rc != XFEMM_OK) return rc;
+        a.part = p->partials.p;
+        ++xb::g_launch; XB_CUDA(cudaLaunchCooperativeKernel((void *)k_precond_only<XFEMM_PRECOND_AMG>, dim3(grid), dim3(512), kargs, 0, st));
     }
     else
     {

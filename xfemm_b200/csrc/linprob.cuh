@@ -18,6 +18,7 @@
 //       256 B (values) / 128 B (columns) line.  sell_src[slot] = CSR index feeding the slot
 //       (-1 = padding) so a refill after re-assembly is one gather pass.
 //       Work vectors x,r,p,u,z,diag,dinv,bint live in the same internal order.
+namespace xb { struct AmgHierarchy; }
 struct xfemm_linprob
 {
     int n = 0;
@@ -40,6 +41,7 @@ struct xfemm_linprob
     xb::DevBuf<double> partials;   // 2 * max_grid
     xb::DevBuf<int> color_slice;
     xb::WideDev<double> wide;      // rows kept out of the SELL slices (layout.h)
+    xb::AmgHierarchy *amg = nullptr; // coarse levels of the multigrid preconditioner (amg.cuh), owned
     int max_grid = 0;
 
     // Dirichlet scratch

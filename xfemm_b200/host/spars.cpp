@@ -13,6 +13,7 @@ static int default_precond()
     const char *e = getenv("XFEMM_PRECOND");
     if (!e) return XFEMM_PRECOND_JACOBI;
     if (!strcmp(e, "mcssor") || !strcmp(e, "1")) return XFEMM_PRECOND_MCSSOR;
+    if (!strcmp(e, "amg") || !strcmp(e, "2")) return XFEMM_PRECOND_AMG;
     return XFEMM_PRECOND_JACOBI;
 }
 
