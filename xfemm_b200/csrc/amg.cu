@@ -2,6 +2,7 @@
 // the sparsity pattern (once per pattern) and the per-solve Galerkin value refresh on the device.
 #include "amg.cuh"
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <numeric>
 
@@ -212,6 +213,24 @@ int amg_refresh(xfemm_linprob *fine, AmgHierarchy &h)
     return XFEMM_OK;
 }
 
+void amg_print_trace(AmgHierarchy &h, cudaStream_t st)
+{
+    if (!h.stamps.p) return;
+    std::vector<unsigned long long> t(AMG_MAX_STAMPS, 0);
+    cudaMemcpyAsync(t.data(), h.stamps.p, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    fprintf(stderr, "[amg trace] levels:");
+    for (size_t l = 0; l < h.level_n.size(); l++) fprintf(stderr, " %d/%d", h.level_n[l], h.level_nnz[l]);
+    fprintf(stderr, "\n[amg trace] phase us:");
+    double total = 0;
+    for (int k = 1; k < AMG_MAX_STAMPS && t[k] > t[k - 1]; k++)
+    {
+        fprintf(stderr, " %.1f", (t[k] - t[k - 1]) * 1e-3);
+        total += (t[k] - t[k - 1]) * 1e-3;
+    }
+    fprintf(stderr, "  (cycle %.1f us)\n", total);
+}
+
 static void fill_level(AmgLev &L, xfemm_linprob *p)
 {
     L.n_pad = p->lay.n_pad; L.nslices = p->lay.nslices;
@@ -225,9 +244,15 @@ void amg_fill_args(xfemm_linprob *fine, AmgHierarchy &h, AmgArgs &g)
 {
     g.nlev = 1 + (int)h.coarse.size();
     const char *e;
-    g.omega = (e = getenv("XFEMM_AMG_OMEGA")) ? atof(e) : 0.7;
-    g.over = (e = getenv("XFEMM_AMG_OVER")) ? atof(e) : 1.8;
-    g.coarse_sweeps = ((e = getenv("XFEMM_AMG_COARSE_SWEEPS")) ? atoi(e) : 31) | 1;
+    g.omega = (e = getenv("XFEMM_AMG_OMEGA")) ? atof(e) : 0.8;
+    g.over = (e = getenv("XFEMM_AMG_OVER")) ? atof(e) : 2.6;
+    g.coarse_sweeps = ((e = getenv("XFEMM_AMG_COARSE_SWEEPS")) ? atoi(e) : 9) | 1;
+    g.stamps = nullptr;
+    if (getenv("XFEMM_AMG_TRACE"))
+    {
+        if (!h.stamps.p && h.stamps.alloc(AMG_MAX_STAMPS) == cudaSuccess) h.stamps.zero(fine->stream);
+        g.stamps = h.stamps.p;
+    }
     fill_level(g.lev[0], fine);
     g.lev[0].b = fine->r.p; // CG residual in, z out
     g.lev[0].x = fine->w.p;

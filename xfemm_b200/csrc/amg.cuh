@@ -42,10 +42,22 @@ struct AmgLev
 struct AmgArgs
 {
     int nlev = 0;
-    int coarse_sweeps = 31; // odd: the result of the coarsest level lands in its t buffer
-    double omega = 0.7, over = 1.8;
+    int coarse_sweeps = 9;  // odd: the result of the coarsest level lands in its t buffer
+    double omega = 0.8, over = 2.6;
+    unsigned long long *stamps = nullptr; // optional (XFEMM_AMG_TRACE): %globaltimer at every phase boundary of a cycle
     AmgLev lev[AMG_MAX_LEVELS];
 };
+
+constexpr int AMG_MAX_STAMPS = 8 * AMG_MAX_LEVELS;
+__device__ __forceinline__ void amg_stamp(const AmgArgs &g, int &k)
+{
+    if (g.stamps && blockIdx.x == 0 && threadIdx.x == 0 && k < AMG_MAX_STAMPS)
+    {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g.stamps[k++] = t;
+    }
+}
 
 // host side: one coarse level = a complete linear problem (pattern, values, SELL layout, vectors)
 struct AmgHierarchy
@@ -60,8 +72,10 @@ struct AmgHierarchy
     std::vector<xfemm_linprob *> coarse; // levels 1..
     std::vector<std::unique_ptr<Transfer>> xfer; // xfer[l]: level l -> l+1
     std::vector<int> level_n, level_nnz;
+    DevBuf<unsigned long long> stamps; // XFEMM_AMG_TRACE
     ~AmgHierarchy();
 };
+void amg_print_trace(AmgHierarchy &h, cudaStream_t st); // phase timings of the last cycle to stderr
 
 int amg_build(xfemm_linprob *fine, std::unique_ptr<AmgHierarchy> &out);
 int amg_refresh(xfemm_linprob *fine, AmgHierarchy &h);
@@ -113,6 +127,8 @@ __device__ __forceinline__ double amg_vcycle(const AmgArgs &g, cooperative_group
     const int last = g.nlev - 1;
     const double w = g.omega;
     double dot = 0.0;
+    int sk = 0;
+    amg_stamp(g, sk);
     // ---- down: pre-smooth from a zero guess, residual, restrict
     {
         const AmgLev &L = g.lev[0];
@@ -126,6 +142,7 @@ __device__ __forceinline__ double amg_vcycle(const AmgArgs &g, cooperative_group
         }
     }
     grid.sync();
+        amg_stamp(g, sk);
     for (int l = 0; l < last; l++)
     {
         const AmgLev &L = g.lev[l];
@@ -135,6 +152,7 @@ __device__ __forceinline__ double amg_vcycle(const AmgArgs &g, cooperative_group
         amg_spmv_phase(L, s0, s1, s_wk[2 * l], s_wk[2 * l + 1], L.x, L.t, s_next,
                        [&](int row, double ax) { L.t[row] = L.b[row] - ax; });
         grid.sync();
+        amg_stamp(g, sk);
         // coarse right-hand side = sum over the aggregate ; coarse pre-smooth fused
         const int c0 = (int)((long long)C.nslices * B / G) * 32, c1 = (int)((long long)C.nslices * (B + 1) / G) * 32;
         for (int I = c0 + threadIdx.x; I < c1; I += blockDim.x)
@@ -145,6 +163,7 @@ __device__ __forceinline__ double amg_vcycle(const AmgArgs &g, cooperative_group
             C.x[I] = w * C.dinv[I] * s;
         }
         grid.sync();
+        amg_stamp(g, sk);
     }
     // ---- coarsest level: Jacobi sweeps by block 0 (x -> t -> x ... ends in t)
     if (B == 0)
@@ -170,6 +189,7 @@ __device__ __forceinline__ double amg_vcycle(const AmgArgs &g, cooperative_group
         }
     }
     grid.sync();
+        amg_stamp(g, sk);
     // ---- up: add the (over-)corrected coarse result, post-smooth into t
     for (int l = last - 1; l >= 0; l--)
     {
@@ -183,11 +203,13 @@ __device__ __forceinline__ double amg_vcycle(const AmgArgs &g, cooperative_group
             if (I >= 0) L.x[i] = fma(over, C.t[I], L.x[i]);
         }
         grid.sync();
+        amg_stamp(g, sk);
         if (l > 0)
         {
             amg_spmv_phase(L, s0, s1, s_wk[2 * l], s_wk[2 * l + 1], L.x, L.t, s_next,
                            [&](int row, double ax) { L.t[row] = fma(w * L.dinv[row], L.b[row] - ax, L.x[row]); });
             grid.sync();
+        amg_stamp(g, sk);
         }
         else
         {
@@ -198,6 +220,7 @@ __device__ __forceinline__ double amg_vcycle(const AmgArgs &g, cooperative_group
             });
         }
     }
+    amg_stamp(g, sk);
     return dot;
 }
 

@@ -9,6 +9,8 @@
 #include <unordered_map>
 #include <cmath>
 #include <cstdlib>
+#include <chrono>
+#include <cstdio>
 
 namespace cg = cooperative_groups;
 
@@ -878,8 +880,13 @@ int xfemm_linprob_periodic(xfemm_linprob *p, int npairs, const int *ni, const in
 
 static int prepare_solver(xfemm_linprob *p, int precond, int *singular)
 {
+    const bool timing = getenv("XFEMM_TIMING") != nullptr;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t0 = now();
+    const bool had_layout = p->layout_precond >= 0, had_amg = p->amg != nullptr;
     int rc = linprob_build_layout(p, precond);
     if (rc != XFEMM_OK) return rc;
+    if (timing && !had_layout) fprintf(stderr, "[xfemm timing] SELL layout build n=%d: %.3f s\n", p->n, now() - t0);
     rc = refresh_values(p, singular);
     if (rc != XFEMM_OK || precond != XFEMM_PRECOND_AMG) return rc;
     if (!p->amg)
@@ -888,6 +895,7 @@ static int prepare_solver(xfemm_linprob *p, int precond, int *singular)
         rc = amg_build(p, h);
         if (rc != XFEMM_OK) return rc;
         p->amg = h.release();
+        if (timing && !had_amg) fprintf(stderr, "[xfemm timing] AMG hierarchy build n=%d: %.3f s\n", p->n, now() - t0);
     }
     return amg_refresh(p, *p->amg);
 }
@@ -986,6 +994,7 @@ int xfemm_linprob_pcg(xfemm_linprob *p, double precision, int warm, int precond,
     XB_CUDA(cudaMemcpyAsync(p->h_mail, p->d_mail.p, 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
     XB_CUDA(cudaStreamSynchronize(st));
     XB_CUDA(cudaGetLastError());
+    if (precond == XFEMM_PRECOND_AMG && g.stamps) amg_print_trace(*p->amg, st);
     local.iterations = (int)p->h_mail[0];
     local.er = p->h_mail[1];
     local.status = (int)p->h_mail[2];

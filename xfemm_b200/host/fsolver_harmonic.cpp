@@ -332,7 +332,8 @@ int FSolver::harmonicSolve(CBigComplexLinProb &L, bool axi, bool verbose)
     if (xfemm_cmag_create(&D, lin, &cmagdev) != XFEMM_OK) { WarnMessage(xfemm_last_error()); return false; }
     stats.t_upload = hwall() - t0;
 
-    const int precond = precondOption >= 0 ? precondOption : L.precond;
+    // the multigrid preconditioner exists for the real problems only
+    const int precond = (precondOption >= 0 && precondOption != XFEMM_PRECOND_AMG) ? precondOption : L.precond;
     int Iter = 0;
     double res = 0, lastres = 0;
     Relax = 1.;

@@ -584,7 +584,12 @@ int FSolver::staticSolve(CBigLinProb &L, bool axi)
     for (int l = 0; l < NumBlockLabels; l++) plan.labelJsrc[l] = labels[l].Jsrc;
     plan.linear = LinearFlag;
     plan.ready = true;
-    return staticNewton(L);
+    t0 = wall();
+    const int ok = staticNewton(L);
+    if (getenv("XFEMM_TIMING"))
+        fprintf(stderr, "[xfemm timing] pattern %.3f s, device create+upload %.3f s, first newton loop %.3f s (pcg %.1f ms)\n",
+                stats.t_pattern, stats.t_upload, wall() - t0, stats.pcg_ms.empty() ? 0. : stats.pcg_ms[0]);
+    return ok;
 }
 
 // Newton / "LinearFlag" loop of Static2D (static2d.cpp:177-1016) on the resident device problem:

@@ -8,13 +8,13 @@
 
 static int default_precond()
 {
-    // Both GPU-parallel replacements of the serial SSOR are available; the default is the one
-    // with the lower measured time to solution on B200.
+    // Three GPU-parallel replacements of the serial SSOR are available; the default is the one
+    // with the lowest measured time to solution on B200.
     const char *e = getenv("XFEMM_PRECOND");
-    if (!e) return XFEMM_PRECOND_JACOBI;
+    if (!e) return XFEMM_PRECOND_AMG;
+    if (!strcmp(e, "jacobi") || !strcmp(e, "0")) return XFEMM_PRECOND_JACOBI;
     if (!strcmp(e, "mcssor") || !strcmp(e, "1")) return XFEMM_PRECOND_MCSSOR;
-    if (!strcmp(e, "amg") || !strcmp(e, "2")) return XFEMM_PRECOND_AMG;
-    return XFEMM_PRECOND_JACOBI;
+    return XFEMM_PRECOND_AMG;
 }
 
 CBigLinProb::CBigLinProb()
