@@ -18,7 +18,7 @@ AmgHierarchy::~AmgHierarchy()
 // Greedy distance-1 aggregation on the pattern.  Rows without off-diagonals stay out (-1): the
 // smoother alone is exact for them.  Wide rows (air-gap rings, see layout.h) never seed an
 // aggregate — their neighbourhood is the whole ring — they join the aggregate of a mesh neighbour.
-static int aggregate(int n, const int *rp, const int *col, int wide_thr, std::vector<int> &agg)
+int aggregate(int n, const int *rp, const int *col, int wide_thr, std::vector<int> &agg)
 {
     agg.assign(n, -1);
     int na = 0;
@@ -68,7 +68,7 @@ static int aggregate(int n, const int *rp, const int *col, int wide_thr, std::ve
 }
 
 // coarse pattern (sorted CSR) + for every coarse slot the fine slots that sum into it
-static void coarse_pattern(int n, const int *rp, const int *col, const std::vector<int> &agg, int nc,
+void coarse_pattern(int n, const int *rp, const int *col, const std::vector<int> &agg, int nc,
                            std::vector<int> &crp, std::vector<int> &ccol, std::vector<int> &gptr, std::vector<int> &gsrc)
 {
     // members of each aggregate
@@ -79,51 +79,75 @@ static void coarse_pattern(int n, const int *rp, const int *col, const std::vect
         std::vector<int> pos(mptr.begin(), mptr.end() - 1);
         for (int i = 0; i < n; i++) if (agg[i] >= 0) mem[pos[agg[i]]++] = i;
     }
+    // Every coarse row is built from its own members only, so the three passes below run in
+    // parallel over coarse rows (per-thread marker arrays); results do not depend on the thread count.
+    // pass 1: distinct coarse columns per coarse row
     crp.assign(nc + 1, 0);
-    ccol.clear();
-    std::vector<int> mark(nc, -1), cols;
-    for (int I = 0; I < nc; I++)
-    {
-        cols.clear();
-        for (int k = mptr[I]; k < mptr[I + 1]; k++)
+    std::vector<std::vector<int>> tcols(64);
+    std::vector<std::pair<int, int>> trange(64, {0, 0});
+    parallel_for(nc, [&](int I0, int I1, int tid) {
+        std::vector<int> mark(nc, -1), cols, &out = tcols[tid];
+        trange[tid] = {I0, I1};
+        for (int I = I0; I < I1; I++)
         {
-            const int i = mem[k];
-            for (int s = rp[i]; s < rp[i + 1]; s++)
+            cols.clear();
+            for (int k = mptr[I]; k < mptr[I + 1]; k++)
             {
-                const int J = agg[col[s]];
-                if (J >= 0 && mark[J] != I) { mark[J] = I; cols.push_back(J); }
+                const int i = mem[k];
+                for (int s = rp[i]; s < rp[i + 1]; s++)
+                {
+                    const int J = agg[col[s]];
+                    if (J >= 0 && mark[J] != I) { mark[J] = I; cols.push_back(J); }
+                }
             }
+            std::sort(cols.begin(), cols.end());
+            out.insert(out.end(), cols.begin(), cols.end());
+            crp[I + 1] = (int)cols.size();
         }
-        std::sort(cols.begin(), cols.end());
-        ccol.insert(ccol.end(), cols.begin(), cols.end());
-        crp[I + 1] = (int)ccol.size();
-    }
-    // fine slot -> coarse slot, then invert by counting sort
-    const int nnzc = (int)ccol.size();
-    std::vector<int> pos(nc, -1);
-    std::vector<int> f2c((size_t)rp[n], -1);
+    }, 4096);
+    for (int I = 0; I < nc; I++) crp[I + 1] += crp[I];
+    const int nnzc = crp[nc];
+    ccol.resize(nnzc);
+    for (int t = 0; t < 64; t++)
+        if (!tcols[t].empty()) std::copy(tcols[t].begin(), tcols[t].end(), ccol.begin() + crp[trange[t].first]);
+    // pass 2: how many fine slots feed each coarse slot
     gptr.assign(nnzc + 1, 0);
-    for (int I = 0; I < nc; I++)
-    {
-        for (int t = crp[I]; t < crp[I + 1]; t++) pos[ccol[t]] = t;
-        for (int k = mptr[I]; k < mptr[I + 1]; k++)
+    parallel_for(nc, [&](int I0, int I1, int) {
+        std::vector<int> pos(nc, -1);
+        for (int I = I0; I < I1; I++)
         {
-            const int i = mem[k];
-            for (int s = rp[i]; s < rp[i + 1]; s++)
+            for (int t = crp[I]; t < crp[I + 1]; t++) pos[ccol[t]] = t;
+            for (int k = mptr[I]; k < mptr[I + 1]; k++)
             {
-                const int J = agg[col[s]];
-                if (J < 0) continue;
-                f2c[s] = pos[J];
-                gptr[pos[J] + 1]++;
+                const int i = mem[k];
+                for (int s = rp[i]; s < rp[i + 1]; s++)
+                {
+                    const int J = agg[col[s]];
+                    if (J >= 0) gptr[pos[J] + 1]++;
+                }
             }
         }
-    }
+    }, 4096);
     for (int t = 0; t < nnzc; t++) gptr[t + 1] += gptr[t];
+    // pass 3: the fine slots of each coarse slot, in ascending fine-slot order within a member row
     gsrc.assign(gptr[nnzc], 0);
-    {
-        std::vector<int> fill(gptr.begin(), gptr.end() - 1);
-        for (int s = 0; s < rp[n]; s++) if (f2c[s] >= 0) gsrc[fill[f2c[s]]++] = s;
-    }
+    parallel_for(nc, [&](int I0, int I1, int) {
+        std::vector<int> pos(nc, -1), fill;
+        for (int I = I0; I < I1; I++)
+        {
+            fill.assign(gptr.begin() + crp[I], gptr.begin() + crp[I + 1]);
+            for (int t = crp[I]; t < crp[I + 1]; t++) pos[ccol[t]] = t - crp[I];
+            for (int k = mptr[I]; k < mptr[I + 1]; k++)
+            {
+                const int i = mem[k];
+                for (int s = rp[i]; s < rp[i + 1]; s++)
+                {
+                    const int J = agg[col[s]];
+                    if (J >= 0) gsrc[fill[pos[J]]++] = s;
+                }
+            }
+        }
+    }, 4096);
 }
 
 __global__ void k_amg_galerkin(int nnzc, const int *__restrict__ gptr, const int *__restrict__ gsrc,

@@ -593,9 +593,12 @@ int xfemm_clinprob_create(int n, int n_nodes, const int *rowptr, const int *coli
     xfemm_clinprob *p = new xfemm_clinprob;
     p->n = n; p->n_nodes = n_nodes; p->nnz = nnz;
     int dev = 0;
-    cudaDeviceProp prop;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { delete p; set_error("cannot query the device"); return XFEMM_ERR_CUDA; }
-    p->num_sms = prop.multiProcessorCount;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    {
+        delete p;
+        set_error("cannot query the device");
+        return XFEMM_ERR_CUDA;
+    }
     if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess) { delete p; set_error("stream create failed"); return XFEMM_ERR_CUDA; }
     p->h_rowptr.assign(rowptr, rowptr + n + 1);
     p->h_col.assign(colidx, colidx + nnz);

@@ -81,8 +81,7 @@ void build_sell_layout(int n, const int *rowptr, const int *col, const std::vect
     // classification of an off-diagonal (i,j): 0 lower (j earlier in the internal order = lower
     // colour), 1 upper, 2 extra (same colour: excluded from the SSOR sweeps).  Sorting inside a
     // window only permutes rows of one colour, so for coloured layouts the class never depends
-    // on the final position; for the uncoloured layout lower/upper is merely a storage split
-    // and is evaluated on the final order below.
+    // on the final position; the uncoloured layout keeps all off-diagonals in one block.
     auto klass = [&](int i, int j, const std::vector<int> &rank) -> int {
         if (colored)
         {
@@ -91,28 +90,34 @@ void build_sell_layout(int n, const int *rowptr, const int *col, const std::vect
             if (ci == cj) return 2;
             return cj < ci ? 0 : 1;
         }
-        return rank[j] < rank[i] ? 0 : 1;
+        (void)rank;
+        return 0; // uncoloured: one block per slice (a lower/upper split would only add padding)
     };
     std::vector<int> rank(n);
     for (int k = 0; k < n; k++) rank[order[k]] = k;
     if (sigma > 1)
     {
         std::vector<int> key(n);
-        for (int i = 0; i < n; i++)
-        {
-            int c[3] = {0, 0, 0};
-            if (!wide[i])
-                for (int s = rowptr[i]; s < rowptr[i + 1]; s++)
-                    if (col[s] != i) c[klass(i, col[s], rank)]++;
-            key[i] = colored ? (std::min(c[0], 63) * 64 + std::min(c[1], 63)) * 64 + std::min(c[2], 63)
-                             : (wide[i] ? 0 : rowptr[i + 1] - rowptr[i]);
-        }
+        parallel_for(n, [&](int i0, int i1, int) {
+            for (int i = i0; i < i1; i++)
+            {
+                int c[3] = {0, 0, 0};
+                if (!wide[i] && colored)
+                    for (int s = rowptr[i]; s < rowptr[i + 1]; s++)
+                        if (col[s] != i) c[klass(i, col[s], rank)]++;
+                key[i] = colored ? (std::min(c[0], 63) * 64 + std::min(c[1], 63)) * 64 + std::min(c[2], 63)
+                                 : (wide[i] ? 0 : rowptr[i + 1] - rowptr[i]);
+            }
+        });
+        std::vector<std::pair<int, int>> windows;
         for (int g = 0; g < ngroups; g++)
             for (int w0 = color_start[g]; w0 < color_start[g + 1]; w0 += sigma)
-            {
-                int w1 = std::min(w0 + sigma, color_start[g + 1]);
-                std::stable_sort(order.begin() + w0, order.begin() + w1, [&](int a, int b) { return key[a] > key[b]; });
-            }
+                windows.emplace_back(w0, std::min(w0 + sigma, color_start[g + 1]));
+        parallel_for((int)windows.size(), [&](int a0, int a1, int) {
+            for (int a = a0; a < a1; a++)
+                std::stable_sort(order.begin() + windows[a].first, order.begin() + windows[a].second,
+                                 [&](int x, int y) { return key[x] > key[y]; });
+        }, 64);
     }
 
     // ---- padded internal numbering: every colour starts on a slice boundary
@@ -135,19 +140,25 @@ void build_sell_layout(int n, const int *rowptr, const int *col, const std::vect
     L.slice_wl.assign(L.nslices, 0);
     L.slice_wu.assign(L.nslices, 0);
     L.n_extra = 0;
-    std::vector<std::pair<int, int>> part[3]; // (internal col, csr index)
     std::vector<int> width(3 * (size_t)L.nslices, 0);
-    for (int r = 0; r < L.n_pad; r++)
-    {
-        int i = L.i2c[r];
-        if (i < 0) continue;
-        int c[3] = {0, 0, 0};
-        if (!wide[i])
-            for (int s = rowptr[i]; s < rowptr[i + 1]; s++)
-                if (col[s] != i) c[klass(i, col[s], L.c2i)]++;
-        L.n_extra += c[2];
-        for (int q = 0; q < 3; q++) width[3 * (size_t)(r / 32) + q] = std::max(width[3 * (size_t)(r / 32) + q], c[q]);
-    }
+    std::vector<long long> extra_part(64, 0);
+    parallel_for(L.nslices, [&](int s0, int s1, int tid) {
+        long long ex = 0;
+        for (int s = s0; s < s1; s++)
+            for (int r = s * 32; r < s * 32 + 32; r++)
+            {
+                int i = L.i2c[r];
+                if (i < 0) continue;
+                int c[3] = {0, 0, 0};
+                if (!wide[i])
+                    for (int q = rowptr[i]; q < rowptr[i + 1]; q++)
+                        if (col[q] != i) c[klass(i, col[q], L.c2i)]++;
+                ex += c[2];
+                for (int q = 0; q < 3; q++) width[3 * (size_t)s + q] = std::max(width[3 * (size_t)s + q], c[q]);
+            }
+        extra_part[tid] += ex;
+    });
+    for (long long e : extra_part) L.n_extra += e;
     long long total = 0;
     for (int s = 0; s < L.nslices; s++)
     {
@@ -161,7 +172,9 @@ void build_sell_layout(int n, const int *rowptr, const int *col, const std::vect
     L.sell_col.assign(total, 0);
     L.sell_src.assign(total, -1);
     L.diag_src.assign(L.n_pad, -1);
-    for (int s = 0; s < L.nslices; s++)
+    parallel_for(L.nslices, [&](int sb, int se, int) {
+    std::vector<std::pair<int, int>> part[3]; // (internal col, csr index)
+    for (int s = sb; s < se; s++)
     {
         const int base = L.slice_ptr[s];
         const int off[3] = {0, L.slice_wl[s], L.slice_wl[s] + L.slice_wu[s]};
@@ -191,6 +204,7 @@ void build_sell_layout(int n, const int *rowptr, const int *col, const std::vect
             }
         }
     }
+    });
 
     // ---- wide rows: row-wise storage in segments
     L.wide_row.clear(); L.wide_rseg.assign(1, 0); L.wide_sptr.assign(1, 0);

@@ -1,8 +1,28 @@
 // Solver layout (internal row order + split SELL-32) built on the host once per pattern.
 #pragma once
+#include <algorithm>
+#include <cstdlib>
+#include <thread>
 #include <vector>
 
 namespace xb {
+
+// Host-side parallel loop: f(begin, end, thread_index) over [0,n) in contiguous chunks.  The set-up
+// code (layouts, multigrid hierarchy, pattern) is integer work over millions of rows; a handful
+// of host threads takes it off the critical path.  XFEMM_HOST_THREADS overrides the thread count.
+template <class F>
+inline void parallel_for(int n, F f, int min_per_thread = 16384)
+{
+    int nt = (int)std::thread::hardware_concurrency();
+    if (const char *e = getenv("XFEMM_HOST_THREADS")) nt = atoi(e);
+    nt = std::max(1, std::min(nt, 32));
+    nt = std::min(nt, std::max(1, n / std::max(1, min_per_thread)));
+    if (nt <= 1) { f(0, n, 0); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++)
+        th.emplace_back([=]() { f((int)((long long)n * t / nt), (int)((long long)n * (t + 1) / nt), t); });
+    for (auto &x : th) x.join();
+}
 
 struct SellLayout
 {

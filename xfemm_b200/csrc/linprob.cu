@@ -689,10 +689,16 @@ int xfemm_linprob_create(int n, const int *rowptr, const int *colidx, xfemm_linp
     int rc = XFEMM_OK;
     auto fail = [&](int code) { delete p; return code; };
     if (cudaGetDevice(&p->device) != cudaSuccess) { set_error("cudaGetDevice failed"); return fail(XFEMM_ERR_CUDA); }
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, p->device) != cudaSuccess) { set_error("cudaGetDeviceProperties failed"); return fail(XFEMM_ERR_CUDA); }
-    if (!prop.cooperativeLaunch) { set_error("device lacks cooperative launch"); return fail(XFEMM_ERR_CUDA); }
-    p->num_sms = prop.multiProcessorCount;
+    // attribute queries, not cudaGetDeviceProperties: that call costs tens of milliseconds and every
+    // multigrid level is a linear problem of its own
+    int coop = 0;
+    if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, p->device) != cudaSuccess ||
+        cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, p->device) != cudaSuccess)
+    {
+        set_error("cannot query the device");
+        return fail(XFEMM_ERR_CUDA);
+    }
+    if (!coop) { set_error("device lacks cooperative launch"); return fail(XFEMM_ERR_CUDA); }
     if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream create failed"); return fail(XFEMM_ERR_CUDA); }
     p->h_rowptr.assign(rowptr, rowptr + n + 1);
     p->h_col.assign(colidx, colidx + nnz);

@@ -260,6 +260,7 @@ public:
         std::vector<double> dirFirst, dirLast, labelJsrc;
         bool linear = true, ready = false, ageDirty = false;
     } plan;
+    std::vector<double> jprevByLabel; // per-label source current accumulated over the solves (added to Jprev on write)
     bool assembleOnly;           // stop after assembly + boundary conditions of the first pass
     bool ageUnionPattern;        // couple all ring nodes of an air-gap element structurally (sweeps)
     // regenerates the ring tables of air-gap element `ageIndex` for new rotor/stator angles [deg]

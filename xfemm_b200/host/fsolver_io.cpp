@@ -738,7 +738,7 @@ int FSolver::WriteHarmonic2D(CBigComplexLinProb &L)
     {
         fprintf(fp, "%i\t%i\t%i\t%i\t%i\t%i\t%i", meshele[i].p[0], meshele[i].p[1], meshele[i].p[2], meshele[i].lbl,
                 meshele[i].e[0], meshele[i].e[1], meshele[i].e[2]);
-        if (!Aprev.empty()) fprintf(fp, "\t%.17g\n", meshele[i].Jprev); else fprintf(fp, "\n");
+        if (!Aprev.empty()) fprintf(fp, "\t%.17g\n", meshele[i].Jprev + (jprevByLabel.empty() ? 0. : jprevByLabel[meshele[i].lbl])); else fprintf(fp, "\n");
     }
     fprintf(fp, "%i\n", NumBlockLabels);
     for (int k = 0; k < NumBlockLabels; k++)

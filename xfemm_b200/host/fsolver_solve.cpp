@@ -552,8 +552,13 @@ int FSolver::staticSolve(CBigLinProb &L, bool axi)
     stats.t_pattern = wall() - t0;
     t0 = wall();
     xfemm_linprob *lin = nullptr;
+    const bool timing = getenv("XFEMM_TIMING") != nullptr;
+    double tt = wall();
+    auto tick = [&](const char *what) { if (timing) { fprintf(stderr, "[xfemm timing]   %s %.3f s\n", what, wall() - tt); tt = wall(); } };
     int rc = xfemm_linprob_create(NumNodes, rowptr, colidx, &lin);
+    tick("linprob_create");
     if (rc == XFEMM_OK) L.attachDevice(lin, rowptr, colidx);
+    tick("attachDevice");
     if (rc == XFEMM_OK && fillmask) rc = xfemm_linprob_set_fill_mask(lin, fillmask);
     xfemm_free(fillmask);
     xfemm_free(rowptr);
@@ -575,7 +580,9 @@ int FSolver::staticSolve(CBigLinProb &L, bool axi)
     D.n_point_src = (int)psNode.size(); D.point_src_node = psNode.data(); D.point_src_val = psVal.data();
     D.ext_zo = extZo * units[LengthUnits]; D.ext_ro = extRo * units[LengthUnits]; D.ext_ri = extRi * units[LengthUnits];
     D.r_eps = 1.e-6 * units[LengthUnits];
+    tick("host tables");
     if (xfemm_mag_create(&D, lin, &magdev) != XFEMM_OK) { WarnMessage(xfemm_last_error()); return false; }
+    tick("mag_create");
     stats.t_upload = wall() - t0;
 
     plan.dirNodes = dirNodes; plan.dirFirst = dirFirst; plan.dirLast = dirLast;
@@ -703,7 +710,9 @@ int FSolver::staticNewton(CBigLinProb &L)
         return false;
     }
     // bookkeeping the reference keeps per element
-    for (int i = 0; i < NumEls; i++) meshele[i].Jprev += Iter * plan.labelJsrc[meshele[i].lbl];
+    // (kept per label and folded into the element records when the .ans file is written)
+    if ((int)jprevByLabel.size() != NumBlockLabels) jprevByLabel.assign(NumBlockLabels, 0.);
+    for (int l = 0; l < NumBlockLabels; l++) jprevByLabel[l] += Iter * plan.labelJsrc[l];
     return true;
 }
 

@@ -7,6 +7,7 @@
 //  xfemm_renumber_cuthill   — cfemm/libfemm/cuthill.cpp:94-350 (Cuthill–McKee, not reversed)
 //  xfemm_renumber_sort_elements — cfemm/libfemm/cuthill.cpp:40-85 (the incomplete comb sort)
 #include "../../include/xfemm_b200.h"
+#include "../csrc/layout.h"
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -57,15 +58,22 @@ int xfemm_pattern_build(int n_rows, int n_elems, const int *tri, int tri_stride,
     }
     std::vector<int> rp(n + 1, 0);
     {
+        // sort+unique of every row in parallel, then one serial compaction pass
+        std::vector<int> len(n);
+        xb::parallel_for(n, [&](int i0, int i1, int) {
+            for (int i = i0; i < i1; i++)
+            {
+                int *b = adj.data() + cnt[i], *e = adj.data() + cnt[i + 1];
+                std::sort(b, e);
+                len[i] = (int)(std::unique(b, e) - b);
+            }
+        });
         size_t w = 0;
         for (int i = 0; i < n; i++)
         {
-            int *b = adj.data() + cnt[i], *e = adj.data() + cnt[i + 1];
-            std::sort(b, e);
-            e = std::unique(b, e);
-            size_t len = e - b;
-            if (adj.data() + w != b) memmove(adj.data() + w, b, len * sizeof(int));
-            w += len;
+            int *b = adj.data() + cnt[i];
+            if (adj.data() + w != b) memmove(adj.data() + w, b, (size_t)len[i] * sizeof(int));
+            w += len[i];
             rp[i + 1] = (int)w;
         }
         adj.resize(w);
@@ -135,11 +143,14 @@ int xfemm_pattern_build(int n_rows, int n_elems, const int *tri, int tri_stride,
     size_t w = 0;
     rowptr[0] = 0;
     std::vector<int> merged;
+    std::vector<char> touched(n, 0); // rows with extra or fill columns (a few thousand of millions)
+    for (auto &kv : extra) touched[kv.first] = 1;
+    for (auto &kv : fill) touched[kv.first] = 1;
     for (int i = 0; i < n; i++)
     {
         const int *b = adj.data() + rp[i], *e = adj.data() + rp[i + 1];
-        auto fe = extra.empty() ? extra.end() : extra.find(i);
-        auto ff = fill.empty() ? fill.end() : fill.find(i);
+        auto fe = touched[i] ? extra.find(i) : extra.end();
+        auto ff = touched[i] ? fill.find(i) : fill.end();
         if (fe == extra.end() && ff == fill.end())
         {
             memcpy(col + w, b, (e - b) * sizeof(int));

@@ -43,11 +43,20 @@ int CBigLinProb::Create(int d, int bw)
     M = (CEntry **)calloc(d, sizeof(CEntry *)); // not populated; see header
     Q = (int *)calloc(d, sizeof(int));
     n = d;
-    rows.assign(d, std::vector<Ent>());
-    lower.assign(d, std::vector<int>());
-    for (int i = 0; i < d; i++) rows[i].push_back(Ent{i, 0.0});
+    // the host-side rows (used only when a caller assembles through Put(), i.e. the hsolver/esolver
+    // style of use) are created on first touch: millions of tiny vectors are not free
+    std::vector<std::vector<Ent>>().swap(rows);
+    std::vector<std::vector<int>>().swap(lower);
     patternDirty = valuesDirty = true;
     return 1;
+}
+
+void CBigLinProb::ensureRows()
+{
+    if (!rows.empty() || n <= 0) return;
+    rows.assign(n, std::vector<Ent>());
+    lower.assign(n, std::vector<int>());
+    for (int i = 0; i < n; i++) rows[i].push_back(Ent{i, 0.0});
 }
 
 void CBigLinProb::attachDevice(xfemm_linprob *d, const int *rowptr, const int *col)
@@ -65,6 +74,7 @@ void CBigLinProb::attachDevice(xfemm_linprob *d, const int *rowptr, const int *c
 
 double *CBigLinProb::findEntry(int p, int q)
 {
+    if (!deviceAssembled) ensureRows();
     if (q < p) std::swap(p, q);
     std::vector<Ent> &r = rows[p];
     auto it = std::lower_bound(r.begin(), r.end(), q, [](const Ent &e, int c) { return e.c < c; });
@@ -84,6 +94,7 @@ void CBigLinProb::fetchDeviceValues()
 
 void CBigLinProb::Put(double v, int p, int q)
 {
+    if (!deviceAssembled) ensureRows();
     if (deviceAssembled)
     {
         fprintf(stderr, "CBigLinProb::Put on a device-assembled problem is not supported\n");
@@ -123,6 +134,7 @@ double CBigLinProb::Dot(double *X, double *Y)
 
 void CBigLinProb::Wipe()
 {
+    if (!deviceAssembled) ensureRows();
     if (deviceAssembled) { if (dev) xfemm_linprob_wipe(dev); hostValuesValid = false; }
     else
         for (auto &r : rows)
@@ -134,6 +146,7 @@ void CBigLinProb::Wipe()
 // SetValue with the reference's band restriction, visiting only the structurally coupled rows
 void CBigLinProb::SetValue(int i, double x)
 {
+    if (!deviceAssembled) ensureRows();
     if (deviceAssembled) { fprintf(stderr, "CBigLinProb::SetValue: use xfemm_linprob_dirichlet on device problems\n"); return; }
     int fst = 0, lst = n;
     if (bdw != 0) { fst = std::max(0, i - bdw); lst = std::min(n, i + bdw); }
@@ -155,6 +168,7 @@ void CBigLinProb::SetValue(int i, double x)
 
 void CBigLinProb::periodicImpl(int i, int j, double sgn)
 {
+    if (!deviceAssembled) ensureRows();
     if (deviceAssembled) { fprintf(stderr, "CBigLinProb::Periodicity: use xfemm_linprob_periodic on device problems\n"); return; }
     if (j < i) std::swap(i, j);
     // the reference scans every row k (KLUDGE sets bdw=0, spars.cpp:371-374); only rows
@@ -191,6 +205,7 @@ void CBigLinProb::AntiPeriodicity(int i, int j) { periodicImpl(i, j, -1.0); }
 
 bool CBigLinProb::syncToDevice()
 {
+    if (!deviceAssembled) ensureRows();
     if (deviceAssembled) return dev != nullptr;
     if (patternDirty || !dev)
     {

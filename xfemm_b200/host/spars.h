@@ -70,6 +70,7 @@ public:
 
 private:
     struct Ent { int c; double x; };
+    void ensureRows();                   // lazily creates the host rows below
     std::vector<std::vector<Ent>> rows;  // upper triangle, sorted by column, first entry = diagonal
     std::vector<std::vector<int>> lower; // lower[i] = rows k<i holding an entry (k,i)
     bool patternDirty, valuesDirty, hostValuesValid, deviceAssembled;
