@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <numeric>
 
 namespace xb {
@@ -13,7 +14,17 @@ int linprob_refresh_values(xfemm_linprob *p, int *singular_row); // linprob.cu
 AmgHierarchy::~AmgHierarchy()
 {
     for (auto *c : coarse) xfemm_linprob_destroy(c);
+    xfer.clear();
+    if (arena.base) cudaFree(arena.base);
 }
+
+// scope guard: DevBuf allocations of this thread come from `a` while alive
+struct ArenaScope
+{
+    DevArena *prev;
+    explicit ArenaScope(DevArena *a) : prev(g_arena) { if (a && a->base) g_arena = a; }
+    ~ArenaScope() { g_arena = prev; }
+};
 
 // Greedy distance-1 aggregation on the pattern.  Rows without off-diagonals stay out (-1): the
 // smoother alone is exact for them.  Wide rows (air-gap rings, see layout.h) never seed an
@@ -160,6 +171,46 @@ __global__ void k_amg_galerkin(int nnzc, const int *__restrict__ gptr, const int
     coarse_vals[t] = s;
 }
 
+// Dense inverse of the coarsest level by Gauss-Jordan on [A | I] (one block; the level has at most
+// AMG_DENSE_MAX rows, is symmetric positive definite and diagonally dominant enough to go without
+// pivoting).  Rows/columns in the internal order of the level; padding rows become identity rows.
+constexpr int AMG_DENSE_MAX = 128;
+__global__ void __launch_bounds__(1024)
+k_amg_dense_inverse(int n, int n_pad, const int *__restrict__ rowptr, const int *__restrict__ col,
+                    const double *__restrict__ vals, const int *__restrict__ c2i, double *W, double *inv)
+{
+    __shared__ double colk[AMG_DENSE_MAX];
+    const int ld = 2 * n_pad;
+    for (int e = threadIdx.x; e < n_pad * ld; e += blockDim.x)
+    {
+        const int r = e / ld, c = e % ld;
+        W[e] = (c == n_pad + r) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_pad; i += blockDim.x) W[(size_t)i * ld + i] = 1.0; // padding rows (overwritten below for real rows)
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) W[(size_t)c2i[i] * ld + c2i[i]] = 0.0;
+    __syncthreads();
+    for (int i = 0; i < n; i++)
+        for (int q = rowptr[i] + threadIdx.x; q < rowptr[i + 1]; q += blockDim.x) W[(size_t)c2i[i] * ld + c2i[col[q]]] = vals[q];
+    __syncthreads();
+    for (int k = 0; k < n_pad; k++)
+    {
+        const double piv = W[(size_t)k * ld + k];
+        __syncthreads();
+        for (int c = threadIdx.x; c < ld; c += blockDim.x) W[(size_t)k * ld + c] /= piv;
+        for (int r = threadIdx.x; r < n_pad; r += blockDim.x) colk[r] = W[(size_t)r * ld + k];
+        __syncthreads();
+        for (int e = threadIdx.x; e < n_pad * ld; e += blockDim.x)
+        {
+            const int r = e / ld, c = e % ld;
+            if (r != k) W[e] = fma(-colk[r], W[(size_t)k * ld + c], W[e]);
+        }
+        __syncthreads();
+    }
+    for (int e = threadIdx.x; e < n_pad * n_pad; e += blockDim.x) inv[e] = W[(size_t)(e / n_pad) * ld + n_pad + e % n_pad];
+}
+
 int amg_build(xfemm_linprob *fine, std::unique_ptr<AmgHierarchy> &out)
 {
     std::unique_ptr<AmgHierarchy> h(new AmgHierarchy);
@@ -176,12 +227,24 @@ int amg_build(xfemm_linprob *fine, std::unique_ptr<AmgHierarchy> &out)
         const int nc = aggregate(cur->n, cur->h_rowptr.data(), cur->h_col.data(), wide_thr, agg);
         if (nc < 1 || nc > cur->n * 0.7) break; // coarsening stalled
         coarse_pattern(cur->n, cur->h_rowptr.data(), cur->h_col.data(), agg, nc, crp, ccol, gptr, gsrc);
+        // levels from the third on live in the L2-pinned arena (see AmgHierarchy::arena)
+        const bool pinned = h->coarse.size() >= 1 && !getenv("XFEMM_AMG_NO_PIN");
+        if (pinned && !h->arena.base)
+        {
+            const size_t cap = (size_t)(1.5 * (28.0 * ccol.size() + 150.0 * nc + 12.0 * cur->n)) + (2u << 20);
+            if (cudaMalloc((void **)&h->arena.base, cap) == cudaSuccess) { h->arena.cap = cap; h->arena.used = 0; }
+            else { h->arena.base = nullptr; (void)cudaGetLastError(); }
+        }
         xfemm_linprob *c = nullptr;
-        int rc = xfemm_linprob_create(nc, crp.data(), ccol.data(), &c);
-        if (rc != XFEMM_OK) return rc;
-        h->coarse.push_back(c);
-        rc = linprob_build_layout(c, XFEMM_PRECOND_JACOBI);
-        if (rc != XFEMM_OK) return rc;
+        int rc;
+        {
+            ArenaScope scope(pinned ? &h->arena : nullptr);
+            rc = xfemm_linprob_create(nc, crp.data(), ccol.data(), &c);
+            if (rc != XFEMM_OK) return rc;
+            h->coarse.push_back(c);
+            rc = linprob_build_layout(c, XFEMM_PRECOND_JACOBI);
+            if (rc != XFEMM_OK) return rc;
+        }
         h->xfer.emplace_back(new AmgHierarchy::Transfer);
         AmgHierarchy::Transfer &T = *h->xfer.back();
         T.nnz_coarse = (long long)ccol.size();
@@ -202,13 +265,48 @@ int amg_build(xfemm_linprob *fine, std::unique_ptr<AmgHierarchy> &out)
             std::vector<int> pos(mptr.begin(), mptr.end() - 1);
             for (int r = 0; r < LF.n_pad; r++) if (agg_int[r] >= 0) mem[pos[agg_int[r]]++] = r;
         }
-        XB_CUDA(T.agg.upload(agg_int.data(), agg_int.size(), st));
-        XB_CUDA(T.mptr.upload(mptr.data(), mptr.size(), st));
-        XB_CUDA(T.mem.upload(mem.data(), mem.size(), st));
+        {
+            ArenaScope scope(pinned ? &h->arena : nullptr);
+            XB_CUDA(T.agg.upload(agg_int.data(), agg_int.size(), st));
+            XB_CUDA(T.mptr.upload(mptr.data(), mptr.size(), st));
+            XB_CUDA(T.mem.upload(mem.data(), mem.size(), st));
+        }
         XB_CUDA(cudaStreamSynchronize(st));
         h->level_n.push_back(nc);
         h->level_nnz.push_back((int)ccol.size());
         cur = c;
+    }
+    // exact solve on the coarsest level when it is small enough for a dense inverse
+    if (!h->coarse.empty() && h->coarse.back()->lay.n_pad <= AMG_DENSE_MAX && !getenv("XFEMM_AMG_NO_DENSE"))
+    {
+        ArenaScope scope(h->arena.base ? &h->arena : nullptr);
+        const size_t np = (size_t)h->coarse.back()->lay.n_pad;
+        XB_CUDA(h->dense_work.alloc(2 * np * np));
+        XB_CUDA(h->dense_inv.alloc(np * np));
+    }
+    // pin the arena in L2 for everything launched on the solver stream
+    if (h->arena.base && h->arena.used > 0)
+    {
+        int dev = 0, max_persist = 0, max_window = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+        const size_t want = std::min<size_t>(h->arena.used, (size_t)std::max(0, max_persist));
+        if (want > 0 && max_window > 0)
+        {
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+            cudaStreamAttrValue attr;
+            memset(&attr, 0, sizeof attr);
+            attr.accessPolicyWindow.base_ptr = h->arena.base;
+            attr.accessPolicyWindow.num_bytes = std::min<size_t>(h->arena.used, (size_t)max_window);
+            attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)want / (double)attr.accessPolicyWindow.num_bytes);
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+            if (cudaStreamSetAttribute(fine->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) (void)cudaGetLastError();
+        }
+        if (getenv("XFEMM_TIMING"))
+            fprintf(stderr, "[xfemm timing] multigrid arena %.1f MB of %.1f MB pinned in L2 (device limit %.1f MB)\n",
+                    h->arena.used / 1048576.0, h->arena.cap / 1048576.0, max_persist / 1048576.0);
     }
     out = std::move(h);
     return XFEMM_OK;
@@ -233,6 +331,13 @@ int amg_refresh(xfemm_linprob *fine, AmgHierarchy &h)
         if (rc != XFEMM_OK) return rc;
         XB_CUDA(cudaStreamSynchronize(c->stream));
         cur = c;
+    }
+    if (h.dense_inv.p)
+    {
+        xfemm_linprob *c = h.coarse.back();
+        ++g_launch, k_amg_dense_inverse<<<1, 1024, 0, st>>>(c->n, c->lay.n_pad, c->rowptr.p, c->col.p, c->vals.p, c->c2i.p,
+                                                            h.dense_work.p, h.dense_inv.p);
+        XB_CUDA(cudaGetLastError());
     }
     return XFEMM_OK;
 }
@@ -271,6 +376,12 @@ void amg_fill_args(xfemm_linprob *fine, AmgHierarchy &h, AmgArgs &g)
     g.omega = (e = getenv("XFEMM_AMG_OMEGA")) ? atof(e) : 0.8;
     g.over = (e = getenv("XFEMM_AMG_OVER")) ? atof(e) : 2.6;
     g.coarse_sweeps = ((e = getenv("XFEMM_AMG_COARSE_SWEEPS")) ? atoi(e) : 9) | 1;
+    // levels with at most this many rows are cycled by one block with __syncthreads (amg_block_cycle)
+    const int local_rows = (e = getenv("XFEMM_AMG_LOCAL_ROWS")) ? atoi(e) : 1024;
+    g.local_from = std::max(1, g.nlev - 1);
+    for (int l = 1; l < g.nlev; l++)
+        if (h.level_n[l] <= local_rows) { g.local_from = l; break; }
+    g.coarse_inv = h.dense_inv.p;
     g.stamps = nullptr;
     if (getenv("XFEMM_AMG_TRACE"))
     {

@@ -18,6 +18,7 @@
 //       block.  M^-1 is a fixed symmetric positive definite operator, so CG applies.
 #pragma once
 #include "linprob.cuh"
+#include "stage.cuh"
 #include <cooperative_groups.h>
 #include <memory>
 
@@ -44,6 +45,8 @@ struct AmgArgs
     int nlev = 0;
     int coarse_sweeps = 9;  // odd: the result of the coarsest level lands in its t buffer
     double omega = 0.8, over = 2.6;
+    int local_from = 1;     // first level handled by one block alone (small levels), <= nlev-1
+    const double *coarse_inv = nullptr; // dense inverse of the coarsest level (n_pad x n_pad, internal order) or null
     unsigned long long *stamps = nullptr; // optional (XFEMM_AMG_TRACE): %globaltimer at every phase boundary of a cycle
     AmgLev lev[AMG_MAX_LEVELS];
 };
@@ -73,6 +76,11 @@ struct AmgHierarchy
     std::vector<std::unique_ptr<Transfer>> xfer; // xfer[l]: level l -> l+1
     std::vector<int> level_n, level_nnz;
     DevBuf<unsigned long long> stamps; // XFEMM_AMG_TRACE
+    // The levels from the third on are latency-bound (a few thousand rows, dependent loads); the
+    // streams of the finest level would evict them from L2 every cycle.  Their buffers are carved
+    // from this one range, which the solver stream pins in L2 (access policy window, persisting).
+    DevArena arena;
+    DevBuf<double> dense_work, dense_inv; // coarsest level: [A | I] scratch and A^-1 (n_pad x n_pad), if small enough
     ~AmgHierarchy();
 };
 void amg_print_trace(AmgHierarchy &h, cudaStream_t st); // phase timings of the last cycle to stderr
@@ -98,10 +106,20 @@ __device__ __forceinline__ double amg_sell_row(const AmgLev &L, int s, int lane,
 // y-phase over the block's slices of level L: calls epi(row, (A x)[row]) for every own row
 template <class Epi>
 __device__ __forceinline__ void amg_spmv_phase(const AmgLev &L, int s0, int s1, int wk0, int wk1, const double *x,
-                                               double *wide_tmp, int *s_next, Epi epi)
+                                               double *wide_tmp, int *s_next, Epi epi, StageSmem *S = nullptr)
 {
     const int lane = threadIdx.x & 31;
     wide_rows_block<double>(L.wide, L.wide_val, L.wide_acc, wk0, wk1, x, wide_tmp);
+    if (S && S->ntiles > 0)
+    {
+        // finest level: the matrix stream comes through the shared-memory ring (stage.cuh)
+        staged_slices(*S, L.slice_ptr, L.sell_val, L.sell_col, s0, s1, x, s_next, [&](int s, int row, double acc) {
+            if (wk1 > wk0 && ((L.wide.mask[s] >> lane) & 1u)) acc += wide_tmp[row];
+            acc = fma(L.diag[row], x[row], acc);
+            epi(row, acc);
+        });
+        return;
+    }
     if (threadIdx.x == 0) *s_next = s0;
     __syncthreads();
     while (true)
@@ -119,17 +137,98 @@ __device__ __forceinline__ void amg_spmv_phase(const AmgLev &L, int s0, int s1, 
     __syncthreads(); // s_next is reused by the next phase
 }
 
+// Levels first..last handled by ONE block with __syncthreads only.  In: lev[first].b and .x
+// (pre-smoothed).  Out: lev[first].t.
+__device__ __forceinline__ void amg_block_cycle(const AmgArgs &g, int first)
+{
+    const int last = g.nlev - 1;
+    const int lane = threadIdx.x & 31, warp_b = threadIdx.x >> 5, nwarps_b = blockDim.x >> 5;
+    const double w = g.omega, over = g.over;
+    auto spmv = [&](const AmgLev &L, const double *src, double *dst, auto epi) {
+        wide_rows_block<double>(L.wide, L.wide_val, L.wide_acc, 0, L.wide.n_rows, src, dst);
+        __syncthreads();
+        for (int s = warp_b; s < L.nslices; s += nwarps_b)
+        {
+            const int row = s * 32 + lane;
+            double acc = amg_sell_row(L, s, lane, src);
+            if (L.wide.n_rows && ((L.wide.mask[s] >> lane) & 1u)) acc += dst[row];
+            acc = fma(L.diag[row], src[row], acc);
+            epi(row, acc);
+        }
+        __syncthreads();
+    };
+    for (int l = first; l < last; l++)
+    {
+        const AmgLev &L = g.lev[l];
+        const AmgLev &C = g.lev[l + 1];
+        spmv(L, L.x, L.t, [&](int row, double ax) { L.t[row] = L.b[row] - ax; });
+        for (int I = threadIdx.x; I < C.n_pad; I += blockDim.x)
+        {
+            double s = 0.0;
+            for (int k = L.mptr[I]; k < L.mptr[I + 1]; k++) s += L.t[L.mem[k]];
+            C.b[I] = s;
+            C.x[I] = w * C.dinv[I] * s;
+        }
+        __syncthreads();
+    }
+    {
+        const AmgLev &L = g.lev[last];
+        if (g.coarse_inv)
+        {
+            // coarsest level: exact solve with the dense inverse prepared by amg_refresh (t = A^-1 b)
+            const int n = L.n_pad;
+            for (int r = warp_b; r < n; r += nwarps_b)
+            {
+                double acc = 0.0;
+                for (int c = lane; c < n; c += 32) acc = fma(g.coarse_inv[(size_t)r * n + c], L.b[c], acc);
+                acc = warp_sum(acc);
+                if (lane == 0) L.t[r] = acc;
+            }
+            __syncthreads();
+        }
+        else
+        {
+            // damped-Jacobi sweeps x -> t -> x ... (odd count: ends in t)
+            double *src = L.x, *dst = L.t;
+            for (int it = 0; it < g.coarse_sweeps; it++)
+            {
+                double *d = dst;
+                const double *sv = src;
+                spmv(L, sv, d, [&](int row, double ax) { d[row] = fma(w * L.dinv[row], L.b[row] - ax, sv[row]); });
+                double *tmp = src; src = dst; dst = tmp;
+            }
+        }
+    }
+    for (int l = last - 1; l >= first; l--)
+    {
+        const AmgLev &L = g.lev[l];
+        const AmgLev &C = g.lev[l + 1];
+        for (int i = threadIdx.x; i < L.n_pad; i += blockDim.x)
+        {
+            const int I = L.agg[i];
+            if (I >= 0) L.x[i] = fma(over, C.t[I], L.x[i]);
+        }
+        __syncthreads();
+        spmv(L, L.x, L.t, [&](int row, double ax) { L.t[row] = fma(w * L.dinv[row], L.b[row] - ax, L.x[row]); });
+    }
+}
+
 // z = M^-1 r.  Level 0: b = r (input), t = z (output), x = scratch.  Returns this thread's partial of r.z.
+// x0_ready: the caller already stored the pre-smoothed x = omega D^-1 r of level 0 (fused into its
+// residual update) and synchronised the grid.
 __device__ __forceinline__ double amg_vcycle(const AmgArgs &g, cooperative_groups::grid_group &grid, int *s_next,
-                                             const int *s_wk /* [2*AMG_MAX_LEVELS] in shared memory */)
+                                             const int *s_wk /* [2*AMG_MAX_LEVELS] in shared memory */,
+                                             StageSmem *S0 /* ring of the finest level, or null */, bool x0_ready = false)
 {
     const int G = gridDim.x, B = blockIdx.x;
     const int last = g.nlev - 1;
-    const double w = g.omega;
+    const int lc = g.local_from; // levels lc..last belong to block 0 alone (1 <= lc <= last unless nlev == 1)
+    const double w = g.omega, over = g.over;
     double dot = 0.0;
     int sk = 0;
     amg_stamp(g, sk);
     // ---- down: pre-smooth from a zero guess, residual, restrict
+    if (!x0_ready || last == 0)
     {
         const AmgLev &L = g.lev[0];
         const int r0 = (int)((long long)L.nslices * B / G) * 32, r1 = (int)((long long)L.nslices * (B + 1) / G) * 32;
@@ -140,17 +239,17 @@ __device__ __forceinline__ double amg_vcycle(const AmgArgs &g, cooperative_group
             for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x) { L.t[i] = L.x[i]; dot = fma(L.b[i], L.x[i], dot); }
             return dot;
         }
-    }
-    grid.sync();
+        grid.sync();
         amg_stamp(g, sk);
-    for (int l = 0; l < last; l++)
+    }
+    for (int l = 0; l < lc; l++)
     {
         const AmgLev &L = g.lev[l];
         const AmgLev &C = g.lev[l + 1];
         const int s0 = (int)((long long)L.nslices * B / G), s1 = (int)((long long)L.nslices * (B + 1) / G);
         // t = b - A x   (t doubles as the scratch the wide rows leave their partial sums in)
         amg_spmv_phase(L, s0, s1, s_wk[2 * l], s_wk[2 * l + 1], L.x, L.t, s_next,
-                       [&](int row, double ax) { L.t[row] = L.b[row] - ax; });
+                       [&](int row, double ax) { L.t[row] = L.b[row] - ax; }, l == 0 ? S0 : nullptr);
         grid.sync();
         amg_stamp(g, sk);
         // coarse right-hand side = sum over the aggregate ; coarse pre-smooth fused
@@ -165,38 +264,17 @@ __device__ __forceinline__ double amg_vcycle(const AmgArgs &g, cooperative_group
         grid.sync();
         amg_stamp(g, sk);
     }
-    // ---- coarsest level: Jacobi sweeps by block 0 (x -> t -> x ... ends in t)
-    if (B == 0)
-    {
-        const AmgLev &L = g.lev[last];
-        const int lane = threadIdx.x & 31, warp_b = threadIdx.x >> 5, nwarps_b = blockDim.x >> 5;
-        double *src = L.x, *dst = L.t;
-        for (int it = 0; it < g.coarse_sweeps; it++)
-        {
-            wide_rows_block<double>(L.wide, L.wide_val, L.wide_acc, 0, L.wide.n_rows, src, dst);
-            __syncthreads();
-            for (int s = warp_b; s < L.nslices; s += nwarps_b)
-            {
-                const int row = s * 32 + lane;
-                double acc = amg_sell_row(L, s, lane, src);
-                if (L.wide.n_rows && ((L.wide.mask[s] >> lane) & 1u)) acc += dst[row];
-                const double xr = src[row];
-                acc = fma(L.diag[row], xr, acc);
-                dst[row] = fma(w * L.dinv[row], L.b[row] - acc, xr);
-            }
-            __syncthreads();
-            double *tmp = src; src = dst; dst = tmp;
-        }
-    }
+    // ---- the small levels: one block, no grid barriers; result in lev[lc].t
+    if (B == 0) amg_block_cycle(g, lc);
     grid.sync();
-        amg_stamp(g, sk);
-    // ---- up: add the (over-)corrected coarse result, post-smooth into t
-    for (int l = last - 1; l >= 0; l--)
+    amg_stamp(g, sk);
+    // ---- up: add the (over-)corrected coarse result (a row-wise gather: a scatter from the coarse rows
+    // was measured 3x slower, its read-modify-writes serialise), then post-smooth into t
+    for (int l = lc - 1; l >= 0; l--)
     {
         const AmgLev &L = g.lev[l];
         const AmgLev &C = g.lev[l + 1];
         const int s0 = (int)((long long)L.nslices * B / G), s1 = (int)((long long)L.nslices * (B + 1) / G);
-        const double over = g.over;
         for (int i = s0 * 32 + threadIdx.x; i < s1 * 32; i += blockDim.x)
         {
             const int I = L.agg[i];
@@ -209,7 +287,7 @@ __device__ __forceinline__ double amg_vcycle(const AmgArgs &g, cooperative_group
             amg_spmv_phase(L, s0, s1, s_wk[2 * l], s_wk[2 * l + 1], L.x, L.t, s_next,
                            [&](int row, double ax) { L.t[row] = fma(w * L.dinv[row], L.b[row] - ax, L.x[row]); });
             grid.sync();
-        amg_stamp(g, sk);
+            amg_stamp(g, sk);
         }
         else
         {
@@ -217,7 +295,7 @@ __device__ __forceinline__ double amg_vcycle(const AmgArgs &g, cooperative_group
                 const double br = L.b[row], z = fma(w * L.dinv[row], br - ax, L.x[row]);
                 L.t[row] = z;
                 dot = fma(br, z, dot);
-            });
+            }, S0);
         }
     }
     amg_stamp(g, sk);

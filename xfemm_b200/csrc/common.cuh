@@ -29,21 +29,40 @@ extern long long g_h2d_bytes, g_d2h_bytes, g_launch;
         if (!(cond)) { xb::set_error("invalid argument: %s", msg); return XFEMM_ERR_ARG; } \
     } while (0)
 
+// Optional bump arena: while g_arena points at one, DevBuf allocations are carved from it, so a
+// group of buffers (the small multigrid levels) ends up in ONE address range that a stream access
+// policy window can pin in L2.  The arena's owner frees the range; arena-backed buffers do not.
+struct DevArena
+{
+    char *base = nullptr;
+    size_t cap = 0, used = 0;
+};
+extern thread_local DevArena *g_arena;
+
 template <typename T>
 struct DevBuf
 {
     T *p = nullptr;
     size_t n = 0;
+    bool in_arena = false;
     DevBuf() = default;
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
     ~DevBuf() { release(); }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void release() { if (p && !in_arena) cudaFree(p); p = nullptr; n = 0; in_arena = false; }
     cudaError_t alloc(size_t count)
     {
         release();
         n = count;
         if (count == 0) return cudaSuccess;
+        const size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
+        if (g_arena && g_arena->used + bytes <= g_arena->cap)
+        {
+            p = (T *)(g_arena->base + g_arena->used);
+            g_arena->used += bytes;
+            in_arena = true;
+            return cudaSuccess;
+        }
         return cudaMalloc((void **)&p, count * sizeof(T));
     }
     cudaError_t upload(const T *h, size_t count, cudaStream_t s = 0)

@@ -28,6 +28,7 @@ void set_error(const char *fmt, ...)
 }
 const char *last_error() { return g_err.c_str(); }
 long long g_h2d_bytes = 0, g_d2h_bytes = 0, g_launch = 0;
+thread_local DevArena *g_arena = nullptr;
 
 static inline int env_int(const char *name, int dflt)
 {
@@ -156,6 +157,8 @@ struct PcgArgs
     WideView wide; // rows outside the SELL slices
     const double *wide_val;
     double *wide_acc;
+    const int4 *tiles;   // slice-aligned tiles of the SELL stream per block (stage.cuh), or null
+    const int *tile_ptr; // gridDim+1
 };
 
 // dynamic distribution of a block's slices over its warps (shared-memory ticket counter)
@@ -168,11 +171,12 @@ __device__ __forceinline__ int next_slice(int *ctr, int lane)
 
 template <int PRECOND>
 __device__ __forceinline__ double precond_apply(const PcgArgs &a, const AmgArgs &g, cg::grid_group &grid, int r0, int r1,
-                                                int warp_g, int nwarps_g, int lane, int *s_next, const int *s_wk)
+                                                int warp_g, int nwarps_g, int lane, int *s_next, const int *s_wk,
+                                                StageSmem *S, bool x0_ready = false)
 {
     // returns this thread's partial of r.z ; z is left in a.z (MC-SSOR, AMG) or implied (Jacobi)
     double dot = 0.0;
-    if (PRECOND == XFEMM_PRECOND_AMG) return amg_vcycle(g, grid, s_next, s_wk);
+    if (PRECOND == XFEMM_PRECOND_AMG) return amg_vcycle(g, grid, s_next, s_wk, S, x0_ready);
     if (PRECOND == XFEMM_PRECOND_JACOBI)
     {
         for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x)
@@ -248,6 +252,16 @@ __global__ void __launch_bounds__(512, 2) k_pcg(PcgArgs a, AmgArgs g)
     double *partA = a.part, *partB = a.part + G;
     int wk0 = 0, wk1 = 0; // wide rows of this block's chunk
     if (a.wide.n_rows) wide_range(a.wide, r0, r1, wk0, wk1);
+    // shared-memory ring for the matrix stream of the finest level (stage.cuh); no tiles → direct loads
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    StageSmem S = stage_carve(dyn_smem);
+    if (a.tiles)
+    {
+        const int t0 = a.tile_ptr[blockIdx.x], t1 = a.tile_ptr[blockIdx.x + 1];
+        S.ntiles = t1 - t0;
+        for (int k = threadIdx.x; k < S.ntiles; k += blockDim.x) S.tile[k] = a.tiles[t0 + k];
+        __syncthreads();
+    }
     if (PRECOND == XFEMM_PRECOND_AMG)
     {
         // wide rows of this block's chunk of every level
@@ -269,7 +283,7 @@ __global__ void __launch_bounds__(512, 2) k_pcg(PcgArgs a, AmgArgs g)
         if (!a.warm) a.x[i] = 0.0;
     }
     grid.sync();
-    double part = precond_apply<PRECOND>(a, g, grid, r0, r1, warp_g, nwarps_g, lane, &s_next, s_wk);
+    double part = precond_apply<PRECOND>(a, g, grid, r0, r1, warp_g, nwarps_g, lane, &s_next, s_wk, &S);
     part = block_sum(part, sm);
     if (threadIdx.x == 0) partA[blockIdx.x] = part;
     grid.sync();
@@ -294,7 +308,7 @@ __global__ void __launch_bounds__(512, 2) k_pcg(PcgArgs a, AmgArgs g)
         grid.sync();
     }
     // ---- z = M^-1 r ; p = z ; res = z.r
-    part = precond_apply<PRECOND>(a, g, grid, r0, r1, warp_g, nwarps_g, lane, &s_next, s_wk);
+    part = precond_apply<PRECOND>(a, g, grid, r0, r1, warp_g, nwarps_g, lane, &s_next, s_wk, &S);
     part = block_sum(part, sm);
     if (threadIdx.x == 0) partB[blockIdx.x] = part;
     grid.sync();
@@ -311,6 +325,19 @@ __global__ void __launch_bounds__(512, 2) k_pcg(PcgArgs a, AmgArgs g)
         // step i: u = A p ; pAp   (warps of a block pull slices of the block's chunk dynamically)
         part = 0.0;
         wide_rows_block<double>(a.wide, a.wide_val, a.wide_acc, wk0, wk1, a.p, a.u);
+        if (S.ntiles > 0)
+        {
+            // matrix stream through the shared-memory ring (stage.cuh)
+            staged_slices(S, a.slice_ptr, a.sell_val, a.sell_col, s0, s1, a.p, &s_next, [&](int s, int row, double acc) {
+                if (wk1 > wk0 && ((a.wide.mask[s] >> lane) & 1u)) acc += a.u[row];
+                const double pr = a.p[row];
+                acc = fma(a.diag[row], pr, acc);
+                a.u[row] = acc;
+                part = fma(pr, acc, part);
+            });
+        }
+        else
+        {
         if (threadIdx.x == 0) s_next = s0;
         __syncthreads();
         for (int s = next_slice(&s_next, lane); s < s1; s = next_slice(&s_next, lane))
@@ -322,6 +349,7 @@ __global__ void __launch_bounds__(512, 2) k_pcg(PcgArgs a, AmgArgs g)
             acc = fma(a.diag[row], pr, acc);
             a.u[row] = acc;
             part = fma(pr, acc, part);
+        }
         }
         part = block_sum(part, sm);
         if (threadIdx.x == 0) partA[blockIdx.x] = part;
@@ -346,11 +374,14 @@ __global__ void __launch_bounds__(512, 2) k_pcg(PcgArgs a, AmgArgs g)
             for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x)
             {
                 a.x[i] = fma(del, a.p[i], a.x[i]);
-                a.r[i] = fma(-del, a.u[i], a.r[i]);
+                const double ri = fma(-del, a.u[i], a.r[i]);
+                a.r[i] = ri;
+                // multigrid: the pre-smoothed iterate of the finest level comes for free here
+                if (PRECOND == XFEMM_PRECOND_AMG) g.lev[0].x[i] = g.omega * a.dinv[i] * ri;
             }
             grid.sync();
             // step iv: z = M^-1 r ; z.r
-            part = precond_apply<PRECOND>(a, g, grid, r0, r1, warp_g, nwarps_g, lane, &s_next, s_wk);
+            part = precond_apply<PRECOND>(a, g, grid, r0, r1, warp_g, nwarps_g, lane, &s_next, s_wk, &S, true);
         }
         part = block_sum(part, sm);
         if (threadIdx.x == 0) partB[blockIdx.x] = part;
@@ -402,7 +433,7 @@ __global__ void __launch_bounds__(512, 2) k_precond_only(PcgArgs a, AmgArgs g)
         }
         __syncthreads();
     }
-    precond_apply<PRECOND>(a, g, grid, r0, r1, warp_g, nwarps_g, lane, &s_next, s_wk);
+    precond_apply<PRECOND>(a, g, grid, r0, r1, warp_g, nwarps_g, lane, &s_next, s_wk, nullptr);
     if (PRECOND == XFEMM_PRECOND_JACOBI)
         for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x) a.z[i] = a.r[i] * a.dinv[i];
 }
@@ -529,6 +560,7 @@ int linprob_build_layout(xfemm_linprob *p, int precond)
     if (p->layout_precond == precond) return XFEMM_OK;
     delete p->amg; // its transfer maps are tied to the internal row order
     p->amg = nullptr;
+    p->tile_grid = -1; // and so are the stream tiles
     SellLayout &L = p->lay;
     const int sigma = env_int("XFEMM_SELL_SIGMA", 1024);
     if (precond == XFEMM_PRECOND_MCSSOR)
@@ -590,10 +622,11 @@ int linprob_refresh_values(xfemm_linprob *p, int *singular_row)
 }
 
 template <typename K>
-static int coop_grid(xfemm_linprob *p, K kernel, int threads, int *grid_out)
+static int coop_grid(xfemm_linprob *p, K kernel, int threads, int *grid_out, size_t dyn_smem = 0)
 {
     int per_sm = 0;
-    XB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0));
+    if (dyn_smem) XB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+    XB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, dyn_smem));
     if (per_sm < 1) { set_error("cooperative kernel does not fit on an SM"); return XFEMM_ERR_CUDA; }
     per_sm = std::min(per_sm, env_int("XFEMM_PCG_BLOCKS_PER_SM", 2));
     int grid = p->num_sms * per_sm;
@@ -625,7 +658,42 @@ static PcgArgs make_args(xfemm_linprob *p, double precision, int warm, int max_i
     a.max_iter = max_iter; a.warm = warm;
     a.mail = p->d_mail.p;
     a.wide = p->wide.view(); a.wide_val = p->wide.val.p; a.wide_acc = p->wide.acc.p;
+    a.tiles = nullptr; a.tile_ptr = nullptr;
     return a;
+}
+
+// Slice-aligned tiles (<= STAGE_TILE_ENT entries) of every block's chunk of the SELL stream for a
+// launch with `grid` blocks (stage.cuh).  Cached per layout and grid size.  Returns false when the
+// staging does not apply (a block would need more tiles than its table holds, or it is disabled).
+static bool ensure_tiles(xfemm_linprob *p, int grid)
+{
+    if (env_int("XFEMM_STAGED", 1) == 0) return false;
+    if (p->tile_grid == grid) return p->tiles.n > 0;
+    p->tile_grid = grid;
+    p->tiles.release(); p->tile_ptr.release();
+    const std::vector<int> &sp = p->lay.slice_ptr;
+    const int ns = p->lay.nslices;
+    std::vector<int4> tiles;
+    std::vector<int> tptr(grid + 1, 0);
+    for (int b = 0; b < grid; b++)
+    {
+        const int s0 = (int)((long long)ns * b / grid), s1 = (int)((long long)ns * (b + 1) / grid);
+        int s = s0;
+        while (s < s1)
+        {
+            int e = s + 1;
+            if (sp[e] - sp[s] > STAGE_TILE_ENT) return false; // a slice wider than a stage (coloured layouts)
+            while (e < s1 && sp[e + 1] - sp[s] <= STAGE_TILE_ENT) e++;
+            tiles.push_back(make_int4(s, e, sp[s], sp[e]));
+            s = e;
+        }
+        tptr[b + 1] = (int)tiles.size();
+        if (tptr[b + 1] - tptr[b] > STAGE_MAX_TILES) return false;
+    }
+    if (tiles.empty()) return false;
+    if (p->tiles.upload(tiles.data(), tiles.size(), p->stream) != cudaSuccess) return false;
+    if (p->tile_ptr.upload(tptr.data(), tptr.size(), p->stream) != cudaSuccess) { p->tiles.release(); return false; }
+    return true;
 }
 
 // y = A x on the solver representation (wide rows first, then the SELL slices)
@@ -976,18 +1044,20 @@ int xfemm_linprob_pcg(xfemm_linprob *p, double precision, int warm, int precond,
         // The reference's three-phase recurrence (u=Ap | x,r update + z.r | p update).  A
         // Chronopoulos–Gear two-barrier arrangement was tried and dropped: it saves one barrier per
         // iteration but moves 20 n more bytes; measured on B200 at 2 M DOF: 0.103 vs 0.093 ms/iteration.
-        rc = coop_grid(p, k_pcg<XFEMM_PRECOND_JACOBI>, 512, &grid);
+        rc = coop_grid(p, k_pcg<XFEMM_PRECOND_JACOBI>, 512, &grid, STAGE_SMEM_BYTES);
         if (rc != XFEMM_OK) return rc;
         a.part = p->partials.p;
+        if (ensure_tiles(p, grid)) { a.tiles = p->tiles.p; a.tile_ptr = p->tile_ptr.p; }
         ++xb::g_launch;
-        XB_CUDA(cudaLaunchCooperativeKernel((void *)k_pcg<XFEMM_PRECOND_JACOBI>, dim3(grid), dim3(512), kargs, 0, st));
+        XB_CUDA(cudaLaunchCooperativeKernel((void *)k_pcg<XFEMM_PRECOND_JACOBI>, dim3(grid), dim3(512), kargs, STAGE_SMEM_BYTES, st));
     }
     else if (precond == XFEMM_PRECOND_AMG)
     {
-        rc = coop_grid(p, k_pcg<XFEMM_PRECOND_AMG>, 512, &grid);
+        rc = coop_grid(p, k_pcg<XFEMM_PRECOND_AMG>, 512, &grid, STAGE_SMEM_BYTES);
         if (rc != XFEMM_OK) return rc;
         a.part = p->partials.p;
-        ++xb::g_launch; XB_CUDA(cudaLaunchCooperativeKernel((void *)k_pcg<XFEMM_PRECOND_AMG>, dim3(grid), dim3(512), kargs, 0, st));
+        if (ensure_tiles(p, grid)) { a.tiles = p->tiles.p; a.tile_ptr = p->tile_ptr.p; }
+        ++xb::g_launch; XB_CUDA(cudaLaunchCooperativeKernel((void *)k_pcg<XFEMM_PRECOND_AMG>, dim3(grid), dim3(512), kargs, STAGE_SMEM_BYTES, st));
     }
     else
     {

@@ -42,6 +42,9 @@ struct xfemm_linprob
     xb::DevBuf<int> color_slice;
     xb::WideDev<double> wide;      // rows kept out of the SELL slices (layout.h)
     xb::AmgHierarchy *amg = nullptr; // coarse levels of the multigrid preconditioner (amg.cuh), owned
+    xb::DevBuf<int4> tiles;        // per-block tiles of the SELL stream for the shared-memory ring (stage.cuh)
+    xb::DevBuf<int> tile_ptr;
+    int tile_grid = -1;            // grid size the tiles were cut for
     int max_grid = 0;
 
     // Dirichlet scratch
