@@ -134,6 +134,34 @@ def run_reference(base, ref_iters, ref_pbc, total_ref_iters):
             "t_load_mesh": m["t_load_mesh"], "t_cuthill": m["t_cuthill"], "n_nodes": m["n_nodes"]}
 
 
+def pcg_bytes_per_iteration(X, S, precond, nnz, n):
+    """Algorithmic bytes of ONE preconditioned CG iteration (FP64 values, int32 indices).
+
+    Krylov part: SpMV 12 nnz + 20 n, dot 16 n, fused x/r update 48 n, direction update 24 n.
+    Jacobi adds 24 n + 16 n (z = D^-1 r, z.r); multicolour SSOR 12 nnz + 40 n + 16 n;
+    the multigrid V-cycle, per level l: pre-smooth 24 n_l, residual 12 nnz_l + 28 n_l, restriction 12 n_l + 24 n_{l+1},
+    prolongation 28 n_l, post-smooth 12 nnz_l + 36 n_l (z.r fused), dense coarsest solve 8 n_c^2.
+    """
+    import ctypes as C
+    krylov = 12.0 * nnz + 108.0 * n
+    if precond == X.PRECOND_JACOBI:
+        return krylov + 40.0 * n, None
+    if precond == X.PRECOND_MCSSOR:
+        return krylov + 12.0 * nnz + 56.0 * n, None
+    L = X.lib().xfemm_fsolver_linprob(S.h)
+    nr = (C.c_int * 16)()
+    nz = (C.c_longlong * 16)()
+    nl = X.lib().xfemm_linprob_amg_levels(L, 16, nr, nz)
+    if nl <= 0:
+        return krylov, None
+    levels = [{"rows": int(nr[l]), "nnz": int(nz[l])} for l in range(nl)]
+    cyc = 0.0
+    for l in range(nl - 1):
+        cyc += 24.0 * nz[l] + 128.0 * nr[l] + 24.0 * nr[l + 1]
+    cyc += 8.0 * nr[nl - 1] ** 2
+    return krylov + cyc, levels
+
+
 def run_partitioned(args, base, workload, rank, local_rank, world):
     """Config 5b: all N GPUs solve ONE linear system (row-block partitioned Jacobi-PCG, halo over NCCL)."""
     import torch
@@ -200,7 +228,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mesh-size", type=float, default=0.0018, help="block-label mesh size in cm (0.0018 → ~2M DOF)")
-    ap.add_argument("--precond", default=os.environ.get("XFEMM_PRECOND", "jacobi"), choices=["jacobi", "mcssor", "amg"])
+    ap.add_argument("--precond", default=os.environ.get("XFEMM_PRECOND", "amg"), choices=["jacobi", "mcssor", "amg"])
     ap.add_argument("--ref-iters", type=int, default=40)
     ap.add_argument("--ref-pbc", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -321,7 +349,9 @@ def main():
     elapsed = time.perf_counter() - t0
     sampler.stop_flag = True
     st = S.stats()
-    # the other GPU-parallel preconditioner on the same resident problem, for the record
+    nnz = X.lib().xfemm_fsolver_nnz(S.h)
+    bytes_iter, levels = pcg_bytes_per_iteration(X, S, precond, nnz, c["n_unknowns"])
+    # the other GPU-parallel preconditioners on the same resident problem, for the record
     variant = None
     if rank == 0 and world == 1:
         variant = []
@@ -333,8 +363,10 @@ def main():
             S.resolve()
             S.resolve()
             vs = S.stats()
-            variant.append({"preconditioner": names[other], "iterations": sum(vs["iters"]),
-                            "pcg_ms": sum(vs["solve_ms"]), "relres": vs["relres"]})
+            vb, _ = pcg_bytes_per_iteration(X, S, other, X.lib().xfemm_fsolver_nnz(S.h), c["n_unknowns"])
+            vms, vit = sum(vs["solve_ms"]), sum(vs["iters"])
+            variant.append({"preconditioner": names[other], "iterations": vit, "pcg_ms": vms, "relres": vs["relres"],
+                            "ms_per_iter": vms / max(1, vit), "algorithmic_gbs": vb * vit / (vms * 1e-3) / 1e9 if vms > 0 else None})
         S.set_option("precond", precond)
     if world > 1:
         t = torch.tensor([elapsed], device="cuda", dtype=torch.float64)
@@ -347,9 +379,7 @@ def main():
 
     problems = args.steps * world
     value = elapsed / problems
-    nnz = X.lib().xfemm_fsolver_nnz(S.h) if hasattr(X.lib(), "xfemm_fsolver_nnz") else 0
     n = c["n_unknowns"]
-    bytes_iter = (12.0 * nnz + 124.0 * n) + ((12.0 * nnz + 40.0 * n) if precond == X.PRECOND_MCSSOR else 0.0)
     pcg_ms = sum(solve_ms) / len(solve_ms)
     its = sum(iters) / len(iters)
     achieved = bytes_iter * its / (pcg_ms * 1e-3) / 1e9 if pcg_ms > 0 else 0.0
@@ -369,9 +399,9 @@ def main():
                    "parallelism": f"rotor-angle sweep: {world} independent positions at a time, one per GPU, no collective",
                    "step": "one rotor position: AGE re-target + assembly + BCs + PCG on the resident mesh"},
         "pcg": {"iterations": its, "reference_iterations": total_ref_iters or None, "ms": pcg_ms,
-                "ms_per_iter": pcg_ms / its if its else None, "relres": st["relres"]},
+                "ms_per_iter": pcg_ms / its if its else None, "relres": st["relres"], "multigrid_levels": levels},
         "assembly": {"ms": sum(asm_ms) / len(asm_ms), "elements_per_s": c["n_elems"] / (1e-3 * sum(asm_ms) / len(asm_ms))},
-        "roofline": {"bound": "hbm", "kernel": "k_pcg (persistent PCG: SpMV + fused vector updates + preconditioner)",
+        "roofline": {"bound": "hbm", "kernel": "k_pcg<%s> (persistent PCG: SpMV + fused vector updates + preconditioner)" % args.precond,
                      "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "bytes_per_iter": bytes_iter},
         "e2e": {"value": e2e, "unit": "s/problem", "h2d_bytes_per_step": int(h2d.value), "d2h_bytes_per_step": int(d2h.value)},

@@ -1,3 +1,4 @@
 cd /root/repo
-timeout 300 python -m pytest tests/test_gpu_linprob.py tests/test_gpu_static.py -m gpu -x -q 2>&1 | tail -3
-for R in 64 1024; do XFEMM_AMG_LOCAL_ROWS=$R XFEMM_AMG_TRACE=1 timeout 600 python bench.py --gpus 1 --steps 3 --warmup 3 --no-cpu-baseline --precond amg 2>gpurun_out/trace.log >gpurun_out/sweep_amg.log; grep -o '"pcg": {[^}]*}' gpurun_out/sweep_amg.log | tail -1; tail -1 gpurun_out/trace.log; done
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+XFEMM_TIMING=1 timeout 900 python bench.py --gpus 1 --steps 3 --warmup 3 --no-cpu-baseline 2>gpurun_out/timing.log >gpurun_out/bench_amg.log; tail -1 gpurun_out/bench_amg.log | python -c "
+import sys,json; d=json.loads(sys.stdin.read()); print({k:d[k] for k in ('value','e2e','roofline')})"; grep -E "release|total|pattern|AMG|SELL|create|attach|mag_" gpurun_out/timing.log | tail -22

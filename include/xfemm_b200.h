@@ -99,6 +99,9 @@ int xfemm_linprob_multa(xfemm_linprob *p, const double *x, double *y);  /* spars
 int xfemm_linprob_multpc(xfemm_linprob *p, int precond, const double *x, double *y); /* :197   */
 /* timing hooks for bench.py: run `reps` SpMVs / PCG iterations on resident data, device-timed */
 int xfemm_linprob_bench_spmv(xfemm_linprob *p, int reps, double *ms_per_rep);
+/* levels of the multigrid hierarchy built by the last XFEMM_PRECOND_AMG solve: rows and full-matrix
+ * non-zeros per level (level 0 = the problem itself); returns the number of levels (0: none built) */
+int xfemm_linprob_amg_levels(xfemm_linprob *p, int max_levels, int *n_rows, long long *nnz);
 
 /* ------------------------------------------------------------------ sparsity pattern
  * Builds the structure CBigLinProb ends up with after assembly + boundary conditions:

@@ -15,7 +15,7 @@ AmgHierarchy::~AmgHierarchy()
 {
     for (auto *c : coarse) xfemm_linprob_destroy(c);
     xfer.clear();
-    if (arena.base) cudaFree(arena.base);
+    if (arena.base) dev_free(arena.base);
 }
 
 // scope guard: DevBuf allocations of this thread come from `a` while alive
@@ -232,7 +232,7 @@ int amg_build(xfemm_linprob *fine, std::unique_ptr<AmgHierarchy> &out)
         if (pinned && !h->arena.base)
         {
             const size_t cap = (size_t)(1.5 * (28.0 * ccol.size() + 150.0 * nc + 12.0 * cur->n)) + (2u << 20);
-            if (cudaMalloc((void **)&h->arena.base, cap) == cudaSuccess) { h->arena.cap = cap; h->arena.used = 0; }
+            if (dev_alloc((void **)&h->arena.base, cap) == cudaSuccess) { h->arena.cap = cap; h->arena.used = 0; }
             else { h->arena.base = nullptr; (void)cudaGetLastError(); }
         }
         xfemm_linprob *c = nullptr;

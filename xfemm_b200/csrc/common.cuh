@@ -29,6 +29,14 @@ extern long long g_h2d_bytes, g_d2h_bytes, g_launch;
         if (!(cond)) { xb::set_error("invalid argument: %s", msg); return XFEMM_ERR_ARG; } \
     } while (0)
 
+// Device memory goes through a small caching allocator (linprob.cu): cudaFree synchronises the
+// device and, with the ~250 buffers of a problem plus its multigrid levels, tearing one problem
+// down and setting the next one up cost ~1 s in cudaFree/cudaMalloc alone.  Freed blocks are kept
+// (keyed by size) and handed out again; repeated solves of same-sized problems allocate nothing.
+cudaError_t dev_alloc(void **p, size_t bytes);
+void dev_free(void *p);
+void dev_cache_flush(); // really frees everything cached
+
 // Optional bump arena: while g_arena points at one, DevBuf allocations are carved from it, so a
 // group of buffers (the small multigrid levels) ends up in ONE address range that a stream access
 // policy window can pin in L2.  The arena's owner frees the range; arena-backed buffers do not.
@@ -49,7 +57,7 @@ struct DevBuf
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
     ~DevBuf() { release(); }
-    void release() { if (p && !in_arena) cudaFree(p); p = nullptr; n = 0; in_arena = false; }
+    void release() { if (p && !in_arena) dev_free(p); p = nullptr; n = 0; in_arena = false; }
     cudaError_t alloc(size_t count)
     {
         release();
@@ -63,7 +71,7 @@ struct DevBuf
             in_arena = true;
             return cudaSuccess;
         }
-        return cudaMalloc((void **)&p, count * sizeof(T));
+        return dev_alloc((void **)&p, count * sizeof(T));
     }
     cudaError_t upload(const T *h, size_t count, cudaStream_t s = 0)
     {

@@ -7,6 +7,8 @@
 #include <cooperative_groups.h>
 #include <algorithm>
 #include <unordered_map>
+#include <mutex>
+#include <vector>
 #include <cmath>
 #include <cstdlib>
 #include <chrono>
@@ -29,6 +31,75 @@ void set_error(const char *fmt, ...)
 const char *last_error() { return g_err.c_str(); }
 long long g_h2d_bytes = 0, g_d2h_bytes = 0, g_launch = 0;
 thread_local DevArena *g_arena = nullptr;
+
+// ---- caching device allocator (see common.cuh) ---------------------------------------------
+namespace {
+std::mutex g_cache_mu;
+std::unordered_map<size_t, std::vector<void *>> g_cache_free; // rounded size -> blocks
+std::unordered_map<void *, size_t> g_cache_size;              // live and cached blocks
+size_t g_cache_bytes = 0;                                      // bytes sitting in the free lists
+bool g_cache_dirty = false;                                    // frees since the last device-wide sync
+inline size_t cache_round(size_t b) { return b < (1u << 20) ? ((b + 511) & ~(size_t)511) : ((b + (1u << 20) - 1) & ~(size_t)((1u << 20) - 1)); }
+} // namespace
+
+void dev_cache_flush()
+{
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    cudaDeviceSynchronize();
+    for (auto &kv : g_cache_free)
+        for (void *q : kv.second) { g_cache_size.erase(q); cudaFree(q); }
+    g_cache_free.clear();
+    g_cache_bytes = 0;
+    g_cache_dirty = false;
+}
+
+cudaError_t dev_alloc(void **p, size_t bytes)
+{
+    const size_t r = cache_round(std::max<size_t>(bytes, 1));
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        auto it = g_cache_free.find(r);
+        if (it != g_cache_free.end() && !it->second.empty())
+        {
+            // a block freed earlier may still be read by work queued on its old stream
+            if (g_cache_dirty) { cudaDeviceSynchronize(); g_cache_dirty = false; }
+            *p = it->second.back();
+            it->second.pop_back();
+            g_cache_bytes -= r;
+            return cudaSuccess;
+        }
+    }
+    cudaError_t e = cudaMalloc(p, r);
+    if (e != cudaSuccess)
+    {
+        (void)cudaGetLastError();
+        dev_cache_flush(); // give the cached blocks back and retry once
+        e = cudaMalloc(p, r);
+        if (e != cudaSuccess) return e;
+    }
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    g_cache_size[*p] = r;
+    return cudaSuccess;
+}
+
+void dev_free(void *p)
+{
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    auto it = g_cache_size.find(p);
+    if (it == g_cache_size.end()) { cudaFree(p); return; }
+    const char *cm = getenv("XFEMM_DEVICE_CACHE_MB");
+    const size_t cap = (size_t)(cm ? atoi(cm) : 16384) << 20;
+    if (g_cache_bytes + it->second > cap)
+    {
+        g_cache_size.erase(it);
+        cudaFree(p);
+        return;
+    }
+    g_cache_free[it->second].push_back(p);
+    g_cache_bytes += it->second;
+    g_cache_dirty = true;
+}
 
 static inline int env_int(const char *name, int dflt)
 {
@@ -1170,6 +1241,18 @@ int xfemm_linprob_multpc(xfemm_linprob *p, int precond, const double *x, double 
     XB_CUDA(cudaStreamSynchronize(st));
     XB_CUDA(cudaGetLastError());
     return XFEMM_OK;
+}
+
+int xfemm_linprob_amg_levels(xfemm_linprob *p, int max_levels, int *n_rows, long long *nnz)
+{
+    if (!p || !p->amg) return 0;
+    const int nl = (int)p->amg->level_n.size();
+    for (int l = 0; l < nl && l < max_levels; l++)
+    {
+        if (n_rows) n_rows[l] = p->amg->level_n[l];
+        if (nnz) nnz[l] = p->amg->level_nnz[l];
+    }
+    return nl;
 }
 
 int xfemm_linprob_bench_spmv(xfemm_linprob *p, int reps, double *ms_per_rep)

@@ -3,6 +3,9 @@
 // ctypes / MEX / Lua bindings (and this repo's tests and bench) can drive the same path.
 #include "fsolver.h"
 #include "../../include/xfemm_b200.h"
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace xb
@@ -81,14 +84,19 @@ int xfemm_fsolver_solve(xfemm_fsolver *s)
     if (!s) return XFEMM_ERR_ARG;
     FSolver &S = s->S;
     int ok;
+    const bool timing = getenv("XFEMM_TIMING") != nullptr;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_start = now();
     if (S.Frequency == 0)
     {
         S.releaseDevice();
         delete s->L;
+        if (timing) fprintf(stderr, "[xfemm timing] release of the previous device problem %.3f s\n", now() - t_start);
         s->L = new CBigLinProb;
         s->L->Precision = S.Precision;
         s->L->Create(S.NumNodes, S.BandWidth);
         ok = (S.ProblemType == femm::PLANAR) ? S.Static2D(*s->L) : S.StaticAxisymmetric(*s->L);
+        if (timing) fprintf(stderr, "[xfemm timing] xfemm_fsolver_solve total %.3f s\n", now() - t_start);
     }
     else
     {
