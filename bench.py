@@ -232,6 +232,7 @@ def main():
     ap.add_argument("--ref-iters", type=int, default=40)
     ap.add_argument("--ref-pbc", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-variants", action="store_true", help="skip the runs with the other preconditioners")
     ap.add_argument("--partitioned", action="store_true",
                     help="config 5b: ONE mesh row-partitioned over the N GPUs (strong scaling) instead of the sweep")
     ap.add_argument("--workdir", default=os.environ.get("XFEMM_BENCH_DIR", "/tmp/xfemm_bench"))
@@ -353,7 +354,7 @@ def main():
     bytes_iter, levels = pcg_bytes_per_iteration(X, S, precond, nnz, c["n_unknowns"])
     # the other GPU-parallel preconditioners on the same resident problem, for the record
     variant = None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not args.no_variants:
         variant = []
         names = {X.PRECOND_JACOBI: "jacobi", X.PRECOND_MCSSOR: "mcssor", X.PRECOND_AMG: "amg"}
         for other in names:

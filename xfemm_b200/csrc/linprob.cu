@@ -557,13 +557,17 @@ __global__ void k_dirichlet(int n, const int *__restrict__ rowptr, const int *__
 // walks the levels, one warp per pair, lanes over the coupled rows k.
 //   item (4 ints): slot(k,i) slot(i,k) slot(k,j) slot(j,k)
 //   meta (6 ints): i, j, type, slot(i,i), slot(j,j), unused
+// lv0 >= 0: only that level, pairs spread over the whole grid (pairs of one level touch disjoint
+// entries; the host launches the levels one after the other).  lv0 < 0: all levels in ONE block.
 __global__ void __launch_bounds__(1024)
 k_periodic(int nlevels, const int *__restrict__ level_ptr, const int *__restrict__ item_ptr,
            const int *__restrict__ meta, const int *__restrict__ items, double *vals, double *b,
-           const unsigned char *__restrict__ fill_mask, unsigned char *created)
+           const unsigned char *__restrict__ fill_mask, unsigned char *created, int lv0)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int lv = 0; lv < nlevels; lv++)
+    const int lane = threadIdx.x & 31;
+    const int warp = (lv0 >= 0 ? blockIdx.x * (blockDim.x >> 5) : 0) + (threadIdx.x >> 5);
+    const int nw = (lv0 >= 0 ? gridDim.x : 1) * (blockDim.x >> 5);
+    for (int lv = (lv0 >= 0 ? lv0 : 0); lv < (lv0 >= 0 ? lv0 + 1 : nlevels); lv++)
     {
         for (int pr = level_ptr[lv] + warp; pr < level_ptr[lv + 1]; pr += nw)
         {
@@ -1014,10 +1018,25 @@ int xfemm_linprob_periodic(xfemm_linprob *p, int npairs, const int *ni, const in
         XB_CUDA(p->pbc_items.upload(items2.data(), items2.size(), st));
         XB_CUDA(cudaStreamSynchronize(st));
         p->pbc_hash = h; p->pbc_pairs = npairs; p->pbc_levels = nlevels;
+        p->h_pbc_level_ptr = level_ptr;
     }
-    ++xb::g_launch, k_periodic<<<1, 1024, 0, p->stream>>>(p->pbc_levels, p->pbc_level_ptr.p, p->pbc_item_ptr.p, p->pbc_meta.p,
+    if (p->pbc_levels <= 32)
+    {
+        // few dependency levels (the usual case: neighbouring boundary nodes share an edge): one launch
+        // per level, one warp per pair over the whole device instead of a 3 ms latency chain in one block
+        for (int lv = 0; lv < p->pbc_levels; lv++)
+        {
+            const int np = p->h_pbc_level_ptr[lv + 1] - p->h_pbc_level_ptr[lv];
+            if (np <= 0) continue;
+            ++xb::g_launch, k_periodic<<<(np + 7) / 8, 256, 0, p->stream>>>(p->pbc_levels, p->pbc_level_ptr.p, p->pbc_item_ptr.p,
+                                                                          p->pbc_meta.p, p->pbc_items.p, p->vals.p, p->b.p,
+                                                                          p->fill_mask.n ? p->fill_mask.p : nullptr, p->created.p, lv);
+        }
+    }
+    else
+        ++xb::g_launch, k_periodic<<<1, 1024, 0, p->stream>>>(p->pbc_levels, p->pbc_level_ptr.p, p->pbc_item_ptr.p, p->pbc_meta.p,
                                           p->pbc_items.p, p->vals.p, p->b.p,
-                                          p->fill_mask.n ? p->fill_mask.p : nullptr, p->created.p);
+                                          p->fill_mask.n ? p->fill_mask.p : nullptr, p->created.p, -1);
     XB_CUDA(cudaGetLastError());
     XB_CUDA(cudaStreamSynchronize(p->stream));
     return XFEMM_OK;
