@@ -369,6 +369,21 @@ def main():
             variant.append({"preconditioner": names[other], "iterations": vit, "pcg_ms": vms, "relres": vs["relres"],
                             "ms_per_iter": vms / max(1, vit), "algorithmic_gbs": vb * vit / (vms * 1e-3) / 1e9 if vms > 0 else None})
         S.set_option("precond", precond)
+    # a sweep that only reads the torque: nodal values stay on the device
+    torque_only = None
+    if rank == 0 and world == 1 and c["n_age"] > 0:
+        S.set_option("fetch_solution", 0)
+        tq = []
+        sync()
+        t1 = time.perf_counter()
+        for i in range(args.steps):
+            S.set_rotor_angle(position(args.warmup + i))
+            S.resolve()
+            tq.append(S.gap_torque(0))
+        sync()
+        torque_only = {"s_per_position": (time.perf_counter() - t1) / args.steps, "torque_Nm": tq,
+                       "positions_deg": [position(args.warmup + i) for i in range(args.steps)]}
+        S.set_option("fetch_solution", 1)
     if world > 1:
         t = torch.tensor([elapsed], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -407,6 +422,7 @@ def main():
                      "frac": achieved / peak, "traffic": None, "bytes_per_iter": bytes_iter},
         "e2e": {"value": e2e, "unit": "s/problem", "h2d_bytes_per_step": int(h2d.value), "d2h_bytes_per_step": int(d2h.value)},
         "variant": variant,
+        "sweep_torque_only": torque_only,
         "host_setup_s": {"load_mesh": t_load, "cuthill": t_cm},
         "gpu_launches": launches,
         "clocks": sampler.summary(),

@@ -211,6 +211,13 @@ int xfemm_linprob_newton_norms(xfemm_linprob *p, double *dv2, double *v2);
 int xfemm_linprob_relax(xfemm_linprob *p, double relax);
 /* planar: b = V*c ; axisymmetric: b = V*c*2*pi*r*0.01 (static2d.cpp:1018-1021, staticaxi.cpp:779-783) */
 int xfemm_mag_solution_to_A(xfemm_mag *m, double *A_host);
+/* DC torque through an air-gap element from the RESIDENT solution (no nodal values leave the device).
+ * Replaces the post-processor's mo_gapintegral(name,0): cfemm/fpproc/fpproc.cpp:1391-1615 (flux density
+ * per ring cell and its harmonics) and 5418-5446 (torque).  cell0/ncells: range in the flattened ring
+ * tables; lengths in metres; br_bt (optional, 2*ncells): radial and tangential flux density per cell [T]. */
+int xfemm_mag_gap_torque(xfemm_mag *m, int cell0, int ncells, double inner_shift, double outer_shift, double arc_step_rad,
+                         double r_mid_m, double dr_m, int bdry_format, int m_harm, double depth_m, double *torque,
+                         double *br_bt);
 
 /* ------------------------------------------------------------------ complex-symmetric linear problem
  * Values, right-hand side and solution are interleaved (re,im) doubles — layout of the reference's
@@ -333,8 +340,11 @@ int xfemm_fsolver_resolve(xfemm_fsolver *s);
  * `age_index` for new inner (rotor) / outer (stator) angles in degrees, as fmesher would write
  * them into the .pbc file (cfemm/fmesher/writepoly.cpp:1853-1966).  Follow with
  * xfemm_fsolver_solve, or with xfemm_fsolver_resolve if the problem was solved with option
- * "age_union_pattern" = 1 (pattern independent of the angle). */
+ * "age_union_pattern", "fetch_solution", "assemble_only" = 1 (pattern independent of the angle). */
 int xfemm_fsolver_set_rotor_angle(xfemm_fsolver *s, int age_index, double inner_angle_deg, double outer_angle_deg);
+/* torque [N m] through air-gap element `age_index` from the resident magnetostatic solution
+ * (= mo_gapintegral(name,0) of the reference's post-processor on the written .ans) */
+int xfemm_fsolver_gap_torque(xfemm_fsolver *s, int age_index, double *torque);
 int xfemm_fsolver_write(xfemm_fsolver *s);     /* WriteStatic2D / WriteHarmonic2D                  */
 int xfemm_fsolver_close(xfemm_fsolver *s);
 int xfemm_fsolver_counts(xfemm_fsolver *s, int *n_nodes, int *n_elems, int *n_pbc, int *n_age,

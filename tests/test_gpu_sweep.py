@@ -82,6 +82,9 @@ def test_gap_torque_via_reference_postprocessor(tmp_path):
         S.write()
         mine = _gap_torque(str(ours), "tb")
         assert abs(mine["TORQUE"] - math.sin(math.radians(angle))) <= tq_tolerance
+        # the same integral evaluated on the device from the resident solution (no .ans, no nodal D2H)
+        dev = S.gap_torque(0)
+        assert abs(dev - mine["TORQUE"]) <= 1e-9 * max(abs(mine["TORQUE"]), 1e-3), (dev, mine["TORQUE"])
         if angle in (0.0, 30.0):
             # the reference solver on the mesh fmesher produced for this angle
             name = "tb" if angle == 0.0 else "tb30"
@@ -94,3 +97,25 @@ def test_gap_torque_via_reference_postprocessor(tmp_path):
             assert abs(mine["TORQUE"] - refq["TORQUE"]) <= 1e-4 * max(abs(refq["TORQUE"]), 1e-2)
             if "ENERGY" in refq and refq["ENERGY"] != 0:
                 assert abs(mine["ENERGY"] - refq["ENERGY"]) <= 1e-4 * abs(refq["ENERGY"])
+
+
+def test_torque_only_sweep_leaves_nodal_values_on_device(tmp_path):
+    """A sweep that reads only the torque: no nodal values are copied back between positions."""
+    S = X.FSolver(stage_case("tb", tmp_path))
+    S.set_option("age_union_pattern", 1)
+    S.load_mesh(False)
+    S.renumber(False)
+    S.solve()
+    S.set_option("fetch_solution", 0)
+    import ctypes as C
+    h2d, d2h = C.c_longlong(0), C.c_longlong(0)
+    X.lib().xfemm_transfer_bytes(C.byref(h2d), C.byref(d2h), 1)
+    tq = []
+    for angle in (0.0, 10.0, 30.0, 60.0, 90.0):
+        S.set_rotor_angle(angle)
+        S.resolve()
+        tq.append(S.gap_torque(0))
+    X.lib().xfemm_transfer_bytes(C.byref(h2d), C.byref(d2h), 0)
+    assert d2h.value < 5 * 64 * 1024  # scalars, flags and the 2x96 flux densities only
+    for angle, t in zip((0.0, 10.0, 30.0, 60.0, 90.0), tq):
+        assert abs(t - math.sin(math.radians(angle))) <= 0.000042 + 2e-4 * abs(math.sin(math.radians(angle))), (angle, t)

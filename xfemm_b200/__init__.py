@@ -88,6 +88,9 @@ SIGNATURES = {
     "xfemm_mag_assemble_static": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double)]),
     "xfemm_mag_get_mu": (C.c_int, [_P, _dp]),
     "xfemm_mag_solution_to_A": (C.c_int, [_P, _dp]),
+    "xfemm_mag_gap_torque": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
+                                       C.c_int, C.c_int, C.c_double, C.POINTER(C.c_double), _P]),
+    "xfemm_fsolver_gap_torque": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double)]),
     "xfemm_clinprob_create": (C.c_int, [C.c_int, C.c_int, _ip, _ip, C.POINTER(_P)]),
     "xfemm_clinprob_destroy": (C.c_int, [_P]),
     "xfemm_clinprob_n": (C.c_int, [_P]),
@@ -384,6 +387,12 @@ class FSolver:
     def set_rotor_angle(self, inner_deg, outer_deg=0.0, age_index=0):
         """Re-targets an air-gap element to a new rotor angle without re-meshing."""
         _check(lib().xfemm_fsolver_set_rotor_angle(self.h, age_index, float(inner_deg), float(outer_deg)), "set_rotor_angle")
+
+    def gap_torque(self, age_index=0):
+        """Torque [N m] through an air-gap element from the resident solution (no .ans file, no nodal D2H)."""
+        t = C.c_double(0)
+        _check(lib().xfemm_fsolver_gap_torque(self.h, age_index, C.byref(t)), "gap_torque")
+        return t.value
 
     def write(self):
         _check(lib().xfemm_fsolver_write(self.h), "write")

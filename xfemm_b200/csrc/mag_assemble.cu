@@ -31,6 +31,7 @@ struct xfemm_mag
     int n_age_cells = 0, n_age_mats = 0;
     xb::DevBuf<int> age_nodes, age_mid;
     xb::DevBuf<double> age_w, age_mats;
+    xb::DevBuf<double> gap_out; // torque + per-cell flux densities of the last gap integral
     // point sources
     int n_psrc = 0;
     xb::DevBuf<int> psrc_node;
@@ -485,6 +486,58 @@ __global__ void k_age_scatter(int ncells, const int *__restrict__ nodes, const d
     }
 }
 
+// DC torque through an air-gap element from the resident solution (reference post-processor:
+// cfemm/fpproc/fpproc.cpp:1391-1615 flux density at the centre of every ring cell from the 10 ring
+// nodes and its harmonics, fpproc.cpp:5418-5446 torque = pi R^2 Depth/mu0 * sum_k Re(brc btc* + brs bts*)).
+// One block; ncells cells starting at cell0 of the flattened ring tables; A = cscale * V.
+// out[0] = torque [N m]; out[1 .. ncells] = Br, out[1+ncells .. 2 ncells] = Bt per cell [T].
+__global__ void k_gap_torque(int cell0, int ncells, const int *__restrict__ nodes, const double *__restrict__ w,
+                             const double *__restrict__ V, double cscale, double ci, double co, double dt, double R,
+                             double dr, int bdry_format, int m, int nharm, double scale, double *out)
+{
+    extern __shared__ double sh[]; // br[ncells], bt[ncells], partial[blockDim/32]
+    double *br = sh, *bt = sh + ncells, *part = sh + 2 * ncells;
+    for (int k = threadIdx.x; k < ncells; k += blockDim.x)
+    {
+        double a[10];
+        for (int q = 0; q < 10; q++) a[q] = cscale * V[nodes[(size_t)(cell0 + k) * 10 + q]] * w[(size_t)(cell0 + k) * 10 + q];
+        const double ci2 = ci * ci, ci3 = ci2 * ci, co2 = co * co, co3 = co2 * co;
+        const double r = (-(ci * a[1]) - 2 * a[2] + 2 * a[3] + ci * (a[2] + a[3] - a[4]) - ci3 * (a[0] - 4 * a[1] + 6 * a[2] - 4 * a[3] + a[4]) +
+                          ci2 * (a[0] - 5 * a[1] + 9 * a[2] - 7 * a[3] + 2 * a[4]) - 2 * a[7] + 2 * a[8] + co * (-a[6] + a[7] + a[8] - a[9]) -
+                          co3 * (a[5] - 4 * a[6] + 6 * a[7] - 4 * a[8] + a[9]) + co2 * (a[5] - 5 * a[6] + 9 * a[7] - 7 * a[8] + 2 * a[9])) / (4 * dt * R);
+        const double t = (ci * a[1] + 2 * a[2] + 2 * a[3] - ci2 * (a[0] - 3 * a[1] + a[2] + 3 * a[3] - 2 * a[4]) + ci * (a[2] - a[3] - a[4]) +
+                          ci3 * (a[0] - 2 * a[1] + 2 * a[3] - a[4]) - co * a[6] + (-2 + co) * (1 + co) * a[7] - 2 * a[8] +
+                          co * (a[8] + co * (a[5] - 3 * a[6] + 3 * a[8] - 2 * a[9]) + a[9] + co2 * (-a[5] + 2 * a[6] - 2 * a[8] + a[9]))) / (4 * dr);
+        br[k] = r; bt[k] = t;
+        out[1 + k] = r; out[1 + ncells + k] = t;
+    }
+    __syncthreads();
+    double tq = 0.0;
+    for (int j = threadIdx.x; j < nharm; j += blockDim.x)
+    {
+        const int nh = bdry_format == 0 ? m * j : m * (2 * j + 1);
+        double brc = 0, brs = 0, btc = 0, bts = 0;
+        for (int k = 0; k < ncells; k++)
+        {
+            const double tta = ((double)k + 0.5) * dt * nh;
+            const double c = cos(tta), s = sin(tta);
+            brc += br[k] * c; brs += br[k] * s; btc += bt[k] * c; bts += bt[k] * s;
+        }
+        const bool whole = (nh == 0) || ((j == nharm - 1) && bdry_format == 0 && (ncells % 2) == 0);
+        const double div = whole ? (double)ncells : (double)ncells / 2.;
+        tq += (brc / div) * (btc / div) + (brs / div) * (bts / div);
+    }
+    tq = xb::warp_sum(tq);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = tq;
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        double t = 0;
+        for (int q = 0; q < (int)(blockDim.x >> 5); q++) t += part[q];
+        out[0] = t * scale;
+    }
+}
+
 __global__ void k_point_sources(int np, const int *__restrict__ node, const double *__restrict__ val, double *b)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -666,6 +719,34 @@ int xfemm_mag_get_mu(xfemm_mag *m, double *mu12)
     XB_ARG(m && mu12, "null pointer");
     XB_CUDA(cudaMemcpyAsync(mu12, m->mu.p, (size_t)m->n_elems * 2 * sizeof(double), cudaMemcpyDeviceToHost, m->lin->stream));
     XB_CUDA(cudaStreamSynchronize(m->lin->stream));
+    return XFEMM_OK;
+}
+
+int xfemm_mag_gap_torque(xfemm_mag *m, int cell0, int ncells, double inner_shift, double outer_shift, double arc_step_rad,
+                         double r_mid_m, double dr_m, int bdry_format, int m_harm, double depth_m, double *torque,
+                         double *br_bt /* optional, 2*ncells */)
+{
+    XB_ARG(m && torque && ncells > 0 && cell0 >= 0 && cell0 + ncells <= m->n_age_cells, "air-gap cell range");
+    XB_ARG(!m->axisymmetric, "gap torque is defined for planar problems");
+    xfemm_linprob *L = m->lin;
+    cudaStream_t st = L->stream;
+    const int nharm = bdry_format == 0 ? ncells / 2 + 1 : (ncells + 1) / 2;
+    const double muo = 1.2566370614359173e-6, PIc = 3.141592653589793238462643383;
+    const double scale = PIc * r_mid_m * r_mid_m * depth_m / muo;
+    if (m->gap_out.n != (size_t)1 + 2 * ncells) XB_CUDA(m->gap_out.alloc((size_t)1 + 2 * ncells));
+    const int threads = 128;
+    const size_t smem = ((size_t)2 * ncells + threads / 32) * sizeof(double);
+    XB_ARG(smem <= 48 * 1024, "air-gap element with too many cells");
+    ++xb::g_launch, k_gap_torque<<<1, threads, smem, st>>>(cell0, ncells, m->age_nodes.p, m->age_w.p, L->V.p, PIc * 4.e-05, inner_shift,
+                                                          outer_shift, arc_step_rad, r_mid_m, dr_m, bdry_format, m_harm, nharm, scale,
+                                                          m->gap_out.p);
+    std::vector<double> h((size_t)1 + 2 * ncells);
+    xb::g_d2h_bytes += (long long)h.size() * 8;
+    XB_CUDA(cudaMemcpyAsync(h.data(), m->gap_out.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    XB_CUDA(cudaStreamSynchronize(st));
+    XB_CUDA(cudaGetLastError());
+    *torque = h[0];
+    if (br_bt) std::copy(h.begin() + 1, h.end(), br_bt);
     return XFEMM_OK;
 }
 

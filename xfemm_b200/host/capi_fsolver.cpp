@@ -116,6 +116,18 @@ int xfemm_fsolver_solve(xfemm_fsolver *s)
     return XFEMM_OK;
 }
 
+int xfemm_fsolver_gap_torque(xfemm_fsolver *s, int age_index, double *torque)
+{
+    if (!s || !torque) return XFEMM_ERR_ARG;
+    if (!s->S.gapTorque(age_index, *torque))
+    {
+        std::string prev = xfemm_last_error();
+        xb::set_error("gap torque failed (%s)", prev.c_str());
+        return XFEMM_ERR_ARG;
+    }
+    return XFEMM_OK;
+}
+
 int xfemm_fsolver_resolve(xfemm_fsolver *s)
 {
     if (!s || !s->L) { xb::set_error("no resident static problem (call xfemm_fsolver_solve first)"); return XFEMM_ERR_ARG; }
@@ -277,6 +289,7 @@ int xfemm_fsolver_set_option(xfemm_fsolver *s, const char *key, double value)
     if (!strcmp(key, "precond")) { s->S.precondOption = (int)value; return XFEMM_OK; }
     if (!strcmp(key, "max_iter")) { s->S.maxIterOption = (int)value; return XFEMM_OK; }
     if (!strcmp(key, "keep_system")) { s->S.keepSystem = value != 0; return XFEMM_OK; }
+    if (!strcmp(key, "fetch_solution")) { s->S.fetchSolution = value != 0; return XFEMM_OK; }
     if (!strcmp(key, "assemble_only")) { s->S.assembleOnly = value != 0; return XFEMM_OK; }
     if (!strcmp(key, "age_union_pattern")) { s->S.ageUnionPattern = value != 0; return XFEMM_OK; }
     xb::set_error("unknown option %s", key);

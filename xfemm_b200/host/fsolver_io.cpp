@@ -111,6 +111,7 @@ FSolver::FSolver()
     keepSystem = false;
     ageUnionPattern = false;
     assembleOnly = false;
+    fetchSolution = true;
 }
 
 FSolver::~FSolver() { releaseDevice(); }

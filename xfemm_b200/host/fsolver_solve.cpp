@@ -704,7 +704,8 @@ int FSolver::staticNewton(CBigLinProb &L)
     stats.newton_iters = Iter;
 
     // results back to the caller's arrays: L.V internal units, L.b = A (static2d.cpp:1018-1021)
-    if (xfemm_linprob_get_solution(lin, L.V) != XFEMM_OK || xfemm_mag_solution_to_A(magdev, L.b) != XFEMM_OK)
+    // (sweeps that only read derived quantities — gapTorque — leave the nodal values on the device)
+    if (fetchSolution && (xfemm_linprob_get_solution(lin, L.V) != XFEMM_OK || xfemm_mag_solution_to_A(magdev, L.b) != XFEMM_OK))
     {
         WarnMessage(xfemm_last_error());
         return false;
@@ -728,6 +729,35 @@ int FSolver::HarmonicAxisymmetric(CBigComplexLinProb &L, bool verbose) { return 
 // table is regenerated here from the table already loaded: ring nodes are mapped onto the annulus
 // grid for every periodic copy, sorted by angle, and bracketed per annulus cell.
 // ---------------------------------------------------------------------------------------
+// Torque through an air-gap element from the solution resident on the device: what the reference
+// obtains by writing the .ans file and evaluating mo_gapintegral(name,0) in fpproc
+// (cfemm/fpproc/fpproc.cpp:1391-1615 and 5418-5446).  Planar magnetostatics.
+bool FSolver::gapTorque(int ageIndex, double &torque)
+{
+    static const double lengthConv[] = {0.0254, 0.001, 0.01, 1., 2.54e-05, 1.e-06}; // metres per unit (fpproc.cpp LengthConv)
+    if (ageIndex < 0 || ageIndex >= (int)agelist.size() || !magdev || Frequency != 0 || ProblemType != PLANAR)
+    {
+        WarnMessage("xfemm_b200: gap torque needs a solved planar magnetostatic problem with that air-gap element\n");
+        return false;
+    }
+    int cell0 = 0;
+    for (int a = 0; a < ageIndex; a++) cell0 += agelist[a].totalArcElements;
+    const CAirGapElement &g = agelist[ageIndex];
+    const double conv = lengthConv[LengthUnits];
+    const double ri = g.ri * conv, ro = g.ro * conv;
+    const double R = (ri + ro) / 2., dr = ro - ri;
+    const double dt = (PI / 180.) * g.totalArcLength / ((double)g.totalArcElements);
+    const int m = (g.BdryFormat == 0) ? (int)std::lround(360. / g.totalArcLength) : (int)std::lround(180. / g.totalArcLength);
+    const double depth = (Depth == -1) ? 1. : Depth * conv;
+    if (xfemm_mag_gap_torque(magdev, cell0, g.totalArcElements, g.InnerShift, g.OuterShift, dt, R, dr, g.BdryFormat, m, depth,
+                             &torque, nullptr) != XFEMM_OK)
+    {
+        WarnMessage(xfemm_last_error());
+        return false;
+    }
+    return true;
+}
+
 bool FSolver::setAirGapAngles(int ageIndex, double innerAngle, double outerAngle)
 {
     if (ageIndex < 0 || ageIndex >= (int)agelist.size()) return false;
