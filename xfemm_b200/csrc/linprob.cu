@@ -605,6 +605,66 @@ k_periodic(int nlevels, const int *__restrict__ level_ptr, const int *__restrict
     }
 }
 
+// Long dependency chains (neighbouring pairs along a periodic boundary share entries, so a list
+// ordered along the boundary is ONE chain): one block, every warp pre-loads the plan of its next pair
+// (indices only, independent of the values) and then waits for its turn; the per-pair critical path is
+// the value loads + stores + a shared-memory hand-off instead of a chain of five dependent loads and a
+// block barrier.  pair_wait[q] = number of pairs (in level-sorted order) that must be finished first.
+__global__ void __launch_bounds__(1024)
+k_periodic_turn(int npairs, const int *__restrict__ pair_wait, const int *__restrict__ item_ptr,
+                const int *__restrict__ meta, const int *__restrict__ items, double *vals, double *b,
+                const unsigned char *__restrict__ fill_mask, unsigned char *created)
+{
+    __shared__ int done;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (threadIdx.x == 0) done = 0;
+    __syncthreads();
+    for (int pr = warp; pr < npairs; pr += nw)
+    {
+        // ---- plan of this pair (does not depend on earlier pairs)
+        const int *m = meta + 6 * pr;
+        const int ni = m[0], nj = m[1], sii = m[3], sjj = m[4];
+        const double sgn = m[2] ? -1.0 : 1.0;
+        const int it0 = item_ptr[pr], it1 = item_ptr[pr + 1], need = pair_wait[pr];
+        int4 q = make_int4(0, 0, 0, 0);
+        if (it0 + lane < it1) q = *reinterpret_cast<const int4 *>(items + 4 * (it0 + lane));
+        // ---- wait for the pairs this one depends on
+        while (*(volatile int *)&done < need) {}
+        __syncwarp();
+        // all value loads of the pair in one round trip: lane 0 also fetches the two diagonals and the RHS
+        double dii = 0, djj = 0, bi = 0, bj = 0;
+        if (lane == 0) { dii = __ldcg(vals + sii); djj = __ldcg(vals + sjj); bi = __ldcg(b + ni); bj = __ldcg(b + nj); }
+        for (int it = it0 + lane; it < it1; it += 32)
+        {
+            if (it != it0 + lane) q = *reinterpret_cast<const int4 *>(items + 4 * it);
+            double v1 = __ldcg(vals + q.x), v2 = __ldcg(vals + q.z);
+            if (v1 != 0.0 || v2 != 0.0)
+            {
+                double c = (v1 + sgn * v2) / 2.0;
+                __stcg(vals + q.x, c); __stcg(vals + q.y, c);
+                __stcg(vals + q.z, sgn * c); __stcg(vals + q.w, sgn * c);
+                if (fill_mask)
+                {
+                    if (fill_mask[q.x]) created[q.x] = 1;
+                    if (fill_mask[q.y]) created[q.y] = 1;
+                    if (fill_mask[q.z]) created[q.z] = 1;
+                    if (fill_mask[q.w]) created[q.w] = 1;
+                }
+            }
+        }
+        if (lane == 0)
+        {
+            double c = m[2] ? 0.5 * (dii + djj) : (dii + djj) / 2.0;
+            __stcg(vals + sii, c); __stcg(vals + sjj, c);
+            double cb = 0.5 * (bi + sgn * bj);
+            __stcg(b + ni, cb); __stcg(b + nj, sgn * cb);
+        }
+        __syncwarp();
+        __threadfence_block();
+        if (lane == 0) atomicAdd(&done, 1);
+    }
+}
+
 // Newton bookkeeping (static2d.cpp:953-989)
 __global__ void k_newton_norms(int n, const double *__restrict__ V, const double *__restrict__ Vold, double *part)
 {
@@ -1019,6 +1079,12 @@ int xfemm_linprob_periodic(xfemm_linprob *p, int npairs, const int *ni, const in
         XB_CUDA(cudaStreamSynchronize(st));
         p->pbc_hash = h; p->pbc_pairs = npairs; p->pbc_levels = nlevels;
         p->h_pbc_level_ptr = level_ptr;
+        // pairs a pair has to wait for: everything in the earlier levels
+        std::vector<int> wait(std::max(1, npairs), 0);
+        for (int l = 0; l < nlevels; l++)
+            for (int q = level_ptr[l]; q < level_ptr[l + 1]; q++) wait[q] = level_ptr[l];
+        XB_CUDA(p->pbc_wait.upload(wait.data(), wait.size(), st));
+        XB_CUDA(cudaStreamSynchronize(st));
     }
     if (p->pbc_levels <= 32)
     {
@@ -1033,6 +1099,10 @@ int xfemm_linprob_periodic(xfemm_linprob *p, int npairs, const int *ni, const in
                                                                           p->fill_mask.n ? p->fill_mask.p : nullptr, p->created.p, lv);
         }
     }
+    else if (env_int("XFEMM_PBC_TURN", 1))
+        ++xb::g_launch, k_periodic_turn<<<1, 1024, 0, p->stream>>>(p->pbc_pairs, p->pbc_wait.p, p->pbc_item_ptr.p, p->pbc_meta.p,
+                                                                  p->pbc_items.p, p->vals.p, p->b.p,
+                                                                  p->fill_mask.n ? p->fill_mask.p : nullptr, p->created.p);
     else
         ++xb::g_launch, k_periodic<<<1, 1024, 0, p->stream>>>(p->pbc_levels, p->pbc_level_ptr.p, p->pbc_item_ptr.p, p->pbc_meta.p,
                                           p->pbc_items.p, p->vals.p, p->b.p,

@@ -56,6 +56,7 @@ struct xfemm_linprob
     int pbc_pairs = 0, pbc_levels = 0, pbc_max_level_pairs = 0;
     xb::DevBuf<int> pbc_level_ptr, pbc_item_ptr, pbc_meta, pbc_items;
     std::vector<int> h_pbc_level_ptr; // host copy: pairs per dependency level
+    xb::DevBuf<int> pbc_wait;         // per pair (level-sorted): pairs that must be finished before it starts
     xb::DevBuf<unsigned char> fill_mask, created; // optional, see xfemm_linprob_set_fill_mask
 
     // result mailbox
