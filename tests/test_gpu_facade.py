@@ -1,0 +1,71 @@
+"""CBigLinProb host facade (the class hsolver/esolver share with fsolver): a caller that
+assembles through Put/AddTo on the host and only solves on the GPU.  The same call sequence is replayed
+on the pinned CPU restatement of the reference class (oracle/oracle_core.c) and the solutions compared."""
+import ctypes as C
+import math
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _oracle_solution(N, scale_second=1.5):
+    import sys
+    sys.path.insert(0, ROOT)
+    from oracle import fsolver_oracle
+    lib = fsolver_oracle.lib()
+    n = N * N
+    m = C.c_void_p(lib.orc_create(n, N + 1))
+    lib.orc_set_precision(m, 1e-10)
+    b = lib.orc_b(m)
+    addto = lambda v, p, q: lib.orc_addto(m, v, p, q)
+    for j in range(N):
+        for i in range(N):
+            k = j * N + i
+            addto(4.0 + 0.01 * (k % 7), k, k)
+            if i + 1 < N:
+                addto(-1.0, k, k + 1)
+            if j + 1 < N:
+                addto(-1.0 - 0.001 * (k % 5), k, k + N)
+            b[k] = math.sin(0.37 * k) + 0.1
+    for j in range(N):
+        lib.orc_setvalue(m, j * N, 0.1 * j)
+    lib.orc_setvalue(m, 0, 0.5)
+    for i in range(1, N - 1):
+        lib.orc_periodicity(m, i, (N - 1) * N + i, 0 if i % 2 == 0 else 1)
+    it1 = lib.orc_pcgsolve(m, 0, 100000)
+    V = lib.orc_V(m)
+    v1 = np.array([V[k] for k in range(n)])
+    for k in range(n):
+        b[k] *= scale_second
+    it2 = lib.orc_pcgsolve(m, 1, 100000)
+    v2 = np.array([V[k] for k in range(n)])
+    lib.orc_destroy(m)
+    return v1, v2, it1, it2
+
+
+@pytest.mark.parametrize("precond", ["amg", "jacobi", "mcssor"])
+def test_host_assembled_problem_solves_on_gpu(precond, tmp_path):
+    exe = str(tmp_path / "facade_driver")
+    host = os.path.join(ROOT, "xfemm_b200", "host")
+    libdir = os.path.join(ROOT, "xfemm_b200")
+    r = subprocess.run(["g++", "-std=c++14", "-O1", "-I" + host, os.path.join(ROOT, "tests", "facade_driver.cpp"), "-o", exe,
+                        "-L" + libdir, "-lxfemm_b200", "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    N = 24
+    r = subprocess.run([exe, str(N)], capture_output=True, text=True, env=dict(os.environ, XFEMM_PRECOND=precond))
+    assert r.returncode == 0, r.stdout[-500:] + r.stderr[-2000:]
+    first, second = r.stdout.split("#\n")
+    v1 = np.array([float(x) for x in first.split()])
+    v2 = np.array([float(x) for x in second.split()])
+    o1, o2, it1, it2 = _oracle_solution(N)
+    assert len(v1) == N * N and len(v2) == N * N
+    assert np.linalg.norm(v1 - o1) <= 1e-8 * np.linalg.norm(o1)
+    assert np.linalg.norm(v2 - o2) <= 1e-8 * np.linalg.norm(o2)
+    # fixed values come out of the iterative solve (spars.cpp:318 keeps the row), the last SetValue wins on node 0
+    assert abs(v1[0] - 0.5) < 1e-9 and abs(v1[5 * N] - 0.5) < 1e-9
+    print(precond, r.stderr.strip(), "oracle iterations", it1, it2)
