@@ -101,7 +101,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(nm)
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.02)
 
     def summary(self):
         s = sorted(self.samples)
@@ -160,6 +160,16 @@ def pcg_bytes_per_iteration(X, S, precond, nnz, n):
         cyc += 24.0 * nz[l] + 128.0 * nr[l] + 24.0 * nr[l + 1]
     cyc += 8.0 * nr[nl - 1] ** 2
     return krylov + cyc, levels
+
+
+def ncu_traffic(precond):
+    """DRAM bytes (read + write) of one launch of the persistent kernel, from the committed ncu --set full
+    capture of this same command (profiles/r01_ncu_traffic.json); None if there is no capture for it."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+        return d[precond]["dram_bytes_per_launch"]
+    except Exception:
+        return None
 
 
 def run_partitioned(args, base, workload, rank, local_rank, world):
@@ -352,6 +362,21 @@ def main():
     st = S.stats()
     nnz = X.lib().xfemm_fsolver_nnz(S.h)
     bytes_iter, levels = pcg_bytes_per_iteration(X, S, precond, nnz, c["n_unknowns"])
+    # a sweep that only reads the torque: nodal values stay on the device (SURVEY §8f-2)
+    torque_only = None
+    if rank == 0 and world == 1 and c["n_age"] > 0:
+        S.set_option("fetch_solution", 0)
+        tq = []
+        sync()
+        t1 = time.perf_counter()
+        for i in range(args.steps):
+            S.set_rotor_angle(position(args.warmup + i))
+            S.resolve()
+            tq.append(S.gap_torque(0))
+        sync()
+        torque_only = {"s_per_position": (time.perf_counter() - t1) / args.steps, "torque_Nm": tq,
+                       "positions_deg": [position(args.warmup + i) for i in range(args.steps)]}
+        S.set_option("fetch_solution", 1)
     # the other GPU-parallel preconditioners on the same resident problem, for the record
     variant = None
     if rank == 0 and world == 1 and not args.no_variants:
@@ -369,21 +394,6 @@ def main():
             variant.append({"preconditioner": names[other], "iterations": vit, "pcg_ms": vms, "relres": vs["relres"],
                             "ms_per_iter": vms / max(1, vit), "algorithmic_gbs": vb * vit / (vms * 1e-3) / 1e9 if vms > 0 else None})
         S.set_option("precond", precond)
-    # a sweep that only reads the torque: nodal values stay on the device (SURVEY §8f-2)
-    torque_only = None
-    if rank == 0 and world == 1 and c["n_age"] > 0:
-        S.set_option("fetch_solution", 0)
-        tq = []
-        sync()
-        t1 = time.perf_counter()
-        for i in range(args.steps):
-            S.set_rotor_angle(position(args.warmup + i))
-            S.resolve()
-            tq.append(S.gap_torque(0))
-        sync()
-        torque_only = {"s_per_position": (time.perf_counter() - t1) / args.steps, "torque_Nm": tq,
-                       "positions_deg": [position(args.warmup + i) for i in range(args.steps)]}
-        S.set_option("fetch_solution", 1)
     if world > 1:
         t = torch.tensor([elapsed], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -419,7 +429,9 @@ def main():
         "assembly": {"ms": sum(asm_ms) / len(asm_ms), "elements_per_s": c["n_elems"] / (1e-3 * sum(asm_ms) / len(asm_ms))},
         "roofline": {"bound": "hbm", "kernel": "k_pcg<%s> (persistent PCG: SpMV + fused vector updates + preconditioner)" % args.precond,
                      "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "bytes_per_iter": bytes_iter},
+                     "frac": achieved / peak, "traffic": ncu_traffic(args.precond), "bytes_per_iter": bytes_iter,
+                     "achieved_note": "algorithmic bytes per launch (bytes_per_iter x iterations) / CUDA-event launch duration; "
+                                      "traffic = DRAM bytes of one launch from the committed ncu capture (profiles/)"},
         "e2e": {"value": e2e, "unit": "s/problem", "h2d_bytes_per_step": int(h2d.value), "d2h_bytes_per_step": int(d2h.value)},
         "variant": variant,
         "sweep_torque_only": torque_only,

@@ -14,6 +14,8 @@ template <class F>
 inline void parallel_for(int n, F f, int min_per_thread = 16384)
 {
     int nt = (int)std::thread::hardware_concurrency();
+    // one process per GPU: share the cores between the ranks of this node (torchrun exports LOCAL_WORLD_SIZE)
+    if (const char *lw = getenv("LOCAL_WORLD_SIZE")) nt /= std::max(1, atoi(lw));
     if (const char *e = getenv("XFEMM_HOST_THREADS")) nt = atoi(e);
     nt = std::max(1, std::min(nt, 32));
     nt = std::min(nt, std::max(1, n / std::max(1, min_per_thread)));
