@@ -8,6 +8,9 @@
 // The parser here is line oriented ("key = value" lines inside [section] / <Begin…>…<End…>
 // blocks) instead of the reference's token stream; it accepts the same files.
 #include "fsolver.h"
+#include <chrono>
+#include <unordered_map>
+#include "../csrc/layout.h"
 #include <algorithm>
 #include <cctype>
 #include <cstdarg>
@@ -470,12 +473,71 @@ struct TextFile
     }
     void skipLine() { restOfLine(); }
 };
+
+// ---- line-parallel parsing of the big mesh files -------------------------------------------
+// The reference reads .node/.ele/.edge with fgets + sscanf, one record per line (fsolver.cpp:362-697).
+// Here the line starts are located once and the records are parsed by a handful of host threads
+// (the files are 100-150 MB of text at 2 M nodes; a serial scan was 1.5 s, most of "load mesh").
+static std::vector<const char *> line_starts(const char *b, const char *e)
+{
+    const size_t len = (size_t)(e - b);
+    const int chunks = 64;
+    std::vector<size_t> cnt(chunks + 1, 0);
+    xb::parallel_for(chunks, [&](int c0, int c1, int) {
+        for (int c = c0; c < c1; c++)
+        {
+            const char *p = b + len * c / chunks, *q = b + len * (c + 1) / chunks;
+            size_t n = 0;
+            while (p < q && (p = (const char *)memchr(p, '\n', (size_t)(q - p))) != nullptr) { n++; p++; }
+            cnt[c + 1] = n;
+        }
+    }, 1);
+    for (int c = 0; c < chunks; c++) cnt[c + 1] += cnt[c];
+    std::vector<const char *> ls(cnt[chunks] + 2);
+    ls[0] = b;
+    xb::parallel_for(chunks, [&](int c0, int c1, int) {
+        for (int c = c0; c < c1; c++)
+        {
+            const char *p = b + len * c / chunks, *q = b + len * (c + 1) / chunks;
+            size_t k = cnt[c] + 1;
+            while (p < q && (p = (const char *)memchr(p, '\n', (size_t)(q - p))) != nullptr) { p++; ls[k++] = p; }
+        }
+    }, 1);
+    ls[cnt[chunks] + 1] = e;
+    ls.resize(cnt[chunks] + 1); // ls[i] = start of line i (a last entry after the final newline may be empty)
+    return ls;
+}
+static inline const char *skip_blank(const char *p) { while (*p == ' ' || *p == '\t' || *p == '\r') p++; return p; }
+static inline bool parse_int(const char *&p, int &v)
+{
+    p = skip_blank(p);
+    bool neg = false;
+    if (*p == '-') { neg = true; p++; } else if (*p == '+') p++;
+    if (*p < '0' || *p > '9') return false;
+    long r = 0;
+    while (*p >= '0' && *p <= '9') r = r * 10 + (*p++ - '0');
+    v = (int)(neg ? -r : r);
+    return true;
+}
+static inline bool parse_double(const char *&p, double &v)
+{
+    p = skip_blank(p);
+    char *q;
+    v = strtod(p, &q);
+    if (q == p) return false;
+    p = q;
+    return true;
+}
 } // namespace
 
 LoadMeshErr FSolver::LoadMesh(bool deleteFiles)
 {
     TextFile F;
     int k = 0, j = 0;
+    const bool timing = getenv("XFEMM_TIMING") != nullptr;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double tt = now();
+    auto tick = [&](const char *what) { if (timing) { fprintf(stderr, "[xfemm timing]   LoadMesh %s %.3f s\n", what, now() - tt); tt = now(); } };
     // ---- nodes (fsolver.cpp:362-391): coordinates to centimetres
     if (!F.open(PathName + ".node")) return BADNODEFILE;
     F.nextInt(k);
@@ -483,17 +545,26 @@ LoadMeshErr FSolver::LoadMesh(bool deleteFiles)
     NumNodes = k;
     meshnode.assign(k, CNode());
     const double cm = 100 * LengthConvMeters[LengthUnits];
-    for (int i = 0; i < k; i++)
     {
-        CNode &nd = meshnode[i];
-        F.nextInt(j);
-        F.nextDouble(nd.x);
-        F.nextDouble(nd.y);
-        F.nextInt(j);
-        nd.BoundaryMarker = (j > 1) ? j - 2 : -1;
-        nd.x *= cm;
-        nd.y *= cm;
+        std::vector<const char *> ls = line_starts(F.buf.data(), F.end);
+        if ((int)ls.size() < k + 1) return BADNODEFILE;
+        xb::parallel_for(k, [&](int i0, int i1, int) {
+            for (int i = i0; i < i1; i++)
+            {
+                CNode &nd = meshnode[i];
+                const char *p = ls[i + 1];
+                int idx = 0, mk = 0;
+                parse_int(p, idx);
+                parse_double(p, nd.x);
+                parse_double(p, nd.y);
+                parse_int(p, mk);
+                nd.BoundaryMarker = (mk > 1) ? mk - 2 : -1;
+                nd.x *= cm;
+                nd.y *= cm;
+            }
+        });
     }
+    tick("nodes");
     // ---- periodic pairs + air-gap elements (fsolver.cpp:393-515)
     if (!F.open(PathName + ".pbc")) return BADPBCFILE;
     F.nextInt(NumPBCs);
@@ -550,12 +621,24 @@ LoadMeshErr FSolver::LoadMesh(bool deleteFiles)
     auto removeMeshFiles = [&]() {
         for (const char *ext : {".ele", ".node", ".pbc", ".poly", ".edge"}) remove((PathName + ext).c_str());
     };
+    {
+        std::vector<const char *> ls = line_starts(F.buf.data(), F.end);
+        if ((int)ls.size() < k + 1) return BADELEMENTFILE;
+        xb::parallel_for(k, [&](int i0, int i1, int) {
+            for (int i = i0; i < i1; i++)
+            {
+                CMElement &el = meshele[i];
+                const char *p = ls[i + 1];
+                int idx = 0;
+                parse_int(p, idx);
+                parse_int(p, el.p[0]); parse_int(p, el.p[1]); parse_int(p, el.p[2]);
+                parse_int(p, el.lbl);
+            }
+        });
+    }
     for (int i = 0; i < k; i++)
     {
         CMElement &el = meshele[i];
-        F.nextInt(j);
-        F.nextInt(el.p[0]); F.nextInt(el.p[1]); F.nextInt(el.p[2]);
-        F.nextInt(el.lbl);
         el.lbl--;
         if (el.lbl < 0) el.lbl = defaultLabel;
         if (el.lbl < 0)
@@ -579,42 +662,58 @@ LoadMeshErr FSolver::LoadMesh(bool deleteFiles)
         el.e[0] = el.e[1] = el.e[2] = -1;
         el.mu1 = -1.; el.mu2 = -1.;
     }
-    // ---- boundary edges (fsolver.cpp:624-697): node → elements adjacency, then tag sides
-    std::vector<int> mptr(NumNodes + 1, 0);
-    for (int i = 0; i < NumEls; i++)
-        for (int s = 0; s < 3; s++) mptr[meshele[i].p[s] + 1]++;
-    for (int i = 0; i < NumNodes; i++) mptr[i + 1] += mptr[i];
-    std::vector<int> mbr(mptr[NumNodes]);
-    {
-        std::vector<int> pos(mptr.begin(), mptr.end() - 1);
-        for (int i = 0; i < NumEls; i++)
-            for (int s = 0; s < 3; s++) mbr[pos[meshele[i].p[s]]++] = i;
-    }
+    tick("elements");
+    // ---- boundary edges (fsolver.cpp:624-697).  The reference walks the elements around the first node
+    // of every tagged edge; equivalently every element side looks its node pair up among the tagged
+    // edges (a few thousand of millions; a later edge of the file overrides an earlier one).
     if (!F.open(PathName + ".edge")) return BADEDGEFILE;
     F.nextInt(k);
     F.nextInt(j);
-    edgeList.clear();
-    edgeList.reserve((size_t)k * 2);
-    for (int i = 0; i < k; i++)
+    edgeList.assign((size_t)k * 2, 0);
+    std::vector<int> edgeMark(k, 0);
     {
-        int n0 = 0, n1 = 0;
-        F.nextInt(j); F.nextInt(n0); F.nextInt(n1); F.nextInt(j);
-        edgeList.push_back(n0);
-        edgeList.push_back(n1);
-        if (j < 0)
-        {
-            j = -(j + 2);
-            for (int q = mptr[n0]; q < mptr[n0 + 1]; q++)
+        std::vector<const char *> ls = line_starts(F.buf.data(), F.end);
+        if ((int)ls.size() < k + 1) return BADEDGEFILE;
+        xb::parallel_for(k, [&](int i0, int i1, int) {
+            for (int i = i0; i < i1; i++)
             {
-                CMElement &el = meshele[mbr[q]];
-                for (int s = 0; s < 3; s++)
-                {
-                    int a = el.p[s], b = el.p[(s + 1) % 3];
-                    if ((a == n0 && b == n1) || (a == n1 && b == n0)) el.e[s] = j;
-                }
+                const char *p = ls[i + 1];
+                int idx = 0;
+                parse_int(p, idx);
+                parse_int(p, edgeList[2 * (size_t)i]); parse_int(p, edgeList[2 * (size_t)i + 1]);
+                parse_int(p, edgeMark[i]);
             }
+        });
+    }
+    {
+        std::unordered_map<long long, int> tagged;
+        for (int i = 0; i < k; i++)
+            if (edgeMark[i] < 0)
+            {
+                const long long a = std::min(edgeList[2 * (size_t)i], edgeList[2 * (size_t)i + 1]);
+                const long long b = std::max(edgeList[2 * (size_t)i], edgeList[2 * (size_t)i + 1]);
+                tagged[a * (long long)NumNodes + b] = -(edgeMark[i] + 2);
+            }
+        if (!tagged.empty())
+        {
+            std::vector<char> onTagged(NumNodes, 0); // cheap pre-filter: nodes that sit on a tagged edge
+            for (const auto &kv : tagged) { onTagged[kv.first / NumNodes] = 1; onTagged[kv.first % NumNodes] = 1; }
+            xb::parallel_for(NumEls, [&](int i0, int i1, int) {
+                for (int i = i0; i < i1; i++)
+                {
+                    CMElement &el = meshele[i];
+                    for (int sd = 0; sd < 3; sd++)
+                    {
+                        const int a = el.p[sd], b = el.p[(sd + 1) % 3];
+                        if (!onTagged[a] || !onTagged[b]) continue;
+                        auto f = tagged.find((long long)std::min(a, b) * NumNodes + std::max(a, b));
+                        if (f != tagged.end()) el.e[sd] = f->second;
+                    }
+                }
+            });
         }
     }
+    tick("edges");
     if (deleteFiles)
         for (const char *ext : {".ele", ".node", ".pbc", ".poly"}) remove((PathName + ext).c_str());
     return NOERROR;

@@ -9,6 +9,7 @@
 //   FSolver::StaticAxisymmetric       cfemm/fsolver/staticaxi.cpp:45-794
 #include "fsolver.h"
 #include "../../include/xfemm_b200.h"
+#include "../csrc/layout.h"
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -60,11 +61,15 @@ void FSolver::SortNodes(const std::vector<int> &newnum)
 int FSolver::SortElements()
 {
     std::vector<int> tri(3 * (size_t)NumEls), order(NumEls);
-    for (int k = 0; k < NumEls; k++)
-        for (int j = 0; j < 3; j++) tri[3 * (size_t)k + j] = meshele[k].p[j];
+    xb::parallel_for(NumEls, [&](int k0, int k1, int) {
+        for (int k = k0; k < k1; k++)
+            for (int j = 0; j < 3; j++) tri[3 * (size_t)k + j] = meshele[k].p[j];
+    });
     if (xfemm_renumber_sort_elements(NumEls, tri.data(), order.data()) != XFEMM_OK) return false;
     std::vector<CMElement> out(NumEls);
-    for (int k = 0; k < NumEls; k++) out[k] = meshele[order[k]];
+    xb::parallel_for(NumEls, [&](int k0, int k1, int) {
+        for (int k = k0; k < k1; k++) out[k] = meshele[order[k]];
+    });
     meshele.swap(out);
     return true;
 }
@@ -90,8 +95,12 @@ int FSolver::Cuthill(bool deleteFiles)
     if (deleteFiles) remove(edgeFile.c_str());
     std::vector<int> newnum(NumNodes);
     int bw = 0;
+    const bool timing = getenv("XFEMM_TIMING") != nullptr;
+    double tt = wall();
+    auto tick = [&](const char *what) { if (timing) { fprintf(stderr, "[xfemm timing]   Cuthill %s %.3f s\n", what, wall() - tt); tt = wall(); } };
     if (xfemm_renumber_cuthill(NumNodes, (int)(edgeList.size() / 2), edgeList.data(), newnum.data(), &bw) != XFEMM_OK)
         return false;
+    tick("numbering");
     BandWidth = bw;
     for (int i = 0; i < NumPBCs; i++)
     {
@@ -103,11 +112,16 @@ int FSolver::Cuthill(bool deleteFiles)
         {
             q.n0 = newnum[q.n0]; q.n1 = newnum[q.n1]; q.n2 = newnum[q.n2]; q.n3 = newnum[q.n3];
         }
-    for (int i = 0; i < NumEls; i++)
-        for (int j = 0; j < 3; j++) meshele[i].p[j] = newnum[meshele[i].p[j]];
+    xb::parallel_for(NumEls, [&](int i0, int i1, int) {
+        for (int i = i0; i < i1; i++)
+            for (int j = 0; j < 3; j++) meshele[i].p[j] = newnum[meshele[i].p[j]];
+    });
+    tick("remap");
     SortNodes(newnum);
     cmPermutation = newnum;
+    tick("SortNodes");
     SortElements();
+    tick("SortElements");
     std::vector<int>().swap(edgeList);
     return true;
 }

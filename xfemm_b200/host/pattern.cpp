@@ -212,8 +212,10 @@ int xfemm_renumber_cuthill(int n_nodes, int n_edges, const int *edges, int *newn
             con[pos[b]++] = a;
         }
     }
-    for (int i = 0; i < n; i++)
-        std::stable_sort(con.begin() + ptr[i], con.begin() + ptr[i + 1], [&](int a, int b) { return deg[a] < deg[b]; });
+    xb::parallel_for(n, [&](int i0, int i1, int) {
+        for (int i = i0; i < i1; i++)
+            std::stable_sort(con.begin() + ptr[i], con.begin() + ptr[i + 1], [&](int a, int b) { return deg[a] < deg[b]; });
+    });
 
     // start node (cuthill.cpp:233-245): the scan stops right after the first index >= 1 at which
     // the running minimum equals 2.
@@ -281,12 +283,12 @@ int xfemm_renumber_cuthill(int n_nodes, int n_edges, const int *edges, int *newn
 int xfemm_renumber_sort_elements(int n_elems, const int *tri, int *order_out)
 {
     if (n_elems < 0 || (n_elems > 0 && (!tri || !order_out))) { xb::set_error("invalid arguments"); return XFEMM_ERR_ARG; }
-    std::vector<int> key(n_elems);
-    for (int k = 0; k < n_elems; k++)
-    {
-        key[k] = tri[3 * (size_t)k] + tri[3 * (size_t)k + 1] + tri[3 * (size_t)k + 2];
-        order_out[k] = k;
-    }
+    // (key, index) pairs.  One pass with gap g only ever compares positions of the same residue mod g,
+    // so the g chains are independent: they are processed in parallel as contiguous blocks of residues,
+    // which replays exactly the swaps of the serial pass.
+    struct KI { int key, idx; };
+    std::vector<KI> a(n_elems);
+    for (int k = 0; k < n_elems; k++) a[k] = {tri[3 * (size_t)k] + tri[3 * (size_t)k + 1] + tri[3 * (size_t)k + 2], k};
     int gap = n_elems;
     bool swapped;
     do
@@ -296,17 +298,24 @@ int xfemm_renumber_sort_elements(int n_elems, const int *tri, int *order_out)
             gap = (int)(((long long)gap * 10) / 13);
             if (gap == 10 || gap == 9) gap = 11;
         }
-        swapped = false;
-        for (int j = 0; j + gap < n_elems; j++)
-        {
-            if (key[j] > key[j + gap])
+        std::vector<char> sw(64, 0);
+        const int g = gap;
+        if (g <= 0) break;
+        xb::parallel_for(g, [&](int r0, int r1, int tid) {
+            bool s = false;
+            for (long long base = 0; base + g < n_elems; base += g)
             {
-                std::swap(key[j], key[j + gap]);
-                std::swap(order_out[j], order_out[j + gap]);
-                swapped = true;
+                const long long hi = std::min<long long>(r1, (long long)n_elems - g - base);
+                KI *x = a.data() + base;
+                for (long long r = r0; r < hi; r++)
+                    if (x[r].key > x[r + g].key) { std::swap(x[r], x[r + g]); s = true; }
             }
-        }
+            if (s) sw[tid] = 1;
+        }, 16);
+        swapped = false;
+        for (char c : sw) swapped = swapped || c;
     } while (gap > 1 && swapped);
+    for (int k = 0; k < n_elems; k++) order_out[k] = a[k].idx;
     return XFEMM_OK;
 }
 
