@@ -99,6 +99,10 @@ int xfemm_linprob_multa(xfemm_linprob *p, const double *x, double *y);  /* spars
 int xfemm_linprob_multpc(xfemm_linprob *p, int precond, const double *x, double *y); /* :197   */
 /* timing hooks for bench.py: run `reps` SpMVs / PCG iterations on resident data, device-timed */
 int xfemm_linprob_bench_spmv(xfemm_linprob *p, int reps, double *ms_per_rep);
+/* optional locality hint: coordinates (x,y per row) of the unknowns.  The solver's internal row order then
+ * follows a Z-curve through the plane instead of the caller's numbering (gathers of a slice hit fewer
+ * sectors, multigrid transfers become local).  Results are unaffected.  xy = NULL removes the hint. */
+int xfemm_linprob_set_coords(xfemm_linprob *p, const double *xy);
 /* levels of the multigrid hierarchy built by the last XFEMM_PRECOND_AMG solve: rows and full-matrix
  * non-zeros per level (level 0 = the problem itself); returns the number of levels (0: none built) */
 int xfemm_linprob_amg_levels(xfemm_linprob *p, int max_levels, int *n_rows, long long *nnz);
@@ -340,7 +344,10 @@ int xfemm_fsolver_resolve(xfemm_fsolver *s);
  * `age_index` for new inner (rotor) / outer (stator) angles in degrees, as fmesher would write
  * them into the .pbc file (cfemm/fmesher/writepoly.cpp:1853-1966).  Follow with
  * xfemm_fsolver_solve, or with xfemm_fsolver_resolve if the problem was solved with option
- * "age_union_pattern", "fetch_solution", "assemble_only" = 1 (pattern independent of the angle). */
+ * "age_union_pattern" = 1 (sparsity pattern independent of the angle).
+ * Other options of xfemm_fsolver_set_option: "fetch_solution" = 0 (leave V and A on the device after a
+ * solve), "assemble_only" = 1 (stop after assembly + boundary conditions), "locality_order" = 1/0/-1
+ * (Z-curve row order inside the solver; -1 = only when the problem is going to be re-solved). */
 int xfemm_fsolver_set_rotor_angle(xfemm_fsolver *s, int age_index, double inner_angle_deg, double outer_angle_deg);
 /* torque [N m] through air-gap element `age_index` from the resident magnetostatic solution
  * (= mo_gapintegral(name,0) of the reference's post-processor on the written .ans) */

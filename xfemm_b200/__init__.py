@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libxfemm_b200.so")
+LIB_PATH = os.environ.get("XFEMM_B200_LIB", os.path.join(_HERE, "libxfemm_b200.so"))  # override: experiments only
 
 PRECOND_JACOBI = 0
 PRECOND_MCSSOR = 1
@@ -69,6 +69,7 @@ SIGNATURES = {
     "xfemm_linprob_multpc": (C.c_int, [_P, C.c_int, _dp, _dp]),
     "xfemm_linprob_bench_spmv": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double)]),
     "xfemm_linprob_amg_levels": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_longlong)]),
+    "xfemm_linprob_set_coords": (C.c_int, [_P, _P]),
     "xfemm_linprob_save_solution": (C.c_int, [_P]),
     "xfemm_linprob_newton_norms": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "xfemm_linprob_relax": (C.c_int, [_P, C.c_double]),

@@ -18,7 +18,7 @@ CPP = ["csrc/layout.cpp", "host/pattern.cpp", "host/fsolver_io.cpp", "host/fsolv
        "host/capi_fsolver.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+              "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + os.environ.get("XFEMM_NVCC_EXTRA", "").split()
 CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-Wall", "-Wno-unused-result"]
 
 

@@ -242,6 +242,20 @@ int amg_build(xfemm_linprob *fine, std::unique_ptr<AmgHierarchy> &out)
             rc = xfemm_linprob_create(nc, crp.data(), ccol.data(), &c);
             if (rc != XFEMM_OK) return rc;
             h->coarse.push_back(c);
+            if ((int)cur->h_xy.size() == 2 * cur->n)
+            {
+                // coarse "node" = centroid of its aggregate: the coarse level follows the same Z-curve
+                std::vector<double> sx(nc, 0.), sy(nc, 0.);
+                std::vector<int> cnt(nc, 0);
+                for (int i = 0; i < cur->n; i++)
+                    if (agg[i] >= 0) { sx[agg[i]] += cur->h_xy[2 * (size_t)i]; sy[agg[i]] += cur->h_xy[2 * (size_t)i + 1]; cnt[agg[i]]++; }
+                c->h_xy.resize(2 * (size_t)nc);
+                for (int I = 0; I < nc; I++)
+                {
+                    c->h_xy[2 * (size_t)I] = (float)(sx[I] / std::max(1, cnt[I]));
+                    c->h_xy[2 * (size_t)I + 1] = (float)(sy[I] / std::max(1, cnt[I]));
+                }
+            }
             rc = linprob_build_layout(c, XFEMM_PRECOND_JACOBI);
             if (rc != XFEMM_OK) return rc;
         }

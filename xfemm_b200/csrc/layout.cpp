@@ -46,7 +46,7 @@ int greedy_coloring(int n, const int *rowptr, const int *col, int max_colors, st
 }
 
 void build_sell_layout(int n, const int *rowptr, const int *col, const std::vector<int> *color_in,
-                       int ncolors, int sigma, SellLayout &L, int wide_threshold)
+                       int ncolors, int sigma, SellLayout &L, int wide_threshold, const int *base_order)
 {
     // rows with more than `wide_threshold` off-diagonals leave the SELL structure (see layout.h)
     std::vector<unsigned char> wide(n, 0);
@@ -57,8 +57,11 @@ void build_sell_layout(int n, const int *rowptr, const int *col, const std::vect
 
     // ---- internal order: by colour (if any), inside a colour keep the caller's order, then
     // sort windows of `sigma` rows by their entry counts so slices are homogeneous.
+    // `base_order` (optional): a locality-preserving sequence of the rows (e.g. along a space-filling
+    // curve through the node coordinates) to start from instead of the caller's numbering
     std::vector<int> order(n);
-    std::iota(order.begin(), order.end(), 0);
+    if (base_order) std::copy(base_order, base_order + n, order.begin());
+    else std::iota(order.begin(), order.end(), 0);
     std::vector<int> color_start; // in rows (unpadded sequence positions)
     const bool colored = color_in && ncolors > 0;
     if (colored)
@@ -69,7 +72,8 @@ void build_sell_layout(int n, const int *rowptr, const int *col, const std::vect
         for (int c = 0; c < ncolors; c++) cnt[c + 1] += cnt[c];
         color_start = cnt;
         std::vector<int> pos(cnt.begin(), cnt.end() - 1);
-        for (int i = 0; i < n; i++) order[pos[color[i]]++] = i;
+        std::vector<int> seq(order);
+        for (int k = 0; k < n; k++) order[pos[color[seq[k]]]++] = seq[k];
     }
     else
     {
@@ -233,6 +237,47 @@ void build_sell_layout(int n, const int *rowptr, const int *col, const std::vect
             L.wide_rseg.push_back((int)L.wide_sptr.size() - 1);
         }
     }
+}
+
+// Z-order (Morton) sequence of points: rows that are close in the plane end up close in memory, so
+// the gathers of a slice hit few sectors and the transfer maps between multigrid levels become local.
+void morton_order(int n, const float *xy, std::vector<int> &order)
+{
+    order.resize(n);
+    if (n == 0) return;
+    float x0 = xy[0], x1 = xy[0], y0 = xy[1], y1 = xy[1];
+    for (int i = 1; i < n; i++)
+    {
+        x0 = std::min(x0, xy[2 * (size_t)i]); x1 = std::max(x1, xy[2 * (size_t)i]);
+        y0 = std::min(y0, xy[2 * (size_t)i + 1]); y1 = std::max(y1, xy[2 * (size_t)i + 1]);
+    }
+    const float span = std::max(std::max(x1 - x0, y1 - y0), 1e-30f);
+    auto spread = [](unsigned v) -> unsigned long long {
+        unsigned long long x = v & 0xffffffffull;
+        x = (x | (x << 16)) & 0x0000ffff0000ffffull;
+        x = (x | (x << 8)) & 0x00ff00ff00ff00ffull;
+        x = (x | (x << 4)) & 0x0f0f0f0f0f0f0f0full;
+        x = (x | (x << 2)) & 0x3333333333333333ull;
+        x = (x | (x << 1)) & 0x5555555555555555ull;
+        return x;
+    };
+    // 11 bits per axis -> 4 M cells; a stable counting sort by cell keeps the caller's (Cuthill-McKee,
+    // already local) order inside a cell and costs three linear passes instead of a comparison sort
+    const int BITS = 11;
+    const float scale = (float)((1 << BITS) - 1);
+    std::vector<unsigned> cell(n);
+    parallel_for(n, [&](int i0, int i1, int) {
+        for (int i = i0; i < i1; i++)
+        {
+            const unsigned qx = (unsigned)((xy[2 * (size_t)i] - x0) / span * scale);
+            const unsigned qy = (unsigned)((xy[2 * (size_t)i + 1] - y0) / span * scale);
+            cell[i] = (unsigned)(spread(qx) | (spread(qy) << 1));
+        }
+    });
+    std::vector<int> start((size_t)(1u << (2 * BITS)) + 1, 0);
+    for (int i = 0; i < n; i++) start[cell[i] + 1]++;
+    for (size_t c = 0; c + 1 < start.size(); c++) start[c + 1] += start[c];
+    for (int i = 0; i < n; i++) order[start[cell[i]]++] = i;
 }
 
 } // namespace xb

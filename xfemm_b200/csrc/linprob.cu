@@ -698,14 +698,18 @@ int linprob_build_layout(xfemm_linprob *p, int precond)
     p->tile_grid = -1; // and so are the stream tiles
     SellLayout &L = p->lay;
     const int sigma = env_int("XFEMM_SELL_SIGMA", 1024);
+    // with node coordinates the internal order follows a Z-curve through the plane (gather locality)
+    std::vector<int> zorder;
+    if ((int)p->h_xy.size() == 2 * p->n && env_int("XFEMM_MORTON", 1)) morton_order(p->n, p->h_xy.data(), zorder);
+    const int *base = zorder.empty() ? nullptr : zorder.data();
     if (precond == XFEMM_PRECOND_MCSSOR)
     {
         std::vector<int> color;
         int nc = greedy_coloring(p->n, p->h_rowptr.data(), p->h_col.data(), env_int("XFEMM_MAX_COLORS", 7), color);
-        build_sell_layout(p->n, p->h_rowptr.data(), p->h_col.data(), &color, nc, sigma, L, env_int("XFEMM_WIDE_ROW", 64));
+        build_sell_layout(p->n, p->h_rowptr.data(), p->h_col.data(), &color, nc, sigma, L, env_int("XFEMM_WIDE_ROW", 64), base);
     }
     else
-        build_sell_layout(p->n, p->h_rowptr.data(), p->h_col.data(), nullptr, 0, sigma, L, env_int("XFEMM_WIDE_ROW", 64));
+        build_sell_layout(p->n, p->h_rowptr.data(), p->h_col.data(), nullptr, 0, sigma, L, env_int("XFEMM_WIDE_ROW", 64), base);
     cudaStream_t st = p->stream;
     XB_CUDA(p->i2c.upload(L.i2c.data(), L.i2c.size(), st));
     XB_CUDA(p->c2i.upload(L.c2i.data(), L.c2i.size(), st));
@@ -1329,6 +1333,23 @@ int xfemm_linprob_multpc(xfemm_linprob *p, int precond, const double *x, double 
     XB_CUDA(cudaMemcpyAsync(y, p->Vold.p, (size_t)p->n * sizeof(double), cudaMemcpyDeviceToHost, st));
     XB_CUDA(cudaStreamSynchronize(st));
     XB_CUDA(cudaGetLastError());
+    return XFEMM_OK;
+}
+
+int xfemm_linprob_set_coords(xfemm_linprob *p, const double *xy)
+{
+    XB_ARG(p, "null handle");
+    if (!xy) { p->h_xy.clear(); return XFEMM_OK; }
+    p->h_xy.resize(2 * (size_t)p->n);
+    for (size_t k = 0; k < p->h_xy.size(); k++) p->h_xy[k] = (float)xy[k];
+    if (p->layout_precond >= 0)
+    {
+        // a layout built before the hint arrived is rebuilt on the next solve
+        p->layout_precond = -1;
+        delete p->amg;
+        p->amg = nullptr;
+        p->tile_grid = -1;
+    }
     return XFEMM_OK;
 }
 

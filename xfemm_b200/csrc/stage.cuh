@@ -16,8 +16,14 @@
 
 namespace xb {
 
-constexpr int STAGE_TILE_ENT = 2048; // entries per tile (16 KB of values + 8 KB of columns)
-constexpr int STAGE_COUNT = 3;
+#ifndef XB_STAGE_TILE_ENT
+#define XB_STAGE_TILE_ENT 2048
+#endif
+#ifndef XB_STAGE_COUNT
+#define XB_STAGE_COUNT 3
+#endif
+constexpr int STAGE_TILE_ENT = XB_STAGE_TILE_ENT; // entries per tile (2048: 16 KB of values + 8 KB of columns)
+constexpr int STAGE_COUNT = XB_STAGE_COUNT;
 constexpr int STAGE_MAX_TILES = 256; // per block
 constexpr size_t STAGE_SMEM_BYTES = (size_t)STAGE_COUNT * STAGE_TILE_ENT * 12 + STAGE_MAX_TILES * 16 + 128;
 static_assert(STAGE_COUNT * (8 + 4 + 4) <= 128, "barriers and counters must fit the tail of the ring");

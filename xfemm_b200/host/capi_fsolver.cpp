@@ -289,6 +289,7 @@ int xfemm_fsolver_set_option(xfemm_fsolver *s, const char *key, double value)
     if (!strcmp(key, "precond")) { s->S.precondOption = (int)value; return XFEMM_OK; }
     if (!strcmp(key, "max_iter")) { s->S.maxIterOption = (int)value; return XFEMM_OK; }
     if (!strcmp(key, "keep_system")) { s->S.keepSystem = value != 0; return XFEMM_OK; }
+    if (!strcmp(key, "locality_order")) { s->S.localityOrder = (int)value; return XFEMM_OK; }
     if (!strcmp(key, "fetch_solution")) { s->S.fetchSolution = value != 0; return XFEMM_OK; }
     if (!strcmp(key, "assemble_only")) { s->S.assembleOnly = value != 0; return XFEMM_OK; }
     if (!strcmp(key, "age_union_pattern")) { s->S.ageUnionPattern = value != 0; return XFEMM_OK; }

@@ -114,6 +114,7 @@ FSolver::FSolver()
     keepSystem = false;
     ageUnionPattern = false;
     assembleOnly = false;
+    localityOrder = -1;
     fetchSolution = true;
 }
 

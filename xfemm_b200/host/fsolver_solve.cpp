@@ -581,6 +581,10 @@ int FSolver::staticSolve(CBigLinProb &L, bool axi)
 
     std::vector<double> xy(2 * (size_t)NumNodes);
     for (int i = 0; i < NumNodes; i++) { xy[2 * (size_t)i] = meshnode[i].x; xy[2 * (size_t)i + 1] = meshnode[i].y; }
+    // Locality hint for the solver's internal row order (Z-curve through the node coordinates): the finer
+    // layout costs ~0.08 s of host time at 2 M nodes and saves ~2 ms per solve, so by default it is used
+    // when the device problem is going to be solved repeatedly (Newton iteration, rotor sweeps).
+    if (localityOrder > 0 || (localityOrder < 0 && (ageUnionPattern || !LinearFlag))) xfemm_linprob_set_coords(lin, xy.data());
     xfemm_mag_desc D;
     memset(&D, 0, sizeof D);
     D.axisymmetric = axi ? 1 : 0;
