@@ -86,3 +86,30 @@ def test_one_by_one_and_zero_rhs():
     # spars.cpp:255-257 returns on res_o == 0 BEFORE V is zeroed: the previous solution stays
     assert info.iterations == 0 and L.get_solution()[0] == 0.5
     L.close()
+
+
+@pytest.mark.parametrize("precond", [X.PRECOND_JACOBI, X.PRECOND_MCSSOR, X.PRECOND_AMG])
+def test_degenerate_systems(precond):
+    """Diagonal matrix (no couplings at all), all rows fixed by SetValue, and an empty periodic list."""
+    n = 100
+    rowptr = np.arange(n + 1, dtype=np.int32)
+    col = np.arange(n, dtype=np.int32)
+    L = X.LinProb(rowptr, col)
+    d = 1.0 + np.arange(n)
+    L.set_values(d)
+    b = np.cos(np.arange(n))
+    L.set_rhs(b)
+    L.pcg(1e-12, precond=precond)
+    assert np.abs(L.get_solution() - b / d).max() < 1e-12
+    L.close()
+    # every row fixed: the solve returns the prescribed values
+    A = _matrix(n=200)
+    L = X.LinProb(A.indptr, A.indices)
+    L.set_values(A.data)
+    L.set_rhs(np.ones(200))
+    vals = np.linspace(-1, 1, 200)
+    L.dirichlet(np.arange(200, dtype=np.int32), vals)
+    L.periodic(np.zeros((0, 3), dtype=np.int32))
+    L.pcg(1e-12, precond=precond)
+    assert np.abs(L.get_solution() - vals).max() < 1e-10
+    L.close()

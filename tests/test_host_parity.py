@@ -123,3 +123,30 @@ def test_no_cpu_fallback(tmp_path):
     with pytest.raises(X.XfemmError):
         X.LinProb(rowptr, col)
     assert X.fsolver_run(stage_case("tb30", tmp_path)) == 2   # main.cpp: exit code 2 = solve failed
+
+
+def test_edge_cases_of_the_host_primitives():
+    """Empty and degenerate inputs of the renumbering / pattern entry points."""
+    # a single node without edges: numbered 0, bandwidth 1
+    newnum, bw = X.renumber_cuthill(1, np.zeros((0, 2), dtype=np.int32))
+    assert list(newnum) == [0] and bw == 1
+    # two disconnected components (the restart branch of cuthill.cpp:269-301): a permutation results
+    newnum, _ = X.renumber_cuthill(5, np.array([[0, 1], [3, 4]], dtype=np.int32))
+    assert sorted(newnum) == [0, 1, 2, 3, 4]
+    # no elements: diagonal-only pattern
+    rp, col = X.pattern_build(4, np.zeros((0, 3), dtype=np.int32))
+    assert list(rp) == [0, 1, 2, 3, 4] and list(col) == [0, 1, 2, 3]
+    # one element, a periodic pair between a mesh node and an isolated node: the neighbours k of node 0 get
+    # entries (k,3) and (3,k); the pair itself stays uncoupled (spars.cpp:421-474 skips k == i, k == j)
+    rp, col, fill = X.pattern_build(4, np.array([[0, 1, 2]], dtype=np.int32), pbc=np.array([[0, 3]], dtype=np.int32), with_fill=True)
+    rows = [set(col[rp[i]:rp[i + 1]]) for i in range(4)]
+    assert rows[3] == {1, 2, 3} and rows[1] == {0, 1, 2, 3} and rows[2] == {0, 1, 2, 3} and rows[0] == {0, 1, 2}
+    assert fill.sum() > 0 and len(fill) == len(col)
+    # element sort of nothing / of one element
+    assert len(X.sort_elements(np.zeros((0, 3), dtype=np.int32))) == 0
+    assert list(X.sort_elements(np.array([[2, 1, 0]], dtype=np.int32))) == [0]
+    # out-of-range indices are refused
+    with pytest.raises(X.XfemmError):
+        X.renumber_cuthill(3, np.array([[0, 5]], dtype=np.int32))
+    with pytest.raises(X.XfemmError):
+        X.pattern_build(3, np.array([[0, 1, 2]], dtype=np.int32), pbc=np.array([[0, 9]], dtype=np.int32))

@@ -428,13 +428,14 @@ __global__ void __launch_bounds__(512, 2) k_pcg(PcgArgs a, AmgArgs g)
         const double pAp = reduce_partials(partA, G, sm);
         if (!(pAp > 0.0)) { status = XFEMM_ERR_DIVERGED; break; }
         const double del = res / pAp;
-        // steps ii, iii: V += del P ; R -= del U   (fused; Jacobi also fuses z.r)
+        // step iii: R -= del U (Jacobi also fuses z.r).  Step ii, V += del P, rides along with step v below:
+        // it needs nothing but P, and keeping x and p out of this phase leaves the vectors the next SpMV
+        // phase gathers from (multigrid: the pre-smoothed iterate) resident in L2.
         if (PRECOND == XFEMM_PRECOND_JACOBI)
         {
             part = 0.0;
             for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x)
             {
-                a.x[i] = fma(del, a.p[i], a.x[i]);
                 double ri = fma(-del, a.u[i], a.r[i]);
                 a.r[i] = ri;
                 part = fma(ri * a.dinv[i], ri, part);
@@ -444,7 +445,6 @@ __global__ void __launch_bounds__(512, 2) k_pcg(PcgArgs a, AmgArgs g)
         {
             for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x)
             {
-                a.x[i] = fma(del, a.p[i], a.x[i]);
                 const double ri = fma(-del, a.u[i], a.r[i]);
                 a.r[i] = ri;
                 // multigrid: the pre-smoothed iterate of the finest level comes for free here
@@ -460,11 +460,13 @@ __global__ void __launch_bounds__(512, 2) k_pcg(PcgArgs a, AmgArgs g)
         const double res_new = reduce_partials(partB, G, sm);
         const double rho = res_new / res;
         res = res_new;
-        // step v: P = Z + rho P
+        // step ii: V += del P, then step v: P = Z + rho P
         for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x)
         {
+            const double pi = a.p[i];
+            a.x[i] = fma(del, pi, a.x[i]);
             double zi = (PRECOND == XFEMM_PRECOND_JACOBI) ? a.r[i] * a.dinv[i] : a.z[i];
-            a.p[i] = fma(rho, a.p[i], zi);
+            a.p[i] = fma(rho, pi, zi);
         }
         it++;
         er = sqrt(res / res_o);
