@@ -189,7 +189,8 @@ def run_partitioned(args, base, workload, rank, local_rank, world):
     S.renumber(False)
     S.solve()
     c = S.counts()
-    D = DistPCG(S)
+    dprec = X.PRECOND_AMG if os.environ.get("XFEMM_DIST_PRECOND") == "amg" else X.PRECOND_JACOBI  # see dist_pcg.py
+    D = DistPCG(S, precond=dprec)
     D.refresh()
     launches0 = int(X.lib().xfemm_launch_count())
     infos = []
@@ -216,7 +217,8 @@ def run_partitioned(args, base, workload, rank, local_rank, world):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": v * 1e3, "higher_is_better": False,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload + " — ONE mesh row-partitioned over the GPUs (config 5b)", "n_nodes": c["n_nodes"],
-                       "nnz_full": nnz, "precision": 1e-10, "preconditioner": "jacobi",
+                       "nnz_full": nnz, "precision": 1e-10,
+                       "preconditioner": "jacobi" if dprec == X.PRECOND_JACOBI else "multigrid V-cycle of each rank's diagonal block",
                        "parallelism": f"row blocks of the Cuthill-McKee ordered matrix, halo all_to_all + 2 all_reduce per iteration (NCCL), {world} ranks",
                        "step": "the linear solve of one problem (assembly is replicated, <1 ms)", "blocks": blocks},
             "pcg": {"iterations": its, "ms": v * 1e3, "ms_per_iter": v * 1e3 / its, "er": infos[-1]["er"]},

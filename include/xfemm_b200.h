@@ -315,6 +315,9 @@ int xfemm_cmag_solution_to_A(xfemm_cmag *m, double *A_host);      /* n complex: 
 typedef struct xfemm_dist xfemm_dist;
 int xfemm_dist_create(xfemm_linprob *g, int r0, int r1, xfemm_dist **out);
 int xfemm_dist_destroy(xfemm_dist *d);
+/* XFEMM_PRECOND_JACOBI (default) or XFEMM_PRECOND_AMG: multigrid V-cycle of each rank's own diagonal block
+ * (additive Schwarz without overlap, no communication inside the cycle); call before xfemm_dist_refresh */
+int xfemm_dist_set_precond(xfemm_dist *d, int precond);
 int xfemm_dist_sizes(xfemm_dist *d, int *n_own, int *n_halo);
 int xfemm_dist_halo_columns(xfemm_dist *d, int *global_cols);              /* sorted global ids this rank needs */
 int xfemm_dist_set_send_rows(xfemm_dist *d, int n_send, const int *global_rows);

@@ -38,12 +38,12 @@ def _run(base, out, nproc, extra):
     return json.loads(line)
 
 
-@pytest.mark.parametrize("nproc", [1, 2, 3])
-def test_partitioned_on_one_gpu_matches_reference(nproc, tmp_path):
+@pytest.mark.parametrize("nproc,precond", [(1, "amg"), (2, "amg"), (2, "jacobi"), (3, "amg")])
+def test_partitioned_on_one_gpu_matches_reference(nproc, precond, tmp_path):
     ref, meta = load_ref("tb30")
     base = stage_case("tb30", tmp_path)
     out = str(tmp_path / "x.npz")
-    info = _run(base, out, nproc, ["--backend", "gloo", "--same-device"])
+    info = _run(base, out, nproc, ["--backend", "gloo", "--same-device", "--precond", precond])
     V = np.load(out)["V"]
     assert rel_l2(V, ref["V"]) <= 1e-6
     assert info["n_gpus"] == nproc and len(info["blocks"]) == nproc

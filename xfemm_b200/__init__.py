@@ -122,6 +122,7 @@ SIGNATURES = {
     "xfemm_dist_create": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P)]),
     "xfemm_dist_destroy": (C.c_int, [_P]),
     "xfemm_dist_sizes": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "xfemm_dist_set_precond": (C.c_int, [_P, C.c_int]),
     "xfemm_dist_halo_columns": (C.c_int, [_P, _ip]),
     "xfemm_dist_set_send_rows": (C.c_int, [_P, C.c_int, _P]),
     "xfemm_dist_refresh": (C.c_int, [_P]),

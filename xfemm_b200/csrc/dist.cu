@@ -23,6 +23,7 @@ struct xfemm_dist
     xb::DevBuf<unsigned char> owned; // per internal row: 1 = owned row
     xb::DevBuf<double> partials;
     int nblk = 0;
+    int precond = XFEMM_PRECOND_JACOBI; // or XFEMM_PRECOND_AMG: V-cycle of the rank's own diagonal block
 };
 
 namespace xb {
@@ -132,6 +133,47 @@ __global__ void kd_direction(int n_pad, const unsigned char *__restrict__ owned,
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x)
         if (owned[i]) p[i] = fma(beta, p[i], r[i] * dinv[i]);
 }
+// multigrid mode: x += alpha p ; r -= alpha u (the preconditioner kernel follows)
+__global__ void kd_update_xr(int n_pad, const unsigned char *__restrict__ owned, const double *__restrict__ g,
+                             const double *__restrict__ p, const double *__restrict__ u, double *x, double *r)
+{
+    const double alpha = g[0] / g[1];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x)
+    {
+        if (!owned[i]) continue;
+        x[i] = fma(alpha, p[i], x[i]);
+        r[i] = fma(-alpha, u[i], r[i]);
+    }
+}
+// partial of r.z over the owned rows
+__global__ void kd_dot_rz(int n_pad, const unsigned char *__restrict__ owned, const double *__restrict__ r,
+                          const double *__restrict__ z, double *part)
+{
+    __shared__ double sm[33];
+    double a = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x)
+        if (owned[i]) a = fma(r[i], z[i], a);
+    a = block_sum(a, sm);
+    if (threadIdx.x == 0) part[blockIdx.x] = a;
+}
+// p = z + beta p (beta = g[2]/g[0]); first = 1: p = z
+__global__ void kd_direction_z(int n_pad, const unsigned char *__restrict__ owned, const double *__restrict__ g,
+                               const double *__restrict__ z, double *p, int first)
+{
+    const double beta = first ? 0.0 : g[2] / g[0];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x)
+        if (owned[i]) p[i] = first ? z[i] : fma(beta, p[i], z[i]);
+}
+// x = 0 ; r = b (owned rows), 0 elsewhere
+__global__ void kd_init_xr(int n_pad, const unsigned char *__restrict__ owned, const double *__restrict__ b, double *x,
+                           double *r, double *p)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x)
+    {
+        x[i] = 0.0; p[i] = 0.0;
+        r[i] = owned[i] ? b[i] : 0.0;
+    }
+}
 __global__ void kd_mark_owned(int n_pad, int n_own, const int *__restrict__ i2c, unsigned char *owned)
 {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -212,6 +254,15 @@ int xfemm_dist_create(xfemm_linprob *g, int r0, int r1, xfemm_dist **out)
     return XFEMM_OK;
 }
 
+// preconditioner of the partitioned solve: XFEMM_PRECOND_JACOBI or XFEMM_PRECOND_AMG (multigrid V-cycle of
+// each rank's own diagonal block — additive Schwarz without overlap; call before xfemm_dist_refresh)
+int xfemm_dist_set_precond(xfemm_dist *d, int precond)
+{
+    XB_ARG(d && (precond == XFEMM_PRECOND_JACOBI || precond == XFEMM_PRECOND_AMG), "preconditioner");
+    d->precond = precond;
+    return XFEMM_OK;
+}
+
 int xfemm_dist_sizes(xfemm_dist *d, int *n_own, int *n_halo)
 {
     XB_ARG(d, "null handle");
@@ -251,7 +302,7 @@ int xfemm_dist_refresh(xfemm_dist *d)
     ++g_launch, kd_copy_block<<<(int)((L->nnz + 255) / 256), 256, 0, st>>>(L->nnz, d->slot_map.p, G->vals.p, L->vals.p);
     ++g_launch, kd_copy_rhs<<<(L->n + 255) / 256, 256, 0, st>>>(L->n, d->n_own, d->r0, G->b.p, L->b.p);
     // SELL refill + diagonal + RHS in internal order (same helpers as the single-GPU solve)
-    int rc = linprob_prepare(L, XFEMM_PRECOND_JACOBI);
+    int rc = linprob_prepare(L, d->precond);
     if (rc != XFEMM_OK) return rc;
     return linprob_load_rhs_internal(L);
 }
@@ -261,6 +312,18 @@ int xfemm_dist_init(xfemm_dist *d, double *scal_dev)
     XB_ARG(d && scal_dev, "null pointer");
     xfemm_linprob *L = d->loc;
     const int n_pad = L->lay.n_pad;
+    if (d->precond == XFEMM_PRECOND_AMG)
+    {
+        // x = 0, r = b ; z = M^-1 r (V-cycle of the rank's diagonal block) ; p = z ; scal = local r.z
+        ++g_launch, kd_init_xr<<<d->nblk, 256, 0, L->stream>>>(n_pad, d->owned.p, L->bint.p, L->x.p, L->r.p, L->p.p);
+        int rc = linprob_apply_amg_resident(L);
+        if (rc != XFEMM_OK) return rc;
+        ++g_launch, kd_direction_z<<<d->nblk, 256, 0, L->stream>>>(n_pad, d->owned.p, scal_dev, L->z.p, L->p.p, 1);
+        ++g_launch, kd_dot_rz<<<d->nblk, 256, 0, L->stream>>>(n_pad, d->owned.p, L->r.p, L->z.p, d->partials.p);
+        ++g_launch, kd_reduce<<<1, 256, 0, L->stream>>>(d->nblk, d->partials.p, scal_dev, 1);
+        XB_CUDA(cudaGetLastError());
+        return XFEMM_OK;
+    }
     ++g_launch, kd_init<<<d->nblk, 256, 0, L->stream>>>(n_pad, d->owned.p, L->bint.p, L->dinv.p, L->x.p, L->r.p, L->p.p, d->partials.p);
     ++g_launch, kd_reduce<<<1, 256, 0, L->stream>>>(d->nblk, d->partials.p, scal_dev, 1);
     XB_CUDA(cudaGetLastError());
@@ -301,6 +364,16 @@ int xfemm_dist_update(xfemm_dist *d, const double *glob_dev, double *scal_dev)
 {
     XB_ARG(d && glob_dev && scal_dev, "null pointer");
     xfemm_linprob *L = d->loc;
+    if (d->precond == XFEMM_PRECOND_AMG)
+    {
+        ++g_launch, kd_update_xr<<<d->nblk, 256, 0, L->stream>>>(L->lay.n_pad, d->owned.p, glob_dev, L->p.p, L->u.p, L->x.p, L->r.p);
+        int rc = linprob_apply_amg_resident(L);
+        if (rc != XFEMM_OK) return rc;
+        ++g_launch, kd_dot_rz<<<d->nblk, 256, 0, L->stream>>>(L->lay.n_pad, d->owned.p, L->r.p, L->z.p, d->partials.p);
+        ++g_launch, kd_reduce<<<1, 256, 0, L->stream>>>(d->nblk, d->partials.p, scal_dev, 1);
+        XB_CUDA(cudaGetLastError());
+        return XFEMM_OK;
+    }
     ++g_launch, kd_update<<<d->nblk, 256, 0, L->stream>>>(L->lay.n_pad, d->owned.p, glob_dev, L->dinv.p, L->p.p, L->u.p, L->x.p, L->r.p, d->partials.p);
     ++g_launch, kd_reduce<<<1, 256, 0, L->stream>>>(d->nblk, d->partials.p, scal_dev, 1);
     XB_CUDA(cudaGetLastError());
@@ -310,6 +383,12 @@ int xfemm_dist_direction(xfemm_dist *d, const double *glob_dev)
 {
     XB_ARG(d && glob_dev, "null pointer");
     xfemm_linprob *L = d->loc;
+    if (d->precond == XFEMM_PRECOND_AMG)
+    {
+        ++g_launch, kd_direction_z<<<d->nblk, 256, 0, L->stream>>>(L->lay.n_pad, d->owned.p, glob_dev, L->z.p, L->p.p, 0);
+        XB_CUDA(cudaGetLastError());
+        return XFEMM_OK;
+    }
     ++g_launch, kd_direction<<<d->nblk, 256, 0, L->stream>>>(L->lay.n_pad, d->owned.p, glob_dev, L->dinv.p, L->r.p, L->p.p);
     XB_CUDA(cudaGetLastError());
     return XFEMM_OK;

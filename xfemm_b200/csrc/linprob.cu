@@ -1160,6 +1160,27 @@ int linprob_load_rhs_internal(xfemm_linprob *p)
     XB_CUDA(cudaGetLastError());
     return XFEMM_OK;
 }
+// z = M^-1 r with the multigrid V-cycle, on the resident vectors of `p` (internal order), asynchronously
+// on p's stream.  The hierarchy must have been prepared (linprob_prepare(p, XFEMM_PRECOND_AMG)).
+int linprob_apply_amg_resident(xfemm_linprob *p)
+{
+    if (!p->amg) { set_error("multigrid hierarchy not prepared"); return XFEMM_ERR_ARG; }
+    PcgArgs a = make_args(p, 0, 0, 0);
+    AmgArgs g;
+    amg_fill_args(p, *p->amg, g);
+    void *kargs[] = {&a, &g};
+    if (p->precond_grid <= 0)
+    {
+        int grid = 0;
+        int rc = coop_grid(p, k_precond_only<XFEMM_PRECOND_AMG>, 512, &grid);
+        if (rc != XFEMM_OK) return rc;
+        p->precond_grid = grid;
+    }
+    a.part = p->partials.p;
+    ++g_launch;
+    XB_CUDA(cudaLaunchCooperativeKernel((void *)k_precond_only<XFEMM_PRECOND_AMG>, dim3(p->precond_grid), dim3(512), kargs, 0, p->stream));
+    return XFEMM_OK;
+}
 int linprob_store_solution_internal(xfemm_linprob *p)
 {
     const int n_pad = p->lay.n_pad;

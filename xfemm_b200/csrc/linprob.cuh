@@ -46,6 +46,7 @@ struct xfemm_linprob
     xb::DevBuf<int4> tiles;        // per-block tiles of the SELL stream for the shared-memory ring (stage.cuh)
     xb::DevBuf<int> tile_ptr;
     int tile_grid = -1;            // grid size the tiles were cut for
+    int precond_grid = 0;          // cached grid of the stand-alone preconditioner kernel
     int max_grid = 0;
 
     // Dirichlet scratch
@@ -70,4 +71,5 @@ int linprob_build_layout(xfemm_linprob *p, int precond);
 int linprob_prepare(xfemm_linprob *p, int precond);
 int linprob_load_rhs_internal(xfemm_linprob *p);
 int linprob_store_solution_internal(xfemm_linprob *p);
+int linprob_apply_amg_resident(xfemm_linprob *p);
 } // namespace xb

@@ -36,7 +36,8 @@ def main(argv=None):
     ap.add_argument("--same-device", action="store_true")
     ap.add_argument("--precision", type=float, default=None)
     ap.add_argument("--repeats", type=int, default=1)
-    ap.add_argument("--check-every", type=int, default=25)
+    ap.add_argument("--check-every", type=int, default=None)
+    ap.add_argument("--precond", default="jacobi", choices=["amg", "jacobi"])
     ap.add_argument("--out", default=None)
     a = ap.parse_args(argv)
 
@@ -70,7 +71,7 @@ def main(argv=None):
         S.renumber()
         S.solve()  # assembly + boundary conditions only
         t_setup = time.perf_counter() - t0
-        D = DistPCG(S)
+        D = DistPCG(S, precond=X.PRECOND_AMG if a.precond == "amg" else X.PRECOND_JACOBI)
         D.refresh()
         prec = a.precision if a.precision is not None else _fem_precision(base + ".fem")
         infos = []
@@ -84,7 +85,7 @@ def main(argv=None):
         halo = [None] * world
         dist.all_gather_object(halo, (D.n_own, D.n_halo, D.n_send))
         if rank == 0:
-            line = {"mode": "row-partitioned pcg", "n_gpus": world, "backend": a.backend, "n": int(D.n),
+            line = {"mode": "row-partitioned pcg", "precond": a.precond, "n_gpus": world, "backend": a.backend, "n": int(D.n),
                     "iterations": infos[-1]["iterations"], "er": infos[-1]["er"], "solve_ms": float(ms.item()),
                     "ms_per_iteration": float(ms.item()) / max(1, infos[-1]["iterations"]),
                     "setup_s": t_setup, "blocks": [{"n_own": h[0], "n_halo": h[1], "n_send": h[2]} for h in halo]}
