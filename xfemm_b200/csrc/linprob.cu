@@ -330,8 +330,7 @@ __global__ void __launch_bounds__(512, 2) k_pcg(PcgArgs a, AmgArgs g)
     {
         const int t0 = a.tile_ptr[blockIdx.x], t1 = a.tile_ptr[blockIdx.x + 1];
         S.ntiles = t1 - t0;
-        for (int k = threadIdx.x; k < S.ntiles; k += blockDim.x) S.tile[k] = a.tiles[t0 + k];
-        __syncthreads();
+        S.tile = a.tiles + t0;
     }
     if (PRECOND == XFEMM_PRECOND_AMG)
     {
@@ -829,7 +828,6 @@ static bool ensure_tiles(xfemm_linprob *p, int grid)
             s = e;
         }
         tptr[b + 1] = (int)tiles.size();
-        if (tptr[b + 1] - tptr[b] > STAGE_MAX_TILES) return false;
     }
     if (tiles.empty()) return false;
     if (p->tiles.upload(tiles.data(), tiles.size(), p->stream) != cudaSuccess) return false;

@@ -24,8 +24,7 @@ namespace xb {
 #endif
 constexpr int STAGE_TILE_ENT = XB_STAGE_TILE_ENT; // entries per tile (2048: 16 KB of values + 8 KB of columns)
 constexpr int STAGE_COUNT = XB_STAGE_COUNT;
-constexpr int STAGE_MAX_TILES = 256; // per block
-constexpr size_t STAGE_SMEM_BYTES = (size_t)STAGE_COUNT * STAGE_TILE_ENT * 12 + STAGE_MAX_TILES * 16 + 128;
+constexpr size_t STAGE_SMEM_BYTES = (size_t)STAGE_COUNT * STAGE_TILE_ENT * 12 + 128;
 static_assert(STAGE_COUNT * (8 + 4 + 4) <= 128, "barriers and counters must fit the tail of the ring");
 
 // per-block view of the ring in dynamic shared memory
@@ -33,7 +32,7 @@ struct StageSmem
 {
     double *val;   // [STAGE_COUNT][STAGE_TILE_ENT]
     int *col;      // [STAGE_COUNT][STAGE_TILE_ENT]
-    int4 *tile;    // [STAGE_MAX_TILES]  {first slice, end slice, first entry, end entry}
+    const int4 *tile; // this block's tiles in global memory: {first slice, end slice, first entry, end entry}
     uint64_t *full; // [STAGE_COUNT]
     int *remaining; // [STAGE_COUNT] slices of the resident tile not yet finished
     int *current;   // [STAGE_COUNT] tile resident (or on its way) in each stage
@@ -45,8 +44,8 @@ __device__ __forceinline__ StageSmem stage_carve(unsigned char *base)
     StageSmem S;
     S.val = (double *)base;
     S.col = (int *)(base + (size_t)STAGE_COUNT * STAGE_TILE_ENT * 8);
-    S.tile = (int4 *)(base + (size_t)STAGE_COUNT * STAGE_TILE_ENT * 12);
-    S.full = (uint64_t *)(base + (size_t)STAGE_COUNT * STAGE_TILE_ENT * 12 + STAGE_MAX_TILES * 16);
+    S.tile = nullptr;
+    S.full = (uint64_t *)(base + (size_t)STAGE_COUNT * STAGE_TILE_ENT * 12);
     S.remaining = (int *)(S.full + STAGE_COUNT);
     S.current = S.remaining + STAGE_COUNT;
     S.ntiles = 0;
