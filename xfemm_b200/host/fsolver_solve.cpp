@@ -683,6 +683,14 @@ int FSolver::staticNewton(CBigLinProb &L)
         PrintMessage("Conjugate Gradient Solver\n");
         xfemm_solve_info info;
         rc = xfemm_linprob_pcg(lin, L.Precision, Iter, precond, maxIterOption, &info);
+        if (rc == XFEMM_ERR_DIVERGED && precond == XFEMM_PRECOND_AMG)
+        {
+            // safety net: the multigrid hierarchy is built from the sparsity pattern alone; should a problem
+            // defeat it, the (slower, always applicable) Jacobi-preconditioned kernel takes over on the GPU
+            PrintMessage("multigrid-preconditioned CG did not converge; retrying with the Jacobi preconditioner\n");
+            rc = xfemm_linprob_pcg(lin, L.Precision, 0 /* cold start: V may hold the failed iterate */, XFEMM_PRECOND_JACOBI,
+                                   maxIterOption, &info);
+        }
         stats.pcg_iters.push_back(info.iterations);
         stats.pcg_ms.push_back(info.solve_ms);
         stats.final_relres = info.relres;

@@ -265,6 +265,8 @@ bool CBigLinProb::PCGSolve(int flag)
     }
     xfemm_solve_info info;
     int rc = xfemm_linprob_pcg(dev, Precision, flag, precond, 0, &info);
+    if (rc == XFEMM_ERR_DIVERGED && precond == XFEMM_PRECOND_AMG) // safety net, see FSolver::staticNewton
+        rc = xfemm_linprob_pcg(dev, Precision, 0, XFEMM_PRECOND_JACOBI, 0, &info);
     lastIterations = info.iterations;
     lastSolveMs = info.solve_ms;
     lastRelRes = info.relres;
