@@ -1,4 +1,8 @@
 cd /root/repo
-timeout 300 python -m pytest tests/test_gpu_linprob.py tests/test_gpu_static.py -m gpu -x -q 2>&1 | tail -2
-free -g | head -2; nproc
-( time timeout 1400 python bench.py --gpus 1 --steps 2 --warmup 3 --no-cpu-baseline --no-variants --mesh-size 0.00057 ) > gpurun_out/bench_20M.log 2> gpurun_out/bench_20M.err; tail -1 gpurun_out/bench_20M.log | cut -c1-3000; tail -5 gpurun_out/bench_20M.err
+timeout 900 python -m pytest tests/test_gpu_static.py tests/test_gpu_sweep.py -m gpu -x -q 2>&1 | tail -3
+XFEMM_TIMING=1 timeout 600 python bench.py --gpus 1 --steps 5 --warmup 3 --no-cpu-baseline --no-variants >gpurun_out/v.log 2>gpurun_out/timing.log; python - <<'PY'
+import json
+d=json.loads(open('/root/repo/gpurun_out/v.log').read().strip().splitlines()[-1])
+print("value", round(d['value']*1e3,2), "e2e", round(d['e2e']['value'],3), "amg pcg ms", round(d['pcg']['ms'],2), "its", d['pcg']['iterations'], "frac", round(d['roofline']['frac'],3))
+PY
+grep -E "total|pattern|newton" gpurun_out/timing.log | head -6

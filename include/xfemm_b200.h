@@ -99,6 +99,10 @@ int xfemm_linprob_multa(xfemm_linprob *p, const double *x, double *y);  /* spars
 int xfemm_linprob_multpc(xfemm_linprob *p, int precond, const double *x, double *y); /* :197   */
 /* timing hooks for bench.py: run `reps` SpMVs / PCG iterations on resident data, device-timed */
 int xfemm_linprob_bench_spmv(xfemm_linprob *p, int reps, double *ms_per_rep);
+/* value-independent part of the set-up of a later xfemm_linprob_pcg with `precond` (solver layout,
+ * multigrid hierarchy): depends on the sparsity pattern only and may run on a host thread while the
+ * assembly / boundary-condition calls work on the same problem */
+int xfemm_linprob_prebuild(xfemm_linprob *p, int precond);
 /* optional locality hint: coordinates (x,y per row) of the unknowns.  The solver's internal row order then
  * follows a Z-curve through the plane instead of the caller's numbering (gathers of a slice hit fewer
  * sectors, multigrid transfers become local).  Results are unaffected.  xy = NULL removes the hint. */

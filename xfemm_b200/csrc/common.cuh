@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstring>
 #include <string>
+#include <atomic>
 #include "../../include/xfemm_b200.h"
 
 namespace xb {
@@ -12,7 +13,7 @@ namespace xb {
 void set_error(const char *fmt, ...);
 
 // bookkeeping for bench.py: bytes crossing PCIe and kernels launched by this library
-extern long long g_h2d_bytes, g_d2h_bytes, g_launch;
+extern std::atomic<long long> g_h2d_bytes, g_d2h_bytes, g_launch; // (a host thread may pre-build the solver structure)
 
 #define XB_CUDA(call)                                                                      \
     do {                                                                                   \

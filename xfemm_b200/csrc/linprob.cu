@@ -29,7 +29,7 @@ void set_error(const char *fmt, ...)
     g_err = buf;
 }
 const char *last_error() { return g_err.c_str(); }
-long long g_h2d_bytes = 0, g_d2h_bytes = 0, g_launch = 0;
+std::atomic<long long> g_h2d_bytes{0}, g_d2h_bytes{0}, g_launch{0};
 thread_local DevArena *g_arena = nullptr;
 
 // ---- caching device allocator (see common.cuh) ---------------------------------------------
@@ -1116,6 +1116,25 @@ int xfemm_linprob_periodic(xfemm_linprob *p, int npairs, const int *ni, const in
     return XFEMM_OK;
 }
 
+// Value-independent part of the solver set-up (SELL layout, stream tiles are cut at launch, multigrid
+// hierarchy): depends on the sparsity pattern only, so a caller may run it on a host thread while the
+// assembly and boundary-condition kernels work on the same problem (they touch rowptr/col/vals/b/V only).
+int xfemm_linprob_prebuild(xfemm_linprob *p, int precond)
+{
+    XB_ARG(p, "null handle");
+    XB_CUDA(cudaSetDevice(p->device)); // a fresh host thread starts on device 0
+    int rc = linprob_build_layout(p, precond);
+    if (rc != XFEMM_OK || precond != XFEMM_PRECOND_AMG) return rc;
+    if (!p->amg)
+    {
+        std::unique_ptr<AmgHierarchy> h;
+        rc = amg_build(p, h);
+        if (rc != XFEMM_OK) return rc;
+        p->amg = h.release();
+    }
+    return XFEMM_OK;
+}
+
 static int prepare_solver(xfemm_linprob *p, int precond, int *singular)
 {
     const bool timing = getenv("XFEMM_TIMING") != nullptr;
@@ -1467,11 +1486,11 @@ int xfemm_linprob_get_exists_mask(xfemm_linprob *p, unsigned char *exists)
 
 void xfemm_transfer_bytes(long long *h2d, long long *d2h, int reset)
 {
-    if (h2d) *h2d = xb::g_h2d_bytes;
-    if (d2h) *d2h = xb::g_d2h_bytes;
+    if (h2d) *h2d = xb::g_h2d_bytes.load();
+    if (d2h) *d2h = xb::g_d2h_bytes.load();
     if (reset) { xb::g_h2d_bytes = 0; xb::g_d2h_bytes = 0; }
 }
-long long xfemm_launch_count(void) { return xb::g_launch; }
+long long xfemm_launch_count(void) { return xb::g_launch.load(); }
 
 void xfemm_free(void *ptr) { free(ptr); }
 

@@ -16,6 +16,7 @@
 #include "cspars.h"
 
 #include <string>
+#include <thread>
 #include <vector>
 
 #ifndef PI
@@ -263,6 +264,8 @@ public:
     std::vector<double> jprevByLabel; // per-label source current accumulated over the solves (added to Jprev on write)
     bool fetchSolution;          // copy V and A back to the host after a solve (default true; sweeps that only need torque switch it off)
     bool gapTorque(int ageIndex, double &torque); // from the resident solution, = fpproc's gap integral 0
+    std::thread prebuild;        // host thread building the solver structure while the first assembly runs
+    void joinPrebuild() { if (prebuild.joinable()) prebuild.join(); }
     int localityOrder;           // 1/0: order the solver's rows along a Z-curve through the nodes; -1 = when the problem is re-solved
     bool assembleOnly;           // stop after assembly + boundary conditions of the first pass
     bool ageUnionPattern;        // couple all ring nodes of an air-gap element structurally (sweeps)

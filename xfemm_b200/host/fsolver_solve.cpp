@@ -42,6 +42,7 @@ static double wall() { return std::chrono::duration<double>(std::chrono::steady_
 
 void FSolver::releaseDevice()
 {
+    joinPrebuild();
     if (magdev) { xfemm_mag_destroy(magdev); magdev = nullptr; }
     if (cmagdev) { xfemm_cmag_destroy(cmagdev); cmagdev = nullptr; }
 }
@@ -492,11 +493,26 @@ int FSolver::staticSolve(CBigLinProb &L, bool axi)
             if ((pp.J.re == 0) && (pp.J.im == 0)) setValue(i, pp.A.re / c);
         }
     }
-    for (int i = 0; i < NumEls; i++)
+    // element table in parallel; the (few) elements with a tagged side are then visited in element order,
+    // which is what fixes the first/last semantics of repeated SetValue calls (static2d.cpp:854-921)
+    std::vector<int> tagged;
+    {
+        std::vector<std::vector<int>> part(64);
+        xb::parallel_for(NumEls, [&](int i0, int i1, int tid) {
+            for (int i = i0; i < i1; i++)
+            {
+                const CMElement &El = meshele[i];
+                int *t4 = &tri[4 * (size_t)i];
+                t4[0] = El.p[0]; t4[1] = El.p[1]; t4[2] = El.p[2]; t4[3] = El.lbl;
+                if (El.e[0] >= 0 || El.e[1] >= 0 || El.e[2] >= 0) part[tid].push_back(i);
+            }
+        });
+        for (auto &v : part) tagged.insert(tagged.end(), v.begin(), v.end());
+        std::sort(tagged.begin(), tagged.end());
+    }
+    for (int i : tagged)
     {
         const CMElement &El = meshele[i];
-        int *t4 = &tri[4 * (size_t)i];
-        t4[0] = El.p[0]; t4[1] = El.p[1]; t4[2] = El.p[2]; t4[3] = El.lbl;
         for (int j = 0; j < 3; j++)
         {
             if (El.e[j] < 0) continue;
@@ -585,6 +601,15 @@ int FSolver::staticSolve(CBigLinProb &L, bool axi)
     // layout costs ~0.08 s of host time at 2 M nodes and saves ~2 ms per solve, so by default it is used
     // when the device problem is going to be solved repeatedly (Newton iteration, rotor sweeps).
     if (localityOrder > 0 || (localityOrder < 0 && (ageUnionPattern || !LinearFlag))) xfemm_linprob_set_coords(lin, xy.data());
+    // The solver structure (SELL layout, multigrid hierarchy) depends on the pattern only: a host thread
+    // builds it while this thread uploads the mesh and runs the first assembly and boundary conditions.
+    if (!assembleOnly && !getenv("XFEMM_NO_PREBUILD"))
+    {
+        joinPrebuild();
+        const int pc = precondOption >= 0 ? precondOption : L.precond;
+        prebuild = std::thread([lin, pc]() { xfemm_linprob_prebuild(lin, pc); });
+    }
+    struct JoinOnExit { FSolver *s; ~JoinOnExit() { s->joinPrebuild(); } } joinOnExit{this}; // never outlive `lin`
     xfemm_mag_desc D;
     memset(&D, 0, sizeof D);
     D.axisymmetric = axi ? 1 : 0;
@@ -680,6 +705,7 @@ int FSolver::staticNewton(CBigLinProb &L)
         }
         if (assembleOnly) { stats.newton_iters = 0; return true; } // the caller solves (row-partitioned PCG)
         xfemm_linprob_save_solution(lin); // V_old = V
+        joinPrebuild(); // the solver structure is needed from here on (a failed pre-build is simply redone by the solve)
         PrintMessage("Conjugate Gradient Solver\n");
         xfemm_solve_info info;
         rc = xfemm_linprob_pcg(lin, L.Precision, Iter, precond, maxIterOption, &info);
