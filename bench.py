@@ -379,13 +379,20 @@ def main():
         sync()
         t1 = time.perf_counter()
         for i in range(args.steps):
-            S.set_rotor_angle(position(args.warmup + i))
+            S.set_rotor_angle(position(args.warmup + args.steps + i))  # the sweep goes on
             S.resolve()
             tq.append(S.gap_torque(0))
         sync()
         torque_only = {"s_per_position": (time.perf_counter() - t1) / args.steps, "torque_Nm": tq,
-                       "positions_deg": [position(args.warmup + i) for i in range(args.steps)]}
+                       "positions_deg": [position(args.warmup + args.steps + i) for i in range(args.steps)]}
         S.set_option("fetch_solution", 1)
+        # the same problem solved from a zero initial guess (what a stand-alone solve of one position costs)
+        S.set_option("warm_resolve", 0)
+        S.resolve()
+        S.resolve()
+        cs = S.stats()
+        torque_only["cold_start"] = {"pcg_ms": sum(cs["solve_ms"]), "iterations": sum(cs["iters"]), "relres": cs["relres"]}
+        S.set_option("warm_resolve", 1)
     # the other GPU-parallel preconditioners on the same resident problem, for the record
     variant = None
     if rank == 0 and world == 1 and not args.no_variants:
@@ -432,7 +439,9 @@ def main():
                    "n_pbc": c["n_pbc"], "precision": 1e-10, "preconditioner": args.precond,
                    "l2_note": "matrix+vectors (%.0f MB) exceed the 126 MB L2" % ((12.0 * nnz + 56.0 * n) / 1e6),
                    "parallelism": f"rotor-angle sweep: {world} independent positions at a time, one per GPU, no collective",
-                   "step": "one rotor position: AGE re-target + assembly + BCs + PCG on the resident mesh"},
+                   "step": "one rotor position of the sweep: AGE re-target + assembly + BCs + PCG on the resident mesh; "
+                           "initial guess = quadratic extrapolation of the three previous positions (same stopping rule; "
+                           "sweep_torque_only.cold_start gives the solve from a zero guess)"},
         "pcg": {"iterations": its, "reference_iterations": total_ref_iters or None, "ms": pcg_ms,
                 "ms_per_iter": pcg_ms / its if its else None, "relres": st["relres"], "multigrid_levels": levels},
         "assembly": {"ms": sum(asm_ms) / len(asm_ms), "elements_per_s": c["n_elems"] / (1e-3 * sum(asm_ms) / len(asm_ms))},

@@ -99,6 +99,13 @@ int xfemm_linprob_multa(xfemm_linprob *p, const double *x, double *y);  /* spars
 int xfemm_linprob_multpc(xfemm_linprob *p, int precond, const double *x, double *y); /* :197   */
 /* timing hooks for bench.py: run `reps` SpMVs / PCG iterations on resident data, device-timed */
 int xfemm_linprob_bench_spmv(xfemm_linprob *p, int reps, double *ms_per_rep);
+/* Solution history for parameter sweeps on one handle (rotor positions): _push records the current solution,
+ * _guess overwrites V with the last recorded solution (extrapolate = 0), the linear (1) or quadratic (2)
+ * extrapolation of the last two / three recorded solutions (equidistant steps assumed) as the initial guess of a
+ * warm-started xfemm_linprob_pcg.  The converged result does not depend on the guess. */
+int xfemm_linprob_history_push(xfemm_linprob *p);
+int xfemm_linprob_history_guess(xfemm_linprob *p, int extrapolate);
+int xfemm_linprob_history_clear(xfemm_linprob *p);
 /* value-independent part of the set-up of a later xfemm_linprob_pcg with `precond` (solver layout,
  * multigrid hierarchy): depends on the sparsity pattern only and may run on a host thread while the
  * assembly / boundary-condition calls work on the same problem */
@@ -354,7 +361,8 @@ int xfemm_fsolver_resolve(xfemm_fsolver *s);
  * "age_union_pattern" = 1 (sparsity pattern independent of the angle).
  * Other options of xfemm_fsolver_set_option: "fetch_solution" = 0 (leave V and A on the device after a
  * solve), "assemble_only" = 1 (stop after assembly + boundary conditions), "locality_order" = 1/0/-1
- * (Z-curve row order inside the solver; -1 = only when the problem is going to be re-solved). */
+ * (Z-curve row order inside the solver; -1 = only when the problem is going to be re-solved),
+ * "warm_resolve" = 0 (xfemm_fsolver_resolve starts from zero instead of the solution left on the device). */
 int xfemm_fsolver_set_rotor_angle(xfemm_fsolver *s, int age_index, double inner_angle_deg, double outer_angle_deg);
 /* torque [N m] through air-gap element `age_index` from the resident magnetostatic solution
  * (= mo_gapintegral(name,0) of the reference's post-processor on the written .ans) */

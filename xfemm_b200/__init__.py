@@ -71,6 +71,9 @@ SIGNATURES = {
     "xfemm_linprob_amg_levels": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_longlong)]),
     "xfemm_linprob_set_coords": (C.c_int, [_P, _P]),
     "xfemm_linprob_prebuild": (C.c_int, [_P, C.c_int]),
+    "xfemm_linprob_history_push": (C.c_int, [_P]),
+    "xfemm_linprob_history_guess": (C.c_int, [_P, C.c_int]),
+    "xfemm_linprob_history_clear": (C.c_int, [_P]),
     "xfemm_linprob_save_solution": (C.c_int, [_P]),
     "xfemm_linprob_newton_norms": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "xfemm_linprob_relax": (C.c_int, [_P, C.c_double]),

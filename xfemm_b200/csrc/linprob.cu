@@ -1462,6 +1462,48 @@ int xfemm_linprob_relax(xfemm_linprob *p, double relax)
     return XFEMM_OK;
 }
 
+// ---- solution history for sweeps: the converged solutions of the last two problems solved on this
+// handle, and an initial guess for the next one by linear extrapolation (equidistant parameter steps)
+__global__ void k_hist_guess(int n, const double *__restrict__ h1, const double *__restrict__ h2,
+                             const double *__restrict__ h3, double *V)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (h3) V[i] = 3.0 * (h1[i] - h2[i]) + h3[i]; // quadratic through the last three
+    else if (h2) V[i] = 2.0 * h1[i] - h2[i];       // linear through the last two
+    else V[i] = h1[i];
+}
+int xfemm_linprob_history_push(xfemm_linprob *p)
+{
+    XB_ARG(p, "null handle");
+    if (p->hist1.n != (size_t)p->n)
+    {
+        XB_CUDA(p->hist1.alloc(p->n)); XB_CUDA(p->hist2.alloc(p->n)); XB_CUDA(p->hist3.alloc(p->n));
+        p->hist_count = 0;
+    }
+    std::swap(p->hist2.p, p->hist3.p); // hist3 <- hist2 <- hist1 <- current
+    std::swap(p->hist1.p, p->hist2.p);
+    XB_CUDA(cudaMemcpyAsync(p->hist1.p, p->V.p, (size_t)p->n * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    if (p->hist_count < 3) p->hist_count++;
+    return XFEMM_OK;
+}
+int xfemm_linprob_history_guess(xfemm_linprob *p, int extrapolate)
+{
+    XB_ARG(p, "null handle");
+    if (p->hist_count <= 0) return XFEMM_OK; // nothing known: V stays as it is
+    const double *h2 = (extrapolate >= 1 && p->hist_count >= 2) ? p->hist2.p : nullptr;
+    const double *h3 = (extrapolate >= 2 && p->hist_count >= 3) ? p->hist3.p : nullptr;
+    ++xb::g_launch, k_hist_guess<<<(p->n + 255) / 256, 256, 0, p->stream>>>(p->n, p->hist1.p, h2, h3, p->V.p);
+    XB_CUDA(cudaGetLastError());
+    return XFEMM_OK;
+}
+int xfemm_linprob_history_clear(xfemm_linprob *p)
+{
+    XB_ARG(p, "null handle");
+    p->hist_count = 0;
+    return XFEMM_OK;
+}
+
 int xfemm_linprob_set_fill_mask(xfemm_linprob *p, const unsigned char *fill)
 {
     XB_ARG(p && fill, "null pointer");

@@ -47,6 +47,8 @@ struct xfemm_linprob
     xb::DevBuf<int> tile_ptr;
     int tile_grid = -1;            // grid size the tiles were cut for
     int precond_grid = 0;          // cached grid of the stand-alone preconditioner kernel
+    xb::DevBuf<double> hist1, hist2, hist3; // solutions of the last three problems solved on this handle (sweeps)
+    int hist_count = 0;
     int max_grid = 0;
 
     // Dirichlet scratch

@@ -131,7 +131,11 @@ int xfemm_fsolver_gap_torque(xfemm_fsolver *s, int age_index, double *torque)
 int xfemm_fsolver_resolve(xfemm_fsolver *s)
 {
     if (!s || !s->L) { xb::set_error("no resident static problem (call xfemm_fsolver_solve first)"); return XFEMM_ERR_ARG; }
-    if (s->S.staticNewton(*s->L) != 1)
+    // the solution of the previous position is still on the device: it is the initial guess of this solve
+    s->S.resolveStart = s->S.warmResolve;
+    const int ok = s->S.staticNewton(*s->L);
+    s->S.resolveStart = false;
+    if (ok != 1)
     {
         std::string prev = xfemm_last_error();
         xb::set_error("solve failed (%s)", prev.c_str());
@@ -290,6 +294,8 @@ int xfemm_fsolver_set_option(xfemm_fsolver *s, const char *key, double value)
     if (!strcmp(key, "max_iter")) { s->S.maxIterOption = (int)value; return XFEMM_OK; }
     if (!strcmp(key, "keep_system")) { s->S.keepSystem = value != 0; return XFEMM_OK; }
     if (!strcmp(key, "locality_order")) { s->S.localityOrder = (int)value; return XFEMM_OK; }
+    if (!strcmp(key, "extrapolate_resolve")) { s->S.extrapolateResolve = value != 0; return XFEMM_OK; }
+    if (!strcmp(key, "warm_resolve")) { s->S.warmResolve = value != 0; return XFEMM_OK; }
     if (!strcmp(key, "fetch_solution")) { s->S.fetchSolution = value != 0; return XFEMM_OK; }
     if (!strcmp(key, "assemble_only")) { s->S.assembleOnly = value != 0; return XFEMM_OK; }
     if (!strcmp(key, "age_union_pattern")) { s->S.ageUnionPattern = value != 0; return XFEMM_OK; }

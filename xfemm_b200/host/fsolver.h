@@ -262,6 +262,9 @@ public:
         bool linear = true, ready = false, ageDirty = false;
     } plan;
     std::vector<double> jprevByLabel; // per-label source current accumulated over the solves (added to Jprev on write)
+    bool warmResolve;            // a re-solve on the resident problem starts from the solution it finds there (default true)
+    bool resolveStart;           // set for the duration of such a re-solve
+    bool extrapolateResolve;     // ... from the linear extrapolation of the last two solutions (equidistant sweeps; default true)
     bool fetchSolution;          // copy V and A back to the host after a solve (default true; sweeps that only need torque switch it off)
     bool gapTorque(int ageIndex, double &torque); // from the resident solution, = fpproc's gap integral 0
     std::thread prebuild;        // host thread building the solver structure while the first assembly runs

@@ -116,6 +116,9 @@ FSolver::FSolver()
     assembleOnly = false;
     localityOrder = -1;
     fetchSolution = true;
+    warmResolve = true;
+    resolveStart = false;
+    extrapolateResolve = true;
 }
 
 FSolver::~FSolver() { releaseDevice(); }

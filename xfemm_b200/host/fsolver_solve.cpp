@@ -669,6 +669,13 @@ int FSolver::staticNewton(CBigLinProb &L)
     const int precond = precondOption >= 0 ? precondOption : L.precond;
     int Iter = 0;
     double res = 0, lastres = 0;
+    // re-solve on the resident problem (next position of a sweep): initial guess from the positions solved
+    // before — the last one, or the linear extrapolation of the last two (equidistant positions)
+    if (resolveStart)
+    {
+        const char *eo = getenv("XFEMM_EXTRAPOLATION_ORDER");
+        xfemm_linprob_history_guess(lin, extrapolateResolve ? (eo ? atoi(eo) : 2) : 0);
+    }
     do
     {
         PrintMessage("Matrix Construction\n");
@@ -708,7 +715,9 @@ int FSolver::staticNewton(CBigLinProb &L)
         joinPrebuild(); // the solver structure is needed from here on (a failed pre-build is simply redone by the solve)
         PrintMessage("Conjugate Gradient Solver\n");
         xfemm_solve_info info;
-        rc = xfemm_linprob_pcg(lin, L.Precision, Iter, precond, maxIterOption, &info);
+        // Newton steps after the first continue from the last iterate (static2d.cpp:929); so does the first
+        // solve of a re-solve on the resident problem (next rotor position: the previous field is close)
+        rc = xfemm_linprob_pcg(lin, L.Precision, (Iter > 0 || resolveStart) ? 1 : 0, precond, maxIterOption, &info);
         if (rc == XFEMM_ERR_DIVERGED && precond == XFEMM_PRECOND_AMG)
         {
             // safety net: the multigrid hierarchy is built from the sparsity pattern alone; should a problem
@@ -754,6 +763,7 @@ int FSolver::staticNewton(CBigLinProb &L)
         Iter++;
     } while (LinearFlag == false);
     stats.newton_iters = Iter;
+    xfemm_linprob_history_push(lin); // remembered as a starting point for the next problem on this handle
 
     // results back to the caller's arrays: L.V internal units, L.b = A (static2d.cpp:1018-1021)
     // (sweeps that only read derived quantities — gapTorque — leave the nodal values on the device)
