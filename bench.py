@@ -77,6 +77,10 @@ def prepare_mesh(workdir, mesh_size, rank=0):
 
 
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons sampled DURING the timed region: NVML every 2 ms (the timed region of
+    the multigrid solver is tens of milliseconds per step), nvidia-smi as a fallback."""
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
+
     def __init__(self, gpu=0):
         super().__init__(daemon=True)
         self.gpu = gpu
@@ -84,11 +88,38 @@ class ClockSampler(threading.Thread):
         self.reasons = set()
         self.stop_flag = False
         self.max_mhz = None
+        self.source = None
 
-    def run(self):
+    def _run_nvml(self):
+        import pynvml as N
+        N.nvmlInit()
+        # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES if it is a plain index list
+        idx = self.gpu
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                idx = int(vis.split(",")[self.gpu])
+            except Exception:
+                pass
+        h = N.nvmlDeviceGetHandleByIndex(idx)
+        self.max_mhz = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+        self.source = "nvml"
+        while not self.stop_flag:
+            self.samples.append(float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)))
+            try:
+                mask = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for nm, bit in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def _run_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        self.source = "nvidia-smi"
         while not self.stop_flag:
             try:
                 r = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
@@ -103,10 +134,16 @@ class ClockSampler(threading.Thread):
                 pass
             time.sleep(0.02)
 
+    def run(self):
+        try:
+            self._run_nvml()
+        except Exception:
+            self._run_smi()
+
     def summary(self):
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(s)}
+                "samples": len(s), "source": self.source}
 
 
 def run_reference(base, ref_iters, ref_pbc, total_ref_iters):
@@ -162,12 +199,13 @@ def pcg_bytes_per_iteration(X, S, precond, nnz, n):
     return krylov + cyc, levels
 
 
-def ncu_traffic(precond):
-    """DRAM bytes (read + write) of one launch of the persistent kernel, from the committed ncu --set full
-    capture of this same command (profiles/r01_ncu_traffic.json); None if there is no capture for it."""
+def ncu_traffic(precond, iterations):
+    """DRAM bytes (read + write) of one launch of the persistent kernel: the per-iteration figure of the committed
+    ncu --set full capture of this command (profiles/r01_ncu_traffic.json: dram bytes of the captured launch /
+    its iteration count) times the iterations of the timed launches; None if there is no capture for it."""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
-        return d[precond]["dram_bytes_per_launch"]
+        d = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))[precond]
+        return d["dram_bytes_per_launch"] / d["iterations"] * iterations
     except Exception:
         return None
 
@@ -236,8 +274,8 @@ def run_partitioned(args, base, workload, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mesh-size", type=float, default=0.0018, help="block-label mesh size in cm (0.0018 → ~2M DOF)")
     ap.add_argument("--precond", default=os.environ.get("XFEMM_PRECOND", "amg"), choices=["jacobi", "mcssor", "amg"])
@@ -402,6 +440,7 @@ def main():
             if other == precond:
                 continue
             S.set_option("precond", other)
+            S.set_option("warm_resolve", 0)  # the comparison is between full solves from a zero guess
             S.resolve()
             S.resolve()
             vs = S.stats()
@@ -410,6 +449,7 @@ def main():
             variant.append({"preconditioner": names[other], "iterations": vit, "pcg_ms": vms, "relres": vs["relres"],
                             "ms_per_iter": vms / max(1, vit), "algorithmic_gbs": vb * vit / (vms * 1e-3) / 1e9 if vms > 0 else None})
         S.set_option("precond", precond)
+        S.set_option("warm_resolve", 1)
     if world > 1:
         t = torch.tensor([elapsed], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -447,7 +487,7 @@ def main():
         "assembly": {"ms": sum(asm_ms) / len(asm_ms), "elements_per_s": c["n_elems"] / (1e-3 * sum(asm_ms) / len(asm_ms))},
         "roofline": {"bound": "hbm", "kernel": "k_pcg<%s> (persistent PCG: SpMV + fused vector updates + preconditioner)" % args.precond,
                      "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": ncu_traffic(args.precond) if args.mesh_size == 0.0018 else None,
+                     "frac": achieved / peak, "traffic": ncu_traffic(args.precond, its) if args.mesh_size == 0.0018 else None,
                      "bytes_per_iter": bytes_iter,
                      "achieved_note": "algorithmic bytes per launch (bytes_per_iter x iterations) / CUDA-event launch duration; "
                                       "traffic = DRAM bytes of one launch from the committed ncu capture (profiles/)"},
