@@ -378,9 +378,10 @@ def main():
         e2e = float(t.item())
 
     # ---- device-resident steps: every step is one rotor position of the 360-position sweep
-    # (rank r takes positions r, r+N, r+2N, … — independent problems, no communication)
+    # (rank r takes the contiguous block of positions r*360/N, r*360/N + 1, … — independent problems, no
+    # communication; consecutive positions per rank keep the extrapolated initial guesses sharp)
     def position(i):
-        return float((rank + i * world) % 360)
+        return float((rank * (360 // world) + i) % 360)
 
     for i in range(args.warmup):
         S.set_rotor_angle(position(i))
@@ -478,7 +479,7 @@ def main():
         "config": {"workload": workload, "n_nodes": c["n_nodes"], "n_elems": c["n_elems"], "nnz_full": nnz,
                    "n_pbc": c["n_pbc"], "precision": 1e-10, "preconditioner": args.precond,
                    "l2_note": "matrix+vectors (%.0f MB) exceed the 126 MB L2" % ((12.0 * nnz + 56.0 * n) / 1e6),
-                   "parallelism": f"rotor-angle sweep: {world} independent positions at a time, one per GPU, no collective",
+                   "parallelism": f"rotor-angle sweep: {world} independent positions at a time, one per GPU (each rank a contiguous block of the 360 positions), no collective",
                    "step": "one rotor position of the sweep: AGE re-target + assembly + BCs + PCG on the resident mesh; "
                            "initial guess = quadratic extrapolation of the three previous positions (same stopping rule; "
                            "sweep_torque_only.cold_start gives the solve from a zero guess)"},

@@ -1,6 +1,7 @@
 cd /root/repo
-( time python bench.py ) > gpurun_out/bench_default.log 2>&1; grep "^real" gpurun_out/bench_default.log; grep "^{" gpurun_out/bench_default.log | python -c "
-import sys,json
-d=json.loads(sys.stdin.read()); print({k:d[k] for k in ('value','steps','warmup','e2e','gpu_launches','clocks')}); print(d['pcg']['ms'], d['pcg']['iterations']); print(d['roofline']['frac'], d['roofline']['traffic']); print(d['variant']); print(d['sweep_torque_only']['s_per_position'], d['sweep_torque_only']['cold_start'])"
-bash gpurun_prof.sh amg > /dev/null 2>&1
-ls -la gpurun_out/prof_amg.ncu-rep
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python bench.py --no-cpu-baseline > gpurun_out/v.log 2>/dev/null; python - <<'PY'
+import json
+d=json.loads(open('/root/repo/gpurun_out/v.log').read().strip().splitlines()[-1])
+print("value", round(d['value']*1e3,2), "e2e", round(d['e2e']['value'],3), "pcg ms", round(d['pcg']['ms'],2), "its", d['pcg']['iterations'], "frac", round(d['roofline']['frac'],3), [(v['preconditioner'], round(v['pcg_ms'],1), v['iterations'], round(v['algorithmic_gbs'])) for v in d['variant']], d['sweep_torque_only']['s_per_position'], d['sweep_torque_only']['cold_start'])
+PY

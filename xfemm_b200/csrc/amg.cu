@@ -366,12 +366,16 @@ void amg_print_trace(AmgHierarchy &h, cudaStream_t st)
     for (size_t l = 0; l < h.level_n.size(); l++) fprintf(stderr, " %d/%d", h.level_n[l], h.level_nnz[l]);
     fprintf(stderr, "\n[amg trace] phase us:");
     double total = 0;
-    for (int k = 1; k < AMG_MAX_STAMPS && t[k] > t[k - 1]; k++)
+    for (int k = 1; k < AMG_MAX_STAMPS - 8 && t[k] > t[k - 1]; k++)
     {
         fprintf(stderr, " %.1f", (t[k] - t[k - 1]) * 1e-3);
         total += (t[k] - t[k - 1]) * 1e-3;
     }
     fprintf(stderr, "  (cycle %.1f us)\n", total);
+    const unsigned long long *c = t.data() + AMG_MAX_STAMPS - 8; // CG part of the last iteration
+    if (c[4] > c[0])
+        fprintf(stderr, "[amg trace] cg part us: spmv+dot %.1f, residual update %.1f, (v-cycle %.1f), direction+solution update %.1f\n",
+                (c[1] - c[0]) * 1e-3, (c[2] - c[1]) * 1e-3, (c[3] - c[2]) * 1e-3, (c[4] - c[3]) * 1e-3);
 }
 
 static void fill_level(AmgLev &L, xfemm_linprob *p)

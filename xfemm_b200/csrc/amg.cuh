@@ -52,9 +52,9 @@ struct AmgArgs
 };
 
 constexpr int AMG_MAX_STAMPS = 8 * AMG_MAX_LEVELS;
-__device__ __forceinline__ void amg_stamp(const AmgArgs &g, int &k)
+__device__ __forceinline__ void amg_stamp(const AmgArgs &g, int &k, int limit = AMG_MAX_STAMPS - 8)
 {
-    if (g.stamps && blockIdx.x == 0 && threadIdx.x == 0 && k < AMG_MAX_STAMPS)
+    if (g.stamps && blockIdx.x == 0 && threadIdx.x == 0 && k < limit)
     {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -106,18 +106,26 @@ __device__ __forceinline__ double amg_sell_row(const AmgLev &L, int s, int lane,
 // y-phase over the block's slices of level L: calls epi(row, (A x)[row]) for every own row
 template <class Epi>
 __device__ __forceinline__ void amg_spmv_phase(const AmgLev &L, int s0, int s1, int wk0, int wk1, const double *x,
-                                               double *wide_tmp, int *s_next, Epi epi, StageSmem *S = nullptr)
+                                               double *wide_tmp, int *s_next, Epi epi, StageSmem *S = nullptr,
+                                               const double *pf0 = nullptr, const double *pf1 = nullptr)
 {
     const int lane = threadIdx.x & 31;
     wide_rows_block<double>(L.wide, L.wide_val, L.wide_acc, wk0, wk1, x, wide_tmp);
     if (S && S->ntiles > 0)
     {
         // finest level: the matrix stream comes through the shared-memory ring (stage.cuh)
-        staged_slices(*S, L.slice_ptr, L.sell_val, L.sell_col, s0, s1, x, s_next, [&](int s, int row, double acc) {
-            if (wk1 > wk0 && ((L.wide.mask[s] >> lane) & 1u)) acc += wide_tmp[row];
-            acc = fma(L.diag[row], x[row], acc);
-            epi(row, acc);
-        });
+        // pf0/pf1: row-indexed arrays the caller's epilogue reads (prefetched while the warp waits for its tile)
+        staged_slices(*S, L.slice_ptr, L.sell_val, L.sell_col, s0, s1, x, s_next,
+                      [&](int row) {
+                          if (pf0) prefetch_l1(pf0 + row);
+                          if (pf1) prefetch_l1(pf1 + row);
+                          return make_double2(L.diag[row], x[row]);
+                      },
+                      [&](int s, int row, double acc, double2 dx) {
+                          if (wk1 > wk0 && ((L.wide.mask[s] >> lane) & 1u)) acc += wide_tmp[row];
+                          acc = fma(dx.x, dx.y, acc);
+                          epi(row, acc);
+                      });
         return;
     }
     if (threadIdx.x == 0) *s_next = s0;
@@ -249,7 +257,7 @@ __device__ __forceinline__ double amg_vcycle(const AmgArgs &g, cooperative_group
         const int s0 = (int)((long long)L.nslices * B / G), s1 = (int)((long long)L.nslices * (B + 1) / G);
         // t = b - A x   (t doubles as the scratch the wide rows leave their partial sums in)
         amg_spmv_phase(L, s0, s1, s_wk[2 * l], s_wk[2 * l + 1], L.x, L.t, s_next,
-                       [&](int row, double ax) { L.t[row] = L.b[row] - ax; }, l == 0 ? S0 : nullptr);
+                       [&](int row, double ax) { L.t[row] = L.b[row] - ax; }, l == 0 ? S0 : nullptr, L.b);
         grid.sync();
         amg_stamp(g, sk);
         // coarse right-hand side = sum over the aggregate ; coarse pre-smooth fused
@@ -295,7 +303,7 @@ __device__ __forceinline__ double amg_vcycle(const AmgArgs &g, cooperative_group
                 const double br = L.b[row], z = fma(w * L.dinv[row], br - ax, L.x[row]);
                 L.t[row] = z;
                 dot = fma(br, z, dot);
-            }, S0);
+            }, S0, L.b, L.dinv);
         }
     }
     amg_stamp(g, sk);

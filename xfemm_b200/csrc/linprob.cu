@@ -393,18 +393,21 @@ __global__ void __launch_bounds__(512, 2) k_pcg(PcgArgs a, AmgArgs g)
     while (true)
     {
         // step i: u = A p ; pAp   (warps of a block pull slices of the block's chunk dynamically)
+        int ck = AMG_MAX_STAMPS - 8; // XFEMM_AMG_TRACE: the phases of the CG part go to the tail of the stamp buffer
+        if (PRECOND == XFEMM_PRECOND_AMG) amg_stamp(g, ck, AMG_MAX_STAMPS);
         part = 0.0;
         wide_rows_block<double>(a.wide, a.wide_val, a.wide_acc, wk0, wk1, a.p, a.u);
         if (S.ntiles > 0)
         {
             // matrix stream through the shared-memory ring (stage.cuh)
-            staged_slices(S, a.slice_ptr, a.sell_val, a.sell_col, s0, s1, a.p, &s_next, [&](int s, int row, double acc) {
-                if (wk1 > wk0 && ((a.wide.mask[s] >> lane) & 1u)) acc += a.u[row];
-                const double pr = a.p[row];
-                acc = fma(a.diag[row], pr, acc);
-                a.u[row] = acc;
-                part = fma(pr, acc, part);
-            });
+            staged_slices(S, a.slice_ptr, a.sell_val, a.sell_col, s0, s1, a.p, &s_next,
+                          [&](int row) { return make_double2(a.diag[row], a.p[row]); },
+                          [&](int s, int row, double acc, double2 dp) {
+                              if (wk1 > wk0 && ((a.wide.mask[s] >> lane) & 1u)) acc += a.u[row];
+                              acc = fma(dp.x, dp.y, acc);
+                              a.u[row] = acc;
+                              part = fma(dp.y, acc, part);
+                          });
         }
         else
         {
@@ -424,6 +427,7 @@ __global__ void __launch_bounds__(512, 2) k_pcg(PcgArgs a, AmgArgs g)
         part = block_sum(part, sm);
         if (threadIdx.x == 0) partA[blockIdx.x] = part;
         grid.sync();
+        if (PRECOND == XFEMM_PRECOND_AMG) amg_stamp(g, ck, AMG_MAX_STAMPS);
         const double pAp = reduce_partials(partA, G, sm);
         if (!(pAp > 0.0)) { status = XFEMM_ERR_DIVERGED; break; }
         const double del = res / pAp;
@@ -450,12 +454,14 @@ __global__ void __launch_bounds__(512, 2) k_pcg(PcgArgs a, AmgArgs g)
                 if (PRECOND == XFEMM_PRECOND_AMG) g.lev[0].x[i] = g.omega * a.dinv[i] * ri;
             }
             grid.sync();
+            if (PRECOND == XFEMM_PRECOND_AMG) amg_stamp(g, ck, AMG_MAX_STAMPS);
             // step iv: z = M^-1 r ; z.r
             part = precond_apply<PRECOND>(a, g, grid, r0, r1, warp_g, nwarps_g, lane, &s_next, s_wk, &S, true);
         }
         part = block_sum(part, sm);
         if (threadIdx.x == 0) partB[blockIdx.x] = part;
         grid.sync();
+        if (PRECOND == XFEMM_PRECOND_AMG) amg_stamp(g, ck, AMG_MAX_STAMPS);
         const double res_new = reduce_partials(partB, G, sm);
         const double rho = res_new / res;
         res = res_new;
@@ -467,6 +473,7 @@ __global__ void __launch_bounds__(512, 2) k_pcg(PcgArgs a, AmgArgs g)
             double zi = (PRECOND == XFEMM_PRECOND_JACOBI) ? a.r[i] * a.dinv[i] : a.z[i];
             a.p[i] = fma(rho, pi, zi);
         }
+        if (PRECOND == XFEMM_PRECOND_AMG) amg_stamp(g, ck, AMG_MAX_STAMPS);
         it++;
         er = sqrt(res / res_o);
         if (!(er == er)) { status = XFEMM_ERR_DIVERGED; break; }

@@ -111,11 +111,19 @@ __device__ __forceinline__ void stage_issue(const StageSmem &S, int k, const dou
     bulk_g2s(S.col + (size_t)st * STAGE_TILE_ENT, sell_col + t.z, ent * 4u, &S.full[st]);
 }
 
+__device__ __forceinline__ void prefetch_l1(const void *p)
+{
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
 // Whole block.  For every slice of [s0,s1) (tiles S.tile[0..ntiles)): acc = sum_k val*x[col] over the
-// slice's SELL entries, then epi(slice, row, acc).  `s_next` is the block's ticket counter.
-template <class Epi>
+// slice's SELL entries, then epi(slice, row, acc, pre(row)).  pre(row) runs as soon as the warp has its
+// ticket — before it waits for the tile — so the row-indexed loads of the epilogue (diagonal, x[row], right-hand
+// side) are in flight during the wait and the gathers.  `s_next` is the block's ticket counter.
+template <class Pre, class Epi>
 __device__ __forceinline__ void staged_slices(StageSmem &S, const int *__restrict__ slice_ptr, const double *sell_val,
-                                              const int *sell_col, int s0, int s1, const double *x, int *s_next, Epi epi)
+                                              const int *sell_col, int s0, int s1, const double *x, int *s_next, Pre pre,
+                                              Epi epi)
 {
     const int lane = threadIdx.x & 31;
     if (threadIdx.x == 0)
@@ -135,6 +143,7 @@ __device__ __forceinline__ void staged_slices(StageSmem &S, const int *__restric
         s = __shfl_sync(0xffffffffu, s, 0);
         if (s >= s1) break;
         const int base = slice_ptr[s], w = (slice_ptr[s + 1] - base) >> 5; // in flight while we wait for the tile
+        const auto pv = pre(s * 32 + lane);
         while (s >= S.tile[k].y) k++;
         const int st = k % STAGE_COUNT;
         // tickets can run several ring cycles ahead of the copies: first make sure the stage holds
@@ -147,7 +156,7 @@ __device__ __forceinline__ void staged_slices(StageSmem &S, const int *__restric
         double acc = 0.0;
 #pragma unroll 8
         for (int q = 0; q < w; q++) acc = fma(v[q * 32], x[c[q * 32]], acc);
-        epi(s, s * 32 + lane, acc);
+        epi(s, s * 32 + lane, acc, pv);
         __syncwarp();
         if (lane == 0)
         {
