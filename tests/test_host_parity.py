@@ -150,3 +150,19 @@ def test_edge_cases_of_the_host_primitives():
         X.renumber_cuthill(3, np.array([[0, 5]], dtype=np.int32))
     with pytest.raises(X.XfemmError):
         X.pattern_build(3, np.array([[0, 1, 2]], dtype=np.int32), pbc=np.array([[0, 9]], dtype=np.int32))
+
+
+@pytest.mark.parametrize("threads", ["1", "4"])
+def test_layout_and_multigrid_setup_invariants(threads, tmp_path):
+    """SELL layout with wide rows (plain, Z-curve, coloured), aggregation and Galerkin maps: tests/layout_check.cpp
+    verifies on the CPU that every matrix entry is stored exactly once, the permutations are consistent and
+    the coarse patterns / slot lists equal a brute-force P^T A P."""
+    import subprocess
+    exe = str(tmp_path / "layout_check")
+    libdir = os.path.join(ROOT, "xfemm_b200")
+    r = subprocess.run(["g++", "-O1", "-std=c++17", os.path.join(ROOT, "tests", "layout_check.cpp"), "-o", exe, "-L" + libdir,
+                        "-lxfemm_b200", "-Wl,-rpath," + libdir, "-lpthread"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for n in ("60", "33"):
+        r = subprocess.run([exe, n], capture_output=True, text=True, env=dict(os.environ, XFEMM_HOST_THREADS=threads))
+        assert r.returncode == 0 and r.stdout.strip() == "ok", r.stdout + r.stderr
