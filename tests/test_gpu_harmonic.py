@@ -67,3 +67,24 @@ def test_harmonic_nonlinear_circuits(name, tmp_path):
     assert np.allclose(A[n_nodes:], ref["A"][n_nodes:], rtol=1e-4, atol=1e-12)
     mu = S.mu()
     assert np.abs(mu - ref["mu"]).max() <= 1e-3 * np.abs(ref["mu"]).max()
+
+
+def test_real_part_multigrid_preconditioner_on_a_problem_without_eddy_currents(tmp_path):
+    """Opt-in XFEMM_PRECOND_AMG for the complex solver: the V-cycle of the real part of the matrix, applied to the real
+    and the imaginary part of the residual.  Same answer, an order of magnitude fewer COCG iterations on tbh."""
+    ref, meta = load_ref("tbh")
+    its = {}
+    for pc in (X.PRECOND_JACOBI, X.PRECOND_AMG):
+        d = tmp_path / str(pc)
+        d.mkdir()
+        S = X.FSolver(stage_case("tbh", str(d)))
+        S.set_option("precond", pc)
+        S.load_mesh(False)
+        S.renumber(False)
+        S.solve()
+        V, A = S.solution()
+        assert rel_l2(A, ref["A"]) <= 1e-6
+        its[pc] = sum(S.stats()["iters"])
+        S.close()
+    print("COCG iterations: jacobi", its[X.PRECOND_JACOBI], "real-part multigrid", its[X.PRECOND_AMG])
+    assert its[X.PRECOND_AMG] * 4 < its[X.PRECOND_JACOBI]

@@ -6,6 +6,7 @@
 // ||r||_2/||b||_2 <= Precision) as one persistent cooperative kernel, seeded like the reference by
 // three CG steps on the normal equations of the preconditioned system (PCGSQStart, cspars.cpp:764-819).
 #include "clinprob.cuh"
+#include "amg.cuh"
 #include <complex>
 #include <cooperative_groups.h>
 #include <algorithm>
@@ -123,6 +124,37 @@ __global__ void kc_reduce2_final(int nblk, const double *part, double *out2)
     if (threadIdx.x == 0) { out2[0] = a; out2[1] = c; }
 }
 
+// values of the real companion problem of XFEMM_PRECOND_AMG: Re(a_ij) between mesh nodes; the appended circuit
+// unknowns (rows/columns >= n_nodes) are decoupled (identity rows: the kernel treats them with a Jacobi step);
+// a diagonal without a positive real part falls back to its modulus
+// (the time-harmonic formulations assemble -K - j*omega*sigma*M: `sgn` = -1 turns the real part positive definite)
+__global__ void kc_diag_sign(int n_nodes, const int *__restrict__ rowptr, const int *__restrict__ col,
+                             const cd *__restrict__ vals, int *counts /* [0]=positive [1]=negative real diagonals */)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    for (int s = rowptr[i]; s < rowptr[i + 1]; s++)
+        if (col[s] == i) { if (vals[s].x > 0) atomicAdd(counts, 1); else if (vals[s].x < 0) atomicAdd(counts + 1, 1); }
+}
+__global__ void kc_fill_real(int n, int n_nodes, const int *__restrict__ rowptr, const int *__restrict__ col,
+                             const cd *__restrict__ vals, double *__restrict__ out, double sgn)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int s = rowptr[i]; s < rowptr[i + 1]; s++)
+    {
+        const int j = col[s];
+        double v;
+        if (i >= n_nodes || j >= n_nodes) v = (i == j) ? 1.0 : 0.0;
+        else
+        {
+            v = sgn * vals[s].x;
+            if (i == j && !(v > 0.0)) { v = sqrt(vals[s].x * vals[s].x + vals[s].y * vals[s].y); if (v == 0.0) v = 1.0; }
+        }
+        out[s] = v;
+    }
+}
+
 __device__ __forceinline__ cd csell_row(const cd *__restrict__ val, const int *__restrict__ col, int base, int k0, int k1,
                                         int lane, const cd *x)
 {
@@ -168,6 +200,12 @@ struct CocgArgs
     WideView wide;
     const cd *wide_val;
     cd *wide_acc;
+    // XFEMM_PRECOND_AMG: rows of the appended circuit unknowns (caller index >= n_nodes) keep the Jacobi step
+    const int *i2c;
+    int n_nodes;
+    double prec_sign; // sign that makes the real part of the matrix positive definite
+    const int4 *tiles;   // stream tiles of the real companion's finest level (stage.cuh), or null
+    const int *tile_ptr;
 };
 
 __device__ __forceinline__ int cnext_slice(int *ctr, int lane)
@@ -179,10 +217,41 @@ __device__ __forceinline__ int cnext_slice(int *ctr, int lane)
 
 // z = M^-1 r ; returns this thread's partial of the unconjugated z.r
 template <int PRECOND>
-__device__ __forceinline__ cd cprecond_apply(const CocgArgs &a, cg::grid_group &grid, int r0, int r1, int warp_g,
-                                             int nwarps_g, int lane)
+__device__ __forceinline__ cd cprecond_apply(const CocgArgs &a, const AmgArgs &g, cg::grid_group &grid, int r0, int r1,
+                                             int warp_g, int nwarps_g, int lane, int *s_next, const int *s_wk, StageSmem *S)
 {
     cd dot = make_double2(0., 0.);
+    if (PRECOND == XFEMM_PRECOND_AMG)
+    {
+        // Multigrid V-cycle of the REAL part of the matrix (stiffness: symmetric positive definite), applied to
+        // the real and the imaginary part of r in turn.  A real symmetric M keeps the preconditioned operator
+        // complex symmetric, which is all COCG needs; the eddy-current term j*omega*sigma*mass is a bounded
+        // perturbation of the stiffness that the Krylov iteration absorbs.
+        const AmgLev &L0 = g.lev[0];
+        for (int comp = 0; comp < 2; comp++)
+        {
+            for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x)
+            {
+                const double bi = comp ? a.r[i].y : a.r[i].x;
+                L0.b[i] = bi;
+                L0.x[i] = g.omega * L0.dinv[i] * bi;
+            }
+            grid.sync();
+            amg_vcycle(g, grid, s_next, s_wk, S, true);
+            for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x)
+            {
+                if (comp) a.z[i].y = a.prec_sign * L0.t[i];
+                else a.z[i].x = a.prec_sign * L0.t[i];
+            }
+            grid.sync(); // the level buffers are reused by the next component / the caller reads z
+        }
+        for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x)
+        {
+            if (a.i2c[i] >= a.n_nodes) a.z[i] = cmul(a.r[i], a.dinv[i]); // circuit unknowns: Jacobi
+            dot = cfma(a.z[i], a.r[i], dot);
+        }
+        return dot;
+    }
     if (PRECOND == XFEMM_PRECOND_JACOBI)
     {
         for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x)
@@ -238,11 +307,14 @@ __device__ __forceinline__ cd cprecond_apply(const CocgArgs &a, cg::grid_group &
 }
 
 template <int PRECOND>
-__global__ void __launch_bounds__(512, 1) k_cocg(CocgArgs a)
+__global__ void __launch_bounds__(512, 1) k_cocg(CocgArgs a, AmgArgs g)
 {
     cg::grid_group grid = cg::this_grid();
     __shared__ double sm[33];
     __shared__ int s_next;
+    __shared__ int s_wk[2 * AMG_MAX_LEVELS];
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    StageSmem S = stage_carve(dyn_smem); // ring for the matrix stream of the real companion's finest level
     const int lane = threadIdx.x & 31;
     const int nwarps_b = blockDim.x >> 5, warp_b = threadIdx.x >> 5;
     const int warp_g = blockIdx.x * nwarps_b + warp_b, nwarps_g = gridDim.x * nwarps_b;
@@ -253,6 +325,23 @@ __global__ void __launch_bounds__(512, 1) k_cocg(CocgArgs a)
     double *partA = a.part, *partB = a.part + 2 * G, *partC = a.part + 4 * G;
     int wk0 = 0, wk1 = 0; // wide rows (circuit rows, air-gap rings) of this block's chunk
     if (a.wide.n_rows) wide_range(a.wide, r0, r1, wk0, wk1);
+    if (PRECOND == XFEMM_PRECOND_AMG)
+    {
+        if (a.tiles)
+        {
+            S.ntiles = a.tile_ptr[blockIdx.x + 1] - a.tile_ptr[blockIdx.x];
+            S.tile = a.tiles + a.tile_ptr[blockIdx.x];
+        }
+        if (threadIdx.x < g.nlev)
+        {
+            const AmgLev &L = g.lev[threadIdx.x];
+            int k0 = 0, k1 = 0;
+            if (L.wide.n_rows)
+                wide_range(L.wide, (int)((long long)L.nslices * blockIdx.x / G) * 32, (int)((long long)L.nslices * (blockIdx.x + 1) / G) * 32, k0, k1);
+            s_wk[2 * threadIdx.x] = k0; s_wk[2 * threadIdx.x + 1] = k1;
+        }
+        __syncthreads();
+    }
 
     // ||b||^2 ; r = b ; x = 0 unless warm
     double pn = 0.0;
@@ -288,7 +377,7 @@ __global__ void __launch_bounds__(512, 1) k_cocg(CocgArgs a)
         }
         grid.sync();
     }
-    cd part = cprecond_apply<PRECOND>(a, grid, r0, r1, warp_g, nwarps_g, lane);
+    cd part = cprecond_apply<PRECOND>(a, g, grid, r0, r1, warp_g, nwarps_g, lane, &s_next, s_wk, &S);
     part = block_sum_c(part, sm);
     if (threadIdx.x == 0) { partB[blockIdx.x] = part.x; partB[G + blockIdx.x] = part.y; }
     grid.sync();
@@ -333,7 +422,7 @@ __global__ void __launch_bounds__(512, 1) k_cocg(CocgArgs a)
         pn = block_sum(pn, sm);
         if (threadIdx.x == 0) partC[blockIdx.x] = pn;
         if (PRECOND != XFEMM_PRECOND_JACOBI) grid.sync();
-        part = cprecond_apply<PRECOND>(a, grid, r0, r1, warp_g, nwarps_g, lane);
+        part = cprecond_apply<PRECOND>(a, g, grid, r0, r1, warp_g, nwarps_g, lane, &s_next, s_wk, &S);
         part = block_sum_c(part, sm);
         if (threadIdx.x == 0) { partB[blockIdx.x] = part.x; partB[G + blockIdx.x] = part.y; }
         grid.sync();
@@ -550,6 +639,7 @@ static CocgArgs cmake_args(xfemm_clinprob *p, double precision, int warm, int ma
     a.max_iter = max_iter; a.warm = warm;
     a.mail = p->d_mail.p;
     a.wide = p->wide.view(); a.wide_val = p->wide.val.p; a.wide_acc = p->wide.acc.p;
+    a.i2c = p->i2c.p; a.n_nodes = p->n_nodes; a.tiles = nullptr; a.tile_ptr = nullptr; a.prec_sign = 1.0;
     return a;
 }
 
@@ -622,7 +712,9 @@ int xfemm_clinprob_create(int n, int n_nodes, const int *rowptr, const int *coli
 int xfemm_clinprob_destroy(xfemm_clinprob *p)
 {
     if (!p) return XFEMM_OK;
-    if (p->stream) { cudaStreamSynchronize(p->stream); cudaStreamDestroy(p->stream); }
+    if (p->stream) cudaStreamSynchronize(p->stream);
+    if (p->re_prec) { xfemm_linprob_destroy(p->re_prec); p->re_prec = nullptr; }
+    if (p->stream) cudaStreamDestroy(p->stream);
     delete p;
     return XFEMM_OK;
 }
@@ -733,13 +825,43 @@ int xfemm_clinprob_get_exists_mask(xfemm_clinprob *p, unsigned char *exists)
 int xfemm_clinprob_cocg(xfemm_clinprob *p, double precision, int warm, int precond, int max_iter, xfemm_solve_info *info)
 {
     XB_ARG(p, "null handle");
-    XB_ARG(precond == XFEMM_PRECOND_JACOBI || precond == XFEMM_PRECOND_MCSSOR, "unknown preconditioner");
+    XB_ARG(precond == XFEMM_PRECOND_JACOBI || precond == XFEMM_PRECOND_MCSSOR || precond == XFEMM_PRECOND_AMG, "unknown preconditioner");
     cudaStream_t st = p->stream;
     cudaEvent_t e0, e1, e2;
     XB_CUDA(cudaEventCreate(&e0)); XB_CUDA(cudaEventCreate(&e1)); XB_CUDA(cudaEventCreate(&e2));
     XB_CUDA(cudaEventRecord(e0, st));
-    int rc = cbuild_layout(p, precond);
+    int rc = cbuild_layout(p, precond == XFEMM_PRECOND_AMG ? XFEMM_PRECOND_JACOBI : precond); // AMG: the uncoloured layout
     if (rc != XFEMM_OK) return rc;
+    AmgArgs g;
+    double prec_sign = 1.0;
+    if (precond == XFEMM_PRECOND_AMG)
+    {
+        // real companion problem on the same pattern: values Re(A), multigrid hierarchy built once per pattern
+        if (!p->re_prec)
+        {
+            rc = xfemm_linprob_create(p->n, p->h_rowptr.data(), p->h_col.data(), &p->re_prec);
+            if (rc != XFEMM_OK) return rc;
+        }
+        xfemm_linprob *R = p->re_prec;
+        int *d_cnt = (int *)(p->d_mail.p + 12);
+        int h_cnt[2] = {0, 0};
+        XB_CUDA(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(int), st));
+        ++g_launch, kc_diag_sign<<<(p->n_nodes + 255) / 256, 256, 0, st>>>(p->n_nodes, p->rowptr.p, p->col.p, p->vals.p, d_cnt);
+        XB_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        XB_CUDA(cudaStreamSynchronize(st));
+        prec_sign = h_cnt[1] > h_cnt[0] ? -1.0 : 1.0;
+        ++g_launch, kc_fill_real<<<(p->n + 255) / 256, 256, 0, st>>>(p->n, p->n_nodes, p->rowptr.p, p->col.p, p->vals.p, R->vals.p, prec_sign);
+        XB_CUDA(cudaStreamSynchronize(st)); // the companion works on its own stream
+        rc = linprob_prepare(R, XFEMM_PRECOND_AMG);
+        if (rc != XFEMM_OK) return rc;
+        XB_CUDA(cudaStreamSynchronize(R->stream));
+        if (R->lay.n_pad != p->lay.n_pad || R->lay.i2c != p->lay.i2c)
+        {
+            set_error("internal row orders of the complex problem and its real companion differ");
+            return XFEMM_ERR_ARG;
+        }
+        amg_fill_args(R, *R->amg, g);
+    }
     int singular = -1;
     rc = crefresh_values(p, &singular);
     if (rc != XFEMM_OK) return rc;
@@ -807,17 +929,27 @@ int xfemm_clinprob_cocg(xfemm_clinprob *p, double precision, int warm, int preco
     }
     if (max_iter <= 0) max_iter = cenv_int("XFEMM_MAX_ITER", 200000);
     CocgArgs a = cmake_args(p, precision, warm ? 1 : 0, max_iter);
-    void *kargs[] = {&a};
+    a.prec_sign = prec_sign;
+    void *kargs[] = {&a, &g};
     int per_sm = 0, grid = 0;
-    void *kern = precond == XFEMM_PRECOND_JACOBI ? (void *)k_cocg<XFEMM_PRECOND_JACOBI> : (void *)k_cocg<XFEMM_PRECOND_MCSSOR>;
-    XB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (void (*)(CocgArgs))kern, 512, 0));
+    void *kern = precond == XFEMM_PRECOND_JACOBI ? (void *)k_cocg<XFEMM_PRECOND_JACOBI>
+                 : precond == XFEMM_PRECOND_AMG  ? (void *)k_cocg<XFEMM_PRECOND_AMG>
+                                                 : (void *)k_cocg<XFEMM_PRECOND_MCSSOR>;
+    const size_t dyn_smem = precond == XFEMM_PRECOND_AMG ? STAGE_SMEM_BYTES : 0;
+    if (dyn_smem) XB_CUDA(cudaFuncSetAttribute((void (*)(CocgArgs, AmgArgs))kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+    XB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (void (*)(CocgArgs, AmgArgs))kern, 512, dyn_smem));
     if (per_sm < 1) { set_error("cooperative kernel does not fit on an SM"); return XFEMM_ERR_CUDA; }
     per_sm = std::min(per_sm, cenv_int("XFEMM_PCG_BLOCKS_PER_SM", 2));
     grid = std::max(1, std::min(p->num_sms * per_sm, (p->lay.nslices + 15) / 16));
     if (p->max_grid < grid) { XB_CUDA(p->partials.alloc((size_t)8 * grid)); p->max_grid = grid; }
     a.part = p->partials.p;
+    if (precond == XFEMM_PRECOND_AMG && linprob_ensure_tiles(p->re_prec, grid))
+    {
+        XB_CUDA(cudaStreamSynchronize(p->re_prec->stream));
+        a.tiles = p->re_prec->tiles.p; a.tile_ptr = p->re_prec->tile_ptr.p;
+    }
     ++g_launch;
-    XB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(512), kargs, 0, st));
+    XB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(512), kargs, dyn_smem, st));
     XB_CUDA(cudaEventRecord(e2, st));
     XB_CUDA(cudaMemcpyAsync(p->h_mail, p->d_mail.p, 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
     XB_CUDA(cudaStreamSynchronize(st));

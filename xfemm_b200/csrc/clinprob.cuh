@@ -7,6 +7,7 @@
 #include <cstdint>
 
 typedef double2 cd;
+struct xfemm_linprob;
 
 struct xfemm_clinprob
 {
@@ -23,6 +24,7 @@ struct xfemm_clinprob
     xb::DevBuf<cd> sell_val, diag, dinv, x, r, p, u, z, w, bint;
     xb::DevBuf<double> partials, d_mail;
     xb::WideDev<cd> wide;
+    xfemm_linprob *re_prec = nullptr; // real companion problem (Re A) carrying the multigrid hierarchy of XFEMM_PRECOND_AMG, owned
     int max_grid = 0;
     double h_mail[16];
     xb::DevBuf<int> dir_idx, dir_nodes;

@@ -1205,6 +1205,8 @@ int linprob_apply_amg_resident(xfemm_linprob *p)
     XB_CUDA(cudaLaunchCooperativeKernel((void *)k_precond_only<XFEMM_PRECOND_AMG>, dim3(p->precond_grid), dim3(512), kargs, 0, p->stream));
     return XFEMM_OK;
 }
+// stream tiles of the finest level for a launch with `grid` blocks (stage.cuh); false: use direct loads
+bool linprob_ensure_tiles(xfemm_linprob *p, int grid) { return ensure_tiles(p, grid); }
 int linprob_store_solution_internal(xfemm_linprob *p)
 {
     const int n_pad = p->lay.n_pad;

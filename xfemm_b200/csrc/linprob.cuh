@@ -74,4 +74,5 @@ int linprob_prepare(xfemm_linprob *p, int precond);
 int linprob_load_rhs_internal(xfemm_linprob *p);
 int linprob_store_solution_internal(xfemm_linprob *p);
 int linprob_apply_amg_resident(xfemm_linprob *p);
+bool linprob_ensure_tiles(xfemm_linprob *p, int grid);
 } // namespace xb
