@@ -1,4 +1,3 @@
 cd /root/repo
-timeout 900 python -m pytest tests/test_gpu_harmonic.py -m gpu -x -q -s 2>&1 | tail -5
-timeout 600 python scratch/harm_big.py 0.0018 2>&1 | tail -1
-HARM_PRECOND=2 timeout 600 python scratch/harm_big.py 0.0018 2>&1 | tail -1
+timeout 900 python -m pytest tests/test_gpu_harmonic.py -m gpu -x -q -s 2>&1 | grep -i "iterations\|passed\|failed\|error" | tail -8
+HC_FIRST=2 timeout 1500 python scratch/harm_cases.py 2>&1 | tail -30

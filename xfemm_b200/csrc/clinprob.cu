@@ -124,20 +124,27 @@ __global__ void kc_reduce2_final(int nblk, const double *part, double *out2)
     if (threadIdx.x == 0) { out2[0] = a; out2[1] = c; }
 }
 
-// values of the real companion problem of XFEMM_PRECOND_AMG: Re(a_ij) between mesh nodes; the appended circuit
-// unknowns (rows/columns >= n_nodes) are decoupled (identity rows: the kernel treats them with a Jacobi step);
-// a diagonal without a positive real part falls back to its modulus
-// (the time-harmonic formulations assemble -K - j*omega*sigma*M: `sgn` = -1 turns the real part positive definite)
+// values of the real companion problem of XFEMM_PRECOND_AMG: sr*Re(a_ij) + si*Im(a_ij) between mesh nodes, sr/si = the
+// signs that make either part positive (semi-)definite (the time-harmonic formulations assemble
+// -K - j*omega*sigma*M, stiffness K and mass M, so both are -1).  With P = K + omega*sigma*M the eigenvalues of
+// P^-1 (K + j*omega*sigma*M) are (k + j m)/(k + m): on the segment between 1 and j whatever the mesh size and the
+// frequency.  The appended circuit unknowns (rows >= n_nodes) are identity rows of the companion (the solver
+// treats them with a Jacobi step); a diagonal that does not come out positive falls back to its modulus.
 __global__ void kc_diag_sign(int n_nodes, const int *__restrict__ rowptr, const int *__restrict__ col,
-                             const cd *__restrict__ vals, int *counts /* [0]=positive [1]=negative real diagonals */)
+                             const cd *__restrict__ vals, int *counts /* diagonals with Re>0, Re<0, Im>0, Im<0 */)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_nodes) return;
     for (int s = rowptr[i]; s < rowptr[i + 1]; s++)
-        if (col[s] == i) { if (vals[s].x > 0) atomicAdd(counts, 1); else if (vals[s].x < 0) atomicAdd(counts + 1, 1); }
+        if (col[s] == i)
+        {
+            if (vals[s].x > 0) atomicAdd(counts, 1); else if (vals[s].x < 0) atomicAdd(counts + 1, 1);
+            if (vals[s].y > 0) atomicAdd(counts + 2, 1); else if (vals[s].y < 0) atomicAdd(counts + 3, 1);
+        }
 }
 __global__ void kc_fill_real(int n, int n_nodes, const int *__restrict__ rowptr, const int *__restrict__ col,
-                             const cd *__restrict__ vals, double *__restrict__ out, double sgn)
+                             const int *__restrict__ src, const cd *__restrict__ vals, double *__restrict__ out,
+                             double sr, double si)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -145,11 +152,12 @@ __global__ void kc_fill_real(int n, int n_nodes, const int *__restrict__ rowptr,
     {
         const int j = col[s];
         double v;
-        if (i >= n_nodes || j >= n_nodes) v = (i == j) ? 1.0 : 0.0;
+        if (i >= n_nodes) v = 1.0; // identity row (the companion pattern holds nothing but its diagonal)
         else
         {
-            v = sgn * vals[s].x;
-            if (i == j && !(v > 0.0)) { v = sqrt(vals[s].x * vals[s].x + vals[s].y * vals[s].y); if (v == 0.0) v = 1.0; }
+            const cd a = vals[src[s]];
+            v = sr * a.x + si * a.y;
+            if (i == j && !(v > 0.0)) { v = sqrt(a.x * a.x + a.y * a.y); if (v == 0.0) v = 1.0; }
         }
         out[s] = v;
     }
@@ -232,7 +240,9 @@ __device__ __forceinline__ cd cprecond_apply(const CocgArgs &a, const AmgArgs &g
         {
             for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x)
             {
-                const double bi = comp ? a.r[i].y : a.r[i].x;
+                // circuit unknowns enter the cycle with a zero residual: their identity rows sit inside aggregates,
+                // and a residual restricted from them (while their own z is replaced below) would make M unsymmetric
+                const double bi = a.i2c[i] >= a.n_nodes ? 0.0 : (comp ? a.r[i].y : a.r[i].x);
                 L0.b[i] = bi;
                 L0.x[i] = g.omega * L0.dinv[i] * bi;
             }
@@ -836,21 +846,39 @@ int xfemm_clinprob_cocg(xfemm_clinprob *p, double precision, int warm, int preco
     double prec_sign = 1.0;
     if (precond == XFEMM_PRECOND_AMG)
     {
-        // real companion problem on the same pattern: values Re(A), multigrid hierarchy built once per pattern
+        // real companion problem (see kc_fill_real): the pattern between mesh nodes plus identity rows for the
+        // circuit unknowns, in the internal row order of this problem; hierarchy built once per pattern
         if (!p->re_prec)
         {
-            rc = xfemm_linprob_create(p->n, p->h_rowptr.data(), p->h_col.data(), &p->re_prec);
+            const int n = p->n, nn = p->n_nodes;
+            std::vector<int> rp(n + 1, 0), rc_, src;
+            rc_.reserve(p->h_col.size()); src.reserve(p->h_col.size());
+            for (int i = 0; i < n; i++)
+            {
+                for (int s = p->h_rowptr[i]; s < p->h_rowptr[i + 1]; s++)
+                {
+                    const int j = p->h_col[s];
+                    if (i < nn ? j < nn : j == i) { rc_.push_back(j); src.push_back(s); }
+                }
+                rp[i + 1] = (int)rc_.size();
+            }
+            rc = xfemm_linprob_create(n, rp.data(), rc_.data(), &p->re_prec);
             if (rc != XFEMM_OK) return rc;
+            for (int r : p->lay.i2c) if (r >= 0) p->re_prec->forced_order.push_back(r);
+            XB_CUDA(p->re_src.upload(src.data(), src.size(), st));
         }
         xfemm_linprob *R = p->re_prec;
         int *d_cnt = (int *)(p->d_mail.p + 12);
-        int h_cnt[2] = {0, 0};
-        XB_CUDA(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(int), st));
+        int h_cnt[4] = {0, 0, 0, 0};
+        XB_CUDA(cudaMemsetAsync(d_cnt, 0, 4 * sizeof(int), st));
         ++g_launch, kc_diag_sign<<<(p->n_nodes + 255) / 256, 256, 0, st>>>(p->n_nodes, p->rowptr.p, p->col.p, p->vals.p, d_cnt);
-        XB_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        XB_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
         XB_CUDA(cudaStreamSynchronize(st));
         prec_sign = h_cnt[1] > h_cnt[0] ? -1.0 : 1.0;
-        ++g_launch, kc_fill_real<<<(p->n + 255) / 256, 256, 0, st>>>(p->n, p->n_nodes, p->rowptr.p, p->col.p, p->vals.p, R->vals.p, prec_sign);
+        double im_sign = h_cnt[3] > h_cnt[2] ? -1.0 : 1.0;
+        if (const char *e = getenv("XFEMM_COMPLEX_AMG_REAL_ONLY")) if (atoi(e)) im_sign = 0.0;
+        ++g_launch, kc_fill_real<<<(p->n + 255) / 256, 256, 0, st>>>(p->n, p->n_nodes, R->rowptr.p, R->col.p, p->re_src.p, p->vals.p,
+                                                                      R->vals.p, prec_sign, im_sign);
         XB_CUDA(cudaStreamSynchronize(st)); // the companion works on its own stream
         rc = linprob_prepare(R, XFEMM_PRECOND_AMG);
         if (rc != XFEMM_OK) return rc;

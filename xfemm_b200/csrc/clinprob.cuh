@@ -24,7 +24,12 @@ struct xfemm_clinprob
     xb::DevBuf<cd> sell_val, diag, dinv, x, r, p, u, z, w, bint;
     xb::DevBuf<double> partials, d_mail;
     xb::WideDev<cd> wide;
-    xfemm_linprob *re_prec = nullptr; // real companion problem (Re A) carrying the multigrid hierarchy of XFEMM_PRECOND_AMG, owned
+    // XFEMM_PRECOND_AMG: real companion problem carrying the multigrid hierarchy (owned).  Its matrix is
+    // |Re A| + |Im A| between mesh nodes (stiffness + omega*sigma*mass, both positive semi-definite: the spectrum of
+    // the preconditioned operator then lies on the segment between 1 and j); its pattern leaves the circuit
+    // unknowns out, re_src[slot of the companion] = slot of this problem.
+    xfemm_linprob *re_prec = nullptr;
+    xb::DevBuf<int> re_src;
     int max_grid = 0;
     double h_mail[16];
     xb::DevBuf<int> dir_idx, dir_nodes;

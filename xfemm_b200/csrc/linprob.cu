@@ -705,11 +705,12 @@ int linprob_build_layout(xfemm_linprob *p, int precond)
     p->amg = nullptr;
     p->tile_grid = -1; // and so are the stream tiles
     SellLayout &L = p->lay;
-    const int sigma = env_int("XFEMM_SELL_SIGMA", 1024);
+    int sigma = env_int("XFEMM_SELL_SIGMA", 1024);
     // with node coordinates the internal order follows a Z-curve through the plane (gather locality)
     std::vector<int> zorder;
     if ((int)p->h_xy.size() == 2 * p->n && env_int("XFEMM_MORTON", 1)) morton_order(p->n, p->h_xy.data(), zorder);
     const int *base = zorder.empty() ? nullptr : zorder.data();
+    if ((int)p->forced_order.size() == p->n) { base = p->forced_order.data(); sigma = 1; } // taken as is: no window sort
     if (precond == XFEMM_PRECOND_MCSSOR)
     {
         std::vector<int> color;

@@ -6,11 +6,22 @@
 #include "../../include/xfemm_b200.h"
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+
+static int default_precond()
+{
+    // multigrid on |Re A| + |Im A| unless XFEMM_PRECOND says otherwise
+    const char *e = getenv("XFEMM_PRECOND");
+    if (!e) return XFEMM_PRECOND_AMG;
+    if (!strcmp(e, "jacobi") || !strcmp(e, "0")) return XFEMM_PRECOND_JACOBI;
+    if (!strcmp(e, "mcssor") || !strcmp(e, "1")) return XFEMM_PRECOND_MCSSOR;
+    return XFEMM_PRECOND_AMG;
+}
 
 CBigComplexLinProb::CBigComplexLinProb()
     : P(nullptr), U(nullptr), R(nullptr), V(nullptr), Z(nullptr), b(nullptr), uu(nullptr), vv(nullptr), M(nullptr),
       Mh(nullptr), Ma(nullptr), Ms(nullptr), n(0), bdw(0), bNewton(0), NumNodes(0), Precision(1e-8), Lambda(1.5),
-      precond(0), lastIterations(0), lastSolveMs(0), lastRelRes(0), dev(nullptr)
+      precond(default_precond()), lastIterations(0), lastSolveMs(0), lastRelRes(0), dev(nullptr)
 {
 }
 
@@ -56,7 +67,10 @@ int CBigComplexLinProb::PBCGSolveMod(int flag, bool)
         return 0;
     }
     xfemm_solve_info info;
-    int rc = xfemm_clinprob_cocg(dev, Precision, flag, precond, 0, &info);
+    // a multigrid attempt that does not converge within 3000 iterations is repeated with Jacobi (see FSolver)
+    int rc = xfemm_clinprob_cocg(dev, Precision, flag, precond, precond == XFEMM_PRECOND_AMG ? 3000 : 0, &info);
+    if (rc == XFEMM_ERR_DIVERGED && precond == XFEMM_PRECOND_AMG)
+        rc = xfemm_clinprob_cocg(dev, Precision, 0, XFEMM_PRECOND_JACOBI, 0, &info);
     lastIterations = info.iterations; lastSolveMs = info.solve_ms; lastRelRes = info.relres;
     if (rc != XFEMM_OK) { fprintf(stderr, "%s\n", xfemm_last_error()); return 0; }
     return xfemm_clinprob_get_solution(dev, (double *)V) == XFEMM_OK;

@@ -371,9 +371,9 @@ int FSolver::harmonicSolve(CBigComplexLinProb &L, bool axi, bool verbose)
         }
         xfemm_clinprob_save_solution(lin);
         xfemm_solve_info info;
-        // XFEMM_PRECOND_AMG here = multigrid on the real part of the matrix (opt-in: it cuts the iterations ~9x on
-        // problems without eddy currents, but COCG stagnates with it on the fixtures that have conductors and
-        // circuit unknowns); a failed attempt is repeated with the Jacobi preconditioner
+        // XFEMM_PRECOND_AMG here = multigrid V-cycle of the real matrix |Re A| + |Im A| (stiffness + omega*sigma*mass)
+        // applied to the real and the imaginary part of the residual; as a safety net an attempt that does not
+        // converge within 3000 iterations is repeated with the Jacobi preconditioner
         rc = xfemm_clinprob_cocg(lin, L.Precision, Iter, precond,
                                  (precond == XFEMM_PRECOND_AMG && maxIterOption <= 0) ? 3000 : maxIterOption, &info);
         if (rc == XFEMM_ERR_DIVERGED && precond == XFEMM_PRECOND_AMG)
