@@ -263,6 +263,21 @@ int xfemm_clinprob_save_solution(xfemm_clinprob *p);
 int xfemm_clinprob_newton_norms(xfemm_clinprob *p, int count, double *dv2, double *v2); /* first `count` rows */
 int xfemm_clinprob_relax(xfemm_clinprob *p, double relax);
 
+
+/* ------------------------------------------------------------------ Newton AC solver ([ACSolver]=1)
+ * Replaces the k=1,2,3 selector of CBigComplexLinProb::Put/Get/MultA/MultConjA (cspars.cpp:146-390), the side-matrix
+ * branches of SetValue/Wipe/Periodicity/AntiPeriodicity (cspars.cpp:511-535, 556-590, 648-668, 732-752) and
+ * KludgeSolve (cspars.cpp:983-1056).  The side matrices Mh (k=1, Hermitian), Ms (k=2, complex symmetric, applied to
+ * conj(x)) and Ma (k=3, anti-Hermitian) are stored on the full CSR pattern of the problem, nnz complex values each. */
+int xfemm_clinprob_enable_newton(xfemm_clinprob *p);
+int xfemm_clinprob_set_side_values(xfemm_clinprob *p, int k, const double *v);
+int xfemm_clinprob_get_side_values(xfemm_clinprob *p, int k, double *v);
+/* y = M x + Mh x + Ms conj(x) + Ma x  (MultA(X,Y,-1)); host vectors of n complex */
+int xfemm_clinprob_mult_newton(xfemm_clinprob *p, const double *x, double *y);
+/* KludgeSolve: <= 10 COCG solves on M with the side terms on the right-hand side, each followed by a line search on
+ * the full residual; stops when ||r||/||b|| < 10*precision.  info->iterations sums the inner COCG iterations. */
+int xfemm_clinprob_kludge_solve(xfemm_clinprob *p, double precision, int warm, int precond, int max_iter, xfemm_solve_info *info);
+
 /* ------------------------------------------------------------------ time-harmonic assembly */
 typedef struct xfemm_cmag_label
 {
@@ -312,8 +327,11 @@ int xfemm_cmag_create(const xfemm_cmag_desc *desc, xfemm_clinprob *lin, xfemm_cm
 int xfemm_cmag_destroy(xfemm_cmag *m);
 int xfemm_cmag_set_labels(xfemm_cmag *m, int n_labels, const xfemm_cmag_label *labels);
 /* one assembly pass (Wipe, AGE blocks with the harmonic sign, elements, boundary sides, RHS terms);
- * iter>0 re-evaluates the permeability of B-H elements by successive approximation */
+ * iter>0 re-evaluates the permeability of B-H elements by successive approximation, or — after
+ * xfemm_cmag_set_newton(m,1), which needs xfemm_clinprob_enable_newton on the problem — builds the Newton
+ * matrices Mn (into M) and Mnh/Mns/Mna (into the side matrices), harmonic2d.cpp:611-636, harmonicaxi.cpp:520-548 */
 int xfemm_cmag_assemble(xfemm_cmag *m, int iter, double *elapsed_ms);
+int xfemm_cmag_set_newton(xfemm_cmag *m, int on);
 int xfemm_cmag_fix_circuit_diagonals(xfemm_cmag *m);
 int xfemm_cmag_get_mu(xfemm_cmag *m, double *mu4);               /* n_elems*4: mu1.re, mu1.im, mu2.re, mu2.im */
 int xfemm_cmag_solution_to_A(xfemm_cmag *m, double *A_host);      /* n complex: A (nodes) and circuit results  */
@@ -379,6 +397,8 @@ int xfemm_fsolver_get_pbc(xfemm_fsolver *s, int *pbc3);
 int xfemm_fsolver_get_permutation(xfemm_fsolver *s, int *newnum);
 int xfemm_fsolver_get_pattern(xfemm_fsolver *s, long long *nnz, int *rowptr, int *colidx); /* colidx NULL → only nnz */
 int xfemm_fsolver_get_system(xfemm_fsolver *s, double *vals_csr, double *rhs); /* last assembled+BC'd system */
+/* Newton AC ([ACSolver]=1, keep_system=1): side matrix k=1 (Mh), 2 (Ms), 3 (Ma) of that system on the same slots */
+int xfemm_fsolver_get_side_matrix(xfemm_fsolver *s, int k, double *vals_csr);
 int xfemm_fsolver_get_solution(xfemm_fsolver *s, double *V, double *A);  /* complex: 2 doubles/entry */
 int xfemm_fsolver_get_mu(xfemm_fsolver *s, double *mu12);
 /* stats: newton steps, per-step Krylov iterations and device ms (arrays sized >= 64) */

@@ -209,6 +209,25 @@ int __wrap__ZN18CBigComplexLinProb12PBCGSolveModEib(CBigComplexLinProb *L, int f
         npy_c128(p + "val.npy", val.data(), val.size());
         npy_c128(p + "rhs.npy", L->b, L->n);
         npy_c128(p + "vin.npy", L->V, L->n);
+        if (L->bNewton)
+        {
+            // side matrices of the Newton AC solver as stored (upper triangle, cspars.h:53-55)
+            CComplexEntry **side[3] = {L->Mh, L->Ms, L->Ma};
+            for (int h = 0; h < 3; h++)
+            {
+                std::vector<int> rp(L->n + 1, 0), cc;
+                std::vector<CComplex> vv;
+                for (int i = 0; i < L->n; i++)
+                {
+                    for (CComplexEntry *e = side[h][i]; e; e = e->next) { cc.push_back(e->c); vv.push_back(e->x); }
+                    rp[i + 1] = (int)cc.size();
+                }
+                std::string q = p + "side" + std::to_string(h + 1) + "_";
+                npy_i32(q + "rowptr.npy", rp.data(), rp.size());
+                npy_i32(q + "col.npy", cc.data(), cc.size());
+                npy_c128(q + "val.npy", vv.data(), vv.size());
+            }
+        }
     }
     int ok = __real__ZN18CBigComplexLinProb12PBCGSolveModEib(L, flag, verbose);
     if (H.dumping && H.step < H.maxsteps)

@@ -177,6 +177,20 @@ def case_harmaxi(tmp):
     return "harmaxi"
 
 
+def case_harm2dn(tmp):
+    """harm2d solved with the Newton AC solver ([ACSolver]=1): side matrices Mh/Ms/Ma and KludgeSolve."""
+    _write_fem(os.path.join(tmp, "harm2dn.fem"), set_key(solenoid("planar", 50, "1e-08", amps=400, magnet_sigma=0.667, bar_amps=500,
+                                                                  steel_extra={"Sigma": 5.8, "Phi_h": 10}), "[ACSolver]", 1))
+    return "harm2dn"
+
+
+def case_harmaxin(tmp):
+    """harmaxi solved with the Newton AC solver."""
+    _write_fem(os.path.join(tmp, "harmaxin.fem"), set_key(solenoid("axisymmetric", 50, "1e-08", amps=100, magnet_sigma=0.667, bar_amps=200,
+                                                                   steel_extra={"Sigma": 5.8}), "[ACSolver]", 1))
+    return "harmaxin"
+
+
 def case_tbh(tmp):
     """TorqueBenchmark geometry (air-gap element + periodic pairs) at 50 Hz with a conducting,
     current-carrying rotor block: exercises the harmonic sign of the AGE blocks and complex periodicity."""
@@ -191,7 +205,8 @@ def case_tbh(tmp):
 
 
 CASES = {"tb": case_tb, "tb30": case_tb30, "temp1": case_temp1, "axi1": case_axi1, "sat2d": case_sat2d,
-         "harm2d": case_harm2d, "harmaxi": case_harmaxi, "tbh": case_tbh}
+         "harm2d": case_harm2d, "harmaxi": case_harmaxi, "tbh": case_tbh,
+         "harm2dn": case_harm2dn, "harmaxin": case_harmaxin}
 
 
 def run_case(name):
@@ -216,6 +231,7 @@ def run_case(name):
     steps = meta["solves"]
     for s in sorted({0, steps - 1}):
         keep += [f"step{s}_{k}" for k in ("rowptr", "col", "val", "rhs", "vin", "vout")]
+        keep += [f"step{s}_side{h}_{k}" for h in (1, 2, 3) for k in ("rowptr", "col", "val")]
     arrays = {}
     for k in keep:
         p = os.path.join(dump, k + ".npy")

@@ -115,3 +115,46 @@ def test_multigrid_with_eddy_currents_and_circuit_unknowns(case, tmp_path):
         S.close()
     print(case, "COCG iterations: jacobi", its[X.PRECOND_JACOBI], "multigrid", its[X.PRECOND_AMG])
     assert its[X.PRECOND_AMG] * 4 < its[X.PRECOND_JACOBI]
+
+
+def _dense_upper(n, rowptr, col, val):
+    import scipy.sparse as sp
+    return sp.csr_matrix((val, col, rowptr), shape=(n, n))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["harm2dn", "harmaxin"])
+def test_newton_ac_solver(case, tmp_path):
+    """[ACSolver]=1: Newton passes with the side matrices Mh/Ms/Ma (assembled on the device next to M) and KludgeSolve.
+    Same number of passes as the reference, its last system (M and the three side matrices, upper triangle as the
+    reference stores them) and its answer."""
+    import scipy.sparse as sp
+    ref, meta = load_ref(case)
+    n_nodes, n = meta["n_nodes"], meta["n_unknowns"]
+    S = _solve(case, tmp_path, X.PRECOND_AMG)
+    st = S.stats()
+    V, A = S.solution()
+    print(case, "Newton passes", st["newton_steps"], "reference", meta["solves"], "COCG iterations per pass", st["iters"],
+          "relL2(A nodes)", rel_l2(A[:n_nodes], ref["A"][:n_nodes]))
+    assert abs(st["newton_steps"] - meta["solves"]) <= 1
+    assert rel_l2(A[:n_nodes], ref["A"][:n_nodes]) <= 1e-6
+    assert np.allclose(A[n_nodes:], ref["A"][n_nodes:], rtol=1e-4, atol=1e-12)
+    if st["newton_steps"] != meta["solves"]:
+        return
+    last = meta["solves"] - 1
+    rowptr, col, vals, rhs = S.system()
+    full = sp.csr_matrix((vals, col, rowptr), shape=(n, n))
+    refM = sp.csr_matrix((ref[f"step{last}_val"], ref[f"step{last}_col"], ref[f"step{last}_rowptr"]), shape=(n, n))
+    scale = np.abs(ref[f"step{last}_val"]).max()
+    assert abs(sp.triu(full) - refM).max() <= 1e-4 * scale
+    for k in (1, 2, 3):
+        mine = sp.triu(sp.csr_matrix((S.side_matrix(k), col, rowptr), shape=(n, n)))
+        theirs = sp.csr_matrix((ref[f"step{last}_side{k}_val"], ref[f"step{last}_side{k}_col"], ref[f"step{last}_side{k}_rowptr"]), shape=(n, n))
+        sc = max(np.abs(ref[f"step{last}_side{k}_val"]).max(), 1e-300)
+        err = abs(mine - theirs).max() / sc
+        print("   side matrix", k, "max |ref|", sc, "rel err", err)
+        assert err <= 1e-4
+        # symmetry class on the full storage: Hermitian / complex symmetric / anti-Hermitian
+        G = sp.csr_matrix((S.side_matrix(k), col, rowptr), shape=(n, n))
+        other = {1: G.conj().T, 2: G.T, 3: -G.conj().T}[k]
+        assert abs(G - other).max() <= 1e-12 * sc

@@ -115,10 +115,16 @@ SIGNATURES = {
     "xfemm_clinprob_save_solution": (C.c_int, [_P]),
     "xfemm_clinprob_newton_norms": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "xfemm_clinprob_relax": (C.c_int, [_P, C.c_double]),
+    "xfemm_clinprob_enable_newton": (C.c_int, [_P]),
+    "xfemm_clinprob_set_side_values": (C.c_int, [_P, C.c_int, _P]),
+    "xfemm_clinprob_get_side_values": (C.c_int, [_P, C.c_int, _P]),
+    "xfemm_clinprob_mult_newton": (C.c_int, [_P, _P, _P]),
+    "xfemm_clinprob_kludge_solve": (C.c_int, [_P, C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(SolveInfo)]),
     "xfemm_cmag_create": (C.c_int, [_P, _P, C.POINTER(_P)]),
     "xfemm_cmag_destroy": (C.c_int, [_P]),
     "xfemm_cmag_set_labels": (C.c_int, [_P, C.c_int, _P]),
     "xfemm_cmag_assemble": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double)]),
+    "xfemm_cmag_set_newton": (C.c_int, [_P, C.c_int]),
     "xfemm_cmag_fix_circuit_diagonals": (C.c_int, [_P]),
     "xfemm_cmag_get_mu": (C.c_int, [_P, _P]),
     "xfemm_cmag_solution_to_A": (C.c_int, [_P, _P]),
@@ -155,6 +161,7 @@ SIGNATURES = {
     "xfemm_fsolver_get_permutation": (C.c_int, [_P, _ip]),
     "xfemm_fsolver_get_pattern": (C.c_int, [_P, C.POINTER(C.c_longlong), _P, _P]),
     "xfemm_fsolver_get_system": (C.c_int, [_P, _P, _P]),
+    "xfemm_fsolver_get_side_matrix": (C.c_int, [_P, C.c_int, _P]),
     "xfemm_fsolver_get_solution": (C.c_int, [_P, _P, _P]),
     "xfemm_fsolver_get_mu": (C.c_int, [_P, _P]),
     "xfemm_fsolver_get_stats": (C.c_int, [_P, C.POINTER(C.c_int), _ip, _dp, _dp, C.POINTER(C.c_double)]),
@@ -448,6 +455,14 @@ class FSolver:
         rhs = np.empty(n, dtype=np.complex128 if cplx else np.float64)
         _check(lib().xfemm_fsolver_get_system(self.h, _ptr(vals), _ptr(rhs)), "get_system")
         return rowptr, col, vals, rhs
+
+    def side_matrix(self, k):
+        """Newton AC: values of Mh (k=1), Ms (k=2) or Ma (k=3) of the last system, on the slots of system()."""
+        nnz = C.c_longlong(0)
+        _check(lib().xfemm_fsolver_get_pattern(self.h, C.byref(nnz), None, None), "get_pattern")
+        vals = np.empty(nnz.value, dtype=np.complex128)
+        _check(lib().xfemm_fsolver_get_side_matrix(self.h, k, _ptr(vals)), "get_side_matrix")
+        return vals
 
     def solution(self):
         c = self.counts()

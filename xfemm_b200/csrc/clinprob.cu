@@ -17,26 +17,6 @@
 namespace cg = cooperative_groups;
 namespace xb {
 
-__device__ __forceinline__ cd cmul(cd a, cd b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-__device__ __forceinline__ cd cadd(cd a, cd b) { return make_double2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ cd csub(cd a, cd b) { return make_double2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ cd cscale(cd a, double s) { return make_double2(a.x * s, a.y * s); }
-__device__ __forceinline__ cd cconj(cd a) { return make_double2(a.x, -a.y); }
-__device__ __forceinline__ cd cfma(cd a, cd b, cd c) // a*b + c
-{
-    return make_double2(fma(a.x, b.x, fma(-a.y, b.y, c.x)), fma(a.x, b.y, fma(a.y, b.x, c.y)));
-}
-__device__ __forceinline__ cd cdiv(cd a, cd b)
-{
-    // Smith's algorithm
-    if (fabs(b.x) >= fabs(b.y))
-    {
-        double t = b.y / b.x, d = b.x + b.y * t;
-        return make_double2((a.x + a.y * t) / d, (a.y - a.x * t) / d);
-    }
-    double t = b.x / b.y, d = b.x * t + b.y;
-    return make_double2((a.x * t + a.y) / d, (a.y * t - a.x) / d);
-}
 __device__ __forceinline__ cd block_sum_c(cd v, double *smem)
 {
     double a = block_sum(v.x, smem);
@@ -463,16 +443,8 @@ __global__ void kc_dir_scatter(int count, const int *__restrict__ nodes, int *di
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k < count) dir_idx[nodes[k]] = k;
 }
-// SetValue (cspars.cpp:482-537): entry {k,i} goes when i is fixed and k lies in [i-bdw, min(i+bdw,NumNodes))
-// or k is a circuit row (k >= NumNodes, always scanned); free row k: b[k] -= A[k,i] x_first(i).
-__device__ __forceinline__ bool cband(int k, int i, int bdw, int n_nodes)
-{
-    if (k >= n_nodes) return true;
-    if (bdw == 0) return true;
-    int lst = i + bdw;
-    if (lst > n_nodes) lst = n_nodes;
-    return k >= i - bdw && k < lst;
-}
+// SetValue (cspars.cpp:482-537): entry {k,i} goes when i is fixed and k is in the scanned band (cband, ccomplex.cuh);
+// free row k: b[k] -= A[k,i] x_first(i).
 __global__ void kc_dirichlet(int n, int n_nodes, const int *__restrict__ rowptr, const int *__restrict__ col, cd *vals, cd *b,
                              const int *__restrict__ dir_idx, const cd *__restrict__ xf, const cd *__restrict__ xl, int bdw)
 {
@@ -735,6 +707,8 @@ int xfemm_clinprob_wipe(xfemm_clinprob *p)
     XB_ARG(p, "null handle");
     XB_CUDA(p->vals.zero(p->stream));
     XB_CUDA(p->b.zero(p->stream));
+    if (p->newton)
+        for (auto *v : {&p->vals_h, &p->vals_s, &p->vals_a}) XB_CUDA(v->zero(p->stream));
     return XFEMM_OK;
 }
 #define XC_IN(buf, src, cnt)                                                                              \
@@ -769,6 +743,7 @@ int xfemm_clinprob_dirichlet(xfemm_clinprob *p, int count, const int *nodes, con
     ++g_launch, kc_dir_scatter<<<(count + 255) / 256, 256, 0, st>>>(count, p->dir_nodes.p, p->dir_idx.p);
     ++g_launch, kc_dirichlet<<<(p->n + 255) / 256, 256, 0, st>>>(p->n, p->n_nodes, p->rowptr.p, p->col.p, p->vals.p, p->b.p,
                                                                   p->dir_idx.p, p->dir_first.p, p->dir_last.p, bdw);
+    if (p->newton) { int rc = cnewton_dirichlet(p, bdw); if (rc != XFEMM_OK) return rc; }
     ++g_launch, kc_fill_int<<<(p->n + 255) / 256, 256, 0, st>>>(p->n, p->dir_idx.p, -1);
     XB_CUDA(cudaGetLastError());
     XB_CUDA(cudaStreamSynchronize(st));
@@ -804,6 +779,7 @@ int xfemm_clinprob_periodic(xfemm_clinprob *p, int npairs, const int *ni, const 
     ++g_launch, kc_periodic<<<1, 1024, 0, p->stream>>>(p->pbc_levels, p->pbc_level_ptr.p, p->pbc_item_ptr.p, p->pbc_meta.p,
                                                        p->pbc_items.p, p->vals.p, p->b.p,
                                                        p->fill_mask.n ? p->fill_mask.p : nullptr, p->created.p);
+    if (p->newton) { int rc = cnewton_periodic(p, npairs, ni, nj); if (rc != XFEMM_OK) return rc; }
     XB_CUDA(cudaGetLastError());
     XB_CUDA(cudaStreamSynchronize(p->stream));
     return XFEMM_OK;

@@ -1,12 +1,13 @@
 // Device-side complex-symmetric linear problem (backend of CBigComplexLinProb; cspars.h:37-95).
 #pragma once
 #include "common.cuh"
+#include "ccomplex.cuh"
 #include "layout.h"
 #include "wide_rows.cuh"
 #include <vector>
 #include <cstdint>
 
-typedef double2 cd;
+using xb::cd;
 struct xfemm_linprob;
 
 struct xfemm_clinprob
@@ -38,5 +39,18 @@ struct xfemm_clinprob
     int pbc_pairs = 0, pbc_levels = 0;
     xb::DevBuf<int> pbc_level_ptr, pbc_item_ptr, pbc_meta, pbc_items;
     xb::DevBuf<unsigned char> fill_mask, created;
+    // Newton AC solver ([ACSolver]=1): the side matrices Mh (Hermitian), Ms (complex symmetric) and Ma
+    // (anti-Hermitian) of cspars.h:53-55, on the same full CSR pattern as `vals`; empty until
+    // xfemm_clinprob_enable_newton.  Wipe, Dirichlet and periodic conditions then act on them too (cnewton.cu).
+    bool newton = false;
+    xb::DevBuf<cd> vals_h, vals_s, vals_a;
+    xb::DevBuf<int> pbc_ij;          // per periodic pair: slot(i,j), slot(j,i)
+    uint64_t pbc_ij_hash = 0;
+    xb::DevBuf<cd> nk_b, nk_v, nk_r, nk_p, nk_u; // scratch vectors of xfemm_clinprob_kludge_solve
 };
+
+namespace xb {
+int cnewton_dirichlet(xfemm_clinprob *p, int bdw);                              // after kc_dirichlet, dir_idx still set
+int cnewton_periodic(xfemm_clinprob *p, int npairs, const int *ni, const int *nj); // after kc_periodic, plan current
+} // namespace xb
 

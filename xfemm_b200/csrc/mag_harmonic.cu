@@ -39,6 +39,7 @@ struct xfemm_cmag
     xb::DevBuf<int> fix_rows;
     double ext_zo = 0, ext_ro = 0, ext_ri = 0;
     xb::DevBuf<int> err_flag;
+    int newton = 0; // [ACSolver]=1: passes with iter>0 build the Newton matrices
 };
 
 namespace xb {
@@ -114,6 +115,34 @@ __device__ __forceinline__ void bh_harmonic(const double *__restrict__ Bd, const
         }
 }
 
+// complex nu = H(B)/B and d nu/d(B^2) = (H'/B^2 - H/B^3)/2 (GetBHProps, CMaterialProp.cpp:1008-1057) for the Newton AC solver
+__device__ __forceinline__ void bh_props_complex(const double *__restrict__ Bd, const double *__restrict__ Hr,
+                                                 const double *__restrict__ Hi, const double *__restrict__ Sr,
+                                                 const double *__restrict__ Si, int npts, double B, cd &v, cd &dv)
+{
+    const double b = fabs(B);
+    if (b == 0) { v = make_double2(Sr[0], Si[0]); dv = make_double2(0., 0.); return; }
+    cd h, dh;
+    if (b > Bd[npts - 1])
+    {
+        const double d = b - Bd[npts - 1];
+        h = make_double2(Hr[npts - 1] + Sr[npts - 1] * d, Hi[npts - 1] + Si[npts - 1] * d);
+        dh = make_double2(Sr[npts - 1], Si[npts - 1]);
+    }
+    else
+    {
+        int i = 0;
+        while (i < npts - 2 && !(b >= Bd[i] && b <= Bd[i + 1])) i++;
+        const double l = Bd[i + 1] - Bd[i], z = (b - Bd[i]) / l, z2 = z * z;
+        const double c0 = (1. - 3. * z2 + 2. * z2 * z), c1 = z * (1. - 2. * z + z2) * l, c2 = z2 * (3. - 2. * z), c3 = z2 * (z - 1.) * l;
+        const double d0 = 6. * z * (z - 1.) / l, d1 = (1. - 4. * z + 3. * z * z), d2 = 6. * z * (1. - z) / l, d3 = z * (3. * z - 2.);
+        h = make_double2(c0 * Hr[i] + c1 * Sr[i] + c2 * Hr[i + 1] + c3 * Sr[i + 1], c0 * Hi[i] + c1 * Si[i] + c2 * Hi[i + 1] + c3 * Si[i + 1]);
+        dh = make_double2(d0 * Hr[i] + d1 * Sr[i] + d2 * Hr[i + 1] + d3 * Sr[i + 1], d0 * Hi[i] + d1 * Si[i] + d2 * Hi[i + 1] + d3 * Si[i + 1]);
+    }
+    v = hsc(h, 1. / b);
+    dv = make_double2(0.5 * (dh.x / (b * b) - h.x / (b * b * b)), 0.5 * (dh.y / (b * b) - h.y / (b * b * b)));
+}
+
 template <bool AXI>
 __global__ void __launch_bounds__(256)
 kh_assemble(int ne, int iter, int n_nodes, double omega, const int4 *__restrict__ tri, const double2 *__restrict__ xy,
@@ -121,7 +150,7 @@ kh_assemble(int ne, int iter, int n_nodes, double omega, const int4 *__restrict_
             const double *__restrict__ bhHr, const double *__restrict__ bhHi, const double *__restrict__ bhSr,
             const double *__restrict__ bhSi, const cd *__restrict__ V, const int *__restrict__ rowptr,
             const int *__restrict__ col, cd *vals, cd *b, double4 *mu_out, double ext_zo, double ext_ro, double ext_ri,
-            int *err)
+            int *err, int newton, cd *vals_h, cd *vals_s, cd *vals_a)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= ne) return;
@@ -261,9 +290,51 @@ kh_assemble(int ne, int iter, int n_nodes, double omega, const int4 *__restrict_
         }
         cd v, dh;
         const int o = L.bh_offset;
+        const cd one = make_double2(1., 0.);
+        if (newton)
+        {
+            // Newton AC (harmonic2d.cpp:611-636, harmonicaxi.cpp:520-548): mu from nu(B); with v = (Mx+My) V and
+            // K = -200 c^3 (d nu/dB^2) / area:  Mn = K Re(v v^H) goes into the complex-symmetric matrix,
+            // Mnh = Re(K) v v^H /2 - Re(Mn) (Hermitian), Mna = j Im(K) v v^H /2 - j Im(Mn) (anti-Hermitian) and
+            // Mns = K v v^T /2 (acts on conj(V)) into the side matrices; all four also feed the right-hand side.
+            cd dv;
+            bh_props_complex(bhB + o, bhHr + o, bhHi + o, bhSr + o, bhSi + o, L.bh_points, B, v, dv);
+            const cd mu = hdiv(one, hsc(v, XB_MUO));
+            mu1 = mu; mu2 = mu;
+            cd vv[3];
+            for (int j = 0; j < 3; j++)
+            {
+                vv[j] = make_double2(0., 0.);
+                for (int w = 0; w < 3; w++) vv[j] = hadd(vv[j], hsc(Vn[w], Mx[j][w] + My[j][w]));
+            }
+            const cd K = hsc(dv, -200. * c * c * c / (AXI ? vol : a));
+            if (mu_out) mu_out[e] = make_double4(mu1.x, mu1.y, mu2.x, mu2.y);
+            const cd i1 = hdiv(one, mu1), i2 = hdiv(one, mu2);
+            for (int j = 0; j < 3; j++)
+            {
+                cd bj = be[j];
+                for (int k = 0; k < 3; k++)
+                {
+                    const cd vvh = hmul(vv[j], make_double2(vv[k].x, -vv[k].y)); // v_j conj(v_k)
+                    const cd mn = hsc(K, vvh.x);
+                    const cd mnh = make_double2(0.5 * K.x * vvh.x - mn.x, 0.5 * K.x * vvh.y);
+                    const cd mna = make_double2(-0.5 * K.y * vvh.y, 0.5 * K.y * vvh.x - mn.y);
+                    const cd mns = hsc(hmul(K, hmul(vv[j], vv[k])), 0.5);
+                    const cd me = hadd(hadd(Me[j][k], mn), hadd(hsc(i2, Mx[j][k]), hsc(i1, My[j][k])));
+                    bj = hadd(bj, hmul(hadd(hadd(mnh, mna), mn), Vn[k]));
+                    bj = hadd(bj, hmul(mns, make_double2(Vn[k].x, -Vn[k].y)));
+                    const int slot = emap[(size_t)(3 * j + k) * ne + e];
+                    hatomic(vals + slot, me);
+                    hatomic(vals_h + slot, mnh);
+                    hatomic(vals_s + slot, mns);
+                    hatomic(vals_a + slot, mna);
+                }
+                hatomic(b + n[j], bj);
+            }
+            return;
+        }
         bh_harmonic(bhB + o, bhHr + o, bhHi + o, bhSr + o, bhSi + o, L.bh_points, B, v, dh);
         // successive approximation with the averaged permeability (harmonic2d.cpp:641-657)
-        const cd one = make_double2(1., 0.);
         const cd murel = hdiv(one, hsc(v, XB_MUO)), muinc = hdiv(one, hsc(dh, XB_MUO));
         const cd K = hdiv(hsc(hmul(murel, muinc), 2.), hadd(murel, muinc));
         mu1 = K; mu2 = K;
@@ -466,6 +537,13 @@ int xfemm_cmag_create(const xfemm_cmag_desc *d, xfemm_clinprob *lin, xfemm_cmag 
     return XFEMM_OK;
 }
 
+int xfemm_cmag_set_newton(xfemm_cmag *m, int on)
+{
+    XB_ARG(m, "null handle");
+    m->newton = on ? 1 : 0;
+    return XFEMM_OK;
+}
+
 int xfemm_cmag_destroy(xfemm_cmag *m)
 {
     delete m;
@@ -482,6 +560,12 @@ int xfemm_cmag_assemble(xfemm_cmag *m, int iter, double *elapsed_ms)
     XB_CUDA(L->vals.zero(st));
     XB_CUDA(L->b.zero(st));
     XB_CUDA(m->err_flag.zero(st));
+    const int newton = (m->newton && iter > 0) ? 1 : 0;
+    if (m->newton)
+    {
+        XB_ARG(L->newton, "xfemm_cmag_set_newton needs xfemm_clinprob_enable_newton on the linear problem");
+        for (auto *v : {&L->vals_h, &L->vals_s, &L->vals_a}) XB_CUDA(v->zero(st));
+    }
     if (m->n_age_cells > 0 && !m->axisymmetric)
     {
         int nt = m->n_age_cells * 55;
@@ -492,11 +576,13 @@ int xfemm_cmag_assemble(xfemm_cmag *m, int iter, double *elapsed_ms)
     if (m->axisymmetric)
         ++g_launch, kh_assemble<true><<<nb, 256, 0, st>>>(m->n_elems, iter, m->n_nodes, m->omega, (const int4 *)m->tri.p,
             (const double2 *)m->xy.p, m->emap.p, m->labels.p, m->bhB.p, m->bhHr.p, m->bhHi.p, m->bhSr.p, m->bhSi.p, L->V.p,
-            L->rowptr.p, L->col.p, L->vals.p, L->b.p, (double4 *)m->mu.p, m->ext_zo, m->ext_ro, m->ext_ri, m->err_flag.p);
+            L->rowptr.p, L->col.p, L->vals.p, L->b.p, (double4 *)m->mu.p, m->ext_zo, m->ext_ro, m->ext_ri, m->err_flag.p,
+            newton, L->vals_h.p, L->vals_s.p, L->vals_a.p);
     else
         ++g_launch, kh_assemble<false><<<nb, 256, 0, st>>>(m->n_elems, iter, m->n_nodes, m->omega, (const int4 *)m->tri.p,
             (const double2 *)m->xy.p, m->emap.p, m->labels.p, m->bhB.p, m->bhHr.p, m->bhHi.p, m->bhSr.p, m->bhSi.p, L->V.p,
-            L->rowptr.p, L->col.p, L->vals.p, L->b.p, (double4 *)m->mu.p, m->ext_zo, m->ext_ro, m->ext_ri, m->err_flag.p);
+            L->rowptr.p, L->col.p, L->vals.p, L->b.p, (double4 *)m->mu.p, m->ext_zo, m->ext_ro, m->ext_ri, m->err_flag.p,
+            newton, L->vals_h.p, L->vals_s.p, L->vals_a.p);
     if (m->n_side > 0)
         ++g_launch, kh_sides<<<(m->n_side + 127) / 128, 128, 0, st>>>(m->n_side, m->n_elems, m->side_es.p, m->side_k.p,
                                                                      (const int4 *)m->tri.p, (const double2 *)m->xy.p, m->emap.p,

@@ -245,6 +245,14 @@ int xfemm_fsolver_get_system(xfemm_fsolver *s, double *vals, double *rhs)
     return XFEMM_OK;
 }
 
+int xfemm_fsolver_get_side_matrix(xfemm_fsolver *s, int k, double *vals)
+{
+    if (!s || k < 1 || k > 3 || !vals) { xb::set_error("handle, k in 1..3, values"); return XFEMM_ERR_ARG; }
+    if (s->S.sysSide[k - 1].empty()) { xb::set_error("no side matrices kept: [ACSolver]=1 and option keep_system=1 are needed"); return XFEMM_ERR_ARG; }
+    memcpy(vals, s->S.sysSide[k - 1].data(), sizeof(double) * s->S.sysSide[k - 1].size());
+    return XFEMM_OK;
+}
+
 int xfemm_fsolver_get_solution(xfemm_fsolver *s, double *V, double *A)
 {
     if (!s) return XFEMM_ERR_ARG;

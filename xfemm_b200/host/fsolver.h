@@ -279,6 +279,7 @@ public:
     bool keepSystem;
     std::vector<int> sysRowptr, sysCol;
     std::vector<double> sysVals, sysRhs;
+    std::vector<double> sysSide[3]; // Newton AC: Mh, Ms, Ma on the slots of sysCol (keep_system)
 
 protected:
     void SortNodes(const std::vector<int> &newnum); // fsolver.cpp:1341-1353

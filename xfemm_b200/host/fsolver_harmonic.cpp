@@ -1,7 +1,7 @@
 // FSolver: host orchestration of the time-harmonic formulations (complex-symmetric systems).
 // Reference behaviour mirrored: FSolver::Harmonic2D (cfemm/fsolver/harmonic2d.cpp:38-890) and
-// FSolver::HarmonicAxisymmetric (cfemm/fsolver/harmonicaxi.cpp:34-821) with [ACSolver]=0
-// (successive approximation).  All O(elements)/O(nnz) arithmetic runs on the GPU (xfemm_cmag_*,
+// FSolver::HarmonicAxisymmetric (cfemm/fsolver/harmonicaxi.cpp:34-821), with [ACSolver]=0
+// (successive approximation) or 1 (Newton: side matrices + KludgeSolve, csrc/cnewton.cu).  All O(elements)/O(nnz) arithmetic runs on the GPU (xfemm_cmag_*,
 // xfemm_clinprob_*); this file prepares the per-label / per-side tables and drives the outer loop.
 #include "fsolver.h"
 #include "../../include/xfemm_b200.h"
@@ -41,13 +41,6 @@ int FSolver::harmonicSolve(CBigComplexLinProb &L, bool axi, bool verbose)
     {
         const int lt = blockproplist[meshele[i].blk].LamType;
         if (lt == 1 || lt == 2) { WarnMessage("On-edge lamination not supported in AC analyses"); return false; }
-    }
-    if (ACSolver == 1)
-    {
-        // the Newton AC solver (Mh/Ms/Ma side matrices + KludgeSolve, cspars.cpp:983-1056) is not
-        // part of this build; the default successive-approximation solver ([ACSolver]=0) is
-        WarnMessage("xfemm_b200: [ACSolver]=1 (Newton AC) is not supported; use the successive approximation solver\n");
-        return false;
     }
     for (int i = 0; i < NumBlockLabels; i++) GetFillFactor(i);
     for (int i = 0; i < NumBlockLabels; i++)
@@ -286,6 +279,10 @@ int FSolver::harmonicSolve(CBigComplexLinProb &L, bool axi, bool verbose)
     for (int k = 0; k < NumPBCs; k++) { pbcI[k] = pbclist[k].x; pbcJ[k] = pbclist[k].y; pbcT[k] = pbclist[k].t; }
     std::vector<int> exI, exJ;
     for (auto &pr : circPairs) { exI.push_back(pr.first); exJ.push_back(pr.second); }
+    // Newton AC: Periodicity/AntiPeriodicity on the side matrices write the entry coupling the two nodes of a pair
+    // (cspars.cpp:664-667, 748-751)
+    if (ACSolver == 1)
+        for (int k = 0; k < NumPBCs; k++) { exI.push_back(pbcI[k]); exJ.push_back(pbcJ[k]); }
 
     // ---- pattern → device problem
     double t0 = hwall();
@@ -333,6 +330,14 @@ int FSolver::harmonicSolve(CBigComplexLinProb &L, bool axi, bool verbose)
     stats.t_upload = hwall() - t0;
 
     const int precond = precondOption >= 0 ? precondOption : L.precond;
+    bool anyBH = false; // an element whose permeability follows a B-H curve (LamType 0): the only source of side-matrix entries
+    for (int i = 0; i < NumEls && !anyBH; i++)
+        anyBH = blockproplist[meshele[i].blk].LamType == 0 && blockproplist[meshele[i].blk].BHpoints > 0;
+    if (ACSolver == 1 && (xfemm_clinprob_enable_newton(lin) != XFEMM_OK || xfemm_cmag_set_newton(cmagdev, 1) != XFEMM_OK))
+    {
+        WarnMessage(xfemm_last_error());
+        return false;
+    }
     int Iter = 0;
     double res = 0, lastres = 0;
     Relax = 1.;
@@ -368,16 +373,38 @@ int FSolver::harmonicSolve(CBigComplexLinProb &L, bool axi, bool verbose)
                     if (ex[q]) { sysCol.push_back(hCol[q]); sysVals.push_back(v0[2 * (size_t)q]); sysVals.push_back(v0[2 * (size_t)q + 1]); }
                 sysRowptr[i + 1] = (int)sysCol.size();
             }
+            for (int h = 0; h < 3; h++)
+            {
+                sysSide[h].clear();
+                if (ACSolver != 1) continue;
+                xfemm_clinprob_get_side_values(lin, h + 1, v0.data());
+                for (size_t q = 0; q < nnz0; q++)
+                    if (ex[q]) { sysSide[h].push_back(v0[2 * q]); sysSide[h].push_back(v0[2 * q + 1]); }
+            }
         }
         xfemm_clinprob_save_solution(lin);
         xfemm_solve_info info;
         // XFEMM_PRECOND_AMG here = multigrid V-cycle of the real matrix |Re A| + |Im A| (stiffness + omega*sigma*mass)
         // applied to the real and the imaginary part of the residual; as a safety net an attempt that does not
         // converge within 3000 iterations is repeated with the Jacobi preconditioner
-        rc = xfemm_clinprob_cocg(lin, L.Precision, Iter, precond,
-                                 (precond == XFEMM_PRECOND_AMG && maxIterOption <= 0) ? 3000 : maxIterOption, &info);
-        if (rc == XFEMM_ERR_DIVERGED && precond == XFEMM_PRECOND_AMG)
-            rc = xfemm_clinprob_cocg(lin, L.Precision, 0, XFEMM_PRECOND_JACOBI, maxIterOption, &info);
+        // Newton AC ([ACSolver]=1): from the second pass on the system carries the side matrices (L.bNewton), the
+        // linear tolerance follows the nonlinear residual (harmonic2d.cpp:821-825) and PBCGSolveMod dispatches to
+        // KludgeSolve (cspars.cpp:1065-1067)
+        const bool newtonPass = ACSolver == 1 && Iter > 0 && anyBH;
+        if (newtonPass)
+        {
+            L.bNewton = 1;
+            L.Precision = std::min(1.e-4, 0.001 * res);
+            if (L.Precision < Precision) L.Precision = Precision;
+            rc = xfemm_clinprob_kludge_solve(lin, L.Precision, Iter, precond, maxIterOption, &info);
+        }
+        else
+        {
+            rc = xfemm_clinprob_cocg(lin, L.Precision, Iter, precond,
+                                     (precond == XFEMM_PRECOND_AMG && maxIterOption <= 0) ? 3000 : maxIterOption, &info);
+            if (rc == XFEMM_ERR_DIVERGED && precond == XFEMM_PRECOND_AMG)
+                rc = xfemm_clinprob_cocg(lin, L.Precision, 0, XFEMM_PRECOND_JACOBI, maxIterOption, &info);
+        }
         stats.pcg_iters.push_back(info.iterations);
         stats.pcg_ms.push_back(info.solve_ms);
         stats.final_relres = info.relres;
@@ -398,7 +425,7 @@ int FSolver::harmonicSolve(CBigComplexLinProb &L, bool axi, bool verbose)
             if (verbose)
             {
                 char outstr[256];
-                snprintf(outstr, sizeof outstr, "Successive Approx(%i) Relax=%.4g\n", Iter, Relax);
+                snprintf(outstr, sizeof outstr, ACSolver == 1 ? "Newton Iteration(%i) Relax=%.4g\n" : "Successive Approx(%i) Relax=%.4g\n", Iter, Relax);
                 PrintMessage(outstr);
             }
         }
