@@ -204,9 +204,26 @@ def case_tbh(tmp):
     return "tbh"
 
 
+def case_tbhn(tmp):
+    """Newton AC solver with periodic pairs and the air-gap element: the tbh problem with the outer regions ("Air",
+    "Ext": the blocks on either side of the periodic boundary circles) given the 1117-steel B-H curve, so that the
+    side matrices Mh/Ms/Ma carry entries on periodic nodes (cspars.cpp:648-668, 732-752)."""
+    case_tbh(tmp)
+    t = open(os.path.join(tmp, "tbh.fem")).read()
+    os.remove(os.path.join(tmp, "tbh.fem"))
+    t = set_key(t, "[ACSolver]", 1)
+    parts = t.split("<BeginBlock>")
+    bh = "<BHPoints> = %d\n" % len(STEEL_BH) + "".join(f"      {x!r}\t{y!r}\n" for x, y in STEEL_BH)
+    for i in (1, 2):  # Air, Ext
+        parts[i] = parts[i].replace("<Mu_x> = 1", "<Mu_x> = 1777", 1).replace("<Mu_y> = 1", "<Mu_y> = 1777", 1)
+        parts[i] = parts[i].replace("<BHPoints> = 0\n", bh, 1)
+    _write_fem(os.path.join(tmp, "tbhn.fem"), "<BeginBlock>".join(parts))
+    return "tbhn"
+
+
 CASES = {"tb": case_tb, "tb30": case_tb30, "temp1": case_temp1, "axi1": case_axi1, "sat2d": case_sat2d,
          "harm2d": case_harm2d, "harmaxi": case_harmaxi, "tbh": case_tbh,
-         "harm2dn": case_harm2dn, "harmaxin": case_harmaxin}
+         "harm2dn": case_harm2dn, "harmaxin": case_harmaxin, "tbhn": case_tbhn}
 
 
 def run_case(name):
