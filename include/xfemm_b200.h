@@ -396,6 +396,9 @@ int xfemm_fsolver_get_elems(xfemm_fsolver *s, int *elems8);              /* p0 p
 int xfemm_fsolver_get_pbc(xfemm_fsolver *s, int *pbc3);
 int xfemm_fsolver_get_permutation(xfemm_fsolver *s, int *newnum);
 int xfemm_fsolver_get_pattern(xfemm_fsolver *s, long long *nnz, int *rowptr, int *colidx); /* colidx NULL → only nnz */
+/* value [deg] of a block label's magnetisation-direction expression (`MagDirFctn`) at the point (x, y) in problem
+ * length units: what the reference obtains from its Lua interpreter per element (static2d.cpp:513-583).  Host only. */
+int xfemm_magdir_eval(const char *expr, double x, double y, double *out);
 int xfemm_fsolver_get_system(xfemm_fsolver *s, double *vals_csr, double *rhs); /* last assembled+BC'd system */
 /* Newton AC ([ACSolver]=1, keep_system=1): side matrix k=1 (Mh), 2 (Ms), 3 (Ma) of that system on the same slots */
 int xfemm_fsolver_get_side_matrix(xfemm_fsolver *s, int k, double *vals_csr);

@@ -59,6 +59,19 @@ def case_tb(tmp):
     return "tb"
 
 
+def case_tbmag(tmp):
+    """TorqueBenchmark with a functional magnetisation direction on both magnet labels (the string the reference
+    evaluates per element with its Lua interpreter, static2d.cpp:513-583): operators, ^, variables and functions."""
+    t = open(os.path.join(SRC, "test", "TorqueBenchmark.fem"), newline="").read().replace("\r\n", "\n")
+    head, sep, tail = t.partition("[NumBlockLabels]")
+    lines = tail.split("\n")
+    fn = {0: "theta + 20*cos(3*theta*PI/180) - R^2/4", 2: "-(x+1)^2*10 + deg(atan2(y+0.5, x+1.5)) + max(1, 2*y, abs(x))"}
+    for k, expr in fn.items():
+        lines[1 + k] = lines[1 + k].rstrip() + '\t"' + expr + '"'
+    _write_fem(os.path.join(tmp, "tbmag.fem"), head + sep + "\n".join(lines))
+    return "tbmag"
+
+
 def case_tb30(tmp):
     """TorqueBenchmark with the rotor turned by 30 degrees (AGE shift path)."""
     t = open(os.path.join(SRC, "test", "TorqueBenchmark.fem"), newline="").read().replace("\r\n", "\n")
@@ -221,7 +234,7 @@ def case_tbhn(tmp):
     return "tbhn"
 
 
-CASES = {"tb": case_tb, "tb30": case_tb30, "temp1": case_temp1, "axi1": case_axi1, "sat2d": case_sat2d,
+CASES = {"tb": case_tb, "tbmag": case_tbmag, "tb30": case_tb30, "temp1": case_temp1, "axi1": case_axi1, "sat2d": case_sat2d,
          "harm2d": case_harm2d, "harmaxi": case_harmaxi, "tbh": case_tbh,
          "harm2dn": case_harm2dn, "harmaxin": case_harmaxin, "tbhn": case_tbhn}
 

@@ -23,7 +23,7 @@ def _solve(name, tmp_path, precond):
     return S
 
 
-@pytest.mark.parametrize("name", ["tb", "tb30"])
+@pytest.mark.parametrize("name", ["tb", "tb30", "tbmag"])
 @pytest.mark.parametrize("precond", [X.PRECOND_JACOBI, X.PRECOND_MCSSOR, X.PRECOND_AMG])
 def test_linear_planar_matches_reference(name, precond, tmp_path):
     ref, meta = load_ref(name)

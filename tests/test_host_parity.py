@@ -166,3 +166,40 @@ def test_layout_and_multigrid_setup_invariants(threads, tmp_path):
     for n in ("60", "33"):
         r = subprocess.run([exe, n], capture_output=True, text=True, env=dict(os.environ, XFEMM_HOST_THREADS=threads))
         assert r.returncode == 0 and r.stdout.strip() == "ok", r.stdout + r.stderr
+
+
+def test_magdir_expression_evaluator():
+    """MagDirFctn strings (the reference runs them through Lua 4.0 in radians mode, static2d.cpp:513-583,
+    liblua/lmathlib.cpp:24): operator precedence incl. right-associative ^ above unary minus, variables, functions;
+    anything outside the expression sublanguage is rejected with a message, never mis-evaluated."""
+    import ctypes, math
+    L = X.lib()
+
+    def ev(expr, x, y):
+        out = ctypes.c_double(0)
+        rc = L.xfemm_magdir_eval(expr.encode(), x, y, ctypes.byref(out))
+        return rc, out.value
+
+    rng = np.random.default_rng(5)
+    cases = [
+        ("theta", lambda x, y, th, R: th),
+        ("theta + 20*cos(3*theta*PI/180) - R^2/4", lambda x, y, th, R: th + 20 * math.cos(3 * th * math.pi / 180) - R ** 2 / 4),
+        ("-(x+1)^2*10 + deg(atan2(y+0.5, x+1.5)) + max(1, 2*y, abs(x))",
+         lambda x, y, th, R: -(x + 1) ** 2 * 10 + math.degrees(math.atan2(y + 0.5, x + 1.5)) + max(1, 2 * y, abs(x))),
+        ("-2^2", lambda *a: -4.0), ("2^3^2", lambda *a: 512.0), ("2^-1", lambda *a: 0.5), ("1-2-3", lambda *a: -4.0),
+        ("8/4/2", lambda *a: 1.0), ("r*z - x*y", lambda *a: 0.0), ("mod(theta+360, 90) + floor(R) + ceil(.5) + 1e1",
+                                                                 lambda x, y, th, R: math.fmod(th + 360, 90) + math.floor(R) + 1 + 10),
+        ("sqrt(x*x+y*y) - R", lambda *a: 0.0), ("min(3, 2, 5) + exp(0) + log(1) + log10(100) + rad(180)/PI + re(2) + im(2)",
+                                                lambda *a: 2 + 1 + 0 + 2 + 1 + 2 + 0),
+    ]
+    for expr, f in cases:
+        for _ in range(5):
+            x, y = rng.uniform(-3, 3, 2)
+            th, R = math.degrees(math.atan2(y, x)), math.hypot(x, y)
+            rc, v = ev(expr, x, y)
+            assert rc == 0, (expr, L.xfemm_last_error())
+            assert abs(v - f(x, y, th, R)) <= 1e-12 * max(1.0, abs(v)), (expr, v, f(x, y, th, R))
+    for bad in ["", "theta +", "foo", "sin()", "atan2(1)", "x = 3", "theta; 2", "(1", "1 2", "cos(1", "a.b", "'s'", "sqrt(-1)", "1/0"]:
+        rc, _ = ev(bad, 1.0, 2.0)
+        assert rc != 0, bad
+        assert L.xfemm_last_error()

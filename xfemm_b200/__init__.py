@@ -161,6 +161,7 @@ SIGNATURES = {
     "xfemm_fsolver_get_permutation": (C.c_int, [_P, _ip]),
     "xfemm_fsolver_get_pattern": (C.c_int, [_P, C.POINTER(C.c_longlong), _P, _P]),
     "xfemm_fsolver_get_system": (C.c_int, [_P, _P, _P]),
+    "xfemm_magdir_eval": (C.c_int, [C.c_char_p, C.c_double, C.c_double, C.POINTER(C.c_double)]),
     "xfemm_fsolver_get_side_matrix": (C.c_int, [_P, C.c_int, _P]),
     "xfemm_fsolver_get_solution": (C.c_int, [_P, _P, _P]),
     "xfemm_fsolver_get_mu": (C.c_int, [_P, _P]),

@@ -15,7 +15,7 @@ CLI = os.path.join(HERE, "fsolver_b200")
 CU = ["csrc/linprob.cu", "csrc/mag_assemble.cu", "csrc/clinprob.cu", "csrc/mag_harmonic.cu", "csrc/dist.cu", "csrc/amg.cu", "csrc/cnewton.cu"]
 CPP = ["csrc/layout.cpp", "host/pattern.cpp", "host/fsolver_io.cpp", "host/fsolver_solve.cpp", "host/fsolver_harmonic.cpp",
        "host/bh_curve.cpp", "host/age_matrix.cpp", "host/spars.cpp", "host/cspars.cpp",
-       "host/capi_fsolver.cpp"]
+       "host/capi_fsolver.cpp", "host/magdir_expr.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + os.environ.get("XFEMM_NVCC_EXTRA", "").split()

@@ -2,6 +2,7 @@
 // and mfemm/mexfsolver.cpp do with the reference class, exposed with plain C types so that
 // ctypes / MEX / Lua bindings (and this repo's tests and bench) can drive the same path.
 #include "fsolver.h"
+#include "magdir_expr.h"
 #include "../../include/xfemm_b200.h"
 #include <chrono>
 #include <cstdio>
@@ -234,6 +235,18 @@ int xfemm_fsolver_get_pattern(xfemm_fsolver *s, long long *nnz, int *rowptr, int
     if (nnz) *nnz = (long long)s->S.sysCol.size();
     if (rowptr) memcpy(rowptr, s->S.sysRowptr.data(), sizeof(int) * s->S.sysRowptr.size());
     if (colidx) memcpy(colidx, s->S.sysCol.data(), sizeof(int) * s->S.sysCol.size());
+    return XFEMM_OK;
+}
+
+int xfemm_magdir_eval(const char *expr, double x, double y, double *out)
+{
+    if (!expr || !out) { xb::set_error("expression and output pointer"); return XFEMM_ERR_ARG; }
+    xbhost::MagDirExpr e;
+    std::string err;
+    if (!e.compile(expr, err)) { xb::set_error("%s", err.c_str()); return XFEMM_ERR_ARG; }
+    const double PI_ = 3.141592653589793238462643383;
+    const xbhost::MagDirVars v = {x, y, atan2(y, x) * 180. / PI_, sqrt(x * x + y * y)};
+    if (!e.eval(v, *out)) { xb::set_error("\"%s\" does not evaluate to a numerical value", expr); return XFEMM_ERR_ARG; }
     return XFEMM_OK;
 }
 

@@ -8,6 +8,7 @@
 //   FSolver::Static2D                 cfemm/fsolver/static2d.cpp:53-1033
 //   FSolver::StaticAxisymmetric       cfemm/fsolver/staticaxi.cpp:45-794
 #include "fsolver.h"
+#include "magdir_expr.h"
 #include "../../include/xfemm_b200.h"
 #include "../csrc/layout.h"
 #include <algorithm>
@@ -331,13 +332,20 @@ int FSolver::staticSolve(CBigLinProb &L, bool axi)
         return false;
     }
     for (int i = 0; i < NumBlockLabels; i++) GetFillFactor(i);
+    // functional magnetisation directions: compiled once per label, evaluated per element below
+    // (the reference runs its Lua interpreter per element, static2d.cpp:513-583 / staticaxi.cpp:354-420)
+    std::vector<xbhost::MagDirExpr> magExpr(NumBlockLabels);
+    bool anyMagDirFctn = false;
     for (int i = 0; i < NumBlockLabels; i++)
         if (!labellist[i].MagDirFctn.empty())
         {
-            // the reference evaluates the expression per element with its embedded Lua
-            // interpreter (static2d.cpp:513-583), which is outside the accelerated path
-            WarnMessage("xfemm_b200: Lua magnetization direction functions are not supported\n");
-            return -7;
+            std::string err;
+            if (!magExpr[i].compile(labellist[i].MagDirFctn, err))
+            {
+                WarnMessage(("xfemm_b200: " + err + "\n").c_str());
+                return -7;
+            }
+            anyMagDirFctn = true;
         }
 
     // ---- circuits (static2d.cpp:84-167): area, conductance and source integrals per circuit
@@ -610,9 +618,33 @@ int FSolver::staticSolve(CBigLinProb &L, bool axi)
         prebuild = std::thread([lin, pc]() { xfemm_linprob_prebuild(lin, pc); });
     }
     struct JoinOnExit { FSolver *s; ~JoinOnExit() { s->joinPrebuild(); } } joinOnExit{this}; // never outlive `lin`
+    std::vector<double> magdirElem;
+    if (anyMagDirFctn)
+    {
+        magdirElem.resize(NumEls);
+        for (int i = 0; i < NumEls; i++)
+        {
+            const int lbl = meshele[i].lbl;
+            double t = labellist[lbl].MagDir;
+            if (!labellist[lbl].MagDirFctn.empty())
+            {
+                double cx = 0, cy = 0;
+                for (int j = 0; j < 3; j++) { cx += meshnode[meshele[i].p[j]].x; cy += meshnode[meshele[i].p[j]].y; }
+                cx = cx / units[LengthUnits] / 3.; cy = cy / units[LengthUnits] / 3.;
+                const xbhost::MagDirVars vars = {cx, cy, atan2(cy, cx) * 180. / PI, sqrt(cx * cx + cy * cy)};
+                if (!magExpr[lbl].eval(vars, t))
+                {
+                    WarnMessage(("\"" + labellist[lbl].MagDirFctn + "\" does not evaluate to a numerical value\n").c_str());
+                    return -7;
+                }
+            }
+            magdirElem[i] = t;
+        }
+    }
     xfemm_mag_desc D;
     memset(&D, 0, sizeof D);
     D.axisymmetric = axi ? 1 : 0;
+    D.magdir_elem = anyMagDirFctn ? magdirElem.data() : nullptr;
     D.n_nodes = NumNodes; D.n_elems = NumEls;
     D.xy = xy.data(); D.tri = tri.data();
     D.n_labels = NumBlockLabels; D.labels = labels.data();
