@@ -272,6 +272,8 @@ int xfemm_clinprob_relax(xfemm_clinprob *p, double relax);
 int xfemm_clinprob_enable_newton(xfemm_clinprob *p);
 int xfemm_clinprob_set_side_values(xfemm_clinprob *p, int k, const double *v);
 int xfemm_clinprob_get_side_values(xfemm_clinprob *p, int k, double *v);
+/* y = G x (conj_g = 0) or conj(G) x for one stored matrix, k = 0 (M), 1, 2, 3: MultA / MultConjA with a selector */
+int xfemm_clinprob_mult(xfemm_clinprob *p, int k, int conj_g, const double *x, double *y);
 /* y = M x + Mh x + Ms conj(x) + Ma x  (MultA(X,Y,-1)); host vectors of n complex */
 int xfemm_clinprob_mult_newton(xfemm_clinprob *p, const double *x, double *y);
 /* KludgeSolve: <= 10 COCG solves on M with the side terms on the right-hand side, each followed by a line search on

@@ -69,3 +69,44 @@ def test_host_assembled_problem_solves_on_gpu(precond, tmp_path):
     # fixed values come out of the iterative solve (spars.cpp:318 keeps the row), the last SetValue wins on node 0
     assert abs(v1[0] - 0.5) < 1e-9 and abs(v1[5 * N] - 0.5) < 1e-9
     print(precond, r.stderr.strip(), "oracle iterations", it1, it2)
+
+
+def _sections(text):
+    out, cur = [], None
+    for ln in text.splitlines():
+        if ln.startswith("#"):
+            cur = [ln[2:], []]
+            out.append(cur)
+        elif ln.strip():
+            re_, im_ = ln.split()
+            cur[1].append(complex(float(re_), float(im_)))
+    return [(t, np.array(v)) for t, v in out]
+
+
+@pytest.mark.parametrize("newton", [0, 1])
+def test_complex_facade_host_assembly_matches_the_reference_class(newton, tmp_path):
+    """CBigComplexLinProb through Put/Get/AddTo (selector k), SetValue, Periodicity/AntiPeriodicity, MultA/MultConjA and
+    PBCGSolveMod: tests/cfacade_driver.cpp built against this repo's facade (GPU) and, by oracle/Makefile, against the
+    unmodified reference class (oracle/_ref/cfacade_ref, CPU).  newton=1 adds side matrices, so that the boundary
+    conditions act on them and PBCGSolveMod dispatches to KludgeSolve."""
+    ref_exe = os.path.join(ROOT, "oracle", "_ref", "cfacade_ref")
+    if not os.path.exists(ref_exe):
+        pytest.skip("oracle/_ref/cfacade_ref not built (run make -C oracle where /root/reference is available)")
+    exe = str(tmp_path / "cfacade_driver")
+    host = os.path.join(ROOT, "xfemm_b200", "host")
+    libdir = os.path.join(ROOT, "xfemm_b200")
+    r = subprocess.run(["g++", "-std=c++14", "-O1", "-I" + host, os.path.join(ROOT, "tests", "cfacade_driver.cpp"), "-o", exe,
+                        "-L" + libdir, "-lxfemm_b200", "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    N = 16
+    mine = subprocess.run([exe, str(N), str(newton)], capture_output=True, text=True)
+    assert mine.returncode == 0, mine.stdout[-300:] + mine.stderr[-2000:]
+    theirs = subprocess.run([ref_exe, str(N), str(newton)], capture_output=True, text=True)
+    assert theirs.returncode == 0, theirs.stderr[-2000:]
+    a, b = _sections(mine.stdout), _sections(theirs.stdout)
+    assert [t for t, _ in a] == [t for t, _ in b] and len(a) == (9 if newton else 4)
+    for (tag, va), (_, vb) in zip(a, b):
+        assert len(va) == len(vb) == N * N + 2
+        err = np.linalg.norm(va - vb) / np.linalg.norm(vb)
+        print(tag, "rel err", err)
+        assert err <= (1e-7 if tag.startswith("V") else 1e-13), tag

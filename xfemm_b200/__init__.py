@@ -119,6 +119,7 @@ SIGNATURES = {
     "xfemm_clinprob_set_side_values": (C.c_int, [_P, C.c_int, _P]),
     "xfemm_clinprob_get_side_values": (C.c_int, [_P, C.c_int, _P]),
     "xfemm_clinprob_mult_newton": (C.c_int, [_P, _P, _P]),
+    "xfemm_clinprob_mult": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
     "xfemm_clinprob_kludge_solve": (C.c_int, [_P, C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(SolveInfo)]),
     "xfemm_cmag_create": (C.c_int, [_P, _P, C.POINTER(_P)]),
     "xfemm_cmag_destroy": (C.c_int, [_P]),
