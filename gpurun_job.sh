@@ -1,2 +1,2 @@
 cd /root/repo
-timeout 900 python -m pytest tests/test_gpu_sibling_solvers.py -m gpu -x -q -s 2>&1 | tail -12
+timeout 900 python -m pytest tests/test_gpu_femmcli.py -m gpu -x -q -s 2>&1 | tail -20

@@ -72,7 +72,11 @@ def build(force=False, verbose=False):
             print(o)
     if jobs or not os.path.exists(LIB):
         _run([NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
-             "-Xcompiler", "-fPIC", "-lcudart_static", "-lpthread", "-ldl", "-lrt"], os.path.join(BUILD, "link.log"))
+             "-Xcompiler", "-fPIC", "-lcudart_static", "-lpthread", "-ldl", "-lrt",
+             # -Bsymbolic: references inside the library bind to its own definitions.  A host program may define
+             # classes of the same names (the reference's FSolver / CBigLinProb live next to this library in
+             # oracle/_ref/femmcli_b200); without it the dynamic linker would route our internal calls to them.
+             "-Xlinker", "-Bsymbolic"], os.path.join(BUILD, "link.log"))
     main_src = os.path.join(HERE, "host", "main.cpp")
     if jobs or _newer(main_src, hdrs, CLI):
         _run(["g++"] + CXX_FLAGS + [main_src, "-o", CLI, "-L" + HERE, "-lxfemm_b200",
