@@ -818,6 +818,8 @@ int xfemm_clinprob_cocg(xfemm_clinprob *p, double precision, int warm, int preco
     XB_CUDA(cudaEventRecord(e0, st));
     int rc = cbuild_layout(p, precond == XFEMM_PRECOND_AMG ? XFEMM_PRECOND_JACOBI : precond); // AMG: the uncoloured layout
     if (rc != XFEMM_OK) return rc;
+    // values unchanged since the previous call (the inner solves of KludgeSolve): keep everything prepared then
+    const bool reuse = p->keep_prepared && p->prepared_precond == precond && (precond != XFEMM_PRECOND_AMG || p->re_prec);
     AmgArgs g;
     double prec_sign = 1.0;
     if (precond == XFEMM_PRECOND_AMG)
@@ -844,31 +846,40 @@ int xfemm_clinprob_cocg(xfemm_clinprob *p, double precision, int warm, int preco
             XB_CUDA(p->re_src.upload(src.data(), src.size(), st));
         }
         xfemm_linprob *R = p->re_prec;
-        int *d_cnt = (int *)(p->d_mail.p + 12);
-        int h_cnt[4] = {0, 0, 0, 0};
-        XB_CUDA(cudaMemsetAsync(d_cnt, 0, 4 * sizeof(int), st));
-        ++g_launch, kc_diag_sign<<<(p->n_nodes + 255) / 256, 256, 0, st>>>(p->n_nodes, p->rowptr.p, p->col.p, p->vals.p, d_cnt);
-        XB_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
-        XB_CUDA(cudaStreamSynchronize(st));
-        prec_sign = h_cnt[1] > h_cnt[0] ? -1.0 : 1.0;
-        double im_sign = h_cnt[3] > h_cnt[2] ? -1.0 : 1.0;
-        if (const char *e = getenv("XFEMM_COMPLEX_AMG_REAL_ONLY")) if (atoi(e)) im_sign = 0.0;
-        ++g_launch, kc_fill_real<<<(p->n + 255) / 256, 256, 0, st>>>(p->n, p->n_nodes, R->rowptr.p, R->col.p, p->re_src.p, p->vals.p,
-                                                                      R->vals.p, prec_sign, im_sign);
-        XB_CUDA(cudaStreamSynchronize(st)); // the companion works on its own stream
-        rc = linprob_prepare(R, XFEMM_PRECOND_AMG);
-        if (rc != XFEMM_OK) return rc;
-        XB_CUDA(cudaStreamSynchronize(R->stream));
-        if (R->lay.n_pad != p->lay.n_pad || R->lay.i2c != p->lay.i2c)
+        if (reuse) prec_sign = p->prepared_sign;
+        else
         {
-            set_error("internal row orders of the complex problem and its real companion differ");
-            return XFEMM_ERR_ARG;
+            int *d_cnt = (int *)(p->d_mail.p + 12);
+            int h_cnt[4] = {0, 0, 0, 0};
+            XB_CUDA(cudaMemsetAsync(d_cnt, 0, 4 * sizeof(int), st));
+            ++g_launch, kc_diag_sign<<<(p->n_nodes + 255) / 256, 256, 0, st>>>(p->n_nodes, p->rowptr.p, p->col.p, p->vals.p, d_cnt);
+            XB_CUDA(cudaMemcpyAsync(h_cnt, d_cnt, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+            XB_CUDA(cudaStreamSynchronize(st));
+            prec_sign = h_cnt[1] > h_cnt[0] ? -1.0 : 1.0;
+            double im_sign = h_cnt[3] > h_cnt[2] ? -1.0 : 1.0;
+            if (const char *e = getenv("XFEMM_COMPLEX_AMG_REAL_ONLY")) if (atoi(e)) im_sign = 0.0;
+            ++g_launch, kc_fill_real<<<(p->n + 255) / 256, 256, 0, st>>>(p->n, p->n_nodes, R->rowptr.p, R->col.p, p->re_src.p, p->vals.p,
+                                                                          R->vals.p, prec_sign, im_sign);
+            XB_CUDA(cudaStreamSynchronize(st)); // the companion works on its own stream
+            rc = linprob_prepare(R, XFEMM_PRECOND_AMG);
+            if (rc != XFEMM_OK) return rc;
+            XB_CUDA(cudaStreamSynchronize(R->stream));
+            if (R->lay.n_pad != p->lay.n_pad || R->lay.i2c != p->lay.i2c)
+            {
+                set_error("internal row orders of the complex problem and its real companion differ");
+                return XFEMM_ERR_ARG;
+            }
         }
         amg_fill_args(R, *R->amg, g);
     }
     int singular = -1;
-    rc = crefresh_values(p, &singular);
-    if (rc != XFEMM_OK) return rc;
+    if (!reuse)
+    {
+        p->prepared_precond = -1;
+        rc = crefresh_values(p, &singular);
+        if (rc != XFEMM_OK) return rc;
+        if (singular < 0) { p->prepared_precond = precond; p->prepared_sign = prec_sign; }
+    }
     xfemm_solve_info local;
     memset(&local, 0, sizeof local);
     local.precond = precond;

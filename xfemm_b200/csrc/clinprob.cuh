@@ -42,6 +42,11 @@ struct xfemm_clinprob
     // Newton AC solver ([ACSolver]=1): the side matrices Mh (Hermitian), Ms (complex symmetric) and Ma
     // (anti-Hermitian) of cspars.h:53-55, on the same full CSR pattern as `vals`; empty until
     // xfemm_clinprob_enable_newton.  Wipe, Dirichlet and periodic conditions then act on them too (cnewton.cu).
+    // KludgeSolve calls the COCG solver up to ten times on unchanged matrix values: while keep_prepared is set the
+    // solver representation and the multigrid hierarchy prepared for `prepared_precond` are reused as they are
+    bool keep_prepared = false;
+    int prepared_precond = -1;
+    double prepared_sign = 1.0;
     bool newton = false;
     xb::DevBuf<cd> vals_h, vals_s, vals_a;
     xb::DevBuf<int> pbc_ij;          // per periodic pair: slot(i,j), slot(j,i)

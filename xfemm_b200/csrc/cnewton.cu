@@ -378,6 +378,10 @@ int xfemm_clinprob_kludge_solve(xfemm_clinprob *p, double precision, int warm, i
     double er = normb2 > 0 ? sqrt(rr / normb2) : 0.0;
     total.relres = er;
     if (er < precision || normb2 == 0.0) return finish(XFEMM_OK);
+    // the matrix does not change between the inner solves: the first one prepares the solver representation and the
+    // multigrid hierarchy, the others reuse them
+    struct KeepPrepared { xfemm_clinprob *p; ~KeepPrepared() { p->keep_prepared = false; } } keep{p};
+    p->keep_prepared = false;
     for (int k = 0; k < 10; k++)
     {
         // b = borig - (Mh V + Ms conj(V) + Ma V)
@@ -393,6 +397,7 @@ int xfemm_clinprob_kludge_solve(xfemm_clinprob *p, double precision, int warm, i
         total.iterations += inner.iterations;
         total.colors = inner.colors;
         if (rc != XFEMM_OK) return finish(rc);
+        p->keep_prepared = true;
         // step length along the new direction that reduces the full residual the most
         ++g_launch, kn_sub<<<nb, 256, 0, st>>>(n, p->V.p, p->nk_v.p, p->nk_p.p);
         if ((rc = nmult(p, true, p->nk_p.p, p->nk_u.p)) != XFEMM_OK) return finish(rc);
