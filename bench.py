@@ -383,6 +383,9 @@ def main():
     def position(i):
         return float((rank * (360 // world) + i) % 360)
 
+    # headline steps: the whole per-problem path every time (assembly of all elements, Dirichlet, periodic pairs, solve);
+    # the library's sweep mode that keeps the position-independent part on the device is timed separately below
+    S.set_option("cache_static_part", 0)
     for i in range(args.warmup):
         S.set_rotor_angle(position(i))
         S.resolve()
@@ -414,17 +417,24 @@ def main():
     torque_only = None
     if rank == 0 and world == 1 and c["n_age"] > 0:
         S.set_option("fetch_solution", 0)
+        S.set_option("cache_static_part", 1)  # library default for sweeps: only the air-gap blocks are re-assembled
+        S.set_rotor_angle(position(args.warmup + args.steps))  # the sweep goes on; this position takes the device copy
+        S.resolve()                                            # of the boundary-conditioned static part (untimed)
         tq = []
         sync()
         t1 = time.perf_counter()
         for i in range(args.steps):
-            S.set_rotor_angle(position(args.warmup + args.steps + i))  # the sweep goes on
+            S.set_rotor_angle(position(args.warmup + args.steps + 1 + i))
             S.resolve()
             tq.append(S.gap_torque(0))
         sync()
         torque_only = {"s_per_position": (time.perf_counter() - t1) / args.steps, "torque_Nm": tq,
-                       "positions_deg": [position(args.warmup + args.steps + i) for i in range(args.steps)]}
+                       "note": "nodal values stay on the device (torque reduced there) and the position-independent, "
+                               "boundary-conditioned part of the system is restored from a device copy: only the air-gap "
+                               "blocks are assembled per position",
+                       "positions_deg": [position(args.warmup + args.steps + 1 + i) for i in range(args.steps)]}
         S.set_option("fetch_solution", 1)
+        S.set_option("cache_static_part", 0)
         # the same problem solved from a zero initial guess (what a stand-alone solve of one position costs)
         S.set_option("warm_resolve", 0)
         S.resolve()

@@ -78,6 +78,10 @@ int xfemm_linprob_n(const xfemm_linprob *p);
 int xfemm_linprob_get_pattern(xfemm_linprob *p, int *rowptr, int *colidx); /* host copy of the CSR pattern; either may be NULL */
 long long xfemm_linprob_nnz(const xfemm_linprob *p);
 int xfemm_linprob_wipe(xfemm_linprob *p);                               /* spars.cpp:348 Wipe  */
+/* device-side copy of the values and the right-hand side (after boundary conditions) and its restore: the
+ * position-independent part of a sweep is assembled once (FSolver, option age_union_pattern) */
+int xfemm_linprob_snapshot(xfemm_linprob *p);
+int xfemm_linprob_restore(xfemm_linprob *p);
 int xfemm_linprob_set_values(xfemm_linprob *p, const double *vals_csr); /* H2D, CSR order      */
 int xfemm_linprob_get_values(xfemm_linprob *p, double *vals_csr);       /* D2H                 */
 int xfemm_linprob_set_rhs(xfemm_linprob *p, const double *b);
@@ -217,6 +221,9 @@ int xfemm_mag_set_age(xfemm_mag *m, int n_age_cells, const int *age_nodes, const
  * solution, looks up nu(B), dnu/dB^2 and adds the Newton term (static2d.cpp:683-805).
  * elapsed_ms (optional) receives the CUDA-event time. */
 int xfemm_mag_assemble_static(xfemm_mag *m, int iter, double *elapsed_ms);
+/* the same in two parts: 1 = everything that does not depend on the rotor position (wipes first), 2 = the air-gap
+ * element blocks added to the current values; 3 = both (= xfemm_mag_assemble_static) */
+int xfemm_mag_assemble_static_parts(xfemm_mag *m, int iter, int parts, double *elapsed_ms);
 /* element permeabilities of the last assembly pass (n_elems*2: mu1, mu2) */
 int xfemm_mag_get_mu(xfemm_mag *m, double *mu12);
 /* Newton bookkeeping on the device (static2d.cpp:953-989): saves V_old, returns
@@ -382,7 +389,10 @@ int xfemm_fsolver_resolve(xfemm_fsolver *s);
  * Other options of xfemm_fsolver_set_option: "fetch_solution" = 0 (leave V and A on the device after a
  * solve), "assemble_only" = 1 (stop after assembly + boundary conditions), "locality_order" = 1/0/-1
  * (Z-curve row order inside the solver; -1 = only when the problem is going to be re-solved),
- * "warm_resolve" = 0 (xfemm_fsolver_resolve starts from zero instead of the solution left on the device). */
+ * "warm_resolve" = 0 (xfemm_fsolver_resolve starts from zero instead of the solution left on the device),
+ * "cache_static_part" = 0 (re-assemble and re-condition everything at every position; by default a linear problem
+ * solved with "age_union_pattern" keeps its position-independent, boundary-conditioned part on the device and a
+ * position only adds its air-gap blocks — used when no air-gap node is a fixed or periodic node). */
 int xfemm_fsolver_set_rotor_angle(xfemm_fsolver *s, int age_index, double inner_angle_deg, double outer_angle_deg);
 /* torque [N m] through air-gap element `age_index` from the resident magnetostatic solution
  * (= mo_gapintegral(name,0) of the reference's post-processor on the written .ans) */

@@ -56,6 +56,8 @@ SIGNATURES = {
     "xfemm_linprob_n": (C.c_int, [_P]),
     "xfemm_linprob_nnz": (C.c_longlong, [_P]),
     "xfemm_linprob_wipe": (C.c_int, [_P]),
+    "xfemm_linprob_snapshot": (C.c_int, [_P]),
+    "xfemm_linprob_restore": (C.c_int, [_P]),
     "xfemm_linprob_set_values": (C.c_int, [_P, _dp]),
     "xfemm_linprob_get_values": (C.c_int, [_P, _dp]),
     "xfemm_linprob_set_rhs": (C.c_int, [_P, _dp]),
@@ -91,6 +93,7 @@ SIGNATURES = {
     "xfemm_mag_set_labels": (C.c_int, [_P, C.c_int, _P]),
     "xfemm_mag_set_age": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, _P]),
     "xfemm_mag_assemble_static": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double)]),
+    "xfemm_mag_assemble_static_parts": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "xfemm_mag_get_mu": (C.c_int, [_P, _dp]),
     "xfemm_mag_solution_to_A": (C.c_int, [_P, _dp]),
     "xfemm_mag_gap_torque": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,

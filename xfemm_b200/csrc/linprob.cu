@@ -965,7 +965,26 @@ int xfemm_linprob_wipe(xfemm_linprob *p)
     return XFEMM_OK;
 }
 
-#define XB_COPY_IN(buf, src, cnt)                                                                        \
+// values + right-hand side as they are now (after the boundary conditions) kept on the device / put back
+int xfemm_linprob_snapshot(xfemm_linprob *p)
+{
+    XB_ARG(p, "null handle");
+    XB_CUDA(p->snap_vals.alloc((size_t)p->nnz));
+    XB_CUDA(p->snap_b.alloc((size_t)p->n));
+    XB_CUDA(cudaMemcpyAsync(p->snap_vals.p, p->vals.p, (size_t)p->nnz * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    XB_CUDA(cudaMemcpyAsync(p->snap_b.p, p->b.p, (size_t)p->n * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    return XFEMM_OK;
+}
+int xfemm_linprob_restore(xfemm_linprob *p)
+{
+    XB_ARG(p, "null handle");
+    XB_ARG((long long)p->snap_vals.n == p->nnz && (int)p->snap_b.n == p->n, "no snapshot taken on this problem");
+    XB_CUDA(cudaMemcpyAsync(p->vals.p, p->snap_vals.p, (size_t)p->nnz * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    XB_CUDA(cudaMemcpyAsync(p->b.p, p->snap_b.p, (size_t)p->n * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    return XFEMM_OK;
+}
+
+#define XB_COPY_IN(buf, src, cnt)                                                                       \
     XB_ARG(p && (src), "null pointer");                                                                    \
     xb::g_h2d_bytes += (long long)(cnt) * 8;                                                               \
     XB_CUDA(cudaMemcpyAsync((buf).p, (src), (size_t)(cnt) * sizeof(double), cudaMemcpyHostToDevice, p->stream)); \

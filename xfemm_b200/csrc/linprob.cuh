@@ -33,6 +33,7 @@ struct xfemm_linprob
     std::vector<int> forced_order; // optional: the internal row order to use as is (a companion of another problem)
     xb::DevBuf<int> rowptr, col;
     xb::DevBuf<double> vals, b, V, Vold;
+    xb::DevBuf<double> snap_vals, snap_b; // xfemm_linprob_snapshot: boundary-conditioned values + RHS to restore from
 
     // solver representation
     xb::SellLayout lay;            // host copy (small vectors kept; big ones cleared after upload)

@@ -668,22 +668,36 @@ int xfemm_mag_destroy(xfemm_mag *m)
 
 int xfemm_mag_assemble_static(xfemm_mag *m, int iter, double *elapsed_ms)
 {
+    return xfemm_mag_assemble_static_parts(m, iter, 3, elapsed_ms);
+}
+
+// parts: bit 0 = wipe + elements + mixed sides + point sources (everything that does not depend on the rotor
+// position), bit 1 = the air-gap element blocks, added to whatever the value array holds.  A sweep on a linear
+// problem assembles and boundary-conditions bit 0 once, keeps a snapshot (xfemm_linprob_snapshot) and afterwards
+// only restores it and adds bit 1 for each position.
+int xfemm_mag_assemble_static_parts(xfemm_mag *m, int iter, int parts, double *elapsed_ms)
+{
     XB_ARG(m && m->lin, "null handle");
+    XB_ARG(parts >= 1 && parts <= 3, "parts is a mask of 1 (position-independent part) and 2 (air-gap blocks)");
     xfemm_linprob *L = m->lin;
     cudaStream_t st = L->stream;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (elapsed_ms) { XB_CUDA(cudaEventCreate(&e0)); XB_CUDA(cudaEventCreate(&e1)); XB_CUDA(cudaEventRecord(e0, st)); }
     // Wipe (static2d.cpp:186-189); on iter 0 the caller hands over a fresh problem, wiping is harmless
-    XB_CUDA(L->vals.zero(st));
-    XB_CUDA(L->b.zero(st));
+    if (parts & 1)
+    {
+        XB_CUDA(L->vals.zero(st));
+        XB_CUDA(L->b.zero(st));
+    }
     XB_CUDA(m->err_flag.zero(st));
-    if (m->n_age_cells > 0)
+    if ((parts & 2) && m->n_age_cells > 0)
     {
         int nt = m->n_age_cells * 55;
         ++xb::g_launch, k_age_scatter<<<(nt + 127) / 128, 128, 0, st>>>(m->n_age_cells, m->age_nodes.p, m->age_w.p, m->age_mid.p,
                                                         m->age_mats.p, L->rowptr.p, L->col.p, L->vals.p, 1.0, m->err_flag.p);
     }
-    if (m->axisymmetric)
+    if (!(parts & 1)) { /* air-gap blocks only */ }
+    else if (m->axisymmetric)
         ++xb::g_launch, k_assemble_staticaxi<<<(m->n_elems + 255) / 256, 256, 0, st>>>(
             m->n_elems, iter, (const int4 *)m->tri.p, (const double2 *)m->xy.p, m->emap.p, m->labels.p,
             m->magdir.n ? m->magdir.p : nullptr, m->bhB.p, m->bhH.p, m->bhS.p, L->V.p, L->vals.p, L->b.p,
@@ -692,11 +706,11 @@ int xfemm_mag_assemble_static(xfemm_mag *m, int iter, double *elapsed_ms)
         ++xb::g_launch, k_assemble_static2d<<<(m->n_elems + 255) / 256, 256, 0, st>>>(
             m->n_elems, iter, (const int4 *)m->tri.p, (const double2 *)m->xy.p, m->emap.p, m->labels.p,
             m->magdir.n ? m->magdir.p : nullptr, m->bhB.p, m->bhH.p, m->bhS.p, L->V.p, L->vals.p, L->b.p, (double2 *)m->mu.p);
-    if (m->n_mixed > 0)
+    if ((parts & 1) && m->n_mixed > 0)
         ++xb::g_launch, k_mixed_edges<<<(m->n_mixed + 127) / 128, 128, 0, st>>>(m->n_mixed, m->n_elems, m->mixed_es.p, m->mixed_c.p,
                                                                 (const int4 *)m->tri.p, (const double2 *)m->xy.p,
                                                                 m->emap.p, L->vals.p, L->b.p, m->axisymmetric);
-    if (m->n_psrc > 0)
+    if ((parts & 1) && m->n_psrc > 0)
         ++xb::g_launch, k_point_sources<<<(m->n_psrc + 127) / 128, 128, 0, st>>>(m->n_psrc, m->psrc_node.p, m->psrc_val.p, L->b.p);
     int flag = 0;
     XB_CUDA(cudaMemcpyAsync(&flag, m->err_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -260,11 +260,15 @@ public:
         std::vector<int> dirNodes, pbcI, pbcJ, pbcT;
         std::vector<double> dirFirst, dirLast, labelJsrc;
         bool linear = true, ready = false, ageDirty = false;
+        // sweeps on a linear problem: the position-independent part (elements, sides, sources, all boundary
+        // conditions) is assembled once and kept on the device; a position restores it and adds its air-gap blocks
+        bool staticPartUsable = false, staticPartCached = false;
     } plan;
     std::vector<double> jprevByLabel; // per-label source current accumulated over the solves (added to Jprev on write)
     bool warmResolve;            // a re-solve on the resident problem starts from the solution it finds there (default true)
     bool resolveStart;           // set for the duration of such a re-solve
     bool extrapolateResolve;     // ... from the linear extrapolation of the last two solutions (equidistant sweeps; default true)
+    bool cacheStaticPart;        // sweeps on linear problems keep the position-independent, boundary-conditioned part on the device (default true)
     bool fetchSolution;          // copy V and A back to the host after a solve (default true; sweeps that only need torque switch it off)
     bool gapTorque(int ageIndex, double &torque); // from the resident solution, = fpproc's gap integral 0
     std::thread prebuild;        // host thread building the solver structure while the first assembly runs

@@ -116,6 +116,7 @@ FSolver::FSolver()
     assembleOnly = false;
     localityOrder = -1;
     fetchSolution = true;
+    cacheStaticPart = true;
     warmResolve = true;
     resolveStart = false;
     extrapolateResolve = true;

@@ -666,6 +666,21 @@ int FSolver::staticSolve(CBigLinProb &L, bool axi)
     for (int l = 0; l < NumBlockLabels; l++) plan.labelJsrc[l] = labels[l].Jsrc;
     plan.linear = LinearFlag;
     plan.ready = true;
+    // The boundary-condition operators are linear in the matrix and only touch entries in the rows/columns of
+    // fixed and periodic nodes.  When no air-gap node is one of those, BC(A_static + A_gap) = BC(A_static) + A_gap:
+    // the static part can be kept (option age_union_pattern = the problem will be re-solved for other positions).
+    plan.staticPartCached = false;
+    plan.staticPartUsable = false;
+    if (LinearFlag && ageUnionPattern && !ageMid.empty() && !keepSystem && !assembleOnly && !getenv("XFEMM_NO_STATIC_CACHE"))
+    {
+        std::vector<unsigned char> bcNode(NumNodes, 0);
+        for (int nd : dirNodes) bcNode[nd] = 1;
+        for (int k = 0; k < NumPBCs; k++) { bcNode[pbcI[k]] = 1; bcNode[pbcJ[k]] = 1; }
+        bool disjoint = true;
+        for (int nd : ageNodes) // 10 per air-gap cell; every ring node appears in some cell at any rotor position
+            if (nd >= 0 && nd < NumNodes && bcNode[nd]) { disjoint = false; break; }
+        plan.staticPartUsable = disjoint;
+    }
     t0 = wall();
     const int ok = staticNewton(L);
     if (getenv("XFEMM_TIMING"))
@@ -711,16 +726,41 @@ int FSolver::staticNewton(CBigLinProb &L)
     do
     {
         PrintMessage("Matrix Construction\n");
-        double ms_asm = 0;
-        if (xfemm_mag_assemble_static(magdev, Iter, &ms_asm) != XFEMM_OK) { WarnMessage(xfemm_last_error()); return false; }
+        double ms_asm = 0, ms_gap = 0;
         double tb = wall();
-        if (xfemm_linprob_dirichlet(lin, (int)plan.dirNodes.size(), plan.dirNodes.data(), plan.dirFirst.data(), plan.dirLast.data(), L.bdw) != XFEMM_OK ||
-            xfemm_linprob_periodic(lin, NumPBCs, plan.pbcI.data(), plan.pbcJ.data(), plan.pbcT.data()) != XFEMM_OK)
+        const bool cacheStatic = plan.staticPartUsable && cacheStaticPart;
+        if (cacheStatic && plan.staticPartCached)
         {
-            WarnMessage(xfemm_last_error());
-            return false;
+            // next position of a sweep: boundary-conditioned static part back from its device copy + this position's
+            // air-gap blocks
+            if (xfemm_linprob_restore(lin) != XFEMM_OK || xfemm_mag_assemble_static_parts(magdev, Iter, 2, &ms_gap) != XFEMM_OK)
+            {
+                WarnMessage(xfemm_last_error());
+                return false;
+            }
         }
-        stats.assemble_ms.push_back(ms_asm + (wall() - tb) * 1e3);
+        else
+        {
+            const int parts = cacheStatic ? 1 : 3;
+            if (xfemm_mag_assemble_static_parts(magdev, Iter, parts, &ms_asm) != XFEMM_OK) { WarnMessage(xfemm_last_error()); return false; }
+            tb = wall();
+            if (xfemm_linprob_dirichlet(lin, (int)plan.dirNodes.size(), plan.dirNodes.data(), plan.dirFirst.data(), plan.dirLast.data(), L.bdw) != XFEMM_OK ||
+                xfemm_linprob_periodic(lin, NumPBCs, plan.pbcI.data(), plan.pbcJ.data(), plan.pbcT.data()) != XFEMM_OK)
+            {
+                WarnMessage(xfemm_last_error());
+                return false;
+            }
+            if (cacheStatic)
+            {
+                if (xfemm_linprob_snapshot(lin) != XFEMM_OK || xfemm_mag_assemble_static_parts(magdev, Iter, 2, &ms_gap) != XFEMM_OK)
+                {
+                    WarnMessage(xfemm_last_error());
+                    return false;
+                }
+                plan.staticPartCached = true;
+            }
+        }
+        stats.assemble_ms.push_back(ms_asm + ms_gap + (wall() - tb) * 1e3);
         if (keepSystem)
         {
             // snapshot for the parity tests, pruned to the entries the reference's linked lists hold
