@@ -119,3 +119,31 @@ def test_torque_only_sweep_leaves_nodal_values_on_device(tmp_path):
     assert d2h.value < 5 * 64 * 1024  # scalars, flags and the 2x96 flux densities only
     for angle, t in zip((0.0, 10.0, 30.0, 60.0, 90.0), tq):
         assert abs(t - math.sin(math.radians(angle))) <= 0.000042 + 2e-4 * abs(math.sin(math.radians(angle))), (angle, t)
+
+
+def test_cached_static_part_gives_the_same_systems_and_answers(tmp_path):
+    """Sweep mode (default with age_union_pattern on a linear problem): the boundary-conditioned, position-independent
+    part of the system is restored from a device copy and only the air-gap blocks are assembled per position.  Same
+    nodal solution and torque as re-assembling and re-conditioning everything (option cache_static_part = 0)."""
+    out = {}
+    for cache in (1, 0):
+        d = tmp_path / str(cache)
+        d.mkdir()
+        S = X.FSolver(stage_case("tb", str(d)))
+        S.set_option("age_union_pattern", 1)
+        S.set_option("cache_static_part", cache)
+        S.load_mesh(False)
+        S.renumber(False)
+        S.solve()
+        res = []
+        for deg in (7.0, 30.0, 123.0):
+            S.set_rotor_angle(deg)
+            S.resolve()
+            res.append((S.solution()[1].copy(), S.gap_torque(0), sum(S.stats()["assemble_ms"])))
+        out[cache] = res
+        S.close()
+    for (a1, t1, ms1), (a0, t0, ms0) in zip(out[1], out[0]):
+        assert rel_l2(a1, a0) <= 1e-9
+        assert abs(t1 - t0) <= 1e-9 * max(1.0, abs(t0))
+    ref30, _ = load_ref("tb30")
+    assert rel_l2(out[1][1][0], ref30["A"]) <= 1e-6
