@@ -1,6 +1,7 @@
 // Host side of the aggregation-multigrid preconditioner (see amg.cuh): hierarchy construction from
 // the sparsity pattern (once per pattern) and the per-solve Galerkin value refresh on the device.
 #include "amg.cuh"
+#include "amg2.cuh"
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -416,6 +417,22 @@ void amg_fill_args(xfemm_linprob *fine, AmgHierarchy &h, AmgArgs &g)
         g.lev[l].agg = h.xfer[l]->agg.p;
         g.lev[l].mptr = h.xfer[l]->mptr.p;
         g.lev[l].mem = h.xfer[l]->mem.p;
+    }
+}
+
+// vectors of the second right-hand side (amg2.cuh): the work vectors of each level's problem that the first
+// component leaves unused.  `fine` = the real companion of a complex problem: none of its own vectors is in use.
+void amg_fill_args2(xfemm_linprob *fine, AmgHierarchy &h, AmgArgs2 &g2)
+{
+    g2.lev[0].b = fine->bint.p;
+    g2.lev[0].x = fine->x.p;
+    g2.lev[0].t = fine->u.p;
+    for (size_t l = 0; l < h.coarse.size(); l++)
+    {
+        xfemm_linprob *c = h.coarse[l];
+        g2.lev[l + 1].x = c->p.p;
+        g2.lev[l + 1].b = c->r.p;
+        g2.lev[l + 1].t = c->z.p;
     }
 }
 

@@ -7,6 +7,7 @@
 // three CG steps on the normal equations of the preconditioned system (PCGSQStart, cspars.cpp:764-819).
 #include "clinprob.cuh"
 #include "amg.cuh"
+#include "amg2.cuh"
 #include <complex>
 #include <cooperative_groups.h>
 #include <algorithm>
@@ -205,40 +206,37 @@ __device__ __forceinline__ int cnext_slice(int *ctr, int lane)
 
 // z = M^-1 r ; returns this thread's partial of the unconjugated z.r
 template <int PRECOND>
-__device__ __forceinline__ cd cprecond_apply(const CocgArgs &a, const AmgArgs &g, cg::grid_group &grid, int r0, int r1,
-                                             int warp_g, int nwarps_g, int lane, int *s_next, const int *s_wk, StageSmem *S)
+__device__ __forceinline__ cd cprecond_apply(const CocgArgs &a, const AmgArgs &g, const AmgArgs2 &g2, cg::grid_group &grid, int r0,
+                                             int r1, int warp_g, int nwarps_g, int lane, int *s_next, const int *s_wk, StageSmem *S)
 {
     cd dot = make_double2(0., 0.);
     if (PRECOND == XFEMM_PRECOND_AMG)
     {
-        // Multigrid V-cycle of the REAL part of the matrix (stiffness: symmetric positive definite), applied to
-        // the real and the imaginary part of r in turn.  A real symmetric M keeps the preconditioned operator
-        // complex symmetric, which is all COCG needs; the eddy-current term j*omega*sigma*mass is a bounded
-        // perturbation of the stiffness that the Krylov iteration absorbs.
+        // Multigrid V-cycle of the REAL matrix P = |Re A| + |Im A| between mesh nodes (stiffness + omega*sigma*mass,
+        // symmetric positive definite; kc_fill_real), applied to the real and the imaginary part of r — both in ONE
+        // cycle (amg2.cuh).  A real symmetric M keeps the preconditioned operator complex symmetric, which is all
+        // COCG needs.
         const AmgLev &L0 = g.lev[0];
-        for (int comp = 0; comp < 2; comp++)
-        {
-            for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x)
-            {
-                // circuit unknowns enter the cycle with a zero residual: their identity rows sit inside aggregates,
-                // and a residual restricted from them (while their own z is replaced below) would make M unsymmetric
-                const double bi = a.i2c[i] >= a.n_nodes ? 0.0 : (comp ? a.r[i].y : a.r[i].x);
-                L0.b[i] = bi;
-                L0.x[i] = g.omega * L0.dinv[i] * bi;
-            }
-            grid.sync();
-            amg_vcycle(g, grid, s_next, s_wk, S, true);
-            for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x)
-            {
-                if (comp) a.z[i].y = a.prec_sign * L0.t[i];
-                else a.z[i].x = a.prec_sign * L0.t[i];
-            }
-            grid.sync(); // the level buffers are reused by the next component / the caller reads z
-        }
+        const AmgVec2 &V0 = g2.lev[0];
         for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x)
         {
-            if (a.i2c[i] >= a.n_nodes) a.z[i] = cmul(a.r[i], a.dinv[i]); // circuit unknowns: Jacobi
-            dot = cfma(a.z[i], a.r[i], dot);
+            // circuit unknowns enter the cycle with a zero residual: their identity rows are outside the hierarchy's
+            // couplings, and their own z is replaced by the Jacobi step below
+            const bool circ = a.i2c[i] >= a.n_nodes;
+            const cd ri = circ ? make_double2(0., 0.) : a.r[i];
+            const double wd = g.omega * L0.dinv[i];
+            L0.b[i] = ri.x; L0.x[i] = wd * ri.x;
+            V0.b[i] = ri.y; V0.x[i] = wd * ri.y;
+        }
+        grid.sync();
+        amg_vcycle2(g, g2, grid, s_next, s_wk, S);
+        // every block post-smoothed its own rows of level 0: no barrier needed before reading them back
+        for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x)
+        {
+            cd zi = make_double2(a.prec_sign * L0.t[i], a.prec_sign * V0.t[i]);
+            if (a.i2c[i] >= a.n_nodes) zi = cmul(a.r[i], a.dinv[i]); // circuit unknowns: Jacobi
+            a.z[i] = zi;
+            dot = cfma(zi, a.r[i], dot);
         }
         return dot;
     }
@@ -297,7 +295,7 @@ __device__ __forceinline__ cd cprecond_apply(const CocgArgs &a, const AmgArgs &g
 }
 
 template <int PRECOND>
-__global__ void __launch_bounds__(512, 1) k_cocg(CocgArgs a, AmgArgs g)
+__global__ void __launch_bounds__(512, 1) k_cocg(CocgArgs a, AmgArgs g, AmgArgs2 g2)
 {
     cg::grid_group grid = cg::this_grid();
     __shared__ double sm[33];
@@ -367,7 +365,7 @@ __global__ void __launch_bounds__(512, 1) k_cocg(CocgArgs a, AmgArgs g)
         }
         grid.sync();
     }
-    cd part = cprecond_apply<PRECOND>(a, g, grid, r0, r1, warp_g, nwarps_g, lane, &s_next, s_wk, &S);
+    cd part = cprecond_apply<PRECOND>(a, g, g2, grid, r0, r1, warp_g, nwarps_g, lane, &s_next, s_wk, &S);
     part = block_sum_c(part, sm);
     if (threadIdx.x == 0) { partB[blockIdx.x] = part.x; partB[G + blockIdx.x] = part.y; }
     grid.sync();
@@ -412,7 +410,7 @@ __global__ void __launch_bounds__(512, 1) k_cocg(CocgArgs a, AmgArgs g)
         pn = block_sum(pn, sm);
         if (threadIdx.x == 0) partC[blockIdx.x] = pn;
         if (PRECOND != XFEMM_PRECOND_JACOBI) grid.sync();
-        part = cprecond_apply<PRECOND>(a, g, grid, r0, r1, warp_g, nwarps_g, lane, &s_next, s_wk, &S);
+        part = cprecond_apply<PRECOND>(a, g, g2, grid, r0, r1, warp_g, nwarps_g, lane, &s_next, s_wk, &S);
         part = block_sum_c(part, sm);
         if (threadIdx.x == 0) { partB[blockIdx.x] = part.x; partB[G + blockIdx.x] = part.y; }
         grid.sync();
@@ -821,6 +819,7 @@ int xfemm_clinprob_cocg(xfemm_clinprob *p, double precision, int warm, int preco
     // values unchanged since the previous call (the inner solves of KludgeSolve): keep everything prepared then
     const bool reuse = p->keep_prepared && p->prepared_precond == precond && (precond != XFEMM_PRECOND_AMG || p->re_prec);
     AmgArgs g;
+    AmgArgs2 g2;
     double prec_sign = 1.0;
     if (precond == XFEMM_PRECOND_AMG)
     {
@@ -871,6 +870,7 @@ int xfemm_clinprob_cocg(xfemm_clinprob *p, double precision, int warm, int preco
             }
         }
         amg_fill_args(R, *R->amg, g);
+        amg_fill_args2(R, *R->amg, g2);
     }
     int singular = -1;
     if (!reuse)
@@ -945,14 +945,14 @@ int xfemm_clinprob_cocg(xfemm_clinprob *p, double precision, int warm, int preco
     if (max_iter <= 0) max_iter = cenv_int("XFEMM_MAX_ITER", 200000);
     CocgArgs a = cmake_args(p, precision, warm ? 1 : 0, max_iter);
     a.prec_sign = prec_sign;
-    void *kargs[] = {&a, &g};
+    void *kargs[] = {&a, &g, &g2};
     int per_sm = 0, grid = 0;
     void *kern = precond == XFEMM_PRECOND_JACOBI ? (void *)k_cocg<XFEMM_PRECOND_JACOBI>
                  : precond == XFEMM_PRECOND_AMG  ? (void *)k_cocg<XFEMM_PRECOND_AMG>
                                                  : (void *)k_cocg<XFEMM_PRECOND_MCSSOR>;
     const size_t dyn_smem = precond == XFEMM_PRECOND_AMG ? STAGE_SMEM_BYTES : 0;
-    if (dyn_smem) XB_CUDA(cudaFuncSetAttribute((void (*)(CocgArgs, AmgArgs))kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
-    XB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (void (*)(CocgArgs, AmgArgs))kern, 512, dyn_smem));
+    if (dyn_smem) XB_CUDA(cudaFuncSetAttribute((void (*)(CocgArgs, AmgArgs, AmgArgs2))kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+    XB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (void (*)(CocgArgs, AmgArgs, AmgArgs2))kern, 512, dyn_smem));
     if (per_sm < 1) { set_error("cooperative kernel does not fit on an SM"); return XFEMM_ERR_CUDA; }
     per_sm = std::min(per_sm, cenv_int("XFEMM_PCG_BLOCKS_PER_SM", 2));
     grid = std::max(1, std::min(p->num_sms * per_sm, (p->lay.nslices + 15) / 16));
