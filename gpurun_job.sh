@@ -1,5 +1,3 @@
 cd /root/repo
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-timeout 900 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; tail -c 600 gpurun_out/bench_default.json; tail -2 gpurun_out/bench_default.err
-timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -c 900 gpurun_out/bench_ref.json
+timeout 900 python scratch/e2e_prof.py 2>&1 | grep -v "^$" | grep "linprob_create\|attachDevice\|host tables\|mag_create\|newton loop\|rep " | tail -12
+timeout 1200 python -m pytest tests/test_gpu_static.py tests/test_gpu_linprob.py tests/test_gpu_facade.py tests/test_gpu_scale.py -m gpu -x -q 2>&1 | tail -3

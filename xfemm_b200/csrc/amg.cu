@@ -3,6 +3,7 @@
 #include "amg.cuh"
 #include "amg2.cuh"
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -212,7 +213,7 @@ k_amg_dense_inverse(int n, int n_pad, const int *__restrict__ rowptr, const int 
     for (int e = threadIdx.x; e < n_pad * n_pad; e += blockDim.x) inv[e] = W[(size_t)(e / n_pad) * ld + n_pad + e % n_pad];
 }
 
-int amg_build(xfemm_linprob *fine, std::unique_ptr<AmgHierarchy> &out)
+int amg_build(xfemm_linprob *fine, std::unique_ptr<AmgHierarchy> &out, std::thread *fine_layout)
 {
     std::unique_ptr<AmgHierarchy> h(new AmgHierarchy);
     const char *e = getenv("XFEMM_AMG_MIN_COARSE");
@@ -225,9 +226,14 @@ int amg_build(xfemm_linprob *fine, std::unique_ptr<AmgHierarchy> &out)
     while ((int)h->coarse.size() + 1 < AMG_MAX_LEVELS && cur->n > min_coarse)
     {
         std::vector<int> agg, crp, ccol, gptr, gsrc;
+        const bool timing = getenv("XFEMM_TIMING") != nullptr;
+        auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        const double ta = now();
         const int nc = aggregate(cur->n, cur->h_rowptr.data(), cur->h_col.data(), wide_thr, agg);
         if (nc < 1 || nc > cur->n * 0.7) break; // coarsening stalled
+        const double tb = now();
         coarse_pattern(cur->n, cur->h_rowptr.data(), cur->h_col.data(), agg, nc, crp, ccol, gptr, gsrc);
+        const double tc = now();
         // levels from the third on live in the L2-pinned arena (see AmgHierarchy::arena)
         const bool pinned = h->coarse.size() >= 1 && !getenv("XFEMM_AMG_NO_PIN");
         if (pinned && !h->arena.base)
@@ -267,6 +273,8 @@ int amg_build(xfemm_linprob *fine, std::unique_ptr<AmgHierarchy> &out)
         XB_CUDA(T.gptr.upload(gptr.data(), gptr.size(), st));
         XB_CUDA(T.gsrc.upload(gsrc.data(), gsrc.size(), st));
         // transfer maps in the internal (SELL) row orders of both levels
+        if (fine_layout && fine_layout->joinable()) fine_layout->join(); // the finest level's layout is needed from here on
+        if (cur == fine && fine->layout_precond < 0) { set_error("the solver layout of the finest level is missing"); return XFEMM_ERR_ARG; }
         const SellLayout &LF = cur->lay, &LC = c->lay;
         std::vector<int> agg_int(LF.n_pad, -1), mptr(LC.n_pad + 1, 0), mem;
         for (int r = 0; r < LF.n_pad; r++)
@@ -287,6 +295,9 @@ int amg_build(xfemm_linprob *fine, std::unique_ptr<AmgHierarchy> &out)
             XB_CUDA(T.mem.upload(mem.data(), mem.size(), st));
         }
         XB_CUDA(cudaStreamSynchronize(st));
+        if (timing && cur->n > 100000)
+            fprintf(stderr, "[xfemm timing]     level %d -> %d rows: aggregate %.3f s, coarse pattern %.3f s, level problem + layout + transfer maps %.3f s\n",
+                    cur->n, nc, tb - ta, tc - tb, now() - tc);
         h->level_n.push_back(nc);
         h->level_nnz.push_back((int)ccol.size());
         cur = c;

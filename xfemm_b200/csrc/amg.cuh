@@ -21,6 +21,7 @@
 #include "stage.cuh"
 #include <cooperative_groups.h>
 #include <memory>
+#include <thread>
 
 namespace xb {
 
@@ -85,7 +86,9 @@ struct AmgHierarchy
 };
 void amg_print_trace(AmgHierarchy &h, cudaStream_t st); // phase timings of the last cycle to stderr
 
-int amg_build(xfemm_linprob *fine, std::unique_ptr<AmgHierarchy> &out);
+// fine_layout: optional host thread that is still building the solver layout of `fine`; the aggregation and the
+// coarse pattern only need the sparsity pattern, the thread is joined before the transfer maps read the layout
+int amg_build(xfemm_linprob *fine, std::unique_ptr<AmgHierarchy> &out, std::thread *fine_layout = nullptr);
 int amg_refresh(xfemm_linprob *fine, AmgHierarchy &h);
 void amg_fill_args(xfemm_linprob *fine, AmgHierarchy &h, AmgArgs &g);
 

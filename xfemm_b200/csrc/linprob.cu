@@ -888,16 +888,26 @@ int xfemm_linprob_create(int n, const int *rowptr, const int *colidx, xfemm_linp
     if (xfemm_device_count() <= 0) { set_error("no CUDA device available: the xfemm_b200 backend has no CPU fallback"); return XFEMM_ERR_CUDA; }
     const long long nnz = rowptr[n];
     // validate: sorted columns, diagonal present
-    for (int i = 0; i < n; i++)
     {
-        bool diag = false;
-        for (int s = rowptr[i]; s < rowptr[i + 1]; s++)
-        {
-            int c = colidx[s];
-            if (c < 0 || c >= n || (s > rowptr[i] && colidx[s - 1] >= c)) { set_error("row %d: columns must be sorted, unique and in range", i); return XFEMM_ERR_ARG; }
-            if (c == i) diag = true;
-        }
-        if (!diag) { set_error("row %d has no diagonal entry", i); return XFEMM_ERR_ARG; }
+        std::atomic<int> bad_cols(n), bad_diag(n); // lowest offending row of either kind (host threads)
+        auto lower = [](std::atomic<int> &a, int v) { int cur = a.load(); while (v < cur && !a.compare_exchange_weak(cur, v)) {} };
+        parallel_for(n, [&](int i0, int i1, int) {
+            for (int i = i0; i < i1; i++)
+            {
+                if (rowptr[i + 1] < rowptr[i]) { lower(bad_cols, i); return; }
+                bool diag = false;
+                for (int s = rowptr[i]; s < rowptr[i + 1]; s++)
+                {
+                    const int c = colidx[s];
+                    if (c < 0 || c >= n || (s > rowptr[i] && colidx[s - 1] >= c)) { lower(bad_cols, i); return; }
+                    if (c == i) diag = true;
+                }
+                if (!diag) { lower(bad_diag, i); return; }
+            }
+        }, 65536);
+        const int bc = bad_cols.load(), bd = bad_diag.load();
+        if (bc < n && bc <= bd) { set_error("row %d: columns must be sorted, unique and in range", bc); return XFEMM_ERR_ARG; }
+        if (bd < n) { set_error("row %d has no diagonal entry", bd); return XFEMM_ERR_ARG; }
     }
     xfemm_linprob *p = new xfemm_linprob;
     p->n = n; p->nnz = nnz;
@@ -1150,14 +1160,38 @@ int xfemm_linprob_prebuild(xfemm_linprob *p, int precond)
 {
     XB_ARG(p, "null handle");
     XB_CUDA(cudaSetDevice(p->device)); // a fresh host thread starts on device 0
+    const bool timing = getenv("XFEMM_TIMING") != nullptr;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
+    if (precond == XFEMM_PRECOND_AMG && !p->amg && p->layout_precond < 0 && !getenv("XFEMM_NO_OVERLAP"))
+    {
+        // the layout of the finest level and the first coarsening (aggregation, coarse pattern, coarse level) only
+        // share the sparsity pattern: two host threads, joined before the transfer maps need both layouts
+        int lrc = XFEMM_OK;
+        std::thread lt([&]() {
+            lrc = cudaSetDevice(p->device) == cudaSuccess ? linprob_build_layout(p, precond) : XFEMM_ERR_CUDA;
+            if (timing) fprintf(stderr, "[xfemm timing]   prebuild: SELL layout n=%d %.3f s (own thread)\n", p->n, now() - t0);
+        });
+        std::unique_ptr<AmgHierarchy> h;
+        int hrc = amg_build(p, h, &lt);
+        if (lt.joinable()) lt.join();
+        if (timing) fprintf(stderr, "[xfemm timing]   prebuild: layout + multigrid hierarchy %.3f s\n", now() - t0);
+        if (lrc != XFEMM_OK) return lrc;
+        if (hrc != XFEMM_OK) return hrc;
+        p->amg = h.release();
+        return XFEMM_OK;
+    }
     int rc = linprob_build_layout(p, precond);
+    if (timing) fprintf(stderr, "[xfemm timing]   prebuild: SELL layout n=%d %.3f s\n", p->n, now() - t0);
     if (rc != XFEMM_OK || precond != XFEMM_PRECOND_AMG) return rc;
     if (!p->amg)
     {
+        const double t1 = now();
         std::unique_ptr<AmgHierarchy> h;
         rc = amg_build(p, h);
         if (rc != XFEMM_OK) return rc;
         p->amg = h.release();
+        if (timing) fprintf(stderr, "[xfemm timing]   prebuild: multigrid hierarchy %.3f s\n", now() - t1);
     }
     return XFEMM_OK;
 }

@@ -9,6 +9,9 @@
 #include "../../include/xfemm_b200.h"
 #include "../csrc/layout.h"
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <unordered_map>
@@ -30,35 +33,58 @@ int xfemm_pattern_build(int n_rows, int n_elems, const int *tri, int tri_stride,
         return XFEMM_ERR_ARG;
     }
     const int n = n_rows;
-    // ---- pass 1: element graph as CSR with duplicates, then sort+unique per row
+    const bool timing = getenv("XFEMM_TIMING") != nullptr;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double tlast = now();
+    auto tick = [&](const char *what) {
+        if (timing) { const double t = now(); fprintf(stderr, "[xfemm timing]   pattern: %s %.3f s\n", what, t - tlast); tlast = t; }
+    };
+    // ---- pass 1: element graph as CSR with duplicates, then sort+unique per row.  Integer work over millions of
+    // elements: the counting and the scatter run on host threads with relaxed atomics (the order inside a row does
+    // not matter, every row is sorted next), the compaction copies rows to their final offsets in parallel.
     std::vector<int> cnt(n + 1, 0);
-    for (int e = 0; e < n_elems; e++)
     {
-        const int *t = tri + (size_t)e * tri_stride;
-        for (int j = 0; j < 3; j++)
-        {
-            if (t[j] < 0 || t[j] >= n) { xb::set_error("element %d: node index out of range", e); return XFEMM_ERR_ARG; }
-            cnt[t[j] + 1] += 2;
-        }
+        std::atomic<int> bad(-1);
+        std::vector<std::atomic<int>> acnt(n);
+        xb::parallel_for(n, [&](int i0, int i1, int) { for (int i = i0; i < i1; i++) acnt[i].store(1, std::memory_order_relaxed); }); // diagonal
+        xb::parallel_for(n_elems, [&](int e0, int e1, int) {
+            for (int e = e0; e < e1; e++)
+            {
+                const int *t = tri + (size_t)e * tri_stride;
+                for (int j = 0; j < 3; j++)
+                {
+                    if (t[j] < 0 || t[j] >= n) { bad.store(e, std::memory_order_relaxed); return; }
+                    acnt[t[j]].fetch_add(2, std::memory_order_relaxed);
+                }
+            }
+        });
+        if (bad.load() >= 0) { xb::set_error("element %d: node index out of range", bad.load()); return XFEMM_ERR_ARG; }
+        for (int i = 0; i < n; i++) cnt[i + 1] = cnt[i] + acnt[i].load(std::memory_order_relaxed);
     }
-    for (int i = 0; i < n; i++) cnt[i + 1] += 1; // diagonal
-    for (int i = 0; i < n; i++) cnt[i + 1] += cnt[i];
+    tick("count");
     std::vector<int> adj((size_t)cnt[n]);
     {
-        std::vector<int> pos(cnt.begin(), cnt.end() - 1);
-        for (int i = 0; i < n; i++) adj[pos[i]++] = i;
-        for (int e = 0; e < n_elems; e++)
-        {
-            const int *t = tri + (size_t)e * tri_stride;
-            const int a = t[0], b = t[1], c = t[2];
-            adj[pos[a]++] = b; adj[pos[a]++] = c;
-            adj[pos[b]++] = a; adj[pos[b]++] = c;
-            adj[pos[c]++] = a; adj[pos[c]++] = b;
-        }
+        std::vector<std::atomic<int>> pos(n);
+        xb::parallel_for(n, [&](int i0, int i1, int) {
+            for (int i = i0; i < i1; i++) { adj[cnt[i]] = i; pos[i].store(cnt[i] + 1, std::memory_order_relaxed); }
+        });
+        xb::parallel_for(n_elems, [&](int e0, int e1, int) {
+            for (int e = e0; e < e1; e++)
+            {
+                const int *t = tri + (size_t)e * tri_stride;
+                const int a = t[0], b = t[1], c = t[2];
+                const int pa = pos[a].fetch_add(2, std::memory_order_relaxed), pb = pos[b].fetch_add(2, std::memory_order_relaxed),
+                          pc = pos[c].fetch_add(2, std::memory_order_relaxed);
+                adj[pa] = b; adj[pa + 1] = c;
+                adj[pb] = a; adj[pb + 1] = c;
+                adj[pc] = a; adj[pc + 1] = b;
+            }
+        });
     }
+    tick("scatter");
     std::vector<int> rp(n + 1, 0);
     {
-        // sort+unique of every row in parallel, then one serial compaction pass
+        // sort+unique of every row in parallel, offsets by one serial scan, parallel copy to the compact array
         std::vector<int> len(n);
         xb::parallel_for(n, [&](int i0, int i1, int) {
             for (int i = i0; i < i1; i++)
@@ -68,16 +94,14 @@ int xfemm_pattern_build(int n_rows, int n_elems, const int *tri, int tri_stride,
                 len[i] = (int)(std::unique(b, e) - b);
             }
         });
-        size_t w = 0;
-        for (int i = 0; i < n; i++)
-        {
-            int *b = adj.data() + cnt[i];
-            if (adj.data() + w != b) memmove(adj.data() + w, b, (size_t)len[i] * sizeof(int));
-            w += len[i];
-            rp[i + 1] = (int)w;
-        }
-        adj.resize(w);
+        for (int i = 0; i < n; i++) rp[i + 1] = rp[i] + len[i];
+        std::vector<int> compact((size_t)rp[n]);
+        xb::parallel_for(n, [&](int i0, int i1, int) {
+            for (int i = i0; i < i1; i++) memcpy(compact.data() + rp[i], adj.data() + cnt[i], (size_t)len[i] * sizeof(int));
+        });
+        adj.swap(compact);
     }
+    tick("sort + compact");
     // ---- extras: AGE blocks and explicit couplings (created by assembly), then the periodic
     // fill (symbolic replay of Periodicity in list order; kept apart so that callers can tell
     // which slots exist only if the value-dependent reference code would have created them)
@@ -132,6 +156,7 @@ int xfemm_pattern_build(int n_rows, int n_elems, const int *tri, int tri_stride,
             add(fill, kk, j);
         }
     }
+    tick("extras + periodic fill");
     // ---- merge
     size_t total = adj.size();
     for (auto &kv : extra) total += kv.second.size();
@@ -140,41 +165,52 @@ int xfemm_pattern_build(int n_rows, int n_elems, const int *tri, int tri_stride,
     int *col = (int *)malloc(sizeof(int) * std::max<size_t>(total, 1));
     unsigned char *isfill = fill_out ? (unsigned char *)calloc(std::max<size_t>(total, 1), 1) : nullptr;
     if (!rowptr || !col || (fill_out && !isfill)) { free(rowptr); free(col); free(isfill); xb::set_error("out of memory"); return XFEMM_ERR_ARG; }
-    size_t w = 0;
-    rowptr[0] = 0;
-    std::vector<int> merged;
-    std::vector<char> touched(n, 0); // rows with extra or fill columns (a few thousand of millions)
+    // row lengths (mesh graph + extras + fill) -> offsets; untouched rows are copied in parallel, the few touched ones
+    // (air-gap rings, circuit rows, periodic nodes) are merged serially
+    std::vector<char> touched(n, 0);
     for (auto &kv : extra) touched[kv.first] = 1;
     for (auto &kv : fill) touched[kv.first] = 1;
+    rowptr[0] = 0;
     for (int i = 0; i < n; i++)
     {
-        const int *b = adj.data() + rp[i], *e = adj.data() + rp[i + 1];
-        auto fe = touched[i] ? extra.find(i) : extra.end();
-        auto ff = touched[i] ? fill.find(i) : fill.end();
-        if (fe == extra.end() && ff == fill.end())
+        size_t len = (size_t)(rp[i + 1] - rp[i]);
+        if (touched[i])
         {
-            memcpy(col + w, b, (e - b) * sizeof(int));
-            w += e - b;
+            auto fe = extra.find(i);
+            auto ff = fill.find(i);
+            if (fe != extra.end()) len += fe->second.size();
+            if (ff != fill.end()) len += ff->second.size();
         }
-        else
-        {
-            merged.assign(b, e);
-            if (fe != extra.end()) merged.insert(merged.end(), fe->second.begin(), fe->second.end());
-            size_t nonfill = merged.size();
-            if (ff != fill.end()) merged.insert(merged.end(), ff->second.begin(), ff->second.end());
-            // (column, is-fill) pairs; the `has` test above guarantees the three sources are disjoint
-            std::vector<std::pair<int, int>> pr(merged.size());
-            for (size_t q = 0; q < merged.size(); q++) pr[q] = {merged[q], q >= nonfill ? 1 : 0};
-            std::sort(pr.begin(), pr.end());
-            for (auto &x : pr)
-            {
-                col[w] = x.first;
-                if (isfill) isfill[w] = (unsigned char)x.second;
-                w++;
-            }
-        }
-        rowptr[i + 1] = (int)w;
+        rowptr[i + 1] = rowptr[i] + (int)len;
     }
+    xb::parallel_for(n, [&](int i0, int i1, int) {
+        for (int i = i0; i < i1; i++)
+            if (!touched[i]) memcpy(col + rowptr[i], adj.data() + rp[i], (size_t)(rp[i + 1] - rp[i]) * sizeof(int));
+    });
+    std::vector<int> merged;
+    for (int i = 0; i < n; i++)
+    {
+        if (!touched[i]) continue;
+        const int *b = adj.data() + rp[i], *e = adj.data() + rp[i + 1];
+        auto fe = extra.find(i);
+        auto ff = fill.find(i);
+        merged.assign(b, e);
+        if (fe != extra.end()) merged.insert(merged.end(), fe->second.begin(), fe->second.end());
+        size_t nonfill = merged.size();
+        if (ff != fill.end()) merged.insert(merged.end(), ff->second.begin(), ff->second.end());
+        // (column, is-fill) pairs; the `has` test above guarantees the three sources are disjoint
+        std::vector<std::pair<int, int>> pr(merged.size());
+        for (size_t q = 0; q < merged.size(); q++) pr[q] = {merged[q], q >= nonfill ? 1 : 0};
+        std::sort(pr.begin(), pr.end());
+        size_t w = (size_t)rowptr[i];
+        for (auto &x : pr)
+        {
+            col[w] = x.first;
+            if (isfill) isfill[w] = (unsigned char)x.second;
+            w++;
+        }
+    }
+    tick("merge");
     if (fill_out) *fill_out = isfill;
     *rowptr_out = rowptr;
     *colidx_out = col;

@@ -63,13 +63,23 @@ void CBigLinProb::attachDevice(xfemm_linprob *d, const int *rowptr, const int *c
 {
     if (dev && dev != d) xfemm_linprob_destroy(dev);
     dev = d;
-    csrRowptr.assign(rowptr, rowptr + n + 1);
-    csrCol.assign(col, col + rowptr[n]);
+    // the pattern stays with the device problem (it keeps a host copy); Get()/patternRowptr() fetch it on first use
+    (void)rowptr; (void)col;
+    std::vector<int>().swap(csrRowptr);
+    std::vector<int>().swap(csrCol);
     deviceAssembled = true;
     hostValuesValid = false;
     // the host rows are not used in this mode
     std::vector<std::vector<Ent>>().swap(rows);
     std::vector<std::vector<int>>().swap(lower);
+}
+
+void CBigLinProb::ensurePattern()
+{
+    if (!deviceAssembled || !dev || !csrRowptr.empty()) return;
+    csrRowptr.resize((size_t)n + 1);
+    csrCol.resize((size_t)xfemm_linprob_nnz(dev));
+    xfemm_linprob_get_pattern(dev, csrRowptr.data(), csrCol.data());
 }
 
 double *CBigLinProb::findEntry(int p, int q)
@@ -114,6 +124,7 @@ double CBigLinProb::Get(int p, int q)
     if (deviceAssembled)
     {
         fetchDeviceValues();
+        ensurePattern();
         if (csrRowptr.empty()) return 0;
         const int *b0 = csrCol.data() + csrRowptr[p], *e0 = csrCol.data() + csrRowptr[p + 1];
         const int *it = std::lower_bound(b0, e0, q);

@@ -65,12 +65,13 @@ public:
     // binds an externally built device problem (ownership passes to this object)
     void attachDevice(xfemm_linprob *d, const int *rowptr, const int *col);
     void invalidateHostCopy() { hostValuesValid = false; }
-    const int *patternRowptr() const { return csrRowptr.data(); }
-    const int *patternCol() const { return csrCol.data(); }
+    const int *patternRowptr() { ensurePattern(); return csrRowptr.data(); }
+    const int *patternCol() { ensurePattern(); return csrCol.data(); }
 
 private:
     struct Ent { int c; double x; };
     void ensureRows();                   // lazily creates the host rows below
+    void ensurePattern();                // device-assembled problems: the host copy of the pattern is fetched on first use
     std::vector<std::vector<Ent>> rows;  // upper triangle, sorted by column, first entry = diagonal
     std::vector<std::vector<int>> lower; // lower[i] = rows k<i holding an entry (k,i)
     bool patternDirty, valuesDirty, hostValuesValid, deviceAssembled;
