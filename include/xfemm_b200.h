@@ -133,6 +133,15 @@ int xfemm_pattern_build(int n_rows /* nodes + appended circuit unknowns */,
                         int n_pbc, const int *pbc_i, const int *pbc_j,
                         int **rowptr_out, int **colidx_out,
                         unsigned char **fill_out /* optional: 1 = slot exists only through the periodic replay */);
+/* the same result with the mesh-graph pass on the GPU (radix sort of (row,column) keys); needs a CUDA device —
+ * this is what FSolver calls; xfemm_pattern_build is the host-only version */
+int xfemm_pattern_build_device(int n_rows /* nodes + appended circuit unknowns */,
+                        int n_elems, const int *tri, int tri_stride /* ints per element: 3 or 4 */,
+                        int n_age_cells, const int *age_nodes /* n_age_cells*10 */,
+                        int n_extra, const int *extra_i, const int *extra_j /* extra symmetric couplings */,
+                        int n_pbc, const int *pbc_i, const int *pbc_j,
+                        int **rowptr_out, int **colidx_out,
+                        unsigned char **fill_out /* optional: 1 = slot exists only through the periodic replay */);
 /* The reference creates periodic fill only where a value is non-zero at that moment
  * (spars.cpp:442: if v1!=0 || v2!=0), which the structural replay cannot know.  Hand the fill
  * flags to the problem and, after the boundary conditions ran, ask which slots the reference's

@@ -113,3 +113,29 @@ def test_degenerate_systems(precond):
     L.pcg(1e-12, precond=precond)
     assert np.abs(L.get_solution() - vals).max() < 1e-10
     L.close()
+
+
+def test_pattern_build_on_the_device_equals_the_host_build():
+    """xfemm_pattern_build_device (mesh graph by a radix sort of (row, column) keys on the GPU; used by FSolver) gives
+    the same CSR as the host build: a fixture with air-gap blocks and periodic fill, a random triangle soup with
+    repeated and degenerate pairs, isolated nodes, and the error for an index out of range."""
+    import os, sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from util import load_ref
+    ref, meta = load_ref("tb")
+    tri = ref["elems"][:, :3]
+    for kw in (dict(pbc=ref["pbc"][:, :2]), dict(), dict(pbc=ref["pbc"][:40, :2], extra=np.array([[0, 4891], [17, 3000]]), with_fill=True)):
+        h = X.pattern_build(meta["n_nodes"], tri, **kw)
+        d = X.pattern_build(meta["n_nodes"], tri, device=True, **kw)
+        assert all(np.array_equal(a, b) for a, b in zip(h, d))
+    rng = np.random.default_rng(11)
+    n = 5000
+    soup = rng.integers(0, n - 100, size=(20000, 3)).astype(np.int32)  # the last 100 nodes stay isolated
+    soup[::7, 1] = soup[::7, 0]  # degenerate elements (a node twice)
+    h = X.pattern_build(n, soup)
+    d = X.pattern_build(n, soup, device=True)
+    assert np.array_equal(h[0], d[0]) and np.array_equal(h[1], d[1])
+    assert np.all(np.diff(h[0])[-100:] == 1)
+    soup[123, 2] = n + 5
+    with pytest.raises(X.XfemmError):
+        X.pattern_build(n, soup, device=True)

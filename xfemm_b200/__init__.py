@@ -82,6 +82,9 @@ SIGNATURES = {
     "xfemm_pattern_build": (C.c_int, [C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, C.c_int, _P, _P, C.c_int, _P, _P,
                                        C.POINTER(C.POINTER(C.c_int)), C.POINTER(C.POINTER(C.c_int)),
                                        C.POINTER(C.POINTER(C.c_ubyte))]),
+    "xfemm_pattern_build_device": (C.c_int, [C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, C.c_int, _P, _P, C.c_int, _P, _P,
+                                       C.POINTER(C.POINTER(C.c_int)), C.POINTER(C.POINTER(C.c_int)),
+                                       C.POINTER(C.POINTER(C.c_ubyte))]),
     "xfemm_linprob_set_fill_mask": (C.c_int, [_P, _P]),
     "xfemm_linprob_get_exists_mask": (C.c_int, [_P, _P]),
     "xfemm_free": (None, [_P]),
@@ -246,8 +249,9 @@ def sort_elements(tri):
     return order
 
 
-def pattern_build(n_rows, tri, age_nodes=None, pbc=None, extra=None, with_fill=False):
-    """Full CSR pattern (rowptr, col[, fill]) of mesh graph + AGE blocks + periodic fill."""
+def pattern_build(n_rows, tri, age_nodes=None, pbc=None, extra=None, with_fill=False, device=False):
+    """Full CSR pattern (rowptr, col[, fill]) of mesh graph + AGE blocks + periodic fill.
+    device=True: mesh-graph pass on the GPU (xfemm_pattern_build_device, what FSolver uses)."""
     fp = C.POINTER(C.c_ubyte)()
     tri = _i32(tri)
     stride = tri.shape[1]
@@ -266,7 +270,8 @@ def pattern_build(n_rows, tri, age_nodes=None, pbc=None, extra=None, with_fill=F
         nex = len(ei)
     rp = C.POINTER(C.c_int)()
     cp = C.POINTER(C.c_int)()
-    _check(lib().xfemm_pattern_build(n_rows, len(tri), _ptr(tri), stride, 0 if age is None else len(age), _ptr(age),
+    build = lib().xfemm_pattern_build_device if device else lib().xfemm_pattern_build
+    _check(build(n_rows, len(tri), _ptr(tri), stride, 0 if age is None else len(age), _ptr(age),
                                      nex, _ptr(ei), _ptr(ej), npbc, _ptr(pi), _ptr(pj), C.byref(rp), C.byref(cp),
                                      C.byref(fp) if with_fill else None),
            "pattern_build")

@@ -288,7 +288,7 @@ int FSolver::harmonicSolve(CBigComplexLinProb &L, bool axi, bool verbose)
     double t0 = hwall();
     int *rowptr = nullptr, *colidx = nullptr;
     unsigned char *fillmask = nullptr;
-    if (xfemm_pattern_build(nUnknowns, NumEls, tri.data(), 4, (int)ageMid.size(), ageNodes.data(), (int)exI.size(), exI.data(),
+    if (xfemm_pattern_build_device(nUnknowns, NumEls, tri.data(), 4, (int)ageMid.size(), ageNodes.data(), (int)exI.size(), exI.data(),
                             exJ.data(), NumPBCs, pbcI.data(), pbcJ.data(), &rowptr, &colidx, keepSystem ? &fillmask : nullptr) != XFEMM_OK)
     {
         WarnMessage(xfemm_last_error());

@@ -581,7 +581,7 @@ int FSolver::staticSolve(CBigLinProb &L, bool axi)
             for (size_t a = 0; a < ring.size(); a++)
                 for (size_t b = a; b < ring.size(); b++) { exI.push_back(ring[a]); exJ.push_back(ring[b]); }
         }
-    if (xfemm_pattern_build(NumNodes, NumEls, tri.data(), 4, (int)ageMid.size(), ageNodes.data(), (int)exI.size(), exI.data(), exJ.data(),
+    if (xfemm_pattern_build_device(NumNodes, NumEls, tri.data(), 4, (int)ageMid.size(), ageNodes.data(), (int)exI.size(), exI.data(), exJ.data(),
                             NumPBCs, pbcI.data(), pbcJ.data(), &rowptr, &colidx, keepSystem ? &fillmask : nullptr) != XFEMM_OK)
     {
         WarnMessage(xfemm_last_error());

@@ -17,28 +17,32 @@
 #include <unordered_map>
 #include <vector>
 
-namespace xb { void set_error(const char *fmt, ...); }
+namespace xb {
+void set_error(const char *fmt, ...);
+int element_graph_device(int n, int n_elems, const int *tri, int tri_stride, std::vector<int> &adj, std::vector<int> &rp); // csrc/pattern_device.cu
+}
 
 extern "C" {
 
-int xfemm_pattern_build(int n_rows, int n_elems, const int *tri, int tri_stride,
-                        int n_age_cells, const int *age_nodes,
-                        int n_extra, const int *extra_i, const int *extra_j,
-                        int n_pbc, const int *pbc_i, const int *pbc_j,
-                        int **rowptr_out, int **colidx_out, unsigned char **fill_out)
+// timing helper of the pattern functions (XFEMM_TIMING)
+struct PatternTicks
 {
-    if (n_rows <= 0 || !rowptr_out || !colidx_out || (n_elems > 0 && (!tri || tri_stride < 3)))
+    bool on = getenv("XFEMM_TIMING") != nullptr;
+    double last = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    void operator()(const char *what)
     {
-        xb::set_error("xfemm_pattern_build: invalid arguments");
-        return XFEMM_ERR_ARG;
+        if (!on) return;
+        const double t = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+        fprintf(stderr, "[xfemm timing]   pattern: %s %.3f s\n", what, t - last);
+        last = t;
     }
-    const int n = n_rows;
-    const bool timing = getenv("XFEMM_TIMING") != nullptr;
-    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    double tlast = now();
-    auto tick = [&](const char *what) {
-        if (timing) { const double t = now(); fprintf(stderr, "[xfemm timing]   pattern: %s %.3f s\n", what, t - tlast); tlast = t; }
-    };
+};
+
+// pass 1 on the host: mesh graph (every node coupled to itself and to the nodes it shares an element with) as CSR
+// with sorted, unique columns
+static int element_graph_host(int n, int n_elems, const int *tri, int tri_stride, std::vector<int> &adj, std::vector<int> &rp,
+                              PatternTicks &tick)
+{
     // ---- pass 1: element graph as CSR with duplicates, then sort+unique per row.  Integer work over millions of
     // elements: the counting and the scatter run on host threads with relaxed atomics (the order inside a row does
     // not matter, every row is sorted next), the compaction copies rows to their final offsets in parallel.
@@ -62,7 +66,7 @@ int xfemm_pattern_build(int n_rows, int n_elems, const int *tri, int tri_stride,
         for (int i = 0; i < n; i++) cnt[i + 1] = cnt[i] + acnt[i].load(std::memory_order_relaxed);
     }
     tick("count");
-    std::vector<int> adj((size_t)cnt[n]);
+    adj.assign((size_t)cnt[n], 0);
     {
         std::vector<std::atomic<int>> pos(n);
         xb::parallel_for(n, [&](int i0, int i1, int) {
@@ -82,7 +86,7 @@ int xfemm_pattern_build(int n_rows, int n_elems, const int *tri, int tri_stride,
         });
     }
     tick("scatter");
-    std::vector<int> rp(n + 1, 0);
+    rp.assign(n + 1, 0);
     {
         // sort+unique of every row in parallel, offsets by one serial scan, parallel copy to the compact array
         std::vector<int> len(n);
@@ -102,6 +106,14 @@ int xfemm_pattern_build(int n_rows, int n_elems, const int *tri, int tri_stride,
         adj.swap(compact);
     }
     tick("sort + compact");
+    return XFEMM_OK;
+}
+
+// pass 2 (host): air-gap blocks, explicit couplings and the periodic fill merged into the mesh graph
+static int pattern_finish(int n, std::vector<int> &adj, std::vector<int> &rp, int n_age_cells, const int *age_nodes, int n_extra,
+                          const int *extra_i, const int *extra_j, int n_pbc, const int *pbc_i, const int *pbc_j, int **rowptr_out,
+                          int **colidx_out, unsigned char **fill_out, PatternTicks &tick)
+{
     // ---- extras: AGE blocks and explicit couplings (created by assembly), then the periodic
     // fill (symbolic replay of Periodicity in list order; kept apart so that callers can tell
     // which slots exist only if the value-dependent reference code would have created them)
@@ -215,6 +227,47 @@ int xfemm_pattern_build(int n_rows, int n_elems, const int *tri, int tri_stride,
     *rowptr_out = rowptr;
     *colidx_out = col;
     return XFEMM_OK;
+}
+
+int xfemm_pattern_build(int n_rows, int n_elems, const int *tri, int tri_stride,
+                        int n_age_cells, const int *age_nodes,
+                        int n_extra, const int *extra_i, const int *extra_j,
+                        int n_pbc, const int *pbc_i, const int *pbc_j,
+                        int **rowptr_out, int **colidx_out, unsigned char **fill_out)
+{
+    if (n_rows <= 0 || !rowptr_out || !colidx_out || (n_elems > 0 && (!tri || tri_stride < 3)))
+    {
+        xb::set_error("xfemm_pattern_build: invalid arguments");
+        return XFEMM_ERR_ARG;
+    }
+    PatternTicks tick;
+    std::vector<int> adj, rp;
+    int rc = element_graph_host(n_rows, n_elems, tri, tri_stride, adj, rp, tick);
+    if (rc != XFEMM_OK) return rc;
+    return pattern_finish(n_rows, adj, rp, n_age_cells, age_nodes, n_extra, extra_i, extra_j, n_pbc, pbc_i, pbc_j, rowptr_out,
+                          colidx_out, fill_out, tick);
+}
+
+// The same with pass 1 on the GPU (csrc/pattern_device.cu: 64-bit (row,column) keys, radix sort, unique) — what
+// FSolver uses; needs a CUDA device.
+int xfemm_pattern_build_device(int n_rows, int n_elems, const int *tri, int tri_stride,
+                               int n_age_cells, const int *age_nodes,
+                               int n_extra, const int *extra_i, const int *extra_j,
+                               int n_pbc, const int *pbc_i, const int *pbc_j,
+                               int **rowptr_out, int **colidx_out, unsigned char **fill_out)
+{
+    if (n_rows <= 0 || !rowptr_out || !colidx_out || (n_elems > 0 && (!tri || tri_stride < 3)))
+    {
+        xb::set_error("xfemm_pattern_build_device: invalid arguments");
+        return XFEMM_ERR_ARG;
+    }
+    PatternTicks tick;
+    std::vector<int> adj, rp;
+    int rc = xb::element_graph_device(n_rows, n_elems, tri, tri_stride, adj, rp);
+    if (rc != XFEMM_OK) return rc;
+    tick("mesh graph on the device");
+    return pattern_finish(n_rows, adj, rp, n_age_cells, age_nodes, n_extra, extra_i, extra_j, n_pbc, pbc_i, pbc_j, rowptr_out,
+                          colidx_out, fill_out, tick);
 }
 
 // Cuthill–McKee exactly as the reference numbers nodes: adjacency from the .edge list in file
