@@ -1,2 +1,4 @@
 cd /root/repo
-timeout 900 python -m pytest tests/test_gpu_linprob.py -m gpu -x -q -k pattern 2>&1 | tail -8
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 900 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; tail -c 400 gpurun_out/bench_default.json; tail -2 gpurun_out/bench_default.err
