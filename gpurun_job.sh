@@ -1,4 +1,8 @@
 cd /root/repo
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-timeout 900 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; tail -c 400 gpurun_out/bench_default.json; tail -2 gpurun_out/bench_default.err
+for o in 3 2; do
+XFEMM_EXTRAPOLATION_ORDER=$o timeout 900 python bench.py --no-variants --no-cpu-baseline --steps 12 --warmup 6 > gpurun_out/bench_o$o.json 2> gpurun_out/bench_o$o.err; python - <<PY
+import json
+j=json.loads(open('/root/repo/gpurun_out/bench_o$o.json').read().strip().splitlines()[-1])
+print("order $o", {k:j[k] for k in ("value",)}, "pcg", j["pcg"]["ms"], j["pcg"]["iterations"], "torque-only", j["sweep_torque_only"]["s_per_position"])
+PY
+done
