@@ -306,7 +306,7 @@ __device__ __forceinline__ double precond_apply(const PcgArgs &a, const AmgArgs 
 }
 
 template <int PRECOND>
-__global__ void __launch_bounds__(512, 2) k_pcg(PcgArgs a, AmgArgs g)
+__global__ void __launch_bounds__(1024, 1) k_pcg(PcgArgs a, AmgArgs g)
 {
     cg::grid_group grid = cg::this_grid();
     __shared__ double sm[33];
@@ -1311,20 +1311,22 @@ int xfemm_linprob_pcg(xfemm_linprob *p, double precision, int warm, int precond,
         // The reference's three-phase recurrence (u=Ap | x,r update + z.r | p update).  A
         // Chronopoulos–Gear two-barrier arrangement was tried and dropped: it saves one barrier per
         // iteration but moves 20 n more bytes; measured on B200 at 2 M DOF: 0.103 vs 0.093 ms/iteration.
-        rc = coop_grid(p, k_pcg<XFEMM_PRECOND_JACOBI>, 512, &grid, STAGE_SMEM_BYTES);
+        const int threads = env_int("XFEMM_PCG_THREADS", 1024);
+        rc = coop_grid(p, k_pcg<XFEMM_PRECOND_JACOBI>, threads, &grid, STAGE_SMEM_BYTES);
         if (rc != XFEMM_OK) return rc;
         a.part = p->partials.p;
         if (ensure_tiles(p, grid)) { a.tiles = p->tiles.p; a.tile_ptr = p->tile_ptr.p; }
         ++xb::g_launch;
-        XB_CUDA(cudaLaunchCooperativeKernel((void *)k_pcg<XFEMM_PRECOND_JACOBI>, dim3(grid), dim3(512), kargs, STAGE_SMEM_BYTES, st));
+        XB_CUDA(cudaLaunchCooperativeKernel((void *)k_pcg<XFEMM_PRECOND_JACOBI>, dim3(grid), dim3(threads), kargs, STAGE_SMEM_BYTES, st));
     }
     else if (precond == XFEMM_PRECOND_AMG)
     {
-        rc = coop_grid(p, k_pcg<XFEMM_PRECOND_AMG>, 512, &grid, STAGE_SMEM_BYTES);
+        const int threads = env_int("XFEMM_PCG_THREADS", 1024);
+        rc = coop_grid(p, k_pcg<XFEMM_PRECOND_AMG>, threads, &grid, STAGE_SMEM_BYTES);
         if (rc != XFEMM_OK) return rc;
         a.part = p->partials.p;
         if (ensure_tiles(p, grid)) { a.tiles = p->tiles.p; a.tile_ptr = p->tile_ptr.p; }
-        ++xb::g_launch; XB_CUDA(cudaLaunchCooperativeKernel((void *)k_pcg<XFEMM_PRECOND_AMG>, dim3(grid), dim3(512), kargs, STAGE_SMEM_BYTES, st));
+        ++xb::g_launch; XB_CUDA(cudaLaunchCooperativeKernel((void *)k_pcg<XFEMM_PRECOND_AMG>, dim3(grid), dim3(threads), kargs, STAGE_SMEM_BYTES, st));
     }
     else
     {

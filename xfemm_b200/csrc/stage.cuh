@@ -20,7 +20,7 @@ namespace xb {
 #define XB_STAGE_TILE_ENT 2048
 #endif
 #ifndef XB_STAGE_COUNT
-#define XB_STAGE_COUNT 3
+#define XB_STAGE_COUNT 6
 #endif
 constexpr int STAGE_TILE_ENT = XB_STAGE_TILE_ENT; // entries per tile (2048: 16 KB of values + 8 KB of columns)
 constexpr int STAGE_COUNT = XB_STAGE_COUNT;
