@@ -273,6 +273,9 @@ int xfemm_clinprob_set_fill_mask(xfemm_clinprob *p, const unsigned char *fill);
 int xfemm_clinprob_get_exists_mask(xfemm_clinprob *p, unsigned char *exists);
 /* cspars.cpp:1062 PBCGSolveMod for the complex-symmetric case: cold start = 3 CG steps on the
  * normal equations (PCGSQStart, :764) then COCG (PBCGSolve, :822); stop on ||r||/||b|| <= precision */
+/* builds what depends on the pattern alone (layout; for XFEMM_PRECOND_AMG also the real companion problem and its
+ * multigrid hierarchy) ahead of the first solve; safe to call from another host thread while assembly runs */
+int xfemm_clinprob_prebuild(xfemm_clinprob *p, int precond);
 int xfemm_clinprob_cocg(xfemm_clinprob *p, double precision, int warm, int precond, int max_iter,
                         xfemm_solve_info *info);
 int xfemm_clinprob_save_solution(xfemm_clinprob *p);

@@ -118,6 +118,7 @@ SIGNATURES = {
     "xfemm_clinprob_set_fill_mask": (C.c_int, [_P, _P]),
     "xfemm_clinprob_get_exists_mask": (C.c_int, [_P, _P]),
     "xfemm_clinprob_cocg": (C.c_int, [_P, C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(SolveInfo)]),
+    "xfemm_clinprob_prebuild": (C.c_int, [_P, C.c_int]),
     "xfemm_clinprob_save_solution": (C.c_int, [_P]),
     "xfemm_clinprob_newton_norms": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "xfemm_clinprob_relax": (C.c_int, [_P, C.c_double]),

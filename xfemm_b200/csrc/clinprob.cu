@@ -670,6 +670,7 @@ int xfemm_clinprob_create(int n, int n_nodes, const int *rowptr, const int *coli
         return XFEMM_ERR_CUDA;
     }
     if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess) { delete p; set_error("stream create failed"); return XFEMM_ERR_CUDA; }
+    p->device = dev;
     p->h_rowptr.assign(rowptr, rowptr + n + 1);
     p->h_col.assign(colidx, colidx + nnz);
     auto body = [&]() -> int {
@@ -804,6 +805,62 @@ int xfemm_clinprob_get_exists_mask(xfemm_clinprob *p, unsigned char *exists)
     return XFEMM_OK;
 }
 
+// Real companion problem of XFEMM_PRECOND_AMG (see kc_fill_real): the pattern between mesh nodes plus identity rows
+// for the circuit unknowns, in the internal row order of this problem (the layout must exist).  Created once.
+static int censure_companion(xfemm_clinprob *p)
+{
+    if (p->re_prec) return XFEMM_OK;
+    const int n = p->n, nn = p->n_nodes;
+    std::vector<int> rp(n + 1, 0);
+    // row lengths, offsets, then the filtered columns and their source slots in parallel
+    parallel_for(n, [&](int i0, int i1, int) {
+        for (int i = i0; i < i1; i++)
+        {
+            int len = 0;
+            for (int s = p->h_rowptr[i]; s < p->h_rowptr[i + 1]; s++)
+            {
+                const int j = p->h_col[s];
+                if (i < nn ? j < nn : j == i) len++;
+            }
+            rp[i + 1] = len;
+        }
+    });
+    for (int i = 0; i < n; i++) rp[i + 1] += rp[i];
+    std::vector<int> rc_((size_t)rp[n]), src((size_t)rp[n]);
+    parallel_for(n, [&](int i0, int i1, int) {
+        for (int i = i0; i < i1; i++)
+        {
+            int w = rp[i];
+            for (int s = p->h_rowptr[i]; s < p->h_rowptr[i + 1]; s++)
+            {
+                const int j = p->h_col[s];
+                if (i < nn ? j < nn : j == i) { rc_[w] = j; src[w] = s; w++; }
+            }
+        }
+    });
+    int rc = xfemm_linprob_create(n, rp.data(), rc_.data(), &p->re_prec);
+    if (rc != XFEMM_OK) return rc;
+    for (int r : p->lay.i2c) if (r >= 0) p->re_prec->forced_order.push_back(r);
+    XB_CUDA(p->re_src.upload(src.data(), src.size(), p->stream));
+    XB_CUDA(cudaStreamSynchronize(p->stream));
+    return XFEMM_OK;
+}
+
+// Everything of the solver that depends on the sparsity pattern alone — the SELL layout and, for
+// XFEMM_PRECOND_AMG, the real companion problem with its layout and multigrid hierarchy — built ahead of the first
+// solve.  FSolver calls it from a host thread while the first assembly runs (as xfemm_linprob_prebuild).
+int xfemm_clinprob_prebuild(xfemm_clinprob *p, int precond)
+{
+    XB_ARG(p, "null handle");
+    XB_ARG(precond == XFEMM_PRECOND_JACOBI || precond == XFEMM_PRECOND_MCSSOR || precond == XFEMM_PRECOND_AMG, "unknown preconditioner");
+    XB_CUDA(cudaSetDevice(p->device)); // a fresh host thread starts on device 0
+    int rc = cbuild_layout(p, precond == XFEMM_PRECOND_AMG ? XFEMM_PRECOND_JACOBI : precond);
+    if (rc != XFEMM_OK || precond != XFEMM_PRECOND_AMG) return rc;
+    rc = censure_companion(p);
+    if (rc != XFEMM_OK) return rc;
+    return xfemm_linprob_prebuild(p->re_prec, XFEMM_PRECOND_AMG);
+}
+
 // PBCGSolveMod (cspars.cpp:1062-1081): cold start → 3 CG steps on the normal equations of the
 // Jacobi-preconditioned system to leave the pathological starting points of COCG, then COCG.
 int xfemm_clinprob_cocg(xfemm_clinprob *p, double precision, int warm, int precond, int max_iter, xfemm_solve_info *info)
@@ -823,27 +880,8 @@ int xfemm_clinprob_cocg(xfemm_clinprob *p, double precision, int warm, int preco
     double prec_sign = 1.0;
     if (precond == XFEMM_PRECOND_AMG)
     {
-        // real companion problem (see kc_fill_real): the pattern between mesh nodes plus identity rows for the
-        // circuit unknowns, in the internal row order of this problem; hierarchy built once per pattern
-        if (!p->re_prec)
-        {
-            const int n = p->n, nn = p->n_nodes;
-            std::vector<int> rp(n + 1, 0), rc_, src;
-            rc_.reserve(p->h_col.size()); src.reserve(p->h_col.size());
-            for (int i = 0; i < n; i++)
-            {
-                for (int s = p->h_rowptr[i]; s < p->h_rowptr[i + 1]; s++)
-                {
-                    const int j = p->h_col[s];
-                    if (i < nn ? j < nn : j == i) { rc_.push_back(j); src.push_back(s); }
-                }
-                rp[i + 1] = (int)rc_.size();
-            }
-            rc = xfemm_linprob_create(n, rp.data(), rc_.data(), &p->re_prec);
-            if (rc != XFEMM_OK) return rc;
-            for (int r : p->lay.i2c) if (r >= 0) p->re_prec->forced_order.push_back(r);
-            XB_CUDA(p->re_src.upload(src.data(), src.size(), st));
-        }
+        rc = censure_companion(p);
+        if (rc != XFEMM_OK) return rc;
         xfemm_linprob *R = p->re_prec;
         if (reuse) prec_sign = p->prepared_sign;
         else

@@ -12,7 +12,7 @@ struct xfemm_linprob;
 
 struct xfemm_clinprob
 {
-    int n = 0, n_nodes = 0;
+    int n = 0, n_nodes = 0, device = 0;
     long long nnz = 0;
     int num_sms = 0;
     cudaStream_t stream = nullptr;

@@ -309,6 +309,15 @@ int FSolver::harmonicSolve(CBigComplexLinProb &L, bool axi, bool verbose)
     xfemm_free(rowptr);
     xfemm_free(colidx);
     if (rc != XFEMM_OK) { WarnMessage(xfemm_last_error()); return false; }
+    // the solver structure (layout, real companion problem, multigrid hierarchy) only needs the pattern: a host
+    // thread builds it while the tables are uploaded and the first system is assembled
+    if (!getenv("XFEMM_NO_PREBUILD"))
+    {
+        joinPrebuild();
+        const int pc = precondOption >= 0 ? precondOption : L.precond;
+        prebuild = std::thread([lin, pc]() { xfemm_clinprob_prebuild(lin, pc); });
+    }
+    struct JoinOnExit { FSolver *s; ~JoinOnExit() { s->joinPrebuild(); } } joinOnExit{this}; // never outlive `lin`
 
     std::vector<double> xy(2 * (size_t)NumNodes);
     for (int i = 0; i < NumNodes; i++) { xy[2 * (size_t)i] = meshnode[i].x; xy[2 * (size_t)i + 1] = meshnode[i].y; }
@@ -383,6 +392,7 @@ int FSolver::harmonicSolve(CBigComplexLinProb &L, bool axi, bool verbose)
             }
         }
         xfemm_clinprob_save_solution(lin);
+        joinPrebuild(); // the solver structure is needed from here on (a failed pre-build is simply redone by the solve)
         xfemm_solve_info info;
         // XFEMM_PRECOND_AMG here = multigrid V-cycle of the real matrix |Re A| + |Im A| (stiffness + omega*sigma*mass)
         // applied to the real and the imaginary part of the residual; as a safety net an attempt that does not
