@@ -18,7 +18,7 @@ static void dump(const char *tag, CComplex *v, int n)
 int main(int argc, char **argv)
 {
     const int N = argc > 1 ? atoi(argv[1]) : 16;     // N x N grid, 5-point stencil
-    const int newton = argc > 2 ? atoi(argv[2]) : 0; // 1: add side matrices
+    const int newton = argc > 2 ? atoi(argv[2]) : 0; // 1: add side matrices; a third argument: dump the matrices, do not solve
     const int nodes = N * N, n = nodes + 2;          // two appended circuit unknowns
     CBigComplexLinProb L;
     L.Precision = 1e-10;
@@ -68,6 +68,23 @@ int main(int argc, char **argv)
     {
         if (i % 2 == 0) L.Periodicity(i, (N - 1) * N + i);
         else L.AntiPeriodicity(i, (N - 1) * N + i);
+    }
+    if (argc > 3)
+    {
+        // host logic only (no device needed): every entry of the four matrices through Get() — both index orders,
+        // i.e. including the conjugation rules — and the right-hand side after the boundary conditions
+        for (int h = 0; h <= 3; h++)
+        {
+            printf("# Get k=%d\n", h);
+            for (int p = 0; p < n; p++)
+                for (int q = 0; q < n; q++)
+                {
+                    const CComplex v = L.Get(p, q, h);
+                    printf("%.17g %.17g\n", v.re, v.im);
+                }
+        }
+        dump("b", L.b, n);
+        return 0;
     }
     // matrix-vector products after the boundary conditions
     CComplex *x = (CComplex *)calloc(n, sizeof(CComplex)), *y = (CComplex *)calloc(n, sizeof(CComplex));

@@ -203,3 +203,33 @@ def test_magdir_expression_evaluator():
         rc, _ = ev(bad, 1.0, 2.0)
         assert rc != 0, bad
         assert L.xfemm_last_error()
+
+
+@pytest.mark.parametrize("newton", [0, 1])
+def test_complex_facade_host_logic_matches_the_reference_class(newton, tmp_path):
+    """Host side of CBigComplexLinProb (no GPU involved): Put/Get with the selector k and its conjugation rules, SetValue,
+    Periodicity / AntiPeriodicity on all four matrices.  tests/cfacade_driver.cpp built against this repo's facade and,
+    by oracle/Makefile, against the unmodified reference class; every entry of M, Mh, Ms, Ma and the right-hand side
+    after the boundary conditions must agree."""
+    import subprocess
+    ref_exe = os.path.join(ROOT, "oracle", "_ref", "cfacade_ref")
+    if not os.path.exists(ref_exe):
+        pytest.skip("oracle/_ref/cfacade_ref not built (run make -C oracle where /root/reference is available)")
+    exe = str(tmp_path / "cfacade_driver")
+    host = os.path.join(ROOT, "xfemm_b200", "host")
+    libdir = os.path.join(ROOT, "xfemm_b200")
+    r = subprocess.run(["g++", "-std=c++14", "-O1", "-I" + host, os.path.join(ROOT, "tests", "cfacade_driver.cpp"), "-o", exe,
+                        "-L" + libdir, "-lxfemm_b200", "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    outs = []
+    for e in (exe, ref_exe):
+        r = subprocess.run([e, "7", str(newton), "dump"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-1000:]
+        outs.append(np.array([[float(x) for x in ln.split()] for ln in r.stdout.splitlines() if not ln.startswith("#")]))
+    mine, theirs = outs
+    n = 7 * 7 + 2
+    assert mine.shape == theirs.shape == (4 * n * n + n, 2)
+    scale = np.abs(theirs).max()
+    assert np.abs(mine - theirs).max() <= 1e-15 * scale
+    if newton:
+        assert np.abs(theirs[n * n:4 * n * n]).max() > 0  # the side matrices are populated
