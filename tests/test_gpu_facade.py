@@ -69,6 +69,25 @@ def test_host_assembled_problem_solves_on_gpu(precond, tmp_path):
     # fixed values come out of the iterative solve (spars.cpp:318 keeps the row), the last SetValue wins on node 0
     assert abs(v1[0] - 0.5) < 1e-9 and abs(v1[5 * N] - 0.5) < 1e-9
     print(precond, r.stderr.strip(), "oracle iterations", it1, it2)
+    # and against the same driver source built on the unmodified reference class (CPU, oracle/Makefile)
+    ref_exe = os.path.join(ROOT, "oracle", "_ref", "facade_ref")
+    if os.path.exists(ref_exe):
+        rr = subprocess.run([ref_exe, str(N)], capture_output=True, text=True)
+        assert rr.returncode == 0, rr.stderr[-1000:]
+        def numbers(text):  # the reference's PCGSolve also prints progress lines
+            out = []
+            for ln in text.splitlines():
+                try:
+                    out.append(float(ln))
+                except ValueError:
+                    pass
+            return np.array(out)
+
+        f1, f2 = rr.stdout.split("#\n")
+        r1, r2 = numbers(f1), numbers(f2)
+        assert len(r1) == N * N and len(r2) == N * N
+        assert np.linalg.norm(v1 - r1) <= 1e-8 * np.linalg.norm(r1)
+        assert np.linalg.norm(v2 - r2) <= 1e-8 * np.linalg.norm(r2)
 
 
 def _sections(text):

@@ -233,3 +233,27 @@ def test_complex_facade_host_logic_matches_the_reference_class(newton, tmp_path)
     assert np.abs(mine - theirs).max() <= 1e-15 * scale
     if newton:
         assert np.abs(theirs[n * n:4 * n * n]).max() > 0  # the side matrices are populated
+
+
+def test_real_facade_host_logic_matches_the_reference_class(tmp_path):
+    """Host side of CBigLinProb (no GPU involved): AddTo/Put/Get, SetValue (first/last value semantics) and
+    Periodicity / AntiPeriodicity as hsolver/esolver use them.  tests/facade_driver.cpp built against this repo's
+    facade and against the unmodified reference class: every entry and the right-hand side agree."""
+    import subprocess
+    ref_exe = os.path.join(ROOT, "oracle", "_ref", "facade_ref")
+    if not os.path.exists(ref_exe):
+        pytest.skip("oracle/_ref/facade_ref not built (run make -C oracle where /root/reference is available)")
+    exe = str(tmp_path / "facade_driver")
+    host = os.path.join(ROOT, "xfemm_b200", "host")
+    libdir = os.path.join(ROOT, "xfemm_b200")
+    r = subprocess.run(["g++", "-std=c++14", "-O1", "-I" + host, os.path.join(ROOT, "tests", "facade_driver.cpp"), "-o", exe,
+                        "-L" + libdir, "-lxfemm_b200", "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    outs = []
+    for e in (exe, ref_exe):
+        r = subprocess.run([e, "9", "dump"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-1000:]
+        outs.append(np.array([float(ln) for ln in r.stdout.splitlines() if not ln.startswith("#")]))
+    mine, theirs = outs
+    assert mine.shape == theirs.shape == (81 * 81 + 81,)
+    assert np.abs(mine - theirs).max() <= 1e-15 * np.abs(theirs).max()
