@@ -257,3 +257,38 @@ def test_real_facade_host_logic_matches_the_reference_class(tmp_path):
     mine, theirs = outs
     assert mine.shape == theirs.shape == (81 * 81 + 81,)
     assert np.abs(mine - theirs).max() <= 1e-15 * np.abs(theirs).max()
+
+
+def test_magdir_evaluator_against_the_reference_lua_interpreter(tmp_path):
+    """The same expressions evaluated by the reference's own Lua 4.0 (oracle/_ref/femmcli) with the variable block
+    Static2D prepends (static2d.cpp:530-531): precedence of ^ and unary minus, radians-mode functions, PI."""
+    import ctypes, math, subprocess
+    femmcli = os.path.join(ROOT, "oracle", "_ref", "femmcli")
+    if not os.path.exists(femmcli):
+        pytest.skip("oracle/_ref/femmcli not built")
+    exprs = ["theta", "theta + 20*cos(3*theta*PI/180) - R^2/4", "-(x+1)^2*10 + deg(atan2(y+0.5, x+1.5)) + max(1, 2*y, abs(x))",
+             "-2^2", "2^3^2", "2^-1", "-x^2", "1-2-3", "8/4/2", "r*z - x*y", "mod(theta+360, 90) + floor(R) + ceil(.5) + 1e1",
+             "min(3, 2, 5) + exp(0) + log(1) + log10(100) + rad(180)/PI", "sin(x)*cos(y) + tan(x/4) + asin(x/4) + acos(y/4) + atan(x)",
+             "sqrt(R) + tanh(x) + cosh(y/3) + sinh(x/3)", "2*-3", "-x*-y", "(1+2)*3^2/4 - -1"]
+    rng = np.random.default_rng(8)
+    pts = rng.uniform(-3, 3, size=(3, 2))
+    lines = []
+    pts = [(float(x), float(y)) for x, y in pts]
+    for x, y in pts:
+        th, R = math.degrees(math.atan2(y, x)), math.hypot(x, y)
+        for e in exprs:
+            lines.append(f"x={x!r}\ny={y!r}\nr=x\nz=y\ntheta={th!r}\nR={R!r}\nwrite(format(\"VAL %.17g\\n\", {e}))")
+    script = tmp_path / "expr.lua"
+    script.write_text("\n".join(lines) + "\nwrite(\"DONE\\n\")\n")
+    r = subprocess.run([femmcli, "--lua-script=expr.lua"], cwd=tmp_path, capture_output=True, text=True)
+    assert "DONE" in r.stdout, r.stdout[-500:] + r.stderr[-500:]
+    ref = [float(ln.split()[1]) for ln in r.stdout.splitlines() if ln.startswith("VAL")]
+    assert len(ref) == len(pts) * len(exprs)
+    L = X.lib()
+    k = 0
+    for x, y in pts:
+        for e in exprs:
+            out = ctypes.c_double(0)
+            assert L.xfemm_magdir_eval(e.encode(), float(x), float(y), ctypes.byref(out)) == 0, (e, L.xfemm_last_error())
+            assert abs(out.value - ref[k]) <= 1e-12 * max(1.0, abs(ref[k])), (e, out.value, ref[k])
+            k += 1
