@@ -172,3 +172,36 @@ def test_newton_ac_solver(case, tmp_path):
         G = sp.csr_matrix((S.side_matrix(k), col, rowptr), shape=(n, n))
         other = {1: G.conj().T, 2: G.T, 3: -G.conj().T}[k]
         assert abs(G - other).max() <= 1e-12 * sc
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["harm2d", "harm2dn", "harmaxin"])
+def test_harmonic_answer_file_through_the_reference_postprocessor(case, tmp_path):
+    """The .ans written by this repo's command line (WriteHarmonic2D) is loaded by the REFERENCE post-processor
+    (oracle/_ref/femmcli): circuit properties (current, voltage drop, flux linkage — complex) and block integrals
+    (A.J, stored energy, hysteresis / lamination losses) agree with those of the reference solver's own .ans within 1e-4."""
+    import os, re, shutil, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    femmcli, ref_solver = os.path.join(root, "oracle", "_ref", "femmcli"), os.path.join(root, "oracle", "_ref", "fsolver")
+    ours = os.path.join(root, "xfemm_b200", "fsolver_b200")
+    if not (os.path.exists(femmcli) and os.path.exists(ref_solver)):
+        pytest.skip("oracle/_ref not built")
+    lua = ('open("%s.fem")\nmi_loadsolution()\n'
+           'for _, c in {"coil", "bar"} do\n  i_, v_, f_ = mo_getcircuitproperties(c)\n'
+           '  write(format("VAL %%.12g %%.12g %%.12g %%.12g %%.12g %%.12g\\n", re(i_), im(i_), re(v_), im(v_), re(f_), im(f_)))\nend\n'
+           'mo_groupselectblock()\nfor _, k in {0, 2, 3} do\n  e_ = mo_blockintegral(k)\n  write(format("VAL %%.12g %%.12g\\n", re(e_), im(e_)))\nend\nwrite("DONE\\n")\n')
+    vals = {}
+    for who, solver in (("ours", ours), ("reference", ref_solver)):
+        d = tmp_path / who
+        d.mkdir()
+        base = stage_case(case, str(d))
+        r = subprocess.run([solver, base], cwd=d, capture_output=True, text=True)
+        assert os.path.exists(base + ".ans"), r.stdout[-500:] + r.stderr[-500:]
+        (d / "post.lua").write_text(lua % os.path.basename(base))
+        r = subprocess.run([femmcli, "--lua-script=post.lua"], cwd=d, capture_output=True, text=True)
+        assert "DONE" in r.stdout, r.stdout[-800:] + r.stderr[-800:]
+        vals[who] = np.array([float(x) for ln in r.stdout.splitlines() if ln.startswith("VAL") for x in ln.split()[1:]])
+    a, b = vals["ours"], vals["reference"]
+    assert a.shape == b.shape and len(a) == 18 and np.all(np.isfinite(b))
+    print(case, "reference post-processor on our .ans:", a, "\n   on the reference's:", b)
+    assert np.all(np.abs(a - b) <= 1e-4 * np.maximum(np.abs(b), 1e-12 + 1e-6 * np.abs(b).max()))
