@@ -490,7 +490,9 @@ def main():
                    "n_pbc": c["n_pbc"], "precision": 1e-10, "preconditioner": args.precond,
                    "l2_note": "matrix+vectors (%.0f MB) exceed the 126 MB L2" % ((12.0 * nnz + 56.0 * n) / 1e6),
                    "parallelism": f"rotor-angle sweep: {world} independent positions at a time, one per GPU (each rank a contiguous block of the 360 positions), no collective",
-                   "step": "one rotor position of the sweep: AGE re-target + assembly + BCs + PCG on the resident mesh; "
+                   "step": "one rotor position of the sweep: AGE re-target + assembly of all elements + Dirichlet + periodic pairs "
+                           "+ PCG on the resident mesh (the library's cache of the position-independent part is switched "
+                           "off here and reported under sweep_torque_only); "
                            "initial guess = quadratic extrapolation of the three previous positions (same stopping rule; "
                            "sweep_torque_only.cold_start gives the solve from a zero guess)"},
         "pcg": {"iterations": its, "reference_iterations": total_ref_iters or None, "ms": pcg_ms,
