@@ -8,6 +8,7 @@
 //   FSolver::Static2D                 cfemm/fsolver/static2d.cpp:53-1033
 //   FSolver::StaticAxisymmetric       cfemm/fsolver/staticaxi.cpp:45-794
 #include "fsolver.h"
+#include <type_traits>
 #include "magdir_expr.h"
 #include "../../include/xfemm_b200.h"
 #include "../csrc/layout.h"
@@ -67,7 +68,26 @@ int FSolver::SortElements()
         for (int k = k0; k < k1; k++)
             for (int j = 0; j < 3; j++) tri[3 * (size_t)k + j] = meshele[k].p[j];
     });
+    const bool timing = getenv("XFEMM_TIMING") != nullptr;
+    const double t0 = wall();
     if (xfemm_renumber_sort_elements(NumEls, tri.data(), order.data()) != XFEMM_OK) return false;
+    if (timing) fprintf(stderr, "[xfemm timing]     SortElements: comb passes %.3f s, sizeof(CMElement) %zu\n", wall() - t0, sizeof(CMElement));
+    if (std::is_trivially_copyable<CMElement>::value)
+    {
+        // gather into raw scratch memory (its pages are first touched by the threads that fill them; a value-initialised
+        // vector of 4 M elements would be faulted in by one thread), then copy back in place
+        CMElement *tmp = (CMElement *)malloc(sizeof(CMElement) * (size_t)std::max(NumEls, 1));
+        if (!tmp) return false;
+        xb::parallel_for(NumEls, [&](int k0, int k1, int) {
+            for (int k = k0; k < k1; k++) memcpy((void *)(tmp + k), (const void *)&meshele[order[k]], sizeof(CMElement));
+        });
+        xb::parallel_for(NumEls, [&](int k0, int k1, int) {
+            if (k1 > k0) memcpy((void *)&meshele[k0], (const void *)(tmp + k0), sizeof(CMElement) * (size_t)(k1 - k0));
+        });
+        free(tmp);
+        if (timing) fprintf(stderr, "[xfemm timing]     SortElements: total %.3f s\n", wall() - t0);
+        return true;
+    }
     std::vector<CMElement> out(NumEls);
     xb::parallel_for(NumEls, [&](int k0, int k1, int) {
         for (int k = k0; k < k1; k++) out[k] = meshele[order[k]];

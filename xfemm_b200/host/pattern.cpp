@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -372,12 +373,23 @@ int xfemm_renumber_cuthill(int n_nodes, int n_edges, const int *edges, int *newn
 int xfemm_renumber_sort_elements(int n_elems, const int *tri, int *order_out)
 {
     if (n_elems < 0 || (n_elems > 0 && (!tri || !order_out))) { xb::set_error("invalid arguments"); return XFEMM_ERR_ARG; }
-    // (key, index) pairs.  One pass with gap g only ever compares positions of the same residue mod g,
-    // so the g chains are independent: they are processed in parallel as contiguous blocks of residues,
-    // which replays exactly the swaps of the serial pass.
+    // (key, index) pairs.  One pass with gap g only ever compares positions of the same residue mod g, so the g chains
+    // are independent.
+    //  * large gaps: the chains are processed in parallel as contiguous blocks of residues, in place — exactly the
+    //    swaps of the serial pass;
+    //  * small gaps (few, long chains): a pass over one chain is a bubble pass, i.e. the element carried forward is
+    //    the running maximum (ties: the later element, the comparison is a strict '>') and position i-1 receives
+    //    min-by-that-rule(carry, element i).  The running maximum is a prefix scan, so the chains are cut into blocks
+    //    of consecutive positions: block maxima in parallel, a short serial scan over the blocks, then every block
+    //    writes its part of the result (out of place) from its incoming carry.  Same result as the serial pass.
     struct KI { int key, idx; };
-    std::vector<KI> a(n_elems);
+    std::vector<KI> bufA(n_elems), bufB;
+    KI *a = bufA.data();
     for (int k = 0; k < n_elems; k++) a[k] = {tri[3 * (size_t)k] + tri[3 * (size_t)k + 1] + tri[3 * (size_t)k + 2], k};
+    int nthreads = (int)std::thread::hardware_concurrency();
+    if (const char *lw = getenv("LOCAL_WORLD_SIZE")) nthreads /= std::max(1, atoi(lw));
+    if (const char *e = getenv("XFEMM_HOST_THREADS")) nthreads = atoi(e);
+    nthreads = std::max(1, std::min(nthreads, 32));
     int gap = n_elems;
     bool swapped;
     do
@@ -387,20 +399,102 @@ int xfemm_renumber_sort_elements(int n_elems, const int *tri, int *order_out)
             gap = (int)(((long long)gap * 10) / 13);
             if (gap == 10 || gap == 9) gap = 11;
         }
-        std::vector<char> sw(64, 0);
         const int g = gap;
         if (g <= 0) break;
-        xb::parallel_for(g, [&](int r0, int r1, int tid) {
-            bool s = false;
-            for (long long base = 0; base + g < n_elems; base += g)
+        std::vector<char> sw(64, 0);
+        const long long chain_len = ((long long)n_elems + g - 1) / g; // elements of the longest chain
+        const int nblocks = (int)std::min<long long>(nthreads, chain_len / 64);
+        if (g < 64 * nthreads && nblocks >= 2 && n_elems > g)
+        {
+            if (bufB.empty()) bufB.resize(n_elems);
+            KI *src = a, *dst = (a == bufA.data()) ? bufB.data() : bufA.data();
+            auto blk0 = [&](int b) { return std::min<long long>(n_elems, (chain_len * b / nblocks) * g); }; // first position of block b
+            // 1. running maximum of every chain inside every block (ties -> the later element)
+            std::vector<KI> bmax((size_t)nblocks * g);
+            std::vector<char> bhas((size_t)nblocks * g, 0);
+            xb::parallel_for(nblocks, [&](int b0, int b1, int) {
+                for (int b = b0; b < b1; b++)
+                {
+                    KI *mx = bmax.data() + (size_t)b * g;
+                    char *has = bhas.data() + (size_t)b * g;
+                    const long long p0 = blk0(b), p1 = blk0(b + 1);
+                    for (long long base = p0; base < p1; base += g)
+                    {
+                        const int lim = (int)std::min<long long>(g, p1 - base);
+                        for (int r = 0; r < lim; r++)
+                        {
+                            const KI e = src[base + r];
+                            if (!has[r]) { mx[r] = e; has[r] = 1; }
+                            else if (!(mx[r].key > e.key)) mx[r] = e;
+                        }
+                    }
+                }
+            }, 1);
+            // 2. carry entering every block (serial over the blocks, g entries each)
+            std::vector<KI> cin((size_t)nblocks * g);
+            std::vector<char> chas((size_t)nblocks * g, 0);
+            for (int r = 0; r < g; r++)
             {
-                const long long hi = std::min<long long>(r1, (long long)n_elems - g - base);
-                KI *x = a.data() + base;
-                for (long long r = r0; r < hi; r++)
-                    if (x[r].key > x[r + g].key) { std::swap(x[r], x[r + g]); s = true; }
+                bool have = false;
+                KI c = {0, 0};
+                for (int b = 0; b < nblocks; b++)
+                {
+                    if (have) { cin[(size_t)b * g + r] = c; chas[(size_t)b * g + r] = 1; }
+                    if (bhas[(size_t)b * g + r])
+                    {
+                        const KI m = bmax[(size_t)b * g + r];
+                        if (!have) { c = m; have = true; }
+                        else if (!(c.key > m.key)) c = m;
+                    }
+                }
             }
-            if (s) sw[tid] = 1;
-        }, 16);
+            // 3. every block writes position (i-1) of its chains for each of its elements i, the last block of a chain
+            //    also the final carry
+            xb::parallel_for(nblocks, [&](int b0, int b1, int tid) {
+                bool s = false;
+                std::vector<KI> carry(g);
+                std::vector<char> have(g);
+                for (int b = b0; b < b1; b++)
+                {
+                    for (int r = 0; r < g; r++) { have[r] = chas[(size_t)b * g + r]; if (have[r]) carry[r] = cin[(size_t)b * g + r]; }
+                    const long long p0 = blk0(b), p1 = blk0(b + 1);
+                    for (long long base = p0; base < p1; base += g)
+                    {
+                        const int lim = (int)std::min<long long>(g, p1 - base);
+                        for (int r = 0; r < lim; r++)
+                        {
+                            const KI e = src[base + r];
+                            if (!have[r]) { carry[r] = e; have[r] = 1; continue; } // first element of the chain
+                            if (carry[r].key > e.key) { dst[base + r - g] = e; s = true; }
+                            else { dst[base + r - g] = carry[r]; carry[r] = e; }
+                        }
+                    }
+                    // chains that end in this block: the carry lands on their last position
+                    for (int r = 0; r < g; r++)
+                    {
+                        if (!have[r]) continue;
+                        const long long last = r + ((long long)(n_elems - 1 - r) / g) * g; // last position of chain r
+                        if (last >= p0 && last < p1) dst[last] = carry[r];
+                    }
+                }
+                if (s) sw[tid] = 1;
+            }, 1);
+            a = dst;
+        }
+        else
+        {
+            xb::parallel_for(g, [&](int r0, int r1, int tid) {
+                bool s = false;
+                for (long long base = 0; base + g < n_elems; base += g)
+                {
+                    const long long hi = std::min<long long>(r1, (long long)n_elems - g - base);
+                    KI *x = a + base;
+                    for (long long r = r0; r < hi; r++)
+                        if (x[r].key > x[r + g].key) { std::swap(x[r], x[r + g]); s = true; }
+                }
+                if (s) sw[tid] = 1;
+            }, 16);
+        }
         swapped = false;
         for (char c : sw) swapped = swapped || c;
     } while (gap > 1 && swapped);
