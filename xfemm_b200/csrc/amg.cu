@@ -163,6 +163,13 @@ void coarse_pattern(int n, const int *rp, const int *col, const std::vector<int>
     }, 4096);
 }
 
+// coarse row of the column of every SELL slot (team levels: prolongation fused into the post-smoothing pass)
+__global__ void k_amg_cagg(long long len, const int *__restrict__ sell_col, const int *__restrict__ agg, int *__restrict__ cagg)
+{
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < len) cagg[i] = agg[sell_col[i]];
+}
+
 __global__ void k_amg_galerkin(int nnzc, const int *__restrict__ gptr, const int *__restrict__ gsrc,
                                const double *__restrict__ fine_vals, double *__restrict__ coarse_vals)
 {
@@ -177,6 +184,7 @@ __global__ void k_amg_galerkin(int nnzc, const int *__restrict__ gptr, const int
 // AMG_DENSE_MAX rows, is symmetric positive definite and diagonally dominant enough to go without
 // pivoting).  Rows/columns in the internal order of the level; padding rows become identity rows.
 constexpr int AMG_DENSE_MAX = 128;
+constexpr int AMG_TEAM_ROWS_MAX = 1 << 18; // no level with more rows is ever given to the team
 __global__ void __launch_bounds__(1024)
 k_amg_dense_inverse(int n, int n_pad, const int *__restrict__ rowptr, const int *__restrict__ col,
                     const double *__restrict__ vals, const int *__restrict__ c2i, double *W, double *inv)
@@ -220,6 +228,9 @@ int amg_build(xfemm_linprob *fine, std::unique_ptr<AmgHierarchy> &out, std::thre
     const int min_coarse = e ? atoi(e) : 64;
     const char *ew = getenv("XFEMM_WIDE_ROW");
     const int wide_thr = ew ? atoi(ew) : 64;
+    // levels with at most this many rows are cycled by a team of blocks with its own barrier (amg_team_cycle)
+    const char *etr = getenv("XFEMM_AMG_TEAM_ROWS");
+    h->team_rows = std::min(AMG_TEAM_ROWS_MAX, etr ? atoi(etr) : 65536);
     xfemm_linprob *cur = fine;
     h->level_n.push_back(fine->n);
     h->level_nnz.push_back((int)fine->nnz);
@@ -235,10 +246,13 @@ int amg_build(xfemm_linprob *fine, std::unique_ptr<AmgHierarchy> &out, std::thre
         coarse_pattern(cur->n, cur->h_rowptr.data(), cur->h_col.data(), agg, nc, crp, ccol, gptr, gsrc);
         const double tc = now();
         // levels from the third on live in the L2-pinned arena (see AmgHierarchy::arena)
+        // XFEMM_AMG_PIN_L1: the second level's solver layout (SELL stream, vectors) as well — not its CSR arrays
+        const bool pin_l1 = h->coarse.empty() && getenv("XFEMM_AMG_PIN_L1") && !getenv("XFEMM_AMG_NO_PIN");
         const bool pinned = h->coarse.size() >= 1 && !getenv("XFEMM_AMG_NO_PIN");
-        if (pinned && !h->arena.base)
+        if ((pinned || pin_l1) && !h->arena.base)
         {
-            const size_t cap = (size_t)(1.5 * (28.0 * ccol.size() + 150.0 * nc + 12.0 * cur->n)) + (2u << 20);
+            const size_t cap = pin_l1 ? (size_t)(1.2 * (18.0 * ccol.size() + 100.0 * nc) + 0.25 * (46.0 * ccol.size() + 150.0 * nc)) + (2u << 20)
+                                      : (size_t)(1.5 * (34.0 * ccol.size() + 150.0 * nc + 12.0 * cur->n)) + (2u << 20);
             if (dev_alloc((void **)&h->arena.base, cap) == cudaSuccess) { h->arena.cap = cap; h->arena.used = 0; }
             else { h->arena.base = nullptr; (void)cudaGetLastError(); }
         }
@@ -249,6 +263,10 @@ int amg_build(xfemm_linprob *fine, std::unique_ptr<AmgHierarchy> &out, std::thre
             rc = xfemm_linprob_create(nc, crp.data(), ccol.data(), &c);
             if (rc != XFEMM_OK) return rc;
             h->coarse.push_back(c);
+            // small levels (the team's): the task-split SpMV pass (amg_spmv_tasks) takes slices of any width up to 256
+            // columns in its stride, so their long rows (air-gap ring couplings) stay in the SELL slices — no
+            // wide-row pre-pass, and the prolongation can be fused into the post-smoothing pass
+            if (nc <= h->team_rows && !getenv("XFEMM_AMG_TEAM_WIDE_ROWS")) c->wide_threshold = 224;
             if ((int)cur->h_xy.size() == 2 * cur->n)
             {
                 // coarse "node" = centroid of its aggregate: the coarse level follows the same Z-curve
@@ -263,7 +281,10 @@ int amg_build(xfemm_linprob *fine, std::unique_ptr<AmgHierarchy> &out, std::thre
                     c->h_xy[2 * (size_t)I + 1] = (float)(sy[I] / std::max(1, cnt[I]));
                 }
             }
-            rc = linprob_build_layout(c, XFEMM_PRECOND_JACOBI);
+            {
+                ArenaScope hot(pin_l1 ? &h->arena : nullptr);
+                rc = linprob_build_layout(c, XFEMM_PRECOND_JACOBI);
+            }
             if (rc != XFEMM_OK) return rc;
         }
         h->xfer.emplace_back(new AmgHierarchy::Transfer);
@@ -293,6 +314,13 @@ int amg_build(xfemm_linprob *fine, std::unique_ptr<AmgHierarchy> &out, std::thre
             XB_CUDA(T.agg.upload(agg_int.data(), agg_int.size(), st));
             XB_CUDA(T.mptr.upload(mptr.data(), mptr.size(), st));
             XB_CUDA(T.mem.upload(mem.data(), mem.size(), st));
+            // a level the team may cycle (amg_fill_args decides): coarse row per SELL slot, unless it has wide rows
+            if (cur != fine && cur->n <= h->team_rows && cur->wide.n_rows == 0 && LF.sell_len > 0)
+            {
+                XB_CUDA(T.cagg.alloc((size_t)LF.sell_len));
+                ++g_launch, k_amg_cagg<<<(unsigned)((LF.sell_len + 255) / 256), 256, 0, st>>>(LF.sell_len, cur->sell_col.p, T.agg.p, T.cagg.p);
+                XB_CUDA(cudaGetLastError());
+            }
         }
         XB_CUDA(cudaStreamSynchronize(st));
         if (timing && cur->n > 100000)
@@ -302,6 +330,8 @@ int amg_build(xfemm_linprob *fine, std::unique_ptr<AmgHierarchy> &out, std::thre
         h->level_nnz.push_back((int)ccol.size());
         cur = c;
     }
+    XB_CUDA(h->team_ctr.alloc(64));
+    XB_CUDA(h->team_ctr.zero(fine->stream));
     // exact solve on the coarsest level when it is small enough for a dense inverse
     if (!h->coarse.empty() && h->coarse.back()->lay.n_pad <= AMG_DENSE_MAX && !getenv("XFEMM_AMG_NO_DENSE"))
     {
@@ -371,11 +401,12 @@ int amg_refresh(xfemm_linprob *fine, AmgHierarchy &h)
 void amg_print_trace(AmgHierarchy &h, cudaStream_t st)
 {
     if (!h.stamps.p) return;
-    std::vector<unsigned long long> t(AMG_MAX_STAMPS, 0);
+    std::vector<unsigned long long> t(AMG_MAX_STAMPS + 16, 0);
     cudaMemcpyAsync(t.data(), h.stamps.p, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
     cudaStreamSynchronize(st);
     fprintf(stderr, "[amg trace] levels:");
-    for (size_t l = 0; l < h.level_n.size(); l++) fprintf(stderr, " %d/%d", h.level_n[l], h.level_nnz[l]);
+    for (size_t l = 0; l < h.level_n.size(); l++)
+        fprintf(stderr, " %d/%d(w%d)", h.level_n[l], h.level_nnz[l], l == 0 ? -1 : h.coarse[l - 1]->wide.n_rows);
     fprintf(stderr, "\n[amg trace] phase us:");
     double total = 0;
     for (int k = 1; k < AMG_MAX_STAMPS - 8 && t[k] > t[k - 1]; k++)
@@ -384,6 +415,10 @@ void amg_print_trace(AmgHierarchy &h, cudaStream_t st)
         total += (t[k] - t[k - 1]) * 1e-3;
     }
     fprintf(stderr, "  (cycle %.1f us)\n", total);
+    const unsigned long long *dd = t.data() + AMG_MAX_STAMPS;
+    if (dd[6] > dd[0])
+        fprintf(stderr, "[amg trace] first team SpMV pass, block 0 (us): table %.2f, row-operand issue %.2f, tasks %.2f, sync %.2f, sums+epilogue %.2f, sync %.2f\n",
+                (dd[1] - dd[0]) * 1e-3, (dd[2] - dd[1]) * 1e-3, (dd[3] - dd[2]) * 1e-3, (dd[4] - dd[3]) * 1e-3, (dd[5] - dd[4]) * 1e-3, (dd[6] - dd[5]) * 1e-3);
     const unsigned long long *c = t.data() + AMG_MAX_STAMPS - 8; // CG part of the last iteration
     if (c[4] > c[0])
         fprintf(stderr, "[amg trace] cg part us: spmv+dot %.1f, residual update %.1f, (v-cycle %.1f), direction+solution update %.1f\n",
@@ -399,24 +434,28 @@ static void fill_level(AmgLev &L, xfemm_linprob *p)
     L.x = p->x.p; L.b = p->bint.p; L.t = p->u.p;
 }
 
-void amg_fill_args(xfemm_linprob *fine, AmgHierarchy &h, AmgArgs &g)
+void amg_fill_args(xfemm_linprob *fine, AmgHierarchy &h, AmgArgs &g, int grid)
 {
     g.nlev = 1 + (int)h.coarse.size();
     const char *e;
     g.omega = (e = getenv("XFEMM_AMG_OMEGA")) ? atof(e) : 0.8;
     g.over = (e = getenv("XFEMM_AMG_OVER")) ? atof(e) : 2.6;
     g.coarse_sweeps = ((e = getenv("XFEMM_AMG_COARSE_SWEEPS")) ? atoi(e) : 9) | 1;
-    // levels with at most this many rows are cycled by one block with __syncthreads (amg_block_cycle)
-    const int local_rows = (e = getenv("XFEMM_AMG_LOCAL_ROWS")) ? atoi(e) : 1024;
-    g.local_from = std::max(1, g.nlev - 1);
+    g.team_from = std::max(1, g.nlev - 1);
     for (int l = 1; l < g.nlev; l++)
-        if (h.level_n[l] <= local_rows) { g.local_from = l; break; }
+        if (h.level_n[l] <= h.team_rows) { g.team_from = l; break; }
+    g.team_blocks = std::max(1, std::min(grid, (e = getenv("XFEMM_AMG_TEAM_BLOCKS")) ? atoi(e) : 32));
+    g.team_ctr = h.team_ctr.p;
+    g.grid_ctr = getenv("XFEMM_CG_GRID_SYNC") ? nullptr : h.team_ctr.p + 32;
+    // both barriers count from zero in every launch; the launch follows on this stream
+    if (cudaMemsetAsync(h.team_ctr.p, 0, 64 * sizeof(unsigned), fine->stream) != cudaSuccess) (void)cudaGetLastError();
     g.coarse_inv = h.dense_inv.p;
     g.stamps = nullptr;
     if (getenv("XFEMM_AMG_TRACE"))
     {
-        if (!h.stamps.p && h.stamps.alloc(AMG_MAX_STAMPS) == cudaSuccess) h.stamps.zero(fine->stream);
+        if (!h.stamps.p && h.stamps.alloc(AMG_MAX_STAMPS + 16) == cudaSuccess) h.stamps.zero(fine->stream);
         g.stamps = h.stamps.p;
+        g.trace_detail = atoi(getenv("XFEMM_AMG_TRACE")) >= 2 ? atoi(getenv("XFEMM_AMG_TRACE")) - 1 : 0;
     }
     fill_level(g.lev[0], fine);
     g.lev[0].b = fine->r.p; // CG residual in, z out
@@ -428,6 +467,7 @@ void amg_fill_args(xfemm_linprob *fine, AmgHierarchy &h, AmgArgs &g)
         g.lev[l].agg = h.xfer[l]->agg.p;
         g.lev[l].mptr = h.xfer[l]->mptr.p;
         g.lev[l].mem = h.xfer[l]->mem.p;
+        g.lev[l].sell_cagg = ((int)l >= g.team_from && !getenv("XFEMM_AMG_NO_FUSED_PROLONGATION")) ? h.xfer[l]->cagg.p : nullptr;
     }
 }
 

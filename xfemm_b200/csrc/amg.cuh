@@ -5,7 +5,7 @@
 // grid barriers per colour.  A V-cycle over a hierarchy of plain (unsmoothed, piecewise-constant)
 // aggregates needs 20-40x fewer CG iterations than Jacobi on these first-order triangle meshes
 // and is made of the same building blocks as the solver itself: SELL-32 SpMV passes, row-wise
-// vector passes and grid barriers, all inside the ONE persistent PCG kernel.
+// vector passes and barriers, all inside the ONE persistent PCG kernel.
 //
 //   hierarchy (host, once per sparsity pattern): greedy distance-1 aggregation on the pattern,
 //       coarse pattern = aggregate graph, per coarse CSR slot the list of fine slots that sum into
@@ -14,18 +14,34 @@
 //       SELL / diagonal refill of each level.
 //   cycle: damped-Jacobi pre- and post-smoothing (same weight → symmetric), coarse correction
 //       scaled by an over-correction factor (plain aggregation under-estimates the correction),
-//       coarsest level (<= 64 rows or stalled coarsening) by a fixed number of Jacobi sweeps in one
-//       block.  M^-1 is a fixed symmetric positive definite operator, so CG applies.
+//       coarsest level (<= 128 rows) by its dense inverse, else by Jacobi sweeps.  M^-1 is a fixed
+//       symmetric positive definite operator, so CG applies.
+//
+// Who runs which level.  The big levels (0 .. team_from-1) are cycled by the whole grid: every block
+// owns a contiguous chunk of the slices of every level, phases are separated by grid barriers.  The
+// small levels (team_from .. last; a few ten thousand rows and less — they hold ~1 % of the data but
+// every phase on them is a chain of two or three dependent L2 accesses plus a barrier) belong to a
+// TEAM of the first `team_blocks` blocks, which synchronise among themselves with a counter barrier
+// (team_sync: ~1/5 of the arrivals of a grid barrier) while the other blocks wait at the one grid
+// barrier behind the team's sub-cycle.  On team levels the prolongation is fused into the
+// post-smoothing pass (x + over*P*t_c is formed on the fly from a coarse-column copy of the SELL
+// columns), which removes one pass and one barrier per level.  All small-level loops load in
+// predicated batches of eight so that a slice costs two round trips, not one per entry.
 #pragma once
 #include "linprob.cuh"
 #include "stage.cuh"
 #include <cooperative_groups.h>
 #include <memory>
 #include <thread>
+#include <type_traits>
 
 namespace xb {
 
 constexpr int AMG_MAX_LEVELS = 12;
+// per-block scratch of the kernels that run the cycle (shared memory): wide-row ranges of the block's chunk
+// of every level (2 ints per level) + the team barrier's epoch
+constexpr int AMG_SWK_EPOCH = 2 * AMG_MAX_LEVELS;
+constexpr int AMG_SWK_SIZE = 2 * AMG_MAX_LEVELS + 2;
 
 // device view of one level, internal (SELL) row order
 struct AmgLev
@@ -39,6 +55,7 @@ struct AmgLev
     double *x = nullptr, *b = nullptr, *t = nullptr; // iterate, right-hand side, result / scratch
     const int *agg = nullptr;                          // row -> row of the next level (-1: not represented)
     const int *mptr = nullptr, *mem = nullptr;         // row of the NEXT level -> member rows of this level
+    const int *sell_cagg = nullptr;                    // team levels without wide rows: agg[sell_col[slot]] (fused prolongation)
 };
 
 struct AmgArgs
@@ -46,11 +63,21 @@ struct AmgArgs
     int nlev = 0;
     int coarse_sweeps = 9;  // odd: the result of the coarsest level lands in its t buffer
     double omega = 0.8, over = 2.6;
-    int local_from = 1;     // first level handled by one block alone (small levels), <= nlev-1
+    int team_from = 1;      // first level handled by the team of blocks (small levels), 1 <= team_from <= nlev-1
+    int team_blocks = 1;    // blocks 0..team_blocks-1 form the team
+    unsigned *team_ctr = nullptr; // arrival counter of the team barrier (device memory, zeroed before the launch)
+    unsigned *grid_ctr = nullptr; // arrival counter of the grid barrier (GridBar), or null: cooperative-groups barrier
     const double *coarse_inv = nullptr; // dense inverse of the coarsest level (n_pad x n_pad, internal order) or null
+    int task_smem_offset = 0; // where the task buffer of amg_spmv_tasks starts in the kernel's dynamic shared memory
+    int trace_detail = 0;   // XFEMM_AMG_TRACE=2: a second stamp in front of every team barrier
     unsigned long long *stamps = nullptr; // optional (XFEMM_AMG_TRACE): %globaltimer at every phase boundary of a cycle
     AmgLev lev[AMG_MAX_LEVELS];
 };
+
+// vectors of a second right-hand side per level (complex solver: real and imaginary part of the residual go
+// through ONE cycle, amg2.cuh); the first component uses AmgLev::x/b/t
+struct AmgVec2 { double *x = nullptr, *b = nullptr, *t = nullptr; };
+struct AmgArgs2 { AmgVec2 lev[AMG_MAX_LEVELS]; };
 
 constexpr int AMG_MAX_STAMPS = 8 * AMG_MAX_LEVELS;
 __device__ __forceinline__ void amg_stamp(const AmgArgs &g, int &k, int limit = AMG_MAX_STAMPS - 8)
@@ -71,12 +98,15 @@ struct AmgHierarchy
         DevBuf<int> gptr, gsrc; // coarse CSR slot -> contributing fine CSR slots
         DevBuf<int> agg;        // fine internal row -> coarse internal row
         DevBuf<int> mptr, mem;  // coarse internal row -> fine internal rows
+        DevBuf<int> cagg;       // fine SELL slot -> coarse internal row of its column (team levels without wide rows)
         long long nnz_coarse = 0;
     };
     std::vector<xfemm_linprob *> coarse; // levels 1..
     std::vector<std::unique_ptr<Transfer>> xfer; // xfer[l]: level l -> l+1
     std::vector<int> level_n, level_nnz;
+    int team_rows = 65536;             // levels with at most this many rows belong to the team (XFEMM_AMG_TEAM_ROWS)
     DevBuf<unsigned long long> stamps; // XFEMM_AMG_TRACE
+    DevBuf<unsigned> team_ctr;         // barrier counters: [0] team, [32] grid (one 128 B line each)
     // The levels from the third on are latency-bound (a few thousand rows, dependent loads); the
     // streams of the finest level would evict them from L2 every cycle.  Their buffers are carved
     // from this one range, which the solver stream pins in L2 (access policy window, persisting).
@@ -90,25 +120,457 @@ void amg_print_trace(AmgHierarchy &h, cudaStream_t st); // phase timings of the 
 // coarse pattern only need the sparsity pattern, the thread is joined before the transfer maps read the layout
 int amg_build(xfemm_linprob *fine, std::unique_ptr<AmgHierarchy> &out, std::thread *fine_layout = nullptr);
 int amg_refresh(xfemm_linprob *fine, AmgHierarchy &h);
-void amg_fill_args(xfemm_linprob *fine, AmgHierarchy &h, AmgArgs &g);
+// grid = blocks of the cooperative launch the arguments are for (the team cannot be larger)
+void amg_fill_args(xfemm_linprob *fine, AmgHierarchy &h, AmgArgs &g, int grid = 1 << 30);
 
 // --------------------------------------------------------------------------------------------
-// device: grid-wide V-cycle.  Every block owns a contiguous chunk of slices of every level.
+// device: per-kernel set-up, the team barrier
 // --------------------------------------------------------------------------------------------
-__device__ __forceinline__ double amg_sell_row(const AmgLev &L, int s, int lane, const double *x)
+__device__ __forceinline__ int amg_chunk(int nslices, int b, int nb) { return (int)((long long)nslices * b / nb); }
+
+// Once per kernel, whole block, before the first cycle (and before the first grid barrier of the kernel):
+// wide-row ranges of this block's chunk of every level — the grid partition for the big levels, the team partition
+// for the team levels — and the team barrier's state.
+__device__ __forceinline__ void amg_kernel_init(const AmgArgs &g, int *s_wk)
 {
-    const int base = L.slice_ptr[s], w = (L.slice_ptr[s + 1] - base) >> 5;
-    double acc = 0.0;
-    const double *v = L.sell_val + base + lane;
-    const int *c = L.sell_col + base + lane;
-#pragma unroll 8
-    for (int k = 0; k < w; k++) acc = fma(__ldcs(v + k * 32), x[__ldcs(c + k * 32)], acc);
-    return acc;
+    const int G = gridDim.x, B = blockIdx.x;
+    if (threadIdx.x < g.nlev)
+    {
+        const int l = threadIdx.x;
+        const AmgLev &L = g.lev[l];
+        int k0 = 0, k1 = 0;
+        if (L.wide.n_rows)
+        {
+            if (l < g.team_from) wide_range(L.wide, amg_chunk(L.nslices, B, G) * 32, amg_chunk(L.nslices, B + 1, G) * 32, k0, k1);
+            else if (B < g.team_blocks)
+                wide_range(L.wide, amg_chunk(L.nslices, B, g.team_blocks) * 32, amg_chunk(L.nslices, B + 1, g.team_blocks) * 32, k0, k1);
+        }
+        s_wk[2 * l] = k0; s_wk[2 * l + 1] = k1;
+    }
+    if (threadIdx.x == 0) { s_wk[AMG_SWK_EPOCH] = 0; s_wk[AMG_SWK_EPOCH + 1] = 0; }
+    __syncthreads();
 }
 
-// y-phase over the block's slices of level L: calls epi(row, (A x)[row]) for every own row
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Counter barrier among `nblocks` blocks that are all resident (cooperative launch).  Monotone arrival counter:
+// barrier number k is complete when the counter has reached k * nblocks; *s_epoch (shared memory) holds k * nblocks.
+// Release/acquire at GPU scope on the counter itself: a red.release + ld.acquire pair costs a fraction of the
+// sequentially-consistent fences (MEMBAR.SC) that __threadfence() / cooperative-groups' grid.sync() compile to.
+__device__ __forceinline__ void counter_barrier(unsigned *ctr, int *s_epoch, int nblocks)
+{
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        const unsigned target = (unsigned)(*s_epoch += nblocks);
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+        while ((int)(ld_acquire_gpu(ctr) - target) < 0) {}
+    }
+    __syncthreads();
+}
+
+// Barrier among the team's blocks
+__device__ __forceinline__ void team_sync(const AmgArgs &g, int *s_wk) { counter_barrier(g.team_ctr, s_wk + AMG_SWK_EPOCH, g.team_blocks); }
+
+// Grid barrier with the interface of cooperative_groups::grid_group::sync(): the counter barrier when the kernel
+// was given a counter, cooperative groups otherwise
+struct GridBar
+{
+    cooperative_groups::grid_group grid;
+    unsigned *ctr;
+    int *s_epoch;
+    __device__ __forceinline__ void sync()
+    {
+        if (ctr) counter_barrier(ctr, s_epoch, gridDim.x);
+        else grid.sync();
+    }
+};
+
+// --------------------------------------------------------------------------------------------
+// device: building blocks shared by the one- and the two-component cycle
+// --------------------------------------------------------------------------------------------
+template <int NC>
+struct AmgV
+{
+    double *x[NC], *b[NC], *t[NC];
+};
+template <int NC>
+__device__ __forceinline__ AmgV<NC> amg_vecs(const AmgArgs &g, const AmgArgs2 *g2, int l)
+{
+    AmgV<NC> v;
+    v.x[0] = g.lev[l].x; v.b[0] = g.lev[l].b; v.t[0] = g.lev[l].t;
+    if (NC > 1) { v.x[NC - 1] = g2->lev[l].x; v.b[NC - 1] = g2->lev[l].b; v.t[NC - 1] = g2->lev[l].t; }
+    return v;
+}
+
+// coarse right-hand side of row I of level C = sum of the fine residuals of its members (ascending), coarse
+// pre-smoothing from a zero guess fused.  Member loads in predicated batches of eight.
+template <int NC>
+__device__ __forceinline__ void amg_restrict_row(const AmgLev &L, const AmgLev &C, const AmgV<NC> &lv, const AmgV<NC> &cv, int I,
+                                                 double w)
+{
+    constexpr int MB = (NC == 1) ? 16 : 8; // members per step: indices first, then all their residuals — two round trips
+    const int k0 = L.mptr[I], k1 = L.mptr[I + 1];
+    const double wd = w * C.dinv[I];
+    double s[NC];
+#pragma unroll
+    for (int m = 0; m < NC; m++) s[m] = 0.0;
+    for (int k = k0; k < k1; k += MB)
+    {
+        int mi[MB];
+#pragma unroll
+        for (int q = 0; q < MB; q++) mi[q] = (k + q < k1) ? L.mem[k + q] : -1;
+        double tv[NC][MB];
+#pragma unroll
+        for (int q = 0; q < MB; q++)
+#pragma unroll
+            for (int m = 0; m < NC; m++) tv[m][q] = mi[q] >= 0 ? lv.t[m][mi[q]] : 0.0;
+#pragma unroll
+        for (int q = 0; q < MB; q++)
+#pragma unroll
+            for (int m = 0; m < NC; m++) s[m] += tv[m][q];
+    }
+#pragma unroll
+    for (int m = 0; m < NC; m++) { cv.b[m][I] = s[m]; cv.x[m][I] = wd * s[m]; }
+}
+
+// the restriction pass of a whole level by `nthr` threads (own register allocation: out of line)
+template <int NC>
+__device__ __noinline__ void amg_restrict_level(const AmgLev &L, const AmgLev &C, AmgV<NC> lv, AmgV<NC> cv, int tid, int nthr, double w)
+{
+    for (int I = tid; I < C.n_pad; I += nthr) amg_restrict_row<NC>(L, C, lv, cv, I, w);
+}
+
+// x[i] += over * ct[agg[i]] for the rows [i0,i1) by `nthr` threads (this thread = `tid`), four rows per thread and
+// step with the loads ahead of the stores
+template <int NC>
+__device__ __noinline__ void amg_prolong_rows(const AmgLev &L, AmgV<NC> lv, AmgV<NC> cv, int i0, int i1, int tid, int nthr, double over)
+{
+    for (int i = i0 + tid; i < i1; i += 4 * nthr)
+    {
+        int I[4];
+        double xv[NC][4];
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+        {
+            const int r = i + q * nthr;
+            I[q] = r < i1 ? L.agg[r] : -1;
+#pragma unroll
+            for (int m = 0; m < NC; m++) xv[m][q] = r < i1 ? lv.x[m][r] : 0.0;
+        }
+        double cvv[NC][4];
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+#pragma unroll
+            for (int m = 0; m < NC; m++) cvv[m][q] = I[q] >= 0 ? cv.t[m][I[q]] : 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+        {
+            const int r = i + q * nthr;
+            if (I[q] >= 0)
+#pragma unroll
+                for (int m = 0; m < NC; m++) lv.x[m][r] = fma(over, cvv[m][q], xv[m][q]);
+        }
+    }
+}
+
+// SpMV pass of every level below the finest (whose matrix is not staged through the shared-memory ring), for a
+// block's slices [s0,s1) — its chunk of the grid partition on the big levels, of the team partition on the small ones.
+//
+// These levels are latency-bound, and what sets the latency is the WIDEST slice: a warp that walks a slice alone pays
+// two dependent round trips (entries, then gathers) per batch of columns, and the couplings of the air-gap ring make
+// a few slices of every coarse level 5-20 batches wide.  So a slice is cut into TASKS of BATCH columns; the block's
+// warps take tasks, not slices, leave the per-row partial sums of a task in shared memory, and after one
+// __syncthreads the warp that owns a slice adds its tasks in ascending order (deterministic) and applies the
+// epilogue.  Whatever the width: one round trip for the entries, one for the gathers.
+//   AMG_EPI_RESIDUAL  t = b - A x'            AMG_EPI_POST  t = x' + w D^-1 (b - A x')
+//   PROL: x' = x + over * P * (t of the next level) formed on the fly (prolongation fused); else x' = x
+// Reads v.x, v.b (cv.t), writes v.t.  Out of line on purpose: own register allocation, one copy of the code.
+enum { AMG_EPI_RESIDUAL = 0, AMG_EPI_POST = 1 };
+constexpr int AMG_TASK_MAXS = 480;                 // slices per group
+constexpr int AMG_TASK_PART_BYTES = 32 * 1024;     // partial sums: MAXT tasks x 32 rows x NC doubles
+constexpr int AMG_TASK_HDR_INTS = 4 + 2 * (AMG_TASK_MAXS + 1) + 128;
+constexpr int AMG_TASK_SMEM_BYTES = ((AMG_TASK_HDR_INTS * 4 + 127) / 128) * 128 + AMG_TASK_PART_BYTES;
+extern __shared__ __align__(128) unsigned char xb_dyn_smem[]; // the kernels' dynamic shared memory (ring first, then this buffer)
+
+template <int NC, bool PROL>
+__device__ __noinline__ void amg_spmv_tasks(const AmgLev &L, AmgV<NC> v, AmgV<NC> cv, int s0, int s1, int wk0, int wk1, int kind,
+                                            double w, double over, unsigned char *tsm, unsigned long long *dbg = nullptr)
+{
+    auto mark = [&](int k) {
+        if (dbg && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[k] = t; }
+    };
+    mark(0);
+    constexpr int BATCH = (NC == 1) ? 8 : 4;
+    constexpr int MAXT = AMG_TASK_PART_BYTES / (32 * 8 * NC); // 128 / 64
+    int *hdr = (int *)tsm;                       // [0] slices of the group, [1] tasks of the group
+    int *first_task = hdr + 4;                   // [MAXS+1] first task of each slice of the group
+    int *slice_base = first_task + AMG_TASK_MAXS + 1; // [MAXS+1] SELL offset of each slice of the group (+ the end)
+    int *task_info = slice_base + AMG_TASK_MAXS + 1;  // [128] (slice of the group << 16) | batch
+    double *part = (double *)(tsm + ((AMG_TASK_HDR_INTS * 4 + 127) / 128) * 128); // [task][component][lane]
+    const int lane = threadIdx.x & 31, warp_b = threadIdx.x >> 5, nwarps_b = blockDim.x >> 5;
+    if (wk1 > wk0)
+    {
+        // rows kept out of the SELL slices (layout.h): their off-diagonal sums go to v.t first
+#pragma unroll
+        for (int m = 0; m < NC; m++)
+        {
+            if (m) __syncthreads(); // the segment scratch is shared by the passes
+            wide_rows_block<double>(L.wide, L.wide_val, L.wide_acc, wk0, wk1, v.x[m], v.t[m]);
+        }
+    }
+    int cur = s0;
+    while (cur < s1) // uniform over the block
+    {
+        // ---- warp 0: task table of the next group of slices
+        if (warp_b == 0)
+        {
+            int nt_total = 0, ns = 0;
+            while (cur + ns < s1 && ns < AMG_TASK_MAXS)
+            {
+                const int s = cur + ns + lane;
+                int nt = 0, a = 0, b = 0;
+                if (s < s1) { a = L.slice_ptr[s]; b = L.slice_ptr[s + 1]; nt = (((b - a) >> 5) + BATCH - 1) / BATCH; }
+                int inc = nt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1)
+                {
+                    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += t;
+                }
+                const bool fits = s < s1 && nt_total + inc <= MAXT && ns + lane < AMG_TASK_MAXS;
+                const int cnt = __popc(__ballot_sync(0xffffffffu, fits)); // a prefix of the lanes: inc is non-decreasing
+                if (fits)
+                {
+                    const int t0 = nt_total + inc - nt;
+                    first_task[ns + lane] = t0;
+                    slice_base[ns + lane] = a;
+                    for (int q = 0; q < nt; q++) task_info[t0 + q] = ((ns + lane) << 16) | q;
+                    if (lane == cnt - 1) slice_base[ns + lane + 1] = b;
+                }
+                const int add = __shfl_sync(0xffffffffu, inc, cnt > 0 ? cnt - 1 : 0);
+                if (cnt > 0) nt_total += add;
+                ns += cnt;
+                if (cnt < 32) break;
+            }
+            if (lane == 0) { first_task[ns] = nt_total; hdr[0] = ns; hdr[1] = nt_total; }
+        }
+        __syncthreads();
+        mark(1);
+        const int ns = hdr[0], ntasks = hdr[1];
+        if (ns == 0) break; // a single slice wider than MAXT * BATCH columns: the host never builds one (amg_build checks)
+        // row operands of this warp's first slice: in flight during the task phase
+        double d0 = 0.0, wd0 = 0.0, xr0[NC], br0[NC];
+        if (warp_b < ns)
+        {
+            const int row = (cur + warp_b) * 32 + lane;
+            d0 = L.diag[row];
+            if (kind == AMG_EPI_POST) wd0 = w * L.dinv[row];
+            int I = -1;
+            if (PROL) I = L.agg[row];
+#pragma unroll
+            for (int m = 0; m < NC; m++)
+            {
+                xr0[m] = v.x[m][row];
+                br0[m] = v.b[m][row];
+                if (PROL) { if (I >= 0) xr0[m] = fma(over, cv.t[m][I], xr0[m]); }
+            }
+        }
+        mark(2);
+        // ---- tasks: BATCH columns of one slice, lane = row
+        for (int t = warp_b; t < ntasks; t += nwarps_b)
+        {
+            const int info = task_info[t], sl = info >> 16, k0 = (info & 0xffff) * BATCH;
+            const int base = slice_base[sl], wdt = (slice_base[sl + 1] - base) >> 5;
+            const int row = (cur + sl) * 32 + lane;
+            const double *vv = L.sell_val + base + lane;
+            const int *cc = L.sell_col + base + lane;
+            const int *ca = PROL ? L.sell_cagg + base + lane : nullptr;
+            double a[BATCH];
+            int j[BATCH], J[BATCH];
+#pragma unroll
+            for (int q = 0; q < BATCH; q++)
+            {
+                const bool ok = k0 + q < wdt;
+                a[q] = ok ? vv[(k0 + q) * 32] : 0.0;
+                j[q] = ok ? cc[(k0 + q) * 32] : row;
+                if (PROL) J[q] = ok ? ca[(k0 + q) * 32] : -1;
+            }
+            double acc[NC];
+#pragma unroll
+            for (int m = 0; m < NC; m++) acc[m] = 0.0;
+#pragma unroll
+            for (int q = 0; q < BATCH; q++)
+            {
+#pragma unroll
+                for (int m = 0; m < NC; m++)
+                {
+                    double xv = v.x[m][j[q]];
+                    if (PROL) { if (J[q] >= 0) xv = fma(over, cv.t[m][J[q]], xv); }
+                    acc[m] = fma(a[q], xv, acc[m]);
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < NC; m++) part[(t * NC + m) * 32 + lane] = acc[m];
+        }
+        mark(3);
+        __syncthreads();
+        mark(4);
+        // ---- the owner of a slice adds its tasks in ascending order and applies the epilogue
+        for (int sl = warp_b; sl < ns; sl += nwarps_b)
+        {
+            const int s = cur + sl, row = s * 32 + lane;
+            double d = d0, wd = wd0, xr[NC], br[NC];
+#pragma unroll
+            for (int m = 0; m < NC; m++) { xr[m] = xr0[m]; br[m] = br0[m]; }
+            if (sl != warp_b)
+            {
+                d = L.diag[row];
+                if (kind == AMG_EPI_POST) wd = w * L.dinv[row];
+                int I = -1;
+                if (PROL) I = L.agg[row];
+#pragma unroll
+                for (int m = 0; m < NC; m++)
+                {
+                    xr[m] = v.x[m][row];
+                    br[m] = v.b[m][row];
+                    if (PROL) { if (I >= 0) xr[m] = fma(over, cv.t[m][I], xr[m]); }
+                }
+            }
+            double acc[NC];
+#pragma unroll
+            for (int m = 0; m < NC; m++) acc[m] = 0.0;
+            for (int t = first_task[sl]; t < first_task[sl + 1]; t++)
+#pragma unroll
+                for (int m = 0; m < NC; m++) acc[m] += part[(t * NC + m) * 32 + lane];
+            if (wk1 > wk0 && ((L.wide.mask[s] >> lane) & 1u))
+#pragma unroll
+                for (int m = 0; m < NC; m++) acc[m] += v.t[m][row];
+#pragma unroll
+            for (int m = 0; m < NC; m++)
+            {
+                const double res = br[m] - fma(d, xr[m], acc[m]);
+                v.t[m][row] = (kind == AMG_EPI_POST) ? fma(wd, res, xr[m]) : res;
+            }
+        }
+        cur += ns;
+        mark(5);
+        __syncthreads(); // the table and the partial sums are reused by the next group
+        mark(6);
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// device: the team's sub-cycle over the levels team_from..last.  In: b and the pre-smoothed x of level
+// team_from.  Out: t of level team_from.  Called by the blocks 0..team_blocks-1 only; the caller follows it
+// with a grid barrier.
+// --------------------------------------------------------------------------------------------
+template <int NC>
+__device__ __noinline__ void amg_team_cycle(const AmgArgs &g, const AmgArgs2 *g2, int *s_wk, int *stamp_k = nullptr)
+{
+    const int first = g.team_from, last = g.nlev - 1;
+    const int T = g.team_blocks, B = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp_b = threadIdx.x >> 5, nwarps_b = blockDim.x >> 5;
+    const int tid_t = B * blockDim.x + threadIdx.x, nthr_t = T * blockDim.x;
+    const double w = g.omega, over = g.over;
+    unsigned char *tsm = xb_dyn_smem + g.task_smem_offset;
+    int sk = stamp_k ? *stamp_k : AMG_MAX_STAMPS; // XFEMM_AMG_TRACE: a stamp behind every team barrier
+    auto tsync = [&]() {
+        if (g.stamps && g.trace_detail) { __syncthreads(); amg_stamp(g, sk); } // block 0's own part of the phase ends here
+        team_sync(g, s_wk);
+        amg_stamp(g, sk);
+    };
+    // SpMV pass over this block's slices of team level l
+    auto spmv = [&](int l, bool prol, const AmgV<NC> &v, const AmgV<NC> &cv, int kind) {
+        const AmgLev &L = g.lev[l];
+        const int s0 = amg_chunk(L.nslices, B, T), s1 = amg_chunk(L.nslices, B + 1, T);
+        unsigned long long *dbg = (g.stamps && g.trace_detail && B == 0 && l == first && kind == AMG_EPI_RESIDUAL) ? g.stamps + AMG_MAX_STAMPS : nullptr;
+        if (prol) amg_spmv_tasks<NC, true>(L, v, cv, s0, s1, s_wk[2 * l], s_wk[2 * l + 1], kind, w, over, tsm);
+        else amg_spmv_tasks<NC, false>(L, v, cv, s0, s1, s_wk[2 * l], s_wk[2 * l + 1], kind, w, over, tsm, dbg);
+    };
+
+    // ---- down
+    for (int l = first; l < last; l++)
+    {
+        const AmgLev &L = g.lev[l];
+        const AmgLev &C = g.lev[l + 1];
+        const AmgV<NC> lv = amg_vecs<NC>(g, g2, l), cv = amg_vecs<NC>(g, g2, l + 1);
+        spmv(l, false, lv, cv, AMG_EPI_RESIDUAL);
+        tsync();
+        amg_restrict_level<NC>(L, C, lv, cv, tid_t, nthr_t, w);
+        tsync();
+    }
+    // ---- coarsest level
+    {
+        const AmgLev &L = g.lev[last];
+        const AmgV<NC> lv = amg_vecs<NC>(g, g2, last);
+        if (g.coarse_inv)
+        {
+            // exact solve with the dense inverse prepared by amg_refresh: t = A^-1 b, one warp per row
+            const int n = L.n_pad;
+            for (int r = B * nwarps_b + warp_b; r < n; r += T * nwarps_b)
+            {
+                double acc[NC];
+#pragma unroll
+                for (int m = 0; m < NC; m++) acc[m] = 0.0;
+                for (int c = lane; c < n; c += 32)
+                {
+                    const double a = g.coarse_inv[(size_t)r * n + c];
+#pragma unroll
+                    for (int m = 0; m < NC; m++) acc[m] = fma(a, lv.b[m][c], acc[m]);
+                }
+#pragma unroll
+                for (int m = 0; m < NC; m++)
+                {
+                    const double vsum = warp_sum(acc[m]);
+                    if (lane == 0) lv.t[m][r] = vsum;
+                }
+            }
+        }
+        else
+        {
+            // damped-Jacobi sweeps x -> t -> x ... (odd count: ends in t)
+            for (int it = 0; it < g.coarse_sweeps; it++)
+            {
+                AmgV<NC> sv = lv;
+                if (it & 1)
+#pragma unroll
+                    for (int m = 0; m < NC; m++) { sv.x[m] = lv.t[m]; sv.t[m] = lv.x[m]; }
+                spmv(last, false, sv, sv, AMG_EPI_POST);
+                if (it + 1 < g.coarse_sweeps) tsync();
+            }
+        }
+        if (last > first) tsync();
+    }
+    // ---- up: t = x' + w D^-1 (b - A x'),  x' = x + over * P * t_coarse
+    for (int l = last - 1; l >= first; l--)
+    {
+        const AmgLev &L = g.lev[l];
+        const AmgV<NC> lv = amg_vecs<NC>(g, g2, l), cv = amg_vecs<NC>(g, g2, l + 1);
+        if (L.sell_cagg) spmv(l, true, lv, cv, AMG_EPI_POST);
+        else
+        {
+            amg_prolong_rows<NC>(L, lv, cv, 0, L.n_pad, tid_t, nthr_t, over);
+            tsync();
+            spmv(l, false, lv, cv, AMG_EPI_POST);
+        }
+        if (l > first) tsync();
+    }
+    if (stamp_k) *stamp_k = sk;
+}
+
+// --------------------------------------------------------------------------------------------
+// device: grid-wide part of the one-component cycle
+// --------------------------------------------------------------------------------------------
+// y-phase over the block's slices of the FINEST level: calls epi(row, (A x)[row]) for every own row; the matrix
+// stream comes through the shared-memory ring (stage.cuh) when the block has tiles
 template <class Epi>
-__device__ __forceinline__ void amg_spmv_phase(const AmgLev &L, int s0, int s1, int wk0, int wk1, const double *x,
+__device__ __forceinline__ void amg_spmv_phase(const AmgLev &L, int s0, int s1, int wk0, int wk1, double *x,
                                                double *wide_tmp, int *s_next, Epi epi, StageSmem *S = nullptr,
                                                const double *pf0 = nullptr, const double *pf1 = nullptr)
 {
@@ -116,7 +578,6 @@ __device__ __forceinline__ void amg_spmv_phase(const AmgLev &L, int s0, int s1, 
     wide_rows_block<double>(L.wide, L.wide_val, L.wide_acc, wk0, wk1, x, wide_tmp);
     if (S && S->ntiles > 0)
     {
-        // finest level: the matrix stream comes through the shared-memory ring (stage.cuh)
         // pf0/pf1: row-indexed arrays the caller's epilogue reads (prefetched while the warp waits for its tile)
         staged_slices(*S, L.slice_ptr, L.sell_val, L.sell_col, s0, s1, x, s_next,
                       [&](int row) {
@@ -140,100 +601,29 @@ __device__ __forceinline__ void amg_spmv_phase(const AmgLev &L, int s0, int s1, 
         s = __shfl_sync(0xffffffffu, s, 0);
         if (s >= s1) break;
         const int row = s * 32 + lane;
-        double acc = amg_sell_row(L, s, lane, x);
+        const int base = L.slice_ptr[s], w = (L.slice_ptr[s + 1] - base) >> 5;
+        const double *v = L.sell_val + base + lane;
+        const int *c = L.sell_col + base + lane;
+        double acc = 0.0;
+#pragma unroll 8
+        for (int k = 0; k < w; k++) acc = fma(__ldcs(v + k * 32), x[__ldcs(c + k * 32)], acc);
         if (wk1 > wk0 && ((L.wide.mask[s] >> lane) & 1u)) acc += wide_tmp[row];
-        acc = fma(L.diag[row], x[row], acc);
-        epi(row, acc);
+        epi(row, fma(L.diag[row], x[row], acc));
     }
     __syncthreads(); // s_next is reused by the next phase
-}
-
-// Levels first..last handled by ONE block with __syncthreads only.  In: lev[first].b and .x
-// (pre-smoothed).  Out: lev[first].t.
-__device__ __forceinline__ void amg_block_cycle(const AmgArgs &g, int first)
-{
-    const int last = g.nlev - 1;
-    const int lane = threadIdx.x & 31, warp_b = threadIdx.x >> 5, nwarps_b = blockDim.x >> 5;
-    const double w = g.omega, over = g.over;
-    auto spmv = [&](const AmgLev &L, const double *src, double *dst, auto epi) {
-        wide_rows_block<double>(L.wide, L.wide_val, L.wide_acc, 0, L.wide.n_rows, src, dst);
-        __syncthreads();
-        for (int s = warp_b; s < L.nslices; s += nwarps_b)
-        {
-            const int row = s * 32 + lane;
-            double acc = amg_sell_row(L, s, lane, src);
-            if (L.wide.n_rows && ((L.wide.mask[s] >> lane) & 1u)) acc += dst[row];
-            acc = fma(L.diag[row], src[row], acc);
-            epi(row, acc);
-        }
-        __syncthreads();
-    };
-    for (int l = first; l < last; l++)
-    {
-        const AmgLev &L = g.lev[l];
-        const AmgLev &C = g.lev[l + 1];
-        spmv(L, L.x, L.t, [&](int row, double ax) { L.t[row] = L.b[row] - ax; });
-        for (int I = threadIdx.x; I < C.n_pad; I += blockDim.x)
-        {
-            double s = 0.0;
-            for (int k = L.mptr[I]; k < L.mptr[I + 1]; k++) s += L.t[L.mem[k]];
-            C.b[I] = s;
-            C.x[I] = w * C.dinv[I] * s;
-        }
-        __syncthreads();
-    }
-    {
-        const AmgLev &L = g.lev[last];
-        if (g.coarse_inv)
-        {
-            // coarsest level: exact solve with the dense inverse prepared by amg_refresh (t = A^-1 b)
-            const int n = L.n_pad;
-            for (int r = warp_b; r < n; r += nwarps_b)
-            {
-                double acc = 0.0;
-                for (int c = lane; c < n; c += 32) acc = fma(g.coarse_inv[(size_t)r * n + c], L.b[c], acc);
-                acc = warp_sum(acc);
-                if (lane == 0) L.t[r] = acc;
-            }
-            __syncthreads();
-        }
-        else
-        {
-            // damped-Jacobi sweeps x -> t -> x ... (odd count: ends in t)
-            double *src = L.x, *dst = L.t;
-            for (int it = 0; it < g.coarse_sweeps; it++)
-            {
-                double *d = dst;
-                const double *sv = src;
-                spmv(L, sv, d, [&](int row, double ax) { d[row] = fma(w * L.dinv[row], L.b[row] - ax, sv[row]); });
-                double *tmp = src; src = dst; dst = tmp;
-            }
-        }
-    }
-    for (int l = last - 1; l >= first; l--)
-    {
-        const AmgLev &L = g.lev[l];
-        const AmgLev &C = g.lev[l + 1];
-        for (int i = threadIdx.x; i < L.n_pad; i += blockDim.x)
-        {
-            const int I = L.agg[i];
-            if (I >= 0) L.x[i] = fma(over, C.t[I], L.x[i]);
-        }
-        __syncthreads();
-        spmv(L, L.x, L.t, [&](int row, double ax) { L.t[row] = fma(w * L.dinv[row], L.b[row] - ax, L.x[row]); });
-    }
 }
 
 // z = M^-1 r.  Level 0: b = r (input), t = z (output), x = scratch.  Returns this thread's partial of r.z.
 // x0_ready: the caller already stored the pre-smoothed x = omega D^-1 r of level 0 (fused into its
 // residual update) and synchronised the grid.
-__device__ __forceinline__ double amg_vcycle(const AmgArgs &g, cooperative_groups::grid_group &grid, int *s_next,
-                                             const int *s_wk /* [2*AMG_MAX_LEVELS] in shared memory */,
+__device__ __forceinline__ double amg_vcycle(const AmgArgs &g, GridBar &grid, int *s_next,
+                                             int *s_wk /* [AMG_SWK_SIZE] in shared memory, see amg_kernel_init */,
                                              StageSmem *S0 /* ring of the finest level, or null */, bool x0_ready = false)
 {
     const int G = gridDim.x, B = blockIdx.x;
     const int last = g.nlev - 1;
-    const int lc = g.local_from; // levels lc..last belong to block 0 alone (1 <= lc <= last unless nlev == 1)
+    const int lc = g.team_from; // levels lc..last belong to the team (1 <= lc <= last unless nlev == 1)
+    const int tid_g = B * blockDim.x + threadIdx.x, nthr_g = G * blockDim.x;
     const double w = g.omega, over = g.over;
     double dot = 0.0;
     int sk = 0;
@@ -242,7 +632,7 @@ __device__ __forceinline__ double amg_vcycle(const AmgArgs &g, cooperative_group
     if (!x0_ready || last == 0)
     {
         const AmgLev &L = g.lev[0];
-        const int r0 = (int)((long long)L.nslices * B / G) * 32, r1 = (int)((long long)L.nslices * (B + 1) / G) * 32;
+        const int r0 = amg_chunk(L.nslices, B, G) * 32, r1 = amg_chunk(L.nslices, B + 1, G) * 32;
         for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x) L.x[i] = w * L.dinv[i] * L.b[i];
         if (last == 0)
         {
@@ -257,26 +647,23 @@ __device__ __forceinline__ double amg_vcycle(const AmgArgs &g, cooperative_group
     {
         const AmgLev &L = g.lev[l];
         const AmgLev &C = g.lev[l + 1];
-        const int s0 = (int)((long long)L.nslices * B / G), s1 = (int)((long long)L.nslices * (B + 1) / G);
+        const int s0 = amg_chunk(L.nslices, B, G), s1 = amg_chunk(L.nslices, B + 1, G);
+        const AmgV<1> lv = amg_vecs<1>(g, nullptr, l), cv = amg_vecs<1>(g, nullptr, l + 1);
         // t = b - A x   (t doubles as the scratch the wide rows leave their partial sums in)
-        amg_spmv_phase(L, s0, s1, s_wk[2 * l], s_wk[2 * l + 1], L.x, L.t, s_next,
-                       [&](int row, double ax) { L.t[row] = L.b[row] - ax; }, l == 0 ? S0 : nullptr, L.b);
+        if (l == 0)
+            amg_spmv_phase(L, s0, s1, s_wk[0], s_wk[1], L.x, L.t, s_next, [&](int row, double ax) { L.t[row] = L.b[row] - ax; }, S0, L.b);
+        else
+            amg_spmv_tasks<1, false>(L, lv, cv, s0, s1, s_wk[2 * l], s_wk[2 * l + 1], AMG_EPI_RESIDUAL, w, over, xb_dyn_smem + g.task_smem_offset);
         grid.sync();
         amg_stamp(g, sk);
-        // coarse right-hand side = sum over the aggregate ; coarse pre-smooth fused
-        const int c0 = (int)((long long)C.nslices * B / G) * 32, c1 = (int)((long long)C.nslices * (B + 1) / G) * 32;
-        for (int I = c0 + threadIdx.x; I < c1; I += blockDim.x)
-        {
-            double s = 0.0;
-            for (int k = L.mptr[I]; k < L.mptr[I + 1]; k++) s += L.t[L.mem[k]];
-            C.b[I] = s;
-            C.x[I] = w * C.dinv[I] * s;
-        }
+        // coarse right-hand side = sum over the aggregate ; coarse pre-smooth fused.  Rows are dealt out
+        // thread by thread over the whole grid (coalesced pointer loads, no tail of idle blocks).
+        amg_restrict_level<1>(L, C, lv, cv, tid_g, nthr_g, w);
         grid.sync();
         amg_stamp(g, sk);
     }
-    // ---- the small levels: one block, no grid barriers; result in lev[lc].t
-    if (B == 0) amg_block_cycle(g, lc);
+    // ---- the small levels: the team, counter barriers; result in lev[lc].t
+    if (B < g.team_blocks) amg_team_cycle<1>(g, nullptr, s_wk, &sk);
     grid.sync();
     amg_stamp(g, sk);
     // ---- up: add the (over-)corrected coarse result (a row-wise gather: a scatter from the coarse rows
@@ -284,19 +671,15 @@ __device__ __forceinline__ double amg_vcycle(const AmgArgs &g, cooperative_group
     for (int l = lc - 1; l >= 0; l--)
     {
         const AmgLev &L = g.lev[l];
-        const AmgLev &C = g.lev[l + 1];
-        const int s0 = (int)((long long)L.nslices * B / G), s1 = (int)((long long)L.nslices * (B + 1) / G);
-        for (int i = s0 * 32 + threadIdx.x; i < s1 * 32; i += blockDim.x)
-        {
-            const int I = L.agg[i];
-            if (I >= 0) L.x[i] = fma(over, C.t[I], L.x[i]);
-        }
+        const int s0 = amg_chunk(L.nslices, B, G), s1 = amg_chunk(L.nslices, B + 1, G);
+        const AmgV<1> lv = amg_vecs<1>(g, nullptr, l), cv = amg_vecs<1>(g, nullptr, l + 1);
+        // own rows only: the post-smoothing pass below gathers x across blocks, hence the barrier
+        amg_prolong_rows<1>(L, lv, cv, s0 * 32, s1 * 32, threadIdx.x, blockDim.x, over);
         grid.sync();
         amg_stamp(g, sk);
         if (l > 0)
         {
-            amg_spmv_phase(L, s0, s1, s_wk[2 * l], s_wk[2 * l + 1], L.x, L.t, s_next,
-                           [&](int row, double ax) { L.t[row] = fma(w * L.dinv[row], L.b[row] - ax, L.x[row]); });
+            amg_spmv_tasks<1, false>(L, lv, cv, s0, s1, s_wk[2 * l], s_wk[2 * l + 1], AMG_EPI_POST, w, over, xb_dyn_smem + g.task_smem_offset);
             grid.sync();
             amg_stamp(g, sk);
         }

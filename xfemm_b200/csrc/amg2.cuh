@@ -8,29 +8,10 @@
 
 namespace xb {
 
-// vectors of the second component per level (the first one uses AmgLev::x/b/t)
-struct AmgVec2 { double *x = nullptr, *b = nullptr, *t = nullptr; };
-struct AmgArgs2 { AmgVec2 lev[AMG_MAX_LEVELS]; };
+// (AmgVec2 / AmgArgs2: vectors of the second component per level, amg.cuh)
 void amg_fill_args2(xfemm_linprob *fine, AmgHierarchy &h, AmgArgs2 &g2);
 
 struct AmgPre2 { double d, xa, xb; };
-
-__device__ __forceinline__ void amg_sell_row2(const AmgLev &L, int s, int lane, const double *xa, const double *xb_,
-                                              double &acca, double &accb)
-{
-    const int base = L.slice_ptr[s], w = (L.slice_ptr[s + 1] - base) >> 5;
-    const double *v = L.sell_val + base + lane;
-    const int *c = L.sell_col + base + lane;
-    acca = 0.0; accb = 0.0;
-#pragma unroll 8
-    for (int k = 0; k < w; k++)
-    {
-        const double a = __ldcs(v + k * 32);
-        const int j = __ldcs(c + k * 32);
-        acca = fma(a, xa[j], acca);
-        accb = fma(a, xb_[j], accb);
-    }
-}
 
 // staged_slices (stage.cuh) with two gathered vectors: epi(slice, row, acc_a, acc_b, pre(row))
 template <class Pre, class Epi>
@@ -93,8 +74,8 @@ __device__ __forceinline__ void staged_slices2(StageSmem &S, const int *__restri
 
 // epi(row, (A xa)[row], (A xb)[row]) for every own row of the block's slices of level L
 template <class Epi>
-__device__ __forceinline__ void amg_spmv_phase2(const AmgLev &L, int s0, int s1, int wk0, int wk1, const double *xa,
-                                                const double *xb_, double *tmpa, double *tmpb, int *s_next, Epi epi,
+__device__ __forceinline__ void amg_spmv_phase2(const AmgLev &L, int s0, int s1, int wk0, int wk1, double *xa,
+                                                double *xb_, double *tmpa, double *tmpb, int *s_next, Epi epi,
                                                 StageSmem *S = nullptr)
 {
     const int lane = threadIdx.x & 31;
@@ -123,8 +104,18 @@ __device__ __forceinline__ void amg_spmv_phase2(const AmgLev &L, int s0, int s1,
         s = __shfl_sync(0xffffffffu, s, 0);
         if (s >= s1) break;
         const int row = s * 32 + lane;
-        double acca, accb;
-        amg_sell_row2(L, s, lane, xa, xb_, acca, accb);
+        const int base = L.slice_ptr[s], w = (L.slice_ptr[s + 1] - base) >> 5;
+        const double *v = L.sell_val + base + lane;
+        const int *c = L.sell_col + base + lane;
+        double acca = 0.0, accb = 0.0;
+#pragma unroll 8
+        for (int k = 0; k < w; k++)
+        {
+            const double a = __ldcs(v + k * 32);
+            const int j = __ldcs(c + k * 32);
+            acca = fma(a, xa[j], acca);
+            accb = fma(a, xb_[j], accb);
+        }
         if (wk1 > wk0 && ((L.wide.mask[s] >> lane) & 1u)) { acca += tmpa[row]; accb += tmpb[row]; }
         const double d = L.diag[row];
         epi(row, fma(d, xa[row], acca), fma(d, xb_[row], accb));
@@ -132,120 +123,21 @@ __device__ __forceinline__ void amg_spmv_phase2(const AmgLev &L, int s0, int s1,
     __syncthreads();
 }
 
-// amg_block_cycle for two components: levels first..last by ONE block
-__device__ __forceinline__ void amg_block_cycle2(const AmgArgs &g, const AmgArgs2 &g2, int first)
-{
-    const int last = g.nlev - 1;
-    const int lane = threadIdx.x & 31, warp_b = threadIdx.x >> 5, nwarps_b = blockDim.x >> 5;
-    const double w = g.omega, over = g.over;
-    auto spmv = [&](const AmgLev &L, const double *sa, const double *sb, double *da, double *db, auto epi) {
-        if (L.wide.n_rows)
-        {
-            wide_rows_block<double>(L.wide, L.wide_val, L.wide_acc, 0, L.wide.n_rows, sa, da);
-            __syncthreads();
-            wide_rows_block<double>(L.wide, L.wide_val, L.wide_acc, 0, L.wide.n_rows, sb, db);
-        }
-        __syncthreads();
-        for (int s = warp_b; s < L.nslices; s += nwarps_b)
-        {
-            const int row = s * 32 + lane;
-            double acca, accb;
-            amg_sell_row2(L, s, lane, sa, sb, acca, accb);
-            if (L.wide.n_rows && ((L.wide.mask[s] >> lane) & 1u)) { acca += da[row]; accb += db[row]; }
-            const double d = L.diag[row];
-            epi(row, fma(d, sa[row], acca), fma(d, sb[row], accb));
-        }
-        __syncthreads();
-    };
-    for (int l = first; l < last; l++)
-    {
-        const AmgLev &L = g.lev[l];
-        const AmgLev &C = g.lev[l + 1];
-        const AmgVec2 &L2 = g2.lev[l];
-        const AmgVec2 &C2 = g2.lev[l + 1];
-        spmv(L, L.x, L2.x, L.t, L2.t, [&](int row, double ax, double bx) { L.t[row] = L.b[row] - ax; L2.t[row] = L2.b[row] - bx; });
-        for (int I = threadIdx.x; I < C.n_pad; I += blockDim.x)
-        {
-            double sa = 0.0, sb = 0.0;
-            for (int k = L.mptr[I]; k < L.mptr[I + 1]; k++) { const int m = L.mem[k]; sa += L.t[m]; sb += L2.t[m]; }
-            const double wd = w * C.dinv[I];
-            C.b[I] = sa; C.x[I] = wd * sa;
-            C2.b[I] = sb; C2.x[I] = wd * sb;
-        }
-        __syncthreads();
-    }
-    {
-        const AmgLev &L = g.lev[last];
-        const AmgVec2 &L2 = g2.lev[last];
-        if (g.coarse_inv)
-        {
-            const int n = L.n_pad;
-            for (int r = warp_b; r < n; r += nwarps_b)
-            {
-                double acca = 0.0, accb = 0.0;
-                for (int c = lane; c < n; c += 32)
-                {
-                    const double a = g.coarse_inv[(size_t)r * n + c];
-                    acca = fma(a, L.b[c], acca);
-                    accb = fma(a, L2.b[c], accb);
-                }
-                acca = warp_sum(acca);
-                accb = warp_sum(accb);
-                if (lane == 0) { L.t[r] = acca; L2.t[r] = accb; }
-            }
-            __syncthreads();
-        }
-        else
-        {
-            double *sa = L.x, *da = L.t, *sb = L2.x, *db = L2.t;
-            for (int it = 0; it < g.coarse_sweeps; it++)
-            {
-                double *oa = da, *ob = db;
-                const double *ia = sa, *ib = sb;
-                spmv(L, ia, ib, oa, ob, [&](int row, double ax, double bx) {
-                    const double wd = w * L.dinv[row];
-                    oa[row] = fma(wd, L.b[row] - ax, ia[row]);
-                    ob[row] = fma(wd, L2.b[row] - bx, ib[row]);
-                });
-                double *tmp = sa; sa = da; da = tmp;
-                tmp = sb; sb = db; db = tmp;
-            }
-        }
-    }
-    for (int l = last - 1; l >= first; l--)
-    {
-        const AmgLev &L = g.lev[l];
-        const AmgLev &C = g.lev[l + 1];
-        const AmgVec2 &L2 = g2.lev[l];
-        const AmgVec2 &C2 = g2.lev[l + 1];
-        for (int i = threadIdx.x; i < L.n_pad; i += blockDim.x)
-        {
-            const int I = L.agg[i];
-            if (I >= 0) { L.x[i] = fma(over, C.t[I], L.x[i]); L2.x[i] = fma(over, C2.t[I], L2.x[i]); }
-        }
-        __syncthreads();
-        spmv(L, L.x, L2.x, L.t, L2.t, [&](int row, double ax, double bx) {
-            const double wd = w * L.dinv[row];
-            L.t[row] = fma(wd, L.b[row] - ax, L.x[row]);
-            L2.t[row] = fma(wd, L2.b[row] - bx, L2.x[row]);
-        });
-    }
-}
-
 // (t, t2) = M^-1 (b, b2) on level 0.  The caller has stored the right-hand sides in lev[0].b / lev2[0].b and the
 // pre-smoothed iterates omega D^-1 b in lev[0].x / lev2[0].x and synchronised the grid.
-__device__ __forceinline__ void amg_vcycle2(const AmgArgs &g, const AmgArgs2 &g2, cooperative_groups::grid_group &grid, int *s_next,
-                                            const int *s_wk, StageSmem *S0)
+__device__ __forceinline__ void amg_vcycle2(const AmgArgs &g, const AmgArgs2 &g2, GridBar &grid, int *s_next,
+                                            int *s_wk, StageSmem *S0)
 {
     const int G = gridDim.x, B = blockIdx.x;
     const int last = g.nlev - 1;
-    const int lc = g.local_from;
+    const int lc = g.team_from;
+    const int tid_g = B * blockDim.x + threadIdx.x, nthr_g = G * blockDim.x;
     const double w = g.omega, over = g.over;
     if (last == 0)
     {
         // degenerate one-level hierarchy: M^-1 = damped Jacobi
         const AmgLev &L = g.lev[0];
-        const int r0 = (int)((long long)L.nslices * B / G) * 32, r1 = (int)((long long)L.nslices * (B + 1) / G) * 32;
+        const int r0 = amg_chunk(L.nslices, B, G) * 32, r1 = amg_chunk(L.nslices, B + 1, G) * 32;
         for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x) { L.t[i] = L.x[i]; g2.lev[0].t[i] = g2.lev[0].x[i]; }
         return;
     }
@@ -254,46 +146,40 @@ __device__ __forceinline__ void amg_vcycle2(const AmgArgs &g, const AmgArgs2 &g2
         const AmgLev &L = g.lev[l];
         const AmgLev &C = g.lev[l + 1];
         const AmgVec2 &L2 = g2.lev[l];
-        const AmgVec2 &C2 = g2.lev[l + 1];
-        const int s0 = (int)((long long)L.nslices * B / G), s1 = (int)((long long)L.nslices * (B + 1) / G);
-        amg_spmv_phase2(L, s0, s1, s_wk[2 * l], s_wk[2 * l + 1], L.x, L2.x, L.t, L2.t, s_next,
-                        [&](int row, double ax, double bx) { L.t[row] = L.b[row] - ax; L2.t[row] = L2.b[row] - bx; },
-                        l == 0 ? S0 : nullptr);
+        const int s0 = amg_chunk(L.nslices, B, G), s1 = amg_chunk(L.nslices, B + 1, G);
+        const AmgV<2> lv = amg_vecs<2>(g, &g2, l), cv = amg_vecs<2>(g, &g2, l + 1);
+        if (l == 0)
+            amg_spmv_phase2(L, s0, s1, s_wk[0], s_wk[1], L.x, L2.x, L.t, L2.t, s_next,
+                            [&](int row, double ax, double bx) { L.t[row] = L.b[row] - ax; L2.t[row] = L2.b[row] - bx; }, S0);
+        else
+            amg_spmv_tasks<2, false>(L, lv, cv, s0, s1, s_wk[2 * l], s_wk[2 * l + 1], AMG_EPI_RESIDUAL, w, over, xb_dyn_smem + g.task_smem_offset);
         grid.sync();
-        const int c0 = (int)((long long)C.nslices * B / G) * 32, c1 = (int)((long long)C.nslices * (B + 1) / G) * 32;
-        for (int I = c0 + threadIdx.x; I < c1; I += blockDim.x)
-        {
-            double sa = 0.0, sb = 0.0;
-            for (int k = L.mptr[I]; k < L.mptr[I + 1]; k++) { const int m = L.mem[k]; sa += L.t[m]; sb += L2.t[m]; }
-            const double wd = w * C.dinv[I];
-            C.b[I] = sa; C.x[I] = wd * sa;
-            C2.b[I] = sb; C2.x[I] = wd * sb;
-        }
+        amg_restrict_level<2>(L, C, lv, cv, tid_g, nthr_g, w);
         grid.sync();
     }
-    if (B == 0) amg_block_cycle2(g, g2, lc);
+    if (B < g.team_blocks) amg_team_cycle<2>(g, &g2, s_wk);
     grid.sync();
     for (int l = lc - 1; l >= 0; l--)
     {
         const AmgLev &L = g.lev[l];
-        const AmgLev &C = g.lev[l + 1];
         const AmgVec2 &L2 = g2.lev[l];
-        const AmgVec2 &C2 = g2.lev[l + 1];
-        const int s0 = (int)((long long)L.nslices * B / G), s1 = (int)((long long)L.nslices * (B + 1) / G);
-        for (int i = s0 * 32 + threadIdx.x; i < s1 * 32; i += blockDim.x)
-        {
-            const int I = L.agg[i];
-            if (I >= 0) { L.x[i] = fma(over, C.t[I], L.x[i]); L2.x[i] = fma(over, C2.t[I], L2.x[i]); }
-        }
+        const int s0 = amg_chunk(L.nslices, B, G), s1 = amg_chunk(L.nslices, B + 1, G);
+        const AmgV<2> lv = amg_vecs<2>(g, &g2, l), cv = amg_vecs<2>(g, &g2, l + 1);
+        amg_prolong_rows<2>(L, lv, cv, s0 * 32, s1 * 32, threadIdx.x, blockDim.x, over);
         grid.sync();
-        amg_spmv_phase2(L, s0, s1, s_wk[2 * l], s_wk[2 * l + 1], L.x, L2.x, L.t, L2.t, s_next,
-                        [&](int row, double ax, double bx) {
-                            const double wd = w * L.dinv[row];
-                            L.t[row] = fma(wd, L.b[row] - ax, L.x[row]);
-                            L2.t[row] = fma(wd, L2.b[row] - bx, L2.x[row]);
-                        },
-                        l == 0 ? S0 : nullptr);
-        if (l > 0) grid.sync();
+        if (l == 0)
+            amg_spmv_phase2(L, s0, s1, s_wk[0], s_wk[1], L.x, L2.x, L.t, L2.t, s_next,
+                            [&](int row, double ax, double bx) {
+                                const double wd = w * L.dinv[row];
+                                L.t[row] = fma(wd, L.b[row] - ax, L.x[row]);
+                                L2.t[row] = fma(wd, L2.b[row] - bx, L2.x[row]);
+                            },
+                            S0);
+        else
+        {
+            amg_spmv_tasks<2, false>(L, lv, cv, s0, s1, s_wk[2 * l], s_wk[2 * l + 1], AMG_EPI_POST, w, over, xb_dyn_smem + g.task_smem_offset);
+            grid.sync();
+        }
     }
 }
 

@@ -206,8 +206,8 @@ __device__ __forceinline__ int cnext_slice(int *ctr, int lane)
 
 // z = M^-1 r ; returns this thread's partial of the unconjugated z.r
 template <int PRECOND>
-__device__ __forceinline__ cd cprecond_apply(const CocgArgs &a, const AmgArgs &g, const AmgArgs2 &g2, cg::grid_group &grid, int r0,
-                                             int r1, int warp_g, int nwarps_g, int lane, int *s_next, const int *s_wk, StageSmem *S)
+__device__ __forceinline__ cd cprecond_apply(const CocgArgs &a, const AmgArgs &g, const AmgArgs2 &g2, GridBar &grid, int r0,
+                                             int r1, int warp_g, int nwarps_g, int lane, int *s_next, int *s_wk, StageSmem *S)
 {
     cd dot = make_double2(0., 0.);
     if (PRECOND == XFEMM_PRECOND_AMG)
@@ -295,12 +295,12 @@ __device__ __forceinline__ cd cprecond_apply(const CocgArgs &a, const AmgArgs &g
 }
 
 template <int PRECOND>
-__global__ void __launch_bounds__(512, 1) k_cocg(CocgArgs a, AmgArgs g, AmgArgs2 g2)
+__global__ void __launch_bounds__(512, 1) k_cocg(const __grid_constant__ CocgArgs a, const __grid_constant__ AmgArgs g, const __grid_constant__ AmgArgs2 g2)
 {
-    cg::grid_group grid = cg::this_grid();
     __shared__ double sm[33];
     __shared__ int s_next;
-    __shared__ int s_wk[2 * AMG_MAX_LEVELS];
+    __shared__ int s_wk[AMG_SWK_SIZE];
+    GridBar grid{cg::this_grid(), PRECOND == XFEMM_PRECOND_AMG ? g.grid_ctr : nullptr, s_wk + AMG_SWK_EPOCH + 1};
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     StageSmem S = stage_carve(dyn_smem); // ring for the matrix stream of the real companion's finest level
     const int lane = threadIdx.x & 31;
@@ -320,15 +320,7 @@ __global__ void __launch_bounds__(512, 1) k_cocg(CocgArgs a, AmgArgs g, AmgArgs2
             S.ntiles = a.tile_ptr[blockIdx.x + 1] - a.tile_ptr[blockIdx.x];
             S.tile = a.tiles + a.tile_ptr[blockIdx.x];
         }
-        if (threadIdx.x < g.nlev)
-        {
-            const AmgLev &L = g.lev[threadIdx.x];
-            int k0 = 0, k1 = 0;
-            if (L.wide.n_rows)
-                wide_range(L.wide, (int)((long long)L.nslices * blockIdx.x / G) * 32, (int)((long long)L.nslices * (blockIdx.x + 1) / G) * 32, k0, k1);
-            s_wk[2 * threadIdx.x] = k0; s_wk[2 * threadIdx.x + 1] = k1;
-        }
-        __syncthreads();
+        amg_kernel_init(g, s_wk);
     }
 
     // ||b||^2 ; r = b ; x = 0 unless warm
@@ -909,6 +901,7 @@ int xfemm_clinprob_cocg(xfemm_clinprob *p, double precision, int warm, int preco
         }
         amg_fill_args(R, *R->amg, g);
         amg_fill_args2(R, *R->amg, g2);
+        XB_CUDA(cudaStreamSynchronize(R->stream)); // the barrier counters are zeroed on the companion's stream
     }
     int singular = -1;
     if (!reuse)
@@ -988,7 +981,8 @@ int xfemm_clinprob_cocg(xfemm_clinprob *p, double precision, int warm, int preco
     void *kern = precond == XFEMM_PRECOND_JACOBI ? (void *)k_cocg<XFEMM_PRECOND_JACOBI>
                  : precond == XFEMM_PRECOND_AMG  ? (void *)k_cocg<XFEMM_PRECOND_AMG>
                                                  : (void *)k_cocg<XFEMM_PRECOND_MCSSOR>;
-    const size_t dyn_smem = precond == XFEMM_PRECOND_AMG ? STAGE_SMEM_BYTES : 0;
+    const size_t dyn_smem = precond == XFEMM_PRECOND_AMG ? STAGE_SMEM_BYTES + AMG_TASK_SMEM_BYTES : 0;
+    g.task_smem_offset = (int)STAGE_SMEM_BYTES;
     if (dyn_smem) XB_CUDA(cudaFuncSetAttribute((void (*)(CocgArgs, AmgArgs, AmgArgs2))kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
     XB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (void (*)(CocgArgs, AmgArgs, AmgArgs2))kern, 512, dyn_smem));
     if (per_sm < 1) { set_error("cooperative kernel does not fit on an SM"); return XFEMM_ERR_CUDA; }
@@ -996,6 +990,7 @@ int xfemm_clinprob_cocg(xfemm_clinprob *p, double precision, int warm, int preco
     grid = std::max(1, std::min(p->num_sms * per_sm, (p->lay.nslices + 15) / 16));
     if (p->max_grid < grid) { XB_CUDA(p->partials.alloc((size_t)8 * grid)); p->max_grid = grid; }
     a.part = p->partials.p;
+    if (precond == XFEMM_PRECOND_AMG) g.team_blocks = std::min(g.team_blocks, grid); // the team lives inside this launch
     if (precond == XFEMM_PRECOND_AMG && linprob_ensure_tiles(p->re_prec, grid))
     {
         XB_CUDA(cudaStreamSynchronize(p->re_prec->stream));

@@ -241,8 +241,8 @@ __device__ __forceinline__ int next_slice(int *ctr, int lane)
 }
 
 template <int PRECOND>
-__device__ __forceinline__ double precond_apply(const PcgArgs &a, const AmgArgs &g, cg::grid_group &grid, int r0, int r1,
-                                                int warp_g, int nwarps_g, int lane, int *s_next, const int *s_wk,
+__device__ __forceinline__ double precond_apply(const PcgArgs &a, const AmgArgs &g, GridBar &grid, int r0, int r1,
+                                                int warp_g, int nwarps_g, int lane, int *s_next, int *s_wk,
                                                 StageSmem *S, bool x0_ready = false)
 {
     // returns this thread's partial of r.z ; z is left in a.z (MC-SSOR, AMG) or implied (Jacobi)
@@ -306,12 +306,12 @@ __device__ __forceinline__ double precond_apply(const PcgArgs &a, const AmgArgs 
 }
 
 template <int PRECOND>
-__global__ void __launch_bounds__(1024, 1) k_pcg(PcgArgs a, AmgArgs g)
+__global__ void __launch_bounds__(1024, 1) k_pcg(const __grid_constant__ PcgArgs a, const __grid_constant__ AmgArgs g)
 {
-    cg::grid_group grid = cg::this_grid();
     __shared__ double sm[33];
     __shared__ int s_next;
-    __shared__ int s_wk[2 * AMG_MAX_LEVELS];
+    __shared__ int s_wk[AMG_SWK_SIZE];
+    GridBar grid{cg::this_grid(), PRECOND == XFEMM_PRECOND_AMG ? g.grid_ctr : nullptr, s_wk + AMG_SWK_EPOCH + 1};
     const int lane = threadIdx.x & 31;
     const int nwarps_b = blockDim.x >> 5, warp_b = threadIdx.x >> 5;
     const int warp_g = blockIdx.x * nwarps_b + warp_b, nwarps_g = gridDim.x * nwarps_b;
@@ -334,16 +334,7 @@ __global__ void __launch_bounds__(1024, 1) k_pcg(PcgArgs a, AmgArgs g)
     }
     if (PRECOND == XFEMM_PRECOND_AMG)
     {
-        // wide rows of this block's chunk of every level
-        if (threadIdx.x < g.nlev)
-        {
-            const AmgLev &L = g.lev[threadIdx.x];
-            int k0 = 0, k1 = 0;
-            if (L.wide.n_rows)
-                wide_range(L.wide, (int)((long long)L.nslices * blockIdx.x / G) * 32, (int)((long long)L.nslices * (blockIdx.x + 1) / G) * 32, k0, k1);
-            s_wk[2 * threadIdx.x] = k0; s_wk[2 * threadIdx.x + 1] = k1;
-        }
-        __syncthreads();
+        amg_kernel_init(g, s_wk); // wide rows of this block's chunk of every level, team barrier state
     }
 
     // ---- res_o = b . M^-1 b   (spars.cpp:257-259) ; z0 is computed with r := b
@@ -437,21 +428,59 @@ __global__ void __launch_bounds__(1024, 1) k_pcg(PcgArgs a, AmgArgs g)
         if (PRECOND == XFEMM_PRECOND_JACOBI)
         {
             part = 0.0;
-            for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x)
+            for (int i = r0 + threadIdx.x; i < r1; i += 4 * blockDim.x)
             {
-                double ri = fma(-del, a.u[i], a.r[i]);
-                a.r[i] = ri;
-                part = fma(ri * a.dinv[i], ri, part);
+                double uv[4], rv[4], dv[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                {
+                    const int k = i + q * blockDim.x;
+                    const bool ok = k < r1;
+                    uv[q] = ok ? a.u[k] : 0.0;
+                    rv[q] = ok ? a.r[k] : 0.0;
+                    dv[q] = ok ? a.dinv[k] : 0.0;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                {
+                    const int k = i + q * blockDim.x;
+                    if (k < r1)
+                    {
+                        const double ri = fma(-del, uv[q], rv[q]);
+                        a.r[k] = ri;
+                        part = fma(ri * dv[q], ri, part);
+                    }
+                }
             }
         }
         else
         {
-            for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x)
+            // four rows per thread and step, loads ahead of the stores (the arrays may alias as far as the compiler
+            // knows: written row by row, every step would wait for the previous one's stores)
+            for (int i = r0 + threadIdx.x; i < r1; i += 4 * blockDim.x)
             {
-                const double ri = fma(-del, a.u[i], a.r[i]);
-                a.r[i] = ri;
-                // multigrid: the pre-smoothed iterate of the finest level comes for free here
-                if (PRECOND == XFEMM_PRECOND_AMG) g.lev[0].x[i] = g.omega * a.dinv[i] * ri;
+                double uv[4], rv[4], dv[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                {
+                    const int k = i + q * blockDim.x;
+                    const bool ok = k < r1;
+                    uv[q] = ok ? a.u[k] : 0.0;
+                    rv[q] = ok ? a.r[k] : 0.0;
+                    if (PRECOND == XFEMM_PRECOND_AMG) dv[q] = ok ? a.dinv[k] : 0.0;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                {
+                    const int k = i + q * blockDim.x;
+                    if (k < r1)
+                    {
+                        const double ri = fma(-del, uv[q], rv[q]);
+                        a.r[k] = ri;
+                        // multigrid: the pre-smoothed iterate of the finest level comes for free here
+                        if (PRECOND == XFEMM_PRECOND_AMG) g.lev[0].x[k] = g.omega * dv[q] * ri;
+                    }
+                }
             }
             grid.sync();
             if (PRECOND == XFEMM_PRECOND_AMG) amg_stamp(g, ck, AMG_MAX_STAMPS);
@@ -466,12 +495,29 @@ __global__ void __launch_bounds__(1024, 1) k_pcg(PcgArgs a, AmgArgs g)
         const double rho = res_new / res;
         res = res_new;
         // step ii: V += del P, then step v: P = Z + rho P
-        for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x)
+        for (int i = r0 + threadIdx.x; i < r1; i += 4 * blockDim.x)
         {
-            const double pi = a.p[i];
-            a.x[i] = fma(del, pi, a.x[i]);
-            double zi = (PRECOND == XFEMM_PRECOND_JACOBI) ? a.r[i] * a.dinv[i] : a.z[i];
-            a.p[i] = fma(rho, pi, zi);
+            double pv[4], xv[4], zv[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+            {
+                const int k = i + q * blockDim.x;
+                const bool ok = k < r1;
+                pv[q] = ok ? a.p[k] : 0.0;
+                xv[q] = ok ? a.x[k] : 0.0;
+                if (PRECOND == XFEMM_PRECOND_JACOBI) zv[q] = ok ? a.r[k] * a.dinv[k] : 0.0;
+                else zv[q] = ok ? a.z[k] : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+            {
+                const int k = i + q * blockDim.x;
+                if (k < r1)
+                {
+                    a.x[k] = fma(del, pv[q], xv[q]);
+                    a.p[k] = fma(rho, pv[q], zv[q]);
+                }
+            }
         }
         if (PRECOND == XFEMM_PRECOND_AMG) amg_stamp(g, ck, AMG_MAX_STAMPS);
         it++;
@@ -488,11 +534,11 @@ __global__ void __launch_bounds__(1024, 1) k_pcg(PcgArgs a, AmgArgs g)
 }
 
 template <int PRECOND>
-__global__ void __launch_bounds__(512, 2) k_precond_only(PcgArgs a, AmgArgs g)
+__global__ void __launch_bounds__(512, 2) k_precond_only(const __grid_constant__ PcgArgs a, const __grid_constant__ AmgArgs g)
 {
-    cg::grid_group grid = cg::this_grid();
     __shared__ int s_next;
-    __shared__ int s_wk[2 * AMG_MAX_LEVELS];
+    __shared__ int s_wk[AMG_SWK_SIZE];
+    GridBar grid{cg::this_grid(), PRECOND == XFEMM_PRECOND_AMG ? g.grid_ctr : nullptr, s_wk + AMG_SWK_EPOCH + 1};
     const int lane = threadIdx.x & 31;
     const int nwarps_b = blockDim.x >> 5, warp_b = threadIdx.x >> 5;
     const int warp_g = blockIdx.x * nwarps_b + warp_b, nwarps_g = gridDim.x * nwarps_b;
@@ -502,15 +548,7 @@ __global__ void __launch_bounds__(512, 2) k_precond_only(PcgArgs a, AmgArgs g)
     const int r0 = s0 * 32, r1 = s1 * 32;
     if (PRECOND == XFEMM_PRECOND_AMG)
     {
-        if (threadIdx.x < g.nlev)
-        {
-            const AmgLev &L = g.lev[threadIdx.x];
-            int k0 = 0, k1 = 0;
-            if (L.wide.n_rows)
-                wide_range(L.wide, (int)((long long)L.nslices * blockIdx.x / G) * 32, (int)((long long)L.nslices * (blockIdx.x + 1) / G) * 32, k0, k1);
-            s_wk[2 * threadIdx.x] = k0; s_wk[2 * threadIdx.x + 1] = k1;
-        }
-        __syncthreads();
+        amg_kernel_init(g, s_wk);
     }
     precond_apply<PRECOND>(a, g, grid, r0, r1, warp_g, nwarps_g, lane, &s_next, s_wk, nullptr);
     if (PRECOND == XFEMM_PRECOND_JACOBI)
@@ -706,6 +744,7 @@ int linprob_build_layout(xfemm_linprob *p, int precond)
     p->tile_grid = -1; // and so are the stream tiles
     SellLayout &L = p->lay;
     int sigma = env_int("XFEMM_SELL_SIGMA", 1024);
+    const int wide_thr = p->wide_threshold >= 0 ? p->wide_threshold : env_int("XFEMM_WIDE_ROW", 64);
     // with node coordinates the internal order follows a Z-curve through the plane (gather locality)
     std::vector<int> zorder;
     if ((int)p->h_xy.size() == 2 * p->n && env_int("XFEMM_MORTON", 1)) morton_order(p->n, p->h_xy.data(), zorder);
@@ -715,10 +754,10 @@ int linprob_build_layout(xfemm_linprob *p, int precond)
     {
         std::vector<int> color;
         int nc = greedy_coloring(p->n, p->h_rowptr.data(), p->h_col.data(), env_int("XFEMM_MAX_COLORS", 7), color);
-        build_sell_layout(p->n, p->h_rowptr.data(), p->h_col.data(), &color, nc, sigma, L, env_int("XFEMM_WIDE_ROW", 64), base);
+        build_sell_layout(p->n, p->h_rowptr.data(), p->h_col.data(), &color, nc, sigma, L, wide_thr, base);
     }
     else
-        build_sell_layout(p->n, p->h_rowptr.data(), p->h_col.data(), nullptr, 0, sigma, L, env_int("XFEMM_WIDE_ROW", 64), base);
+        build_sell_layout(p->n, p->h_rowptr.data(), p->h_col.data(), nullptr, 0, sigma, L, wide_thr, base);
     cudaStream_t st = p->stream;
     XB_CUDA(p->i2c.upload(L.i2c.data(), L.i2c.size(), st));
     XB_CUDA(p->c2i.upload(L.c2i.data(), L.c2i.size(), st));
@@ -1245,18 +1284,19 @@ int linprob_apply_amg_resident(xfemm_linprob *p)
     if (!p->amg) { set_error("multigrid hierarchy not prepared"); return XFEMM_ERR_ARG; }
     PcgArgs a = make_args(p, 0, 0, 0);
     AmgArgs g;
-    amg_fill_args(p, *p->amg, g);
     void *kargs[] = {&a, &g};
     if (p->precond_grid <= 0)
     {
         int grid = 0;
-        int rc = coop_grid(p, k_precond_only<XFEMM_PRECOND_AMG>, 512, &grid);
+        int rc = coop_grid(p, k_precond_only<XFEMM_PRECOND_AMG>, 512, &grid, AMG_TASK_SMEM_BYTES);
         if (rc != XFEMM_OK) return rc;
         p->precond_grid = grid;
     }
+    amg_fill_args(p, *p->amg, g, p->precond_grid);
+    g.task_smem_offset = 0;
     a.part = p->partials.p;
     ++g_launch;
-    XB_CUDA(cudaLaunchCooperativeKernel((void *)k_precond_only<XFEMM_PRECOND_AMG>, dim3(p->precond_grid), dim3(512), kargs, 0, p->stream));
+    XB_CUDA(cudaLaunchCooperativeKernel((void *)k_precond_only<XFEMM_PRECOND_AMG>, dim3(p->precond_grid), dim3(512), kargs, AMG_TASK_SMEM_BYTES, p->stream));
     return XFEMM_OK;
 }
 // stream tiles of the finest level for a launch with `grid` blocks (stage.cuh); false: use direct loads
@@ -1303,7 +1343,6 @@ int xfemm_linprob_pcg(xfemm_linprob *p, double precision, int warm, int precond,
     PcgArgs a = make_args(p, precision, warm ? 1 : 0, max_iter);
     int grid = 0;
     AmgArgs g;
-    if (precond == XFEMM_PRECOND_AMG) amg_fill_args(p, *p->amg, g);
     void *kargs[] = {&a, &g};
     XB_CUDA(cudaEventRecord(e1, st));
     if (precond == XFEMM_PRECOND_JACOBI)
@@ -1322,11 +1361,14 @@ int xfemm_linprob_pcg(xfemm_linprob *p, double precision, int warm, int precond,
     else if (precond == XFEMM_PRECOND_AMG)
     {
         const int threads = env_int("XFEMM_PCG_THREADS", 1024);
-        rc = coop_grid(p, k_pcg<XFEMM_PRECOND_AMG>, threads, &grid, STAGE_SMEM_BYTES);
+        const size_t smem = STAGE_SMEM_BYTES + AMG_TASK_SMEM_BYTES; // matrix-stream ring, then the task buffer of the coarse levels
+        rc = coop_grid(p, k_pcg<XFEMM_PRECOND_AMG>, threads, &grid, smem);
         if (rc != XFEMM_OK) return rc;
+        amg_fill_args(p, *p->amg, g, grid);
+        g.task_smem_offset = (int)STAGE_SMEM_BYTES;
         a.part = p->partials.p;
         if (ensure_tiles(p, grid)) { a.tiles = p->tiles.p; a.tile_ptr = p->tile_ptr.p; }
-        ++xb::g_launch; XB_CUDA(cudaLaunchCooperativeKernel((void *)k_pcg<XFEMM_PRECOND_AMG>, dim3(grid), dim3(threads), kargs, STAGE_SMEM_BYTES, st));
+        ++xb::g_launch; XB_CUDA(cudaLaunchCooperativeKernel((void *)k_pcg<XFEMM_PRECOND_AMG>, dim3(grid), dim3(threads), kargs, smem, st));
     }
     else
     {
@@ -1413,7 +1455,6 @@ int xfemm_linprob_multpc(xfemm_linprob *p, int precond, const double *x, double 
     PcgArgs a = make_args(p, 0, 0, 0);
     int grid = 0;
     AmgArgs g;
-    if (precond == XFEMM_PRECOND_AMG) amg_fill_args(p, *p->amg, g);
     void *kargs[] = {&a, &g};
     if (precond == XFEMM_PRECOND_JACOBI)
     {
@@ -1423,10 +1464,12 @@ int xfemm_linprob_multpc(xfemm_linprob *p, int precond, const double *x, double 
     }
     else if (precond == XFEMM_PRECOND_AMG)
     {
-        rc = coop_grid(p, k_precond_only<XFEMM_PRECOND_AMG>, 512, &grid);
+        rc = coop_grid(p, k_precond_only<XFEMM_PRECOND_AMG>, 512, &grid, AMG_TASK_SMEM_BYTES);
         if (rc != XFEMM_OK) return rc;
+        amg_fill_args(p, *p->amg, g, grid);
+        g.task_smem_offset = 0;
         a.part = p->partials.p;
-        ++xb::g_launch; XB_CUDA(cudaLaunchCooperativeKernel((void *)k_precond_only<XFEMM_PRECOND_AMG>, dim3(grid), dim3(512), kargs, 0, st));
+        ++xb::g_launch; XB_CUDA(cudaLaunchCooperativeKernel((void *)k_precond_only<XFEMM_PRECOND_AMG>, dim3(grid), dim3(512), kargs, AMG_TASK_SMEM_BYTES, st));
     }
     else
     {

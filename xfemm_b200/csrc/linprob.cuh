@@ -30,6 +30,7 @@ struct xfemm_linprob
     // boundary representation
     std::vector<int> h_rowptr, h_col;
     std::vector<float> h_xy;       // optional node coordinates (x,y per row): locality hint for the internal order
+    int wide_threshold = -1;       // rows with more off-diagonals are kept out of the SELL slices (-1: XFEMM_WIDE_ROW, 64)
     std::vector<int> forced_order; // optional: the internal row order to use as is (a companion of another problem)
     xb::DevBuf<int> rowptr, col;
     xb::DevBuf<double> vals, b, V, Vold;
