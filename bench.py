@@ -36,8 +36,30 @@ sys.path.insert(0, ROOT)
 REF = os.path.join(ROOT, "oracle", "_ref")
 GOLD_FEM = os.path.join(ROOT, "tests", "golden", "tb", "tb.fem")
 
-# reference SSOR-PCG iteration counts measured with the unmodified reference
-REF_ITERS = {0.0018: 1868, 0.0053: 641, 0.0167: 214, 0.053: 116}
+PROFILES = os.path.join(ROOT, "profiles")
+
+
+def reference_record(mesh_size):
+    """Full, unscaled run of the unmodified reference on this workload, recorded by tests/golden/make_golden_scale.py
+    (build container) — iteration count, phase times — or None.  The SSOR-PCG iteration count is a property of the
+    assembled system, not of the machine: it is what the sampled reference arm scales its iteration sample to."""
+    gdir = os.path.join(ROOT, "tests", "golden")
+    for name in sorted(os.listdir(gdir)):
+        f = os.path.join(gdir, name, "golden.json")
+        if os.path.exists(f):
+            g = json.load(open(f))
+            if abs(g.get("mesh_size", -1) - mesh_size) < 1e-12:
+                return g
+    return None
+
+
+def workload_config(workload, mesh_size, n_nodes, n_elems, n_pbc):
+    """The `config` object: identical for the GPU arm and the reference arm (everything that is specific to one
+    implementation lives under `implementation`)."""
+    return {"workload": workload, "mesh_size_cm": mesh_size, "n_nodes": n_nodes, "n_elems": n_elems, "n_pbc": n_pbc,
+            "precision": 1e-10,
+            "l2": ("inputs larger than L2" if 140.0 * n_nodes > 126e6 else "inputs SMALLER than L2 (not the headline size)")
+                  + ": matrix + vectors of one problem are about %.0f MB (140 B per node) against 126 MB" % (140.0 * n_nodes / 1e6)}
 
 
 def set_mesh_size(text, size):
@@ -147,7 +169,10 @@ class ClockSampler(threading.Thread):
 
 
 def run_reference(base, ref_iters, ref_pbc, total_ref_iters):
-    """Times the unmodified reference on a bounded sample and scales to one whole problem."""
+    """Times the unmodified reference (oracle/_ref/ref_harness: the reference's own objects, one thread — it has no
+    threading) on one whole problem.  ref_iters / ref_pbc > 0: a bounded sample — full assembly + Dirichlet, `ref_pbc`
+    periodic pairs, `ref_iters` SSOR-PCG iterations — scaled to the full pair count and to the reference's
+    iteration count for this system; both <= 0: the full run, nothing scaled."""
     h = os.path.join(REF, "ref_harness")
     if not os.path.exists(h):
         raise RuntimeError("oracle/_ref/ref_harness is missing")
@@ -160,15 +185,47 @@ def run_reference(base, ref_iters, ref_pbc, total_ref_iters):
     pbc_applied = max(1, m["pbc_applied"]) if n_pbc else 0
     t_pbc_full = m["t_pbc"] * (n_pbc / pbc_applied) if n_pbc else 0.0
     it_done = sum(m["iters"]) or 1
+    full = ref_iters <= 0 and ref_pbc <= 0
+    if full:
+        # the harness does not replay the recurrence in a full run: the count comes from the record of the same system
+        it_done = total_ref_iters or it_done
     ms_per_iter = 1e3 * sum(m["pcg_secs"]) / it_done
     iters_full = total_ref_iters if total_ref_iters else it_done
-    t_pcg_full = ms_per_iter * 1e-3 * iters_full
+    t_pcg_full = sum(m["pcg_secs"]) if full else ms_per_iter * 1e-3 * iters_full
     t_asm = m["t_assembly_first"]
+    sample = (f"FULL run, nothing scaled: assembly+Dirichlet {t_asm:.2f}s, {n_pbc} periodic pairs {t_pbc_full:.1f}s, "
+              f"SSOR-PCG {t_pcg_full:.1f}s ({iters_full} iterations); harness wall {wall:.0f}s" if full else
+              f"full assembly+Dirichlet ({t_asm:.2f}s), {pbc_applied}/{n_pbc} periodic pairs, "
+              f"{it_done} of {iters_full} SSOR-PCG iterations ({ms_per_iter:.1f} ms/iter); harness wall {wall:.0f}s")
     return {"s_per_problem": t_asm + t_pbc_full + t_pcg_full, "t_assembly": t_asm, "t_pbc_scaled": t_pbc_full,
-            "t_pcg_scaled": t_pcg_full, "ms_per_iter": ms_per_iter, "iters_assumed": iters_full,
-            "sample": f"full assembly+Dirichlet ({t_asm:.2f}s), {pbc_applied}/{n_pbc} periodic pairs, "
-                      f"{it_done} of {iters_full} SSOR-PCG iterations ({ms_per_iter:.1f} ms/iter); harness wall {wall:.0f}s",
-            "t_load_mesh": m["t_load_mesh"], "t_cuthill": m["t_cuthill"], "n_nodes": m["n_nodes"]}
+            "t_pcg_scaled": t_pcg_full, "ms_per_iter": ms_per_iter, "iters_assumed": iters_full, "full": full,
+            "sample": sample, "t_load_mesh": m["t_load_mesh"], "t_cuthill": m["t_cuthill"], "n_nodes": m["n_nodes"],
+            "n_elems": m["n_elems"], "n_pbc": n_pbc, "harness_wall_s": wall}
+
+
+def reference_calibration(info, mesh_size):
+    """The sampled arm next to the full runs on record: tests/golden (build container) and, when one was made on a GPU
+    box, profiles/r02_reference_full_gpubox_<mesh>.json.  sample_over_full compares like with like (same host) only
+    for the latter."""
+    cal = {}
+    g = reference_record(mesh_size)
+    if g:
+        f = g["full_reference_run"]
+        cal["build_container_full_run"] = {"s_per_problem": f["phases_s"]["t_assembly_first"] + f["phases_s"]["t_pbc"] + f["phases_s"]["t_pcg"],
+                                           "iterations": g["reference_iterations"], "ms_per_iteration": f["ms_per_iteration"],
+                                           "periodic_pairs_s": f["phases_s"]["t_pbc"], "source": "tests/golden (make_golden_scale.py)"}
+    p = os.path.join(PROFILES, f"r02_reference_full_gpubox_ms{mesh_size}.json")
+    if os.path.exists(p):
+        try:
+            f = json.loads(open(p).read().strip().splitlines()[-1])
+            cal["gpu_box_full_run"] = {"s_per_problem": f["value"], "sample": f["cpu_baseline"]["sample"], "source": os.path.relpath(p, ROOT)}
+            if not info["full"]:
+                r = info["s_per_problem"] / f["value"]
+                cal["sample_over_gpu_box_full_run"] = r
+                cal["within_5pct"] = bool(abs(r - 1.0) <= 0.05)
+        except Exception as ex:
+            cal["gpu_box_full_run"] = f"unreadable: {ex}"
+    return cal
 
 
 def pcg_bytes_per_iteration(X, S, precond, nnz, n):
@@ -210,61 +267,101 @@ def ncu_traffic(precond, iterations):
         return None
 
 
+def measured_hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
 def run_partitioned(args, base, workload, rank, local_rank, world):
-    """Config 5b: all N GPUs solve ONE linear system (row-block partitioned Jacobi-PCG, halo over NCCL)."""
+    """Config 5b: all N GPUs solve ONE linear system.  Row-partitioned multigrid-preconditioned CG with the SAME
+    hierarchy as on one GPU: one persistent kernel per GPU, halo entries and the two scalars of an iteration as peer
+    stores + flags over NVLink (xfemm_dpcg_*, csrc/dist_amg.cu).  `--dist-solver nccl` runs the round-1 path instead
+    (Jacobi, torch.distributed collectives per iteration) for comparison.  scaling = strong."""
     import torch
     import torch.distributed as dist
     import xfemm_b200 as X
-    from xfemm_b200.dist_pcg import DistPCG
+    import ctypes as C
 
-    if world == 1:
+    if world == 1 and not dist.is_initialized():
         dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29517", rank=0, world_size=1,
                                 device_id=torch.device(f"cuda:{local_rank}"))
+    t0 = time.time()
     S = X.FSolver(base)
     S.set_option("assemble_only", 1)
-    S.set_option("precond", X.PRECOND_JACOBI)
+    S.set_option("precond", X.PRECOND_AMG)
+    S.set_option("locality_order", 1)  # Z-curve row order: a rank's rows are a compact patch of the mesh, its halo a few thousand rows
     S.load_mesh(False)
     S.renumber(False)
     S.solve()
+    t_setup = time.time() - t0
     c = S.counts()
-    dprec = X.PRECOND_AMG if os.environ.get("XFEMM_DIST_PRECOND") == "amg" else X.PRECOND_JACOBI  # see dist_pcg.py
-    D = DistPCG(S, precond=dprec)
-    D.refresh()
+    nnz = X.lib().xfemm_fsolver_nnz(S.h)
+    n = c["n_unknowns"]
+    if args.dist_solver == "nccl":
+        from xfemm_b200.dist_pcg import DistPCG
+        D = DistPCG(S, precond=X.PRECOND_JACOBI)
+        D.refresh()
+        solve = lambda: D.solve(1e-10)
+        bytes_iter, levels, label = 12.0 * nnz + 148.0 * n, None, "jacobi, NCCL collectives per iteration (round-1 path)"
+    else:
+        from xfemm_b200.dist_amg import DistAmgPCG
+        t0 = time.time()
+        D = DistAmgPCG(S)
+        t_plan = time.time() - t0
+        solve = lambda: D.solve(1e-10)
+        bytes_iter, levels = pcg_bytes_per_iteration(X, S, X.PRECOND_AMG, nnz, n)
+        label = "multigrid V-cycle, global hierarchy"
     launches0 = int(X.lib().xfemm_launch_count())
     infos = []
+    sampler = ClockSampler(local_rank)
     for i in range(args.warmup + args.steps):
         dist.barrier()
         torch.cuda.synchronize()
         if i == args.warmup:
             launches0 = int(X.lib().xfemm_launch_count())
-        infos.append(D.solve(1e-10))
+            if rank == 0:
+                sampler.start()
+        infos.append(solve())
+    sampler.stop_flag = True
     infos = infos[args.warmup:]
     ms = torch.tensor([sum(i["solve_ms"] for i in infos) / len(infos)], dtype=torch.float64, device="cuda")
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    blocks = [None] * world
-    dist.all_gather_object(blocks, {"n_own": D.n_own, "n_halo": D.n_halo, "n_send": D.n_send})
-    V = D.gather_solution()
+    V = D.solution() if args.dist_solver != "nccl" else D.gather_solution()
+    plan = D.stats() if args.dist_solver != "nccl" else None
+    plans = [None] * world
+    dist.all_gather_object(plans, plan)
     if rank == 0:
         its = infos[-1]["iterations"]
-        nnz = X.lib().xfemm_fsolver_nnz(S.h)
-        n = c["n_unknowns"]
-        bytes_iter = 12.0 * nnz + 124.0 * n
         v = float(ms.item()) * 1e-3
-        print(json.dumps({
+        peak, peak_src = measured_hbm_peak()
+        achieved = bytes_iter * its / v / 1e9
+        rec = reference_record(args.mesh_size)
+        line = {
             "metric": "fsolver_static2d_s_per_problem", "value": v, "unit": "s/problem", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": v * 1e3, "higher_is_better": False,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload + " — ONE mesh row-partitioned over the GPUs (config 5b)", "n_nodes": c["n_nodes"],
-                       "nnz_full": nnz, "precision": 1e-10,
-                       "preconditioner": "jacobi" if dprec == X.PRECOND_JACOBI else "multigrid V-cycle of each rank's diagonal block",
-                       "parallelism": f"row blocks of the Cuthill-McKee ordered matrix, halo all_to_all + 2 all_reduce per iteration (NCCL), {world} ranks",
-                       "step": "the linear solve of one problem (assembly is replicated, <1 ms)", "blocks": blocks},
-            "pcg": {"iterations": its, "ms": v * 1e3, "ms_per_iter": v * 1e3 / its, "er": infos[-1]["er"]},
-            "roofline": {"bound": "hbm", "kernel": "kd_spmv_dot + kd_update + kd_direction (per rank)",
-                         "achieved": bytes_iter * its / v / 1e9, "peak": 6650.0 * world, "unit": "GB/s",
-                         "frac": bytes_iter * its / v / 1e9 / (6650.0 * world), "traffic": None},
+            "config": workload_config(workload + " — ONE mesh row-partitioned over the GPUs (config 5b)", args.mesh_size,
+                                      c["n_nodes"], c["n_elems"], c["n_pbc"]),
+            "implementation": {"nnz_full": nnz, "preconditioner": label,
+                               "parallelism": f"{world} ranks, contiguous ranges of the Z-curve ordered rows of the big multigrid levels; small "
+                                              "levels cycled by every rank; halo + scalars as peer stores and flags over NVLink inside one "
+                                              "persistent kernel per GPU" if args.dist_solver != "nccl" else
+                                              f"{world} ranks, row blocks of the Cuthill-McKee ordered matrix, all_to_all + 2 all_reduce per iteration (NCCL)",
+                               "step": "the linear solve of one problem (assembly and multigrid value refresh are replicated on every rank, untimed here: <2 ms)",
+                               "plan_per_rank": plans, "multigrid_levels": levels},
+            "pcg": {"iterations": its, "reference_iterations": sum(rec["reference_iterations"]) if rec else None,
+                    "ms": v * 1e3, "ms_per_iter": v * 1e3 / max(1, its), "er": infos[-1]["er"]},
+            "roofline": {"bound": "hbm", "kernel": "k_dpcg (persistent partitioned PCG, all ranks)" if args.dist_solver != "nccl" else "kd_* + NCCL",
+                         "achieved": achieved, "peak": peak * world, "peak_source": peak_src + f" x {world} GPUs", "unit": "GB/s",
+                         "frac": achieved / (peak * world), "traffic": None, "bytes_per_iter": bytes_iter},
+            "e2e": None,
+            "host_setup_s": {"load_renumber_assemble_hierarchy": t_setup},
             "gpu_launches": int(X.lib().xfemm_launch_count()) - launches0,
-            "solution_norm": float((V * V).sum() ** 0.5)}))
+            "clocks": sampler.summary(),
+            "solution_norm": float((V * V).sum() ** 0.5)}
+        print(json.dumps(line))
     D.close()
     S.close()
     dist.destroy_process_group()
@@ -281,10 +378,14 @@ def main():
     ap.add_argument("--precond", default=os.environ.get("XFEMM_PRECOND", "amg"), choices=["jacobi", "mcssor", "amg"])
     ap.add_argument("--ref-iters", type=int, default=40)
     ap.add_argument("--ref-pbc", type=int, default=40)
+    ap.add_argument("--ref-full", action="store_true",
+                    help="reference arm: ONE full, unscaled run of the reference (all periodic pairs, all iterations; "
+                         "minutes at 2 M nodes) instead of the bounded sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true", help="skip the runs with the other preconditioners")
     ap.add_argument("--partitioned", action="store_true",
                     help="config 5b: ONE mesh row-partitioned over the N GPUs (strong scaling) instead of the sweep")
+    ap.add_argument("--dist-solver", default="peer", choices=["peer", "nccl"], help="--partitioned: peer-memory multigrid kernel (default) or the round-1 NCCL/Jacobi path")
     ap.add_argument("--workdir", default=os.environ.get("XFEMM_BENCH_DIR", "/tmp/xfemm_bench"))
     args = ap.parse_args()
 
@@ -293,7 +394,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     workload = f"TorqueBenchmark planar magnetostatic, fmesher mesh size {args.mesh_size} cm, linear, Static2D FP64 PCG"
     workdir = os.path.join(args.workdir, f"ms{args.mesh_size}")
-    total_ref_iters = REF_ITERS.get(args.mesh_size, 0)
+    rec = reference_record(args.mesh_size)
+    total_ref_iters = sum(rec["reference_iterations"]) if rec else 0
 
     if args.impl == "reference":
         if rank != 0:
@@ -301,16 +403,25 @@ def main():
         base = prepare_mesh(workdir, args.mesh_size)
         vals = []
         info = None
-        for _ in range(max(1, min(args.steps, 2))):
-            info = run_reference(base, args.ref_iters, args.ref_pbc, total_ref_iters)
+        if args.ref_full:
+            info = run_reference(base, 0, 0, total_ref_iters)
             vals.append(info["s_per_problem"])
+        else:
+            for _ in range(max(1, min(args.steps, 2))):
+                info = run_reference(base, args.ref_iters, args.ref_pbc, total_ref_iters)
+                vals.append(info["s_per_problem"])
         v = sum(vals) / len(vals)
         line = {"impl": "reference", "metric": "fsolver_static2d_s_per_problem", "value": v, "unit": "s/problem",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": v * 1e3,
                 "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload, "n_nodes": info["n_nodes"]},
+                "config": workload_config(workload, args.mesh_size, info["n_nodes"], info["n_elems"], info["n_pbc"]),
                 "cpu_baseline": {"value": v, "unit": "s/problem", "cores": 1, "kind": "reference", "sample": info["sample"]},
-                "e2e": {"value": v, "unit": "s/problem", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+                "e2e": {"value": v, "unit": "s/problem", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "reference_phases_s": {"assembly": info["t_assembly"], "periodic_pairs": info["t_pbc_scaled"], "pcg": info["t_pcg_scaled"],
+                                       "ms_per_iteration": info["ms_per_iter"], "iterations": info["iters_assumed"],
+                                       "load_mesh": info["t_load_mesh"], "cuthill": info["t_cuthill"]},
+                "calibration": reference_calibration(info, args.mesh_size),
+                "timed_region_s": info["harness_wall_s"] if args.ref_full else None}
         print(json.dumps(line))
         return 0
 
@@ -476,18 +587,13 @@ def main():
     pcg_ms = sum(solve_ms) / len(solve_ms)
     its = sum(iters) / len(iters)
     achieved = bytes_iter * its / (pcg_ms * 1e-3) / 1e9 if pcg_ms > 0 else 0.0
-    peak, peak_src = 6650.0, "fallback"
-    try:
-        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
-        peak_src = "measured"
-    except Exception:
-        pass
+    peak, peak_src = measured_hbm_peak()
     line = {
         "metric": "fsolver_static2d_s_per_problem", "value": value, "unit": "s/problem", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": value * 1e3 * world, "higher_is_better": False,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload, "n_nodes": c["n_nodes"], "n_elems": c["n_elems"], "nnz_full": nnz,
-                   "n_pbc": c["n_pbc"], "precision": 1e-10, "preconditioner": args.precond,
+        "config": workload_config(workload, args.mesh_size, c["n_nodes"], c["n_elems"], c["n_pbc"]),
+        "implementation": {"nnz_full": nnz, "preconditioner": args.precond,
                    "l2_note": "matrix+vectors (%.0f MB) exceed the 126 MB L2" % ((12.0 * nnz + 56.0 * n) / 1e6),
                    "parallelism": f"rotor-angle sweep: {world} independent positions at a time, one per GPU (each rank a contiguous block of the 360 positions), no collective",
                    "step": "one rotor position of the sweep: AGE re-target + assembly of all elements + Dirichlet + periodic pairs "
@@ -515,7 +621,7 @@ def main():
         try:
             info = run_reference(base, args.ref_iters, args.ref_pbc, total_ref_iters)
             line["cpu_baseline"] = {"value": info["s_per_problem"], "unit": "s/problem", "cores": 1, "kind": "reference",
-                                    "sample": info["sample"]}
+                                    "sample": info["sample"], "calibration": reference_calibration(info, args.mesh_size)}
         except Exception as ex:  # the line must still print
             line["cpu_baseline"] = {"value": None, "unit": "s/problem", "cores": 1, "kind": "reference",
                                     "sample": f"unavailable: {ex}"}

@@ -381,6 +381,31 @@ int xfemm_dist_direction(xfemm_dist *d, const double *glob_dev);           /* p 
 int xfemm_dist_get_solution(xfemm_dist *d, double *x_own);
 unsigned long long xfemm_dist_stream(xfemm_dist *d);                       /* cudaStream_t the kernels run on */
 
+/* ------------------------------------------------------------------ one mesh over several GPUs, multigrid-preconditioned
+ * (csrc/dist_amg.cu).  The recurrence and the stopping rule are CBigLinProb::PCGSolve's (cfemm/libfemm/spars.cpp:238-316),
+ * the preconditioner is the SAME multigrid hierarchy as on one GPU (iteration counts do not depend on the rank
+ * count).  One process per GPU; every rank holds the assembled, boundary-conditioned problem `p` and works on a
+ * contiguous share of the rows of the big levels; halo entries and the two scalars of an iteration travel as peer
+ * stores + flags over NVLink inside ONE persistent kernel per GPU (no collective call, no host in the loop).
+ *   create  : plan (send lists) + symmetric communication arena of this rank
+ *   ipc_handle / connect : exchange of the 64-byte CUDA IPC handles of the arenas through any channel the host
+ *             has (torch.distributed, MPI ...), all `world` handles in rank order;  connect_files: rendezvous
+ *             through files <dir>/<job>.<rank> for hosts without one (the C++ front end)
+ *   solve   : every rank, same arguments; the kernels wait for each other on the device (deadline
+ *             XFEMM_DIST_TIMEOUT_MS, default 20 s: a lost rank gives XFEMM_ERR_DIVERGED, not a hung GPU).
+ *             info->solve_ms = the persistent kernel (CUDA events)
+ *   share_solution, [host barrier], finish : own rows of x to every rank, then the complete solution in p's V */
+typedef struct xfemm_dpcg xfemm_dpcg;
+int xfemm_dpcg_create(xfemm_linprob *p, int rank, int world, xfemm_dpcg **out);
+int xfemm_dpcg_destroy(xfemm_dpcg *d);
+int xfemm_dpcg_ipc_handle(xfemm_dpcg *d, void *handle64);
+int xfemm_dpcg_connect(xfemm_dpcg *d, const void *handles /* world x 64 bytes */);
+int xfemm_dpcg_connect_files(xfemm_dpcg *d, const char *dir, const char *job, int timeout_s);
+int xfemm_dpcg_stats(xfemm_dpcg *d, int *partitioned_levels, long long *list_entries /* [12] */, long long *arena_bytes);
+int xfemm_dpcg_solve(xfemm_dpcg *d, double precision, int warm, int max_iter, xfemm_solve_info *info);
+int xfemm_dpcg_share_solution(xfemm_dpcg *d);
+int xfemm_dpcg_finish(xfemm_dpcg *d);
+
 /* ------------------------------------------------------------------ file-level entry
  * The call a user of fsolver / mexfsolver makes: basename without ".fem";
  * returns 0 ok, 1 problem loading .fem, 2 solve failed (main.cpp:72-83, mexfsolver.cpp:122-134). */

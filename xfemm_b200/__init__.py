@@ -152,6 +152,15 @@ SIGNATURES = {
     "xfemm_dist_direction": (C.c_int, [_P, _P]),
     "xfemm_dist_get_solution": (C.c_int, [_P, _dp]),
     "xfemm_dist_stream": (C.c_ulonglong, [_P]),
+    "xfemm_dpcg_create": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P)]),
+    "xfemm_dpcg_destroy": (C.c_int, [_P]),
+    "xfemm_dpcg_ipc_handle": (C.c_int, [_P, _P]),
+    "xfemm_dpcg_connect": (C.c_int, [_P, _P]),
+    "xfemm_dpcg_connect_files": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_int]),
+    "xfemm_dpcg_stats": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
+    "xfemm_dpcg_solve": (C.c_int, [_P, C.c_double, C.c_int, C.c_int, C.POINTER(SolveInfo)]),
+    "xfemm_dpcg_share_solution": (C.c_int, [_P]),
+    "xfemm_dpcg_finish": (C.c_int, [_P]),
     "xfemm_fsolver_linprob": (_P, [_P]),
     "xfemm_fsolver_run": (C.c_int, [C.c_char_p, C.c_int]),
     "xfemm_fsolver_open": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(_P)]),

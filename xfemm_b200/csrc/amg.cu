@@ -401,7 +401,7 @@ int amg_refresh(xfemm_linprob *fine, AmgHierarchy &h)
 void amg_print_trace(AmgHierarchy &h, cudaStream_t st)
 {
     if (!h.stamps.p) return;
-    std::vector<unsigned long long> t(AMG_MAX_STAMPS + 16, 0);
+    std::vector<unsigned long long> t(AMG_MAX_STAMPS + 16 + AMG_BLOCK_STAMPS, 0);
     cudaMemcpyAsync(t.data(), h.stamps.p, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
     cudaStreamSynchronize(st);
     fprintf(stderr, "[amg trace] levels:");
@@ -419,6 +419,21 @@ void amg_print_trace(AmgHierarchy &h, cudaStream_t st)
     if (dd[6] > dd[0])
         fprintf(stderr, "[amg trace] first team SpMV pass, block 0 (us): table %.2f, row-operand issue %.2f, tasks %.2f, sync %.2f, sums+epilogue %.2f, sync %.2f\n",
                 (dd[1] - dd[0]) * 1e-3, (dd[2] - dd[1]) * 1e-3, (dd[3] - dd[2]) * 1e-3, (dd[4] - dd[3]) * 1e-3, (dd[5] - dd[4]) * 1e-3, (dd[6] - dd[5]) * 1e-3);
+    for (int ph = 0; ph < 3; ph++)
+    {
+        const unsigned long long *bs = t.data() + AMG_MAX_STAMPS + 16 + 160 * ph, t0 = bs[159];
+        if (!t0) continue;
+        double mn = 1e30, mx = 0, sum = 0; int cnt = 0, arg = -1;
+        for (int b = 0; b < 159; b++) if (bs[b] > t0) { double d = (bs[b] - t0) * 1e-3; mn = std::min(mn, d); if (d > mx) { mx = d; arg = b; } sum += d; cnt++; }
+        if (cnt) fprintf(stderr, "[amg trace] %s: blocks finish after min %.1f / mean %.1f / max %.1f us (block %d last, %d blocks)\n",
+                         ph == 0 ? "CG SpMV" : ph == 1 ? "level-0 residual SpMV" : "level-0 post-smoothing SpMV", mn, sum / cnt, mx, arg, cnt);
+        if (cnt && ph == 0)
+        {
+            fprintf(stderr, "[amg trace]   per block (us):");
+            for (int b = 0; b < 159; b++) if (bs[b] > t0) fprintf(stderr, " %.0f", (bs[b] - t0) * 1e-3);
+            fprintf(stderr, "\n");
+        }
+    }
     const unsigned long long *c = t.data() + AMG_MAX_STAMPS - 8; // CG part of the last iteration
     if (c[4] > c[0])
         fprintf(stderr, "[amg trace] cg part us: spmv+dot %.1f, residual update %.1f, (v-cycle %.1f), direction+solution update %.1f\n",
@@ -453,7 +468,7 @@ void amg_fill_args(xfemm_linprob *fine, AmgHierarchy &h, AmgArgs &g, int grid)
     g.stamps = nullptr;
     if (getenv("XFEMM_AMG_TRACE"))
     {
-        if (!h.stamps.p && h.stamps.alloc(AMG_MAX_STAMPS + 16) == cudaSuccess) h.stamps.zero(fine->stream);
+        if (!h.stamps.p && h.stamps.alloc(AMG_MAX_STAMPS + 16 + AMG_BLOCK_STAMPS) == cudaSuccess) h.stamps.zero(fine->stream);
         g.stamps = h.stamps.p;
         g.trace_detail = atoi(getenv("XFEMM_AMG_TRACE")) >= 2 ? atoi(getenv("XFEMM_AMG_TRACE")) - 1 : 0;
     }

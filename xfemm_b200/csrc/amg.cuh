@@ -40,8 +40,17 @@ namespace xb {
 constexpr int AMG_MAX_LEVELS = 12;
 // per-block scratch of the kernels that run the cycle (shared memory): wide-row ranges of the block's chunk
 // of every level (2 ints per level) + the team barrier's epoch
-constexpr int AMG_SWK_EPOCH = 2 * AMG_MAX_LEVELS;
-constexpr int AMG_SWK_SIZE = 2 * AMG_MAX_LEVELS + 2;
+constexpr int AMG_SWK_EPOCH = 2 * AMG_MAX_LEVELS;     // [+0] team barrier epoch, [+1] grid barrier epoch
+constexpr int AMG_SWK_TAB = 2 * AMG_MAX_LEVELS + 2;   // per level: offset of the block's resident task table (ints), -1: none
+constexpr int AMG_SWK_SIZE = 3 * AMG_MAX_LEVELS + 2;
+// dynamic shared memory of the kernels that run the cycle: [matrix-stream ring (stage.cuh)] [task buffer] [task tables]
+constexpr int AMG_TASK_MAXS = 480;                 // slices per group of amg_spmv_tasks
+constexpr int AMG_TASK_PART_BYTES = 32 * 1024;     // partial sums: MAXT tasks x 32 rows x NC doubles
+constexpr int AMG_TASK_HDR_INTS = 4 + 2 * (AMG_TASK_MAXS + 1) + 128;
+constexpr int AMG_TASK_HDR_BYTES = ((AMG_TASK_HDR_INTS * 4 + 127) / 128) * 128;
+constexpr int AMG_TABLE_INTS = 2048;               // resident task tables of the block's chunks of the coarse levels
+constexpr int AMG_TASK_SMEM_BYTES = AMG_TASK_HDR_BYTES + AMG_TASK_PART_BYTES + AMG_TABLE_INTS * 4;
+extern __shared__ __align__(128) unsigned char xb_dyn_smem[]; // the kernels' dynamic shared memory
 
 // device view of one level, internal (SELL) row order
 struct AmgLev
@@ -90,6 +99,20 @@ __device__ __forceinline__ void amg_stamp(const AmgArgs &g, int &k, int limit = 
     }
 }
 
+// XFEMM_AMG_TRACE=2: every block records when it finished phase `ph` (0 CG SpMV, 1 level-0 residual, 2 level-0
+// post-smoothing) of the last iteration, and when the phase started (block 0 only, slot 160*ph+159)
+constexpr int AMG_BLOCK_STAMPS = 3 * 160;
+__device__ __forceinline__ void amg_block_stamp(const AmgArgs &g, int ph, bool start = false)
+{
+    if (g.stamps && g.trace_detail && threadIdx.x == 0 && blockIdx.x < 159)
+    {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (!start) g.stamps[AMG_MAX_STAMPS + 16 + 160 * ph + blockIdx.x] = t;
+        else if (blockIdx.x == 0) g.stamps[AMG_MAX_STAMPS + 16 + 160 * ph + 159] = t;
+    }
+}
+
 // host side: one coarse level = a complete linear problem (pattern, values, SELL layout, vectors)
 struct AmgHierarchy
 {
@@ -128,12 +151,61 @@ void amg_fill_args(xfemm_linprob *fine, AmgHierarchy &h, AmgArgs &g, int grid = 
 // --------------------------------------------------------------------------------------------
 __device__ __forceinline__ int amg_chunk(int nslices, int b, int nb) { return (int)((long long)nslices * b / nb); }
 
-// Once per kernel, whole block, before the first cycle (and before the first grid barrier of the kernel):
-// wide-row ranges of this block's chunk of every level — the grid partition for the big levels, the team partition
-// for the team levels — and the team barrier's state.
-__device__ __forceinline__ void amg_kernel_init(const AmgArgs &g, int *s_wk)
+// Warp-collective: task table of the group of slices that starts at `cur` (see amg_spmv_tasks): as many slices as fit
+// `maxs` slices and `maxt` tasks of `batch` columns.  first_task / slice_base get one entry per slice plus the end,
+// task_info one (slice of the group << 16 | batch number) per task.  Returns the slices covered; *ntasks the tasks.
+__device__ __forceinline__ int amg_task_table(const int *slice_ptr, int cur, int s1, int maxs, int maxt, int batch, int *first_task,
+                                              int *slice_base, int *task_info, int *ntasks)
+{
+    const int lane = threadIdx.x & 31;
+    int nt_total = 0, ns = 0;
+    while (cur + ns < s1 && ns < maxs)
+    {
+        const int s = cur + ns + lane;
+        int nt = 0, a = 0, b = 0;
+        if (s < s1) { a = slice_ptr[s]; b = slice_ptr[s + 1]; nt = (((b - a) >> 5) + batch - 1) / batch; }
+        int inc = nt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        const bool fits = s < s1 && nt_total + inc <= maxt && ns + lane < maxs;
+        const int cnt = __popc(__ballot_sync(0xffffffffu, fits)); // a prefix of the lanes: inc is non-decreasing
+        if (fits)
+        {
+            const int t0 = nt_total + inc - nt;
+            first_task[ns + lane] = t0;
+            slice_base[ns + lane] = a;
+            for (int q = 0; q < nt; q++) task_info[t0 + q] = ((ns + lane) << 16) | q;
+            if (lane == cnt - 1) slice_base[ns + lane + 1] = b;
+        }
+        const int add = __shfl_sync(0xffffffffu, inc, cnt > 0 ? cnt - 1 : 0);
+        if (cnt > 0) nt_total += add;
+        ns += cnt;
+        if (cnt < 32) break;
+    }
+    if (lane == 0) first_task[ns] = nt_total;
+    *ntasks = nt_total;
+    return ns;
+}
+
+// Once per kernel, whole block, before the first cycle.  `sg` = the block's copy of the arguments in shared memory
+// (raw storage of sizeof(AmgArgs)): the coarse-level code is out of line and would otherwise read the kernel
+// parameters through generic loads — a round trip to L2 each after every barrier; shared memory is a few cycles.
+//   - wide-row ranges of this block's chunk of every level (grid partition for the big levels, team partition for
+//     the team levels), the barrier epochs
+//   - resident task tables (amg_spmv_tasks) of the block's chunk of every coarse level that fits one group
+template <int NC>
+__device__ __forceinline__ const AmgArgs &amg_kernel_init(const AmgArgs &g, unsigned char *sg_raw, int *s_wk)
 {
     const int G = gridDim.x, B = blockIdx.x;
+    {
+        const unsigned *src = (const unsigned *)&g;
+        unsigned *dst = (unsigned *)sg_raw;
+        for (int i = threadIdx.x; i < (int)(sizeof(AmgArgs) / 4); i += blockDim.x) dst[i] = src[i];
+    }
     if (threadIdx.x < g.nlev)
     {
         const int l = threadIdx.x;
@@ -146,9 +218,35 @@ __device__ __forceinline__ void amg_kernel_init(const AmgArgs &g, int *s_wk)
                 wide_range(L.wide, amg_chunk(L.nslices, B, g.team_blocks) * 32, amg_chunk(L.nslices, B + 1, g.team_blocks) * 32, k0, k1);
         }
         s_wk[2 * l] = k0; s_wk[2 * l + 1] = k1;
+        s_wk[AMG_SWK_TAB + l] = -1;
     }
     if (threadIdx.x == 0) { s_wk[AMG_SWK_EPOCH] = 0; s_wk[AMG_SWK_EPOCH + 1] = 0; }
     __syncthreads();
+    if (threadIdx.x < 32)
+    {
+        constexpr int BATCH = (NC == 1) ? 8 : 4;
+        constexpr int MAXT = AMG_TASK_PART_BYTES / (32 * 8 * NC);
+        int *tab = (int *)(xb_dyn_smem + g.task_smem_offset + AMG_TASK_HDR_BYTES + AMG_TASK_PART_BYTES);
+        int used = 0;
+        for (int l = 1; l < g.nlev; l++)
+        {
+            const AmgLev &L = g.lev[l];
+            int s0 = 0, s1 = 0;
+            if (l < g.team_from) { s0 = amg_chunk(L.nslices, B, G); s1 = amg_chunk(L.nslices, B + 1, G); }
+            else if (B < g.team_blocks) { s0 = amg_chunk(L.nslices, B, g.team_blocks); s1 = amg_chunk(L.nslices, B + 1, g.team_blocks); }
+            const int nsl = s1 - s0, need = 2 + 2 * (nsl + 1) + MAXT;
+            if (nsl <= 0 || nsl > AMG_TASK_MAXS || used + need > AMG_TABLE_INTS) continue;
+            int *t = tab + used, ntasks = 0;
+            const int ns = amg_task_table(L.slice_ptr, s0, s1, nsl, MAXT, BATCH, t + 2, t + 2 + (nsl + 1), t + 2 + 2 * (nsl + 1), &ntasks);
+            if (ns == nsl) // the whole chunk is one group: keep the table
+            {
+                if (threadIdx.x == 0) { t[0] = ns; t[1] = ntasks; s_wk[AMG_SWK_TAB + l] = used; }
+                used += need;
+            }
+        }
+    }
+    __syncthreads();
+    return *reinterpret_cast<const AmgArgs *>(sg_raw);
 }
 
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p)
@@ -292,15 +390,11 @@ __device__ __noinline__ void amg_prolong_rows(const AmgLev &L, AmgV<NC> lv, AmgV
 //   PROL: x' = x + over * P * (t of the next level) formed on the fly (prolongation fused); else x' = x
 // Reads v.x, v.b (cv.t), writes v.t.  Out of line on purpose: own register allocation, one copy of the code.
 enum { AMG_EPI_RESIDUAL = 0, AMG_EPI_POST = 1 };
-constexpr int AMG_TASK_MAXS = 480;                 // slices per group
-constexpr int AMG_TASK_PART_BYTES = 32 * 1024;     // partial sums: MAXT tasks x 32 rows x NC doubles
-constexpr int AMG_TASK_HDR_INTS = 4 + 2 * (AMG_TASK_MAXS + 1) + 128;
-constexpr int AMG_TASK_SMEM_BYTES = ((AMG_TASK_HDR_INTS * 4 + 127) / 128) * 128 + AMG_TASK_PART_BYTES;
-extern __shared__ __align__(128) unsigned char xb_dyn_smem[]; // the kernels' dynamic shared memory (ring first, then this buffer)
 
 template <int NC, bool PROL>
 __device__ __noinline__ void amg_spmv_tasks(const AmgLev &L, AmgV<NC> v, AmgV<NC> cv, int s0, int s1, int wk0, int wk1, int kind,
-                                            double w, double over, unsigned char *tsm, unsigned long long *dbg = nullptr)
+                                            double w, double over, unsigned char *tsm, const int *table = nullptr,
+                                            unsigned long long *dbg = nullptr)
 {
     auto mark = [&](int k) {
         if (dbg && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[k] = t; }
@@ -309,60 +403,37 @@ __device__ __noinline__ void amg_spmv_tasks(const AmgLev &L, AmgV<NC> v, AmgV<NC
     constexpr int BATCH = (NC == 1) ? 8 : 4;
     constexpr int MAXT = AMG_TASK_PART_BYTES / (32 * 8 * NC); // 128 / 64
     int *hdr = (int *)tsm;                       // [0] slices of the group, [1] tasks of the group
-    int *first_task = hdr + 4;                   // [MAXS+1] first task of each slice of the group
-    int *slice_base = first_task + AMG_TASK_MAXS + 1; // [MAXS+1] SELL offset of each slice of the group (+ the end)
-    int *task_info = slice_base + AMG_TASK_MAXS + 1;  // [128] (slice of the group << 16) | batch
-    double *part = (double *)(tsm + ((AMG_TASK_HDR_INTS * 4 + 127) / 128) * 128); // [task][component][lane]
+    const int *first_task = hdr + 4;             // [MAXS+1] first task of each slice of the group
+    const int *slice_base = first_task + AMG_TASK_MAXS + 1; // [MAXS+1] SELL offset of each slice of the group (+ the end)
+    const int *task_info = slice_base + AMG_TASK_MAXS + 1;  // [128] (slice of the group << 16) | batch
+    double *part = (double *)(tsm + AMG_TASK_HDR_BYTES);    // [task][component][lane]
     const int lane = threadIdx.x & 31, warp_b = threadIdx.x >> 5, nwarps_b = blockDim.x >> 5;
-    if (wk1 > wk0)
+    if (table)
     {
-        // rows kept out of the SELL slices (layout.h): their off-diagonal sums go to v.t first
-#pragma unroll
-        for (int m = 0; m < NC; m++)
-        {
-            if (m) __syncthreads(); // the segment scratch is shared by the passes
-            wide_rows_block<double>(L.wide, L.wide_val, L.wide_acc, wk0, wk1, v.x[m], v.t[m]);
-        }
+        // resident table of the whole chunk (built once per kernel by amg_kernel_init)
+        first_task = table + 2;
+        slice_base = first_task + (s1 - s0 + 1);
+        task_info = slice_base + (s1 - s0 + 1);
     }
     int cur = s0;
     while (cur < s1) // uniform over the block
     {
-        // ---- warp 0: task table of the next group of slices
-        if (warp_b == 0)
+        int ns, ntasks;
+        if (table) { ns = table[0]; ntasks = table[1]; }
+        else
         {
-            int nt_total = 0, ns = 0;
-            while (cur + ns < s1 && ns < AMG_TASK_MAXS)
+            // ---- warp 0: task table of the next group of slices
+            if (warp_b == 0)
             {
-                const int s = cur + ns + lane;
-                int nt = 0, a = 0, b = 0;
-                if (s < s1) { a = L.slice_ptr[s]; b = L.slice_ptr[s + 1]; nt = (((b - a) >> 5) + BATCH - 1) / BATCH; }
-                int inc = nt;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1)
-                {
-                    const int t = __shfl_up_sync(0xffffffffu, inc, o);
-                    if (lane >= o) inc += t;
-                }
-                const bool fits = s < s1 && nt_total + inc <= MAXT && ns + lane < AMG_TASK_MAXS;
-                const int cnt = __popc(__ballot_sync(0xffffffffu, fits)); // a prefix of the lanes: inc is non-decreasing
-                if (fits)
-                {
-                    const int t0 = nt_total + inc - nt;
-                    first_task[ns + lane] = t0;
-                    slice_base[ns + lane] = a;
-                    for (int q = 0; q < nt; q++) task_info[t0 + q] = ((ns + lane) << 16) | q;
-                    if (lane == cnt - 1) slice_base[ns + lane + 1] = b;
-                }
-                const int add = __shfl_sync(0xffffffffu, inc, cnt > 0 ? cnt - 1 : 0);
-                if (cnt > 0) nt_total += add;
-                ns += cnt;
-                if (cnt < 32) break;
+                int nt = 0;
+                const int n = amg_task_table(L.slice_ptr, cur, s1, AMG_TASK_MAXS, MAXT, BATCH, hdr + 4, hdr + 4 + AMG_TASK_MAXS + 1,
+                                             hdr + 4 + 2 * (AMG_TASK_MAXS + 1), &nt);
+                if (lane == 0) { hdr[0] = n; hdr[1] = nt; }
             }
-            if (lane == 0) { first_task[ns] = nt_total; hdr[0] = ns; hdr[1] = nt_total; }
+            __syncthreads();
+            ns = hdr[0]; ntasks = hdr[1];
         }
-        __syncthreads();
         mark(1);
-        const int ns = hdr[0], ntasks = hdr[1];
         if (ns == 0) break; // a single slice wider than MAXT * BATCH columns: the host never builds one (amg_build checks)
         // row operands of this warp's first slice: in flight during the task phase
         double d0 = 0.0, wd0 = 0.0, xr0[NC], br0[NC];
@@ -382,6 +453,17 @@ __device__ __noinline__ void amg_spmv_tasks(const AmgLev &L, AmgV<NC> v, AmgV<NC
             }
         }
         mark(2);
+        // rows kept out of the SELL slices (layout.h), dealt out to the warps from the last one down, alongside the
+        // tasks: their off-diagonal sums go to v.t, where the owner of the slice picks them up after the barrier
+        if (wk1 > wk0 && cur == s0)
+        {
+#pragma unroll
+            for (int m = 0; m < NC; m++)
+            {
+                double *tm = v.t[m];
+                wide_rows_warp(L.wide, L.wide_val, wk0, wk1, v.x[m], [&](int row, double off) { tm[row] = off; });
+            }
+        }
         // ---- tasks: BATCH columns of one slice, lane = row
         for (int t = warp_b; t < ntasks; t += nwarps_b)
         {
@@ -465,6 +547,13 @@ __device__ __noinline__ void amg_spmv_tasks(const AmgLev &L, AmgV<NC> v, AmgV<NC
     }
 }
 
+// the block's resident task table of level l, or null
+__device__ __forceinline__ const int *amg_table(const AmgArgs &g, const int *s_wk, int l)
+{
+    const int off = s_wk[AMG_SWK_TAB + l];
+    return off >= 0 ? (const int *)(xb_dyn_smem + g.task_smem_offset + AMG_TASK_HDR_BYTES + AMG_TASK_PART_BYTES) + off : nullptr;
+}
+
 // --------------------------------------------------------------------------------------------
 // device: the team's sub-cycle over the levels team_from..last.  In: b and the pre-smoothed x of level
 // team_from.  Out: t of level team_from.  Called by the blocks 0..team_blocks-1 only; the caller follows it
@@ -490,8 +579,9 @@ __device__ __noinline__ void amg_team_cycle(const AmgArgs &g, const AmgArgs2 *g2
         const AmgLev &L = g.lev[l];
         const int s0 = amg_chunk(L.nslices, B, T), s1 = amg_chunk(L.nslices, B + 1, T);
         unsigned long long *dbg = (g.stamps && g.trace_detail && B == 0 && l == first && kind == AMG_EPI_RESIDUAL) ? g.stamps + AMG_MAX_STAMPS : nullptr;
-        if (prol) amg_spmv_tasks<NC, true>(L, v, cv, s0, s1, s_wk[2 * l], s_wk[2 * l + 1], kind, w, over, tsm);
-        else amg_spmv_tasks<NC, false>(L, v, cv, s0, s1, s_wk[2 * l], s_wk[2 * l + 1], kind, w, over, tsm, dbg);
+        const int *table = s_wk[AMG_SWK_TAB + l] >= 0 ? (const int *)(tsm + AMG_TASK_HDR_BYTES + AMG_TASK_PART_BYTES) + s_wk[AMG_SWK_TAB + l] : nullptr;
+        if (prol) amg_spmv_tasks<NC, true>(L, v, cv, s0, s1, s_wk[2 * l], s_wk[2 * l + 1], kind, w, over, tsm, table);
+        else amg_spmv_tasks<NC, false>(L, v, cv, s0, s1, s_wk[2 * l], s_wk[2 * l + 1], kind, w, over, tsm, table, dbg);
     };
 
     // ---- down
@@ -575,10 +665,11 @@ __device__ __forceinline__ void amg_spmv_phase(const AmgLev &L, int s0, int s1, 
                                                const double *pf0 = nullptr, const double *pf1 = nullptr)
 {
     const int lane = threadIdx.x & 31;
-    wide_rows_block<double>(L.wide, L.wide_val, L.wide_acc, wk0, wk1, x, wide_tmp);
     if (S && S->ntiles > 0)
     {
-        // pf0/pf1: row-indexed arrays the caller's epilogue reads (prefetched while the warp waits for its tile)
+        // pf0/pf1: row-indexed arrays the caller's epilogue reads (prefetched while the warp waits for its tile).
+        // The wide rows of the chunk go to a few warps BEFORE they join the stream (no block-wide pre-pass in front of
+        // it: a single wide row used to hold its whole block up by ~9 us); the stream skips the flagged rows.
         staged_slices(*S, L.slice_ptr, L.sell_val, L.sell_col, s0, s1, x, s_next,
                       [&](int row) {
                           if (pf0) prefetch_l1(pf0 + row);
@@ -586,12 +677,16 @@ __device__ __forceinline__ void amg_spmv_phase(const AmgLev &L, int s0, int s1, 
                           return make_double2(L.diag[row], x[row]);
                       },
                       [&](int s, int row, double acc, double2 dx) {
-                          if (wk1 > wk0 && ((L.wide.mask[s] >> lane) & 1u)) acc += wide_tmp[row];
-                          acc = fma(dx.x, dx.y, acc);
-                          epi(row, acc);
+                          if (wk1 > wk0 && ((L.wide.mask[s] >> lane) & 1u)) return;
+                          epi(row, fma(dx.x, dx.y, acc));
+                      },
+                      [&]() {
+                          if (wk1 > wk0)
+                              wide_rows_warp(L.wide, L.wide_val, wk0, wk1, x, [&](int row, double off) { epi(row, fma(L.diag[row], x[row], off)); });
                       });
         return;
     }
+    wide_rows_block<double>(L.wide, L.wide_val, L.wide_acc, wk0, wk1, x, wide_tmp);
     if (threadIdx.x == 0) *s_next = s0;
     __syncthreads();
     while (true)
@@ -616,7 +711,8 @@ __device__ __forceinline__ void amg_spmv_phase(const AmgLev &L, int s0, int s1, 
 // z = M^-1 r.  Level 0: b = r (input), t = z (output), x = scratch.  Returns this thread's partial of r.z.
 // x0_ready: the caller already stored the pre-smoothed x = omega D^-1 r of level 0 (fused into its
 // residual update) and synchronised the grid.
-__device__ __forceinline__ double amg_vcycle(const AmgArgs &g, GridBar &grid, int *s_next,
+__device__ __forceinline__ double amg_vcycle(const AmgArgs &g, const AmgArgs &sg /* copy in shared memory, for the out-of-line passes */,
+                                             GridBar &grid, int *s_next,
                                              int *s_wk /* [AMG_SWK_SIZE] in shared memory, see amg_kernel_init */,
                                              StageSmem *S0 /* ring of the finest level, or null */, bool x0_ready = false)
 {
@@ -646,24 +742,28 @@ __device__ __forceinline__ double amg_vcycle(const AmgArgs &g, GridBar &grid, in
     for (int l = 0; l < lc; l++)
     {
         const AmgLev &L = g.lev[l];
-        const AmgLev &C = g.lev[l + 1];
         const int s0 = amg_chunk(L.nslices, B, G), s1 = amg_chunk(L.nslices, B + 1, G);
         const AmgV<1> lv = amg_vecs<1>(g, nullptr, l), cv = amg_vecs<1>(g, nullptr, l + 1);
         // t = b - A x   (t doubles as the scratch the wide rows leave their partial sums in)
         if (l == 0)
+        {
+            amg_block_stamp(g, 1, true);
             amg_spmv_phase(L, s0, s1, s_wk[0], s_wk[1], L.x, L.t, s_next, [&](int row, double ax) { L.t[row] = L.b[row] - ax; }, S0, L.b);
+            amg_block_stamp(g, 1);
+        }
         else
-            amg_spmv_tasks<1, false>(L, lv, cv, s0, s1, s_wk[2 * l], s_wk[2 * l + 1], AMG_EPI_RESIDUAL, w, over, xb_dyn_smem + g.task_smem_offset);
+            amg_spmv_tasks<1, false>(sg.lev[l], lv, cv, s0, s1, s_wk[2 * l], s_wk[2 * l + 1], AMG_EPI_RESIDUAL, w, over,
+                                     xb_dyn_smem + g.task_smem_offset, amg_table(g, s_wk, l));
         grid.sync();
         amg_stamp(g, sk);
         // coarse right-hand side = sum over the aggregate ; coarse pre-smooth fused.  Rows are dealt out
         // thread by thread over the whole grid (coalesced pointer loads, no tail of idle blocks).
-        amg_restrict_level<1>(L, C, lv, cv, tid_g, nthr_g, w);
+        amg_restrict_level<1>(sg.lev[l], sg.lev[l + 1], lv, cv, tid_g, nthr_g, w);
         grid.sync();
         amg_stamp(g, sk);
     }
     // ---- the small levels: the team, counter barriers; result in lev[lc].t
-    if (B < g.team_blocks) amg_team_cycle<1>(g, nullptr, s_wk, &sk);
+    if (B < g.team_blocks) amg_team_cycle<1>(sg, nullptr, s_wk, &sk);
     grid.sync();
     amg_stamp(g, sk);
     // ---- up: add the (over-)corrected coarse result (a row-wise gather: a scatter from the coarse rows
@@ -674,22 +774,25 @@ __device__ __forceinline__ double amg_vcycle(const AmgArgs &g, GridBar &grid, in
         const int s0 = amg_chunk(L.nslices, B, G), s1 = amg_chunk(L.nslices, B + 1, G);
         const AmgV<1> lv = amg_vecs<1>(g, nullptr, l), cv = amg_vecs<1>(g, nullptr, l + 1);
         // own rows only: the post-smoothing pass below gathers x across blocks, hence the barrier
-        amg_prolong_rows<1>(L, lv, cv, s0 * 32, s1 * 32, threadIdx.x, blockDim.x, over);
+        amg_prolong_rows<1>(sg.lev[l], lv, cv, s0 * 32, s1 * 32, threadIdx.x, blockDim.x, over);
         grid.sync();
         amg_stamp(g, sk);
         if (l > 0)
         {
-            amg_spmv_tasks<1, false>(L, lv, cv, s0, s1, s_wk[2 * l], s_wk[2 * l + 1], AMG_EPI_POST, w, over, xb_dyn_smem + g.task_smem_offset);
+            amg_spmv_tasks<1, false>(sg.lev[l], lv, cv, s0, s1, s_wk[2 * l], s_wk[2 * l + 1], AMG_EPI_POST, w, over,
+                                     xb_dyn_smem + g.task_smem_offset, amg_table(g, s_wk, l));
             grid.sync();
             amg_stamp(g, sk);
         }
         else
         {
+            amg_block_stamp(g, 2, true);
             amg_spmv_phase(L, s0, s1, s_wk[0], s_wk[1], L.x, L.t, s_next, [&](int row, double ax) {
                 const double br = L.b[row], z = fma(w * L.dinv[row], br - ax, L.x[row]);
                 L.t[row] = z;
                 dot = fma(br, z, dot);
             }, S0, L.b, L.dinv);
+            amg_block_stamp(g, 2);
         }
     }
     amg_stamp(g, sk);

@@ -125,7 +125,7 @@ __device__ __forceinline__ void amg_spmv_phase2(const AmgLev &L, int s0, int s1,
 
 // (t, t2) = M^-1 (b, b2) on level 0.  The caller has stored the right-hand sides in lev[0].b / lev2[0].b and the
 // pre-smoothed iterates omega D^-1 b in lev[0].x / lev2[0].x and synchronised the grid.
-__device__ __forceinline__ void amg_vcycle2(const AmgArgs &g, const AmgArgs2 &g2, GridBar &grid, int *s_next,
+__device__ __forceinline__ void amg_vcycle2(const AmgArgs &g, const AmgArgs &sg, const AmgArgs2 &g2, GridBar &grid, int *s_next,
                                             int *s_wk, StageSmem *S0)
 {
     const int G = gridDim.x, B = blockIdx.x;
@@ -152,12 +152,13 @@ __device__ __forceinline__ void amg_vcycle2(const AmgArgs &g, const AmgArgs2 &g2
             amg_spmv_phase2(L, s0, s1, s_wk[0], s_wk[1], L.x, L2.x, L.t, L2.t, s_next,
                             [&](int row, double ax, double bx) { L.t[row] = L.b[row] - ax; L2.t[row] = L2.b[row] - bx; }, S0);
         else
-            amg_spmv_tasks<2, false>(L, lv, cv, s0, s1, s_wk[2 * l], s_wk[2 * l + 1], AMG_EPI_RESIDUAL, w, over, xb_dyn_smem + g.task_smem_offset);
+            amg_spmv_tasks<2, false>(sg.lev[l], lv, cv, s0, s1, s_wk[2 * l], s_wk[2 * l + 1], AMG_EPI_RESIDUAL, w, over, xb_dyn_smem + g.task_smem_offset,
+                                         amg_table(g, s_wk, l));
         grid.sync();
-        amg_restrict_level<2>(L, C, lv, cv, tid_g, nthr_g, w);
+        amg_restrict_level<2>(sg.lev[l], sg.lev[l + 1], lv, cv, tid_g, nthr_g, w);
         grid.sync();
     }
-    if (B < g.team_blocks) amg_team_cycle<2>(g, &g2, s_wk);
+    if (B < g.team_blocks) amg_team_cycle<2>(sg, &g2, s_wk);
     grid.sync();
     for (int l = lc - 1; l >= 0; l--)
     {
@@ -165,7 +166,7 @@ __device__ __forceinline__ void amg_vcycle2(const AmgArgs &g, const AmgArgs2 &g2
         const AmgVec2 &L2 = g2.lev[l];
         const int s0 = amg_chunk(L.nslices, B, G), s1 = amg_chunk(L.nslices, B + 1, G);
         const AmgV<2> lv = amg_vecs<2>(g, &g2, l), cv = amg_vecs<2>(g, &g2, l + 1);
-        amg_prolong_rows<2>(L, lv, cv, s0 * 32, s1 * 32, threadIdx.x, blockDim.x, over);
+        amg_prolong_rows<2>(sg.lev[l], lv, cv, s0 * 32, s1 * 32, threadIdx.x, blockDim.x, over);
         grid.sync();
         if (l == 0)
             amg_spmv_phase2(L, s0, s1, s_wk[0], s_wk[1], L.x, L2.x, L.t, L2.t, s_next,
@@ -177,7 +178,8 @@ __device__ __forceinline__ void amg_vcycle2(const AmgArgs &g, const AmgArgs2 &g2
                             S0);
         else
         {
-            amg_spmv_tasks<2, false>(L, lv, cv, s0, s1, s_wk[2 * l], s_wk[2 * l + 1], AMG_EPI_POST, w, over, xb_dyn_smem + g.task_smem_offset);
+            amg_spmv_tasks<2, false>(sg.lev[l], lv, cv, s0, s1, s_wk[2 * l], s_wk[2 * l + 1], AMG_EPI_POST, w, over, xb_dyn_smem + g.task_smem_offset,
+                                     amg_table(g, s_wk, l));
             grid.sync();
         }
     }

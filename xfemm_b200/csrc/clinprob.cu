@@ -206,7 +206,7 @@ __device__ __forceinline__ int cnext_slice(int *ctr, int lane)
 
 // z = M^-1 r ; returns this thread's partial of the unconjugated z.r
 template <int PRECOND>
-__device__ __forceinline__ cd cprecond_apply(const CocgArgs &a, const AmgArgs &g, const AmgArgs2 &g2, GridBar &grid, int r0,
+__device__ __forceinline__ cd cprecond_apply(const CocgArgs &a, const AmgArgs &g, const AmgArgs &sg, const AmgArgs2 &g2, GridBar &grid, int r0,
                                              int r1, int warp_g, int nwarps_g, int lane, int *s_next, int *s_wk, StageSmem *S)
 {
     cd dot = make_double2(0., 0.);
@@ -229,7 +229,7 @@ __device__ __forceinline__ cd cprecond_apply(const CocgArgs &a, const AmgArgs &g
             V0.b[i] = ri.y; V0.x[i] = wd * ri.y;
         }
         grid.sync();
-        amg_vcycle2(g, g2, grid, s_next, s_wk, S);
+        amg_vcycle2(g, sg, g2, grid, s_next, s_wk, S);
         // every block post-smoothed its own rows of level 0: no barrier needed before reading them back
         for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x)
         {
@@ -300,6 +300,8 @@ __global__ void __launch_bounds__(512, 1) k_cocg(const __grid_constant__ CocgArg
     __shared__ double sm[33];
     __shared__ int s_next;
     __shared__ int s_wk[AMG_SWK_SIZE];
+    __shared__ __align__(16) unsigned char sg_raw[PRECOND == XFEMM_PRECOND_AMG ? sizeof(AmgArgs) : 16];
+    const AmgArgs *sgp = &g; // multigrid: the block's shared-memory copy of g for the out-of-line passes (amg_kernel_init)
     GridBar grid{cg::this_grid(), PRECOND == XFEMM_PRECOND_AMG ? g.grid_ctr : nullptr, s_wk + AMG_SWK_EPOCH + 1};
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     StageSmem S = stage_carve(dyn_smem); // ring for the matrix stream of the real companion's finest level
@@ -320,7 +322,7 @@ __global__ void __launch_bounds__(512, 1) k_cocg(const __grid_constant__ CocgArg
             S.ntiles = a.tile_ptr[blockIdx.x + 1] - a.tile_ptr[blockIdx.x];
             S.tile = a.tiles + a.tile_ptr[blockIdx.x];
         }
-        amg_kernel_init(g, s_wk);
+        sgp = &amg_kernel_init<2>(g, sg_raw, s_wk);
     }
 
     // ||b||^2 ; r = b ; x = 0 unless warm
@@ -357,7 +359,7 @@ __global__ void __launch_bounds__(512, 1) k_cocg(const __grid_constant__ CocgArg
         }
         grid.sync();
     }
-    cd part = cprecond_apply<PRECOND>(a, g, g2, grid, r0, r1, warp_g, nwarps_g, lane, &s_next, s_wk, &S);
+    cd part = cprecond_apply<PRECOND>(a, g, *sgp, g2, grid, r0, r1, warp_g, nwarps_g, lane, &s_next, s_wk, &S);
     part = block_sum_c(part, sm);
     if (threadIdx.x == 0) { partB[blockIdx.x] = part.x; partB[G + blockIdx.x] = part.y; }
     grid.sync();
@@ -402,7 +404,7 @@ __global__ void __launch_bounds__(512, 1) k_cocg(const __grid_constant__ CocgArg
         pn = block_sum(pn, sm);
         if (threadIdx.x == 0) partC[blockIdx.x] = pn;
         if (PRECOND != XFEMM_PRECOND_JACOBI) grid.sync();
-        part = cprecond_apply<PRECOND>(a, g, g2, grid, r0, r1, warp_g, nwarps_g, lane, &s_next, s_wk, &S);
+        part = cprecond_apply<PRECOND>(a, g, *sgp, g2, grid, r0, r1, warp_g, nwarps_g, lane, &s_next, s_wk, &S);
         part = block_sum_c(part, sm);
         if (threadIdx.x == 0) { partB[blockIdx.x] = part.x; partB[G + blockIdx.x] = part.y; }
         grid.sync();

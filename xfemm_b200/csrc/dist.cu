@@ -28,6 +28,11 @@ struct xfemm_dist
 
 namespace xb {
 
+// res / pAp and res_new / res with the guards of the single-GPU kernel (k_pcg stops on pAp <= 0 and on NaN): an exactly
+// zero residual (diagonal or fully fixed system) or a non-positive curvature gives a zero step, which freezes the
+// iterate; the host sees the non-finite or stalled residual and reports XFEMM_ERR_DIVERGED / convergence.
+__device__ __forceinline__ double guarded_ratio(double num, double den) { return (den > 0.0 && num == num) ? num / den : 0.0; }
+
 __global__ void kd_copy_block(long long nnz_loc, const int *__restrict__ slot_map, const double *__restrict__ gvals, double *lvals)
 {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -112,7 +117,7 @@ __global__ void kd_update(int n_pad, const unsigned char *__restrict__ owned, co
                           double *x, double *r, double *part)
 {
     __shared__ double sm[33];
-    const double alpha = g[0] / g[1];
+    const double alpha = guarded_ratio(g[0], g[1]);
     double a = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x)
     {
@@ -129,7 +134,7 @@ __global__ void kd_update(int n_pad, const unsigned char *__restrict__ owned, co
 __global__ void kd_direction(int n_pad, const unsigned char *__restrict__ owned, const double *__restrict__ g,
                              const double *__restrict__ dinv, const double *__restrict__ r, double *p)
 {
-    const double beta = g[2] / g[0];
+    const double beta = guarded_ratio(g[2], g[0]);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x)
         if (owned[i]) p[i] = fma(beta, p[i], r[i] * dinv[i]);
 }
@@ -137,7 +142,7 @@ __global__ void kd_direction(int n_pad, const unsigned char *__restrict__ owned,
 __global__ void kd_update_xr(int n_pad, const unsigned char *__restrict__ owned, const double *__restrict__ g,
                              const double *__restrict__ p, const double *__restrict__ u, double *x, double *r)
 {
-    const double alpha = g[0] / g[1];
+    const double alpha = guarded_ratio(g[0], g[1]);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x)
     {
         if (!owned[i]) continue;
@@ -160,7 +165,7 @@ __global__ void kd_dot_rz(int n_pad, const unsigned char *__restrict__ owned, co
 __global__ void kd_direction_z(int n_pad, const unsigned char *__restrict__ owned, const double *__restrict__ g,
                                const double *__restrict__ z, double *p, int first)
 {
-    const double beta = first ? 0.0 : g[2] / g[0];
+    const double beta = first ? 0.0 : guarded_ratio(g[2], g[0]);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x)
         if (owned[i]) p[i] = first ? z[i] : fma(beta, p[i], z[i]);
 }

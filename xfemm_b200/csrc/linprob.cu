@@ -4,6 +4,7 @@
 // kernel (no host round trips inside the Krylov loop), Dirichlet / periodic boundary kernels.
 #include "linprob.cuh"
 #include "amg.cuh"
+#include "pcg_args.cuh"
 #include <cooperative_groups.h>
 #include <algorithm>
 #include <unordered_map>
@@ -33,36 +34,62 @@ std::atomic<long long> g_h2d_bytes{0}, g_d2h_bytes{0}, g_launch{0};
 thread_local DevArena *g_arena = nullptr;
 
 // ---- caching device allocator (see common.cuh) ---------------------------------------------
+// Free lists are kept per (device, rounded size): a process may use several devices (xfemm_cuda_init(device)), and a
+// block freed on one must never be handed to a problem on another.
 namespace {
 std::mutex g_cache_mu;
-std::unordered_map<size_t, std::vector<void *>> g_cache_free; // rounded size -> blocks
-std::unordered_map<void *, size_t> g_cache_size;              // live and cached blocks
-size_t g_cache_bytes = 0;                                      // bytes sitting in the free lists
-bool g_cache_dirty = false;                                    // frees since the last device-wide sync
+struct CacheKey
+{
+    int dev;
+    size_t bytes;
+    bool operator==(const CacheKey &o) const { return dev == o.dev && bytes == o.bytes; }
+};
+struct CacheKeyHash
+{
+    size_t operator()(const CacheKey &k) const { return std::hash<size_t>()(k.bytes * 31 + (size_t)k.dev); }
+};
+std::unordered_map<CacheKey, std::vector<void *>, CacheKeyHash> g_cache_free; // (device, rounded size) -> blocks
+std::unordered_map<void *, CacheKey> g_cache_size;                            // live and cached blocks
+size_t g_cache_bytes = 0;                                                     // bytes sitting in the free lists
+std::unordered_map<int, bool> g_cache_dirty;                                  // per device: frees since its last sync
 inline size_t cache_round(size_t b) { return b < (1u << 20) ? ((b + 511) & ~(size_t)511) : ((b + (1u << 20) - 1) & ~(size_t)((1u << 20) - 1)); }
+inline size_t cache_cap()
+{
+    static const size_t cap = [] { const char *cm = getenv("XFEMM_DEVICE_CACHE_MB"); return (size_t)(cm ? atoi(cm) : 16384) << 20; }();
+    return cap;
+}
+inline int current_device() { int d = 0; cudaGetDevice(&d); return d; }
 } // namespace
 
 void dev_cache_flush()
 {
     std::lock_guard<std::mutex> lk(g_cache_mu);
-    cudaDeviceSynchronize();
+    const int here = current_device();
     for (auto &kv : g_cache_free)
+    {
+        if (kv.second.empty()) continue;
+        cudaSetDevice(kv.first.dev);
+        cudaDeviceSynchronize();
         for (void *q : kv.second) { g_cache_size.erase(q); cudaFree(q); }
+        kv.second.clear();
+    }
+    cudaSetDevice(here);
     g_cache_free.clear();
     g_cache_bytes = 0;
-    g_cache_dirty = false;
+    g_cache_dirty.clear();
 }
 
 cudaError_t dev_alloc(void **p, size_t bytes)
 {
     const size_t r = cache_round(std::max<size_t>(bytes, 1));
+    const int dev = current_device();
     {
         std::lock_guard<std::mutex> lk(g_cache_mu);
-        auto it = g_cache_free.find(r);
+        auto it = g_cache_free.find(CacheKey{dev, r});
         if (it != g_cache_free.end() && !it->second.empty())
         {
-            // a block freed earlier may still be read by work queued on its old stream
-            if (g_cache_dirty) { cudaDeviceSynchronize(); g_cache_dirty = false; }
+            // a block freed earlier may still be read by work queued on its old stream (same device)
+            if (g_cache_dirty[dev]) { cudaDeviceSynchronize(); g_cache_dirty[dev] = false; }
             *p = it->second.back();
             it->second.pop_back();
             g_cache_bytes -= r;
@@ -78,7 +105,7 @@ cudaError_t dev_alloc(void **p, size_t bytes)
         if (e != cudaSuccess) return e;
     }
     std::lock_guard<std::mutex> lk(g_cache_mu);
-    g_cache_size[*p] = r;
+    g_cache_size[*p] = CacheKey{dev, r};
     return cudaSuccess;
 }
 
@@ -88,17 +115,16 @@ void dev_free(void *p)
     std::lock_guard<std::mutex> lk(g_cache_mu);
     auto it = g_cache_size.find(p);
     if (it == g_cache_size.end()) { cudaFree(p); return; }
-    const char *cm = getenv("XFEMM_DEVICE_CACHE_MB");
-    const size_t cap = (size_t)(cm ? atoi(cm) : 16384) << 20;
-    if (g_cache_bytes + it->second > cap)
+    const CacheKey key = it->second;
+    if (g_cache_bytes + key.bytes > cache_cap())
     {
         g_cache_size.erase(it);
         cudaFree(p);
         return;
     }
-    g_cache_free[it->second].push_back(p);
-    g_cache_bytes += it->second;
-    g_cache_dirty = true;
+    g_cache_free[key].push_back(p);
+    g_cache_bytes += key.bytes;
+    g_cache_dirty[key.dev] = true;
 }
 
 static inline int env_int(const char *name, int dflt)
@@ -215,23 +241,6 @@ __global__ void k_reduce2_final(int nblk, const double *part, double *out2)
 // =====================================================================================
 // Persistent preconditioned CG (reference recurrence: spars.cpp:238-316)
 // =====================================================================================
-struct PcgArgs
-{
-    int n_pad, nslices, ncolors;
-    const int *slice_ptr, *slice_wl, *slice_wu, *sell_col, *color_slice;
-    const double *sell_val, *diag, *dinv, *b;
-    double *x, *r, *p, *u, *z, *w;
-    double *part; // 2*gridDim
-    double precision, omega;
-    int max_iter, warm;
-    double *mail; // [0]=iters [1]=er [2]=status [3]=res_o [4]=res
-    WideView wide; // rows outside the SELL slices
-    const double *wide_val;
-    double *wide_acc;
-    const int4 *tiles;   // slice-aligned tiles of the SELL stream per block (stage.cuh), or null
-    const int *tile_ptr; // gridDim+1
-};
-
 // dynamic distribution of a block's slices over its warps (shared-memory ticket counter)
 __device__ __forceinline__ int next_slice(int *ctr, int lane)
 {
@@ -241,13 +250,13 @@ __device__ __forceinline__ int next_slice(int *ctr, int lane)
 }
 
 template <int PRECOND>
-__device__ __forceinline__ double precond_apply(const PcgArgs &a, const AmgArgs &g, GridBar &grid, int r0, int r1,
+__device__ __forceinline__ double precond_apply(const PcgArgs &a, const AmgArgs &g, const AmgArgs &sg, GridBar &grid, int r0, int r1,
                                                 int warp_g, int nwarps_g, int lane, int *s_next, int *s_wk,
                                                 StageSmem *S, bool x0_ready = false)
 {
     // returns this thread's partial of r.z ; z is left in a.z (MC-SSOR, AMG) or implied (Jacobi)
     double dot = 0.0;
-    if (PRECOND == XFEMM_PRECOND_AMG) return amg_vcycle(g, grid, s_next, s_wk, S, x0_ready);
+    if (PRECOND == XFEMM_PRECOND_AMG) return amg_vcycle(g, sg, grid, s_next, s_wk, S, x0_ready);
     if (PRECOND == XFEMM_PRECOND_JACOBI)
     {
         for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x)
@@ -308,6 +317,8 @@ __device__ __forceinline__ double precond_apply(const PcgArgs &a, const AmgArgs 
 template <int PRECOND>
 __global__ void __launch_bounds__(1024, 1) k_pcg(const __grid_constant__ PcgArgs a, const __grid_constant__ AmgArgs g)
 {
+    __shared__ __align__(16) unsigned char sg_raw[PRECOND == XFEMM_PRECOND_AMG ? sizeof(AmgArgs) : 16];
+    const AmgArgs *sgp = &g; // multigrid: the block's shared-memory copy of g for the out-of-line passes (amg_kernel_init)
     __shared__ double sm[33];
     __shared__ int s_next;
     __shared__ int s_wk[AMG_SWK_SIZE];
@@ -332,10 +343,7 @@ __global__ void __launch_bounds__(1024, 1) k_pcg(const __grid_constant__ PcgArgs
         S.ntiles = t1 - t0;
         S.tile = a.tiles + t0;
     }
-    if (PRECOND == XFEMM_PRECOND_AMG)
-    {
-        amg_kernel_init(g, s_wk); // wide rows of this block's chunk of every level, team barrier state
-    }
+    if (PRECOND == XFEMM_PRECOND_AMG) sgp = &amg_kernel_init<1>(g, sg_raw, s_wk);
 
     // ---- res_o = b . M^-1 b   (spars.cpp:257-259) ; z0 is computed with r := b
     for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x)
@@ -344,7 +352,7 @@ __global__ void __launch_bounds__(1024, 1) k_pcg(const __grid_constant__ PcgArgs
         if (!a.warm) a.x[i] = 0.0;
     }
     grid.sync();
-    double part = precond_apply<PRECOND>(a, g, grid, r0, r1, warp_g, nwarps_g, lane, &s_next, s_wk, &S);
+    double part = precond_apply<PRECOND>(a, g, *sgp, grid, r0, r1, warp_g, nwarps_g, lane, &s_next, s_wk, &S);
     part = block_sum(part, sm);
     if (threadIdx.x == 0) partA[blockIdx.x] = part;
     grid.sync();
@@ -369,7 +377,7 @@ __global__ void __launch_bounds__(1024, 1) k_pcg(const __grid_constant__ PcgArgs
         grid.sync();
     }
     // ---- z = M^-1 r ; p = z ; res = z.r
-    part = precond_apply<PRECOND>(a, g, grid, r0, r1, warp_g, nwarps_g, lane, &s_next, s_wk, &S);
+    part = precond_apply<PRECOND>(a, g, *sgp, grid, r0, r1, warp_g, nwarps_g, lane, &s_next, s_wk, &S);
     part = block_sum(part, sm);
     if (threadIdx.x == 0) partB[blockIdx.x] = part;
     grid.sync();
@@ -387,21 +395,31 @@ __global__ void __launch_bounds__(1024, 1) k_pcg(const __grid_constant__ PcgArgs
         int ck = AMG_MAX_STAMPS - 8; // XFEMM_AMG_TRACE: the phases of the CG part go to the tail of the stamp buffer
         if (PRECOND == XFEMM_PRECOND_AMG) amg_stamp(g, ck, AMG_MAX_STAMPS);
         part = 0.0;
-        wide_rows_block<double>(a.wide, a.wide_val, a.wide_acc, wk0, wk1, a.p, a.u);
+        if (PRECOND == XFEMM_PRECOND_AMG) amg_block_stamp(g, 0, true);
         if (S.ntiles > 0)
         {
             // matrix stream through the shared-memory ring (stage.cuh)
             staged_slices(S, a.slice_ptr, a.sell_val, a.sell_col, s0, s1, a.p, &s_next,
                           [&](int row) { return make_double2(a.diag[row], a.p[row]); },
                           [&](int s, int row, double acc, double2 dp) {
-                              if (wk1 > wk0 && ((a.wide.mask[s] >> lane) & 1u)) acc += a.u[row];
+                              if (wk1 > wk0 && ((a.wide.mask[s] >> lane) & 1u)) return; // a wide row: see `before`
                               acc = fma(dp.x, dp.y, acc);
                               a.u[row] = acc;
                               part = fma(dp.y, acc, part);
+                          },
+                          [&]() {
+                              // the wide rows of the chunk: a few warps, before they join the stream
+                              if (wk1 > wk0)
+                                  wide_rows_warp(a.wide, a.wide_val, wk0, wk1, a.p, [&](int row, double off) {
+                                      const double pr = a.p[row], acc = fma(a.diag[row], pr, off);
+                                      a.u[row] = acc;
+                                      part = fma(pr, acc, part);
+                                  });
                           });
         }
         else
         {
+        wide_rows_block<double>(a.wide, a.wide_val, a.wide_acc, wk0, wk1, a.p, a.u);
         if (threadIdx.x == 0) s_next = s0;
         __syncthreads();
         for (int s = next_slice(&s_next, lane); s < s1; s = next_slice(&s_next, lane))
@@ -415,6 +433,7 @@ __global__ void __launch_bounds__(1024, 1) k_pcg(const __grid_constant__ PcgArgs
             part = fma(pr, acc, part);
         }
         }
+        if (PRECOND == XFEMM_PRECOND_AMG) amg_block_stamp(g, 0);
         part = block_sum(part, sm);
         if (threadIdx.x == 0) partA[blockIdx.x] = part;
         grid.sync();
@@ -485,7 +504,7 @@ __global__ void __launch_bounds__(1024, 1) k_pcg(const __grid_constant__ PcgArgs
             grid.sync();
             if (PRECOND == XFEMM_PRECOND_AMG) amg_stamp(g, ck, AMG_MAX_STAMPS);
             // step iv: z = M^-1 r ; z.r
-            part = precond_apply<PRECOND>(a, g, grid, r0, r1, warp_g, nwarps_g, lane, &s_next, s_wk, &S, true);
+            part = precond_apply<PRECOND>(a, g, *sgp, grid, r0, r1, warp_g, nwarps_g, lane, &s_next, s_wk, &S, true);
         }
         part = block_sum(part, sm);
         if (threadIdx.x == 0) partB[blockIdx.x] = part;
@@ -536,6 +555,8 @@ __global__ void __launch_bounds__(1024, 1) k_pcg(const __grid_constant__ PcgArgs
 template <int PRECOND>
 __global__ void __launch_bounds__(512, 2) k_precond_only(const __grid_constant__ PcgArgs a, const __grid_constant__ AmgArgs g)
 {
+    __shared__ __align__(16) unsigned char sg_raw[PRECOND == XFEMM_PRECOND_AMG ? sizeof(AmgArgs) : 16];
+    const AmgArgs *sgp = &g;
     __shared__ int s_next;
     __shared__ int s_wk[AMG_SWK_SIZE];
     GridBar grid{cg::this_grid(), PRECOND == XFEMM_PRECOND_AMG ? g.grid_ctr : nullptr, s_wk + AMG_SWK_EPOCH + 1};
@@ -546,11 +567,8 @@ __global__ void __launch_bounds__(512, 2) k_precond_only(const __grid_constant__
     const int s0 = (int)((long long)a.nslices * blockIdx.x / G);
     const int s1 = (int)((long long)a.nslices * (blockIdx.x + 1) / G);
     const int r0 = s0 * 32, r1 = s1 * 32;
-    if (PRECOND == XFEMM_PRECOND_AMG)
-    {
-        amg_kernel_init(g, s_wk);
-    }
-    precond_apply<PRECOND>(a, g, grid, r0, r1, warp_g, nwarps_g, lane, &s_next, s_wk, nullptr);
+    if (PRECOND == XFEMM_PRECOND_AMG) sgp = &amg_kernel_init<1>(g, sg_raw, s_wk);
+    precond_apply<PRECOND>(a, g, *sgp, grid, r0, r1, warp_g, nwarps_g, lane, &s_next, s_wk, nullptr);
     if (PRECOND == XFEMM_PRECOND_JACOBI)
         for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x) a.z[i] = a.r[i] * a.dinv[i];
 }
@@ -830,7 +848,7 @@ static int coop_grid(xfemm_linprob *p, K kernel, int threads, int *grid_out, siz
     return XFEMM_OK;
 }
 
-static PcgArgs make_args(xfemm_linprob *p, double precision, int warm, int max_iter)
+PcgArgs linprob_make_args(xfemm_linprob *p, double precision, int warm, int max_iter)
 {
     PcgArgs a;
     a.n_pad = p->lay.n_pad; a.nslices = p->lay.nslices; a.ncolors = p->lay.ncolors;
@@ -852,19 +870,21 @@ static PcgArgs make_args(xfemm_linprob *p, double precision, int warm, int max_i
 // Slice-aligned tiles (<= STAGE_TILE_ENT entries) of every block's chunk of the SELL stream for a
 // launch with `grid` blocks (stage.cuh).  Cached per layout and grid size.  Returns false when the
 // staging does not apply (a block would need more tiles than its table holds, or it is disabled).
-static bool ensure_tiles(xfemm_linprob *p, int grid)
+// first / end: the range of slices the launch works on (a rank's share of a partitioned solve, dist_amg.cu); -1: all
+static bool ensure_tiles(xfemm_linprob *p, int grid, int first = -1, int end = -1)
 {
     if (env_int("XFEMM_STAGED", 1) == 0) return false;
-    if (p->tile_grid == grid) return p->tiles.n > 0;
-    p->tile_grid = grid;
+    if (first < 0) { first = 0; end = p->lay.nslices; }
+    if (p->tile_grid == grid && p->tile_first == first && p->tile_end == end) return p->tiles.n > 0;
+    p->tile_grid = grid; p->tile_first = first; p->tile_end = end;
     p->tiles.release(); p->tile_ptr.release();
     const std::vector<int> &sp = p->lay.slice_ptr;
-    const int ns = p->lay.nslices;
+    const int ns = end - first;
     std::vector<int4> tiles;
     std::vector<int> tptr(grid + 1, 0);
     for (int b = 0; b < grid; b++)
     {
-        const int s0 = (int)((long long)ns * b / grid), s1 = (int)((long long)ns * (b + 1) / grid);
+        const int s0 = first + (int)((long long)ns * b / grid), s1 = first + (int)((long long)ns * (b + 1) / grid);
         int s = s0;
         while (s < s1)
         {
@@ -1282,7 +1302,7 @@ int linprob_load_rhs_internal(xfemm_linprob *p)
 int linprob_apply_amg_resident(xfemm_linprob *p)
 {
     if (!p->amg) { set_error("multigrid hierarchy not prepared"); return XFEMM_ERR_ARG; }
-    PcgArgs a = make_args(p, 0, 0, 0);
+    PcgArgs a = linprob_make_args(p, 0, 0, 0);
     AmgArgs g;
     void *kargs[] = {&a, &g};
     if (p->precond_grid <= 0)
@@ -1301,6 +1321,15 @@ int linprob_apply_amg_resident(xfemm_linprob *p)
 }
 // stream tiles of the finest level for a launch with `grid` blocks (stage.cuh); false: use direct loads
 bool linprob_ensure_tiles(xfemm_linprob *p, int grid) { return ensure_tiles(p, grid); }
+bool linprob_ensure_tiles_range(xfemm_linprob *p, int grid, int first, int end) { return ensure_tiles(p, grid, first, end); }
+// the problem's V (caller order) into `dst` (internal order): initial guess of a warm start
+int linprob_load_guess_internal(xfemm_linprob *p, double *dst)
+{
+    const int n_pad = p->lay.n_pad;
+    ++g_launch, k_to_internal<<<(n_pad + 255) / 256, 256, 0, p->stream>>>(n_pad, p->i2c.p, p->V.p, dst);
+    XB_CUDA(cudaGetLastError());
+    return XFEMM_OK;
+}
 int linprob_store_solution_internal(xfemm_linprob *p)
 {
     const int n_pad = p->lay.n_pad;
@@ -1340,7 +1369,7 @@ int xfemm_linprob_pcg(xfemm_linprob *p, double precision, int warm, int precond,
     ++xb::g_launch, k_to_internal<<<(n_pad + 255) / 256, 256, 0, st>>>(n_pad, p->i2c.p, p->b.p, p->bint.p);
     if (warm) ++xb::g_launch, k_to_internal<<<(n_pad + 255) / 256, 256, 0, st>>>(n_pad, p->i2c.p, p->V.p, p->x.p);
     if (max_iter <= 0) max_iter = env_int("XFEMM_MAX_ITER", 200000);
-    PcgArgs a = make_args(p, precision, warm ? 1 : 0, max_iter);
+    PcgArgs a = linprob_make_args(p, precision, warm ? 1 : 0, max_iter);
     int grid = 0;
     AmgArgs g;
     void *kargs[] = {&a, &g};
@@ -1382,6 +1411,20 @@ int xfemm_linprob_pcg(xfemm_linprob *p, double precision, int warm, int precond,
     XB_CUDA(cudaStreamSynchronize(st));
     XB_CUDA(cudaGetLastError());
     if (precond == XFEMM_PRECOND_AMG && g.stamps) amg_print_trace(*p->amg, st);
+    if (precond == XFEMM_PRECOND_AMG && g.stamps && g.trace_detail)
+    {
+        // per block: SELL entries / wide rows of its chunk of the finest level (to set against the per-block times)
+        const std::vector<int> &sp = p->lay.slice_ptr;
+        fprintf(stderr, "[amg trace]   per block (k entries / wide rows):");
+        for (int b = 0; b < grid; b++)
+        {
+            const int s0 = (int)((long long)p->lay.nslices * b / grid), s1 = (int)((long long)p->lay.nslices * (b + 1) / grid);
+            int nw = 0;
+            for (int r : p->lay.wide_row) if (r >= s0 * 32 && r < s1 * 32) nw++;
+            fprintf(stderr, " %d/%d", (sp[s1] - sp[s0]) / 1000, nw);
+        }
+        fprintf(stderr, "\n");
+    }
     local.iterations = (int)p->h_mail[0];
     local.er = p->h_mail[1];
     local.status = (int)p->h_mail[2];
@@ -1452,7 +1495,7 @@ int xfemm_linprob_multpc(xfemm_linprob *p, int precond, const double *x, double 
     const int n_pad = p->lay.n_pad;
     XB_CUDA(cudaMemcpyAsync(p->Vold.p, x, (size_t)p->n * sizeof(double), cudaMemcpyHostToDevice, st));
     ++xb::g_launch, k_to_internal<<<(n_pad + 255) / 256, 256, 0, st>>>(n_pad, p->i2c.p, p->Vold.p, p->r.p);
-    PcgArgs a = make_args(p, 0, 0, 0);
+    PcgArgs a = linprob_make_args(p, 0, 0, 0);
     int grid = 0;
     AmgArgs g;
     void *kargs[] = {&a, &g};

@@ -49,6 +49,7 @@ struct xfemm_linprob
     xb::DevBuf<int4> tiles;        // per-block tiles of the SELL stream for the shared-memory ring (stage.cuh)
     xb::DevBuf<int> tile_ptr;
     int tile_grid = -1;            // grid size the tiles were cut for
+    int tile_first = -1, tile_end = -1; // and the range of slices
     int precond_grid = 0;          // cached grid of the stand-alone preconditioner kernel
     xb::DevBuf<double> hist1, hist2, hist3; // solutions of the last three problems solved on this handle (sweeps)
     int hist_count = 0;
@@ -78,4 +79,6 @@ int linprob_load_rhs_internal(xfemm_linprob *p);
 int linprob_store_solution_internal(xfemm_linprob *p);
 int linprob_apply_amg_resident(xfemm_linprob *p);
 bool linprob_ensure_tiles(xfemm_linprob *p, int grid);
+bool linprob_ensure_tiles_range(xfemm_linprob *p, int grid, int first, int end);
+int linprob_load_guess_internal(xfemm_linprob *p, double *dst);
 } // namespace xb

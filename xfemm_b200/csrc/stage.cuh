@@ -120,10 +120,13 @@ __device__ __forceinline__ void prefetch_l1(const void *p)
 // slice's SELL entries, then epi(slice, row, acc, pre(row)).  pre(row) runs as soon as the warp has its
 // ticket — before it waits for the tile — so the row-indexed loads of the epilogue (diagonal, x[row], right-hand
 // side) are in flight during the wait and the gathers.  `s_next` is the block's ticket counter.
-template <class Pre, class Epi>
+// before(): runs once per warp after the ring has been started and before the warp takes its first ticket — the
+// place for work that would otherwise hold up the whole block in front of the stream (the wide rows, wide_rows.cuh).
+struct StageNoBefore { __device__ __forceinline__ void operator()() const {} };
+template <class Pre, class Epi, class Before = StageNoBefore>
 __device__ __forceinline__ void staged_slices(StageSmem &S, const int *__restrict__ slice_ptr, const double *sell_val,
                                               const int *sell_col, int s0, int s1, const double *x, int *s_next, Pre pre,
-                                              Epi epi)
+                                              Epi epi, Before before = Before())
 {
     const int lane = threadIdx.x & 31;
     if (threadIdx.x == 0)
@@ -135,6 +138,7 @@ __device__ __forceinline__ void staged_slices(StageSmem &S, const int *__restric
         for (int k = 0; k < S.ntiles && k < STAGE_COUNT; k++) stage_issue(S, k, sell_val, sell_col);
     }
     __syncthreads();
+    before();
     int k = 0;
     while (true)
     {

@@ -55,8 +55,22 @@ __device__ __forceinline__ void wide_rows_block(const WideView &w, const T *__re
     {
         const int q1 = w.sptr[sg + 1];
         T acc = w_zero((const T *)nullptr);
-#pragma unroll 8
-        for (int q = w.sptr[sg] + lane; q < q1; q += 32) acc = w_fma(val[q], x[w.col[q]], acc);
+        // a segment has at most 256 entries: eight per lane, all loads in flight together (see wide_rows_warp)
+        for (int qb = w.sptr[sg] + lane; qb < q1; qb += 256)
+        {
+            T a[8];
+            int j[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+            {
+                const int q = qb + 32 * u;
+                const bool ok = q < q1;
+                a[u] = ok ? val[q] : w_zero((const T *)nullptr);
+                j[u] = ok ? w.col[q] : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) acc = w_fma(a[u], x[j[u]], acc);
+        }
         acc = w_warp_sum(acc);
         if (lane == 0) seg_acc[sg] = acc;
     }
@@ -66,6 +80,41 @@ __device__ __forceinline__ void wide_rows_block(const WideView &w, const T *__re
         T s = w_zero((const T *)nullptr);
         for (int sg = w.rseg[k]; sg < w.rseg[k + 1]; sg++) s = w_add(s, seg_acc[sg]);
         y[w.row[k]] = s;
+    }
+}
+
+// The wide rows [k0,k1) dealt out to the warps of the block, last warp first: a warp forms the off-diagonal sum of a
+// whole row (its segments are contiguous) and lane 0 hands it to epi(row, sum).  No block-wide step: the other warps
+// of the block go on with the regular slices meanwhile (stage.cuh: `before`), which then SKIP the rows flagged in the
+// per-slice mask — the wide warp is the only writer of a wide row.
+template <class Epi>
+__device__ __forceinline__ void wide_rows_warp(const WideView &w, const double *__restrict__ val, int k0, int k1, const double *x, Epi epi)
+{
+    const int lane = threadIdx.x & 31, warp_b = threadIdx.x >> 5, nwarps_b = blockDim.x >> 5;
+    for (int k = k0 + (nwarps_b - 1 - warp_b); k < k1; k += nwarps_b)
+    {
+        const int row = w.row[k];
+        const int q0 = w.sptr[w.rseg[k]], q1 = w.sptr[w.rseg[k + 1]];
+        double acc = 0.0;
+        // eight entries per lane and step, all loads of a step in flight together (a plain loop with a run-time trip
+        // count of six or seven goes through the compiler's remainder loop: one dependent round trip pair per entry)
+        for (int qb = q0 + lane; qb < q1; qb += 256)
+        {
+            double a[8];
+            int j[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+            {
+                const int q = qb + 32 * u;
+                const bool ok = q < q1;
+                a[u] = ok ? val[q] : 0.0;
+                j[u] = ok ? w.col[q] : row;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) acc = fma(a[u], x[j[u]], acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) epi(row, acc);
     }
 }
 

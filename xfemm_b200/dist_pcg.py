@@ -217,7 +217,11 @@ class DistPCG:
                     for _ in range(check_every):
                         self._iteration()
                     its += check_every
-                er = math.sqrt(max(float(g[0].item()), 0.0) / res0)
+                res = float(g[0].item())
+                if not math.isfinite(res) or res < 0.0:
+                    # the single-GPU kernel reports XFEMM_ERR_DIVERGED for NaN / breakdown; so does this path
+                    raise self.X.XfemmError(f"partitioned PCG diverged after {its} iterations (residual {res})")
+                er = math.sqrt(res / res0)
             t1.record()
             t1.synchronize()
         return {"iterations": its, "er": er, "solve_ms": t0.elapsed_time(t1), "graph": graph is not None,

@@ -38,6 +38,10 @@ def main(argv=None):
     ap.add_argument("--repeats", type=int, default=1)
     ap.add_argument("--check-every", type=int, default=None)
     ap.add_argument("--precond", default="jacobi", choices=["amg", "jacobi"])
+    ap.add_argument("--solver", default="nccl", choices=["nccl", "peer"],
+                    help="nccl: round-1 path (kernels + torch.distributed collectives per iteration, Jacobi or block-local "
+                         "multigrid); peer: ONE persistent kernel per GPU with the global multigrid hierarchy, halo and "
+                         "scalars as peer stores over NVLink (xfemm_dpcg_*, csrc/dist_amg.cu)")
     ap.add_argument("--out", default=None)
     a = ap.parse_args(argv)
 
@@ -71,6 +75,26 @@ def main(argv=None):
         S.renumber()
         S.solve()  # assembly + boundary conditions only
         t_setup = time.perf_counter() - t0
+        if a.solver == "peer":
+            from xfemm_b200.dist_amg import DistAmgPCG
+            D = DistAmgPCG(S)
+            prec = a.precision if a.precision is not None else _fem_precision(base + ".fem")
+            infos = [D.solve(prec) for _ in range(a.repeats)]
+            ms = torch.tensor([min(i["solve_ms"] for i in infos)], dtype=torch.float64, device="cuda")
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            V = D.solution()
+            if rank == 0:
+                line = {"mode": "row-partitioned multigrid pcg, peer stores", "n_gpus": world, "backend": a.backend, "n": int(D.n),
+                        "iterations": infos[-1]["iterations"], "er": infos[-1]["er"], "solve_ms": float(ms.item()),
+                        "ms_per_iteration": float(ms.item()) / max(1, infos[-1]["iterations"]), "setup_s": t_setup,
+                        "plan": D.stats()}
+                print(json.dumps(line), flush=True)
+                if a.out:
+                    np.savez(a.out, V=V, perm=S.permutation())
+            D.close()
+            S.close()
+            shutil.rmtree(tmp, ignore_errors=True)
+            return
         D = DistPCG(S, precond=X.PRECOND_AMG if a.precond == "amg" else X.PRECOND_JACOBI)
         D.refresh()
         prec = a.precision if a.precision is not None else _fem_precision(base + ".fem")

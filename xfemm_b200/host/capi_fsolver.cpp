@@ -160,6 +160,9 @@ int xfemm_fsolver_write(xfemm_fsolver *s)
 {
     if (!s) return XFEMM_ERR_ARG;
     int ok = 0;
+    // a sweep that kept the nodal values on the device (option fetch_solution = 0): bring them over now rather than
+    // write the previous position's field
+    if (s->L && !s->S.fetchDeviceSolution(*s->L)) { xb::set_error("could not fetch the solution from the device"); return XFEMM_ERR_CUDA; }
     if (s->L) ok = s->S.WriteStatic2D(*s->L);
     else if (s->Lc) ok = s->S.WriteHarmonic2D(*s->Lc);
     if (!ok) { xb::set_error("couldn't write results to disk"); return XFEMM_ERR_IO; }
@@ -271,6 +274,7 @@ int xfemm_fsolver_get_solution(xfemm_fsolver *s, double *V, double *A)
     if (!s) return XFEMM_ERR_ARG;
     if (s->L)
     {
+        if (!s->S.fetchDeviceSolution(*s->L)) { xb::set_error("could not fetch the solution from the device"); return XFEMM_ERR_CUDA; }
         if (V) memcpy(V, s->L->V, sizeof(double) * s->L->n);
         if (A) memcpy(A, s->L->b, sizeof(double) * s->L->n);
         return XFEMM_OK;
@@ -321,6 +325,8 @@ int xfemm_fsolver_set_option(xfemm_fsolver *s, const char *key, double value)
     if (!strcmp(key, "cache_static_part")) { s->S.cacheStaticPart = value != 0; return XFEMM_OK; }
     if (!strcmp(key, "assemble_only")) { s->S.assembleOnly = value != 0; return XFEMM_OK; }
     if (!strcmp(key, "age_union_pattern")) { s->S.ageUnionPattern = value != 0; return XFEMM_OK; }
+    if (!strcmp(key, "dist_rank")) { s->S.distRank = (int)value; return XFEMM_OK; }
+    if (!strcmp(key, "dist_world")) { s->S.distWorld = (int)value; return XFEMM_OK; }
     xb::set_error("unknown option %s", key);
     return XFEMM_ERR_ARG;
 }

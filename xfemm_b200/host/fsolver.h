@@ -249,6 +249,13 @@ public:
     // newnum[i] = solver index of mesh-file node i (the Cuthill–McKee permutation), kept for parity checks
     std::vector<int> cmPermutation;
     std::vector<int> edgeList;   // .edge node pairs cached by LoadMesh for Cuthill
+    // One mesh over several GPUs (one process per GPU, every process runs the same FSolver calls): rank / size of
+    // this process.  distWorld > 1 routes the linear solves of Static2D / StaticAxisymmetric through xfemm_dpcg_*
+    // (csrc/dist_amg.cu); the processes find each other through files XFEMM_DIST_DIR/XFEMM_DIST_JOB.<rank>
+    // (defaults: /dev/shm, "xfemm_dpcg").  Options "dist_rank" / "dist_world" of xfemm_fsolver_set_option; the
+    // fsolver command line reads XFEMM_DIST_RANK / XFEMM_DIST_WORLD.
+    int distRank = 0, distWorld = 1;
+    struct xfemm_dpcg *dpcg = nullptr; // owned, tied to the resident device problem
     int precondOption;           // XFEMM_PRECOND_* or -1 = backend default
     int maxIterOption;           // <=0 = backend default
     xfemm_mag *magdev;           // device mesh of the last solve (kept for queries), owned
@@ -264,12 +271,14 @@ public:
         // conditions) is assembled once and kept on the device; a position restores it and adds its air-gap blocks
         bool staticPartUsable = false, staticPartCached = false;
     } plan;
-    std::vector<double> jprevByLabel; // per-label source current accumulated over the solves (added to Jprev on write)
     bool warmResolve;            // a re-solve on the resident problem starts from the solution it finds there (default true)
     bool resolveStart;           // set for the duration of such a re-solve
     bool extrapolateResolve;     // ... from the linear extrapolation of the last two solutions (equidistant sweeps; default true)
     bool cacheStaticPart;        // sweeps on linear problems keep the position-independent, boundary-conditioned part on the device (default true)
     bool fetchSolution;          // copy V and A back to the host after a solve (default true; sweeps that only need torque switch it off)
+    bool hostSolutionStale = false; // the last solve left V and A on the device (fetchSolution was off): see fetchDeviceSolution
+    // copies V and A of the last static solve from the device into L.V / L.b if they were left there; false on a CUDA error
+    bool fetchDeviceSolution(CBigLinProb &L);
     bool gapTorque(int ageIndex, double &torque); // from the resident solution, = fpproc's gap integral 0
     std::thread prebuild;        // host thread building the solver structure while the first assembly runs
     void joinPrebuild() { if (prebuild.joinable()) prebuild.join(); }

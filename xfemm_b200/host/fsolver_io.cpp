@@ -109,6 +109,9 @@ FSolver::FSolver()
     PrintMessage = &PrintWarningMsg;
     precondOption = -1;
     maxIterOption = 0;
+    // one mesh over several GPUs (see fsolver.h): the command line and unmodified callers pick it up from the environment
+    if (const char *w = getenv("XFEMM_DIST_WORLD")) distWorld = std::max(1, atoi(w));
+    if (const char *r = getenv("XFEMM_DIST_RANK")) distRank = std::max(0, atoi(r));
     magdev = nullptr;
     cmagdev = nullptr;
     keepSystem = false;
@@ -843,7 +846,7 @@ int FSolver::WriteHarmonic2D(CBigComplexLinProb &L)
     {
         fprintf(fp, "%i\t%i\t%i\t%i\t%i\t%i\t%i", meshele[i].p[0], meshele[i].p[1], meshele[i].p[2], meshele[i].lbl,
                 meshele[i].e[0], meshele[i].e[1], meshele[i].e[2]);
-        if (!Aprev.empty()) fprintf(fp, "\t%.17g\n", meshele[i].Jprev + (jprevByLabel.empty() ? 0. : jprevByLabel[meshele[i].lbl])); else fprintf(fp, "\n");
+        if (!Aprev.empty()) fprintf(fp, "\t%.17g\n", meshele[i].Jprev); else fprintf(fp, "\n");
     }
     fprintf(fp, "%i\n", NumBlockLabels);
     for (int k = 0; k < NumBlockLabels; k++)

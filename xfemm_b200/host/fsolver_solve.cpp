@@ -45,6 +45,7 @@ static double wall() { return std::chrono::duration<double>(std::chrono::steady_
 void FSolver::releaseDevice()
 {
     joinPrebuild();
+    if (dpcg) { xfemm_dpcg_destroy(dpcg); dpcg = nullptr; }
     if (magdev) { xfemm_mag_destroy(magdev); magdev = nullptr; }
     if (cmagdev) { xfemm_cmag_destroy(cmagdev); cmagdev = nullptr; }
 }
@@ -628,7 +629,8 @@ int FSolver::staticSolve(CBigLinProb &L, bool axi)
     // Locality hint for the solver's internal row order (Z-curve through the node coordinates): the finer
     // layout costs ~0.08 s of host time at 2 M nodes and saves ~2 ms per solve, so by default it is used
     // when the device problem is going to be solved repeatedly (Newton iteration, rotor sweeps).
-    if (localityOrder > 0 || (localityOrder < 0 && (ageUnionPattern || !LinearFlag))) xfemm_linprob_set_coords(lin, xy.data());
+    // (a partitioned solve always: a rank's share of the rows is then a compact patch of the mesh, its halo small)
+    if (localityOrder > 0 || distWorld > 1 || (localityOrder < 0 && (ageUnionPattern || !LinearFlag))) xfemm_linprob_set_coords(lin, xy.data());
     // The solver structure (SELL layout, multigrid hierarchy) depends on the pattern only: a host thread
     // builds it while this thread uploads the mesh and runs the first assembly and boundary conditions.
     if (!assembleOnly && !getenv("XFEMM_NO_PREBUILD"))
@@ -809,8 +811,24 @@ int FSolver::staticNewton(CBigLinProb &L)
         xfemm_solve_info info;
         // Newton steps after the first continue from the last iterate (static2d.cpp:929); so does the first
         // solve of a re-solve on the resident problem (next rotor position: the previous field is close)
+        if (distWorld > 1)
+        {
+            // one mesh over several GPUs: every process has assembled the same system; the solve is shared
+            memset(&info, 0, sizeof info);
+            if (!dpcg)
+            {
+                const char *dir = getenv("XFEMM_DIST_DIR"), *job = getenv("XFEMM_DIST_JOB");
+                rc = xfemm_dpcg_create(lin, distRank, distWorld, &dpcg);
+                if (rc == XFEMM_OK) rc = xfemm_dpcg_connect_files(dpcg, dir ? dir : "/dev/shm", job ? job : "xfemm_dpcg", 300);
+            }
+            else rc = XFEMM_OK;
+            if (rc == XFEMM_OK) rc = xfemm_dpcg_solve(dpcg, L.Precision, (Iter > 0 || resolveStart) ? 1 : 0, maxIterOption, &info);
+            if (rc == XFEMM_OK) rc = xfemm_dpcg_share_solution(dpcg);
+            if (rc == XFEMM_OK) rc = xfemm_dpcg_finish(dpcg);
+        }
+        else
         rc = xfemm_linprob_pcg(lin, L.Precision, (Iter > 0 || resolveStart) ? 1 : 0, precond, maxIterOption, &info);
-        if (rc == XFEMM_ERR_DIVERGED && precond == XFEMM_PRECOND_AMG)
+        if (rc == XFEMM_ERR_DIVERGED && precond == XFEMM_PRECOND_AMG && distWorld <= 1)
         {
             // safety net: the multigrid hierarchy is built from the sparsity pattern alone; should a problem
             // defeat it, the (slower, always applicable) Jacobi-preconditioned kernel takes over on the GPU
@@ -859,15 +877,24 @@ int FSolver::staticNewton(CBigLinProb &L)
 
     // results back to the caller's arrays: L.V internal units, L.b = A (static2d.cpp:1018-1021)
     // (sweeps that only read derived quantities — gapTorque — leave the nodal values on the device)
-    if (fetchSolution && (xfemm_linprob_get_solution(lin, L.V) != XFEMM_OK || xfemm_mag_solution_to_A(magdev, L.b) != XFEMM_OK))
+    hostSolutionStale = true;
+    if (fetchSolution && !fetchDeviceSolution(L)) return false;
+    // The reference also accumulates meshele[i].Jprev += Jsrc on every pass of a non-incremental problem
+    // (static2d.cpp:506); nothing reads it afterwards — WriteStatic2D does not print it and WriteHarmonic2D prints the
+    // value loaded from a previous solution (harmonic2d.cpp:947) — so it is not kept here.
+    return true;
+}
+
+bool FSolver::fetchDeviceSolution(CBigLinProb &L)
+{
+    if (!hostSolutionStale) return true;
+    if (!L.device() || !magdev) { WarnMessage("xfemm_b200: no device solution to fetch\n"); return false; }
+    if (xfemm_linprob_get_solution(L.device(), L.V) != XFEMM_OK || xfemm_mag_solution_to_A(magdev, L.b) != XFEMM_OK)
     {
         WarnMessage(xfemm_last_error());
         return false;
     }
-    // bookkeeping the reference keeps per element
-    // (kept per label and folded into the element records when the .ans file is written)
-    if ((int)jprevByLabel.size() != NumBlockLabels) jprevByLabel.assign(NumBlockLabels, 0.);
-    for (int l = 0; l < NumBlockLabels; l++) jprevByLabel[l] += Iter * plan.labelJsrc[l];
+    hostSolutionStale = false;
     return true;
 }
 
