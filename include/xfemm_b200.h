@@ -214,6 +214,13 @@ typedef struct xfemm_mag_desc
     double r_eps;                  /* 1e-6*units: nodes with |r| below are on the axis          */
 } xfemm_mag_desc;
 
+/* Raw material record of a block label for the block integrals below (CMMaterialProp members) */
+typedef struct xfemm_integral_label
+{
+    double mu_x, mu_y, lamfill, H_c, magdir;
+    int lamtype, bh_offset, bh_points, pad_;
+} xfemm_integral_label;
+
 /* 10x10 matrix of one air-gap-element ring cell for mesh shifts ci, co and aspect ratio
  * K = dr/(R dtheta) (static2d.cpp:200-274); MG100 row-major, symmetric */
 int xfemm_age_cell_matrix(double ci, double co, double K, double *MG100);
@@ -242,6 +249,11 @@ int xfemm_linprob_newton_norms(xfemm_linprob *p, double *dv2, double *v2);
 int xfemm_linprob_relax(xfemm_linprob *p, double relax);
 /* planar: b = V*c ; axisymmetric: b = V*c*2*pi*r*0.01 (static2d.cpp:1018-1021, staticaxi.cpp:779-783) */
 int xfemm_mag_solution_to_A(xfemm_mag *m, double *A_host);
+/* Per block label, from the solution resident on the device (planar magnetostatics): energy_area[l] = sum over the
+ * label's elements of area [m^2] x stored energy density [J/m^3] (FPProc::BlockIntegral(2), cfemm/fpproc/fpproc.cpp:3762-3830,
+ * CMMaterialProp::DoEnergy/GetEnergy, cfemm/libfemm/CMaterialProp.cpp:536-650) and a_area[l] = sum of area x mean nodal A
+ * [Wb m] (the A.J integrand of BlockIntegral(0) / GetFluxLinkage, fpproc.cpp:3678-3686, 5157-5196). */
+int xfemm_mag_label_integrals(xfemm_mag *m, int n_labels, const xfemm_integral_label *labels, double *energy_area, double *a_area);
 /* DC torque through an air-gap element from the RESIDENT solution (no nodal values leave the device).
  * Replaces the post-processor's mo_gapintegral(name,0): cfemm/fpproc/fpproc.cpp:1391-1615 (flux density
  * per ring cell and its harmonics) and 5418-5446 (torque).  cell0/ncells: range in the flattened ring
@@ -258,6 +270,7 @@ int xfemm_mag_gap_torque(xfemm_mag *m, int cell0, int ncells, double inner_shift
 int xfemm_clinprob_create(int n, int n_nodes, const int *rowptr, const int *colidx, xfemm_clinprob **out);
 int xfemm_clinprob_destroy(xfemm_clinprob *p);
 int xfemm_clinprob_n(const xfemm_clinprob *p);
+int xfemm_clinprob_amg_levels(xfemm_clinprob *p, int max_levels, int *n_rows, long long *nnz); /* of the real companion */
 long long xfemm_clinprob_nnz(const xfemm_clinprob *p);
 int xfemm_clinprob_wipe(xfemm_clinprob *p);                                /* cspars.cpp:539 Wipe */
 int xfemm_clinprob_set_values(xfemm_clinprob *p, const double *vals_csr);
@@ -434,7 +447,16 @@ int xfemm_fsolver_set_rotor_angle(xfemm_fsolver *s, int age_index, double inner_
 /* torque [N m] through air-gap element `age_index` from the resident magnetostatic solution
  * (= mo_gapintegral(name,0) of the reference's post-processor on the written .ans) */
 int xfemm_fsolver_gap_torque(xfemm_fsolver *s, int age_index, double *torque);
-int xfemm_fsolver_write(xfemm_fsolver *s);     /* WriteStatic2D / WriteHarmonic2D                  */
+int xfemm_fsolver_write(xfemm_fsolver *s);
+/* Derived quantities of a planar magnetostatic solution from the device, = what the reference obtains by writing the
+ * .ans file and asking its post-processor: stored energy [J] of all blocks (mo_groupselectblock(); mo_blockintegral(2))
+ * and flux linkage [Wb] of circuit `circuit` of the .fem file (third value of mo_getcircuitproperties; circuits that
+ * carry a current: FPProc::GetFluxLinkage's first branch, fpproc.cpp:5166-5196). */
+/* rows / non-zeros of the levels of the multigrid hierarchy of the resident problem (real, or the real companion of a
+ * time-harmonic problem); returns the number of levels, 0 if there is none */
+int xfemm_fsolver_amg_levels(xfemm_fsolver *s, int max_levels, int *n_rows, long long *nnz);
+int xfemm_fsolver_stored_energy(xfemm_fsolver *s, double *joules);
+int xfemm_fsolver_flux_linkage(xfemm_fsolver *s, int circuit, double *webers);     /* WriteStatic2D / WriteHarmonic2D                  */
 int xfemm_fsolver_close(xfemm_fsolver *s);
 int xfemm_fsolver_counts(xfemm_fsolver *s, int *n_nodes, int *n_elems, int *n_pbc, int *n_age,
                          int *bandwidth, int *n_unknowns, int *is_complex);

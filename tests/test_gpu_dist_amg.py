@@ -61,7 +61,7 @@ def test_one_rank_equals_the_single_gpu_solver(case, tmp_path):
     info = D.solve(meta["precision"])
     V = D.solution()
     print(case, "single-GPU kernel", info1.iterations, "iterations; partitioned kernel, one rank:", info, D.stats())
-    assert info["iterations"] == info1.iterations
+    assert abs(info["iterations"] - info1.iterations) <= 1  # same recurrence, another summation order
     assert rel_l2(V, V1) <= 10 * meta["precision"]  # two runs of the same recurrence with different summation orders
     # warm start from the solution: converged at once
     info2 = D.solve(meta["precision"], warm=True)
@@ -86,3 +86,43 @@ def test_ranks_over_peer_memory(tmp_path):
         counts[nproc] = info["iterations"]
     one = _run(base, str(tmp_path / "x1.npz"), 1)["iterations"]
     assert all(abs(c - one) <= 1 for c in counts.values()), (one, counts)
+
+
+def test_fsolver_command_line_on_two_gpus(tmp_path):
+    """The C++ front end: two `fsolver_b200` processes (XFEMM_DIST_RANK / XFEMM_DIST_WORLD, one GPU each) solve ONE
+    problem together — FSolver::Static2D routes its linear solve through xfemm_dpcg_*, the processes find each other
+    through files — and both write the same .ans as a single-GPU run (nodal A within the solver precision)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    cli = os.path.join(ROOT, "xfemm_b200", "fsolver_b200")
+    job = f"xfemm_test_{os.getpid()}"
+    procs, dirs = [], []
+    for r in range(2):
+        d = tmp_path / f"rank{r}"
+        d.mkdir()
+        stage_case("tb30", str(d))
+        dirs.append(d)
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES=str(r), XFEMM_DIST_RANK=str(r), XFEMM_DIST_WORLD="2", XFEMM_DIST_JOB=job,
+                   XFEMM_DIST_TIMEOUT_MS="15000")
+        procs.append(subprocess.Popen([cli, "tb30"], cwd=str(d), env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    for r in range(2):
+        for f in (f"/dev/shm/{job}.{r}",):
+            if os.path.exists(f):
+                os.remove(f)
+    assert all(p.returncode == 0 for p in procs), outs
+    single = tmp_path / "single"
+    single.mkdir()
+    stage_case("tb30", str(single))
+    r = subprocess.run([cli, "tb30"], cwd=str(single), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+    def nodal_A(path):
+        lines = open(path).read().split("[Solution]")[1].strip().splitlines()
+        n = int(lines[0])
+        return np.array([float(ln.split()[2]) for ln in lines[1:1 + n]])
+
+    a1 = nodal_A(single / "tb30.ans")
+    for d in dirs:
+        assert rel_l2(nodal_A(d / "tb30.ans"), a1) <= 1e-8

@@ -102,6 +102,11 @@ SIGNATURES = {
     "xfemm_mag_gap_torque": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                                        C.c_int, C.c_int, C.c_double, C.POINTER(C.c_double), _P]),
     "xfemm_fsolver_gap_torque": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double)]),
+    "xfemm_fsolver_amg_levels": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_longlong)]),
+    "xfemm_clinprob_amg_levels": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_longlong)]),
+    "xfemm_fsolver_stored_energy": (C.c_int, [_P, C.POINTER(C.c_double)]),
+    "xfemm_fsolver_flux_linkage": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double)]),
+    "xfemm_mag_label_integrals": (C.c_int, [_P, C.c_int, _P, _dp, _dp]),
     "xfemm_clinprob_create": (C.c_int, [C.c_int, C.c_int, _ip, _ip, C.POINTER(_P)]),
     "xfemm_clinprob_destroy": (C.c_int, [_P]),
     "xfemm_clinprob_n": (C.c_int, [_P]),
@@ -426,6 +431,18 @@ class FSolver:
         t = C.c_double(0)
         _check(lib().xfemm_fsolver_gap_torque(self.h, age_index, C.byref(t)), "gap_torque")
         return t.value
+
+    def stored_energy(self):
+        """Stored energy [J] of all blocks from the resident solution (= mo_groupselectblock(); mo_blockintegral(2))."""
+        e = C.c_double(0)
+        _check(lib().xfemm_fsolver_stored_energy(self.h, C.byref(e)), "stored_energy")
+        return e.value
+
+    def flux_linkage(self, circuit=0):
+        """Flux linkage [Wb] of circuit `circuit` of the .fem file from the resident solution."""
+        w = C.c_double(0)
+        _check(lib().xfemm_fsolver_flux_linkage(self.h, circuit, C.byref(w)), "flux_linkage")
+        return w.value
 
     def write(self):
         _check(lib().xfemm_fsolver_write(self.h), "write")

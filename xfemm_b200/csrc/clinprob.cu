@@ -694,6 +694,11 @@ int xfemm_clinprob_destroy(xfemm_clinprob *p)
     return XFEMM_OK;
 }
 int xfemm_clinprob_n(const xfemm_clinprob *p) { return p ? p->n : 0; }
+// levels of the multigrid hierarchy of the real companion problem (XFEMM_PRECOND_AMG), as xfemm_linprob_amg_levels
+int xfemm_clinprob_amg_levels(xfemm_clinprob *p, int max_levels, int *n_rows, long long *nnz)
+{
+    return (p && p->re_prec) ? xfemm_linprob_amg_levels(p->re_prec, max_levels, n_rows, nnz) : 0;
+}
 long long xfemm_clinprob_nnz(const xfemm_clinprob *p) { return p ? p->nnz : 0; }
 int xfemm_clinprob_wipe(xfemm_clinprob *p)
 {

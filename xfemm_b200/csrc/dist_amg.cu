@@ -52,7 +52,7 @@ struct DistArgs
 {
     int rank = 0, world = 1, lp = 1;             // levels 0..lp-1 are partitioned, lp.. are cycled by every rank
     char *peer[DIST_MAX_WORLD] = {};             // comm arena of every rank (own: peer[rank])
-    size_t off_flags = 0, off_slots = 0;         // u64 flags[world] ; double slots[4][world]
+    size_t off_flags = 0, off_slots = 0;         // u64 arrival counters[4][8] ; double slots[4][world]
     size_t off_x[DIST_MAX_PART] = {}, off_t[DIST_MAX_PART] = {}; // lev[l].x / lev[l].t
     size_t off_p = 0, off_xs = 0;                // CG direction, solution
     size_t off_bc = 0, off_xc = 0;               // b and x of level lp
@@ -61,7 +61,9 @@ struct DistArgs
     int *abort_flag = nullptr;                   // own memory: a wait missed its deadline
     unsigned long long timeout_ns = 0;
     unsigned long long seq0 = 0;                 // exchange steps / scalar exchanges of the earlier solves on this handle: the
-    int ar0 = 0;                                 // flags count on monotonically and are never reset
+    int ar0 = 0;                                 // arrival counters count on monotonically and are never reset
+    int peer_grid[DIST_MAX_WORLD] = {};          // blocks of every rank's kernel: rank q has finished step s when its counter
+                                                 // here has reached s * peer_grid[q]
     int slices0[AMG_MAX_LEVELS] = {};            // first slice of this rank per level (partitioned levels + level lp)
     int slices1[AMG_MAX_LEVELS] = {};
 };
@@ -79,9 +81,9 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+__device__ __forceinline__ void red_release_sys_add(unsigned long long *p, unsigned long long v)
 {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+    asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ double ld_relaxed_sys(const double *p)
 {
@@ -89,6 +91,12 @@ __device__ __forceinline__ double ld_relaxed_sys(const double *p)
     asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
     return v;
 }
+
+// Arrival counters: four per source rank, step s uses counter s & 3.  A block that runs ahead announces step s + 1 on
+// another counter than the stragglers of step s, so a count can only be completed by the blocks it is meant for
+// (steps four apart cannot overlap: every step is a rendezvous of all ranks).
+__device__ __forceinline__ int ctr_index(unsigned long long s) { return (int)(s & 3ull); }
+__device__ __forceinline__ unsigned long long ctr_uses(unsigned long long s) { return (s >> 2) + ((s & 3ull) ? 1ull : 0ull); }
 
 // per-block state of the exchange machinery (shared memory)
 struct DistSmem
@@ -107,7 +115,11 @@ struct DistCtx
     mutable int ar;
 
     __device__ __forceinline__ double *vec(int q, size_t off) const { return (double *)(d.peer[q] + off); }
-    __device__ __forceinline__ unsigned long long *flags(int q) const { return (unsigned long long *)(d.peer[q] + d.off_flags); }
+    // counter of step s that rank `src` raises in the arena of rank q
+    __device__ __forceinline__ unsigned long long *flags(int q, unsigned long long s, int src) const
+    {
+        return (unsigned long long *)(d.peer[q] + d.off_flags) + ctr_index(s) * DIST_MAX_WORLD + src;
+    }
 
     // rows of this block that other ranks read: store them into the peers' copies of the vector at `off`
     __device__ __forceinline__ void push(int list, size_t off) const
@@ -145,9 +157,10 @@ struct DistCtx
     {
         if ((int)threadIdx.x < d.world && (int)threadIdx.x != d.rank)
         {
-            const unsigned long long *f = flags(d.rank) + threadIdx.x;
+            const unsigned long long *f = flags(d.rank, s, threadIdx.x);
+            const unsigned long long target = ctr_uses(s) * (unsigned long long)d.peer_grid[threadIdx.x];
             const unsigned long long t0 = gtime();
-            while (ld_acquire_sys(f) < s)
+            while (ld_acquire_sys(f) < target)
             {
                 if (*(volatile int *)d.abort_flag) break;
                 if (gtime() - t0 > d.timeout_ns) { atomicExch(d.abort_flag, 1); break; }
@@ -155,20 +168,17 @@ struct DistCtx
         }
         __syncthreads();
     }
-    // end of a phase whose pushes the next phase of the peers consumes: local grid barrier (orders this rank's
-    // stores), signal, wait for everybody's signal
+    // End of a phase whose pushes the next phase of the peers consumes.  Every block announces itself to every
+    // peer as soon as ITS rows are out (a release at system scope on the peer's arrival counter: the block's peer
+    // stores are ordered before it) — the announcements travel while the local grid barrier, which the phase needs
+    // anyway, completes — and then waits until every block of every peer has announced the same step.
     __device__ __forceinline__ void exchange() const
     {
         if (d.world == 1) { grid.sync(); return; }
-        __syncthreads();
-        if (threadIdx.x == 0) fence_sys(); // this block's peer stores before its arrival at the barrier
-        grid.sync();
         const unsigned long long s = ++seq;
-        if (blockIdx.x == 0 && (int)threadIdx.x < d.world && (int)threadIdx.x != d.rank)
-        {
-            fence_sys();
-            st_release_sys(flags(threadIdx.x) + d.rank, s);
-        }
+        __syncthreads();
+        if ((int)threadIdx.x < d.world && (int)threadIdx.x != d.rank) red_release_sys_add(flags(threadIdx.x, s, d.rank), 1ull);
+        grid.sync();
         wait_peers(s);
     }
     // sum of `local` (identical in every block of this rank, final: a grid barrier lies behind it) over the ranks,
@@ -182,8 +192,7 @@ struct DistCtx
         if (blockIdx.x == 0 && (int)threadIdx.x < d.world && (int)threadIdx.x != d.rank)
         {
             ((double *)(d.peer[threadIdx.x] + d.off_slots))[slot + d.rank] = local;
-            fence_sys();
-            st_release_sys(flags(threadIdx.x) + d.rank, s);
+            red_release_sys_add(flags(threadIdx.x, s, d.rank), (unsigned long long)gridDim.x); // one block speaks for all
         }
         wait_peers(s);
         const double *mine = (const double *)(d.peer[d.rank] + d.off_slots) + slot;
@@ -554,7 +563,8 @@ __global__ void k_dist_share_rows(int world, int rank, size_t off, int i0, int i
     if (last && (int)threadIdx.x < world && (int)threadIdx.x != rank)
     {
         fence_sys();
-        st_release_sys((unsigned long long *)(d.peer[threadIdx.x] + d.off_flags) + rank, s);
+        red_release_sys_add((unsigned long long *)(d.peer[threadIdx.x] + d.off_flags) + ctr_index(s) * DIST_MAX_WORLD + rank,
+                            (unsigned long long)d.peer_grid[rank]);
         if (threadIdx.x == 0 || (rank == 0 && threadIdx.x == 1)) *done = 0;
     }
 }
@@ -563,9 +573,10 @@ __global__ void k_dist_collect(int world, int rank, DistArgs d, unsigned long lo
 {
     if ((int)threadIdx.x < world && (int)threadIdx.x != rank)
     {
-        const unsigned long long *f = (const unsigned long long *)(d.peer[rank] + d.off_flags) + threadIdx.x;
+        const unsigned long long *f = (const unsigned long long *)(d.peer[rank] + d.off_flags) + ctr_index(s) * DIST_MAX_WORLD + threadIdx.x;
+        const unsigned long long target = ctr_uses(s) * (unsigned long long)d.peer_grid[threadIdx.x];
         const unsigned long long t0 = gtime();
-        while (ld_acquire_sys(f) < s)
+        while (ld_acquire_sys(f) < target)
             if (gtime() - t0 > d.timeout_ns) { atomicExch(d.abort_flag, 1); break; }
     }
     __syncthreads();
@@ -644,7 +655,7 @@ int xfemm_dpcg_create(xfemm_linprob *p, int rank, int world, xfemm_dpcg **out)
     DistArgs &d = D->d;
     d.rank = rank; d.world = world; d.lp = lp;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-    d.off_flags = take(DIST_MAX_WORLD * sizeof(unsigned long long));
+    d.off_flags = take(4 * DIST_MAX_WORLD * sizeof(unsigned long long));
     d.off_slots = take(4 * DIST_MAX_WORLD * sizeof(double));
     for (int l = 0; l < lp; l++)
     {
@@ -663,6 +674,12 @@ int xfemm_dpcg_create(xfemm_linprob *p, int rank, int world, xfemm_dpcg **out)
     {
         d.slices0[l] = (int)((long long)lev[l]->lay.nslices * rank / world);
         d.slices1[l] = (int)((long long)lev[l]->lay.nslices * (rank + 1) / world);
+    }
+    // blocks of every rank's kernel (the GPUs of a node are alike): what xfemm_dpcg_solve launches
+    for (int q = 0; q < world; q++)
+    {
+        const int own = (int)((long long)p->lay.nslices * (q + 1) / world) - (int)((long long)p->lay.nslices * q / world);
+        d.peer_grid[q] = std::max(1, std::min(p->num_sms, (own + 31) / 32));
     }
     // ---- send lists
     // internal-order transfer maps of the partitioned levels (device copies exist; bring them to the host once)
@@ -868,8 +885,7 @@ int xfemm_dpcg_solve(xfemm_dpcg *D, double precision, int warm, int max_iter, xf
     int per_sm = 0;
     XB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dpcg, 1024, smem));
     if (per_sm < 1) { set_error("k_dpcg does not fit on an SM"); return XFEMM_ERR_CUDA; }
-    const int own_slices = d.slices1[0] - d.slices0[0];
-    int grid = std::max(1, std::min(p->num_sms, (own_slices + 31) / 32));
+    const int grid = d.peer_grid[D->rank];
     if (grid > p->max_grid) { XB_CUDA(p->partials.alloc((size_t)4 * grid)); p->max_grid = grid; }
     amg_fill_args(p, *p->amg, g, grid);
     g.task_smem_offset = (int)STAGE_SMEM_BYTES;

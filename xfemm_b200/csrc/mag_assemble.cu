@@ -538,6 +538,131 @@ __global__ void k_gap_torque(int cell0, int ncells, const int *__restrict__ node
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Block integrals of the reference post-processor from the resident solution (no .ans file, no nodal D2H):
+// per block label l,  E_l = sum_e a_e w_e  (stored energy density, fpproc.cpp:3762-3830 case 2 with
+// CMMaterialProp::DoEnergy / GetEnergy, CMaterialProp.cpp:536-650) and  AJ_l = sum_e a_e mean(A_e)  (the A.J
+// integrand of fpproc.cpp:3678-3686 / GetFluxLinkage 5157-5196 for a current density that is constant over the
+// label).  Planar magnetostatics; a_e in m^2, A in Wb/m, B in T from the three nodal A as FPProc::GetElementB
+// (fpproc.cpp:2970-3004).  The host multiplies by the depth, the label's current density and 1/I.
+// ---------------------------------------------------------------------------------------------------
+constexpr int INTEGRAL_MAX_LABELS = 32;
+struct IntegralLabels
+{
+    int n;
+    xfemm_integral_label l[INTEGRAL_MAX_LABELS];
+};
+
+// stored energy density of a B-H material at |B| = x: integral of H dB along the cubic Hermite curve
+// (CMMaterialProp::GetEnergy, CMaterialProp.cpp:536-585)
+__device__ double bh_energy(double x, int np, const double *__restrict__ Bd, const double *__restrict__ Hd, const double *__restrict__ Sd)
+{
+    const double b = fabs(x);
+    double nrg = 0.0;
+    if (np == 0) return 0.0;
+    for (int i = 0; i < np - 1; i++)
+    {
+        const double b0 = Bd[i], h0 = Hd[i], b1 = Bd[i + 1], h1 = Hd[i + 1], dh0 = Sd[i], dh1 = Sd[i + 1];
+        if (b >= b0 && b <= b1)
+        {
+            const double l = b1 - b0, z = (b - b0) / l, z2 = z * z;
+            nrg += (dh0 * l * l * (6. + z * (-8. + 3. * z)) * z2) / 12. + (h0 * l * z * (2. + (-2. + z) * z2)) / 2. -
+                   (h1 * l * (-2. + z) * z2 * z) / 2. + (dh1 * l * l * (-4. + 3. * z) * z2 * z) / 12;
+            return nrg;
+        }
+        nrg += ((b0 - b1) * ((b0 - b1) * (dh0 - dh1) - 6. * (h0 + h1))) / 12.;
+    }
+    const double h0 = Hd[np - 1], dh0 = Sd[np - 1], b0 = Bd[np - 1];
+    nrg += ((b - b0) * (b * dh0 - b0 * dh0 + 2 * h0)) / 2.;
+    return nrg;
+}
+
+__global__ void __launch_bounds__(256)
+k_label_integrals(int ne, const int4 *__restrict__ tri, const double2 *__restrict__ xy, const double *__restrict__ V, double cscale,
+                  const double *__restrict__ magdir_elem, const double *__restrict__ bhB, const double *__restrict__ bhH,
+                  const double *__restrict__ bhS, IntegralLabels T, double *part /* [gridDim][2][n] */, int *unsupported)
+{
+    __shared__ double sm[33];
+    double accE[INTEGRAL_MAX_LABELS], accA[INTEGRAL_MAX_LABELS];
+#pragma unroll
+    for (int l = 0; l < INTEGRAL_MAX_LABELS; l++) { accE[l] = 0.0; accA[l] = 0.0; }
+    const double muo = 4.e-7 * XB_PI;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += gridDim.x * blockDim.x)
+    {
+        const int4 t = tri[e];
+        const int lb = t.w;
+        if (lb < 0 || lb >= T.n) continue;
+        const xfemm_integral_label &M = T.l[lb];
+        const double2 p0 = xy[t.x], p1 = xy[t.y], p2 = xy[t.z];
+        const double b0 = p1.y - p2.y, b1 = p2.y - p0.y, b2 = p0.y - p1.y;
+        const double c0 = p2.x - p1.x, c1 = p0.x - p2.x, c2 = p1.x - p0.x;
+        const double da = b0 * c1 - b1 * c0;         // cm^2 (twice the area)
+        const double a = fabs(da) * 0.5e-4;          // m^2
+        const double A0 = cscale * V[t.x], A1 = cscale * V[t.y], A2 = cscale * V[t.z];
+        const double B1 = (A0 * c0 + A1 * c1 + A2 * c2) / (da * 0.01);
+        const double B2 = -(A0 * b0 + A1 * b1 + A2 * b2) / (da * 0.01);
+        double w = 0.0;
+        if (M.lamtype > 2) { atomicExch(unsupported, 1); }
+        else if (M.H_c != 0.0)
+        {
+            if (M.bh_points != 0) atomicExch(unsupported, 2);
+            else
+            {
+                // second-quadrant representation of a linear permanent magnet (fpproc.cpp:3786-3800)
+                const double dir = (magdir_elem ? magdir_elem[e] : M.magdir) * XB_PI / 180.;
+                const double H1 = B1 / (M.mu_x * muo) - M.H_c * cos(dir), H2 = B2 / (M.mu_y * muo) - M.H_c * sin(dir);
+                w = 0.5 * muo * (M.mu_x * H1 * H1 + M.mu_y * H2 * H2);
+            }
+        }
+        else if (M.bh_points == 0)
+        {
+            // CMMaterialProp::DoEnergy, linear branch, literally (CMaterialProp.cpp:606-632; types 1 and 2 use b1 twice)
+            double h1 = 0, h2 = 0;
+            if (M.lamtype == 0) { h1 = B1 / ((1. + M.lamfill * (M.mu_x - 1.)) * muo); h2 = B2 / ((1. + M.lamfill * (M.mu_y - 1.)) * muo); }
+            if (M.lamtype == 1) { h1 = B1 / ((1. + M.lamfill * (M.mu_x - 1.)) * muo); h2 = B1 * (M.lamfill / (M.mu_y * muo) + (1. - M.lamfill) / muo); }
+            if (M.lamtype == 2) { h2 = B1 / ((1. + M.lamfill * (M.mu_y - 1.)) * muo); h1 = B1 * (M.lamfill / (M.mu_x * muo) + (1. - M.lamfill) / muo); }
+            w = (h1 * B1 + h2 * B2) / 2.;
+        }
+        else
+        {
+            const double *Bd = bhB + M.bh_offset, *Hd = bhH + M.bh_offset, *Sd = bhS + M.bh_offset;
+            if (M.lamtype == 0) w = bh_energy(sqrt(B1 * B1 + B2 * B2), M.bh_points, Bd, Hd, Sd);
+            if (M.lamtype == 1)
+            {
+                const double biron = sqrt((B1 / M.lamfill) * (B1 / M.lamfill) + B2 * B2), bair = B2;
+                w = M.lamfill * bh_energy(biron, M.bh_points, Bd, Hd, Sd) + (1 - M.lamfill) * bair * bair / (2. * muo);
+            }
+            if (M.lamtype == 2)
+            {
+                const double biron = sqrt((B2 / M.lamfill) * (B2 / M.lamfill) + B1 * B1), bair = B1;
+                w = M.lamfill * bh_energy(biron, M.bh_points, Bd, Hd, Sd) + (1 - M.lamfill) * bair * bair / (2. * muo);
+            }
+        }
+        const double mA = a * (A0 + A1 + A2) / 3.;
+        // the label index is data: select the accumulator without dynamic indexing of the register arrays
+#pragma unroll
+        for (int l = 0; l < INTEGRAL_MAX_LABELS; l++)
+            if (l == lb) { accE[l] += a * w; accA[l] += mA; }
+    }
+    for (int l = 0; l < T.n; l++)
+    {
+        double ve = 0.0, va = 0.0;
+#pragma unroll
+        for (int q = 0; q < INTEGRAL_MAX_LABELS; q++) if (q == l) { ve = accE[q]; va = accA[q]; }
+        ve = block_sum(ve, sm);
+        va = block_sum(va, sm);
+        if (threadIdx.x == 0) { part[((size_t)blockIdx.x * 2 + 0) * T.n + l] = ve; part[((size_t)blockIdx.x * 2 + 1) * T.n + l] = va; }
+    }
+}
+__global__ void k_label_integrals_final(int nblk, int n2, const double *__restrict__ part, double *out)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x; // one thread per output, blocks added in order: deterministic
+    if (q >= n2) return;
+    double s = 0.0;
+    for (int b = 0; b < nblk; b++) s += part[(size_t)b * n2 + q];
+    out[q] = s;
+}
+
 __global__ void k_point_sources(int np, const int *__restrict__ node, const double *__restrict__ val, double *b)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -761,6 +886,46 @@ int xfemm_mag_gap_torque(xfemm_mag *m, int cell0, int ncells, double inner_shift
     XB_CUDA(cudaGetLastError());
     *torque = h[0];
     if (br_bt) std::copy(h.begin() + 1, h.end(), br_bt);
+    return XFEMM_OK;
+}
+
+int xfemm_mag_label_integrals(xfemm_mag *m, int n_labels, const xfemm_integral_label *labels, double *energy_area, double *a_area)
+{
+    XB_ARG(m && labels && energy_area && a_area, "null pointer");
+    XB_ARG(!m->axisymmetric, "block integrals on the device are provided for planar problems (axisymmetric: write the .ans and use the post-processor)");
+    XB_ARG(n_labels >= 1 && n_labels <= xb::INTEGRAL_MAX_LABELS, "between 1 and 32 block labels");
+    xfemm_linprob *L = m->lin;
+    cudaStream_t st = L->stream;
+    xb::IntegralLabels T;
+    T.n = n_labels;
+    for (int l = 0; l < n_labels; l++) T.l[l] = labels[l];
+    const int nblk = std::max(1, std::min((m->n_elems + 255) / 256, L->num_sms * 4));
+    xb::DevBuf<double> part, out;
+    xb::DevBuf<int> flag;
+    XB_CUDA(part.alloc((size_t)nblk * 2 * n_labels));
+    XB_CUDA(out.alloc((size_t)2 * n_labels));
+    XB_CUDA(flag.alloc(1));
+    XB_CUDA(flag.zero(st));
+    const double PIc = 3.141592653589793238462643383;
+    ++xb::g_launch;
+    xb::k_label_integrals<<<nblk, 256, 0, st>>>(m->n_elems, (const int4 *)m->tri.p, (const double2 *)m->xy.p, L->V.p, PIc * 4.e-05,
+                                                m->magdir.n ? m->magdir.p : nullptr, m->bhB.p, m->bhH.p, m->bhS.p, T, part.p, flag.p);
+    ++xb::g_launch;
+    xb::k_label_integrals_final<<<1, 64, 0, st>>>(nblk, 2 * n_labels, part.p, out.p);
+    std::vector<double> h((size_t)2 * n_labels);
+    int unsupported = 0;
+    xb::g_d2h_bytes += (long long)h.size() * 8 + 4;
+    XB_CUDA(cudaMemcpyAsync(h.data(), out.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    XB_CUDA(cudaMemcpyAsync(&unsupported, flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    XB_CUDA(cudaStreamSynchronize(st));
+    XB_CUDA(cudaGetLastError());
+    if (unsupported)
+    {
+        xb::set_error(unsupported == 1 ? "stored energy of wound regions (LamType > 2) is not evaluated on the device"
+                                       : "stored energy of non-linear permanent magnets is not evaluated on the device");
+        return XFEMM_ERR_ARG;
+    }
+    for (int l = 0; l < n_labels; l++) { energy_area[l] = h[l]; a_area[l] = h[(size_t)n_labels + l]; }
     return XFEMM_OK;
 }
 

@@ -129,6 +129,30 @@ int xfemm_fsolver_gap_torque(xfemm_fsolver *s, int age_index, double *torque)
     return XFEMM_OK;
 }
 
+int xfemm_fsolver_stored_energy(xfemm_fsolver *s, double *joules)
+{
+    if (!s || !joules) return XFEMM_ERR_ARG;
+    if (!s->S.storedEnergy(*joules))
+    {
+        std::string prev = xfemm_last_error();
+        xb::set_error("stored energy failed (%s)", prev.c_str());
+        return XFEMM_ERR_ARG;
+    }
+    return XFEMM_OK;
+}
+
+int xfemm_fsolver_flux_linkage(xfemm_fsolver *s, int circuit, double *webers)
+{
+    if (!s || !webers) return XFEMM_ERR_ARG;
+    if (!s->S.fluxLinkage(circuit, *webers))
+    {
+        std::string prev = xfemm_last_error();
+        xb::set_error("flux linkage failed (%s)", prev.c_str());
+        return XFEMM_ERR_ARG;
+    }
+    return XFEMM_OK;
+}
+
 int xfemm_fsolver_resolve(xfemm_fsolver *s)
 {
     if (!s || !s->L) { xb::set_error("no resident static problem (call xfemm_fsolver_solve first)"); return XFEMM_ERR_ARG; }
@@ -188,8 +212,16 @@ xfemm_linprob *xfemm_fsolver_linprob(xfemm_fsolver *s) { return (s && s->L) ? s-
 
 long long xfemm_fsolver_nnz(xfemm_fsolver *s)
 {
+    if (s && s->Lc && s->Lc->device()) return xfemm_clinprob_nnz(s->Lc->device());
     if (!s || !s->L || !s->L->device()) return 0;
     return xfemm_linprob_nnz(s->L->device());
+}
+
+int xfemm_fsolver_amg_levels(xfemm_fsolver *s, int max_levels, int *n_rows, long long *nnz)
+{
+    if (s && s->L && s->L->device()) return xfemm_linprob_amg_levels(s->L->device(), max_levels, n_rows, nnz);
+    if (s && s->Lc && s->Lc->device()) return xfemm_clinprob_amg_levels(s->Lc->device(), max_levels, n_rows, nnz);
+    return 0;
 }
 
 int xfemm_fsolver_get_nodes(xfemm_fsolver *s, double *xy, int *bc)

@@ -1,4 +1,6 @@
 // CBigComplexLinProb facade (reference: cfemm/libfemm/cspars.cpp:119-1081), see cspars.h.
+#include <cmath>
+#include <vector>
 #include "cspars.h"
 #include "../../include/xfemm_b200.h"
 #include <algorithm>
@@ -326,6 +328,92 @@ void CBigComplexLinProb::MultConjA(CComplex *X, CComplex *Y, int k)
     if (k != 0 && k != 2) { fprintf(stderr, "xfemm_b200: MultConjA is provided for k = 0 and 2 (the ones the solvers use)\n"); return; }
     if (xfemm_clinprob_mult(dev, k, 1, (const double *)X, (double *)Y) != XFEMM_OK)
         fprintf(stderr, "xfemm_b200: MultConjA failed: %s\n", xfemm_last_error());
+}
+
+// ---- stand-alone pieces of the reference's public surface ------------------------------------------------
+void CBigComplexLinProb::MultPC(CComplex *X, CComplex *Y)
+{
+    // y = D^-1 x (see the header for why this is not the reference's SSOR sweep)
+    for (int i = 0; i < n; i++)
+    {
+        const CComplex d = Get(i, i);
+        Y[i] = (d.re != 0 || d.im != 0) ? X[i] / d : X[i];
+    }
+}
+
+void CBigComplexLinProb::MultAPPA(CComplex *X, CComplex *Y)
+{
+    // Y = conj( A P conj( P A X ) ): the Hermitian positive operator PCGSQStart iterates on (cspars.cpp:406-415)
+    MultA(X, Z);
+    MultPC(Z, Y);
+    for (int i = 0; i < n; i++) Y[i] = Y[i].Conj();
+    MultPC(Y, Z);
+    MultA(Z, Y);
+    for (int i = 0; i < n; i++) Y[i] = Y[i].Conj();
+}
+
+int CBigComplexLinProb::PCGSQStart()
+{
+    // three conjugate-gradient steps on the squared problem to seed V (cspars.cpp:764-819)
+    for (int i = 0; i < n; i++)
+    {
+        const CComplex d = Get(i, i);
+        if (d.re == 0 && d.im == 0) { fprintf(stderr, "singular flag tripped."); return 0; }
+    }
+    // right-hand side of the squared problem: conj( A P conj( P b ) )
+    MultPC(b, Z);
+    for (int i = 0; i < n; i++) Z[i] = Z[i].Conj();
+    MultPC(Z, P);
+    MultA(P, Z);
+    for (int i = 0; i < n; i++) { R[i] = Z[i].Conj(); V[i] = 0; P[i] = R[i]; }
+    CComplex res = ConjDot(R, R);
+    for (int k = 0; k < 3; k++)
+    {
+        if (res.re == 0 && res.im == 0) break;
+        MultAPPA(P, U);
+        const CComplex del = res / ConjDot(P, U);
+        for (int i = 0; i < n; i++) { V[i] += del * P[i]; R[i] -= del * U[i]; }
+        const CComplex resNew = ConjDot(R, R), rho = resNew / res;
+        res = resNew;
+        for (int i = 0; i < n; i++) P[i] = R[i] + rho * P[i];
+    }
+    return 1;
+}
+
+int CBigComplexLinProb::BiCGSTAB(int flag)
+{
+    // right-preconditioned BiCGSTAB on the full Newton operator (MultA(.,.,-1)), cspars.cpp:897-980
+    auto norm2 = [&](const CComplex *x) { double s = 0; for (int i = 0; i < n; i++) s += x[i].re * x[i].re + x[i].im * x[i].im; return sqrt(s); };
+    std::vector<CComplex> P2(n), Z2(n), R2(n), T(n);
+    if (!flag) for (int i = 0; i < n; i++) V[i] = 0;
+    MultA(V, R, -1);
+    for (int i = 0; i < n; i++) { R[i] = b[i] - R[i]; R2[i] = R[i]; }
+    const double normb = norm2(b);
+    if (normb == 0) return 1;
+    CComplex alf = 0, om = 0, rho1 = 0, rho2 = 0;
+    double er = norm2(R) / normb;
+    for (int k = 0; k < 1000000 && er >= Precision; k++)
+    {
+        rho1 = ConjDot(R2.data(), R).re;
+        if (k == 0) for (int i = 0; i < n; i++) P[i] = R[i];
+        else
+        {
+            const CComplex bta = (rho1 / rho2) * alf / om;
+            for (int i = 0; i < n; i++) P[i] = R[i] + bta * (P[i] - om * U[i]);
+        }
+        MultPC(P, P2.data());
+        MultA(P2.data(), U, -1);
+        alf = rho1 / ConjDot(R2.data(), U).re;
+        for (int i = 0; i < n; i++) Z[i] = R[i] - alf * U[i];
+        MultPC(Z, Z2.data());
+        MultA(Z2.data(), T.data(), -1);
+        om = ConjDot(T.data(), Z).re / ConjDot(T.data(), T.data()).re;
+        for (int i = 0; i < n; i++) { V[i] = V[i] + alf * P2[i] + om * Z2[i]; R[i] = Z[i] - om * T[i]; }
+        rho2 = rho1;
+        er = norm2(R) / normb;
+        if (!(er == er)) return 0;
+    }
+    return er < Precision ? 1 : 0;
 }
 
 int CBigComplexLinProb::solve(int flag, bool sqStart)

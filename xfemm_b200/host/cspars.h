@@ -50,6 +50,15 @@ public:
     int PBCGSolveMod(int flag, bool verbose = false); // dispatcher: KludgeSolve when bNewton
     int PBCGSolve(int flag);                          // COCG on M from V (flag != 0) or from zero
     int KludgeSolve(int flag);
+    // The remaining public routines of the reference class (cspars.h:37-95), for callers that drive the iteration
+    // themselves.  MultPC applies THIS backend's stand-alone preconditioner — the diagonal (Jacobi) — in place of
+    // the reference's serial SSOR sweep (cspars.cpp:439-480), which has no GPU-parallel equivalent; the solvers
+    // above use the multigrid cycle inside their persistent kernel.  MultAPPA, PCGSQStart and BiCGSTAB (dead code in
+    // the reference: its only call is commented out, cspars.cpp:1066) are built on MultA / MultPC exactly as there.
+    void MultPC(CComplex *X, CComplex *Y);
+    void MultAPPA(CComplex *X, CComplex *Y);
+    int PCGSQStart();
+    int BiCGSTAB(int flag);
 
     int precond, lastIterations;
     double lastSolveMs, lastRelRes;

@@ -266,6 +266,7 @@ public:
     {
         std::vector<int> dirNodes, pbcI, pbcJ, pbcT;
         std::vector<double> dirFirst, dirLast, labelJsrc;
+        std::vector<int> labelBhOffset, labelBhPoints; // B-H table of each label in the device arrays
         bool linear = true, ready = false, ageDirty = false;
         // sweeps on a linear problem: the position-independent part (elements, sides, sources, all boundary
         // conditions) is assembled once and kept on the device; a position restores it and adds its air-gap blocks
@@ -280,6 +281,11 @@ public:
     // copies V and A of the last static solve from the device into L.V / L.b if they were left there; false on a CUDA error
     bool fetchDeviceSolution(CBigLinProb &L);
     bool gapTorque(int ageIndex, double &torque); // from the resident solution, = fpproc's gap integral 0
+    // from the resident solution (planar magnetostatics): stored energy of all blocks [J] = fpproc's block integral 2 over
+    // every block; flux linkage [Wb] of circuit `circ` of the .fem file (a circuit that carries a current)
+    bool storedEnergy(double &joules);
+    bool fluxLinkage(int circ, double &webers);
+    bool labelIntegrals(std::vector<double> &energyArea, std::vector<double> &aArea);
     std::thread prebuild;        // host thread building the solver structure while the first assembly runs
     void joinPrebuild() { if (prebuild.joinable()) prebuild.join(); }
     int localityOrder;           // 1/0: order the solver's rows along a Z-curve through the nodes; -1 = when the problem is re-solved

@@ -685,7 +685,14 @@ int FSolver::staticSolve(CBigLinProb &L, bool axi)
     plan.dirNodes = dirNodes; plan.dirFirst = dirFirst; plan.dirLast = dirLast;
     plan.pbcI = pbcI; plan.pbcJ = pbcJ; plan.pbcT = pbcT;
     plan.labelJsrc.resize(NumBlockLabels);
-    for (int l = 0; l < NumBlockLabels; l++) plan.labelJsrc[l] = labels[l].Jsrc;
+    plan.labelBhOffset.resize(NumBlockLabels);
+    plan.labelBhPoints.resize(NumBlockLabels);
+    for (int l = 0; l < NumBlockLabels; l++)
+    {
+        plan.labelJsrc[l] = labels[l].Jsrc;
+        plan.labelBhOffset[l] = labels[l].bh_offset;
+        plan.labelBhPoints[l] = labels[l].bh_points;
+    }
     plan.linear = LinearFlag;
     plan.ready = true;
     // The boundary-condition operators are linear in the matrix and only touch entries in the rows/columns of
@@ -936,6 +943,68 @@ bool FSolver::gapTorque(int ageIndex, double &torque)
         WarnMessage(xfemm_last_error());
         return false;
     }
+    return true;
+}
+
+// Block integrals from the resident solution: what the reference obtains from fpproc after writing
+// and re-reading the .ans file.  cfemm/fpproc/fpproc.cpp:3762-3830 (stored energy), 5157-5196 (flux linkage).
+bool FSolver::labelIntegrals(std::vector<double> &energyArea, std::vector<double> &aArea)
+{
+    if (!magdev || !plan.ready || Frequency != 0 || ProblemType != PLANAR)
+    {
+        WarnMessage("xfemm_b200: block integrals on the device need a solved planar magnetostatic problem\n");
+        return false;
+    }
+    std::vector<xfemm_integral_label> T(NumBlockLabels);
+    for (int l = 0; l < NumBlockLabels; l++)
+    {
+        const CMSolverMaterialProp &M = blockproplist[labellist[l].BlockType];
+        T[l].mu_x = M.mu_x; T[l].mu_y = M.mu_y; T[l].lamfill = M.LamFill; T[l].H_c = M.H_c; T[l].magdir = labellist[l].MagDir;
+        T[l].lamtype = M.LamType; T[l].bh_offset = plan.labelBhOffset[l]; T[l].bh_points = plan.labelBhPoints[l]; T[l].pad_ = 0;
+    }
+    energyArea.assign(NumBlockLabels, 0.);
+    aArea.assign(NumBlockLabels, 0.);
+    if (xfemm_mag_label_integrals(magdev, NumBlockLabels, T.data(), energyArea.data(), aArea.data()) != XFEMM_OK)
+    {
+        WarnMessage(xfemm_last_error());
+        return false;
+    }
+    return true;
+}
+
+bool FSolver::storedEnergy(double &joules)
+{
+    std::vector<double> e, a;
+    if (!labelIntegrals(e, a)) return false;
+    const double depth = (Depth == -1) ? 1. : Depth * LengthConvMeters[LengthUnits];
+    joules = 0;
+    for (double v : e) joules += v * depth;
+    return true;
+}
+
+bool FSolver::fluxLinkage(int circ, double &webers)
+{
+    // circuits of the .fem file; series circuits were expanded into one parallel circuit per label by
+    // LoadProblemFile (fsolver.cpp:278-317): OrigCirc leads back
+    if (circ < 0 || circ >= NumCircPropsOrig) { WarnMessage("xfemm_b200: no such circuit\n"); return false; }
+    const CComplex amps = circproplist[circ].Amps;
+    if (amps.re == 0 && amps.im == 0)
+    {
+        WarnMessage("xfemm_b200: the flux linkage of a circuit without current is not evaluated on the device\n");
+        return false;
+    }
+    std::vector<double> e, a;
+    if (!labelIntegrals(e, a)) return false;
+    const double depth = (Depth == -1) ? 1. : Depth * LengthConvMeters[LengthUnits];
+    double aj = 0;
+    for (int l = 0; l < NumBlockLabels; l++)
+    {
+        int c = labellist[l].InCircuit;
+        if (c < 0) continue;
+        if (c >= NumCircPropsOrig) c = circproplist[c].OrigCirc;
+        if (c == circ) aj += a[l] * plan.labelJsrc[l] * 1.e6 * depth; // MA/m^2 -> A/m^2
+    }
+    webers = aj / amps.re;
     return true;
 }
 
