@@ -93,3 +93,33 @@ def test_nonlinear_newton_matches_reference(name, tmp_path):
     mu = S.mu()
     refmu = ref["mu"][:, [0, 2]]
     assert np.abs(mu - refmu).max() <= 1e-4 * np.abs(refmu).max()
+
+
+def test_prevsoln_mesh_reuse(tmp_path):
+    """[PrevSoln] with [PrevType] = 0 (fsolver.cpp:224-239, 990-1081): the mesh comes out of an earlier .ans file, in its
+    solver numbering, LoadMesh and Cuthill are skipped.  The reference returns the identical field for the
+    TorqueBenchmark (checked with oracle/_ref/fsolver when this test was written); so must this backend."""
+    import re
+    base = stage_case("tb", tmp_path)
+    S = X.FSolver(base)
+    S.load_mesh(False)
+    S.renumber(False)
+    S.solve()
+    S.write()
+    A1 = S.solution()[1].copy()
+    S.close()
+    text = open(base + ".fem").read()
+    text2 = re.sub(r'\[PrevSoln\]\s*=\s*""', '[PrevSoln]    =  "%s.ans"' % base, text)
+    assert text2 != text
+    base2 = str(tmp_path / "tb_prev")
+    open(base2 + ".fem", "w").write(text2)
+    # no mesh files next to tb_prev.fem: the front end must not look for them
+    rc = X.fsolver_run(base2)
+    assert rc == 0
+    S2 = X.FSolver(base2)
+    S2.load_mesh(True)
+    S2.renumber(True)
+    S2.solve()
+    A2 = S2.solution()[1]
+    assert rel_l2(A2, A1) <= 1e-9
+    S2.close()

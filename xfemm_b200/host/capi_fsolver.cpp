@@ -76,6 +76,7 @@ int xfemm_fsolver_load_mesh(xfemm_fsolver *s, int delete_files)
 int xfemm_fsolver_renumber(xfemm_fsolver *s, int delete_files)
 {
     if (!s) return XFEMM_ERR_ARG;
+    if (s->S.meshLoadedFromPrevSolution) return XFEMM_OK; // the mesh of a [PrevSoln] file is in solver numbering already (fsolver.cpp:1224)
     if (!s->S.Cuthill(delete_files != 0)) { xb::set_error("problem renumbering node points"); return XFEMM_ERR_IO; }
     return XFEMM_OK;
 }

@@ -228,6 +228,10 @@ public:
 
     // ---- operations (same names, argument meaning and return conventions as the reference)
     bool LoadProblemFile();                        // fsolver.cpp:202-348
+    // [PrevSoln] with [PrevType] = 0: the mesh (nodes, elements, periodic pairs, air-gap tables) comes from an earlier
+    // .ans file in its solver numbering; LoadMesh and Cuthill are then no-ops (fsolver.cpp:224-239, 357, 990-1081)
+    bool loadPreviousSolution(bool loadAprev);
+    bool meshLoadedFromPrevSolution = false;
     LoadMeshErr LoadMesh(bool deleteFiles = true); // fsolver.cpp:350-718
     int Cuthill(bool deleteFiles = true);          // cuthill.cpp:94-391
     int SortElements();                            // cuthill.cpp:40-85

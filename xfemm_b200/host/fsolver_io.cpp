@@ -383,12 +383,19 @@ bool FSolver::LoadProblemFile()
     Relax = 1.;
     std::string femFile = PathName + ".fem";
     if (!parseFem(femFile)) return false;
+    meshLoadedFromPrevSolution = false;
     if (!previousSolutionFile.empty())
     {
-        // [PrevSoln] (incremental / frozen permeability, mesh reuse) is a host-side feature of the
-        // reference (fsolver.cpp:224-239, 990-1081) that is outside the accelerated path.
-        WarnMessage("xfemm_b200: [PrevSoln] problems are not supported by the B200 backend\n");
-        return false;
+        // [PrevType] 1 / 2 (incremental / frozen permeability) do not run in the reference itself (DESIGN.md §2, row b)
+        if (PrevType != 0)
+        {
+            WarnMessage("xfemm_b200: [PrevSoln] with [PrevType] 1 or 2 (incremental / frozen permeability) is not supported\n");
+            return false;
+        }
+        // mesh reuse.  The reference returns from here without the B-H set-up and the circuit expansion below
+        // (fsolver.cpp:237), which leaves a problem with B-H materials or series circuits unusable there; both are
+        // done here as for any other problem.
+        if (!loadPreviousSolution(false)) return false;
     }
     // B-H spline set-up on the host (fsolver.cpp:243-276)
     for (auto &prop : blockproplist)
@@ -538,8 +545,131 @@ static inline bool parse_double(const char *&p, double &v)
 }
 } // namespace
 
+// Mesh out of the [Solution] section of an earlier .ans file (reference: FSolver::loadPreviousSolution and the four
+// Load...FromSolution routines, fsolver.cpp:720-1081).  Line-oriented like the reference's fgets/sscanf: a static
+// .ans has 4 numbers per element line, a harmonic one 8; what a line does not hold keeps the element's default —
+// e[] = {0,0,0}, i.e. boundary property 0 on every side, exactly as the reference's CElement() leaves it.
+bool FSolver::loadPreviousSolution(bool loadAprev)
+{
+    if (previousSolutionFile.empty()) return false;
+    FILE *fp = fopen(previousSolutionFile.c_str(), "rt");
+    if (!fp)
+    {
+        WarnMessage(("Failed to open the specified previous solution file, file path was:\n" + previousSolutionFile + "\n").c_str());
+        return false;
+    }
+    char s[1024], q[256];
+    bool hasSolution = false;
+    while (fgets(s, sizeof s, fp))
+    {
+        q[0] = 0;
+        sscanf(s, "%255s", q);
+        std::string key(q);
+        for (auto &ch : key) ch = (char)tolower((unsigned char)ch);
+        if (key.compare(0, 11, "[frequency]") == 0)
+        {
+            double prevFreq = 0;
+            const char *eq = strchr(s, '=');
+            if (eq) sscanf(eq + 1, "%lf", &prevFreq);
+            if (prevFreq != 0)
+            {
+                fclose(fp);
+                WarnMessage(("Previous solution file (" + previousSolutionFile + ") appears to be an AC problem, only DC previous solutions are presently supported\n").c_str());
+                return false;
+            }
+        }
+        if (key.compare(0, 10, "[solution]") == 0) { hasSolution = true; break; }
+    }
+    if (!hasSolution)
+    {
+        fclose(fp);
+        WarnMessage(("No solution was found in previous solution file, file path was:\n" + previousSolutionFile + "\n").c_str());
+        return false;
+    }
+    auto line = [&]() { return fgets(s, sizeof s, fp) != nullptr; };
+    const double toCm = 100. * LengthConvMeters[LengthUnits];
+    // nodes: x y A marker
+    NumNodes = 0;
+    if (line()) sscanf(s, "%i", &NumNodes);
+    Aprev.clear();
+    meshnode.assign((size_t)std::max(0, NumNodes), CNode());
+    for (int i = 0; i < NumNodes && line(); i++)
+    {
+        double a = 0;
+        CNode &nd = meshnode[i];
+        sscanf(s, "%lf %lf %lf %i", &nd.x, &nd.y, &a, &nd.BoundaryMarker);
+        nd.x *= toCm; nd.y *= toCm;
+        if (loadAprev) Aprev.push_back(a);
+    }
+    // elements
+    NumEls = 0;
+    if (line()) sscanf(s, "%i", &NumEls);
+    meshele.assign((size_t)std::max(0, NumEls), femmsolver::CMElement());
+    for (int i = 0; i < NumEls && line(); i++)
+    {
+        femmsolver::CMElement &e = meshele[i];
+        e.e[0] = e.e[1] = e.e[2] = 0; // the reference's constructor default, kept when the line has 4 fields only
+        sscanf(s, "%i %i %i %i %i %i %i %lf", &e.p[0], &e.p[1], &e.p[2], &e.lbl, &e.e[0], &e.e[1], &e.e[2], &e.Jprev);
+        if (e.lbl < 0 || e.lbl >= (int)labellist.size()) { fclose(fp); WarnMessage("previous solution: element with an unknown block label\n"); return false; }
+        e.blk = labellist[e.lbl].BlockType;
+    }
+    // per-label circuit results: skipped
+    int numLabels = 0;
+    if (line()) sscanf(s, "%i", &numLabels);
+    for (int i = 0; i < numLabels; i++) line();
+    // periodic pairs
+    NumPBCs = 0;
+    pbclist.clear();
+    if (line())
+    {
+        sscanf(s, "%i", &NumPBCs);
+        for (int i = 0; i < NumPBCs && line(); i++)
+        {
+            CCommonPoint c;
+            sscanf(s, "%i %i %i", &c.x, &c.y, &c.t);
+            pbclist.push_back(c);
+        }
+    }
+    // air-gap elements
+    NumAirGapElems = 0;
+    agelist.clear();
+    if (line()) sscanf(s, "%i", &NumAirGapElems);
+    for (int i = 0; i < NumAirGapElems; i++)
+    {
+        femmsolver::CAirGapElement age;
+        if (!line()) break;
+        age.BdryName = s;
+        if (!line()) break;
+        sscanf(s, "%i %lf %lf %lf %lf %lf %lf %lf %i %lf %lf", &age.BdryFormat, &age.InnerAngle, &age.OuterAngle, &age.ri, &age.ro,
+               &age.totalArcLength, &age.agc.re, &age.agc.im, &age.totalArcElements, &age.InnerShift, &age.OuterShift);
+        for (int k = 0; k <= age.totalArcElements && line(); k++)
+        {
+            CQuadPoint qp = {0, 0, 0, 0, 0, 0, 0, 0};
+            sscanf(s, "%i %lf %i %lf %i %lf %i %lf", &qp.n0, &qp.w0, &qp.n1, &qp.w1, &qp.n2, &qp.w2, &qp.n3, &qp.w3);
+            if (qp.n0 < 0 || qp.n1 < 0 || qp.n2 < 0 || qp.n3 < 0)
+            {
+                fclose(fp);
+                WarnMessage("An error occured while reading pbc file, quadNode has negative node number.\n");
+                return false;
+            }
+            age.quadNode.push_back(qp);
+        }
+        agelist.push_back(age);
+    }
+    fclose(fp);
+    // the file is in solver numbering already: no renumbering, and no bandwidth was computed (the reference creates
+    // its linear problem with the constructor's BandWidth = 0, which its SetValue reads as "scan every row")
+    BandWidth = 0;
+    cmPermutation.resize((size_t)NumNodes);
+    for (int i = 0; i < NumNodes; i++) cmPermutation[i] = i;
+    edgeList.clear();
+    meshLoadedFromPrevSolution = true;
+    return true;
+}
+
 LoadMeshErr FSolver::LoadMesh(bool deleteFiles)
 {
+    if (meshLoadedFromPrevSolution) return NOERROR; // fsolver.cpp:357
     TextFile F;
     int k = 0, j = 0;
     const bool timing = getenv("XFEMM_TIMING") != nullptr;

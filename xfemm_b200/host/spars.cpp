@@ -136,6 +136,41 @@ double CBigLinProb::Get(int p, int q)
 
 void CBigLinProb::AddTo(double v, int p, int q) { Put(Get(p, q) + v, p, q); }
 
+CEntry **CBigLinProb::Entries()
+{
+    if (!M || n <= 0) return M;
+    entryPool.clear();
+    std::vector<size_t> first((size_t)n + 1, 0);
+    if (deviceAssembled)
+    {
+        fetchDeviceValues();
+        ensurePattern();
+        if (csrRowptr.empty()) return M;
+        for (int i = 0; i < n; i++)
+        {
+            first[i] = entryPool.size();
+            for (int s = csrRowptr[i]; s < csrRowptr[i + 1]; s++)
+                if (csrCol[s] >= i) { CEntry e; e.c = csrCol[s]; e.x = csrVals[s]; entryPool.push_back(e); }
+        }
+    }
+    else
+    {
+        ensureRows();
+        for (int i = 0; i < n; i++)
+        {
+            first[i] = entryPool.size();
+            for (const Ent &r : rows[i]) { CEntry e; e.c = r.c; e.x = r.x; entryPool.push_back(e); }
+        }
+    }
+    first[n] = entryPool.size();
+    for (int i = 0; i < n; i++)
+    {
+        M[i] = first[i + 1] > first[i] ? &entryPool[first[i]] : nullptr;
+        for (size_t k = first[i]; k + 1 < first[i + 1]; k++) entryPool[k].next = &entryPool[k + 1];
+    }
+    return M;
+}
+
 double CBigLinProb::Dot(double *X, double *Y)
 {
     double z = 0;

@@ -34,7 +34,8 @@ public:
     double *U;
     double *Z;
     double *b;  // RHS of linear equation
-    CEntry **M; // kept for source compatibility; not populated (entries live in `rows`)
+    CEntry **M; // row lists of the reference (upper triangle, ascending columns, diagonal first): filled ON DEMAND by
+                // Entries() — the solver itself keeps the matrix on the device; walking M without that call finds nulls
     int n;
     int bdw;
     double Precision;
@@ -56,6 +57,11 @@ public:
     void Wipe();
     double Dot(double *X, double *Y);
     void ComputeBandwidth();
+    // Materialises the reference's storage — M[i] = singly linked list of the stored entries of row i, columns >= i
+    // ascending, first node the diagonal (spars.h:25-35, spars.cpp:95-99) — from the current matrix, wherever it lives
+    // (host rows of a Put()-assembled problem, or the device values of a device-assembled one), and returns M.  For
+    // callers that walk the lists (white-box harnesses); the lists are a snapshot, later Put()s do not update them.
+    CEntry **Entries();
 
     // ---- B200 backend
     int precond;       // XFEMM_PRECOND_*, default from env XFEMM_PRECOND or multicolour SSOR
@@ -78,6 +84,7 @@ private:
     xfemm_linprob *dev;
     std::vector<int> csrRowptr, csrCol;
     std::vector<double> csrVals;
+    std::vector<CEntry> entryPool; // nodes of the lists handed out by Entries()
     double *findEntry(int p, int q);
     bool syncToDevice();
     void periodicImpl(int i, int j, double sgn);
