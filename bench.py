@@ -109,6 +109,7 @@ class ClockSampler(threading.Thread):
         self.samples = []
         self.reasons = set()
         self.stop_flag = False
+        self.active = True   # samples are kept only while set (start the thread early: NVML initialisation takes ~0.1 s)
         self.max_mhz = None
         self.source = None
 
@@ -127,6 +128,9 @@ class ClockSampler(threading.Thread):
         self.max_mhz = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
         self.source = "nvml"
         while not self.stop_flag:
+            if not self.active:
+                time.sleep(0.001)
+                continue
             self.samples.append(float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)))
             try:
                 mask = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
@@ -256,15 +260,31 @@ def pcg_bytes_per_iteration(X, S, precond, nnz, n):
     return krylov + cyc, levels
 
 
+def kernel_source_sha16():
+    """Hash of the CUDA sources: an ncu capture is only quoted for the kernels it was taken from."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "xfemm_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh")):
+            h.update(f.encode())
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def ncu_traffic(precond, iterations):
     """DRAM bytes (read + write) of one launch of the persistent kernel: the per-iteration figure of the committed
-    ncu --set full capture of this command (profiles/r01_ncu_traffic.json: dram bytes of the captured launch /
-    its iteration count) times the iterations of the timed launches; None if there is no capture for it."""
+    ncu --set full capture of this command (profiles/r02_ncu_traffic.json: dram bytes of the captured launch / its
+    iteration count) times the iterations of the timed launches.  (None, why) when there is no capture of THESE
+    sources: the file records the hash of xfemm_b200/csrc it was taken from."""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))[precond]
-        return d["dram_bytes_per_launch"] / d["iterations"] * iterations
-    except Exception:
-        return None
+        f = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))
+        d = f[precond]
+        if f.get("source_sha16") != kernel_source_sha16():
+            return None, "the committed ncu capture (profiles/r02_ncu_traffic.json) is of an earlier version of the kernels: not quoted"
+        return d["dram_bytes_per_launch"] / d["iterations"] * iterations, "profiles/r02_ncu_traffic.json"
+    except Exception as ex:
+        return None, f"no capture: {ex}"
 
 
 def measured_hbm_peak():
@@ -689,14 +709,16 @@ def main():
     # headline steps: the whole per-problem path every time (assembly of all elements, Dirichlet, periodic pairs, solve);
     # the library's sweep mode that keeps the position-independent part on the device is timed separately below
     S.set_option("cache_static_part", 0)
+    sampler = ClockSampler(local_rank)
+    sampler.active = False
+    if rank == 0:
+        sampler.start()
     for i in range(args.warmup):
         S.set_rotor_angle(position(i))
         S.resolve()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync()
+    sampler.active = True
     t0 = time.perf_counter()
     ev0.record()
     launches0 = int(X.lib().xfemm_launch_count())
@@ -745,6 +767,18 @@ def main():
         cs = S.stats()
         torque_only["cold_start"] = {"pcg_ms": sum(cs["solve_ms"]), "iterations": sum(cs["iters"]), "relres": cs["relres"]}
         S.set_option("warm_resolve", 1)
+    # the deterministic (gather-based) assembly next to the default one (FP64 atomics), same resident problem
+    det_asm = None
+    if rank == 0 and world == 1:
+        S.set_option("deterministic_assembly", 1)
+        S.resolve()  # builds the contributor lists (once per mesh)
+        tms = []
+        for i in range(3):
+            S.resolve()
+            tms.append(sum(S.stats()["assemble_ms"]))
+        S.set_option("deterministic_assembly", 0)
+        det_asm = {"ms": min(tms), "atomic_ms": min(asm_ms), "elements_per_s": c["n_elems"] / (1e-3 * min(tms)),
+                   "note": "assembly + boundary conditions of one step; deterministic = element contributions gathered per CSR slot in a fixed order"}
     # the other GPU-parallel preconditioners on the same resident problem, for the record
     variant = None
     if rank == 0 and world == 1 and not args.no_variants:
@@ -768,18 +802,68 @@ def main():
         t = torch.tensor([elapsed], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed = float(t.item())
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return 0
+    # ---- config 5b next to the sweep: the SAME mesh solved ONCE by all N GPUs together (row-partitioned multigrid PCG
+    # over peer memory, csrc/dist_amg.cu).  An extra leg after the timed region; a watchdog keeps it from ever costing
+    # the headline line.  At this mesh size the solve is latency-bound and does not speed up with N — the strong-
+    # scaling records at 20 M nodes are under profiles/ (bench.py --partitioned --mesh-size 0.00057).
+    single_mesh = None
+    leg_done = threading.Event()
+    held = {"line": None}
+
+    def watchdog():
+        if not leg_done.wait(timeout=float(os.environ.get("XFEMM_BENCH_LEG_TIMEOUT", "240"))):
+            if rank == 0 and held["line"] is not None:
+                held["line"]["single_mesh_all_gpus"] = {"error": "the extra leg did not finish in time; skipped"}
+                print(json.dumps(held["line"]), flush=True)
+            os._exit(0)
+
+    def partitioned_leg():
+        from xfemm_b200.dist_amg import DistAmgPCG
+        P = X.FSolver(base)
+        P.set_option("assemble_only", 1)
+        P.set_option("precond", X.PRECOND_AMG)
+        P.set_option("locality_order", 1)
+        P.load_mesh(False)
+        P.renumber(False)
+        P.solve()
+        D = DistAmgPCG(P)
+        infos = [D.solve(1e-10) for _ in range(3)]
+        msl = torch.tensor([min(i["solve_ms"] for i in infos)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(msl, op=dist.ReduceOp.MAX)
+        Vn = float(np.linalg.norm(D.solution()))
+        out = {"what": "ONE problem of this mesh solved by all ranks together (strong scaling; extra leg, not in `value`)",
+               "n_gpus": world, "iterations": infos[-1]["iterations"], "solve_ms": float(msl.item()),
+               "ms_per_iter": float(msl.item()) / max(1, infos[-1]["iterations"]), "solution_norm": Vn, "plan_rank0": D.stats(),
+               "data_path": "peer stores + arrival counters over NVLink inside one persistent kernel per GPU; NCCL only for the host barriers",
+               "records_at_20M_nodes": "profiles/r02_bench_partitioned_20M_{1,4,8}gpu.json"}
+        D.close()
+        P.close()
+        return out
 
     problems = args.steps * world
+    if world > 1 and not os.environ.get("XFEMM_BENCH_NO_SINGLE_MESH"):
+        import numpy as np
+        S.close()  # frees the sweep handle's device memory first
+        if rank != 0:
+            threading.Thread(target=watchdog, daemon=True).start()
+            try:
+                partitioned_leg()
+            except Exception:
+                pass
+            leg_done.set()
+            dist.destroy_process_group()
+            return 0
+    elif rank != 0:
+        dist.destroy_process_group()
+        return 0
+
     value = elapsed / problems
     n = c["n_unknowns"]
     pcg_ms = sum(solve_ms) / len(solve_ms)
     its = sum(iters) / len(iters)
     achieved = bytes_iter * its / (pcg_ms * 1e-3) / 1e9 if pcg_ms > 0 else 0.0
     peak, peak_src = measured_hbm_peak()
+    traffic, traffic_src = ncu_traffic(args.precond, its) if args.mesh_size == 0.0018 else (None, "captured at mesh size 0.0018 only")
     line = {
         "metric": "fsolver_static2d_s_per_problem", "value": value, "unit": "s/problem", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": value * 1e3 * world, "higher_is_better": False,
@@ -798,18 +882,19 @@ def main():
         "assembly": {"ms": sum(asm_ms) / len(asm_ms), "elements_per_s": c["n_elems"] / (1e-3 * sum(asm_ms) / len(asm_ms))},
         "roofline": {"bound": "hbm", "kernel": "k_pcg<%s> (persistent PCG: SpMV + fused vector updates + preconditioner)" % args.precond,
                      "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": ncu_traffic(args.precond, its) if args.mesh_size == 0.0018 else None,
+                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                      "bytes_per_iter": bytes_iter,
                      "achieved_note": "algorithmic bytes per launch (bytes_per_iter x iterations) / CUDA-event launch duration; "
                                       "traffic = DRAM bytes of one launch from the committed ncu capture (profiles/)"},
         "e2e": {"value": e2e, "unit": "s/problem", "h2d_bytes_per_step": int(h2d.value), "d2h_bytes_per_step": int(d2h.value)},
         "variant": variant,
+        "assembly_deterministic": det_asm,
         "sweep_torque_only": torque_only,
         "host_setup_s": {"load_mesh": t_load, "cuthill": t_cm},
         "gpu_launches": launches,
         "clocks": sampler.summary(),
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # the CPU baseline is timed at N = 1 only
         try:
             info = run_reference(base, args.ref_iters, args.ref_pbc, total_ref_iters)
             line["cpu_baseline"] = {"value": info["s_per_problem"], "unit": "s/problem", "cores": 1, "kind": "reference",
@@ -817,7 +902,15 @@ def main():
         except Exception as ex:  # the line must still print
             line["cpu_baseline"] = {"value": None, "unit": "s/problem", "cores": 1, "kind": "reference",
                                     "sample": f"unavailable: {ex}"}
-    print(json.dumps(line))
+    if world > 1 and not os.environ.get("XFEMM_BENCH_NO_SINGLE_MESH"):
+        held["line"] = line
+        threading.Thread(target=watchdog, daemon=True).start()
+        try:
+            line["single_mesh_all_gpus"] = partitioned_leg()
+        except Exception as ex:
+            line["single_mesh_all_gpus"] = {"error": str(ex)[:300]}
+        leg_done.set()
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0

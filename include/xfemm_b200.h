@@ -248,6 +248,10 @@ int xfemm_linprob_save_solution(xfemm_linprob *p);
 int xfemm_linprob_newton_norms(xfemm_linprob *p, double *dv2, double *v2);
 int xfemm_linprob_relax(xfemm_linprob *p, double relax);
 /* planar: b = V*c ; axisymmetric: b = V*c*2*pi*r*0.01 (static2d.cpp:1018-1021, staticaxi.cpp:779-783) */
+/* 1: deterministic assembly — the element kernels store their contributions in a scratch array and a gather pass adds
+ * them per CSR slot / row in a fixed order (bit-reproducible run to run); 0 (default): FP64 atomics straight into the
+ * slots (the sum order, hence the last bits, vary).  Reference scatter: cfemm/fsolver/static2d.cpp:807-815. */
+int xfemm_mag_set_deterministic(xfemm_mag *m, int on);
 int xfemm_mag_solution_to_A(xfemm_mag *m, double *A_host);
 /* Per block label, from the solution resident on the device (planar magnetostatics): energy_area[l] = sum over the
  * label's elements of area [m^2] x stored energy density [J/m^3] (FPProc::BlockIntegral(2), cfemm/fpproc/fpproc.cpp:3762-3830,

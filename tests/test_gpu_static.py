@@ -123,3 +123,37 @@ def test_prevsoln_mesh_reuse(tmp_path):
     A2 = S2.solution()[1]
     assert rel_l2(A2, A1) <= 1e-9
     S2.close()
+
+
+@pytest.mark.parametrize("case", ["tb", "temp1", "axi1"])
+def test_deterministic_assembly(case, tmp_path):
+    """Row-owner gather assembly (option deterministic_assembly) next to the FP64-atomic scatter (static2d.cpp:807-815):
+    the two agree to rounding (1e-15 of the largest entry), the deterministic one is bit-identical run to run, and the
+    solutions agree to the solver precision."""
+    out = {}
+    for mode in ("atomic", "det1", "det2"):
+        d = tmp_path / mode
+        d.mkdir()
+        S = X.FSolver(stage_case(case, str(d)))
+        S.set_option("keep_system", 1)
+        S.set_option("deterministic_assembly", 0 if mode == "atomic" else 1)
+        S.load_mesh(False)
+        S.renumber(False)
+        S.solve()
+        rowptr, col, vals, rhs = S.system()
+        out[mode] = (vals.copy(), rhs.copy(), S.solution()[1].copy(), S.stats()["newton_steps"])
+        S.close()
+    va, ra, Aa, na = out["atomic"]
+    v1, r1, A1, n1 = out["det1"]
+    v2, r2, A2, n2 = out["det2"]
+    if na == 1:
+        # linear problem: the kept system is the first (only) assembly — bit for bit the same in two runs.  (With Newton
+        # passes the later assemblies see a field that went through the Krylov solver, whose dot products are summed in
+        # an order that depends on the run-time distribution of slices over warps.)
+        assert np.array_equal(v1, v2) and np.array_equal(r1, r2), "the deterministic assembly is not bit-reproducible"
+    else:
+        assert np.max(np.abs(v1 - v2)) <= 1e-9 * np.max(np.abs(v1))
+    assert na == n1
+    assert np.max(np.abs(va - v1)) <= 1e-13 * np.max(np.abs(va))
+    assert np.max(np.abs(ra - r1)) <= 1e-13 * max(np.max(np.abs(ra)), 1e-300)
+    assert rel_l2(A1, Aa) <= 1e-7

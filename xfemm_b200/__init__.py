@@ -106,6 +106,7 @@ SIGNATURES = {
     "xfemm_clinprob_amg_levels": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_longlong)]),
     "xfemm_fsolver_stored_energy": (C.c_int, [_P, C.POINTER(C.c_double)]),
     "xfemm_fsolver_flux_linkage": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double)]),
+    "xfemm_mag_set_deterministic": (C.c_int, [_P, C.c_int]),
     "xfemm_mag_label_integrals": (C.c_int, [_P, C.c_int, _P, _dp, _dp]),
     "xfemm_clinprob_create": (C.c_int, [C.c_int, C.c_int, _ip, _ip, C.POINTER(_P)]),
     "xfemm_clinprob_destroy": (C.c_int, [_P]),

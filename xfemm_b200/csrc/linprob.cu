@@ -7,6 +7,7 @@
 #include "pcg_args.cuh"
 #include <cooperative_groups.h>
 #include <algorithm>
+#include <functional>
 #include <unordered_map>
 #include <mutex>
 #include <vector>
@@ -729,6 +730,87 @@ k_periodic_turn(int npairs, const int *__restrict__ pair_wait, const int *__rest
     }
 }
 
+// Long dependency chains, worked through in shared memory.  Pairs that share matrix entries must be applied in list
+// order (the averaging does not commute), and neighbouring pairs along a periodic boundary do share entries, so a
+// boundary is one chain of up to thousands of pairs; through global memory every link of it costs a round trip to L2
+// (~0.7 us per pair).  Here the host cuts every chain (= connected component of the sharing relation; different chains
+// are independent and get a block each) into segments whose entries fit shared memory: the block loads the entries of
+// a segment, ONE warp applies its pairs in order out of shared memory (~50 cycles per pair), the block writes them
+// back.  Same arithmetic, same order, same value-dependent fill rule as k_periodic / k_periodic_turn.
+constexpr int PBC_SEG_SLOTS = 8192, PBC_SEG_ITEMS = 4096, PBC_SEG_PAIRS = 1024;
+constexpr size_t PBC_SMEM_BYTES = (size_t)PBC_SEG_SLOTS * 9 + (size_t)PBC_SEG_ITEMS * 8 + (size_t)PBC_SEG_PAIRS * 16;
+__global__ void __launch_bounds__(1024)
+k_periodic_chains(const int *__restrict__ chain_seg, const int *__restrict__ seg_slot, const int *__restrict__ seg_gid,
+                  const int *__restrict__ seg_pair, const int *__restrict__ seg_item, const int4 *__restrict__ pair_tab,
+                  const ushort4 *__restrict__ sitems, long long nnz, double *vals, double *b,
+                  const unsigned char *__restrict__ fill_mask, unsigned char *created)
+{
+    extern __shared__ __align__(16) unsigned char pbc_smem[];
+    double *sv = (double *)pbc_smem;                                        // [PBC_SEG_SLOTS] values
+    ushort4 *it = (ushort4 *)(pbc_smem + (size_t)PBC_SEG_SLOTS * 8);        // [PBC_SEG_ITEMS] local slots of an item
+    int4 *pt = (int4 *)(pbc_smem + (size_t)PBC_SEG_SLOTS * 8 + (size_t)PBC_SEG_ITEMS * 8); // [PBC_SEG_PAIRS]
+    unsigned char *cr = pbc_smem + (size_t)PBC_SEG_SLOTS * 8 + (size_t)PBC_SEG_ITEMS * 8 + (size_t)PBC_SEG_PAIRS * 16; // written?
+    const int lane = threadIdx.x & 31;
+    for (int sg = chain_seg[blockIdx.x]; sg < chain_seg[blockIdx.x + 1]; sg++)
+    {
+        const int g0 = seg_slot[sg], ns = seg_slot[sg + 1] - g0;
+        const int p0 = seg_pair[sg], np = seg_pair[sg + 1] - p0;
+        const int i0 = seg_item[sg], ni = seg_item[sg + 1] - i0;
+        for (int t = threadIdx.x; t < ns; t += blockDim.x)
+        {
+            const int gid = seg_gid[g0 + t];
+            sv[t] = gid < nnz ? __ldcg(vals + gid) : __ldcg(b + (gid - nnz));
+            cr[t] = 0;
+        }
+        for (int t = threadIdx.x; t < ni; t += blockDim.x) it[t] = sitems[i0 + t];
+        for (int t = threadIdx.x; t < np; t += blockDim.x) pt[t] = pair_tab[p0 + t];
+        __syncthreads();
+        if (threadIdx.x < 32)
+        {
+            for (int pr = 0; pr < np; pr++)
+            {
+                const int4 m = pt[pr];
+                const int a0 = m.x & 0xffff, a1 = (m.x >> 16) & 0xffff;
+                const double sgn = m.w ? -1.0 : 1.0;
+                for (int q = a0 + lane; q < a1; q += 32)
+                {
+                    const ushort4 s4 = it[q];
+                    const double v1 = sv[s4.x], v2 = sv[s4.z];
+                    if (v1 != 0.0 || v2 != 0.0)
+                    {
+                        const double c = (v1 + sgn * v2) / 2.0;
+                        sv[s4.x] = c; sv[s4.y] = c; sv[s4.z] = sgn * c; sv[s4.w] = sgn * c;
+                        cr[s4.x] = 1; cr[s4.y] = 1; cr[s4.z] = 1; cr[s4.w] = 1;
+                    }
+                }
+                if (lane == 0)
+                {
+                    const int la = m.y & 0xffff, lb = (m.y >> 16) & 0xffff, lbi = m.z & 0xffff, lbj = (m.z >> 16) & 0xffff;
+                    const double dii = sv[la], djj = sv[lb];
+                    const double c = m.w ? 0.5 * (dii + djj) : (dii + djj) / 2.0;
+                    sv[la] = c; sv[lb] = c;
+                    const double cb = 0.5 * (sv[lbi] + sgn * sv[lbj]);
+                    sv[lbi] = cb; sv[lbj] = sgn * cb;
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < ns; t += blockDim.x)
+        {
+            const int gid = seg_gid[g0 + t];
+            if (gid < nnz)
+            {
+                __stcg(vals + gid, sv[t]);
+                if (cr[t] && fill_mask && fill_mask[gid]) created[gid] = 1;
+            }
+            else __stcg(b + (gid - nnz), sv[t]);
+        }
+        __threadfence_block();
+        __syncthreads(); // the next segment of the chain may load entries this one wrote
+    }
+}
+
 // Newton bookkeeping (static2d.cpp:953-989)
 __global__ void k_newton_norms(int n, const double *__restrict__ V, const double *__restrict__ Vold, double *part)
 {
@@ -1185,8 +1267,111 @@ int xfemm_linprob_periodic(xfemm_linprob *p, int npairs, const int *ni, const in
             for (int q = level_ptr[l]; q < level_ptr[l + 1]; q++) wait[q] = level_ptr[l];
         XB_CUDA(p->pbc_wait.upload(wait.data(), wait.size(), st));
         XB_CUDA(cudaStreamSynchronize(st));
+        p->pbc_chains = 0;
+        if (nlevels > 32 && p->nnz + p->n < (1ll << 31) && env_int("XFEMM_PBC_CHAINS", 1))
+        {
+            // ---- chains and segments for k_periodic_chains (pairs in LIST order: k indexes ni/nj/type, items, meta)
+            auto ids_of = [&](int k, std::vector<long long> &out) {
+                out.clear();
+                for (int t = item_ptr[k] * 4; t < item_ptr[k + 1] * 4; t++) out.push_back(items[t]);
+                const int *m = &meta[(size_t)6 * k];
+                out.push_back(m[3]); out.push_back(m[4]);
+                out.push_back(p->nnz + m[0]); out.push_back(p->nnz + m[1]); // right-hand side entries
+            };
+            std::vector<int> parent(npairs);
+            for (int k = 0; k < npairs; k++) parent[k] = k;
+            std::function<int(int)> root = [&](int x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; };
+            std::unordered_map<long long, int> first_pair;
+            std::vector<long long> ids;
+            for (int k = 0; k < npairs; k++)
+            {
+                ids_of(k, ids);
+                for (long long id : ids)
+                {
+                    auto f = first_pair.find(id);
+                    if (f == first_pair.end()) first_pair[id] = k;
+                    else { const int a = root(f->second), b2 = root(k); if (a != b2) parent[std::max(a, b2)] = std::min(a, b2); }
+                }
+            }
+            std::vector<int> chain_of(npairs, -1), chain_root;
+            std::vector<std::vector<int>> chains;
+            for (int k = 0; k < npairs; k++)
+            {
+                const int r = root(k);
+                if (chain_of[r] < 0) { chain_of[r] = (int)chains.size(); chains.emplace_back(); }
+                chains[chain_of[r]].push_back(k);
+            }
+            std::vector<int> chain_seg(1, 0), seg_slot(1, 0), seg_pair(1, 0), seg_item(1, 0), seg_gid;
+            std::vector<int4> pair_tab;
+            std::vector<ushort4> sitems;
+            bool ok = true;
+            for (const auto &ch : chains)
+            {
+                size_t q = 0;
+                while (q < ch.size() && ok)
+                {
+                    std::unordered_map<long long, int> local;
+                    std::vector<int> gids;
+                    int nitems = 0, npair = 0;
+                    auto lid = [&](long long id) {
+                        auto f = local.find(id);
+                        if (f != local.end()) return f->second;
+                        const int v = (int)gids.size();
+                        local[id] = v; gids.push_back((int)id);
+                        return v;
+                    };
+                    while (q < ch.size() && npair < PBC_SEG_PAIRS)
+                    {
+                        const int k = ch[q];
+                        const int cnt = item_ptr[k + 1] - item_ptr[k];
+                        ids_of(k, ids);
+                        size_t fresh = 0;
+                        for (long long id : ids) if (!local.count(id)) fresh++;
+                        if (npair > 0 && ((int)gids.size() + (int)fresh > PBC_SEG_SLOTS || nitems + cnt > PBC_SEG_ITEMS)) break;
+                        if ((int)fresh > PBC_SEG_SLOTS || cnt > PBC_SEG_ITEMS) { ok = false; break; } // one pair does not fit: other kernel
+                        const int it0 = nitems;
+                        for (int t = item_ptr[k]; t < item_ptr[k + 1]; t++)
+                        {
+                            ushort4 s4;
+                            s4.x = (unsigned short)lid(items[4 * t]); s4.y = (unsigned short)lid(items[4 * t + 1]);
+                            s4.z = (unsigned short)lid(items[4 * t + 2]); s4.w = (unsigned short)lid(items[4 * t + 3]);
+                            sitems.push_back(s4);
+                        }
+                        nitems += cnt;
+                        const int *m = &meta[(size_t)6 * k];
+                        const int la = lid(m[3]), lb = lid(m[4]), lbi = lid(p->nnz + m[0]), lbj = lid(p->nnz + m[1]);
+                        pair_tab.push_back(make_int4(it0 | (nitems << 16), la | (lb << 16), lbi | (lbj << 16), m[2]));
+                        npair++; q++;
+                    }
+                    if (!ok) break;
+                    seg_gid.insert(seg_gid.end(), gids.begin(), gids.end());
+                    seg_slot.push_back((int)seg_gid.size());
+                    seg_pair.push_back((int)pair_tab.size());
+                    seg_item.push_back((int)sitems.size());
+                }
+                chain_seg.push_back((int)seg_slot.size() - 1);
+            }
+            if (ok && !chains.empty())
+            {
+                if (sitems.empty()) sitems.push_back(ushort4{0, 0, 0, 0});
+                XB_CUDA(p->pbc_chain_seg.upload(chain_seg.data(), chain_seg.size(), st));
+                XB_CUDA(p->pbc_seg_slot.upload(seg_slot.data(), seg_slot.size(), st));
+                XB_CUDA(p->pbc_seg_gid.upload(seg_gid.data(), seg_gid.size(), st));
+                XB_CUDA(p->pbc_seg_pair.upload(seg_pair.data(), seg_pair.size(), st));
+                XB_CUDA(p->pbc_seg_item.upload(seg_item.data(), seg_item.size(), st));
+                XB_CUDA(p->pbc_pair_tab.upload(pair_tab.data(), pair_tab.size(), st));
+                XB_CUDA(p->pbc_sitems.upload(sitems.data(), sitems.size(), st));
+                XB_CUDA(cudaStreamSynchronize(st));
+                XB_CUDA(cudaFuncSetAttribute(k_periodic_chains, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PBC_SMEM_BYTES));
+                p->pbc_chains = (int)chains.size();
+            }
+        }
     }
-    if (p->pbc_levels <= 32)
+    if (p->pbc_chains > 0)
+        ++xb::g_launch, k_periodic_chains<<<p->pbc_chains, 1024, PBC_SMEM_BYTES, p->stream>>>(
+            p->pbc_chain_seg.p, p->pbc_seg_slot.p, p->pbc_seg_gid.p, p->pbc_seg_pair.p, p->pbc_seg_item.p, p->pbc_pair_tab.p,
+            p->pbc_sitems.p, p->nnz, p->vals.p, p->b.p, p->fill_mask.n ? p->fill_mask.p : nullptr, p->created.p);
+    else if (p->pbc_levels <= 32)
     {
         // few dependency levels (the usual case: neighbouring boundary nodes share an edge): one launch
         // per level, one warp per pair over the whole device instead of a 3 ms latency chain in one block

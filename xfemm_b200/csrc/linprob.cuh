@@ -65,6 +65,11 @@ struct xfemm_linprob
     xb::DevBuf<int> pbc_level_ptr, pbc_item_ptr, pbc_meta, pbc_items;
     std::vector<int> h_pbc_level_ptr; // host copy: pairs per dependency level
     xb::DevBuf<int> pbc_wait;         // per pair (level-sorted): pairs that must be finished before it starts
+    // long dependency chains: chains of pairs cut into segments that are worked through in shared memory (k_periodic_chains)
+    int pbc_chains = 0;
+    xb::DevBuf<int> pbc_chain_seg, pbc_seg_slot, pbc_seg_gid, pbc_seg_pair, pbc_seg_item;
+    xb::DevBuf<int4> pbc_pair_tab;
+    xb::DevBuf<ushort4> pbc_sitems;
     xb::DevBuf<unsigned char> fill_mask, created; // optional, see xfemm_linprob_set_fill_mask
 
     // result mailbox

@@ -4,6 +4,8 @@
 // B-H reluctivity lookup + Newton d(nu)/dB^2 term on the device, FP64 atomics into the fixed
 // CSR pattern of the bound linear problem through a per-element slot map built once per mesh.
 #include "linprob.cuh"
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <vector>
 #include <algorithm>
 #include <cmath>
@@ -38,6 +40,13 @@ struct xfemm_mag
     xb::DevBuf<double> psrc_val;
     double ext_zo = 0, ext_ro = 0, ext_ri = 0, r_eps = 0;
     xb::DevBuf<int> err_flag;
+    // deterministic ("row-owner gather") assembly: element kernels store their 9 + 3 contributions in det_scratch
+    // (slot q*ne+e, right-hand side 9*ne + j*ne + e), a gather pass adds, per CSR slot / row, its contributors in
+    // ascending order of that index (lists built once per mesh: stable radix sort by target)
+    int deterministic = 0;
+    xb::DevBuf<double> det_scratch; // 12 * n_elems
+    xb::DevBuf<int> det_src;        // 12 * n_elems contributor indices, sorted by target
+    xb::DevBuf<int> det_ptr;        // nnz + n_nodes + 1
 };
 
 namespace xb {
@@ -115,7 +124,7 @@ k_assemble_static2d(int ne, int iter, const int4 *__restrict__ tri, const double
                     const int *__restrict__ emap, const xfemm_mag_label *__restrict__ labels,
                     const double *__restrict__ magdir_elem, const double *__restrict__ bhB,
                     const double *__restrict__ bhH, const double *__restrict__ bhS,
-                    const double *__restrict__ V, double *vals, double *b, double2 *mu_out)
+                    const double *__restrict__ V, double *vals, double *b, double2 *mu_out, int det)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= ne) return;
@@ -243,9 +252,14 @@ k_assemble_static2d(int ne, int iter, const int4 *__restrict__ tri, const double
         {
             const double me = Mx[j][k] / mu2 + My[j][k] / mu1 + Mn[j][k];
             bj += Mn[j][k] * Vn[k];
-            atomicAdd(vals + emap[(size_t)(3 * j + k) * ne + e], -me);
+            // det: own scratch cell of this contribution (vals = b = the scratch array): a plain, coalesced store;
+            // k_det_gather adds the cells up per slot
+            const size_t cell = (size_t)(3 * j + k) * ne + e;
+            if (det) vals[cell] = -me;
+            else atomicAdd(vals + emap[cell], -me);
         }
-        atomicAdd(b + n[j], -bj);
+        if (det) b[(size_t)(9 + j) * ne + e] = -bj;
+        else atomicAdd(b + n[j], -bj);
     }
 }
 
@@ -260,7 +274,7 @@ k_assemble_staticaxi(int ne, int iter, const int4 *__restrict__ tri, const doubl
                      const double *__restrict__ magdir_elem, const double *__restrict__ bhB,
                      const double *__restrict__ bhH, const double *__restrict__ bhS,
                      const double *__restrict__ V, double *vals, double *b, double2 *mu_out,
-                     double ext_zo, double ext_ro, double ext_ri)
+                     double ext_zo, double ext_ro, double ext_ri, int det)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= ne) return;
@@ -430,16 +444,21 @@ k_assemble_staticaxi(int ne, int iter, const int4 *__restrict__ tri, const doubl
         {
             const double me = Mx[j][k] / mu2 + My[j][k] / mu1 + Mn[j][k];
             bj += Mn[j][k] * Vn[k];
-            atomicAdd(vals + emap[(size_t)(3 * j + k) * ne + e], -me);
+            // det: own scratch cell of this contribution (vals = b = the scratch array): a plain, coalesced store;
+            // k_det_gather adds the cells up per slot
+            const size_t cell = (size_t)(3 * j + k) * ne + e;
+            if (det) vals[cell] = -me;
+            else atomicAdd(vals + emap[cell], -me);
         }
-        atomicAdd(b + n[j], -bj);
+        if (det) b[(size_t)(9 + j) * ne + e] = -bj;
+        else atomicAdd(b + n[j], -bj);
     }
 }
 
 // mixed (Robin) boundary edges, BdryFormat==2 (static2d.cpp:460-480; staticaxi.cpp:308-329 adds 2r)
 __global__ void k_mixed_edges(int nm, int ne, const int *__restrict__ es, const double *__restrict__ c01,
                               const int4 *__restrict__ tri, const double2 *__restrict__ xy,
-                              const int *__restrict__ emap, double *vals, double *b, int axi)
+                              const int *__restrict__ emap, double *vals, double *b, int axi, int det)
 {
     int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= nm) return;
@@ -451,13 +470,14 @@ __global__ void k_mixed_edges(int nm, int ne, const int *__restrict__ es, const 
     const double l = sqrt((B.x - A.x) * (B.x - A.x) + (B.y - A.y) * (B.y - A.y));
     const double rfac = axi ? 2. * ((A.x + B.x) / 2.) : 1.;
     const double K = axi ? -0.0001 * c * rfac * c01[2 * m] * l / 6. : -0.0001 * c * c01[2 * m] * l / 6.;
-    atomicAdd(vals + emap[(size_t)(3 * j + j) * ne + e], -(K * 2.));
-    atomicAdd(vals + emap[(size_t)(3 * k + k) * ne + e], -(K * 2.));
-    atomicAdd(vals + emap[(size_t)(3 * j + k) * ne + e], -K);
-    atomicAdd(vals + emap[(size_t)(3 * k + j) * ne + e], -K);
+    auto slot = [&](int a, int bq) { const size_t cell = (size_t)(3 * a + bq) * ne + e; return det ? cell : (size_t)emap[cell]; };
+    atomicAdd(vals + slot(j, j), -(K * 2.));
+    atomicAdd(vals + slot(k, k), -(K * 2.));
+    atomicAdd(vals + slot(j, k), -K);
+    atomicAdd(vals + slot(k, j), -K);
     const double K2 = axi ? (c01[2 * m + 1] * l / 2.) * 0.0001 * rfac : (c01[2 * m + 1] * l / 2.) * 0.0001;
-    atomicAdd(b + n[j], -K2);
-    atomicAdd(b + n[k], -K2);
+    atomicAdd(b + (det ? (size_t)(9 + j) * ne + e : (size_t)n[j]), -K2);
+    atomicAdd(b + (det ? (size_t)(9 + k) * ne + e : (size_t)n[k]), -K2);
 }
 
 // air-gap element ring cells: L.AddTo(MG[ii][jj]*ww[ii]*ww[jj], nn[ii], nn[jj]) for jj>=ii
@@ -483,6 +503,75 @@ __global__ void k_age_scatter(int ncells, const int *__restrict__ nodes, const d
         const int s2 = csr_find(rowptr, col, bnode, a);
         if (s2 < 0) { atomicExch(err, 2); return; }
         atomicAdd(vals + s2, v);
+    }
+}
+
+// ---- deterministic assembly (see xfemm_mag::deterministic) -------------------------------------------
+// target of contribution idx: a CSR slot (idx < 9 ne) or nnz + row (right-hand side)
+__global__ void k_det_keys(int ne, long long nnz, const int *__restrict__ emap, const int4 *__restrict__ tri, int *keys, int *vals_idx)
+{
+    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (idx >= 12ll * ne) return;
+    vals_idx[idx] = (int)idx;
+    if (idx < 9ll * ne) { keys[idx] = emap[idx]; return; }
+    const int j = (int)((idx - 9ll * ne) / ne), e = (int)((idx - 9ll * ne) % ne);
+    const int4 t = tri[e];
+    keys[idx] = (int)nnz + (j == 0 ? t.x : j == 1 ? t.y : t.z);
+}
+__global__ void k_det_count(long long len, const int *__restrict__ keys, int *cnt)
+{
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < len) atomicAdd(cnt + keys[i], 1);
+}
+// vals[s] += sum of the contributions of slot s, b[r] += those of row r, each list in ascending contributor order
+__global__ void k_det_gather(long long nnz, int n, const int *__restrict__ ptr, const int *__restrict__ src,
+                             const double *__restrict__ scratch, double *vals, double *b)
+{
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= nnz + n) return;
+    const int k0 = ptr[t], k1 = ptr[t + 1];
+    if (k0 == k1) return;
+    double sum = 0.0;
+    for (int k = k0; k < k1; k += 4)
+    {
+        // four at a time, loads first (lists are short: ~3 contributors per slot, ~6 per row)
+        int i0 = src[k], i1 = k + 1 < k1 ? src[k + 1] : -1, i2 = k + 2 < k1 ? src[k + 2] : -1, i3 = k + 3 < k1 ? src[k + 3] : -1;
+        const double v0 = scratch[i0], v1 = i1 >= 0 ? scratch[i1] : 0.0, v2 = i2 >= 0 ? scratch[i2] : 0.0, v3 = i3 >= 0 ? scratch[i3] : 0.0;
+        sum += v0; sum += v1; sum += v2; sum += v3;
+    }
+    if (t < nnz) vals[t] += sum;
+    else b[t - nnz] += sum;
+}
+// air-gap blocks in a fixed order: one block, the cells one after the other, the 55 pairs of a cell in parallel
+__global__ void k_age_scatter_ordered(int ncells, const int *__restrict__ nodes, const double *__restrict__ w,
+                                      const int *__restrict__ mid, const double *__restrict__ mats,
+                                      const int *__restrict__ rowptr, const int *__restrict__ col, double *vals, double sign, int *err)
+{
+    for (int cell = 0; cell < ncells; cell++)
+    {
+        const int t = threadIdx.x;
+        if (t < 55)
+        {
+            int q = t, ii = 0;
+            while (q >= 10 - ii) { q -= 10 - ii; ii++; }
+            const int jj = ii + q;
+            const int a = nodes[cell * 10 + ii], bnode = nodes[cell * 10 + jj];
+            const double v = sign * (mats[mid[cell] * 100 + ii * 10 + jj] * w[cell * 10 + ii] * w[cell * 10 + jj]);
+            const int s1 = csr_find(rowptr, col, a, bnode);
+            if (s1 < 0) atomicExch(err, 2);
+            else
+            {
+                atomicAdd(vals + s1, v); // within a cell a slot is hit at most twice (repeated ring node): commutative
+                if (a != bnode)
+                {
+                    const int s2 = csr_find(rowptr, col, bnode, a);
+                    if (s2 < 0) atomicExch(err, 2);
+                    else atomicAdd(vals + s2, v);
+                }
+            }
+        }
+        __threadfence_block();
+        __syncthreads();
     }
 }
 
@@ -800,6 +889,45 @@ int xfemm_mag_assemble_static(xfemm_mag *m, int iter, double *elapsed_ms)
 // position), bit 1 = the air-gap element blocks, added to whatever the value array holds.  A sweep on a linear
 // problem assembles and boundary-conditions bit 0 once, keeps a snapshot (xfemm_linprob_snapshot) and afterwards
 // only restores it and adds bit 1 for each position.
+// contributor lists of the deterministic assembly: once per mesh
+static int det_prepare(xfemm_mag *m)
+{
+    if (m->det_ptr.n) return XFEMM_OK;
+    xfemm_linprob *L = m->lin;
+    cudaStream_t st = L->stream;
+    const long long len = 12ll * m->n_elems, targets = L->nnz + m->n_nodes;
+    XB_ARG(len < (1ll << 31) && targets < (1ll << 31), "mesh too large for the deterministic assembly lists");
+    xb::DevBuf<int> keys, keys2, idx, cnt;
+    xb::DevBuf<unsigned char> tmp;
+    XB_CUDA(keys.alloc(len)); XB_CUDA(keys2.alloc(len)); XB_CUDA(idx.alloc(len));
+    XB_CUDA(m->det_src.alloc(len));
+    XB_CUDA(cnt.alloc(targets + 1)); XB_CUDA(cnt.zero(st));
+    XB_CUDA(m->det_ptr.alloc(targets + 1));
+    XB_CUDA(m->det_scratch.alloc(len));
+    ++xb::g_launch, xb::k_det_keys<<<(unsigned)((len + 255) / 256), 256, 0, st>>>(m->n_elems, L->nnz, m->emap.p, (const int4 *)m->tri.p, keys.p, idx.p);
+    int end_bit = 1;
+    while ((1ll << end_bit) <= targets && end_bit < 31) end_bit++;
+    size_t bytes = 0;
+    XB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys.p, keys2.p, idx.p, m->det_src.p, (int)len, 0, end_bit, st));
+    XB_CUDA(tmp.alloc(bytes));
+    XB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, keys.p, keys2.p, idx.p, m->det_src.p, (int)len, 0, end_bit, st)); // stable
+    ++xb::g_launch, xb::k_det_count<<<(unsigned)((len + 255) / 256), 256, 0, st>>>(len, keys.p, cnt.p);
+    size_t bytes2 = 0;
+    XB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes2, cnt.p, m->det_ptr.p, (int)(targets + 1), st));
+    if (bytes2 > tmp.n) XB_CUDA(tmp.alloc(bytes2));
+    XB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, bytes2, cnt.p, m->det_ptr.p, (int)(targets + 1), st));
+    XB_CUDA(cudaStreamSynchronize(st));
+    XB_CUDA(cudaGetLastError());
+    return XFEMM_OK;
+}
+
+int xfemm_mag_set_deterministic(xfemm_mag *m, int on)
+{
+    XB_ARG(m, "null handle");
+    m->deterministic = on ? 1 : 0;
+    return XFEMM_OK;
+}
+
 int xfemm_mag_assemble_static_parts(xfemm_mag *m, int iter, int parts, double *elapsed_ms)
 {
     XB_ARG(m && m->lin, "null handle");
@@ -815,7 +943,16 @@ int xfemm_mag_assemble_static_parts(xfemm_mag *m, int iter, int parts, double *e
         XB_CUDA(L->b.zero(st));
     }
     XB_CUDA(m->err_flag.zero(st));
-    if ((parts & 2) && m->n_age_cells > 0)
+    const int det = m->deterministic;
+    if (det && (parts & 1))
+    {
+        int rc = det_prepare(m);
+        if (rc != XFEMM_OK) return rc; // (no zeroing: every cell of the scratch array is stored by the element kernel)
+    }
+    // element contributions: straight into the CSR slots (FP64 atomics), or into the scratch cells of the
+    // deterministic mode (vals = b = scratch, see the kernels)
+    double *ev = det ? m->det_scratch.p : L->vals.p, *eb = det ? m->det_scratch.p : L->b.p;
+    if (!det && (parts & 2) && m->n_age_cells > 0)
     {
         int nt = m->n_age_cells * 55;
         ++xb::g_launch, k_age_scatter<<<(nt + 127) / 128, 128, 0, st>>>(m->n_age_cells, m->age_nodes.p, m->age_w.p, m->age_mid.p,
@@ -825,16 +962,25 @@ int xfemm_mag_assemble_static_parts(xfemm_mag *m, int iter, int parts, double *e
     else if (m->axisymmetric)
         ++xb::g_launch, k_assemble_staticaxi<<<(m->n_elems + 255) / 256, 256, 0, st>>>(
             m->n_elems, iter, (const int4 *)m->tri.p, (const double2 *)m->xy.p, m->emap.p, m->labels.p,
-            m->magdir.n ? m->magdir.p : nullptr, m->bhB.p, m->bhH.p, m->bhS.p, L->V.p, L->vals.p, L->b.p,
-            (double2 *)m->mu.p, m->ext_zo, m->ext_ro, m->ext_ri);
+            m->magdir.n ? m->magdir.p : nullptr, m->bhB.p, m->bhH.p, m->bhS.p, L->V.p, ev, eb,
+            (double2 *)m->mu.p, m->ext_zo, m->ext_ro, m->ext_ri, det);
     else
         ++xb::g_launch, k_assemble_static2d<<<(m->n_elems + 255) / 256, 256, 0, st>>>(
             m->n_elems, iter, (const int4 *)m->tri.p, (const double2 *)m->xy.p, m->emap.p, m->labels.p,
-            m->magdir.n ? m->magdir.p : nullptr, m->bhB.p, m->bhH.p, m->bhS.p, L->V.p, L->vals.p, L->b.p, (double2 *)m->mu.p);
+            m->magdir.n ? m->magdir.p : nullptr, m->bhB.p, m->bhH.p, m->bhS.p, L->V.p, ev, eb, (double2 *)m->mu.p, det);
     if ((parts & 1) && m->n_mixed > 0)
         ++xb::g_launch, k_mixed_edges<<<(m->n_mixed + 127) / 128, 128, 0, st>>>(m->n_mixed, m->n_elems, m->mixed_es.p, m->mixed_c.p,
                                                                 (const int4 *)m->tri.p, (const double2 *)m->xy.p,
-                                                                m->emap.p, L->vals.p, L->b.p, m->axisymmetric);
+                                                                m->emap.p, ev, eb, m->axisymmetric, det);
+    if (det && (parts & 1))
+    {
+        const long long targets = L->nnz + m->n_nodes;
+        ++xb::g_launch, k_det_gather<<<(unsigned)((targets + 255) / 256), 256, 0, st>>>(L->nnz, m->n_nodes, m->det_ptr.p, m->det_src.p,
+                                                                                       m->det_scratch.p, L->vals.p, L->b.p);
+    }
+    if (det && (parts & 2) && m->n_age_cells > 0)
+        ++xb::g_launch, k_age_scatter_ordered<<<1, 64, 0, st>>>(m->n_age_cells, m->age_nodes.p, m->age_w.p, m->age_mid.p, m->age_mats.p,
+                                                                 L->rowptr.p, L->col.p, L->vals.p, 1.0, m->err_flag.p);
     if ((parts & 1) && m->n_psrc > 0)
         ++xb::g_launch, k_point_sources<<<(m->n_psrc + 127) / 128, 128, 0, st>>>(m->n_psrc, m->psrc_node.p, m->psrc_val.p, L->b.p);
     int flag = 0;

@@ -358,6 +358,12 @@ int xfemm_fsolver_set_option(xfemm_fsolver *s, const char *key, double value)
     if (!strcmp(key, "cache_static_part")) { s->S.cacheStaticPart = value != 0; return XFEMM_OK; }
     if (!strcmp(key, "assemble_only")) { s->S.assembleOnly = value != 0; return XFEMM_OK; }
     if (!strcmp(key, "age_union_pattern")) { s->S.ageUnionPattern = value != 0; return XFEMM_OK; }
+    if (!strcmp(key, "deterministic_assembly"))
+    {
+        s->S.deterministicAssembly = value != 0;
+        if (s->S.magdev) xfemm_mag_set_deterministic(s->S.magdev, value != 0); // a resident problem switches at once
+        return XFEMM_OK;
+    }
     if (!strcmp(key, "dist_rank")) { s->S.distRank = (int)value; return XFEMM_OK; }
     if (!strcmp(key, "dist_world")) { s->S.distWorld = (int)value; return XFEMM_OK; }
     xb::set_error("unknown option %s", key);

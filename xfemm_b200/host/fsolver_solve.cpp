@@ -679,6 +679,7 @@ int FSolver::staticSolve(CBigLinProb &L, bool axi)
     D.r_eps = 1.e-6 * units[LengthUnits];
     tick("host tables");
     if (xfemm_mag_create(&D, lin, &magdev) != XFEMM_OK) { WarnMessage(xfemm_last_error()); return false; }
+    if (deterministicAssembly || getenv("XFEMM_DETERMINISTIC")) xfemm_mag_set_deterministic(magdev, 1);
     tick("mag_create");
     stats.t_upload = wall() - t0;
 
