@@ -74,6 +74,8 @@ struct AmgArgs
     double omega = 0.8, over = 2.6;
     int team_from = 1;      // first level handled by the team of blocks (small levels), 1 <= team_from <= nlev-1
     int team_blocks = 1;    // blocks 0..team_blocks-1 form the team
+    int solo_from = 1 << 20; // levels >= solo_from (a few hundred rows) are cycled by block 0 ALONE with __syncthreads: on them
+                            // a barrier between blocks costs more than the whole level
     unsigned *team_ctr = nullptr; // arrival counter of the team barrier (device memory, zeroed before the launch)
     unsigned *grid_ctr = nullptr; // arrival counter of the grid barrier (GridBar), or null: cooperative-groups barrier
     const double *coarse_inv = nullptr; // dense inverse of the coarsest level (n_pad x n_pad, internal order) or null
@@ -191,6 +193,9 @@ __device__ __forceinline__ int amg_task_table(const int *slice_ptr, int cur, int
     return ns;
 }
 
+// blocks that share level l of the team's sub-cycle: the team, or block 0 alone on the smallest levels
+__device__ __forceinline__ int amg_team_width(const AmgArgs &g, int l) { return l >= g.solo_from ? 1 : g.team_blocks; }
+
 // Once per kernel, whole block, before the first cycle.  `sg` = the block's copy of the arguments in shared memory
 // (raw storage of sizeof(AmgArgs)): the coarse-level code is out of line and would otherwise read the kernel
 // parameters through generic loads — a round trip to L2 each after every barrier; shared memory is a few cycles.
@@ -214,8 +219,8 @@ __device__ __forceinline__ const AmgArgs &amg_kernel_init(const AmgArgs &g, unsi
         if (L.wide.n_rows)
         {
             if (l < g.team_from) wide_range(L.wide, amg_chunk(L.nslices, B, G) * 32, amg_chunk(L.nslices, B + 1, G) * 32, k0, k1);
-            else if (B < g.team_blocks)
-                wide_range(L.wide, amg_chunk(L.nslices, B, g.team_blocks) * 32, amg_chunk(L.nslices, B + 1, g.team_blocks) * 32, k0, k1);
+            else if (B < amg_team_width(g, l))
+                wide_range(L.wide, amg_chunk(L.nslices, B, amg_team_width(g, l)) * 32, amg_chunk(L.nslices, B + 1, amg_team_width(g, l)) * 32, k0, k1);
         }
         s_wk[2 * l] = k0; s_wk[2 * l + 1] = k1;
         s_wk[AMG_SWK_TAB + l] = -1;
@@ -233,7 +238,7 @@ __device__ __forceinline__ const AmgArgs &amg_kernel_init(const AmgArgs &g, unsi
             const AmgLev &L = g.lev[l];
             int s0 = 0, s1 = 0;
             if (l < g.team_from) { s0 = amg_chunk(L.nslices, B, G); s1 = amg_chunk(L.nslices, B + 1, G); }
-            else if (B < g.team_blocks) { s0 = amg_chunk(L.nslices, B, g.team_blocks); s1 = amg_chunk(L.nslices, B + 1, g.team_blocks); }
+            else if (B < amg_team_width(g, l)) { s0 = amg_chunk(L.nslices, B, amg_team_width(g, l)); s1 = amg_chunk(L.nslices, B + 1, amg_team_width(g, l)); }
             const int nsl = s1 - s0, need = 2 + 2 * (nsl + 1) + MAXT;
             if (nsl <= 0 || nsl > AMG_TASK_MAXS || used + need > AMG_TABLE_INTS) continue;
             int *t = tab + used, ntasks = 0;
@@ -563,13 +568,14 @@ template <int NC>
 __device__ __noinline__ void amg_team_cycle(const AmgArgs &g, const AmgArgs2 *g2, int *s_wk, int *stamp_k = nullptr)
 {
     const int first = g.team_from, last = g.nlev - 1;
-    const int T = g.team_blocks, B = blockIdx.x;
+    const int B = blockIdx.x;
     const int lane = threadIdx.x & 31, warp_b = threadIdx.x >> 5, nwarps_b = blockDim.x >> 5;
-    const int tid_t = B * blockDim.x + threadIdx.x, nthr_t = T * blockDim.x;
     const double w = g.omega, over = g.over;
     unsigned char *tsm = xb_dyn_smem + g.task_smem_offset;
     int sk = stamp_k ? *stamp_k : AMG_MAX_STAMPS; // XFEMM_AMG_TRACE: a stamp behind every team barrier
-    auto tsync = [&]() {
+    // barrier behind a phase on level l: among the blocks that share the level
+    auto sync = [&](int l) {
+        if (l >= g.solo_from) { __syncthreads(); return; }
         if (g.stamps && g.trace_detail) { __syncthreads(); amg_stamp(g, sk); } // block 0's own part of the phase ends here
         team_sync(g, s_wk);
         amg_stamp(g, sk);
@@ -577,28 +583,35 @@ __device__ __noinline__ void amg_team_cycle(const AmgArgs &g, const AmgArgs2 *g2
     // SpMV pass over this block's slices of team level l
     auto spmv = [&](int l, bool prol, const AmgV<NC> &v, const AmgV<NC> &cv, int kind) {
         const AmgLev &L = g.lev[l];
+        const int T = amg_team_width(g, l);
         const int s0 = amg_chunk(L.nslices, B, T), s1 = amg_chunk(L.nslices, B + 1, T);
         unsigned long long *dbg = (g.stamps && g.trace_detail && B == 0 && l == first && kind == AMG_EPI_RESIDUAL) ? g.stamps + AMG_MAX_STAMPS : nullptr;
         const int *table = s_wk[AMG_SWK_TAB + l] >= 0 ? (const int *)(tsm + AMG_TASK_HDR_BYTES + AMG_TASK_PART_BYTES) + s_wk[AMG_SWK_TAB + l] : nullptr;
         if (prol) amg_spmv_tasks<NC, true>(L, v, cv, s0, s1, s_wk[2 * l], s_wk[2 * l + 1], kind, w, over, tsm, table);
         else amg_spmv_tasks<NC, false>(L, v, cv, s0, s1, s_wk[2 * l], s_wk[2 * l + 1], kind, w, over, tsm, table, dbg);
     };
+    // does this block take part in level l?
+    auto in = [&](int l) { return B < amg_team_width(g, l); };
 
     // ---- down
     for (int l = first; l < last; l++)
     {
+        if (!in(l)) break; // the rest of the way down and back up to here is block 0's
         const AmgLev &L = g.lev[l];
         const AmgLev &C = g.lev[l + 1];
         const AmgV<NC> lv = amg_vecs<NC>(g, g2, l), cv = amg_vecs<NC>(g, g2, l + 1);
+        const int T = amg_team_width(g, l);
         spmv(l, false, lv, cv, AMG_EPI_RESIDUAL);
-        tsync();
-        amg_restrict_level<NC>(L, C, lv, cv, tid_t, nthr_t, w);
-        tsync();
+        sync(l);
+        amg_restrict_level<NC>(L, C, lv, cv, B * blockDim.x + threadIdx.x, T * blockDim.x, w);
+        sync(l); // (the last team level hands over to block 0 through a team barrier: everybody passes it)
     }
     // ---- coarsest level
+    if (in(last))
     {
         const AmgLev &L = g.lev[last];
         const AmgV<NC> lv = amg_vecs<NC>(g, g2, last);
+        const int T = amg_team_width(g, last);
         if (g.coarse_inv)
         {
             // exact solve with the dense inverse prepared by amg_refresh: t = A^-1 b, one warp per row
@@ -632,24 +645,34 @@ __device__ __noinline__ void amg_team_cycle(const AmgArgs &g, const AmgArgs2 *g2
 #pragma unroll
                     for (int m = 0; m < NC; m++) { sv.x[m] = lv.t[m]; sv.t[m] = lv.x[m]; }
                 spmv(last, false, sv, sv, AMG_EPI_POST);
-                if (it + 1 < g.coarse_sweeps) tsync();
+                if (it + 1 < g.coarse_sweeps) sync(last);
             }
         }
-        if (last > first) tsync();
+        if (last > first) sync(last);
     }
     // ---- up: t = x' + w D^-1 (b - A x'),  x' = x + over * P * t_coarse
     for (int l = last - 1; l >= first; l--)
     {
+        if (!in(l))
+            continue;
+        if (l + 1 >= g.solo_from && l < g.solo_from)
+        {
+            // block 0 comes back from its solo levels: the team waits for it here (block 0's stores to the vectors of
+            // level l + 1 are ordered by the barrier's release)
+            team_sync(g, s_wk);
+            amg_stamp(g, sk);
+        }
         const AmgLev &L = g.lev[l];
         const AmgV<NC> lv = amg_vecs<NC>(g, g2, l), cv = amg_vecs<NC>(g, g2, l + 1);
+        const int T = amg_team_width(g, l);
         if (L.sell_cagg) spmv(l, true, lv, cv, AMG_EPI_POST);
         else
         {
-            amg_prolong_rows<NC>(L, lv, cv, 0, L.n_pad, tid_t, nthr_t, over);
-            tsync();
+            amg_prolong_rows<NC>(L, lv, cv, 0, L.n_pad, B * blockDim.x + threadIdx.x, T * blockDim.x, over);
+            sync(l);
             spmv(l, false, lv, cv, AMG_EPI_POST);
         }
-        if (l > first) tsync();
+        if (l > first) sync(l);
     }
     if (stamp_k) *stamp_k = sk;
 }
@@ -662,8 +685,13 @@ __device__ __noinline__ void amg_team_cycle(const AmgArgs &g, const AmgArgs2 *g2
 template <class Epi>
 __device__ __forceinline__ void amg_spmv_phase(const AmgLev &L, int s0, int s1, int wk0, int wk1, double *x,
                                                double *wide_tmp, int *s_next, Epi epi, StageSmem *S = nullptr,
-                                               const double *pf0 = nullptr, const double *pf1 = nullptr)
+                                               const double *pf0 = nullptr, const double *pf1 = nullptr, int wr0 = -1, int wr1 = 0,
+                                               int wstride = 1)
 {
+    // the wide rows this block takes (before its warps join the stream): wr0, wr0 + wstride, ... < wr1.  Default: the
+    // wide rows of the whole level dealt out over the blocks; the partitioned solver passes the block's own ones
+    // (stride 1), because a block pushes the rows of its chunk to the peers without a barrier in between.
+    if (wr0 < 0) { wr0 = (int)blockIdx.x; wr1 = L.wide.n_rows; wstride = (int)gridDim.x; }
     const int lane = threadIdx.x & 31;
     if (S && S->ntiles > 0)
     {
@@ -677,12 +705,14 @@ __device__ __forceinline__ void amg_spmv_phase(const AmgLev &L, int s0, int s1, 
                           return make_double2(L.diag[row], x[row]);
                       },
                       [&](int s, int row, double acc, double2 dx) {
-                          if (wk1 > wk0 && ((L.wide.mask[s] >> lane) & 1u)) return;
+                          if (L.wide.n_rows && ((L.wide.mask[s] >> lane) & 1u)) return;
                           epi(row, fma(dx.x, dx.y, acc));
                       },
                       [&]() {
-                          if (wk1 > wk0)
-                              wide_rows_warp(L.wide, L.wide_val, wk0, wk1, x, [&](int row, double off) { epi(row, fma(L.diag[row], x[row], off)); });
+                          // wide rows [wr0, wr1) of the level (all of them, or a rank's), dealt out over the blocks
+                          if (wr1 > wr0)
+                              wide_rows_warp(L.wide, L.wide_val, wr0, wr1, x,
+                                             [&](int row, double off) { epi(row, fma(L.diag[row], x[row], off)); }, wstride);
                       });
         return;
     }

@@ -214,7 +214,8 @@ __device__ __forceinline__ void dist_chunk(const DistArgs &d, int l, int &s0, in
 // the V-cycle with the big levels partitioned over the ranks.  z = M^-1 r: level 0 b = r, t = z, x = scratch
 // (pre-smoothed iterate stored and pushed by the caller).  Returns this thread's partial of r.z (own rows).
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double dist_vcycle(const AmgArgs &g, const AmgArgs &sg, const DistCtx &X, int *s_next, int *s_wk, StageSmem *S0)
+__device__ __forceinline__ double dist_vcycle(const AmgArgs &g, const AmgArgs &sg, const DistCtx &X, int *s_next, int *s_wk, StageSmem *S0,
+                                              int wr0, int wr1 /* wide rows of this block's chunk of the finest level */)
 {
     const DistArgs &d = X.d;
     const int lp = d.lp;
@@ -231,7 +232,8 @@ __device__ __forceinline__ double dist_vcycle(const AmgArgs &g, const AmgArgs &s
         dist_chunk(d, l + 1, c0, c1);
         const AmgV<1> lv = amg_vecs<1>(g, nullptr, l), cv = amg_vecs<1>(g, nullptr, l + 1);
         if (l == 0)
-            amg_spmv_phase(L, s0, s1, s_wk[0], s_wk[1], L.x, L.t, s_next, [&](int row, double ax) { L.t[row] = L.b[row] - ax; }, S0, L.b);
+            amg_spmv_phase(L, s0, s1, s_wk[0], s_wk[1], L.x, L.t, s_next, [&](int row, double ax) { L.t[row] = L.b[row] - ax; }, S0, L.b,
+                           nullptr, wr0, wr1, 1);
         else
             amg_spmv_tasks<1, false>(sg.lev[l], lv, cv, s0, s1, s_wk[2 * l], s_wk[2 * l + 1], AMG_EPI_RESIDUAL, w, over, tsm, amg_table(g, s_wk, l));
         X.push(3 * l + DL_R, d.off_t[l]);
@@ -273,7 +275,7 @@ __device__ __forceinline__ double dist_vcycle(const AmgArgs &g, const AmgArgs &s
                 const double br = L.b[row], z = fma(w * L.dinv[row], br - ax, L.x[row]);
                 L.t[row] = z;
                 dot = fma(br, z, dot);
-            }, S0, L.b, L.dinv);
+            }, S0, L.b, L.dinv, wr0, wr1, 1);
         }
     }
     return dot;
@@ -298,8 +300,9 @@ k_dpcg(const __grid_constant__ PcgArgs a, const __grid_constant__ AmgArgs g, con
     dist_chunk(d, 0, s0, s1);
     const int r0 = s0 * 32, r1 = s1 * 32;
     double *partA = a.part, *partB = a.part + G;
-    int wk0 = 0, wk1 = 0;
+    int wk0 = 0, wk1 = 0; // wide rows of this block's chunk of the finest level
     if (a.wide.n_rows) wide_range(a.wide, r0, r1, wk0, wk1);
+    const int wr0 = wk0, wr1 = wk1;
     StageSmem S = stage_carve(xb_dyn_smem);
     if (a.tiles)
     {
@@ -321,8 +324,8 @@ k_dpcg(const __grid_constant__ PcgArgs a, const __grid_constant__ AmgArgs g, con
         if (L.wide.n_rows)
         {
             if (l < d.lp) { int c0, c1; dist_chunk(d, l, c0, c1); wide_range(L.wide, c0 * 32, c1 * 32, k0, k1); }
-            else if (B < g.team_blocks)
-                wide_range(L.wide, amg_chunk(L.nslices, B, g.team_blocks) * 32, amg_chunk(L.nslices, B + 1, g.team_blocks) * 32, k0, k1);
+            else if (B < amg_team_width(g, l))
+                wide_range(L.wide, amg_chunk(L.nslices, B, amg_team_width(g, l)) * 32, amg_chunk(L.nslices, B + 1, amg_team_width(g, l)) * 32, k0, k1);
         }
         s_wk[2 * l] = k0; s_wk[2 * l + 1] = k1;
         s_wk[AMG_SWK_TAB + l] = -1;
@@ -358,7 +361,7 @@ k_dpcg(const __grid_constant__ PcgArgs a, const __grid_constant__ AmgArgs g, con
             const AmgLev &L = g.lev[l];
             int c0 = 0, c1 = 0;
             if (l < d.lp) dist_chunk(d, l, c0, c1);
-            else if (B < g.team_blocks) { c0 = amg_chunk(L.nslices, B, g.team_blocks); c1 = amg_chunk(L.nslices, B + 1, g.team_blocks); }
+            else if (B < amg_team_width(g, l)) { c0 = amg_chunk(L.nslices, B, amg_team_width(g, l)); c1 = amg_chunk(L.nslices, B + 1, amg_team_width(g, l)); }
             const int nsl = c1 - c0, need = 2 + 2 * (nsl + 1) + MAXT;
             if (nsl <= 0 || nsl > AMG_TASK_MAXS || used + need > AMG_TABLE_INTS) continue;
             int *t = tab + used, ntasks = 0;
@@ -380,7 +383,7 @@ k_dpcg(const __grid_constant__ PcgArgs a, const __grid_constant__ AmgArgs g, con
         for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x) L0.x[i] = g.omega * a.dinv[i] * a.r[i];
         X.push(DL_H, d.off_x[0]);
         X.exchange();
-        double part = dist_vcycle(g, sg, X, &s_next, s_wk, &S);
+        double part = dist_vcycle(g, sg, X, &s_next, s_wk, &S, wr0, wr1);
         part = block_sum(part, sm);
         if (threadIdx.x == 0) part_out[B] = part;
         grid.sync();
@@ -439,12 +442,13 @@ k_dpcg(const __grid_constant__ PcgArgs a, const __grid_constant__ AmgArgs g, con
             staged_slices(S, a.slice_ptr, a.sell_val, a.sell_col, s0, s1, a.p, &s_next,
                           [&](int row) { return make_double2(a.diag[row], a.p[row]); },
                           [&](int s, int row, double acc, double2 dp) {
-                              if (wk1 > wk0 && ((a.wide.mask[s] >> lane) & 1u)) return; // a wide row: see `before`
+                              if (a.wide.n_rows && ((a.wide.mask[s] >> lane) & 1u)) return; // a wide row: see `before`
                               acc = fma(dp.x, dp.y, acc);
                               a.u[row] = acc;
                               part = fma(dp.y, acc, part);
                           },
                           [&]() {
+                              // the wide rows of this block's own chunk (see amg_spmv_phase)
                               if (wk1 > wk0)
                                   wide_rows_warp(a.wide, a.wide_val, wk0, wk1, a.p, [&](int row, double off) {
                                       const double pr = a.p[row], acc = fma(a.diag[row], pr, off);
@@ -502,7 +506,7 @@ k_dpcg(const __grid_constant__ PcgArgs a, const __grid_constant__ AmgArgs g, con
         }
         X.push(DL_H, d.off_x[0]);
         X.exchange();
-        part = dist_vcycle(g, sg, X, &s_next, s_wk, &S);
+        part = dist_vcycle(g, sg, X, &s_next, s_wk, &S, wr0, wr1);
         part = block_sum(part, sm);
         if (threadIdx.x == 0) partB[B] = part;
         grid.sync();

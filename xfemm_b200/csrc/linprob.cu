@@ -403,19 +403,20 @@ __global__ void __launch_bounds__(1024, 1) k_pcg(const __grid_constant__ PcgArgs
             staged_slices(S, a.slice_ptr, a.sell_val, a.sell_col, s0, s1, a.p, &s_next,
                           [&](int row) { return make_double2(a.diag[row], a.p[row]); },
                           [&](int s, int row, double acc, double2 dp) {
-                              if (wk1 > wk0 && ((a.wide.mask[s] >> lane) & 1u)) return; // a wide row: see `before`
+                              if (a.wide.n_rows && ((a.wide.mask[s] >> lane) & 1u)) return; // a wide row: see `before`
                               acc = fma(dp.x, dp.y, acc);
                               a.u[row] = acc;
                               part = fma(dp.y, acc, part);
                           },
                           [&]() {
-                              // the wide rows of the chunk: a few warps, before they join the stream
-                              if (wk1 > wk0)
-                                  wide_rows_warp(a.wide, a.wide_val, wk0, wk1, a.p, [&](int row, double off) {
+                              // the wide rows of the matrix, dealt out over the blocks: a warp or two of each, before
+                              // they join the stream
+                              if (a.wide.n_rows)
+                                  wide_rows_warp(a.wide, a.wide_val, (int)blockIdx.x, a.wide.n_rows, a.p, [&](int row, double off) {
                                       const double pr = a.p[row], acc = fma(a.diag[row], pr, off);
                                       a.u[row] = acc;
                                       part = fma(pr, acc, part);
-                                  });
+                                  }, (int)gridDim.x);
                           });
         }
         else

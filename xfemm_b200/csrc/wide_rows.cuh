@@ -87,11 +87,15 @@ __device__ __forceinline__ void wide_rows_block(const WideView &w, const T *__re
 // whole row (its segments are contiguous) and lane 0 hands it to epi(row, sum).  No block-wide step: the other warps
 // of the block go on with the regular slices meanwhile (stage.cuh: `before`), which then SKIP the rows flagged in the
 // per-slice mask — the wide warp is the only writer of a wide row.
+// stride > 1: the rows k0, k0 + stride, ... (the caller deals the wide rows of a whole level out over the blocks —
+// k0 = first row of the range + block index, stride = blocks — when the epilogue touches nothing but the row itself:
+// the handful of blocks whose chunks hold the air-gap ring would otherwise be the stragglers of every pass).
 template <class Epi>
-__device__ __forceinline__ void wide_rows_warp(const WideView &w, const double *__restrict__ val, int k0, int k1, const double *x, Epi epi)
+__device__ __forceinline__ void wide_rows_warp(const WideView &w, const double *__restrict__ val, int k0, int k1, const double *x, Epi epi,
+                                               int stride = 1)
 {
     const int lane = threadIdx.x & 31, warp_b = threadIdx.x >> 5, nwarps_b = blockDim.x >> 5;
-    for (int k = k0 + (nwarps_b - 1 - warp_b); k < k1; k += nwarps_b)
+    for (int k = k0 + stride * (nwarps_b - 1 - warp_b); k < k1; k += stride * nwarps_b)
     {
         const int row = w.row[k];
         const int q0 = w.sptr[w.rseg[k]], q1 = w.sptr[w.rseg[k + 1]];
