@@ -12,7 +12,7 @@ BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libxfemm_b200.so")
 CLI = os.path.join(HERE, "fsolver_b200")
 
-CU = ["csrc/linprob.cu", "csrc/mag_assemble.cu", "csrc/clinprob.cu", "csrc/mag_harmonic.cu", "csrc/dist.cu", "csrc/dist_amg.cu", "csrc/amg.cu", "csrc/cnewton.cu", "csrc/pattern_device.cu"]
+CU = ["csrc/linprob.cu", "csrc/mag_assemble.cu", "csrc/clinprob.cu", "csrc/mag_harmonic.cu", "csrc/dist.cu", "csrc/dist_amg.cu", "csrc/amg.cu", "csrc/cnewton.cu", "csrc/pattern_device.cu", "csrc/layout_device.cu", "csrc/amg_setup.cu"]
 CPP = ["csrc/layout.cpp", "host/pattern.cpp", "host/fsolver_io.cpp", "host/fsolver_solve.cpp", "host/fsolver_harmonic.cpp",
        "host/bh_curve.cpp", "host/age_matrix.cpp", "host/spars.cpp", "host/cspars.cpp",
        "host/capi_fsolver.cpp", "host/magdir_expr.cpp"]

@@ -12,6 +12,11 @@
 namespace xb {
 
 int linprob_refresh_values(xfemm_linprob *p, int *singular_row); // linprob.cu
+// amg_setup.cu
+int amg_coarse_pattern_device(xfemm_linprob *cur, const int *d_agg, int nc, std::vector<int> &crp, std::vector<int> &ccol,
+                              DevBuf<int> &gptr, DevBuf<int> &gsrc, cudaStream_t st);
+int amg_centroids_device(xfemm_linprob *cur, xfemm_linprob *c, const int *d_agg, cudaStream_t st);
+int amg_transfer_maps_device(xfemm_linprob *cur, xfemm_linprob *c, const int *d_agg, AmgHierarchy::Transfer &T, cudaStream_t st);
 
 AmgHierarchy::~AmgHierarchy()
 {
@@ -78,6 +83,17 @@ int aggregate(int n, const int *rp, const int *col, int wide_thr, std::vector<in
         na++;
     }
     return na;
+}
+
+// The first coarsening only needs the pattern: a host thread starts on it the moment a problem is created, next to
+// the uploads, the assembly set-up and the device layout; amg_build() collects the result.  Small problems and
+// XFEMM_NO_EARLY_AGG skip it.
+void linprob_start_aggregation(xfemm_linprob *p)
+{
+    if (p->n < 20000 || getenv("XFEMM_NO_EARLY_AGG") || p->agg_thread.joinable()) return;
+    const char *ew = getenv("XFEMM_WIDE_ROW");
+    p->agg_wide_thr = ew ? atoi(ew) : 64;
+    p->agg_thread = std::thread([p]() { p->agg_early_nc = aggregate(p->n, p->h_rowptr.data(), p->h_col.data(), p->agg_wide_thr, p->agg_early); });
 }
 
 // coarse pattern (sorted CSR) + for every coarse slot the fine slots that sum into it
@@ -234,16 +250,59 @@ int amg_build(xfemm_linprob *fine, std::unique_ptr<AmgHierarchy> &out, std::thre
     xfemm_linprob *cur = fine;
     h->level_n.push_back(fine->n);
     h->level_nnz.push_back((int)fine->nnz);
+    const bool on_device = !getenv("XFEMM_HOST_HIERARCHY");
+    const bool check = on_device && getenv("XFEMM_HIERARCHY_CHECK");
+    auto differs = [&](const char *what, int level) { set_error("device hierarchy set-up differs from the host's: %s (level %d)", what, level); return XFEMM_ERR_ARG; };
     while ((int)h->coarse.size() + 1 < AMG_MAX_LEVELS && cur->n > min_coarse)
     {
         std::vector<int> agg, crp, ccol, gptr, gsrc;
         const bool timing = getenv("XFEMM_TIMING") != nullptr;
         auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
         const double ta = now();
-        const int nc = aggregate(cur->n, cur->h_rowptr.data(), cur->h_col.data(), wide_thr, agg);
+        // the aggregates: a sequential greedy pass on the host — started when the pattern arrived (linprob_start_aggregation)
+        int nc;
+        if (cur->agg_thread.joinable() && cur->agg_wide_thr == wide_thr)
+        {
+            cur->agg_thread.join();
+            agg.swap(cur->agg_early);
+            nc = cur->agg_early_nc;
+        }
+        else
+        {
+            if (cur->agg_thread.joinable()) cur->agg_thread.join();
+            nc = aggregate(cur->n, cur->h_rowptr.data(), cur->h_col.data(), wide_thr, agg);
+        }
         if (nc < 1 || nc > cur->n * 0.7) break; // coarsening stalled
         const double tb = now();
-        coarse_pattern(cur->n, cur->h_rowptr.data(), cur->h_col.data(), agg, nc, crp, ccol, gptr, gsrc);
+        cudaStream_t st = fine->stream;
+        h->xfer.emplace_back(new AmgHierarchy::Transfer);
+        AmgHierarchy::Transfer &T = *h->xfer.back();
+        DevBuf<int> d_agg;
+        if (on_device)
+        {
+            XB_CUDA(d_agg.upload(agg.data(), agg.size(), st));
+            int rc = amg_coarse_pattern_device(cur, d_agg.p, nc, crp, ccol, T.gptr, T.gsrc, st);
+            if (rc != XFEMM_OK) return rc;
+        }
+        if (!on_device || check)
+        {
+            std::vector<int> crp2, ccol2;
+            coarse_pattern(cur->n, cur->h_rowptr.data(), cur->h_col.data(), agg, nc, check ? crp2 : crp, check ? ccol2 : ccol, gptr, gsrc);
+            if (check)
+            {
+                if (crp2 != crp || ccol2 != ccol) return differs("coarse pattern", (int)h->coarse.size());
+                std::vector<int> a(gptr.size()), b(gsrc.size());
+                XB_CUDA(cudaMemcpy(a.data(), T.gptr.p, a.size() * sizeof(int), cudaMemcpyDeviceToHost));
+                XB_CUDA(cudaMemcpy(b.data(), T.gsrc.p, b.size() * sizeof(int), cudaMemcpyDeviceToHost));
+                if (T.gptr.n != gptr.size() || a != gptr || b != gsrc) return differs("Galerkin gather lists", (int)h->coarse.size());
+            }
+            else
+            {
+                XB_CUDA(T.gptr.upload(gptr.data(), gptr.size(), st));
+                XB_CUDA(T.gsrc.upload(gsrc.data(), gsrc.size(), st));
+            }
+        }
+        T.nnz_coarse = (long long)ccol.size();
         const double tc = now();
         // levels from the third on live in the L2-pinned arena (see AmgHierarchy::arena)
         // XFEMM_AMG_PIN_L1: the second level's solver layout (SELL stream, vectors) as well — not its CSR arrays
@@ -256,6 +315,9 @@ int amg_build(xfemm_linprob *fine, std::unique_ptr<AmgHierarchy> &out, std::thre
             if (dev_alloc((void **)&h->arena.base, cap) == cudaSuccess) { h->arena.cap = cap; h->arena.used = 0; }
             else { h->arena.base = nullptr; (void)cudaGetLastError(); }
         }
+        // the layout of the finest level (internal order, device copy of the coordinates) is needed from here on
+        if (fine_layout && fine_layout->joinable()) fine_layout->join();
+        if (cur == fine && fine->layout_precond < 0) { set_error("the solver layout of the finest level is missing"); return XFEMM_ERR_ARG; }
         xfemm_linprob *c = nullptr;
         int rc;
         {
@@ -270,15 +332,26 @@ int amg_build(xfemm_linprob *fine, std::unique_ptr<AmgHierarchy> &out, std::thre
             if ((int)cur->h_xy.size() == 2 * cur->n)
             {
                 // coarse "node" = centroid of its aggregate: the coarse level follows the same Z-curve
-                std::vector<double> sx(nc, 0.), sy(nc, 0.);
-                std::vector<int> cnt(nc, 0);
-                for (int i = 0; i < cur->n; i++)
-                    if (agg[i] >= 0) { sx[agg[i]] += cur->h_xy[2 * (size_t)i]; sy[agg[i]] += cur->h_xy[2 * (size_t)i + 1]; cnt[agg[i]]++; }
-                c->h_xy.resize(2 * (size_t)nc);
-                for (int I = 0; I < nc; I++)
+                const bool dev_xy = on_device && cur->d_xy.n == 2 * (size_t)cur->n;
+                if (dev_xy)
                 {
-                    c->h_xy[2 * (size_t)I] = (float)(sx[I] / std::max(1, cnt[I]));
-                    c->h_xy[2 * (size_t)I + 1] = (float)(sy[I] / std::max(1, cnt[I]));
+                    rc = amg_centroids_device(cur, c, d_agg.p, st);
+                    if (rc != XFEMM_OK) return rc;
+                }
+                if (!dev_xy || check)
+                {
+                    std::vector<double> sx(nc, 0.), sy(nc, 0.);
+                    std::vector<int> cnt(nc, 0);
+                    for (int i = 0; i < cur->n; i++)
+                        if (agg[i] >= 0) { sx[agg[i]] += cur->h_xy[2 * (size_t)i]; sy[agg[i]] += cur->h_xy[2 * (size_t)i + 1]; cnt[agg[i]]++; }
+                    std::vector<float> hxy(2 * (size_t)nc);
+                    for (int I = 0; I < nc; I++)
+                    {
+                        hxy[2 * (size_t)I] = (float)(sx[I] / std::max(1, cnt[I]));
+                        hxy[2 * (size_t)I + 1] = (float)(sy[I] / std::max(1, cnt[I]));
+                    }
+                    if (dev_xy && hxy != c->h_xy) return differs("centroids", (int)h->coarse.size());
+                    c->h_xy.swap(hxy);
                 }
             }
             {
@@ -287,33 +360,45 @@ int amg_build(xfemm_linprob *fine, std::unique_ptr<AmgHierarchy> &out, std::thre
             }
             if (rc != XFEMM_OK) return rc;
         }
-        h->xfer.emplace_back(new AmgHierarchy::Transfer);
-        AmgHierarchy::Transfer &T = *h->xfer.back();
-        T.nnz_coarse = (long long)ccol.size();
-        cudaStream_t st = fine->stream;
-        XB_CUDA(T.gptr.upload(gptr.data(), gptr.size(), st));
-        XB_CUDA(T.gsrc.upload(gsrc.data(), gsrc.size(), st));
         // transfer maps in the internal (SELL) row orders of both levels
-        if (fine_layout && fine_layout->joinable()) fine_layout->join(); // the finest level's layout is needed from here on
-        if (cur == fine && fine->layout_precond < 0) { set_error("the solver layout of the finest level is missing"); return XFEMM_ERR_ARG; }
         const SellLayout &LF = cur->lay, &LC = c->lay;
-        std::vector<int> agg_int(LF.n_pad, -1), mptr(LC.n_pad + 1, 0), mem;
-        for (int r = 0; r < LF.n_pad; r++)
-        {
-            const int i = LF.i2c[r];
-            if (i >= 0 && agg[i] >= 0) { agg_int[r] = LC.c2i[agg[i]]; mptr[agg_int[r] + 1]++; }
-        }
-        for (int R = 0; R < LC.n_pad; R++) mptr[R + 1] += mptr[R];
-        mem.assign(std::max(1, mptr[LC.n_pad]), 0);
-        {
-            std::vector<int> pos(mptr.begin(), mptr.end() - 1);
-            for (int r = 0; r < LF.n_pad; r++) if (agg_int[r] >= 0) mem[pos[agg_int[r]]++] = r;
-        }
         {
             ArenaScope scope(pinned ? &h->arena : nullptr);
-            XB_CUDA(T.agg.upload(agg_int.data(), agg_int.size(), st));
-            XB_CUDA(T.mptr.upload(mptr.data(), mptr.size(), st));
-            XB_CUDA(T.mem.upload(mem.data(), mem.size(), st));
+            if (on_device)
+            {
+                rc = amg_transfer_maps_device(cur, c, d_agg.p, T, st);
+                if (rc != XFEMM_OK) return rc;
+            }
+            if (!on_device || check)
+            {
+                std::vector<int> agg_int(LF.n_pad, -1), mptr(LC.n_pad + 1, 0), mem;
+                for (int r = 0; r < LF.n_pad; r++)
+                {
+                    const int i = LF.i2c[r];
+                    if (i >= 0 && agg[i] >= 0) { agg_int[r] = LC.c2i[agg[i]]; mptr[agg_int[r] + 1]++; }
+                }
+                for (int R = 0; R < LC.n_pad; R++) mptr[R + 1] += mptr[R];
+                mem.assign(std::max(1, mptr[LC.n_pad]), 0);
+                {
+                    std::vector<int> pos(mptr.begin(), mptr.end() - 1);
+                    for (int r = 0; r < LF.n_pad; r++) if (agg_int[r] >= 0) mem[pos[agg_int[r]]++] = r;
+                }
+                if (check)
+                {
+                    std::vector<int> a(agg_int.size()), b(mptr.size()), m2(mptr[LC.n_pad]);
+                    XB_CUDA(cudaMemcpy(a.data(), T.agg.p, a.size() * sizeof(int), cudaMemcpyDeviceToHost));
+                    XB_CUDA(cudaMemcpy(b.data(), T.mptr.p, b.size() * sizeof(int), cudaMemcpyDeviceToHost));
+                    XB_CUDA(cudaMemcpy(m2.data(), T.mem.p, m2.size() * sizeof(int), cudaMemcpyDeviceToHost));
+                    mem.resize(m2.size());
+                    if (a != agg_int || b != mptr || m2 != mem) return differs("transfer maps", (int)h->coarse.size() - 1);
+                }
+                else
+                {
+                    XB_CUDA(T.agg.upload(agg_int.data(), agg_int.size(), st));
+                    XB_CUDA(T.mptr.upload(mptr.data(), mptr.size(), st));
+                    XB_CUDA(T.mem.upload(mem.data(), mem.size(), st));
+                }
+            }
             // a level the team may cycle (amg_fill_args decides): coarse row per SELL slot, unless it has wide rows
             if (cur != fine && cur->n <= h->team_rows && cur->wide.n_rows == 0 && LF.sell_len > 0)
             {

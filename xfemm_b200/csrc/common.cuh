@@ -47,6 +47,13 @@ struct DevArena
     size_t cap = 0, used = 0;
 };
 extern thread_local DevArena *g_arena;
+// scope guard: allocations of this thread bypass the arena (temporaries of a set-up step)
+struct NoArena
+{
+    DevArena *prev;
+    NoArena() : prev(g_arena) { g_arena = nullptr; }
+    ~NoArena() { g_arena = prev; }
+};
 
 template <typename T>
 struct DevBuf

@@ -210,32 +210,39 @@ void build_sell_layout(int n, const int *rowptr, const int *col, const std::vect
     }
     });
 
-    // ---- wide rows: row-wise storage in segments
+    std::vector<int> wide_rows;
+    if (any_wide)
+        for (int i = 0; i < n; i++) if (wide[i]) wide_rows.push_back(i);
+    build_wide_part(rowptr, col, wide_rows, L);
+}
+
+// The wide rows (caller numbers, any order) of a layout whose i2c/c2i are known: row-wise storage in segments
+// (layout.h), ascending internal row.
+void build_wide_part(const int *rowptr, const int *col, const std::vector<int> &wide_rows, SellLayout &L)
+{
     L.wide_row.clear(); L.wide_rseg.assign(1, 0); L.wide_sptr.assign(1, 0);
     L.wide_col.clear(); L.wide_src.clear(); L.slice_wide.clear();
-    if (any_wide)
+    if (wide_rows.empty()) return;
+    L.slice_wide.assign(L.nslices, 0u);
+    for (int i : wide_rows) L.wide_row.push_back(L.c2i[i]);
+    std::sort(L.wide_row.begin(), L.wide_row.end());
+    std::vector<std::pair<int, int>> ent;
+    for (int r : L.wide_row)
     {
-        L.slice_wide.assign(L.nslices, 0u);
-        std::vector<std::pair<int, int>> ent;
-        for (int r = 0; r < L.n_pad; r++)
+        const int i = L.i2c[r];
+        L.slice_wide[r / 32] |= 1u << (r % 32);
+        ent.clear();
+        for (int q = rowptr[i]; q < rowptr[i + 1]; q++)
+            if (col[q] != i) ent.emplace_back(L.c2i[col[q]], q);
+        std::sort(ent.begin(), ent.end());
+        for (size_t k = 0; k < ent.size(); k++)
         {
-            int i = L.i2c[r];
-            if (i < 0 || !wide[i]) continue;
-            L.slice_wide[r / 32] |= 1u << (r % 32);
-            L.wide_row.push_back(r);
-            ent.clear();
-            for (int q = rowptr[i]; q < rowptr[i + 1]; q++)
-                if (col[q] != i) ent.emplace_back(L.c2i[col[q]], q);
-            std::sort(ent.begin(), ent.end());
-            for (size_t k = 0; k < ent.size(); k++)
-            {
-                if (k && k % SellLayout::WIDE_SEG == 0) L.wide_sptr.push_back((int)L.wide_col.size());
-                L.wide_col.push_back(ent[k].first);
-                L.wide_src.push_back(ent[k].second);
-            }
-            L.wide_sptr.push_back((int)L.wide_col.size());
-            L.wide_rseg.push_back((int)L.wide_sptr.size() - 1);
+            if (k && k % SellLayout::WIDE_SEG == 0) L.wide_sptr.push_back((int)L.wide_col.size());
+            L.wide_col.push_back(ent[k].first);
+            L.wide_src.push_back(ent[k].second);
         }
+        L.wide_sptr.push_back((int)L.wide_col.size());
+        L.wide_rseg.push_back((int)L.wide_sptr.size() - 1);
     }
 }
 

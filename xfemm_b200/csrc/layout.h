@@ -56,6 +56,7 @@ struct SellLayout
 int greedy_coloring(int n, const int *rowptr, const int *col, int max_colors, std::vector<int> &color);
 void build_sell_layout(int n, const int *rowptr, const int *col, const std::vector<int> *color,
                        int ncolors, int sigma, SellLayout &L, int wide_threshold = 64, const int *base_order = nullptr);
+void build_wide_part(const int *rowptr, const int *col, const std::vector<int> &wide_rows, SellLayout &L);
 void morton_order(int n, const float *xy, std::vector<int> &order);
 
 } // namespace xb

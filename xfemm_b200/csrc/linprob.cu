@@ -836,6 +836,9 @@ __global__ void k_relax(int n, double *V, const double *__restrict__ Vold, doubl
 // =====================================================================================
 // host side
 // =====================================================================================
+int linprob_build_layout_device(xfemm_linprob *p, int sigma, int wide_thr, bool use_coords); // layout_device.cu
+int linprob_check_layout_device(xfemm_linprob *p, const SellLayout &H);
+
 int linprob_build_layout(xfemm_linprob *p, int precond)
 {
     if (precond == XFEMM_PRECOND_AMG) precond = XFEMM_PRECOND_JACOBI; // same uncoloured layout
@@ -846,30 +849,53 @@ int linprob_build_layout(xfemm_linprob *p, int precond)
     SellLayout &L = p->lay;
     int sigma = env_int("XFEMM_SELL_SIGMA", 1024);
     const int wide_thr = p->wide_threshold >= 0 ? p->wide_threshold : env_int("XFEMM_WIDE_ROW", 64);
-    // with node coordinates the internal order follows a Z-curve through the plane (gather locality)
-    std::vector<int> zorder;
-    if ((int)p->h_xy.size() == 2 * p->n && env_int("XFEMM_MORTON", 1)) morton_order(p->n, p->h_xy.data(), zorder);
-    const int *base = zorder.empty() ? nullptr : zorder.data();
-    if ((int)p->forced_order.size() == p->n) { base = p->forced_order.data(); sigma = 1; } // taken as is: no window sort
-    if (precond == XFEMM_PRECOND_MCSSOR)
-    {
-        std::vector<int> color;
-        int nc = greedy_coloring(p->n, p->h_rowptr.data(), p->h_col.data(), env_int("XFEMM_MAX_COLORS", 7), color);
-        build_sell_layout(p->n, p->h_rowptr.data(), p->h_col.data(), &color, nc, sigma, L, wide_thr, base);
-    }
-    else
-        build_sell_layout(p->n, p->h_rowptr.data(), p->h_col.data(), nullptr, 0, sigma, L, wide_thr, base);
     cudaStream_t st = p->stream;
-    XB_CUDA(p->i2c.upload(L.i2c.data(), L.i2c.size(), st));
-    XB_CUDA(p->c2i.upload(L.c2i.data(), L.c2i.size(), st));
-    XB_CUDA(p->slice_ptr.upload(L.slice_ptr.data(), L.slice_ptr.size(), st));
-    XB_CUDA(p->slice_wl.upload(L.slice_wl.data(), L.slice_wl.size(), st));
-    XB_CUDA(p->slice_wu.upload(L.slice_wu.data(), L.slice_wu.size(), st));
-    XB_CUDA(p->sell_col.upload(L.sell_col.data(), L.sell_col.size(), st));
-    XB_CUDA(p->sell_src.upload(L.sell_src.data(), L.sell_src.size(), st));
-    XB_CUDA(p->diag_src.upload(L.diag_src.data(), L.diag_src.size(), st));
-    XB_CUDA(p->color_slice.upload(L.color_slice.data(), L.color_slice.size(), st));
-    XB_CUDA(p->wide.upload(L, st));
+    // the uncoloured layout is built on the device from the resident CSR pattern (layout_device.cu); the host
+    // builder remains for the multicolour one and as the reference of the XFEMM_LAYOUT_CHECK self-test
+    const bool on_device = precond != XFEMM_PRECOND_MCSSOR && !env_int("XFEMM_HOST_LAYOUT", 0);
+    const bool check = on_device && env_int("XFEMM_LAYOUT_CHECK", 0);
+    const bool use_coords = env_int("XFEMM_MORTON", 1) != 0;
+    if (on_device)
+    {
+        int rc = linprob_build_layout_device(p, sigma, wide_thr, use_coords);
+        if (rc != XFEMM_OK) return rc;
+    }
+    if (!on_device || check)
+    {
+        SellLayout Hc;
+        SellLayout &H = check ? Hc : L;
+        // with node coordinates the internal order follows a Z-curve through the plane (gather locality)
+        std::vector<int> zorder;
+        if ((int)p->h_xy.size() == 2 * p->n && use_coords) morton_order(p->n, p->h_xy.data(), zorder);
+        const int *base = zorder.empty() ? nullptr : zorder.data();
+        if ((int)p->forced_order.size() == p->n) { base = p->forced_order.data(); sigma = 1; } // taken as is: no window sort
+        if (precond == XFEMM_PRECOND_MCSSOR)
+        {
+            std::vector<int> color;
+            int nc = greedy_coloring(p->n, p->h_rowptr.data(), p->h_col.data(), env_int("XFEMM_MAX_COLORS", 7), color);
+            build_sell_layout(p->n, p->h_rowptr.data(), p->h_col.data(), &color, nc, sigma, H, wide_thr, base);
+        }
+        else
+            build_sell_layout(p->n, p->h_rowptr.data(), p->h_col.data(), nullptr, 0, sigma, H, wide_thr, base);
+        if (check)
+        {
+            int rc = linprob_check_layout_device(p, H);
+            if (rc != XFEMM_OK) return rc;
+        }
+        else
+        {
+            XB_CUDA(p->i2c.upload(L.i2c.data(), L.i2c.size(), st));
+            XB_CUDA(p->c2i.upload(L.c2i.data(), L.c2i.size(), st));
+            XB_CUDA(p->slice_ptr.upload(L.slice_ptr.data(), L.slice_ptr.size(), st));
+            XB_CUDA(p->slice_wl.upload(L.slice_wl.data(), L.slice_wl.size(), st));
+            XB_CUDA(p->slice_wu.upload(L.slice_wu.data(), L.slice_wu.size(), st));
+            XB_CUDA(p->sell_col.upload(L.sell_col.data(), L.sell_col.size(), st));
+            XB_CUDA(p->sell_src.upload(L.sell_src.data(), L.sell_src.size(), st));
+            XB_CUDA(p->diag_src.upload(L.diag_src.data(), L.diag_src.size(), st));
+            XB_CUDA(p->color_slice.upload(L.color_slice.data(), L.color_slice.size(), st));
+            XB_CUDA(p->wide.upload(L, st));
+        }
+    }
     XB_CUDA(p->sell_val.alloc(L.sell_len));
     for (auto *v : {&p->diag, &p->dinv, &p->x, &p->r, &p->p, &p->u, &p->z, &p->w, &p->bint})
     {
@@ -1069,6 +1095,7 @@ int xfemm_linprob_create(int n, const int *rowptr, const int *colidx, xfemm_linp
     if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream create failed"); return fail(XFEMM_ERR_CUDA); }
     p->h_rowptr.assign(rowptr, rowptr + n + 1);
     p->h_col.assign(colidx, colidx + nnz);
+    linprob_start_aggregation(p); // host thread: first coarsening of a later multigrid set-up, beside the uploads below
     auto body = [&]() -> int {
         XB_CUDA(p->rowptr.upload(rowptr, n + 1, p->stream));
         XB_CUDA(p->col.upload(colidx, nnz, p->stream));
@@ -1716,6 +1743,7 @@ int xfemm_linprob_multpc(xfemm_linprob *p, int precond, const double *x, double 
 int xfemm_linprob_set_coords(xfemm_linprob *p, const double *xy)
 {
     XB_ARG(p, "null handle");
+    p->d_xy.release();
     if (!xy) { p->h_xy.clear(); return XFEMM_OK; }
     p->h_xy.resize(2 * (size_t)p->n);
     for (size_t k = 0; k < p->h_xy.size(); k++) p->h_xy[k] = (float)xy[k];

@@ -5,6 +5,7 @@
 #include "wide_rows.cuh"
 #include <vector>
 #include <cstdint>
+#include <thread>
 
 // Data layout in HBM (all FP64 values, int32 indices):
 //   "boundary" representation, numbered as the caller numbers unknowns (Cuthill–McKee order):
@@ -30,6 +31,13 @@ struct xfemm_linprob
     // boundary representation
     std::vector<int> h_rowptr, h_col;
     std::vector<float> h_xy;       // optional node coordinates (x,y per row): locality hint for the internal order
+    xb::DevBuf<float> d_xy;        // device copy of h_xy (left by the device layout builder for the multigrid set-up)
+    // aggregates of the first coarsening, computed by a host thread from the moment the pattern is known
+    // (xb::linprob_start_aggregation; joined by amg_build or the destructor)
+    std::thread agg_thread;
+    std::vector<int> agg_early;
+    int agg_early_nc = 0, agg_wide_thr = -1;
+    ~xfemm_linprob() { if (agg_thread.joinable()) agg_thread.join(); }
     int wide_threshold = -1;       // rows with more off-diagonals are kept out of the SELL slices (-1: XFEMM_WIDE_ROW, 64)
     std::vector<int> forced_order; // optional: the internal row order to use as is (a companion of another problem)
     xb::DevBuf<int> rowptr, col;
@@ -79,6 +87,7 @@ struct xfemm_linprob
 
 namespace xb {
 int linprob_build_layout(xfemm_linprob *p, int precond);
+void linprob_start_aggregation(xfemm_linprob *p); // amg.cu
 int linprob_prepare(xfemm_linprob *p, int precond);
 int linprob_load_rhs_internal(xfemm_linprob *p);
 int linprob_store_solution_internal(xfemm_linprob *p);
