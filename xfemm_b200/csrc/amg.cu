@@ -51,26 +51,29 @@ int aggregate(int n, const int *rp, const int *col, int wide_thr, std::vector<in
         for (int s = rp[i]; s < rp[i + 1]; s++) agg[col[s]] = na;
         agg[i] = na++;
     }
-    // pass 2: leftovers join the neighbouring aggregate (of pass 1) they are connected to most
+    // pass 2: leftovers join the neighbouring aggregate (of pass 1) they are connected to most — every row decides from
+    // the pass-1 state alone, so the host threads share the rows
     std::vector<int> agg1(agg);
-    std::vector<std::pair<int, int>> cnt;
-    for (int i = 0; i < n; i++)
-    {
-        if (agg1[i] >= 0 || rp[i + 1] - rp[i] <= 1) continue;
-        const bool wi = is_wide(i);
-        cnt.clear();
-        for (int s = rp[i]; s < rp[i + 1]; s++)
+    parallel_for(n, [&](int i0, int i1, int) {
+        std::vector<std::pair<int, int>> cnt;
+        for (int i = i0; i < i1; i++)
         {
-            const int j = col[s];
-            if (j == i || agg1[j] < 0 || (wi && is_wide(j))) continue;
-            bool found = false;
-            for (auto &c : cnt) if (c.first == agg1[j]) { c.second++; found = true; break; }
-            if (!found) cnt.emplace_back(agg1[j], 1);
+            if (agg1[i] >= 0 || rp[i + 1] - rp[i] <= 1) continue;
+            const bool wi = is_wide(i);
+            cnt.clear();
+            for (int s = rp[i]; s < rp[i + 1]; s++)
+            {
+                const int j = col[s];
+                if (j == i || agg1[j] < 0 || (wi && is_wide(j))) continue;
+                bool found = false;
+                for (auto &c : cnt) if (c.first == agg1[j]) { c.second++; found = true; break; }
+                if (!found) cnt.emplace_back(agg1[j], 1);
+            }
+            int best = -1, bc = 0;
+            for (auto &c : cnt) if (c.second > bc || (c.second == bc && c.first < best)) { best = c.first; bc = c.second; }
+            if (best >= 0) agg[i] = best;
         }
-        int best = -1, bc = 0;
-        for (auto &c : cnt) if (c.second > bc || (c.second == bc && c.first < best)) { best = c.first; bc = c.second; }
-        if (best >= 0) agg[i] = best;
-    }
+    }, 65536);
     // pass 3: what is still free forms aggregates with its free neighbours
     for (int i = 0; i < n; i++)
     {

@@ -84,7 +84,7 @@ static cudaError_t fetch(std::vector<T> &h, const T *d, size_t count, cudaStream
 {
     h.resize(count);
     g_d2h_bytes += (long long)(count * sizeof(T));
-    return count ? cudaMemcpyAsync(h.data(), d, count * sizeof(T), cudaMemcpyDeviceToHost, st) : cudaSuccess;
+    return count ? copy_d2h(h.data(), d, count * sizeof(T), st) : cudaSuccess; // (big ones through the pinned ring)
 }
 
 static int bits_for(unsigned long long v) { int b = 1; while (b < 64 && (v >> b)) b++; return b; }

@@ -38,6 +38,11 @@ cudaError_t dev_alloc(void **p, size_t bytes);
 void dev_free(void *p);
 void dev_cache_flush(); // really frees everything cached
 
+// Copies between big pageable host arrays and the device, staged through a pinned ring by several host threads
+// (linprob.cu).  copy_h2d returns once the source has been read; copy_d2h returns with the data in place.
+cudaError_t copy_h2d(void *dst, const void *src, size_t bytes, cudaStream_t st);
+cudaError_t copy_d2h(void *dst, const void *src, size_t bytes, cudaStream_t st);
+
 // Optional bump arena: while g_arena points at one, DevBuf allocations are carved from it, so a
 // group of buffers (the small multigrid levels) ends up in ONE address range that a stream access
 // policy window can pin in L2.  The arena's owner frees the range; arena-backed buffers do not.
@@ -86,7 +91,7 @@ struct DevBuf
         if (count != n) { cudaError_t e = alloc(count); if (e != cudaSuccess) return e; }
         if (count == 0) return cudaSuccess;
         g_h2d_bytes += (long long)(count * sizeof(T));
-        return cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s);
+        return copy_h2d(p, h, count * sizeof(T), s);
     }
     cudaError_t zero(cudaStream_t s = 0) { return n ? cudaMemsetAsync(p, 0, n * sizeof(T), s) : cudaSuccess; }
 };

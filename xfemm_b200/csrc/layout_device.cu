@@ -123,7 +123,7 @@ static cudaError_t fetch(std::vector<T> &h, const T *d, size_t count, cudaStream
 {
     h.resize(count);
     g_d2h_bytes += (long long)(count * sizeof(T));
-    return count ? cudaMemcpyAsync(h.data(), d, count * sizeof(T), cudaMemcpyDeviceToHost, st) : cudaSuccess;
+    return count ? copy_d2h(h.data(), d, count * sizeof(T), st) : cudaSuccess; // (big ones through the pinned ring)
 }
 
 // Fills p->lay (host part) and the device tables i2c, c2i, slice_ptr, slice_wl, slice_wu, sell_col, sell_src, diag_src,

@@ -1002,7 +1002,7 @@ int xfemm_mag_assemble_static_parts(xfemm_mag *m, int iter, int parts, double *e
 int xfemm_mag_get_mu(xfemm_mag *m, double *mu12)
 {
     XB_ARG(m && mu12, "null pointer");
-    XB_CUDA(cudaMemcpyAsync(mu12, m->mu.p, (size_t)m->n_elems * 2 * sizeof(double), cudaMemcpyDeviceToHost, m->lin->stream));
+    XB_CUDA(xb::copy_d2h(mu12, m->mu.p, (size_t)m->n_elems * 2 * sizeof(double), m->lin->stream));
     XB_CUDA(cudaStreamSynchronize(m->lin->stream));
     return XFEMM_OK;
 }
@@ -1084,7 +1084,7 @@ int xfemm_mag_solution_to_A(xfemm_mag *m, double *A_host)
     ++xb::g_launch;
     xb::g_d2h_bytes += (long long)m->n_nodes * 8;
     k_scale_to_A<<<(m->n_nodes + 255) / 256, 256, 0, st>>>(m->n_nodes, L->V.p, (const double2 *)m->xy.p, m->axisymmetric, L->b.p);
-    XB_CUDA(cudaMemcpyAsync(A_host, L->b.p, (size_t)m->n_nodes * sizeof(double), cudaMemcpyDeviceToHost, st));
+    XB_CUDA(xb::copy_d2h(A_host, L->b.p, (size_t)m->n_nodes * sizeof(double), st));
     XB_CUDA(cudaStreamSynchronize(st));
     XB_CUDA(cudaGetLastError());
     return XFEMM_OK;

@@ -85,8 +85,8 @@ int element_graph_device(int n, int n_elems, const int *tri, int tri_stride, std
     ++g_launch, kp_rowptr<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(n, m, k_in.p, d_rp.p);
     adj.resize((size_t)m);
     rp.resize((size_t)n + 1);
-    XB_CUDA(cudaMemcpyAsync(adj.data(), d_col.p, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, st));
-    XB_CUDA(cudaMemcpyAsync(rp.data(), d_rp.p, ((size_t)n + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
+    XB_CUDA(copy_d2h(adj.data(), d_col.p, (size_t)m * sizeof(int), st));
+    XB_CUDA(copy_d2h(rp.data(), d_rp.p, ((size_t)n + 1) * sizeof(int), st));
     XB_CUDA(cudaStreamSynchronize(st));
     XB_CUDA(cudaGetLastError());
     g_d2h_bytes += ((long long)m + n + 1) * 4;

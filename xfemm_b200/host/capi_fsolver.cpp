@@ -15,6 +15,8 @@ void set_error(const char *fmt, ...);
 void age_cell_matrix(double ci, double co, double K, double *MG);
 }
 
+namespace xb { void tune_host_allocator(); } // csrc/linprob.cu: big host blocks stay in the heap between solves
+
 extern "C" int xfemm_age_cell_matrix(double ci, double co, double K, double *MG100)
 {
     if (!MG100 || K == 0) { xb::set_error("invalid arguments"); return XFEMM_ERR_ARG; }
@@ -48,6 +50,7 @@ int xfemm_fsolver_run(const char *basename, int verbose)
 
 int xfemm_fsolver_open(const char *basename, int verbose, xfemm_fsolver **out)
 {
+    xb::tune_host_allocator();
     if (!basename || !out) { xb::set_error("null argument"); return XFEMM_ERR_ARG; }
     xfemm_fsolver *s = new xfemm_fsolver;
     s->verbose = verbose != 0;

@@ -343,6 +343,7 @@ using xbhost::flatten_age;
 // ---------------------------------------------------------------------------------------
 int FSolver::staticSolve(CBigLinProb &L, bool axi)
 {
+    const double tEnter = wall();
     const double c = PI * 4.e-05;
     static const double units[] = {2.54, 0.1, 1., 100., 0.00254, 1.e-04};
     stats = FSolverStats();
@@ -369,16 +370,36 @@ int FSolver::staticSolve(CBigLinProb &L, bool axi)
             anyMagDirFctn = true;
         }
 
+    // ---- one pass of the host threads over the element records (96 B each, 380 MB at 4 M elements): the flat
+    // element table for the device, the elements with a tagged side, the elements that sit in a circuit.  The serial
+    // passes below visit only those lists, in element order.
+    std::vector<int> tri(4 * (size_t)NumEls);
+    std::vector<int> tagged, inCircuit;
+    {
+        std::vector<std::vector<int>> partTag(64), partCirc(64);
+        xb::parallel_for(NumEls, [&](int i0, int i1, int tid) {
+            for (int i = i0; i < i1; i++)
+            {
+                const CMElement &El = meshele[i];
+                int *t4 = &tri[4 * (size_t)i];
+                t4[0] = El.p[0]; t4[1] = El.p[1]; t4[2] = El.p[2]; t4[3] = El.lbl;
+                if (El.e[0] >= 0 || El.e[1] >= 0 || El.e[2] >= 0) partTag[tid].push_back(i);
+                if (NumCircProps > 0 && El.lbl >= 0 && labellist[El.lbl].InCircuit != -1) partCirc[tid].push_back(i);
+            }
+        });
+        for (auto &v : partTag) tagged.insert(tagged.end(), v.begin(), v.end()); // (chunks are contiguous and ascending)
+        for (auto &v : partCirc) inCircuit.insert(inCircuit.end(), v.begin(), v.end());
+    }
+
     // ---- circuits (static2d.cpp:84-167): area, conductance and source integrals per circuit
     if (NumCircProps > 0)
     {
         std::vector<double> I1(NumCircProps, 0.), I2(NumCircProps, 0.), I3(NumCircProps, 0.);
-        for (int i = 0; i < NumEls; i++)
+        // (over the elements that belong to a circuit, in element order: the order fixes the rounding of the integrals)
+        for (int i : inCircuit)
         {
             const CMElement &El = meshele[i];
-            if (El.lbl < 0) continue;
             const int ic = labellist[El.lbl].InCircuit;
-            if (ic == -1) continue;
             const int *n = El.p;
             double p0 = meshnode[n[1]].y - meshnode[n[2]].y, p1 = meshnode[n[2]].y - meshnode[n[0]].y;
             double q0 = meshnode[n[2]].x - meshnode[n[1]].x, q1 = meshnode[n[0]].x - meshnode[n[2]].x;
@@ -490,7 +511,6 @@ int FSolver::staticSolve(CBigLinProb &L, bool axi)
             if (labelNonlinear[meshele[i].lbl]) LinearFlag = false;
 
     // ---- element table, mixed-BC edges, Dirichlet list, point sources
-    std::vector<int> tri(4 * (size_t)NumEls);
     std::vector<int> mixedES;
     std::vector<double> mixedC;
     std::vector<int> dirNodes;
@@ -503,7 +523,19 @@ int FSolver::staticSolve(CBigLinProb &L, bool axi)
     };
     std::vector<int> psNode;
     std::vector<double> psVal;
-    for (int i = 0; i < NumNodes; i++)
+    // nodes with a point property or (axisymmetric) on the axis: a handful among millions — the host threads find
+    // them, the two passes below visit them in node order
+    std::vector<int> special;
+    {
+        const double axisTol = units[LengthUnits] * 1.e-06;
+        std::vector<std::vector<int>> part(64);
+        xb::parallel_for(NumNodes, [&](int i0, int i1, int tid) {
+            for (int i = i0; i < i1; i++)
+                if (meshnode[i].BoundaryMarker >= 0 || (axi && fabs(meshnode[i].x) < axisTol)) part[tid].push_back(i);
+        });
+        for (auto &v : part) special.insert(special.end(), v.begin(), v.end());
+    }
+    for (int i : special)
         if (meshnode[i].BoundaryMarker >= 0)
         {
             psNode.push_back(i);
@@ -512,7 +544,7 @@ int FSolver::staticSolve(CBigLinProb &L, bool axi)
             psVal.push_back(pv);
         }
     // fixed potentials at points (static2d.cpp:827-838) come first, then along segments
-    for (int i = 0; i < NumNodes; i++)
+    for (int i : special)
     {
         // staticaxi.cpp:644-651: nodes on the axis are pinned to zero
         if (axi && fabs(meshnode[i].x) < (units[LengthUnits] * 1.e-06)) { setValue(i, 0.); continue; }
@@ -522,23 +554,8 @@ int FSolver::staticSolve(CBigLinProb &L, bool axi)
             if ((pp.J.re == 0) && (pp.J.im == 0)) setValue(i, pp.A.re / c);
         }
     }
-    // element table in parallel; the (few) elements with a tagged side are then visited in element order,
-    // which is what fixes the first/last semantics of repeated SetValue calls (static2d.cpp:854-921)
-    std::vector<int> tagged;
-    {
-        std::vector<std::vector<int>> part(64);
-        xb::parallel_for(NumEls, [&](int i0, int i1, int tid) {
-            for (int i = i0; i < i1; i++)
-            {
-                const CMElement &El = meshele[i];
-                int *t4 = &tri[4 * (size_t)i];
-                t4[0] = El.p[0]; t4[1] = El.p[1]; t4[2] = El.p[2]; t4[3] = El.lbl;
-                if (El.e[0] >= 0 || El.e[1] >= 0 || El.e[2] >= 0) part[tid].push_back(i);
-            }
-        });
-        for (auto &v : part) tagged.insert(tagged.end(), v.begin(), v.end());
-        std::sort(tagged.begin(), tagged.end());
-    }
+    // the (few) elements with a tagged side, visited in element order, which is what fixes the first/last semantics
+    // of repeated SetValue calls (static2d.cpp:854-921)
     for (int i : tagged)
     {
         const CMElement &El = meshele[i];
@@ -587,6 +604,7 @@ int FSolver::staticSolve(CBigLinProb &L, bool axi)
 
     // ---- sparsity pattern → device problem
     double t0 = wall();
+    if (getenv("XFEMM_TIMING")) fprintf(stderr, "[xfemm timing]   host tables before the pattern %.3f s\n", t0 - tEnter);
     int *rowptr = nullptr, *colidx = nullptr;
     unsigned char *fillmask = nullptr;
     // rotor-angle sweeps re-target the air-gap tables on the resident problem: couple every pair of
@@ -625,7 +643,9 @@ int FSolver::staticSolve(CBigLinProb &L, bool axi)
     if (rc != XFEMM_OK) { WarnMessage(xfemm_last_error()); return false; }
 
     std::vector<double> xy(2 * (size_t)NumNodes);
-    for (int i = 0; i < NumNodes; i++) { xy[2 * (size_t)i] = meshnode[i].x; xy[2 * (size_t)i + 1] = meshnode[i].y; }
+    xb::parallel_for(NumNodes, [&](int i0, int i1, int) {
+        for (int i = i0; i < i1; i++) { xy[2 * (size_t)i] = meshnode[i].x; xy[2 * (size_t)i + 1] = meshnode[i].y; }
+    });
     // Locality hint for the solver's internal row order (Z-curve through the node coordinates): the finer
     // layout costs ~0.08 s of host time at 2 M nodes and saves ~2 ms per solve, so by default it is used
     // when the device problem is going to be solved repeatedly (Newton iteration, rotor sweeps).
