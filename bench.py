@@ -232,13 +232,14 @@ def reference_calibration(info, mesh_size):
     return cal
 
 
-def pcg_bytes_per_iteration(X, S, precond, nnz, n):
+def pcg_bytes_per_iteration(X, S, precond, nnz, n, scatter_ok=True):
     """Algorithmic bytes of ONE preconditioned CG iteration (FP64 values, int32 indices).
 
     Krylov part: SpMV 12 nnz + 20 n, dot 16 n, fused x/r update 48 n, direction update 24 n.
     Jacobi adds 24 n + 16 n (z = D^-1 r, z.r); multicolour SSOR 12 nnz + 40 n + 16 n;
-    the multigrid V-cycle, per level l: pre-smooth 24 n_l, residual 12 nnz_l + 28 n_l, restriction 12 n_l + 24 n_{l+1},
-    prolongation 28 n_l, post-smooth 12 nnz_l + 36 n_l (z.r fused), dense coarsest solve 8 n_c^2.
+    the multigrid V-cycle, per level l: pre-smooth 24 n_l, residual 12 nnz_l + 28 n_l, restriction 12 n_l + 24 n_{l+1}
+    (by scatter from the residual pass: 24 n_{l+1} only), prolongation 28 n_l, post-smooth 12 nnz_l + 36 n_l (z.r fused),
+    dense coarsest solve 8 n_c^2.
     """
     import ctypes as C
     krylov = 12.0 * nnz + 108.0 * n
@@ -253,9 +254,14 @@ def pcg_bytes_per_iteration(X, S, precond, nnz, n):
     if nl <= 0:
         return krylov, None
     levels = [{"rows": int(nr[l]), "nnz": int(nz[l])} for l in range(nl)]
+    # restriction by scatter (the default of the one-GPU real solver with a dense coarsest solve; off in deterministic
+    # runs): the residual pass adds into the coarse iterate instead of storing the residual, and the restriction pass
+    # with its reads of the residual and of the member lists (12 n_l) is gone
+    scatter = scatter_ok and nr[nl - 1] <= 128 and not (os.environ.get("XFEMM_DETERMINISTIC") or os.environ.get("XFEMM_AMG_ORDERED_RESTRICT"))
+    per_row = 116.0 if scatter else 128.0
     cyc = 0.0
     for l in range(nl - 1):
-        cyc += 24.0 * nz[l] + 128.0 * nr[l] + 24.0 * nr[l + 1]
+        cyc += 24.0 * nz[l] + per_row * nr[l] + 24.0 * nr[l + 1]
     cyc += 8.0 * nr[nl - 1] ** 2
     return krylov + cyc, levels
 
@@ -331,7 +337,7 @@ def run_partitioned(args, base, workload, rank, local_rank, world):
         D = DistAmgPCG(S)
         t_plan = time.time() - t0
         solve = lambda: D.solve(1e-10)
-        bytes_iter, levels = pcg_bytes_per_iteration(X, S, X.PRECOND_AMG, nnz, n)
+        bytes_iter, levels = pcg_bytes_per_iteration(X, S, X.PRECOND_AMG, nnz, n, scatter_ok=False)  # (ordered restriction pass)
         label = "multigrid V-cycle, global hierarchy"
     launches0 = int(X.lib().xfemm_launch_count())
     infos = []

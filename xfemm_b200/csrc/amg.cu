@@ -12,6 +12,7 @@
 namespace xb {
 
 int linprob_refresh_values(xfemm_linprob *p, int *singular_row); // linprob.cu
+int linprob_refresh_values_on(xfemm_linprob *p, cudaStream_t st);
 // amg_setup.cu
 int amg_coarse_pattern_device(xfemm_linprob *cur, const int *d_agg, int nc, std::vector<int> &crp, std::vector<int> &ccol,
                               DevBuf<int> &gptr, DevBuf<int> &gsrc, cudaStream_t st);
@@ -199,45 +200,57 @@ __global__ void k_amg_galerkin(int nnzc, const int *__restrict__ gptr, const int
     coarse_vals[t] = s;
 }
 
-// Dense inverse of the coarsest level by Gauss-Jordan on [A | I] (one block; the level has at most
-// AMG_DENSE_MAX rows, is symmetric positive definite and diagonally dominant enough to go without
-// pivoting).  Rows/columns in the internal order of the level; padding rows become identity rows.
+// The same with one WARP per coarse slot, for the small levels: the couplings of the air-gap ring funnel into a
+// few coarse slots whose gather lists hold thousands of entries, and a single thread walking such a list (two
+// dependent loads per entry) took 0.2 ms on the last level.  Lane-strided partial sums, fixed-order shuffle tree.
+__global__ void k_amg_galerkin_warp(int nnzc, const int *__restrict__ gptr, const int *__restrict__ gsrc,
+                                    const double *__restrict__ fine_vals, double *__restrict__ coarse_vals)
+{
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (t >= nnzc) return;
+    double s = 0.0;
+    for (int k = gptr[t] + lane; k < gptr[t + 1]; k += 32) s += fine_vals[gsrc[k]];
+    s = warp_sum(s);
+    if (lane == 0) coarse_vals[t] = s;
+}
+
+// Dense inverse of the coarsest level by Gauss-Jordan without pivoting (the level is symmetric positive definite),
+// in place in shared memory: at step k column k of the work matrix takes the k-th column of the inverse-in-progress —
+// the operations of an elimination on [A | I], without storing the unit columns.  One block; at most AMG_DENSE_MAX
+// rows (128 x 128 doubles = 128 KB of dynamic shared memory).  Rows/columns in the internal order of the level;
+// padding rows are identity rows.
 constexpr int AMG_DENSE_MAX = 128;
 constexpr int AMG_TEAM_ROWS_MAX = 1 << 18; // no level with more rows is ever given to the team
 __global__ void __launch_bounds__(1024)
 k_amg_dense_inverse(int n, int n_pad, const int *__restrict__ rowptr, const int *__restrict__ col,
-                    const double *__restrict__ vals, const int *__restrict__ c2i, double *W, double *inv)
+                    const double *__restrict__ vals, const int *__restrict__ c2i, double *inv)
 {
-    __shared__ double colk[AMG_DENSE_MAX];
-    const int ld = 2 * n_pad;
-    for (int e = threadIdx.x; e < n_pad * ld; e += blockDim.x)
-    {
-        const int r = e / ld, c = e % ld;
-        W[e] = (c == n_pad + r) ? 1.0 : 0.0;
-    }
+    extern __shared__ double dense_w[]; // n_pad x n_pad, then n_pad for the pivot column
+    double *W = dense_w, *colk = dense_w + (size_t)n_pad * n_pad;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    for (int e = tid; e < n_pad * n_pad; e += nthr) W[e] = (e / n_pad == e % n_pad) ? 1.0 : 0.0;
     __syncthreads();
-    for (int i = threadIdx.x; i < n_pad; i += blockDim.x) W[(size_t)i * ld + i] = 1.0; // padding rows (overwritten below for real rows)
+    for (int i = tid; i < n; i += nthr) W[c2i[i] * n_pad + c2i[i]] = 0.0;
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) W[(size_t)c2i[i] * ld + c2i[i]] = 0.0;
-    __syncthreads();
-    for (int i = 0; i < n; i++)
-        for (int q = rowptr[i] + threadIdx.x; q < rowptr[i + 1]; q += blockDim.x) W[(size_t)c2i[i] * ld + c2i[col[q]]] = vals[q];
+    for (int i = tid; i < n; i += nthr) // one thread per row: its entries are distinct slots
+        for (int q = rowptr[i]; q < rowptr[i + 1]; q++) W[c2i[i] * n_pad + c2i[col[q]]] = vals[q];
     __syncthreads();
     for (int k = 0; k < n_pad; k++)
     {
-        const double piv = W[(size_t)k * ld + k];
+        const double piv = W[k * n_pad + k];
+        for (int r = tid; r < n_pad; r += nthr) colk[r] = W[r * n_pad + k];
         __syncthreads();
-        for (int c = threadIdx.x; c < ld; c += blockDim.x) W[(size_t)k * ld + c] /= piv;
-        for (int r = threadIdx.x; r < n_pad; r += blockDim.x) colk[r] = W[(size_t)r * ld + k];
+        // row k: divided by the pivot; its own column holds the unit column's 1 / piv
+        for (int c = tid; c < n_pad; c += nthr) W[k * n_pad + c] = (c == k ? 1.0 : W[k * n_pad + c]) / piv;
         __syncthreads();
-        for (int e = threadIdx.x; e < n_pad * ld; e += blockDim.x)
+        for (int e = tid; e < n_pad * n_pad; e += nthr)
         {
-            const int r = e / ld, c = e % ld;
-            if (r != k) W[e] = fma(-colk[r], W[(size_t)k * ld + c], W[e]);
+            const int r = e / n_pad, c = e % n_pad;
+            if (r != k) W[e] = fma(-colk[r], W[k * n_pad + c], c == k ? 0.0 : W[e]);
         }
         __syncthreads();
     }
-    for (int e = threadIdx.x; e < n_pad * n_pad; e += blockDim.x) inv[e] = W[(size_t)(e / n_pad) * ld + n_pad + e % n_pad];
+    for (int e = tid; e < n_pad * n_pad; e += nthr) inv[e] = W[e];
 }
 
 int amg_build(xfemm_linprob *fine, std::unique_ptr<AmgHierarchy> &out, std::thread *fine_layout)
@@ -425,7 +438,6 @@ int amg_build(xfemm_linprob *fine, std::unique_ptr<AmgHierarchy> &out, std::thre
     {
         ArenaScope scope(h->arena.base ? &h->arena : nullptr);
         const size_t np = (size_t)h->coarse.back()->lay.n_pad;
-        XB_CUDA(h->dense_work.alloc(2 * np * np));
         XB_CUDA(h->dense_inv.alloc(np * np));
     }
     // pin the arena in L2 for everything launched on the solver stream
@@ -459,6 +471,7 @@ int amg_build(xfemm_linprob *fine, std::unique_ptr<AmgHierarchy> &out, std::thre
 // level l+1 values = P^T A_l P (gather-sum), then the SELL / diagonal refill of that level
 int amg_refresh(xfemm_linprob *fine, AmgHierarchy &h)
 {
+    // everything on the finest level's stream, nothing read back: one queue of small kernels, no host round trips
     cudaStream_t st = fine->stream;
     xfemm_linprob *cur = fine;
     for (size_t l = 0; l < h.coarse.size(); l++)
@@ -466,21 +479,26 @@ int amg_refresh(xfemm_linprob *fine, AmgHierarchy &h)
         xfemm_linprob *c = h.coarse[l];
         AmgHierarchy::Transfer &T = *h.xfer[l];
         const int nnzc = (int)T.nnz_coarse;
-        ++g_launch, k_amg_galerkin<<<(nnzc + 255) / 256, 256, 0, st>>>(nnzc, T.gptr.p, T.gsrc.p, cur->vals.p, c->vals.p);
+        if (nnzc > 262144) ++g_launch, k_amg_galerkin<<<(nnzc + 255) / 256, 256, 0, st>>>(nnzc, T.gptr.p, T.gsrc.p, cur->vals.p, c->vals.p);
+        else ++g_launch, k_amg_galerkin_warp<<<(unsigned)(((size_t)nnzc * 32 + 255) / 256), 256, 0, st>>>(nnzc, T.gptr.p, T.gsrc.p, cur->vals.p, c->vals.p);
         XB_CUDA(cudaGetLastError());
-        // the coarse problem owns its own stream: order its refill behind the Galerkin kernel
-        XB_CUDA(cudaStreamSynchronize(st));
-        int singular = -1;
-        int rc = linprob_refresh_values(c, &singular);
+        int rc = linprob_refresh_values_on(c, st);
         if (rc != XFEMM_OK) return rc;
-        XB_CUDA(cudaStreamSynchronize(c->stream));
         cur = c;
     }
     if (h.dense_inv.p)
     {
         xfemm_linprob *c = h.coarse.back();
-        ++g_launch, k_amg_dense_inverse<<<1, 1024, 0, st>>>(c->n, c->lay.n_pad, c->rowptr.p, c->col.p, c->vals.p, c->c2i.p,
-                                                            h.dense_work.p, h.dense_inv.p);
+        const int np = c->lay.n_pad;
+        const size_t smem = ((size_t)np * np + np) * sizeof(double);
+        static bool attr_set = false; // (one device per process)
+        if (!attr_set)
+        {
+            XB_CUDA(cudaFuncSetAttribute(k_amg_dense_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(((size_t)AMG_DENSE_MAX * AMG_DENSE_MAX + AMG_DENSE_MAX) * sizeof(double))));
+            attr_set = true;
+        }
+        ++g_launch, k_amg_dense_inverse<<<1, 1024, smem, st>>>(c->n, np, c->rowptr.p, c->col.p, c->vals.p, c->c2i.p, h.dense_inv.p);
         XB_CUDA(cudaGetLastError());
     }
     return XFEMM_OK;
@@ -553,6 +571,9 @@ void amg_fill_args(xfemm_linprob *fine, AmgHierarchy &h, AmgArgs &g, int grid)
     g.solo_from = 1 << 20;
     for (int l = g.team_from + 1; l < g.nlev; l++)
         if (h.level_n[l] <= solo_rows) { g.solo_from = l; break; }
+    // restriction by scatter (AmgArgs::scatter_restrict): real one-component cycles with an exact coarsest solve, unless
+    // the run has to be reproducible bit for bit
+    g.scatter_restrict = (h.dense_inv.p && !fine->deterministic && !getenv("XFEMM_DETERMINISTIC") && !getenv("XFEMM_AMG_ORDERED_RESTRICT")) ? 1 : 0;
     g.team_ctr = h.team_ctr.p;
     g.grid_ctr = getenv("XFEMM_CG_GRID_SYNC") ? nullptr : h.team_ctr.p + 32;
     // both barriers count from zero in every launch; the launch follows on this stream

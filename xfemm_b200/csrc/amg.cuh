@@ -74,6 +74,12 @@ struct AmgArgs
     double omega = 0.8, over = 2.6;
     int team_from = 1;      // first level handled by the team of blocks (small levels), 1 <= team_from <= nlev-1
     int team_blocks = 1;    // blocks 0..team_blocks-1 form the team
+    // Restriction by scatter (one-component cycles with a dense coarsest solve): the residual pass of level l adds
+    // w * dinv_c[I] * r_i straight into the coarse iterate x_c[I] (red.add.f64 in L2) instead of storing r and running
+    // a restriction pass behind a barrier; the coarse right-hand side is recovered row-locally as x_c * diag_c / w.
+    // One phase and one barrier less per level; the order of the additions is not fixed, so deterministic runs
+    // (XFEMM_DETERMINISTIC, option deterministic_assembly) keep the ordered restriction pass.
+    int scatter_restrict = 0;
     int solo_from = 1 << 20; // levels >= solo_from (a few hundred rows) are cycled by block 0 ALONE with __syncthreads: on them
                             // a barrier between blocks costs more than the whole level
     unsigned *team_ctr = nullptr; // arrival counter of the team barrier (device memory, zeroed before the launch)
@@ -193,6 +199,19 @@ __device__ __forceinline__ int amg_task_table(const int *slice_ptr, int cur, int
     return ns;
 }
 
+// scatter_restrict: the coarse iterates collect additions and have to start from zero — every block clears its share of
+// all of them (a few hundred thousand doubles).  Called at kernel start and when a cycle no longer needs them.
+__device__ __forceinline__ void amg_zero_coarse_iterates(const AmgArgs &g)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    for (int l = 1; l < g.nlev; l++)
+    {
+        double *x = g.lev[l].x;
+        const int n = g.lev[l].n_pad;
+        for (int i = tid; i < n; i += nthr) x[i] = 0.0;
+    }
+}
+
 // blocks that share level l of the team's sub-cycle: the team, or block 0 alone on the smallest levels
 __device__ __forceinline__ int amg_team_width(const AmgArgs &g, int l) { return l >= g.solo_from ? 1 : g.team_blocks; }
 
@@ -226,6 +245,7 @@ __device__ __forceinline__ const AmgArgs &amg_kernel_init(const AmgArgs &g, unsi
         s_wk[AMG_SWK_TAB + l] = -1;
     }
     if (threadIdx.x == 0) { s_wk[AMG_SWK_EPOCH] = 0; s_wk[AMG_SWK_EPOCH + 1] = 0; }
+    if (NC == 1 && g.scatter_restrict) amg_zero_coarse_iterates(g); // (the callers' first barrier precedes the first cycle)
     __syncthreads();
     if (threadIdx.x < 32)
     {
@@ -394,12 +414,13 @@ __device__ __noinline__ void amg_prolong_rows(const AmgLev &L, AmgV<NC> lv, AmgV
 //   AMG_EPI_RESIDUAL  t = b - A x'            AMG_EPI_POST  t = x' + w D^-1 (b - A x')
 //   PROL: x' = x + over * P * (t of the next level) formed on the fly (prolongation fused); else x' = x
 // Reads v.x, v.b (cv.t), writes v.t.  Out of line on purpose: own register allocation, one copy of the code.
-enum { AMG_EPI_RESIDUAL = 0, AMG_EPI_POST = 1 };
+//   AMG_EPI_SCATTER   b = x * diag / w (stored), then x_c[agg] += w * dinv_c[agg] * (b - A x)   — scatter_restrict
+enum { AMG_EPI_RESIDUAL = 0, AMG_EPI_POST = 1, AMG_EPI_SCATTER = 2 };
 
 template <int NC, bool PROL>
 __device__ __noinline__ void amg_spmv_tasks(const AmgLev &L, AmgV<NC> v, AmgV<NC> cv, int s0, int s1, int wk0, int wk1, int kind,
                                             double w, double over, unsigned char *tsm, const int *table = nullptr,
-                                            unsigned long long *dbg = nullptr)
+                                            unsigned long long *dbg = nullptr, const double *cdinv = nullptr)
 {
     auto mark = [&](int k) {
         if (dbg && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); dbg[k] = t; }
@@ -453,7 +474,7 @@ __device__ __noinline__ void amg_spmv_tasks(const AmgLev &L, AmgV<NC> v, AmgV<NC
             for (int m = 0; m < NC; m++)
             {
                 xr0[m] = v.x[m][row];
-                br0[m] = v.b[m][row];
+                br0[m] = (kind == AMG_EPI_SCATTER) ? xr0[m] * d0 / w : v.b[m][row];
                 if (PROL) { if (I >= 0) xr0[m] = fma(over, cv.t[m][I], xr0[m]); }
             }
         }
@@ -525,7 +546,7 @@ __device__ __noinline__ void amg_spmv_tasks(const AmgLev &L, AmgV<NC> v, AmgV<NC
                 for (int m = 0; m < NC; m++)
                 {
                     xr[m] = v.x[m][row];
-                    br[m] = v.b[m][row];
+                    br[m] = (kind == AMG_EPI_SCATTER) ? xr[m] * d / w : v.b[m][row];
                     if (PROL) { if (I >= 0) xr[m] = fma(over, cv.t[m][I], xr[m]); }
                 }
             }
@@ -542,7 +563,13 @@ __device__ __noinline__ void amg_spmv_tasks(const AmgLev &L, AmgV<NC> v, AmgV<NC
             for (int m = 0; m < NC; m++)
             {
                 const double res = br[m] - fma(d, xr[m], acc[m]);
-                v.t[m][row] = (kind == AMG_EPI_POST) ? fma(wd, res, xr[m]) : res;
+                if (kind == AMG_EPI_SCATTER)
+                {
+                    v.b[m][row] = br[m]; // the post-smoothing pass of this level reads it
+                    const int I = L.agg[row];
+                    if (I >= 0) atomicAdd(cv.x[m] + I, w * cdinv[I] * res);
+                }
+                else v.t[m][row] = (kind == AMG_EPI_POST) ? fma(wd, res, xr[m]) : res;
             }
         }
         cur += ns;
@@ -587,9 +614,11 @@ __device__ __noinline__ void amg_team_cycle(const AmgArgs &g, const AmgArgs2 *g2
         const int s0 = amg_chunk(L.nslices, B, T), s1 = amg_chunk(L.nslices, B + 1, T);
         unsigned long long *dbg = (g.stamps && g.trace_detail && B == 0 && l == first && kind == AMG_EPI_RESIDUAL) ? g.stamps + AMG_MAX_STAMPS : nullptr;
         const int *table = s_wk[AMG_SWK_TAB + l] >= 0 ? (const int *)(tsm + AMG_TASK_HDR_BYTES + AMG_TASK_PART_BYTES) + s_wk[AMG_SWK_TAB + l] : nullptr;
+        const double *cdinv = l + 1 < g.nlev ? g.lev[l + 1].dinv : nullptr;
         if (prol) amg_spmv_tasks<NC, true>(L, v, cv, s0, s1, s_wk[2 * l], s_wk[2 * l + 1], kind, w, over, tsm, table);
-        else amg_spmv_tasks<NC, false>(L, v, cv, s0, s1, s_wk[2 * l], s_wk[2 * l + 1], kind, w, over, tsm, table, dbg);
+        else amg_spmv_tasks<NC, false>(L, v, cv, s0, s1, s_wk[2 * l], s_wk[2 * l + 1], kind, w, over, tsm, table, dbg, cdinv);
     };
+    const bool scatter = NC == 1 && g.scatter_restrict != 0;
     // does this block take part in level l?
     auto in = [&](int l) { return B < amg_team_width(g, l); };
 
@@ -601,6 +630,13 @@ __device__ __noinline__ void amg_team_cycle(const AmgArgs &g, const AmgArgs2 *g2
         const AmgLev &C = g.lev[l + 1];
         const AmgV<NC> lv = amg_vecs<NC>(g, g2, l), cv = amg_vecs<NC>(g, g2, l + 1);
         const int T = amg_team_width(g, l);
+        if (scatter)
+        {
+            // residual and restriction in one pass: the coarse iterate collects the rows' contributions
+            spmv(l, false, lv, cv, AMG_EPI_SCATTER);
+            sync(l);
+            continue;
+        }
         spmv(l, false, lv, cv, AMG_EPI_RESIDUAL);
         sync(l);
         amg_restrict_level<NC>(L, C, lv, cv, B * blockDim.x + threadIdx.x, T * blockDim.x, w);
@@ -624,8 +660,10 @@ __device__ __noinline__ void amg_team_cycle(const AmgArgs &g, const AmgArgs2 *g2
                 for (int c = lane; c < n; c += 32)
                 {
                     const double a = g.coarse_inv[(size_t)r * n + c];
+                    // (scatter_restrict: the right-hand side is implied by the collected iterate)
+                    const double sc = (scatter && last > 0) ? L.diag[c] / w : 0.0;
 #pragma unroll
-                    for (int m = 0; m < NC; m++) acc[m] = fma(a, lv.b[m][c], acc[m]);
+                    for (int m = 0; m < NC; m++) acc[m] = fma(a, (scatter && last > 0) ? lv.x[m][c] * sc : lv.b[m][c], acc[m]);
                 }
 #pragma unroll
                 for (int m = 0; m < NC; m++)
@@ -778,14 +816,25 @@ __device__ __forceinline__ double amg_vcycle(const AmgArgs &g, const AmgArgs &sg
         if (l == 0)
         {
             amg_block_stamp(g, 1, true);
-            amg_spmv_phase(L, s0, s1, s_wk[0], s_wk[1], L.x, L.t, s_next, [&](int row, double ax) { L.t[row] = L.b[row] - ax; }, S0, L.b);
+            if (g.scatter_restrict)
+            {
+                const AmgLev &C = g.lev[1];
+                amg_spmv_phase(L, s0, s1, s_wk[0], s_wk[1], L.x, L.t, s_next, [&](int row, double ax) {
+                    const int I = L.agg[row];
+                    if (I >= 0) atomicAdd(C.x + I, w * C.dinv[I] * (L.b[row] - ax));
+                }, S0, L.b);
+            }
+            else
+                amg_spmv_phase(L, s0, s1, s_wk[0], s_wk[1], L.x, L.t, s_next, [&](int row, double ax) { L.t[row] = L.b[row] - ax; }, S0, L.b);
             amg_block_stamp(g, 1);
         }
         else
-            amg_spmv_tasks<1, false>(sg.lev[l], lv, cv, s0, s1, s_wk[2 * l], s_wk[2 * l + 1], AMG_EPI_RESIDUAL, w, over,
-                                     xb_dyn_smem + g.task_smem_offset, amg_table(g, s_wk, l));
+            amg_spmv_tasks<1, false>(sg.lev[l], lv, cv, s0, s1, s_wk[2 * l], s_wk[2 * l + 1],
+                                     g.scatter_restrict ? AMG_EPI_SCATTER : AMG_EPI_RESIDUAL, w, over,
+                                     xb_dyn_smem + g.task_smem_offset, amg_table(g, s_wk, l), nullptr, sg.lev[l + 1].dinv);
         grid.sync();
         amg_stamp(g, sk);
+        if (g.scatter_restrict) continue; // the residual pass has restricted already
         // coarse right-hand side = sum over the aggregate ; coarse pre-smooth fused.  Rows are dealt out
         // thread by thread over the whole grid (coalesced pointer loads, no tail of idle blocks).
         amg_restrict_level<1>(sg.lev[l], sg.lev[l + 1], lv, cv, tid_g, nthr_g, w);
@@ -805,6 +854,8 @@ __device__ __forceinline__ double amg_vcycle(const AmgArgs &g, const AmgArgs &sg
         const AmgV<1> lv = amg_vecs<1>(g, nullptr, l), cv = amg_vecs<1>(g, nullptr, l + 1);
         // own rows only: the post-smoothing pass below gathers x across blocks, hence the barrier
         amg_prolong_rows<1>(sg.lev[l], lv, cv, s0 * 32, s1 * 32, threadIdx.x, blockDim.x, over);
+        // the coarse iterates have served this cycle (their levels are done): ready to collect the next one's
+        if (l == 0 && g.scatter_restrict) amg_zero_coarse_iterates(g);
         grid.sync();
         amg_stamp(g, sk);
         if (l > 0)

@@ -907,6 +907,7 @@ int xfemm_clinprob_cocg(xfemm_clinprob *p, double precision, int warm, int preco
             }
         }
         amg_fill_args(R, *R->amg, g);
+        g.scatter_restrict = 0; // (this kernel runs the ordered restriction pass)
         amg_fill_args2(R, *R->amg, g2);
         XB_CUDA(cudaStreamSynchronize(R->stream)); // the barrier counters are zeroed on the companion's stream
     }

@@ -644,6 +644,7 @@ int xfemm_dpcg_create(xfemm_linprob *p, int rank, int world, xfemm_dpcg **out)
     AmgHierarchy &h = *p->amg;
     AmgArgs g;
     amg_fill_args(p, h, g, 1 << 20);
+    g.scatter_restrict = 0; // (this kernel runs the ordered restriction pass)
     const int nlev = g.nlev;
     XB_ARG(nlev >= 2, "the hierarchy has a single level: nothing to partition");
     int lp = g.team_from;
@@ -892,6 +893,7 @@ int xfemm_dpcg_solve(xfemm_dpcg *D, double precision, int warm, int max_iter, xf
     const int grid = d.peer_grid[D->rank];
     if (grid > p->max_grid) { XB_CUDA(p->partials.alloc((size_t)4 * grid)); p->max_grid = grid; }
     amg_fill_args(p, *p->amg, g, grid);
+    g.scatter_restrict = 0; // (this kernel runs the ordered restriction pass)
     g.task_smem_offset = (int)STAGE_SMEM_BYTES;
     g.stamps = nullptr;
     if (g.team_from != D->lp) { set_error("the hierarchy changed since xfemm_dpcg_create"); return XFEMM_ERR_ARG; }

@@ -1038,6 +1038,21 @@ int linprob_refresh_values(xfemm_linprob *p, int *singular_row)
     return XFEMM_OK;
 }
 
+// the same on a stream of the caller's choice, without the zero-diagonal report and without waiting (multigrid levels:
+// amg_refresh queues all of them behind each other)
+int linprob_refresh_values_on(xfemm_linprob *p, cudaStream_t st)
+{
+    const SellLayout &L = p->lay;
+    int *d_flag = (int *)(p->d_mail.p + 8);
+    int blocks = (int)std::min<long long>((L.sell_len + 255) / 256, (long long)p->num_sms * 16);
+    if (blocks < 1) blocks = 1;
+    ++xb::g_launch, k_sell_fill<<<blocks, 256, 0, st>>>(L.sell_len, p->sell_src.p, p->vals.p, p->sell_val.p);
+    p->wide.fill(p->vals.p, st);
+    ++xb::g_launch, k_diag_fill<<<(L.n_pad + 255) / 256, 256, 0, st>>>(L.n_pad, p->diag_src.p, p->vals.p, p->diag.p, p->dinv.p, d_flag);
+    XB_CUDA(cudaGetLastError());
+    return XFEMM_OK;
+}
+
 template <typename K>
 static int coop_grid(xfemm_linprob *p, K kernel, int threads, int *grid_out, size_t dyn_smem = 0)
 {

@@ -38,6 +38,7 @@ struct xfemm_linprob
     std::vector<int> agg_early;
     int agg_early_nc = 0, agg_wide_thr = -1;
     ~xfemm_linprob() { if (agg_thread.joinable()) agg_thread.join(); }
+    int deterministic = 0;         // bit-reproducible solves asked for (xfemm_mag_set_deterministic): no scatter restriction
     int wide_threshold = -1;       // rows with more off-diagonals are kept out of the SELL slices (-1: XFEMM_WIDE_ROW, 64)
     std::vector<int> forced_order; // optional: the internal row order to use as is (a companion of another problem)
     xb::DevBuf<int> rowptr, col;

@@ -925,6 +925,7 @@ int xfemm_mag_set_deterministic(xfemm_mag *m, int on)
 {
     XB_ARG(m, "null handle");
     m->deterministic = on ? 1 : 0;
+    if (m->lin) m->lin->deterministic = m->deterministic; // the multigrid cycle then keeps its ordered restriction pass
     return XFEMM_OK;
 }
 
