@@ -479,7 +479,7 @@ int amg_refresh(xfemm_linprob *fine, AmgHierarchy &h)
         xfemm_linprob *c = h.coarse[l];
         AmgHierarchy::Transfer &T = *h.xfer[l];
         const int nnzc = (int)T.nnz_coarse;
-        if (nnzc > 262144) ++g_launch, k_amg_galerkin<<<(nnzc + 255) / 256, 256, 0, st>>>(nnzc, T.gptr.p, T.gsrc.p, cur->vals.p, c->vals.p);
+        if (nnzc > 65536) ++g_launch, k_amg_galerkin<<<(nnzc + 255) / 256, 256, 0, st>>>(nnzc, T.gptr.p, T.gsrc.p, cur->vals.p, c->vals.p);
         else ++g_launch, k_amg_galerkin_warp<<<(unsigned)(((size_t)nnzc * 32 + 255) / 256), 256, 0, st>>>(nnzc, T.gptr.p, T.gsrc.p, cur->vals.p, c->vals.p);
         XB_CUDA(cudaGetLastError());
         int rc = linprob_refresh_values_on(c, st);

@@ -915,6 +915,51 @@ k_periodic_chains(const int *__restrict__ chain_seg, const int *__restrict__ seg
     }
 }
 
+// Periodic pairs at the granularity of their UNITS.  The averaging of a pair (spars.cpp:366-474) is a set of
+// independent small operations: one per coupled row k (two reads, four writes: the entries (k,i), (i,k), (k,j), (j,k)),
+// one for the two diagonals, one for the two right-hand-side entries.  Pairs have to be applied in list order only
+// where they touch the SAME entries, and an entry is touched by the pairs of its row and of its column — two, a few
+// more at corners.  So while neighbouring pairs chain a whole boundary together (thousands of dependency levels pair by
+// pair), the units need a handful of levels: a unit's level = 1 + the highest level of an earlier unit that shares an
+// entry with it.  One launch per level, one thread per unit, the whole device; same arithmetic and, per entry, the
+// same order of operations as the reference's list-order loop.
+//   flags: bit 0 anti-periodic pair, bit 1 diagonal unit (slots x,z), bit 2 right-hand-side unit (rows x,z)
+__global__ void k_periodic_units(int u0, int u1, const int4 *__restrict__ unit_slots, const int *__restrict__ unit_flags,
+                                 double *vals, double *b, const unsigned char *__restrict__ fill_mask, unsigned char *created)
+{
+    const int u = u0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= u1) return;
+    const int4 q = unit_slots[u];
+    const int f = unit_flags[u];
+    const double sgn = (f & 1) ? -1.0 : 1.0;
+    if (f & 4)
+    {
+        const double cb = 0.5 * (b[q.x] + sgn * b[q.z]);
+        b[q.x] = cb; b[q.z] = sgn * cb;
+        return;
+    }
+    if (f & 2)
+    {
+        const double dii = vals[q.x], djj = vals[q.z];
+        const double c = (f & 1) ? 0.5 * (dii + djj) : (dii + djj) / 2.0;
+        vals[q.x] = c; vals[q.z] = c;
+        return;
+    }
+    const double v1 = vals[q.x], v2 = vals[q.z];
+    if (v1 != 0.0 || v2 != 0.0)
+    {
+        const double c = (v1 + sgn * v2) / 2.0;
+        vals[q.x] = c; vals[q.y] = c; vals[q.z] = sgn * c; vals[q.w] = sgn * c;
+        if (fill_mask)
+        {
+            if (fill_mask[q.x]) created[q.x] = 1;
+            if (fill_mask[q.y]) created[q.y] = 1;
+            if (fill_mask[q.z]) created[q.z] = 1;
+            if (fill_mask[q.w]) created[q.w] = 1;
+        }
+    }
+}
+
 // Newton bookkeeping (static2d.cpp:953-989)
 __global__ void k_newton_norms(int n, const double *__restrict__ V, const double *__restrict__ Vold, double *part)
 {
@@ -1434,8 +1479,51 @@ int xfemm_linprob_periodic(xfemm_linprob *p, int npairs, const int *ni, const in
             for (int q = level_ptr[l]; q < level_ptr[l + 1]; q++) wait[q] = level_ptr[l];
         XB_CUDA(p->pbc_wait.upload(wait.data(), wait.size(), st));
         XB_CUDA(cudaStreamSynchronize(st));
+        // ---- units and their levels (k_periodic_units); list order: k indexes items / meta
+        p->pbc_unit_levels = 0;
+        if (nlevels > 1 && env_int("XFEMM_PBC_UNITS", 1))
+        {
+            std::unordered_map<long long, int> last; // entry id (slot, or -1 - row for the right-hand side) -> level of its last unit
+            std::vector<int4> us;
+            std::vector<int> uf, ul;
+            int nul = 0;
+            auto unit = [&](int4 slots, int flags, std::initializer_list<long long> ids) {
+                int lv = 0;
+                for (long long id : ids) { auto f = last.find(id); if (f != last.end()) lv = std::max(lv, f->second + 1); }
+                for (long long id : ids) last[id] = lv;
+                us.push_back(slots); uf.push_back(flags); ul.push_back(lv);
+                nul = std::max(nul, lv + 1);
+            };
+            for (int k = 0; k < npairs; k++)
+            {
+                const int *m = &meta[(size_t)6 * k];
+                const int anti = m[2] ? 1 : 0;
+                for (int t = item_ptr[k]; t < item_ptr[k + 1]; t++)
+                {
+                    const int *q = &items[(size_t)4 * t];
+                    unit(make_int4(q[0], q[1], q[2], q[3]), anti, {q[0], q[1], q[2], q[3]});
+                }
+                unit(make_int4(m[3], m[3], m[4], m[4]), anti | 2, {m[3], m[4]});
+                unit(make_int4(m[0], m[0], m[1], m[1]), anti | 4, {-1 - (long long)m[0], -1 - (long long)m[1]});
+            }
+            if (nul <= 64)
+            {
+                std::vector<int> order(us.size());
+                for (size_t u = 0; u < us.size(); u++) order[u] = (int)u;
+                std::stable_sort(order.begin(), order.end(), [&](int a, int b2) { return ul[a] < ul[b2]; });
+                std::vector<int4> us2(us.size());
+                std::vector<int> uf2(us.size());
+                p->h_pbc_unit_ptr.assign(nul + 1, 0);
+                for (size_t u = 0; u < us.size(); u++) { us2[u] = us[order[u]]; uf2[u] = uf[order[u]]; p->h_pbc_unit_ptr[ul[order[u]] + 1]++; }
+                for (int l = 0; l < nul; l++) p->h_pbc_unit_ptr[l + 1] += p->h_pbc_unit_ptr[l];
+                XB_CUDA(p->pbc_unit_slots.upload(us2.data(), us2.size(), st));
+                XB_CUDA(p->pbc_unit_flags.upload(uf2.data(), uf2.size(), st));
+                XB_CUDA(cudaStreamSynchronize(st));
+                p->pbc_unit_levels = nul;
+            }
+        }
         p->pbc_chains = 0;
-        if (nlevels > 32 && p->nnz + p->n < (1ll << 31) && env_int("XFEMM_PBC_CHAINS", 1))
+        if (p->pbc_unit_levels == 0 && nlevels > 32 && p->nnz + p->n < (1ll << 31) && env_int("XFEMM_PBC_CHAINS", 1))
         {
             // ---- chains and segments for k_periodic_chains (pairs in LIST order: k indexes ni/nj/type, items, meta)
             auto ids_of = [&](int k, std::vector<long long> &out) {
@@ -1534,7 +1622,17 @@ int xfemm_linprob_periodic(xfemm_linprob *p, int npairs, const int *ni, const in
             }
         }
     }
-    if (p->pbc_chains > 0)
+    if (p->pbc_unit_levels > 0)
+    {
+        for (int lv = 0; lv < p->pbc_unit_levels; lv++)
+        {
+            const int u0 = p->h_pbc_unit_ptr[lv], u1 = p->h_pbc_unit_ptr[lv + 1];
+            if (u1 <= u0) continue;
+            ++xb::g_launch, k_periodic_units<<<(unsigned)((u1 - u0 + 255) / 256), 256, 0, p->stream>>>(
+                u0, u1, p->pbc_unit_slots.p, p->pbc_unit_flags.p, p->vals.p, p->b.p, p->fill_mask.n ? p->fill_mask.p : nullptr, p->created.p);
+        }
+    }
+    else if (p->pbc_chains > 0)
         ++xb::g_launch, k_periodic_chains<<<p->pbc_chains, 1024, PBC_SMEM_BYTES, p->stream>>>(
             p->pbc_chain_seg.p, p->pbc_seg_slot.p, p->pbc_seg_gid.p, p->pbc_seg_pair.p, p->pbc_seg_item.p, p->pbc_pair_tab.p,
             p->pbc_sitems.p, p->nnz, p->vals.p, p->b.p, p->fill_mask.n ? p->fill_mask.p : nullptr, p->created.p);

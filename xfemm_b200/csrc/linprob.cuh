@@ -79,6 +79,11 @@ struct xfemm_linprob
     xb::DevBuf<int> pbc_chain_seg, pbc_seg_slot, pbc_seg_gid, pbc_seg_pair, pbc_seg_item;
     xb::DevBuf<int4> pbc_pair_tab;
     xb::DevBuf<ushort4> pbc_sitems;
+    // the pairs' units grouped by dependency level (k_periodic_units): the usual path
+    int pbc_unit_levels = 0;
+    std::vector<int> h_pbc_unit_ptr;
+    xb::DevBuf<int4> pbc_unit_slots;
+    xb::DevBuf<int> pbc_unit_flags;
     xb::DevBuf<unsigned char> fill_mask, created; // optional, see xfemm_linprob_set_fill_mask
 
     // result mailbox
