@@ -245,6 +245,7 @@ int xfemm_mag_get_mu(xfemm_mag *m, double *mu12);
 /* Newton bookkeeping on the device (static2d.cpp:953-989): saves V_old, returns
  * ||V-V_old||^2 and ||V||^2, blends V = relax*V + (1-relax)*V_old. */
 int xfemm_linprob_save_solution(xfemm_linprob *p);
+int xfemm_linprob_restore_solution(xfemm_linprob *p); /* V = V_old: the saved iterate as the starting guess of a retry */
 int xfemm_linprob_newton_norms(xfemm_linprob *p, double *dv2, double *v2);
 int xfemm_linprob_relax(xfemm_linprob *p, double relax);
 /* planar: b = V*c ; axisymmetric: b = V*c*2*pi*r*0.01 (static2d.cpp:1018-1021, staticaxi.cpp:779-783) */

@@ -65,3 +65,21 @@ def test_partitioned_over_nccl(tmp_path):
     info = _run(base, out, min(n, 8), ["--backend", "nccl"])
     assert rel_l2(np.load(out)["V"], ref["V"]) <= 1e-6
     print(info)
+
+
+def test_partitioned_zero_residual_is_not_reported_as_converged_nan(tmp_path):
+    """An exactly zero residual (here: zero right-hand side) makes alpha = 0/0 in an unguarded CG step.  The device
+    kernels freeze the iterate instead (csrc/dist.cu: guarded_ratio) and the host loop raises on a non-finite residual:
+    the run either returns the zero solution or fails loudly — never a NaN vector labelled converged."""
+    base = stage_case("tb30", tmp_path)
+    out = str(tmp_path / "z.npz")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+           "-m", "xfemm_b200.dist_run", base, "--out", out, "--backend", "gloo", "--same-device", "--precond", "jacobi", "--zero-rhs"]
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
+    if r.returncode != 0:
+        assert "diverged" in (r.stdout + r.stderr), (r.stdout[-2000:] + r.stderr[-3000:])
+        return
+    V = np.load(out)["V"]
+    assert np.all(np.isfinite(V)) and np.all(V == 0.0)

@@ -2042,6 +2042,13 @@ int xfemm_linprob_save_solution(xfemm_linprob *p)
     return XFEMM_OK;
 }
 
+int xfemm_linprob_restore_solution(xfemm_linprob *p)
+{
+    XB_ARG(p, "null handle");
+    XB_CUDA(cudaMemcpyAsync(p->V.p, p->Vold.p, (size_t)p->n * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    return XFEMM_OK;
+}
+
 int xfemm_linprob_newton_norms(xfemm_linprob *p, double *dv2, double *v2)
 {
     XB_ARG(p && dv2 && v2, "null pointer");

@@ -43,6 +43,7 @@ def main(argv=None):
                          "multigrid); peer: ONE persistent kernel per GPU with the global multigrid hierarchy, halo and "
                          "scalars as peer stores over NVLink (xfemm_dpcg_*, csrc/dist_amg.cu)")
     ap.add_argument("--out", default=None)
+    ap.add_argument("--zero-rhs", action="store_true", help="test hook: solve with a zero right-hand side (exactly zero residual)")
     a = ap.parse_args(argv)
 
     import torch
@@ -74,6 +75,9 @@ def main(argv=None):
         S.load_mesh()
         S.renumber()
         S.solve()  # assembly + boundary conditions only
+        if a.zero_rhs:
+            glin = X.lib().xfemm_fsolver_linprob(S.h)
+            X.check(X.lib().xfemm_linprob_set_rhs(glin, np.zeros(X.lib().xfemm_linprob_n(glin), dtype=np.float64)), "set_rhs")
         t_setup = time.perf_counter() - t0
         if a.solver == "peer":
             from xfemm_b200.dist_amg import DistAmgPCG

@@ -861,8 +861,10 @@ int FSolver::staticNewton(CBigLinProb &L)
             // safety net: the multigrid hierarchy is built from the sparsity pattern alone; should a problem
             // defeat it, the (slower, always applicable) Jacobi-preconditioned kernel takes over on the GPU
             PrintMessage("multigrid-preconditioned CG did not converge; retrying with the Jacobi preconditioner\n");
-            rc = xfemm_linprob_pcg(lin, L.Precision, 0 /* cold start: V may hold the failed iterate */, XFEMM_PRECOND_JACOBI,
-                                   maxIterOption, &info);
+            // V may hold the failed iterate: go back to the saved one, which is the warm start the first attempt had
+            const int warm = (Iter > 0 || resolveStart) ? 1 : 0;
+            if (warm) xfemm_linprob_restore_solution(lin);
+            rc = xfemm_linprob_pcg(lin, L.Precision, warm, XFEMM_PRECOND_JACOBI, maxIterOption, &info);
         }
         stats.pcg_iters.push_back(info.iterations);
         stats.pcg_ms.push_back(info.solve_ms);
