@@ -62,3 +62,24 @@ def test_device_layout_equals_host_layout_231k():
     base = bench.prepare_mesh(os.path.join(work, "ms0.005"), 0.005)
     A, st = _solve(base, {"precond": 2, "locality_order": 1, "age_union_pattern": 1}, {"XFEMM_LAYOUT_CHECK": "1", "XFEMM_HIERARCHY_CHECK": "1"})
     assert st["iters"][0] < 200
+
+
+@pytest.mark.parametrize("case", ["tbh", "harm2d"])
+def test_device_layout_equals_host_layout_complex(tmp_path, case):
+    """The complex problem (and its real companion carrying the multigrid hierarchy) through the same builders."""
+    base = stage_case(case, str(tmp_path))
+    env = {"XFEMM_LAYOUT_CHECK": "1", "XFEMM_HIERARCHY_CHECK": "1"}
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        S = X.FSolver(base)
+        S.load_mesh(False)
+        S.renumber(False)
+        S.solve()  # a mismatch fails the solve with an error that names the table
+        S.close()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v

@@ -6,6 +6,7 @@
 // ||r||_2/||b||_2 <= Precision) as one persistent cooperative kernel, seeded like the reference by
 // three CG steps on the normal equations of the preconditioned system (PCGSQStart, cspars.cpp:764-819).
 #include "clinprob.cuh"
+#include "layout_device.cuh"
 #include "amg.cuh"
 #include "amg2.cuh"
 #include <complex>
@@ -544,25 +545,47 @@ static int cbuild_layout(xfemm_clinprob *p, int precond)
     if (p->layout_precond == precond) return XFEMM_OK;
     SellLayout &L = p->lay;
     const int sigma = cenv_int("XFEMM_SELL_SIGMA", 1024);
-    if (precond == XFEMM_PRECOND_MCSSOR)
-    {
-        std::vector<int> color;
-        int nc = greedy_coloring(p->n, p->h_rowptr.data(), p->h_col.data(), cenv_int("XFEMM_MAX_COLORS", 7), color);
-        build_sell_layout(p->n, p->h_rowptr.data(), p->h_col.data(), &color, nc, sigma, L, cenv_int("XFEMM_WIDE_ROW", 64));
-    }
-    else
-        build_sell_layout(p->n, p->h_rowptr.data(), p->h_col.data(), nullptr, 0, sigma, L, cenv_int("XFEMM_WIDE_ROW", 64));
+    const int wide_thr = cenv_int("XFEMM_WIDE_ROW", 64);
     cudaStream_t st = p->stream;
-    XB_CUDA(p->i2c.upload(L.i2c.data(), L.i2c.size(), st));
-    XB_CUDA(p->c2i.upload(L.c2i.data(), L.c2i.size(), st));
-    XB_CUDA(p->slice_ptr.upload(L.slice_ptr.data(), L.slice_ptr.size(), st));
-    XB_CUDA(p->slice_wl.upload(L.slice_wl.data(), L.slice_wl.size(), st));
-    XB_CUDA(p->slice_wu.upload(L.slice_wu.data(), L.slice_wu.size(), st));
-    XB_CUDA(p->sell_col.upload(L.sell_col.data(), L.sell_col.size(), st));
-    XB_CUDA(p->sell_src.upload(L.sell_src.data(), L.sell_src.size(), st));
-    XB_CUDA(p->diag_src.upload(L.diag_src.data(), L.diag_src.size(), st));
-    XB_CUDA(p->color_slice.upload(L.color_slice.data(), L.color_slice.size(), st));
-    XB_CUDA(p->wide.upload(L, st));
+    // the uncoloured layout comes from the device builder shared with the real problem (layout_device.cuh)
+    const bool on_device = precond != XFEMM_PRECOND_MCSSOR && !cenv_int("XFEMM_HOST_LAYOUT", 0);
+    const bool check = on_device && cenv_int("XFEMM_LAYOUT_CHECK", 0);
+    if (on_device)
+    {
+        int rc = build_layout_device(p, sigma, wide_thr, nullptr, nullptr, nullptr);
+        if (rc != XFEMM_OK) return rc;
+    }
+    if (!on_device || check)
+    {
+        SellLayout Hc;
+        SellLayout &H = check ? Hc : L;
+        if (precond == XFEMM_PRECOND_MCSSOR)
+        {
+            std::vector<int> color;
+            int nc = greedy_coloring(p->n, p->h_rowptr.data(), p->h_col.data(), cenv_int("XFEMM_MAX_COLORS", 7), color);
+            build_sell_layout(p->n, p->h_rowptr.data(), p->h_col.data(), &color, nc, sigma, H, wide_thr);
+        }
+        else
+            build_sell_layout(p->n, p->h_rowptr.data(), p->h_col.data(), nullptr, 0, sigma, H, wide_thr);
+        if (check)
+        {
+            int rc = check_layout_device(p, H);
+            if (rc != XFEMM_OK) return rc;
+        }
+        else
+        {
+            XB_CUDA(p->i2c.upload(L.i2c.data(), L.i2c.size(), st));
+            XB_CUDA(p->c2i.upload(L.c2i.data(), L.c2i.size(), st));
+            XB_CUDA(p->slice_ptr.upload(L.slice_ptr.data(), L.slice_ptr.size(), st));
+            XB_CUDA(p->slice_wl.upload(L.slice_wl.data(), L.slice_wl.size(), st));
+            XB_CUDA(p->slice_wu.upload(L.slice_wu.data(), L.slice_wu.size(), st));
+            XB_CUDA(p->sell_col.upload(L.sell_col.data(), L.sell_col.size(), st));
+            XB_CUDA(p->sell_src.upload(L.sell_src.data(), L.sell_src.size(), st));
+            XB_CUDA(p->diag_src.upload(L.diag_src.data(), L.diag_src.size(), st));
+            XB_CUDA(p->color_slice.upload(L.color_slice.data(), L.color_slice.size(), st));
+            XB_CUDA(p->wide.upload(L, st));
+        }
+    }
     XB_CUDA(p->sell_val.alloc(L.sell_len));
     for (auto *v : {&p->diag, &p->dinv, &p->x, &p->r, &p->p, &p->u, &p->z, &p->w, &p->bint})
     {
