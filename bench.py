@@ -740,7 +740,6 @@ def main():
     launches = int(X.lib().xfemm_launch_count()) - launches0
     sync()
     elapsed = time.perf_counter() - t0
-    sampler.stop_flag = True
     st = S.stats()
     nnz = X.lib().xfemm_fsolver_nnz(S.h)
     bytes_iter, levels = pcg_bytes_per_iteration(X, S, precond, nnz, c["n_unknowns"])
@@ -773,6 +772,10 @@ def main():
         cs = S.stats()
         torque_only["cold_start"] = {"pcg_ms": sum(cs["solve_ms"]), "iterations": sum(cs["iters"]), "relres": cs["relres"]}
         S.set_option("warm_resolve", 1)
+    # (an NVML query takes tens of milliseconds while the GPU is busy: the sampler keeps running through the
+    # torque-only steps — the same kernels under the same load — so that the 0.2 s of headline steps are not
+    # represented by a single sample)
+    sampler.stop_flag = True
     # the deterministic (gather-based) assembly next to the default one (FP64 atomics), same resident problem
     det_asm = None
     if rank == 0 and world == 1:
