@@ -311,6 +311,7 @@ def run_partitioned(args, base, workload, rank, local_rank, world):
     import ctypes as C
 
     if world == 1 and not dist.is_initialized():
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29517", rank=0, world_size=1,
                                 device_id=torch.device(f"cuda:{local_rank}"))
     t0 = time.time()
@@ -648,6 +649,8 @@ def main():
     import xfemm_b200 as X
 
     if world > 1:
+        # stdout carries the ONE JSON line: NCCL's own messages (its version banner at the first communicator) go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     torch.cuda.set_device(local_rank)
     X.cuda_init(local_rank)
