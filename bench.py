@@ -388,7 +388,7 @@ def run_partitioned(args, base, workload, rank, local_rank, world):
             "gpu_launches": int(X.lib().xfemm_launch_count()) - launches0,
             "clocks": sampler.summary(),
             "solution_norm": float((V * V).sum() ** 0.5)}
-        print(json.dumps(line))
+        emit(line)
     D.close()
     S.close()
     dist.destroy_process_group()
@@ -577,9 +577,19 @@ def run_config(args, key):
                           "hours and was not made: no s/problem figure is extrapolated" % (it_done, "%.1f ms each" % ms_it if ms_it else "complex solver: whole first solve", passes)}
         except Exception as ex:
             line["cpu_baseline"] = {"value": None, "unit": "s/problem", "cores": 1, "kind": "reference", "sample": f"unavailable: {ex}"}
-    print(json.dumps(line))
+    emit(line)
     S.close()
     return 0
+
+
+_OUT = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    out = _OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -605,6 +615,12 @@ def main():
     ap.add_argument("--dist-solver", default="peer", choices=["peer", "nccl"], help="--partitioned: peer-memory multigrid kernel (default) or the round-1 NCCL/Jacobi path")
     ap.add_argument("--workdir", default=os.environ.get("XFEMM_BENCH_DIR", "/tmp/xfemm_bench"))
     args = ap.parse_args()
+    # stdout carries one JSON line and nothing else: whatever a library prints there (NCCL's version banner, solver
+    # chatter) is sent to stderr from here on
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -641,7 +657,7 @@ def main():
                                        "load_mesh": info["t_load_mesh"], "cuthill": info["t_cuthill"]},
                 "calibration": reference_calibration(info, args.mesh_size),
                 "timed_region_s": info["harness_wall_s"] if args.ref_full else None}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     import torch
@@ -826,7 +842,7 @@ def main():
         if not leg_done.wait(timeout=float(os.environ.get("XFEMM_BENCH_LEG_TIMEOUT", "240"))):
             if rank == 0 and held["line"] is not None:
                 held["line"]["single_mesh_all_gpus"] = {"error": "the extra leg did not finish in time; skipped"}
-                print(json.dumps(held["line"]), flush=True)
+                emit(held["line"])
             os._exit(0)
 
     def partitioned_leg():
@@ -922,7 +938,7 @@ def main():
         except Exception as ex:
             line["single_mesh_all_gpus"] = {"error": str(ex)[:300]}
         leg_done.set()
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
