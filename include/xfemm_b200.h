@@ -24,6 +24,8 @@
 #ifndef XFEMM_B200_H
 #define XFEMM_B200_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -149,6 +151,11 @@ int xfemm_pattern_build_device(int n_rows /* nodes + appended circuit unknowns *
 int xfemm_linprob_set_fill_mask(xfemm_linprob *p, const unsigned char *fill);
 int xfemm_linprob_get_exists_mask(xfemm_linprob *p, unsigned char *exists);
 void xfemm_free(void *ptr);
+/* Page-lock / release a caller-owned host array (cudaHostRegister): copies between it and the device then run by
+ * DMA at full PCIe speed instead of being staged.  Worth it for arrays that are transferred many times (the result
+ * arrays of a sweep); the host mirror's CBigLinProb does it for V and b from the second fetch on. */
+int xfemm_host_register(void *ptr, size_t bytes);
+int xfemm_host_unregister(void *ptr);
 
 /* ------------------------------------------------------------------ renumbering (host, integer, bit-exact)
  * edges: n_edges*2 node pairs in .edge file order.  newnum_out[i] = new index of node i.

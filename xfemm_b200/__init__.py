@@ -62,6 +62,8 @@ SIGNATURES = {
     "xfemm_linprob_get_values": (C.c_int, [_P, _dp]),
     "xfemm_linprob_set_rhs": (C.c_int, [_P, _dp]),
     "xfemm_linprob_restore_solution": (C.c_int, [_P]),
+    "xfemm_host_register": (C.c_int, [_P, C.c_size_t]),
+    "xfemm_host_unregister": (C.c_int, [_P]),
     "xfemm_linprob_get_rhs": (C.c_int, [_P, _dp]),
     "xfemm_linprob_set_solution": (C.c_int, [_P, _dp]),
     "xfemm_linprob_get_solution": (C.c_int, [_P, _dp]),

@@ -10,6 +10,8 @@
 #include <functional>
 #include <unordered_map>
 #include <mutex>
+#include <condition_variable>
+#include <pthread.h>
 #include <malloc.h>
 #include <vector>
 #include <cmath>
@@ -169,20 +171,88 @@ StageRing *stage_ring()
     return r.ok ? &r : nullptr;
 }
 
+// Three helper threads that live as long as the process (created on first use, re-created in a forked child): the
+// staging copies are a few hundred microseconds of memcpy each, so starting threads per chunk cost more than it saved.
+// The caller takes one share itself.
+class CopyPool
+{
+    static constexpr int HELPERS = 3;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    char *dst = nullptr;
+    const char *src = nullptr;
+    size_t bytes = 0;
+    unsigned long long generation = 0;
+    int pending = 0;
+    bool started = false;
+
+    static void share(char *d, const char *s, size_t n, int part, int parts)
+    {
+        const size_t unit = 4096, units = (n + unit - 1) / unit;
+        const size_t a = std::min(n, units * part / parts * unit), b = std::min(n, units * (part + 1) / parts * unit);
+        if (b > a) memcpy(d + a, s + a, b - a);
+    }
+    void worker(int id)
+    {
+        unsigned long long seen = 0;
+        std::unique_lock<std::mutex> lk(mu);
+        for (;;)
+        {
+            cv_work.wait(lk, [&] { return generation != seen; });
+            seen = generation;
+            char *d = dst; const char *s = src; const size_t n = bytes;
+            lk.unlock();
+            share(d, s, n, id + 1, HELPERS + 1);
+            lk.lock();
+            if (--pending == 0) cv_done.notify_one();
+        }
+    }
+
+public:
+    void copy(char *d, const char *s, size_t n)
+    {
+        if (n < (1u << 20)) { memcpy(d, s, n); return; }
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            if (!started)
+            {
+                for (int i = 0; i < HELPERS; i++) std::thread([this, i] { worker(i); }).detach();
+                started = true;
+            }
+            dst = d; src = s; bytes = n; pending = HELPERS; generation++;
+        }
+        cv_work.notify_all();
+        share(d, s, n, 0, HELPERS + 1);
+        std::unique_lock<std::mutex> lk(mu);
+        cv_done.wait(lk, [&] { return pending == 0; });
+    }
+};
+CopyPool *g_copy_pool = nullptr;
+std::once_flag g_copy_pool_once;
+
 void host_copy(char *dst, const char *src, size_t bytes)
 {
-    const int units = (int)((bytes + 65535) / 65536); // 64 KB units, at least 2 MB per thread
-    parallel_for(units, [&](int u0, int u1, int) {
-        const size_t a = (size_t)u0 * 65536, b = std::min(bytes, (size_t)u1 * 65536);
-        if (b > a) memcpy(dst + a, src + a, b - a);
-    }, 32);
+    std::call_once(g_copy_pool_once, [] {
+        g_copy_pool = new CopyPool;
+        // a forked child has none of the helper threads: it gets a pool of its own (the parent's object is leaked there)
+        pthread_atfork(nullptr, nullptr, [] { g_copy_pool = new CopyPool; });
+    });
+    g_copy_pool->copy(dst, src, bytes); // (callers hold the ring's mutex: one copy at a time)
+}
+
+// is this host pointer page-locked (cudaHostAlloc / cudaHostRegister)?  Then the DMA engine can use it directly.
+bool host_pinned(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
 }
 } // namespace
 
 // returns when `src` has been read (the caller may reuse it); the device copy is ordered on `st`
 cudaError_t copy_h2d(void *dst, const void *src, size_t bytes, cudaStream_t st)
 {
-    StageRing *r = bytes >= STAGE_MIN ? stage_ring() : nullptr;
+    StageRing *r = (bytes >= STAGE_MIN && !host_pinned(src)) ? stage_ring() : nullptr;
     if (!r) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
     std::lock_guard<std::mutex> lk(r->mu);
     cudaError_t e = cudaSuccess;
@@ -201,7 +271,7 @@ cudaError_t copy_h2d(void *dst, const void *src, size_t bytes, cudaStream_t st)
 // returns with the data in `dst` (everything queued on `st` before the call has completed by then)
 cudaError_t copy_d2h(void *dst, const void *src, size_t bytes, cudaStream_t st)
 {
-    StageRing *r = bytes >= STAGE_MIN ? stage_ring() : nullptr;
+    StageRing *r = (bytes >= STAGE_MIN && !host_pinned(dst)) ? stage_ring() : nullptr;
     if (!r)
     {
         cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st);
@@ -2146,5 +2216,18 @@ void xfemm_transfer_bytes(long long *h2d, long long *d2h, int reset)
 long long xfemm_launch_count(void) { return xb::g_launch.load(); }
 
 void xfemm_free(void *ptr) { free(ptr); }
+
+int xfemm_host_register(void *ptr, size_t bytes)
+{
+    XB_ARG(ptr && bytes > 0, "null pointer");
+    XB_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+    return XFEMM_OK;
+}
+int xfemm_host_unregister(void *ptr)
+{
+    XB_ARG(ptr, "null pointer");
+    XB_CUDA(cudaHostUnregister(ptr));
+    return XFEMM_OK;
+}
 
 } // extern "C"

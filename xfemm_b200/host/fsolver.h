@@ -282,6 +282,7 @@ public:
     bool cacheStaticPart;        // sweeps on linear problems keep the position-independent, boundary-conditioned part on the device (default true)
     bool fetchSolution;          // copy V and A back to the host after a solve (default true; sweeps that only need torque switch it off)
     bool hostSolutionStale = false; // the last solve left V and A on the device (fetchSolution was off): see fetchDeviceSolution
+    int solutionFetches = 0; // fetches from the current device problem (reset with it)
     // copies V and A of the last static solve from the device into L.V / L.b if they were left there; false on a CUDA error
     bool fetchDeviceSolution(CBigLinProb &L);
     bool gapTorque(int ageIndex, double &torque); // from the resident solution, = fpproc's gap integral 0

@@ -45,6 +45,7 @@ static double wall() { return std::chrono::duration<double>(std::chrono::steady_
 void FSolver::releaseDevice()
 {
     joinPrebuild();
+    solutionFetches = 0;
     if (dpcg) { xfemm_dpcg_destroy(dpcg); dpcg = nullptr; }
     if (magdev) { xfemm_mag_destroy(magdev); magdev = nullptr; }
     if (cmagdev) { xfemm_cmag_destroy(cmagdev); cmagdev = nullptr; }
@@ -766,6 +767,9 @@ int FSolver::staticNewton(CBigLinProb &L)
     const int precond = precondOption >= 0 ? precondOption : L.precond;
     int Iter = 0;
     double res = 0, lastres = 0;
+    const bool stepTiming = getenv("XFEMM_STEP_TIMING") != nullptr;
+    const double tStep0 = wall();
+    double tAsm0 = 0, tAsm1 = 0, tSolve0 = 0, tSolve1 = 0;
     // re-solve on the resident problem (next position of a sweep): initial guess from the positions solved
     // before — the last one, or the linear extrapolation of the last two (equidistant positions)
     if (resolveStart)
@@ -778,6 +782,7 @@ int FSolver::staticNewton(CBigLinProb &L)
         PrintMessage("Matrix Construction\n");
         double ms_asm = 0, ms_gap = 0;
         double tb = wall();
+        tAsm0 = tb;
         const bool cacheStatic = plan.staticPartUsable && cacheStaticPart;
         if (cacheStatic && plan.staticPartCached)
         {
@@ -811,6 +816,7 @@ int FSolver::staticNewton(CBigLinProb &L)
             }
         }
         stats.assemble_ms.push_back(ms_asm + ms_gap + (wall() - tb) * 1e3);
+        tAsm1 = wall();
         if (keepSystem)
         {
             // snapshot for the parity tests, pruned to the entries the reference's linked lists hold
@@ -836,6 +842,7 @@ int FSolver::staticNewton(CBigLinProb &L)
         xfemm_linprob_save_solution(lin); // V_old = V
         joinPrebuild(); // the solver structure is needed from here on (a failed pre-build is simply redone by the solve)
         PrintMessage("Conjugate Gradient Solver\n");
+        tSolve0 = wall();
         xfemm_solve_info info;
         // Newton steps after the first continue from the last iterate (static2d.cpp:929); so does the first
         // solve of a re-solve on the resident problem (next rotor position: the previous field is close)
@@ -866,6 +873,7 @@ int FSolver::staticNewton(CBigLinProb &L)
             if (warm) xfemm_linprob_restore_solution(lin);
             rc = xfemm_linprob_pcg(lin, L.Precision, warm, XFEMM_PRECOND_JACOBI, maxIterOption, &info);
         }
+        tSolve1 = wall();
         stats.pcg_iters.push_back(info.iterations);
         stats.pcg_ms.push_back(info.solve_ms);
         stats.final_relres = info.relres;
@@ -908,7 +916,13 @@ int FSolver::staticNewton(CBigLinProb &L)
     // results back to the caller's arrays: L.V internal units, L.b = A (static2d.cpp:1018-1021)
     // (sweeps that only read derived quantities — gapTorque — leave the nodal values on the device)
     hostSolutionStale = true;
+    const double tFetch0 = wall();
     if (fetchSolution && !fetchDeviceSolution(L)) return false;
+    if (stepTiming)
+        fprintf(stderr, "[xfemm step] before assembly %.3f ms, assembly + BC %.3f ms (wall), to solver %.3f ms, solve call %.3f ms (kernel %.3f ms), "
+                        "after solve %.3f ms, fetch %.3f ms, total %.3f ms\n",
+                (tAsm0 - tStep0) * 1e3, (tAsm1 - tAsm0) * 1e3, (tSolve0 - tAsm1) * 1e3, (tSolve1 - tSolve0) * 1e3,
+                stats.pcg_ms.empty() ? 0. : stats.pcg_ms.back(), (tFetch0 - tSolve1) * 1e3, (wall() - tFetch0) * 1e3, (wall() - tStep0) * 1e3);
     // The reference also accumulates meshele[i].Jprev += Jsrc on every pass of a non-incremental problem
     // (static2d.cpp:506); nothing reads it afterwards — WriteStatic2D does not print it and WriteHarmonic2D prints the
     // value loaded from a previous solution (harmonic2d.cpp:947) — so it is not kept here.
@@ -919,6 +933,9 @@ bool FSolver::fetchDeviceSolution(CBigLinProb &L)
 {
     if (!hostSolutionStale) return true;
     if (!L.device() || !magdev) { WarnMessage("xfemm_b200: no device solution to fetch\n"); return false; }
+    // a problem whose results are fetched again and again (positions of a sweep): from the second time on into
+    // page-locked arrays
+    if (++solutionFetches == 2) L.pinResultArrays();
     if (xfemm_linprob_get_solution(L.device(), L.V) != XFEMM_OK || xfemm_mag_solution_to_A(magdev, L.b) != XFEMM_OK)
     {
         WarnMessage(xfemm_last_error());

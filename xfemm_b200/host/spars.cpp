@@ -24,8 +24,25 @@ CBigLinProb::CBigLinProb()
 {
 }
 
+void CBigLinProb::pinResultArrays()
+{
+    if (resultPinned || !V || !b || n <= 0) return;
+    if (xfemm_host_register(V, sizeof(double) * (size_t)n) != XFEMM_OK) return;
+    if (xfemm_host_register(b, sizeof(double) * (size_t)n) != XFEMM_OK) { xfemm_host_unregister(V); return; }
+    resultPinned = true;
+}
+
+void CBigLinProb::unpinResultArrays()
+{
+    if (!resultPinned) return;
+    xfemm_host_unregister(V);
+    xfemm_host_unregister(b);
+    resultPinned = false;
+}
+
 CBigLinProb::~CBigLinProb()
 {
+    unpinResultArrays();
     if (dev) xfemm_linprob_destroy(dev);
     free(V); free(P); free(R); free(U); free(Z); free(b); free(M); free(Q);
     n = 0;
@@ -33,6 +50,7 @@ CBigLinProb::~CBigLinProb()
 
 int CBigLinProb::Create(int d, int bw)
 {
+    unpinResultArrays();
     bdw = bw;
     b = (double *)calloc(d, sizeof(double));
     V = (double *)calloc(d, sizeof(double));

@@ -71,6 +71,10 @@ public:
     // binds an externally built device problem (ownership passes to this object)
     void attachDevice(xfemm_linprob *d, const int *rowptr, const int *col);
     void invalidateHostCopy() { hostValuesValid = false; }
+    // Page-locks V and b (cudaHostRegister) so that results copied back from the device land there by DMA at full
+    // PCIe speed: worth its one-time cost (milliseconds) when a resident problem is solved again and again (sweeps).
+    // Undone by the destructor / the next Create().
+    void pinResultArrays();
     const int *patternRowptr() { ensurePattern(); return csrRowptr.data(); }
     const int *patternCol() { ensurePattern(); return csrCol.data(); }
 
@@ -81,6 +85,8 @@ private:
     std::vector<std::vector<Ent>> rows;  // upper triangle, sorted by column, first entry = diagonal
     std::vector<std::vector<int>> lower; // lower[i] = rows k<i holding an entry (k,i)
     bool patternDirty, valuesDirty, hostValuesValid, deviceAssembled;
+    bool resultPinned = false;
+    void unpinResultArrays();
     xfemm_linprob *dev;
     std::vector<int> csrRowptr, csrCol;
     std::vector<double> csrVals;
