@@ -565,7 +565,7 @@ void amg_fill_args(xfemm_linprob *fine, AmgHierarchy &h, AmgArgs &g, int grid)
     g.team_from = std::max(1, g.nlev - 1);
     for (int l = 1; l < g.nlev; l++)
         if (h.level_n[l] <= h.team_rows) { g.team_from = l; break; }
-    g.team_blocks = std::max(1, std::min(grid, (e = getenv("XFEMM_AMG_TEAM_BLOCKS")) ? atoi(e) : 32));
+    g.team_blocks = std::max(1, std::min(grid, (e = getenv("XFEMM_AMG_TEAM_BLOCKS")) ? atoi(e) : 48));
     // the smallest levels (at most this many rows) are block 0's alone; never the first team level
     const int solo_rows = (e = getenv("XFEMM_AMG_SOLO_ROWS")) ? atoi(e) : 0; // measured neutral at 2 M nodes (0.294 vs 0.293 ms/iteration): off by default
     g.solo_from = 1 << 20;
