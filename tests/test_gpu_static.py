@@ -157,3 +157,32 @@ def test_deterministic_assembly(case, tmp_path):
     assert np.max(np.abs(va - v1)) <= 1e-13 * np.max(np.abs(va))
     assert np.max(np.abs(ra - r1)) <= 1e-13 * max(np.max(np.abs(ra)), 1e-300)
     assert rel_l2(A1, Aa) <= 1e-7
+
+
+@pytest.mark.parametrize("name,tol", [("sat2d", 1e-11), ("axi1", 2e-10)])
+def test_newton_jacobian_at_the_reference_iterate(name, tol, tmp_path):
+    """The Jacobian and right-hand side of the LAST Newton pass, assembled at exactly the iterate the reference
+    assembled them at (`step{k}_vin` of the dump: the vector its PCGSolve was entered with is the iterate its element
+    loop has just linearised about).  Takes the solver tolerances out of the comparison that
+    test_nonlinear_newton_matches_reference has to allow for: B-H lookup, Newton terms and boundary conditions agree with
+    the reference to rounding: 1e-11 of the largest entry for the planar case (measured 4e-14; right-hand side 2e-12), 2e-10 for the axisymmetric
+    one (measured 8e-11: its element matrices carry 1/R factors and the nodes next to the axis differences of nearly
+    equal radii, evaluated here in a different order)."""
+    ref, meta = load_ref(name)
+    S = _solve(name, tmp_path, X.PRECOND_MCSSOR)      # builds the resident problem (and solves it)
+    last = meta["solves"] - 1
+    lin = X.lib().xfemm_fsolver_linprob(S.h)
+    vin = np.ascontiguousarray(ref[f"step{last}_vin"], dtype=np.float64)
+    X.check(X.lib().xfemm_linprob_set_solution(lin, vin), "set_solution")
+    S.set_option("warm_resolve", 0)
+    S.set_option("assemble_only", 1)
+    S.set_option("assemble_iter", last)
+    S.resolve()                                        # assembly + boundary conditions of pass `last`, no solve
+    rowptr, col, vals, rhs = S.system()
+    urp, ucol, uval = upper_from_full(rowptr, col, vals)
+    assert np.array_equal(urp, ref[f"step{last}_rowptr"]) and np.array_equal(ucol, ref[f"step{last}_col"])
+    scale = np.abs(ref[f"step{last}_val"]).max()
+    dv = np.abs(uval - ref[f"step{last}_val"]).max() / scale
+    db = np.abs(rhs - ref[f"step{last}_rhs"]).max() / np.abs(ref[f"step{last}_rhs"]).max()
+    print(name, "pass", last, "Jacobian", dv, "rhs", db)
+    assert dv <= tol and db <= tol

@@ -360,6 +360,7 @@ int xfemm_fsolver_set_option(xfemm_fsolver *s, const char *key, double value)
     if (!strcmp(key, "fetch_solution")) { s->S.fetchSolution = value != 0; return XFEMM_OK; }
     if (!strcmp(key, "cache_static_part")) { s->S.cacheStaticPart = value != 0; return XFEMM_OK; }
     if (!strcmp(key, "assemble_only")) { s->S.assembleOnly = value != 0; return XFEMM_OK; }
+    if (!strcmp(key, "assemble_iter")) { s->S.assembleIter = (int)value; return XFEMM_OK; }
     if (!strcmp(key, "age_union_pattern")) { s->S.ageUnionPattern = value != 0; return XFEMM_OK; }
     if (!strcmp(key, "deterministic_assembly"))
     {

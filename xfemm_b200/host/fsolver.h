@@ -295,6 +295,8 @@ public:
     void joinPrebuild() { if (prebuild.joinable()) prebuild.join(); }
     int localityOrder;           // 1/0: order the solver's rows along a Z-curve through the nodes; -1 = when the problem is re-solved
     bool assembleOnly;           // stop after assembly + boundary conditions of the first pass
+    int assembleIter = 0;        // ... which then counts as Newton pass number `assembleIter` (> 0: the Jacobian of the
+                                 // iterate that is on the device, xfemm_linprob_set_solution; parity tests of the Newton terms)
     bool deterministicAssembly = false; // gather-based assembly in a fixed order instead of FP64 atomics (option "deterministic_assembly", env XFEMM_DETERMINISTIC)
     bool ageUnionPattern;        // couple all ring nodes of an air-gap element structurally (sweeps)
     // regenerates the ring tables of air-gap element `ageIndex` for new rotor/stator angles [deg]

@@ -765,7 +765,8 @@ int FSolver::staticNewton(CBigLinProb &L)
         plan.ageDirty = false;
     }
     const int precond = precondOption >= 0 ? precondOption : L.precond;
-    int Iter = 0;
+    int Iter = (assembleOnly && assembleIter > 0) ? assembleIter : 0;
+    if (Iter > 0) LinearFlag = false; // a later pass of a nonlinear problem: B-H terms from the iterate on the device
     double res = 0, lastres = 0;
     const bool stepTiming = getenv("XFEMM_STEP_TIMING") != nullptr;
     const double tStep0 = wall();
