@@ -381,10 +381,23 @@ CComplex CMSolverMaterialProp::GetdHdB(double Bv)
     }
 }
 
+// The reference's Get_v lives in the base class and calls the base class's REAL-valued field (CMaterialProp.cpp:488-491,
+// 899-904: Re of the signed complex interpolation, zero for a material without a curve), not the solver class's GetH:
+// its result has no imaginary part even when the curve carries a hysteresis lag.
 CComplex CMSolverMaterialProp::Get_v(double Bv)
 {
     if (Bv == 0) return slope[0];
-    return CComplex(cplx(GetH(Bv)) / Bv);
+    const double b = fabs(Bv);
+    double field = 0;
+    if (BHpoints != 0)
+    {
+        const HermiteSegment seg(Bdata, BHpoints, b);
+        cplx h = 0;
+        if (seg.where == HermiteSegment::BEYOND) h = cplx(Hdata[seg.k]) + cplx(slope[seg.k]) * (b - Bdata[seg.k]);
+        else if (seg.where == HermiteSegment::INSIDE) h = seg.value(Hdata, slope);
+        field = (cplx(Bv / b) * h).real();
+    }
+    return CComplex(field / Bv);
 }
 
 void CMSolverMaterialProp::GetBHProps(double Bv, CComplex &v, CComplex &dv)
