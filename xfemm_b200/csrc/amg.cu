@@ -491,12 +491,13 @@ int amg_refresh(xfemm_linprob *fine, AmgHierarchy &h)
         xfemm_linprob *c = h.coarse.back();
         const int np = c->lay.n_pad;
         const size_t smem = ((size_t)np * np + np) * sizeof(double);
-        static bool attr_set = false; // (one device per process)
-        if (!attr_set)
+        static bool attr_set[64] = {}; // per device: function attributes belong to the device's context
+        const int dev = fine->device >= 0 && fine->device < 64 ? fine->device : 0;
+        if (!attr_set[dev])
         {
             XB_CUDA(cudaFuncSetAttribute(k_amg_dense_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(((size_t)AMG_DENSE_MAX * AMG_DENSE_MAX + AMG_DENSE_MAX) * sizeof(double))));
-            attr_set = true;
+            attr_set[dev] = true;
         }
         ++g_launch, k_amg_dense_inverse<<<1, 1024, smem, st>>>(c->n, np, c->rowptr.p, c->col.p, c->vals.p, c->c2i.p, h.dense_inv.p);
         XB_CUDA(cudaGetLastError());
