@@ -5,6 +5,7 @@
 // xfemm_clinprob_*); this file prepares the per-label / per-side tables and drives the outer loop.
 #include "fsolver.h"
 #include "../../include/xfemm_b200.h"
+#include "../csrc/layout.h"
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -37,10 +38,23 @@ int FSolver::harmonicSolve(CBigComplexLinProb &L, bool axi, bool verbose)
         WarnMessage("xfemm_b200: no CUDA device available (this backend has no CPU solve path)\n");
         return false;
     }
-    for (int i = 0; i < NumEls; i++)
+    // one pass of the host threads over the element records: on-edge laminations (not supported in AC analyses) and the
+    // elements that sit in a circuit — the serial sums below visit those alone, in element order
+    std::vector<int> inCircuit;
     {
-        const int lt = blockproplist[meshele[i].blk].LamType;
-        if (lt == 1 || lt == 2) { WarnMessage("On-edge lamination not supported in AC analyses"); return false; }
+        std::vector<std::vector<int>> part(64);
+        std::vector<char> onEdge(64, 0);
+        xb::parallel_for(NumEls, [&](int i0, int i1, int tid) {
+            for (int i = i0; i < i1; i++)
+            {
+                const int lt = blockproplist[meshele[i].blk].LamType;
+                if (lt == 1 || lt == 2) onEdge[tid] = 1;
+                if (NumCircProps > 0 && meshele[i].lbl >= 0 && labellist[meshele[i].lbl].InCircuit != -1) part[tid].push_back(i);
+            }
+        });
+        for (char f : onEdge)
+            if (f) { WarnMessage("On-edge lamination not supported in AC analyses"); return false; }
+        for (auto &v : part) inCircuit.insert(inCircuit.end(), v.begin(), v.end()); // (chunks are contiguous and ascending)
     }
     for (int i = 0; i < NumBlockLabels; i++) GetFillFactor(i);
     for (int i = 0; i < NumBlockLabels; i++)
@@ -50,12 +64,10 @@ int FSolver::harmonicSolve(CBigComplexLinProb &L, bool axi, bool verbose)
     if (NumCircProps > 0)
     {
         std::vector<cplx> C1(NumCircProps, 0.), C2(NumCircProps, 0.), C3(NumCircProps, 0.);
-        for (int i = 0; i < NumEls; i++)
+        for (int i : inCircuit)
         {
             const CMElement &El = meshele[i];
-            if (El.lbl < 0) continue;
             const int ic = labellist[El.lbl].InCircuit;
-            if (ic == -1) continue;
             const int *n = El.p;
             double p0 = meshnode[n[1]].y - meshnode[n[2]].y, p1 = meshnode[n[2]].y - meshnode[n[0]].y;
             double q0 = meshnode[n[2]].x - meshnode[n[1]].x, q1 = meshnode[n[0]].x - meshnode[n[2]].x;
@@ -172,9 +184,7 @@ int FSolver::harmonicSolve(CBigComplexLinProb &L, bool axi, bool verbose)
         T.is_external = bl.IsExternal ? 1 : 0;
         if (bp.BHpoints != 0) labelNonlinear[l] = 1;
     }
-    bool LinearFlag = true;
-    for (int i = 0; i < NumEls && LinearFlag; i++)
-        if (labelNonlinear[meshele[i].lbl]) LinearFlag = false;
+    bool LinearFlag = true; // (decided in the element pass below)
 
     // ---- element table, boundary sides, Dirichlet list, RHS terms, circuit couplings
     const int nUnknowns = NumNodes + NumCircProps;
@@ -196,7 +206,19 @@ int FSolver::harmonicSolve(CBigComplexLinProb &L, bool axi, bool verbose)
     };
     std::vector<int> rhsRow;
     std::vector<double> rhsVal;
-    for (int i = 0; i < NumNodes; i++)
+    // nodes with a point property or (axisymmetric) on the axis: a handful among millions — found by the host threads,
+    // visited in node order by the two passes below
+    std::vector<int> special;
+    {
+        const double axisTol = units[LengthUnits] * 1.e-06;
+        std::vector<std::vector<int>> part(64);
+        xb::parallel_for(NumNodes, [&](int i0, int i1, int tid) {
+            for (int i = i0; i < i1; i++)
+                if (meshnode[i].BoundaryMarker >= 0 || (axi && meshnode[i].x < axisTol)) part[tid].push_back(i);
+        });
+        for (auto &v : part) special.insert(special.end(), v.begin(), v.end());
+    }
+    for (int i : special)
         if (meshnode[i].BoundaryMarker >= 0)
         {
             const CMPointProp &pp = nodeproplist[meshnode[i].BoundaryMarker];
@@ -215,7 +237,7 @@ int FSolver::harmonicSolve(CBigComplexLinProb &L, bool axi, bool verbose)
         }
         else fixRows.push_back(NumNodes + i);
     }
-    for (int i = 0; i < NumNodes; i++)
+    for (int i : special)
     {
         if (axi && meshnode[i].x < (units[LengthUnits] * 1.e-06)) { setValue(i, 0.); continue; } // harmonicaxi.cpp:648-653
         if (meshnode[i].BoundaryMarker >= 0)
@@ -224,14 +246,39 @@ int FSolver::harmonicSolve(CBigComplexLinProb &L, bool axi, bool verbose)
             if ((pp.J.re == 0) && (pp.J.im == 0)) setValue(i, cplx(pp.A.re, pp.A.im) / c);
         }
     }
-    std::set<std::pair<int, int>> circPairs;
-    for (int i = 0; i < NumEls; i++)
+    // second pass of the host threads: the flat element table for the device, the elements with a tagged side, the
+    // (node, circuit unknown) couplings of the elements whose circuit carries an unknown, and whether any element sits
+    // in a B-H material.  The tagged elements are then visited in element order (first/last semantics of SetValue).
+    std::vector<std::pair<int, int>> circPairs; // sorted, unique
+    std::vector<int> tagged;
+    {
+        std::vector<std::vector<int>> partTag(64);
+        std::vector<std::vector<std::pair<int, int>>> partPairs(64);
+        std::vector<char> nonlinear(64, 0);
+        xb::parallel_for(NumEls, [&](int i0, int i1, int tid) {
+            for (int i = i0; i < i1; i++)
+            {
+                const CMElement &El = meshele[i];
+                int *t4 = &tri[4 * (size_t)i];
+                t4[0] = El.p[0]; t4[1] = El.p[1]; t4[2] = El.p[2]; t4[3] = El.lbl;
+                if (labelNonlinear[El.lbl]) nonlinear[tid] = 1;
+                if (labels[El.lbl].circuit >= 0)
+                    for (int j = 0; j < 3; j++) partPairs[tid].emplace_back(El.p[j], NumNodes + labels[El.lbl].circuit);
+                if (El.e[0] >= 0 || El.e[1] >= 0 || El.e[2] >= 0) partTag[tid].push_back(i);
+            }
+            // a node is shared by ~6 elements: thin the thread's list before the merge
+            std::sort(partPairs[tid].begin(), partPairs[tid].end());
+            partPairs[tid].erase(std::unique(partPairs[tid].begin(), partPairs[tid].end()), partPairs[tid].end());
+        });
+        for (char f : nonlinear) if (f) LinearFlag = false;
+        for (auto &v : partTag) tagged.insert(tagged.end(), v.begin(), v.end()); // (chunks are contiguous and ascending)
+        for (auto &v : partPairs) circPairs.insert(circPairs.end(), v.begin(), v.end());
+        std::sort(circPairs.begin(), circPairs.end());
+        circPairs.erase(std::unique(circPairs.begin(), circPairs.end()), circPairs.end());
+    }
+    for (int i : tagged)
     {
         const CMElement &El = meshele[i];
-        int *t4 = &tri[4 * (size_t)i];
-        t4[0] = El.p[0]; t4[1] = El.p[1]; t4[2] = El.p[2]; t4[3] = El.lbl;
-        if (labels[El.lbl].circuit >= 0)
-            for (int j = 0; j < 3; j++) circPairs.insert({El.p[j], NumNodes + labels[El.lbl].circuit});
         for (int j = 0; j < 3; j++)
         {
             if (El.e[j] < 0) continue;
@@ -320,7 +367,9 @@ int FSolver::harmonicSolve(CBigComplexLinProb &L, bool axi, bool verbose)
     struct JoinOnExit { FSolver *s; ~JoinOnExit() { s->joinPrebuild(); } } joinOnExit{this}; // never outlive `lin`
 
     std::vector<double> xy(2 * (size_t)NumNodes);
-    for (int i = 0; i < NumNodes; i++) { xy[2 * (size_t)i] = meshnode[i].x; xy[2 * (size_t)i + 1] = meshnode[i].y; }
+    xb::parallel_for(NumNodes, [&](int i0, int i1, int) {
+        for (int i = i0; i < i1; i++) { xy[2 * (size_t)i] = meshnode[i].x; xy[2 * (size_t)i + 1] = meshnode[i].y; }
+    });
     xfemm_cmag_desc D;
     memset(&D, 0, sizeof D);
     D.axisymmetric = axi ? 1 : 0;
