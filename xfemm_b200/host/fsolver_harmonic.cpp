@@ -27,6 +27,8 @@ static double hwall() { return std::chrono::duration<double>(std::chrono::steady
 
 int FSolver::harmonicSolve(CBigComplexLinProb &L, bool axi, bool verbose)
 {
+    const double tEnter = hwall();
+    const bool timing = getenv("XFEMM_TIMING") != nullptr;
     const double c = PI * 4.e-05;
     static const double units[] = {2.54, 0.1, 1., 100., 0.00254, 1.e-04};
     const cplx I1(0, 1), deg45(1, 1);
@@ -333,6 +335,7 @@ int FSolver::harmonicSolve(CBigComplexLinProb &L, bool axi, bool verbose)
 
     // ---- pattern → device problem
     double t0 = hwall();
+    if (timing) fprintf(stderr, "[xfemm timing]   host tables before the pattern %.3f s\n", t0 - tEnter);
     int *rowptr = nullptr, *colidx = nullptr;
     unsigned char *fillmask = nullptr;
     if (xfemm_pattern_build_device(nUnknowns, NumEls, tri.data(), 4, (int)ageMid.size(), ageNodes.data(), (int)exI.size(), exI.data(),
@@ -399,6 +402,7 @@ int FSolver::harmonicSolve(CBigComplexLinProb &L, bool axi, bool verbose)
     int Iter = 0;
     double res = 0, lastres = 0;
     Relax = 1.;
+    const double tLoop = hwall();
     do
     {
         if (verbose) PrintMessage("Matrix Construction\n");
@@ -492,11 +496,16 @@ int FSolver::harmonicSolve(CBigComplexLinProb &L, bool axi, bool verbose)
         Iter++;
     } while (LinearFlag == false);
     stats.newton_iters = Iter;
+    const double tFetch = hwall();
+    if (timing)
+        fprintf(stderr, "[xfemm timing] pattern %.3f s, device create+upload %.3f s, %d pass(es) %.3f s (krylov %.1f ms)\n",
+                stats.t_pattern, stats.t_upload, Iter, tFetch - tLoop, stats.pcg_ms.empty() ? 0. : stats.pcg_ms[0]);
     if (xfemm_clinprob_get_solution(lin, (double *)L.V) != XFEMM_OK || xfemm_cmag_solution_to_A(cmagdev, (double *)L.b) != XFEMM_OK)
     {
         WarnMessage(xfemm_last_error());
         return false;
     }
+    if (timing) fprintf(stderr, "[xfemm timing]   result copies %.3f s, harmonic solve total %.3f s\n", hwall() - tFetch, hwall() - tEnter);
     // element permeabilities back to the mesh records (read by nothing in the writer, kept for callers)
     return true;
 }
