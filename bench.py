@@ -782,6 +782,13 @@ def main():
                                "boundary-conditioned part of the system is restored from a device copy: only the air-gap "
                                "blocks are assembled per position",
                        "positions_deg": [position(args.warmup + args.steps + 1 + i) for i in range(args.steps)]}
+        # the other device-side reductions a sweep reads instead of nodal values (outside the timed loop): stored energy
+        # of all blocks; flux linkage per circuit where the problem has circuits (TorqueBenchmark has none)
+        try:
+            torque_only["stored_energy_J_last_position"] = S.stored_energy()
+            torque_only["flux_linkage_Wb_last_position"] = S.flux_linkage(0) if c.get("n_circuits", 0) > 0 else None
+        except Exception as ex:  # noqa: BLE001 — a missing reduction must not cost the bench line
+            torque_only["stored_energy_J_last_position"] = f"unavailable: {ex}"
         S.set_option("fetch_solution", 1)
         S.set_option("cache_static_part", 0)
         # the same problem solved from a zero initial guess (what a stand-alone solve of one position costs)
