@@ -351,3 +351,90 @@ def test_bh_curve_tables_against_the_reference_material_class(tmp_path):
             assert err <= 1e-10, (c["name"], width, err)
     print({c["name"]: c["worst"] for c in cases})
     print(f"bh tables: {identical} of {total} values bit-identical to the reference, worst deviation {worst:.2e} of the column scale")
+
+
+def test_periodic_unit_levels_reproduce_list_order_semantics():
+    """Row a8.  The device applies periodic pairs unit by unit (one unit per coupled row k, one for the two diagonals, one
+    for the two right-hand-side entries), units grouped into dependency levels: level = 1 + the highest level of an
+    earlier unit that shares an entry (csrc/linprob.cu, xfemm_linprob_periodic / k_periodic_units).  This is the same
+    rule in numpy, run on random banded systems with chains of neighbouring pairs, the units of a level applied in a
+    SHUFFLED order, against the pinned CPU restatement of the reference's sequential loop (oracle orc_periodicity =
+    spars.cpp:366-474): the results have to be bit-identical, whatever the order inside a level."""
+    import ctypes as C
+    from oracle import fsolver_oracle as O
+    L = O.lib()
+    rng = np.random.default_rng(7)
+    for trial in range(6):
+        n, bw = 90, 4
+        half = n // 2
+        A = np.zeros((n, n))
+        for i in range(n):
+            for j in range(i, min(n, i + bw + 1)):
+                if i == j or rng.random() < 0.8:
+                    A[i, j] = A[j, i] = rng.normal() + (6.0 if i == j else 0.0)
+        b = rng.normal(size=n)
+        # a chain of neighbouring pairs (i, i + half): consecutive pairs share entries; a few anti-periodic, one node in two pairs
+        pairs = [(i, i + half, int(rng.random() < 0.3)) for i in range(3, 3 + 18)]
+        pairs.append((5, 80, 0))
+        # ---- reference semantics: the oracle's sequential loop on upper-triangular storage
+        m = L.orc_create(n, 0)
+        for i in range(n):
+            for j in range(i, n):
+                if A[i, j] != 0.0:
+                    L.orc_put(m, float(A[i, j]), i, j)
+        bref = np.ctypeslib.as_array(L.orc_b(m), shape=(n,))
+        bref[:] = b
+        for i, j, t in pairs:
+            L.orc_periodicity(m, i, j, t)
+        Aref = np.array([[L.orc_get(m, min(i, j), max(i, j)) for j in range(n)] for i in range(n)])
+        bref = bref.copy()
+        L.orc_destroy(m)
+        # ---- structural pattern incl. the fill a symbolic replay creates (what xfemm_pattern_build does)
+        P = A != 0.0
+        for i, j, _ in pairs:
+            ks = [k for k in range(n) if (P[k, i] or P[k, j]) and k not in (i, j)]
+            for k in ks:
+                P[k, i] = P[i, k] = P[k, j] = P[j, k] = True
+        # ---- units and their levels, pairs in list order
+        units, last = [], {}
+
+        def add(kind, ids, payload):
+            lv = max((last[e] + 1 for e in ids if e in last), default=0)
+            for e in ids:
+                last[e] = lv
+            units.append((lv, kind, payload))
+
+        for i, j, t in pairs:
+            if j < i:
+                i, j = j, i
+            s = -1.0 if t else 1.0
+            for k in range(n):
+                if k in (i, j) or not (P[k, i] or P[k, j]):
+                    continue
+                add("item", [("a", k, i), ("a", i, k), ("a", k, j), ("a", j, k)], (k, i, j, s))
+            add("diag", [("a", i, i), ("a", j, j)], (i, j, s))
+            add("rhs", [("b", i), ("b", j)], (i, j, s))
+        nlev = max(u[0] for u in units) + 1
+        assert nlev < len(pairs)  # far fewer levels than a pair-by-pair chain would need
+        Aw, bw_ = A.copy(), b.copy()
+        for lv in range(nlev):
+            todo = [u for u in units if u[0] == lv]
+            rng.shuffle(todo)
+            for _, kind, p in todo:
+                if kind == "item":
+                    k, i, j, s = p
+                    v1, v2 = Aw[k, i], Aw[k, j]
+                    if v1 != 0.0 or v2 != 0.0:
+                        c = (v1 + s * v2) / 2.0
+                        Aw[k, i] = Aw[i, k] = c
+                        Aw[k, j] = Aw[j, k] = s * c
+                elif kind == "diag":
+                    i, j, s = p
+                    c = 0.5 * (Aw[i, i] + Aw[j, j])
+                    Aw[i, i] = Aw[j, j] = c
+                else:
+                    i, j, s = p
+                    c = 0.5 * (bw_[i] + s * bw_[j])
+                    bw_[i], bw_[j] = c, s * c
+        assert np.array_equal(Aw, Aref), trial
+        assert np.array_equal(bw_, bref), trial
